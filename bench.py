@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""Benchmark of the EPS training step (BASELINE.json metric: EPS train imgs/s, fwd+bwd, on B200).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W     # the reference's CPU einsum path (oracle port)
+
+Workload ("cfg2", BASELINE.json configs[1]): EPSesPlusLinear with 2 stacked EPS layers (4,4),(3,6) + linear on
+FashionMNIST-shaped synthetic 28x28 data, per-GPU batch 512, float32, one step = forward + cross-entropy +
+backward + gradient all-reduce (N>1) + Adam update.  Weak scaling: per-GPU batch fixed.
+Prints ONE JSON line on rank 0 (contract in the task statement; extra keys: roofline, cpu_baseline, e2e,
+gpu_launches, clocks, patches_per_s).
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+WORKLOADS = {
+    # name: (epses_specs, image_size, Q_0, default per-GPU batch, 2*nu feature scale)
+    "cfg2": (((4, 4), (3, 6)), 28, 2, 512, 1.45646),   # README.org:23, two_epses_on_fashionmnist.py:40-41
+    "cfg1": (((2, 2),), 28, 2, 128, 2.0),              # tests-scale single layer
+    "one_eps": (((4, 4),), 28, 2, 128, 1.0),           # replicate_90.19_vacc_experiment shape
+}
+
+
+def synth_batch(batch, image_size, scale, seed, dtype):
+    """Synthetic FashionMNIST-shaped batch: pixels u ~ U[0,1], phi = (sin^2, cos^2)(pi u / 2) * scale
+    (dctn/dataset_loading.py:33-36), layout (1, B, H, W, 2); labels uniform in [0, 10)."""
+    g = torch.Generator().manual_seed(seed)
+    u = torch.rand(batch, image_size, image_size, generator=g, dtype=torch.float64)
+    x = torch.stack((scale * torch.sin(u * math.pi / 2) ** 2, scale * torch.cos(u * math.pi / 2) ** 2), dim=-1)[None]
+    y = torch.randint(0, 10, (batch,), generator=g)
+    return x.to(dtype), y
+
+
+def layer_dims(specs, image_size, Q0, batch):
+    """Per-layer (K, Q_in, Q_out, H_in, P, D) and algorithmic flops 2*P*D*O."""
+    out, h, q = [], image_size, Q0
+    for K, O in specs:
+        ho = h - K + 1
+        P = batch * ho * ho
+        D = q ** (K * K)
+        out.append(dict(K=K, Q=q, O=O, H=h, P=P, D=D, flops=2.0 * P * D * O))
+        h, q = ho, O
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons for GPU `index` every 200 ms while running."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"],
+                    capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's own CPU implementation of the path: the oracle port of dctn/eps.py:19-40 (explicit
+    4-step einsum path) stacked as dctn/eps_plus_linear.py:138-147, autograd backward, Adam — PyTorch CPU ops
+    with all host threads.  (The reference is pure Python and cannot travel to the GPU box; oracle/ is its
+    pinned restatement.)  Each step is a bounded sample of the workload (batch `sample_batch`)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import eps_oracle as O
+
+    specs, image_size, Q0, _, scale = WORKLOADS[args.workload]
+    threads = torch.get_num_threads()
+    dtype = torch.float32
+    torch.manual_seed(0)
+    cores = [torch.nn.Parameter(c) for c in
+             [(q ** (-(K * K) / 2)) * torch.randn(*(q,) * (K * K), o) for (K, o), q in zip(specs, [Q0] + [o for _, o in specs[:-1]])]]
+    side = image_size - sum(k - 1 for k, _ in specs)
+    lin = torch.nn.Linear(side * side * specs[-1][1], 10)
+    opt = torch.optim.Adam(list(cores) + list(lin.parameters()), lr=1.11e-4)
+
+    def step(x, y):
+        opt.zero_grad(set_to_none=True)
+        logits = O.eps_plus_linear_forward(cores, lin.weight, lin.bias, x)
+        loss = F.cross_entropy(logits, y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    # size the per-step sample so that the whole run stays within ~150 s
+    x1, y1 = synth_batch(2, image_size, scale, 1, dtype)
+    t0 = time.perf_counter(); step(x1, y1); t_probe = (time.perf_counter() - t0) / 2  # s per image
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    sb = args.sample_batch or int(max(1, min(32, budget / max(t_probe, 1e-6))))
+    x, y = synth_batch(sb, image_size, scale, 2, dtype)
+    for _ in range(args.warmup):
+        step(x, y)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(x, y)
+    dt = time.perf_counter() - t0
+    ms = dt / args.steps * 1e3
+    value = sb * args.steps / dt
+    dims = layer_dims(specs, image_size, Q0, sb)
+    line = {
+        "impl": "reference", "metric": "eps_train_images_per_s", "value": value, "unit": "img/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "epses_specs": specs, "image_size": image_size, "per_gpu_batch": WORKLOADS[args.workload][3],
+                   "step": "fwd+cross_entropy+bwd+adam"},
+        "patches_per_s": sum(d["P"] for d in dims) * args.steps / dt,
+        "cpu_baseline": {"value": value, "unit": "img/s", "cores": threads, "kind": "port",
+                         "sample": f"batch {sb} per step (full workload batch {WORKLOADS[args.workload][3]}), {args.steps} timed steps, "
+                                   f"torch CPU einsum path, os.cpu_count()={os.cpu_count()}"},
+        "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(workload, seconds=20.0):
+    """Bounded CPU run of the oracle port of the same training step (rank 0, N=1 only)."""
+    from oracle import eps_oracle as O
+
+    specs, image_size, Q0, _, scale = WORKLOADS[workload]
+    threads = torch.get_num_threads()
+    torch.manual_seed(0)
+    qs = [Q0] + [o for _, o in specs[:-1]]
+    cores = [((q ** (-(K * K) / 2)) * torch.randn(*(q,) * (K * K), o)).requires_grad_(True) for (K, o), q in zip(specs, qs)]
+    side = image_size - sum(k - 1 for k, _ in specs)
+    w = (torch.randn(10, side * side * specs[-1][1]) * 0.01).requires_grad_(True)
+    b = torch.zeros(10, requires_grad=True)
+
+    def step(x, y):
+        for t in cores + [w, b]:
+            t.grad = None
+        F.cross_entropy(O.eps_plus_linear_forward(cores, w, b, x), y).backward()
+
+    x1, y1 = synth_batch(2, image_size, scale, 1, torch.float32)
+    t0 = time.perf_counter(); step(x1, y1); per_img = (time.perf_counter() - t0) / 2
+    sb = int(max(1, min(32, seconds / 3.0 / max(per_img, 1e-6))))
+    x, y = synth_batch(sb, image_size, scale, 2, torch.float32)
+    step(x, y)  # warm-up
+    t0 = time.perf_counter()
+    n = 2
+    for _ in range(n):
+        step(x, y)
+    dt = time.perf_counter() - t0
+    return {"value": sb * n / dt, "unit": "img/s", "cores": threads, "kind": "port",
+            "sample": f"fwd+bwd of the same model at batch {sb} (full batch {WORKLOADS[workload][3]}), {n} timed steps after 1 warm-up, "
+                      f"oracle port of the reference's 4-step einsum path on torch CPU, os.cpu_count()={os.cpu_count()}"}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p.get("hbm_gbs"), "bf16_tflops": p.get("bf16_tflops"), "bf16_tflops_sustained": p.get("bf16_tflops_sustained"), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def time_op(fn, flush, iters=5, warmup=2):
+    """Average device time (ms) of fn() with CUDA events on the current stream, L2 flushed before each call."""
+    for _ in range(warmup):
+        fn()
+    times = []
+    for _ in range(iters):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record()
+        e.synchronize()
+        times.append(s.elapsed_time(e))
+    return sum(times) / len(times)
+
+
+def kernel_rooflines(model, specs, image_size, Q0, batch, dev, flush):
+    """Times every EPS kernel call of one step in isolation (CUDA events) and reports achieved algorithmic
+    throughput: flops = 2*P*D*O per contraction (dinput = 2 such contractions: dKR1 and dKR2), bytes as in
+    BASELINE.md section 3."""
+    from dctn_b200 import _lib
+    from dctn_b200 import eps as E
+
+    peaks = measured_peaks()
+    dims = layer_dims(specs, image_size, Q0, batch)
+    res = []
+    x = torch.rand(1, batch, image_size, image_size, Q0, device=dev)
+    for li, d in enumerate(dims):
+        core = model.epses[li].detach()
+        plan = E._plan(1, d["K"], d["Q"], d["O"], torch.float32, E._default_variant)
+        B, H = batch, d["H"]
+        Ho = H - d["K"] + 1
+        out = torch.empty(B, Ho, Ho, d["O"], device=dev)
+        gout = torch.randn_like(out)
+        dcore = torch.empty_like(core)
+        dx = torch.empty_like(x)
+        lib = _lib.lib()
+        st = torch.cuda.current_stream().cuda_stream
+        ws = [torch.empty(lib.dctn_eps_workspace_bytes(plan, B, H, H, k), dtype=torch.uint8, device=dev) for k in range(3)]
+        calls = {
+            "forward": (lambda: lib.dctn_eps_forward(plan, x.data_ptr(), core.data_ptr(), out.data_ptr(), B, H, H, ws[0].data_ptr(), ws[0].numel(), st), 1),
+            "backward_core": (lambda: lib.dctn_eps_backward_core(plan, x.data_ptr(), gout.data_ptr(), dcore.data_ptr(), B, H, H, ws[1].data_ptr(), ws[1].numel(), st), 1),
+        }
+        if li > 0:
+            calls["backward_input"] = (lambda: lib.dctn_eps_backward_input(plan, x.data_ptr(), core.data_ptr(), gout.data_ptr(), dx.data_ptr(), B, H, H, ws[2].data_ptr(), ws[2].numel(), st), 2)
+        es = 4
+        xbytes = B * H * H * d["Q"] * es
+        obytes = d["P"] * d["O"] * es
+        cbytes = d["D"] * d["O"] * es
+        alg_bytes = {"forward": xbytes + obytes + cbytes, "backward_core": xbytes + obytes + cbytes,
+                     "backward_input": 2 * xbytes + obytes + cbytes}
+        for name, (fn, nflop) in calls.items():
+            l0 = _lib.launch_count()
+            rc = fn()
+            assert rc == 0, _lib.last_error()
+            launches = _lib.launch_count() - l0
+            ms = time_op(fn, flush)
+            flops = nflop * d["flops"]
+            res.append({"kernel": f"eps_{name}[L{li + 1} K={d['K']} Qin={d['Q']} Qout={d['O']}]", "ms": ms, "launches": launches,
+                        "tflops": flops / ms / 1e9, "gbs": alg_bytes[name] / ms / 1e6, "flops": flops, "bytes": alg_bytes[name]})
+        x = out.unsqueeze(0)
+    top = max(res, key=lambda r: r["ms"])
+    ai = top["flops"] / top["bytes"]
+    ridge = peaks["bf16_tflops"] * 1e3 / peaks["hbm_gbs"]
+    if ai >= ridge / 20:  # far above the fp32 ridge (11 flop/B): compute bound, report against the tensor-pipe peak
+        roof = {"bound": "tensor", "achieved": top["tflops"], "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": top["tflops"] / peaks["bf16_tflops"], "traffic": None}
+    else:
+        roof = {"bound": "hbm", "achieved": top["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": top["gbs"] / peaks["hbm_gbs"], "traffic": None}
+    roof.update({"kernel": top["kernel"], "ms_per_call": top["ms"], "launches_per_call": top["launches"], "peak_source": peaks["source"],
+                 "algorithmic_flops_per_call": top["flops"], "algorithmic_bytes_per_call": top["bytes"],
+                 "note": "fp32-accurate path: tcgen05 kind::tf32 needs 3 MMA passes per product, so the ceiling of "
+                         "`frac` against the bf16 peak is 1/6; see DESIGN.md",
+                 "all_kernels": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items() if k in ("kernel", "ms", "tflops", "gbs", "launches")} for r in res]})
+    return roof
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    from dctn_b200 import _lib
+    from dctn_b200.eps_plus_linear import EPSesPlusLinear, UnitTheoreticalOutputStd
+    from dctn_b200.parallel import GradAllReducer
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a CUDA device: there is no CPU fallback"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
+
+    specs, image_size, Q0, default_batch, scale = WORKLOADS[args.workload]
+    batch = args.batch or default_batch
+    torch.manual_seed(0)
+    model = EPSesPlusLinear(specs, UnitTheoreticalOutputStd(), 1.0, dev, torch.float32, image_size=image_size, Q_0=Q0)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1.11e-4)
+    reducer = GradAllReducer(model.parameters())
+    nb = 4  # distinct synthetic batches, rotated
+    host = [synth_batch(batch, image_size, scale, 1000 + rank * 17 + i, torch.float32) for i in range(nb)]
+    host = [(x.pin_memory(), y.pin_memory()) for x, y in host]
+    resident = [(x.to(dev), y.to(dev)) for x, y in host]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step(x, y):
+        opt.zero_grad(set_to_none=True)
+        loss = F.cross_entropy(model(x), y)
+        loss.backward()
+        reducer.wait()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, e2e):
+        """Sum of per-step device times (CUDA events on the launching stream); L2 flushed (untimed) before each step."""
+        total_ms = 0.0
+        last = None
+        for i in range(nsteps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            if e2e:
+                hx, hy = host[i % nb]
+                x, y = hx.to(dev, non_blocking=True), hy.to(dev, non_blocking=True)
+                last = step(x, y).item()  # device -> host read of the step's result
+            else:
+                x, y = resident[i % nb]
+                last = step(x, y)
+            e.record()
+            e.synchronize()
+            total_ms += s.elapsed_time(e)
+        return total_ms, last
+
+    for i in range(max(args.warmup, 3)):
+        step(*resident[i % nb])
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = _lib.launch_count()
+    wall0 = time.perf_counter()
+    ms_total, last = timed(args.steps, e2e=False)
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = _lib.launch_count() - l0
+    ms_e2e, last_loss = timed(args.steps, e2e=True)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = t.tolist()
+
+    if rank == 0:
+        dims = layer_dims(specs, image_size, Q0, batch)
+        imgs = batch * world * args.steps
+        value = imgs / (ms_total / 1e3)
+        hx, hy = host[0]
+        line = {
+            "metric": "eps_train_images_per_s", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "epses_specs": specs, "image_size": image_size, "per_gpu_batch": batch,
+                       "global_batch": batch * world, "parallelism": f"dp{world}", "step": "fwd+cross_entropy+bwd+grad_allreduce+adam",
+                       "variant": os.environ.get("DCTN_B200_VARIANT", "auto"),
+                       "l2": "256 MiB memset between timed steps (untimed); per-step CUDA-event times summed",
+                       "wall_s_incl_flush": round(wall, 4)},
+            "patches_per_s": sum(d["P"] for d in dims) * world * args.steps / (ms_total / 1e3),
+            "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "img/s", "h2d_bytes_per_step": hx.numel() * hx.element_size() + hy.numel() * hy.element_size(),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": last_loss},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if world == 1 or args.roofline:
+            line["roofline"] = kernel_rooflines(model, specs, image_size, Q0, batch, dev, flush)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_sample(args.workload)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg2")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
+    ap.add_argument("--sample-batch", type=int, default=0, help="reference arm: images per step (default: sized to ~150 s total)")
+    ap.add_argument("--roofline", action="store_true", help="also time the kernels in isolation when N>1")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

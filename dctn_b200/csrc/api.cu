@@ -1,0 +1,287 @@
+// C ABI of libdctn_b200.so (include/dctn_b200.h): plan cache, geometry, per-shape dispatch.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+
+#include "../../include/dctn_b200.h"
+#include "common.cuh"
+#include "eps_kernels.h"
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+int dctn_set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int dctn_set_cuda_error(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return DCTN_ERR_CUDA;
+}
+void dctn_count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+// ------------------------------------------------------------------------------------------------ plan
+struct dctn_plan {
+  int C, K, Q, O, dtype, variant;
+  int n, m;
+  int a_nh, a_nl, b_nh, b_nl;
+  long long A, Bn, N, D;
+  std::string desc;
+};
+
+static std::mutex g_plan_mu;
+static std::map<std::tuple<int, int, int, int, int, int>, dctn_plan*> g_plans;
+
+static bool pow_fits(int q, int e, long long limit, long long* out) {
+  long long r = 1;
+  for (int i = 0; i < e; ++i) {
+    r *= q;
+    if (r > limit) return false;
+  }
+  *out = r;
+  return true;
+}
+
+static void fill_geom(const dctn_plan* pl, int B, int H, int W, EpsGeom* g) {
+  memset(g, 0, sizeof(*g));
+  g->C = pl->C; g->K = pl->K; g->Q = pl->Q; g->O = pl->O;
+  g->n = pl->n; g->m = pl->m;
+  g->A = (int)pl->A; g->Bn = (int)pl->Bn; g->N = (int)pl->N;
+  g->a_nh = pl->a_nh; g->a_nl = pl->a_nl; g->b_nh = pl->b_nh; g->b_nl = pl->b_nl;
+  g->AH = ipow_host(pl->Q, pl->a_nh); g->AL = ipow_host(pl->Q, pl->a_nl);
+  g->BH = ipow_host(pl->Q, pl->b_nh); g->BL = ipow_host(pl->Q, pl->b_nl);
+  g->B = B; g->H = H; g->W = W; g->Ho = H - pl->K + 1; g->Wo = W - pl->K + 1;
+  g->P = (long long)B * g->Ho * g->Wo;
+  long long chan = (long long)B * H * W * pl->Q;
+  for (int dh = 0; dh < pl->K; ++dh)
+    for (int dw = 0; dw < pl->K; ++dw)
+      for (int c = 0; c < pl->C; ++c) {
+        int j = (dh * pl->K + dw) * pl->C + c;  // dctn/align.py:20-46
+        g->foff[j] = c * chan + ((long long)dh * W + dw) * pl->Q;
+      }
+}
+
+extern "C" int dctn_version(void) { return DCTN_B200_VERSION; }
+extern "C" const char* dctn_last_error(void) { return g_err; }
+extern "C" unsigned long long dctn_launch_count(void) { return g_launches.load(); }
+
+extern "C" const dctn_plan_t* dctn_eps_plan_get(int C, int K, int Qin, int Qout, int dtype, int variant) {
+  if (C < 1 || K < 1 || Qin < 1 || Qout < 1) {
+    dctn_set_error(DCTN_ERR_BAD_ARG, "plan: C, K, Qin, Qout must be positive (got %d %d %d %d)", C, K, Qin, Qout);
+    return nullptr;
+  }
+  if (dtype != DCTN_F32 && dtype != DCTN_F64) {
+    dctn_set_error(DCTN_ERR_BAD_ARG, "plan: dtype must be DCTN_F32 or DCTN_F64");
+    return nullptr;
+  }
+  if (variant < DCTN_VARIANT_AUTO || variant > DCTN_VARIANT_DIRECT) {
+    dctn_set_error(DCTN_ERR_BAD_ARG, "plan: unknown variant %d", variant);
+    return nullptr;
+  }
+  auto key = std::make_tuple(C, K, Qin, Qout, dtype, variant);
+  std::lock_guard<std::mutex> lk(g_plan_mu);
+  auto it = g_plans.find(key);
+  if (it != g_plans.end()) return it->second;
+
+  int n = K * K * C;
+  if (n > DCTN_MAXN) {
+    dctn_set_error(DCTN_ERR_UNSUPPORTED, "plan: K*K*C = %d factors per patch exceeds the limit %d", n, DCTN_MAXN);
+    return nullptr;
+  }
+  int m = (n + 1) / 2;  // the reference's split, dctn/eps.py:25-27
+  long long A, Bn;
+  const long long LIM = 1ll << 30;
+  if (!pow_fits(Qin, m, LIM, &A) || !pow_fits(Qin, n - m, LIM, &Bn) || Bn * Qout > LIM || A * Bn * Qout >= (1ll << 31)) {
+    dctn_set_error(DCTN_ERR_UNSUPPORTED, "plan: core with Qin^(K*K*C) = %d^%d elements is too large", Qin, n);
+    return nullptr;
+  }
+  if ((variant == DCTN_VARIANT_TC3 || variant == DCTN_VARIANT_TC1) && dtype != DCTN_F32) {
+    dctn_set_error(DCTN_ERR_UNSUPPORTED, "plan: the tcgen05 TF32 variants are float32 only");
+    return nullptr;
+  }
+  dctn_plan* pl = new dctn_plan();
+  pl->C = C; pl->K = K; pl->Q = Qin; pl->O = Qout; pl->dtype = dtype; pl->variant = variant;
+  pl->n = n; pl->m = m; pl->A = A; pl->Bn = Bn; pl->N = Bn * Qout; pl->D = A * Bn;
+  pl->a_nl = m / 2; pl->a_nh = m - pl->a_nl;
+  pl->b_nl = (n - m) / 2; pl->b_nh = (n - m) - pl->b_nl;
+  char buf[512];
+  snprintf(buf, sizeof(buf),
+           "EPS plan C=%d K=%d Qin=%d Qout=%d %s variant=%d: n=%d factors, split m=%d (A=%lld, Bn=%lld, N=%lld, D=%lld), "
+           "tables A:(%d|%d) B:(%d|%d)",
+           C, K, Qin, Qout, dtype == DCTN_F32 ? "f32" : "f64", variant, n, m, A, Bn, pl->N, pl->D, pl->a_nh,
+           pl->a_nl, pl->b_nh, pl->b_nl);
+  pl->desc = buf;
+  g_plans[key] = pl;
+  return pl;
+}
+
+extern "C" const char* dctn_eps_plan_describe(const dctn_plan_t* plan) { return plan ? plan->desc.c_str() : "(null plan)"; }
+
+// ------------------------------------------------------------------------------------------------ dispatch
+enum Family { FAM_FFMA = 1, FAM_TC = 2, FAM_DIRECT = 4 };
+
+static int check_call(const dctn_plan_t* pl, int B, int H, int W) {
+  if (!pl) return dctn_set_error(DCTN_ERR_BAD_ARG, "null plan");
+  if (B < 1 || H < pl->K || W < pl->K)
+    return dctn_set_error(DCTN_ERR_BAD_ARG, "input (B=%d, H=%d, W=%d) must have B >= 1 and H, W >= kernel_size %d", B, H, W, pl->K);
+  return 0;
+}
+
+// which kernel family serves `kind` for this plan/geometry
+static int pick_family(const dctn_plan_t* pl, const EpsGeom& g, int kind) {
+  switch (pl->variant) {
+    case DCTN_VARIANT_FFMA: return FAM_FFMA;
+    case DCTN_VARIANT_TC3:
+    case DCTN_VARIANT_TC1: return tc_supported(g, kind) ? FAM_TC : -1;
+    case DCTN_VARIANT_DIRECT: return (kind == DCTN_WS_FORWARD && direct_supported(g, pl->dtype)) ? FAM_DIRECT : -1;
+    default: break;
+  }
+  if (kind == DCTN_WS_FORWARD && direct_supported(g, pl->dtype)) return FAM_DIRECT;
+  if (pl->dtype == DCTN_F32 && tc_supported(g, kind)) return FAM_TC;
+  return FAM_FFMA;
+}
+
+extern "C" size_t dctn_eps_workspace_bytes(const dctn_plan_t* pl, int B, int H, int W, int kind) {
+  if (check_call(pl, B, H, W)) return 0;
+  EpsGeom g;
+  fill_geom(pl, B, H, W, &g);
+  int fam = pick_family(pl, g, kind);
+  size_t bytes = 0;
+  if (fam == FAM_FFMA) bytes = pl->dtype == DCTN_F32 ? ffma_workspace_bytes<float>(g, kind) : ffma_workspace_bytes<double>(g, kind);
+  else if (fam == FAM_TC) bytes = tc_workspace_bytes(g, kind);
+  return bytes + 256;  // never zero, so callers can always pass a valid pointer
+}
+
+static int check_ws(const dctn_plan_t* pl, int B, int H, int W, int kind, void* ws, size_t ws_bytes) {
+  size_t need = dctn_eps_workspace_bytes(pl, B, H, W, kind);
+  if (!ws || ws_bytes < need)
+    return dctn_set_error(DCTN_ERR_WORKSPACE, "workspace of %zu bytes needed, got %zu (%p)", need, ws_bytes, ws);
+  return 0;
+}
+
+extern "C" int dctn_eps_forward(const dctn_plan_t* pl, const void* x, const void* core, void* out, int B, int H,
+                                int W, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_call(pl, B, H, W);
+  if (rc) return rc;
+  if (!x || !core || !out) return dctn_set_error(DCTN_ERR_BAD_ARG, "forward: null tensor pointer");
+  if ((rc = check_ws(pl, B, H, W, DCTN_WS_FORWARD, ws, ws_bytes))) return rc;
+  EpsGeom g;
+  fill_geom(pl, B, H, W, &g);
+  cudaStream_t st = (cudaStream_t)stream;
+  int fam = pick_family(pl, g, DCTN_WS_FORWARD);
+  if (fam < 0) return dctn_set_error(DCTN_ERR_UNSUPPORTED, "forward: requested kernel variant %d does not support this shape (%s)", pl->variant, pl->desc.c_str());
+  if (fam == FAM_DIRECT)
+    return pl->dtype == DCTN_F32 ? direct_forward<float>(g, (const float*)x, (const float*)core, (float*)out, st)
+                                 : direct_forward<double>(g, (const double*)x, (const double*)core, (double*)out, st);
+  if (fam == FAM_TC)
+    return tc_forward(g, (const float*)x, (const float*)core, (float*)out, ws, pl->variant == DCTN_VARIANT_TC1 ? 1 : 3, st);
+  return pl->dtype == DCTN_F32 ? ffma_forward<float>(g, (const float*)x, (const float*)core, (float*)out, ws, st)
+                               : ffma_forward<double>(g, (const double*)x, (const double*)core, (double*)out, ws, st);
+}
+
+extern "C" int dctn_eps_backward_core(const dctn_plan_t* pl, const void* x, const void* gout, void* dcore, int B,
+                                      int H, int W, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_call(pl, B, H, W);
+  if (rc) return rc;
+  if (!x || !gout || !dcore) return dctn_set_error(DCTN_ERR_BAD_ARG, "backward_core: null tensor pointer");
+  if ((rc = check_ws(pl, B, H, W, DCTN_WS_BACKWARD_CORE, ws, ws_bytes))) return rc;
+  EpsGeom g;
+  fill_geom(pl, B, H, W, &g);
+  cudaStream_t st = (cudaStream_t)stream;
+  int fam = pick_family(pl, g, DCTN_WS_BACKWARD_CORE);
+  if (fam < 0) return dctn_set_error(DCTN_ERR_UNSUPPORTED, "backward_core: requested kernel variant %d does not support this shape (%s)", pl->variant, pl->desc.c_str());
+  if (fam == FAM_TC)
+    return tc_backward_core(g, (const float*)x, (const float*)gout, (float*)dcore, ws, pl->variant == DCTN_VARIANT_TC1 ? 1 : 3, st);
+  return pl->dtype == DCTN_F32 ? ffma_backward_core<float>(g, (const float*)x, (const float*)gout, (float*)dcore, ws, st)
+                               : ffma_backward_core<double>(g, (const double*)x, (const double*)gout, (double*)dcore, ws, st);
+}
+
+extern "C" int dctn_eps_backward_input(const dctn_plan_t* pl, const void* x, const void* core, const void* gout,
+                                       void* dx, int B, int H, int W, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_call(pl, B, H, W);
+  if (rc) return rc;
+  if (!x || !core || !gout || !dx) return dctn_set_error(DCTN_ERR_BAD_ARG, "backward_input: null tensor pointer");
+  if ((rc = check_ws(pl, B, H, W, DCTN_WS_BACKWARD_INPUT, ws, ws_bytes))) return rc;
+  EpsGeom g;
+  fill_geom(pl, B, H, W, &g);
+  cudaStream_t st = (cudaStream_t)stream;
+  int fam = pick_family(pl, g, DCTN_WS_BACKWARD_INPUT);
+  if (fam < 0) return dctn_set_error(DCTN_ERR_UNSUPPORTED, "backward_input: requested kernel variant %d does not support this shape (%s)", pl->variant, pl->desc.c_str());
+  if (fam == FAM_TC)
+    return tc_backward_input(g, (const float*)x, (const float*)core, (const float*)gout, (float*)dx, ws, pl->variant == DCTN_VARIANT_TC1 ? 1 : 3, st);
+  return pl->dtype == DCTN_F32
+             ? ffma_backward_input<float>(g, (const float*)x, (const float*)core, (const float*)gout, (float*)dx, ws, st)
+             : ffma_backward_input<double>(g, (const double*)x, (const double*)core, (const double*)gout, (double*)dx, ws, st);
+}
+
+// ------------------------------------------------------------------------------------------------ logmatmulexp
+extern "C" int dctn_logmatmulexp_forward(const void* A, const void* B, void* out, int Th, int R, int I, int dtype,
+                                         void* stream) {
+  if (!A || !B || !out) return dctn_set_error(DCTN_ERR_BAD_ARG, "logmatmulexp: null tensor pointer");
+  if (Th < 1 || R < 1 || I < 1) return dctn_set_error(DCTN_ERR_BAD_ARG, "logmatmulexp: sizes must be positive (%d, %d, %d)", Th, R, I);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DCTN_F32) return lme_forward<float>((const float*)A, (const float*)B, (float*)out, Th, R, I, st);
+  if (dtype == DCTN_F64) return lme_forward<double>((const double*)A, (const double*)B, (double*)out, Th, R, I, st);
+  return dctn_set_error(DCTN_ERR_BAD_ARG, "logmatmulexp: bad dtype %d", dtype);
+}
+
+extern "C" int dctn_logmatmulexp_backward(const void* A, const void* B, const void* out, const void* gout, void* dA,
+                                          void* dB, int Th, int R, int I, int dtype, void* stream) {
+  if (!A || !B || !out || !gout) return dctn_set_error(DCTN_ERR_BAD_ARG, "logmatmulexp backward: null tensor pointer");
+  if (Th < 1 || R < 1 || I < 1) return dctn_set_error(DCTN_ERR_BAD_ARG, "logmatmulexp: sizes must be positive (%d, %d, %d)", Th, R, I);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DCTN_F32)
+    return lme_backward<float>((const float*)A, (const float*)B, (const float*)out, (const float*)gout, (float*)dA, (float*)dB, Th, R, I, st);
+  if (dtype == DCTN_F64)
+    return lme_backward<double>((const double*)A, (const double*)B, (const double*)out, (const double*)gout, (double*)dA, (double*)dB, Th, R, I, st);
+  return dctn_set_error(DCTN_ERR_BAD_ARG, "logmatmulexp: bad dtype %d", dtype);
+}
+
+// ------------------------------------------------------------------------------------------------ host-buffer entry
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+extern "C" size_t dctn_eps_forward_host_device_bytes(const dctn_plan_t* pl, int B, int H, int W) {
+  if (check_call(pl, B, H, W)) return 0;
+  size_t es = pl->dtype == DCTN_F32 ? 4 : 8;
+  size_t xb = (size_t)pl->C * B * H * W * pl->Q * es;
+  size_t cb = (size_t)pl->D * pl->O * es;
+  size_t ob = (size_t)B * (H - pl->K + 1) * (W - pl->K + 1) * pl->O * es;
+  return align256(xb) + align256(cb) + align256(ob) + dctn_eps_workspace_bytes(pl, B, H, W, DCTN_WS_FORWARD);
+}
+
+extern "C" int dctn_eps_forward_host(const dctn_plan_t* pl, const void* x_host, const void* core_host, void* out_host,
+                                     int B, int H, int W, void* scratch, size_t scratch_bytes, void* stream) {
+  int rc = check_call(pl, B, H, W);
+  if (rc) return rc;
+  if (!x_host || !core_host || !out_host) return dctn_set_error(DCTN_ERR_BAD_ARG, "forward_host: null host pointer");
+  size_t need = dctn_eps_forward_host_device_bytes(pl, B, H, W);
+  if (!scratch || scratch_bytes < need)
+    return dctn_set_error(DCTN_ERR_WORKSPACE, "forward_host: device scratch of %zu bytes needed, got %zu", need, scratch_bytes);
+  size_t es = pl->dtype == DCTN_F32 ? 4 : 8;
+  size_t xb = (size_t)pl->C * B * H * W * pl->Q * es;
+  size_t cb = (size_t)pl->D * pl->O * es;
+  size_t ob = (size_t)B * (H - pl->K + 1) * (W - pl->K + 1) * pl->O * es;
+  char* base = (char*)scratch;
+  void* xd = base;
+  void* cd = base + align256(xb);
+  void* od = base + align256(xb) + align256(cb);
+  void* ws = base + align256(xb) + align256(cb) + align256(ob);
+  size_t wsb = scratch_bytes - (align256(xb) + align256(cb) + align256(ob));
+  cudaStream_t st = (cudaStream_t)stream;
+  DCTN_CUDA_CHECK_RET(cudaMemcpyAsync(xd, x_host, xb, cudaMemcpyHostToDevice, st));
+  DCTN_CUDA_CHECK_RET(cudaMemcpyAsync(cd, core_host, cb, cudaMemcpyHostToDevice, st));
+  rc = dctn_eps_forward(pl, xd, cd, od, B, H, W, ws, wsb, stream);
+  if (rc) return rc;
+  DCTN_CUDA_CHECK_RET(cudaMemcpyAsync(out_host, od, ob, cudaMemcpyDeviceToHost, st));
+  DCTN_CUDA_CHECK_RET(cudaStreamSynchronize(st));
+  return 0;
+}

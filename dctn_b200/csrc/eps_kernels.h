@@ -1,0 +1,26 @@
+// Internal launcher interface between api.cu and the kernel families.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include "common.cuh"
+
+// ---- CUDA-core family (eps_ffma.cu): any shape, float / double
+template <typename T> size_t ffma_workspace_bytes(const EpsGeom& g, int kind);
+template <typename T> int ffma_forward(const EpsGeom& g, const T* x, const T* core, T* out, void* ws, cudaStream_t st);
+template <typename T> int ffma_backward_core(const EpsGeom& g, const T* x, const T* gout, T* dcore, void* ws, cudaStream_t st);
+template <typename T> int ffma_backward_input(const EpsGeom& g, const T* x, const T* core, const T* gout, T* dx, void* ws, cudaStream_t st);
+
+// ---- streaming thread-per-patch family for tiny cores (eps_direct.cu): HBM-bound shapes
+bool direct_supported(const EpsGeom& g, int dtype);
+template <typename T> int direct_forward(const EpsGeom& g, const T* x, const T* core, T* out, cudaStream_t st);
+
+// ---- tcgen05 TF32 family (eps_tc.cu): float only, large cores
+bool tc_supported(const EpsGeom& g, int kind);
+size_t tc_workspace_bytes(const EpsGeom& g, int kind);
+int tc_forward(const EpsGeom& g, const float* x, const float* core, float* out, void* ws, int passes, cudaStream_t st);
+int tc_backward_core(const EpsGeom& g, const float* x, const float* gout, float* dcore, void* ws, int passes, cudaStream_t st);
+int tc_backward_input(const EpsGeom& g, const float* x, const float* core, const float* gout, float* dx, void* ws, int passes, cudaStream_t st);
+
+// ---- logmatmulexp (logmatmulexp.cu)
+template <typename T> int lme_forward(const T* A, const T* B, T* out, int Th, int R, int I, cudaStream_t st);
+template <typename T> int lme_backward(const T* A, const T* B, const T* out, const T* gout, T* dA, T* dB, int Th, int R, int I, cudaStream_t st);

@@ -1,0 +1,240 @@
+"""EPS operator — same API as the reference's dctn/eps.py, contraction done by CUDA kernels.
+
+``eps(core, input)`` contracts, for every K x K patch of ``input`` (C, B, H, W, Q_in), the rank-one product
+of the K*K*C per-pixel vectors with ``core`` ((Q_in,)*(K*K*C) + (Q_out,)) and returns (B, H-K+1, W-K+1, Q_out)
+(reference: dctn/eps.py:19-40).  It is differentiable w.r.t. both arguments through
+:class:`EpsFunction`, which saves only ``(core, input)`` and calls the C ABI of libdctn_b200.so
+(include/dctn_b200.h): no Q^(K*K)-sized intermediate is ever kept for backward.
+"""
+from __future__ import annotations
+
+import logging
+import math
+import os
+from typing import Dict, Tuple
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import _lib
+
+_DTYPES = {torch.float32: _lib.F32, torch.float64: _lib.F64}
+_default_variant = _lib.VARIANTS.get(os.environ.get("DCTN_B200_VARIANT", "auto").lower(), _lib.VARIANT_AUTO)
+_plans: Dict[Tuple[int, int, int, int, int, int], int] = {}
+
+
+def set_default_variant(name: str) -> None:
+    """Select the kernel family for subsequent calls: 'auto' | 'ffma' | 'tc3' | 'tc1' | 'direct'."""
+    global _default_variant
+    _default_variant = _lib.VARIANTS[name.lower()]
+
+
+def get_default_variant() -> str:
+    return {v: k for k, v in _lib.VARIANTS.items()}[_default_variant]
+
+
+def _plan(C: int, K: int, Q: int, O: int, dtype: torch.dtype, variant: int) -> int:
+    key = (C, K, Q, O, _DTYPES[dtype], variant)
+    handle = _plans.get(key)
+    if handle is None:
+        handle = _lib.lib().dctn_eps_plan_get(*key)
+        if not handle:
+            raise RuntimeError(f"no EPS kernel plan for C={C} K={K} Q_in={Q} Q_out={O} {dtype}: {_lib.last_error()}")
+        _plans[key] = handle
+    return handle
+
+
+def plan_description(core: Tensor, input: Tensor) -> str:
+    C, K, Q, O = _infer(core, input)
+    return _lib.lib().dctn_eps_plan_describe(_plan(C, K, Q, O, input.dtype, _default_variant)).decode()
+
+
+def _infer(core: Tensor, input: Tensor) -> Tuple[int, int, int, int]:
+    """Shape contract of dctn/eps.py:20-23 (AssertionError on mismatch, like the reference)."""
+    num_channels, batch_size, height, width, in_size = input.shape
+    kernel_size = math.isqrt((core.ndim - 1) // num_channels)
+    assert core.shape[:-1] == tuple(in_size for _ in range(kernel_size ** 2 * num_channels))
+    return num_channels, kernel_size, in_size, core.shape[-1]
+
+
+def _check_device(core: Tensor, input: Tensor) -> None:
+    if not (input.is_cuda and core.is_cuda):
+        raise RuntimeError(
+            "dctn_b200.eps runs on CUDA tensors only (no CPU fallback); got "
+            f"core on {core.device}, input on {input.device}"
+        )
+    if core.device != input.device:
+        raise RuntimeError(f"core ({core.device}) and input ({input.device}) must be on the same device")
+    if input.dtype not in _DTYPES or core.dtype != input.dtype:
+        raise TypeError(f"eps supports float32/float64 with matching dtypes, got core {core.dtype}, input {input.dtype}")
+
+
+def _workspace(plan: int, B: int, H: int, W: int, kind: int, device) -> Tensor:
+    nbytes = _lib.lib().dctn_eps_workspace_bytes(plan, B, H, W, kind)
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
+class EpsFunction(torch.autograd.Function):
+    """autograd node of one EPS layer (forward: K1, backward: K2 core-gradient + K3 input-gradient)."""
+
+    @staticmethod
+    def forward(ctx, core: Tensor, input: Tensor, variant: int) -> Tensor:
+        C, K, Q, O = _infer(core, input)
+        _, B, H, W, _ = input.shape
+        core_c = core.detach().contiguous()
+        x_c = input.detach().contiguous()
+        plan = _plan(C, K, Q, O, input.dtype, variant)
+        out = torch.empty((B, H - K + 1, W - K + 1, O), dtype=input.dtype, device=input.device)
+        with torch.cuda.device(input.device):
+            ws = _workspace(plan, B, H, W, _lib.WS_FORWARD, input.device)
+            rc = _lib.lib().dctn_eps_forward(
+                plan, x_c.data_ptr(), core_c.data_ptr(), out.data_ptr(), B, H, W, ws.data_ptr(), ws.numel(),
+                torch.cuda.current_stream().cuda_stream,
+            )
+        _lib.check(rc, "dctn_eps_forward")
+        ctx.save_for_backward(core_c, x_c)
+        ctx.plan = plan
+        ctx.core_shape = core.shape
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout: Tensor):
+        core_c, x_c = ctx.saved_tensors
+        _, B, H, W, _ = x_c.shape
+        gout = gout.contiguous()
+        dcore = dx = None
+        lib = _lib.lib()
+        with torch.cuda.device(x_c.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            if ctx.needs_input_grad[0]:
+                dcore = torch.empty_like(core_c)
+                ws = _workspace(ctx.plan, B, H, W, _lib.WS_BACKWARD_CORE, x_c.device)
+                rc = lib.dctn_eps_backward_core(
+                    ctx.plan, x_c.data_ptr(), gout.data_ptr(), dcore.data_ptr(), B, H, W, ws.data_ptr(), ws.numel(), stream
+                )
+                _lib.check(rc, "dctn_eps_backward_core")
+                dcore = dcore.view(ctx.core_shape)
+            if ctx.needs_input_grad[1]:
+                dx = torch.empty_like(x_c)
+                ws = _workspace(ctx.plan, B, H, W, _lib.WS_BACKWARD_INPUT, x_c.device)
+                rc = lib.dctn_eps_backward_input(
+                    ctx.plan, x_c.data_ptr(), core_c.data_ptr(), gout.data_ptr(), dx.data_ptr(), B, H, W,
+                    ws.data_ptr(), ws.numel(), stream,
+                )
+                _lib.check(rc, "dctn_eps_backward_input")
+        return dcore, dx, None
+
+
+def eps(core: Tensor, input: Tensor) -> Tensor:
+    """Drop-in for dctn/eps.py:19-40."""
+    _infer(core, input)  # AssertionError first, as in the reference
+    _check_device(core, input)
+    return EpsFunction.apply(core, input, _default_variant)
+
+
+def eps_one_by_one(core: Tensor, input: Tensor) -> Tensor:
+    """Drop-in for dctn/eps.py:43-63.  The reference contracts one aligned factor at a time; the result is
+    the same tensor, so this routes to the same fused kernel."""
+    out = eps(core, input)
+    num_channels, batch_size, height, width, in_size = input.shape
+    kernel_size = math.isqrt((core.ndim - 1) // num_channels)
+    assert out.shape == (batch_size, height - kernel_size + 1, width - kernel_size + 1, core.shape[-1])
+    return out
+
+
+def calc_eps_shape(kernel_size: int, in_num_channels: int, in_size: int, out_size: int) -> Tuple[int, ...]:
+    """Shape an EPS core with these parameters must have (dctn/eps.py:66-70)."""
+    return (in_size,) * (kernel_size ** 2 * in_num_channels) + (out_size,)
+
+
+spec_to_shape = calc_eps_shape  # dctn/eps.py:184-187 is the same function under another name
+
+
+def total_in_dim_size(kernel_size: int, in_num_channels: int, in_size: int) -> int:
+    return in_size ** (in_num_channels * kernel_size ** 2)
+
+
+def is_eps(a: Tensor) -> bool:
+    """Whether `a` can plausibly be an EPS core judging by its shape (dctn/eps.py:115-117)."""
+    return a.ndim >= 2 and all(s == a.shape[0] for s in a.shape[:-1])
+
+
+def matrix_shape(eps_core: Tensor) -> Tuple[int, int]:
+    """(out_size, total input size) — dctn/eps.py:99-103."""
+    assert is_eps(eps_core)
+    return eps_core.shape[-1], math.prod(eps_core.shape[:-1])
+
+
+def contract_on_input_dims(a: Tensor, b: Tensor) -> Tensor:
+    """(out dim of a, out dim of b) Gram matrix over all input dims (dctn/eps.py:106-112)."""
+    assert is_eps(a) and is_eps(b)
+    return a.reshape(-1, a.shape[-1]).T @ b.reshape(-1, b.shape[-1])
+
+
+def inner_product(a: Tensor, b: Tensor) -> Tensor:
+    """Frobenius inner product of two cores of equal shape (dctn/eps.py:120-123)."""
+    assert a.shape == b.shape
+    assert is_eps(a)
+    return torch.dot(a.reshape(-1), b.reshape(-1))
+
+
+@torch.no_grad()
+def transform_in_slices(eps_core: Tensor, x: Tensor, batch_size: int) -> Tensor:
+    """Forward-only transform of a whole dataset x (C, N, H, W, Q_in) in slices of `batch_size` samples;
+    returns (1, N, H', W', Q_out) (dctn/eps.py:126-137).  Slices of a C>1 tensor are non-contiguous;
+    EpsFunction makes them contiguous."""
+    assert is_eps(eps_core)
+    outs = [eps(eps_core, piece) for piece in x.split(batch_size, dim=1)]
+    return torch.cat(outs).unsqueeze(0)
+
+
+def make_eps_unit_theoretical_output_std(
+    kernel_size: int, in_num_channels: int, in_size: int, out_size: int, device: torch.device, dtype: torch.dtype
+) -> Tensor:
+    """randn core scaled by D^-1/2 so that the forward pass preserves the std (dctn/eps.py:144-160)."""
+    std = total_in_dim_size(kernel_size, in_num_channels, in_size) ** -0.5
+    logging.getLogger(f"{__name__}.make_eps_unit_theoretical_output_std").info(
+        f"Multiplying the output of randn by {std:.30e}"
+    )
+    shape = calc_eps_shape(kernel_size, in_num_channels, in_size, out_size)
+    return std * torch.randn(*shape, dtype=dtype).to(device)
+
+
+def make_eps_unit_empirical_output_std(
+    kernel_size: int, out_size: int, input: Tensor, device: torch.device, dtype: torch.dtype, batch_size: int
+) -> Tensor:
+    """randn core rescaled so that its output on `input` has unit (biased) std (dctn/eps.py:163-181)."""
+    num_channels, dataset_size, height, width, in_size = input.shape
+    core = torch.randn(*(in_size,) * (kernel_size ** 2 * num_channels), out_size, dtype=dtype).to(device)
+    output = transform_in_slices(core, input.to(device, dtype), batch_size)
+    inv_std = output.std(unbiased=False) ** -1
+    logger = logging.getLogger(f"{__name__}.make_eps_unit_empirical_output_std")
+    logger.info(f"Multiplying the output of randn by {inv_std:.30e}")
+    core *= inv_std
+    logger.info(f"Initialized an EPS with empirical std = {core.std(unbiased=False):.30e}")
+    return core
+
+
+class EPS(nn.Module):
+    """One EPS layer holding its ``core`` parameter (dctn/eps.py:73-96)."""
+
+    def __init__(self, kernel_size: int, in_num_channels: int, in_size: int, out_size: int):
+        super().__init__()
+        self.kernel_size = kernel_size
+        self.in_num_channels = in_num_channels
+        self.in_size = in_size
+        self.out_size = out_size
+        self.core = nn.Parameter(
+            make_eps_unit_theoretical_output_std(
+                kernel_size, in_num_channels, in_size, out_size, torch.device("cpu"), torch.float32
+            )
+        )
+
+    @property
+    def matrix_shape(self) -> Tuple[int, int]:
+        return matrix_shape(self.core)
+
+    def forward(self, input: Tensor) -> Tensor:
+        return eps(self.core, input)

@@ -1,0 +1,65 @@
+"""Log-space matrix product — API of dctn/logmatmulexp.py:5-22.
+
+``logmatmulexp(log_A, log_B)`` = log(exp(log_A) @ exp(log_B)) for 2-D inputs, computed by a max-shifted
+online-logsumexp CUDA kernel.  Neither forward nor backward materialises the (Theta, R, I) tensor the
+reference builds, so ``logmatmulexp_lowmem`` (checkpointing in the reference) is the same function.
+"""
+import torch
+from torch import Tensor
+
+from . import _lib
+
+_DTYPES = {torch.float32: _lib.F32, torch.float64: _lib.F64}
+
+
+class _LogMatMulExp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, log_A: Tensor, log_B: Tensor) -> Tensor:
+        theta, R = log_A.shape
+        I = log_B.shape[1]
+        a = log_A.detach().contiguous()
+        b = log_B.detach().contiguous()
+        out = torch.empty((theta, I), dtype=a.dtype, device=a.device)
+        with torch.cuda.device(a.device):
+            rc = _lib.lib().dctn_logmatmulexp_forward(
+                a.data_ptr(), b.data_ptr(), out.data_ptr(), theta, R, I, _DTYPES[a.dtype],
+                torch.cuda.current_stream().cuda_stream,
+            )
+        _lib.check(rc, "dctn_logmatmulexp_forward")
+        ctx.save_for_backward(a, b, out)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout: Tensor):
+        a, b, out = ctx.saved_tensors
+        theta, R = a.shape
+        I = b.shape[1]
+        gout = gout.contiguous()
+        dA = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        dB = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(a.device):
+            rc = _lib.lib().dctn_logmatmulexp_backward(
+                a.data_ptr(), b.data_ptr(), out.data_ptr(), gout.data_ptr(),
+                dA.data_ptr() if dA is not None else None, dB.data_ptr() if dB is not None else None,
+                theta, R, I, _DTYPES[a.dtype], torch.cuda.current_stream().cuda_stream,
+            )
+        _lib.check(rc, "dctn_logmatmulexp_backward")
+        return dA, dB
+
+
+def logmatmulexp(log_A: Tensor, log_B: Tensor, /) -> Tensor:
+    """log_A: Theta x R, log_B: R x I -> (log_A.exp() @ log_B.exp()).log(), stable forward and backward."""
+    theta, R = log_A.shape  # ValueError for non 2-D input, like the reference's unpacking
+    I = log_B.shape[1]
+    assert log_B.shape == (R, I)
+    if not (log_A.is_cuda and log_B.is_cuda):
+        raise RuntimeError("dctn_b200.logmatmulexp runs on CUDA tensors only (no CPU fallback)")
+    if log_A.dtype not in _DTYPES or log_A.dtype != log_B.dtype:
+        raise TypeError(f"logmatmulexp supports matching float32/float64 inputs, got {log_A.dtype} and {log_B.dtype}")
+    return _LogMatMulExp.apply(log_A, log_B)
+
+
+def logmatmulexp_lowmem(log_A: Tensor, log_B: Tensor, /) -> Tensor:
+    """Same as logmatmulexp; the CUDA path never saves a (Theta, R, I)-shaped tensor."""
+    return logmatmulexp(log_A, log_B)

@@ -1,0 +1,118 @@
+/*
+ * dctn_b200 — C ABI of the B200-native EPS contraction library (libdctn_b200.so).
+ *
+ * The reference (philip-bl/dctn) is pure Python: it has no FFI/plugin interface, its boundary for
+ * this path is the Python function signature.  The entry points below are what a binding for the
+ * reference's hot path binds instead of the opt_einsum/torch.einsum calls; each one cites the
+ * reference call site it replaces.  INTEGRATION.md shows the ctypes stub and the
+ * torch.autograd.Function a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers unless the name ends in
+ *     `_host`; every tensor is dense row-major ("contiguous");
+ *   - every launch goes on the cudaStream_t passed by the caller (as a void*), nothing synchronises;
+ *   - the library allocates no device memory: scratch is a caller-provided workspace whose size is
+ *     queried with dctn_eps_workspace_bytes();
+ *   - functions return 0 on success and a negative dctn_status on failure, never throw;
+ *     dctn_last_error() returns a thread-local message.  There is no CPU fallback.
+ *
+ * Tensor layouts (reference names)
+ *   input  x    : (C, B, H, W, Q_in)        dctn/eps.py:20
+ *   core        : (Q_in,)*(K*K*C) + (Q_out,) dctn/eps.py:22,66-70; flat view [D = Q_in^(K*K*C)][Q_out],
+ *                 factor j = (dh*K + dw)*C + c is the j-th (slowest-first) index  dctn/align.py:20-46
+ *   output      : (B, H-K+1, W-K+1, Q_out)   dctn/eps.py:39
+ */
+#ifndef DCTN_B200_H
+#define DCTN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCTN_B200_VERSION 100 /* 0.1.0 */
+
+typedef enum dctn_status {
+  DCTN_OK = 0,
+  DCTN_ERR_BAD_ARG = -1,      /* null pointer, non-positive size, image smaller than the kernel */
+  DCTN_ERR_UNSUPPORTED = -2,  /* shape outside what the kernels implement (message says which limit) */
+  DCTN_ERR_WORKSPACE = -3,    /* workspace pointer null or smaller than dctn_eps_workspace_bytes() */
+  DCTN_ERR_CUDA = -4          /* a CUDA runtime call failed (message holds cudaGetErrorString) */
+} dctn_status;
+
+typedef enum dctn_dtype { DCTN_F32 = 0, DCTN_F64 = 1 } dctn_dtype;
+
+/* Kernel family selection ("static per-shape kernel plan", replaces the opt_einsum path cache
+ * dctn/contraction_path_cache.py:19-35 and the hard-coded path dctn/eps.py:25-30). */
+typedef enum dctn_variant {
+  DCTN_VARIANT_AUTO = 0, /* library picks per shape (default) */
+  DCTN_VARIANT_FFMA = 1, /* CUDA-core FMA kernels, exact fp32/fp64 arithmetic, any shape */
+  DCTN_VARIANT_TC3 = 2,  /* tcgen05 TF32 tensor cores, 3-pass split (hi*hi + hi*lo + lo*hi): fp32-accurate */
+  DCTN_VARIANT_TC1 = 3,  /* tcgen05 TF32 single pass (rel. err ~1e-3), opt-in only */
+  DCTN_VARIANT_DIRECT = 4 /* thread-per-patch streaming kernel for tiny cores (HBM-bound shapes) */
+} dctn_variant;
+
+typedef enum dctn_ws_kind {
+  DCTN_WS_FORWARD = 0,
+  DCTN_WS_BACKWARD_CORE = 1,
+  DCTN_WS_BACKWARD_INPUT = 2
+} dctn_ws_kind;
+
+typedef struct dctn_plan dctn_plan_t; /* opaque, owned by the library's plan cache, never freed by the caller */
+
+int dctn_version(void);
+const char* dctn_last_error(void);
+
+/* Returns the cached plan for an EPS layer (kernel_size K, in_num_channels C, in_size Qin,
+ * out_size Qout — dctn/eps.py:66-70 calc_eps_shape), or NULL (see dctn_last_error).  Thread-safe. */
+const dctn_plan_t* dctn_eps_plan_get(int C, int K, int Qin, int Qout, int dtype, int variant);
+
+/* Human-readable description of the plan (split, tile shapes, kernel family); static storage per plan. */
+const char* dctn_eps_plan_describe(const dctn_plan_t* plan);
+
+/* Scratch bytes needed by the call `kind` on a (C,B,H,W,Qin) input. */
+size_t dctn_eps_workspace_bytes(const dctn_plan_t* plan, int B, int H, int W, int kind);
+
+/* out = eps(core, x).  Replaces dctn/eps.py:19-40 (align views + 4-step opt_einsum contraction);
+ * eps_one_by_one (dctn/eps.py:43-63) maps to the same call. */
+int dctn_eps_forward(const dctn_plan_t* plan, const void* x, const void* core, void* out,
+                     int B, int H, int W, void* workspace, size_t workspace_bytes, void* stream);
+
+/* dcore = d<gout, eps(core, x)>/dcore.  Replaces autograd through dctn/eps.py:31-40 w.r.t. `core`
+ * (dense reduction over all patches).  dcore is overwritten (not accumulated). */
+int dctn_eps_backward_core(const dctn_plan_t* plan, const void* x, const void* gout, void* dcore,
+                           int B, int H, int W, void* workspace, size_t workspace_bytes, void* stream);
+
+/* dx = d<gout, eps(core, x)>/dx.  Replaces autograd through dctn/eps.py:31-40 w.r.t. `input`
+ * (needed for layers >= 2, dctn/epses_composition.py:139-141).  dx is overwritten. */
+int dctn_eps_backward_input(const dctn_plan_t* plan, const void* x, const void* core, const void* gout,
+                            void* dx, int B, int H, int W, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
+/* out[t,i] = log sum_r exp(log_A[t,r] + log_B[r,i]).  Replaces dctn/logmatmulexp.py:5-14. */
+int dctn_logmatmulexp_forward(const void* log_A, const void* log_B, void* out, int Theta, int R, int I,
+                              int dtype, void* stream);
+
+/* Gradients of the above given out (saved from forward) and gout; nothing Theta*R*I-sized is kept,
+ * which is what logmatmulexp_lowmem (dctn/logmatmulexp.py:17-22) buys with checkpointing.
+ * dA / dB may be NULL to skip. */
+int dctn_logmatmulexp_backward(const void* log_A, const void* log_B, const void* out, const void* gout,
+                               void* dA, void* dB, int Theta, int R, int I, int dtype, void* stream);
+
+/* Host-buffer convenience entry (end-to-end path): copies x and core from HOST memory, runs the
+ * forward on `stream`, copies `out` back and synchronises the stream.  All three pointers are host
+ * pointers; device scratch of dctn_eps_forward_host_device_bytes() bytes is passed by the caller. */
+size_t dctn_eps_forward_host_device_bytes(const dctn_plan_t* plan, int B, int H, int W);
+int dctn_eps_forward_host(const dctn_plan_t* plan, const void* x_host, const void* core_host,
+                          void* out_host, int B, int H, int W, void* device_scratch,
+                          size_t device_scratch_bytes, void* stream);
+
+/* Counts kernels launched by this library on the calling process since load (bench.py's gpu_launches). */
+unsigned long long dctn_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCTN_B200_H */

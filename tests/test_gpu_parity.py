@@ -1,0 +1,283 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against
+(1) golden vectors produced by the unmodified reference, (2) the CPU oracle on seeded inputs, and
+(3) size-independent identities at BASELINE.json's full sizes.
+
+Tolerances (Frobenius-relative):
+  float64 kernels vs float64 reference : 1e-11
+  float32 kernels (FFMA and 3-pass TF32 tcgen05) vs float64 reference : 1e-5
+"""
+from functools import reduce
+
+import pytest
+import torch
+
+from conftest import CONVSBS_CASES, EPS_GOLDEN_CASES, LME_GOLDEN_CASES, load_golden
+from oracle import eps_oracle as O
+from oracle.eps_oracle import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float64: 1e-11, torch.float32: 1e-5}
+DEV = "cuda:0"
+
+
+def _eps_fwd_bwd(core64, x64, gout64, dtype, variant="auto"):
+    from dctn_b200 import eps as E
+
+    old = E.get_default_variant()
+    E.set_default_variant(variant)
+    try:
+        core = core64.to(DEV, dtype).requires_grad_(True)
+        x = x64.to(DEV, dtype).requires_grad_(True)
+        out = E.eps(core, x)
+        out.backward(gout64.to(DEV, dtype))
+        torch.cuda.synchronize()
+        return out.detach(), core.grad, x.grad
+    finally:
+        E.set_default_variant(old)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("name", EPS_GOLDEN_CASES)
+def test_eps_golden(name, dtype):
+    g = load_golden(name)
+    out, dcore, dx = _eps_fwd_bwd(g["core"], g["x"], g["gout"], dtype)
+    assert out.shape == g["out"].shape and out.dtype == dtype
+    assert rel_err(out, g["out"]) <= TOL[dtype]
+    assert rel_err(dcore, g["dcore"]) <= TOL[dtype]
+    assert rel_err(dx, g["dx"]) <= TOL[dtype]
+
+
+@pytest.mark.parametrize("name", EPS_GOLDEN_CASES[:3])
+def test_eps_one_by_one_golden(name):
+    """reference tests/test_eps.py:9-61 exercise eps_one_by_one."""
+    from dctn_b200.eps import eps_one_by_one
+
+    g = load_golden(name)
+    out = eps_one_by_one(g["core"].to(DEV), g["x"].to(DEV))
+    assert rel_err(out, g["out_one_by_one"]) <= TOL[torch.float64]
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("name", CONVSBS_CASES)
+def test_eps_matches_convsbs(name, dtype):
+    """reference tests/test_conversion_of_convsbs_to_eps.py:13-56 (output and input-gradient vs ConvSBS)."""
+    g = load_golden(name)
+    out, _, dx = _eps_fwd_bwd(g["eps_tensor"], g["x"], g["gout"], dtype)
+    tol = 1e-9 if dtype == torch.float64 else 1e-5
+    assert rel_err(out, g["convsbs_out"]) <= tol
+    assert rel_err(dx, g["convsbs_dx"]) <= tol
+
+
+# (C, B, H, W, Q, K, O) — seeded random shapes checked against the oracle; includes the paper's layer
+# shapes (K=4,Q=2,O=4 and K=3,Q=4,O=6), CIFAR-shaped (Q=23 -> O=24), ragged patch counts, B=1, H=K.
+ORACLE_SHAPES = [
+    (1, 3, 9, 8, 2, 4, 4),
+    (1, 2, 7, 6, 4, 3, 6),
+    (1, 2, 6, 5, 23, 2, 24),
+    (1, 5, 28, 28, 2, 2, 2),
+    (1, 1, 2, 2, 2, 2, 3),
+    (1, 1, 3, 7, 3, 3, 2),
+    (2, 3, 5, 4, 3, 2, 4),
+    (1, 2, 8, 8, 4, 2, 23),
+    (1, 130, 4, 4, 2, 2, 6),
+    (1, 2, 5, 5, 12, 2, 24),
+    (1, 3, 4, 6, 5, 1, 7),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("shape", ORACLE_SHAPES)
+def test_eps_vs_oracle(shape, dtype):
+    C, B, H, W, Q, K, Oq = shape
+    g = torch.Generator().manual_seed(hash(shape) % (2 ** 31))
+    n = K * K * C
+    x = torch.randn(C, B, H, W, Q, dtype=torch.float64, generator=g) * (0.9 if n > 4 else 1.0)
+    core = torch.randn(*(Q,) * n, Oq, dtype=torch.float64, generator=g) * Q ** (-n / 2)
+    gout = torch.randn(B, H - K + 1, W - K + 1, Oq, dtype=torch.float64, generator=g)
+    if dtype == torch.float32:  # compare on the float32-rounded inputs, in float64 arithmetic
+        x, core, gout = x.float().double(), core.float().double(), gout.float().double()
+    want = O.eps_4step(core, x)
+    want_dcore, want_dx = O.eps_grads(core, x, gout)
+    out, dcore, dx = _eps_fwd_bwd(core, x, gout, dtype)
+    assert rel_err(out, want) <= TOL[dtype]
+    assert rel_err(dcore, want_dcore) <= TOL[dtype]
+    assert rel_err(dx, want_dx) <= TOL[dtype]
+
+
+@pytest.mark.parametrize("variant", ["ffma"])
+@pytest.mark.parametrize("shape", [(1, 3, 9, 8, 2, 4, 4), (1, 2, 7, 6, 4, 3, 6), (1, 5, 12, 12, 2, 2, 2)])
+def test_eps_forced_variant_vs_oracle(shape, variant):
+    C, B, H, W, Q, K, Oq = shape
+    g = torch.Generator().manual_seed(7)
+    n = K * K * C
+    x = (torch.randn(C, B, H, W, Q, dtype=torch.float64, generator=g) * 0.9).float().double()
+    core = (torch.randn(*(Q,) * n, Oq, dtype=torch.float64, generator=g) * Q ** (-n / 2)).float().double()
+    gout = torch.randn(B, H - K + 1, W - K + 1, Oq, dtype=torch.float64, generator=g).float().double()
+    want = O.eps_4step(core, x)
+    want_dcore, want_dx = O.eps_grads(core, x, gout)
+    out, dcore, dx = _eps_fwd_bwd(core, x, gout, torch.float32, variant)
+    assert rel_err(out, want) <= 1e-5 and rel_err(dcore, want_dcore) <= 1e-5 and rel_err(dx, want_dx) <= 1e-5
+
+
+def test_eps_non_contiguous_input_and_no_grad_paths():
+    """transform_in_slices hands eps() non-contiguous slices when C > 1 (dctn/eps.py:136)."""
+    from dctn_b200.eps import eps, transform_in_slices
+
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 7, 5, 5, 2, dtype=torch.float64, generator=g)
+    core = torch.randn(*(2,) * 8, 3, dtype=torch.float64, generator=g)
+    want = torch.cat([O.eps_4step(core, s) for s in x.split(3, dim=1)]).unsqueeze(0)
+    got = transform_in_slices(core.to(DEV), x.to(DEV), 3)
+    assert got.shape == want.shape and rel_err(got, want) <= 1e-11
+    xs = x.to(DEV)[:, 1:4]
+    assert not xs.is_contiguous()
+    assert rel_err(eps(core.to(DEV), xs), O.eps_4step(core, x[:, 1:4])) <= 1e-11
+    # only the core requires grad (layer 1 of a model: input is data)
+    c = core.to(DEV).requires_grad_(True)
+    eps(c, x.to(DEV)).sum().backward()
+    assert c.grad is not None
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_composition_three_layers(dtype):
+    from dctn_b200.epses_composition import contract_with_input
+
+    g = load_golden("composition_3layers")
+    cores = [g[k].to(DEV, dtype).requires_grad_(True) for k in ("e1", "e2", "e3")]
+    x = g["x"].to(DEV, dtype).requires_grad_(True)
+    out = contract_with_input(cores, x)
+    out.backward(g["gout"].to(DEV, dtype))
+    assert rel_err(out, g["out"]) <= TOL[dtype]
+    for c, k in zip(cores, ("de1", "de2", "de3")):
+        assert rel_err(c.grad, g[k]) <= TOL[dtype]
+    assert rel_err(x.grad, g["dx"]) <= TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("name,specs,img", [("epl_cfg1_k2q2", ((2, 2),), 28), ("epl_two_layers", ((3, 4), (2, 6)), 10)])
+def test_eps_plus_linear_logits_and_grads(name, specs, img, dtype):
+    """Config-1-shaped model and a 2-layer model: logits, loss and every parameter gradient vs the reference."""
+    from dctn_b200.eps_plus_linear import EPSesPlusLinear, UnitTheoreticalOutputStd
+
+    g = load_golden(name)
+    model = EPSesPlusLinear(specs, UnitTheoreticalOutputStd(), 1.0, torch.device(DEV), dtype, image_size=img)
+    with torch.no_grad():
+        for i in range(len(specs)):
+            model.epses[i].copy_(g[f"eps{i}"])
+        model.linear.weight.copy_(g["weight"])
+        model.linear.bias.copy_(g["bias"])
+    logits = model(g["x"].to(DEV, dtype))
+    loss = torch.nn.functional.cross_entropy(logits, g["y"].to(DEV))
+    loss.backward()
+    assert rel_err(logits, g["logits"]) <= TOL[dtype]
+    assert rel_err(loss, g["loss"]) <= TOL[dtype]
+    for i in range(len(specs)):
+        assert rel_err(model.epses[i].grad, g[f"deps{i}"]) <= TOL[dtype]
+    assert rel_err(model.linear.weight.grad, g["dweight"]) <= TOL[dtype]
+    assert rel_err(model.linear.bias.grad, g["dbias"]) <= TOL[dtype]
+    assert rel_err(model.epswise_l2_regularizer(), g["reg_epswise"]) <= TOL[dtype]
+    assert rel_err(model.epses_composition_l2_regularizer(), g["reg_composition"]) <= 10 * TOL[dtype]
+
+
+def test_core_dropout_is_one_mask_per_step():
+    from dctn_b200.eps_plus_linear import EPSesPlusLinear, UnitTheoreticalOutputStd
+
+    model = EPSesPlusLinear(((2, 2),), UnitTheoreticalOutputStd(), 0.5, torch.device(DEV), torch.float32, image_size=6)
+    x = torch.rand(1, 4, 6, 6, 2, device=DEV)
+    model.train()
+    torch.manual_seed(5)
+    a = model(x)
+    torch.manual_seed(5)
+    b = model(x)
+    assert torch.equal(a, b)  # same seed -> same mask -> identical (what the DP ranks rely on)
+    model.eval()
+    assert not torch.equal(model(x), a)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("name", LME_GOLDEN_CASES)
+def test_logmatmulexp_golden(name, dtype):
+    from dctn_b200.logmatmulexp import logmatmulexp, logmatmulexp_lowmem
+
+    g = load_golden(name)
+    A = g["log_A"].to(DEV, dtype).requires_grad_(True)
+    B = g["log_B"].to(DEV, dtype).requires_grad_(True)
+    if dtype == torch.float32:  # reference values on the float32-rounded inputs
+        a64, b64 = A.detach().double().cpu(), B.detach().double().cpu()
+        want = O.logmatmulexp(a64, b64)
+        want_dA, want_dB = O.logmatmulexp_grads(a64, b64, g["gout"].float().double())
+    else:
+        want, want_dA, want_dB = g["out"], g["dA"], g["dB"]
+    out = logmatmulexp(A, B)
+    out.backward(g["gout"].to(DEV, dtype))
+    tol = 1e-11 if dtype == torch.float64 else 1e-5
+    assert rel_err(out, want) <= tol
+    assert rel_err(A.grad, want_dA) <= tol and rel_err(B.grad, want_dB) <= tol
+    assert rel_err(logmatmulexp_lowmem(A.detach(), B.detach()), want) <= tol
+    assert torch.isfinite(out).all()
+
+
+def test_logmatmulexp_chain_and_extremes():
+    from dctn_b200.logmatmulexp import logmatmulexp
+
+    g = load_golden("lme_chain6")
+    mats = [g[f"m{i}"].to(DEV) for i in range(6)]
+    mats[0].requires_grad_(True)
+    out = reduce(logmatmulexp, mats)
+    out.backward(torch.ones_like(out))
+    assert rel_err(out, g["out"]) <= 1e-11
+    assert rel_err(mats[0].grad, g["dm0"]) <= 1e-11
+    # -inf entries (log of zero probabilities) must not produce NaNs
+    A = torch.full((4, 5), float("-inf"), device=DEV, dtype=torch.float32)
+    A[:, 0] = 0.0
+    B = torch.randn(5, 3, device=DEV)
+    out = logmatmulexp(A, B)
+    assert torch.allclose(out, B[0].expand(4, 3), atol=1e-6)
+
+
+# ---------------------------------------------------------------- full BASELINE sizes, oracle-free identities
+FULL_LAYERS = [
+    # (name, B, H, W, Q, K, O)  — config 2: layer 1 and layer 2 at batch 512; config 1 at batch 128 (float64)
+    ("cfg2_L1", 512, 28, 28, 2, 4, 4, torch.float32),
+    ("cfg2_L2", 512, 25, 25, 4, 3, 6, torch.float32),
+    ("cfg1", 128, 28, 28, 2, 2, 2, torch.float64),
+]
+
+
+@pytest.mark.parametrize("name,B,H,W,Q,K,Oq,dtype", FULL_LAYERS)
+def test_full_size_identities(name, B, H, W, Q, K, Oq, dtype):
+    """At full size the oracle is too slow; use exact algebraic identities of the contraction instead:
+       * adjointness:   <gout, eps(core, x)> == <dcore, core>      (eps is linear in core)
+       * homogeneity:   <dx, x> == n * <gout, eps(core, x)>        (eps is multilinear in the n factors)
+       * linearity in core: eps(2.5*c1 - c2, x) == 2.5*eps(c1, x) - eps(c2, x)
+       * batch independence: the first image's patches equal a B=1 run (checked against the oracle)."""
+    from dctn_b200.eps import eps
+
+    gen = torch.Generator().manual_seed(11)
+    n = K * K
+    x = (torch.rand(1, B, H, W, Q, generator=gen, dtype=torch.float64) * 1.2 + 0.2).to(DEV, dtype).requires_grad_(True)
+    c1 = (torch.randn(*(Q,) * n, Oq, generator=gen, dtype=torch.float64) * Q ** (-n / 2)).to(DEV, dtype).requires_grad_(True)
+    c2 = (torch.randn(*(Q,) * n, Oq, generator=gen, dtype=torch.float64) * Q ** (-n / 2)).to(DEV, dtype)
+    out = eps(c1, x)
+    gout = torch.randn(out.shape, generator=gen, dtype=torch.float64).to(DEV, dtype)
+    out.backward(gout)
+    inner = (gout.double() * out.detach().double()).sum()
+    tol = 1e-10 if dtype == torch.float64 else 2e-5
+    assert abs(((c1.grad.double() * c1.detach().double()).sum() - inner) / inner) <= tol
+    assert abs(((x.grad.double() * x.detach().double()).sum() - n * inner) / (n * inner)) <= tol
+    with torch.no_grad():
+        lin = eps(2.5 * c1 - c2, x)
+        assert rel_err(lin, 2.5 * out.detach().double() - eps(c2, x).double()) <= tol
+    # first image against the oracle
+    want0 = O.eps_4step(c1.detach().double().cpu(), x.detach().double().cpu()[:, :1])
+    assert rel_err(out[:1], want0) <= (1e-11 if dtype == torch.float64 else 1e-5)
+    # core-gradient of a single image against the oracle
+    want_dc, want_dx = O.eps_grads(c1.detach().double().cpu(), x.detach().double().cpu()[:, :1], gout[:1].double().cpu())
+    c3 = c1.detach().clone().requires_grad_(True)
+    x3 = x.detach()[:, :1].clone().requires_grad_(True)
+    eps(c3, x3).backward(gout[:1])
+    assert rel_err(c3.grad, want_dc) <= (1e-11 if dtype == torch.float64 else 1e-5)
+    assert rel_err(x3.grad, want_dx) <= (1e-11 if dtype == torch.float64 else 1e-5)
+    # input gradient of the batch run restricted to image 0 equals the single-image run (patches independent)
+    assert rel_err(x.grad[:, :1], x3.grad) <= (1e-11 if dtype == torch.float64 else 1e-5)
