@@ -544,6 +544,18 @@ template <typename T> long long post_patch_chunk(const EpsGeom& g, long long row
 // public launchers (declared in eps_kernels.h)
 // ------------------------------------------------------------------------------------------------
 template <typename T>
+int launch_reduce_partials(const T* part, T* out, long long count, int splits, cudaStream_t st) {
+  int blocks = (int)((count + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  reduce_partials_kernel<T><<<blocks, 256, 0, st>>>(part, out, count, splits);
+  dctn_count_launch();
+  DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  return 0;
+}
+template int launch_reduce_partials<float>(const float*, float*, long long, int, cudaStream_t);
+template int launch_reduce_partials<double>(const double*, double*, long long, int, cudaStream_t);
+
+template <typename T>
 size_t ffma_workspace_bytes(const EpsGeom& g, int kind) {
   if (kind == 0) {
     long long pc = post_patch_chunk<T>(g, g.N);
@@ -598,13 +610,7 @@ int ffma_backward_core(const EpsGeom& g, const T* x, const T* gout, T* dcore, vo
   k<<<grid, NTHREADS, smem, st>>>(a);
   dctn_count_launch();
   DCTN_CUDA_CHECK_RET(cudaGetLastError());
-  long long count = (long long)g.A * g.N;
-  int blocks = (int)((count + 255) / 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  reduce_partials_kernel<T><<<blocks, 256, 0, st>>>(a.part, dcore, count, splits);
-  dctn_count_launch();
-  DCTN_CUDA_CHECK_RET(cudaGetLastError());
-  return 0;
+  return launch_reduce_partials<T>(a.part, dcore, (long long)g.A * g.N, splits, st);
 }
 
 template <typename T>

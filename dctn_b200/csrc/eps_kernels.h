@@ -10,6 +10,9 @@ template <typename T> int ffma_forward(const EpsGeom& g, const T* x, const T* co
 template <typename T> int ffma_backward_core(const EpsGeom& g, const T* x, const T* gout, T* dcore, void* ws, cudaStream_t st);
 template <typename T> int ffma_backward_input(const EpsGeom& g, const T* x, const T* core, const T* gout, T* dx, void* ws, cudaStream_t st);
 
+// out[i] = sum_z part[z*count + i], fixed order (deterministic split-K reduction)
+template <typename T> int launch_reduce_partials(const T* part, T* out, long long count, int splits, cudaStream_t st);
+
 // ---- streaming thread-per-patch family for tiny cores (eps_direct.cu): HBM-bound shapes
 bool direct_supported(const EpsGeom& g, int dtype);
 template <typename T> int direct_forward(const EpsGeom& g, const T* x, const T* core, T* out, cudaStream_t st);

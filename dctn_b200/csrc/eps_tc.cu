@@ -1,8 +1,300 @@
-// tcgen05 TF32 family — placeholder until the kernels land (reports "unsupported" so AUTO never picks it).
+// tcgen05 (5th-gen tensor core) kernel family for the EPS contraction, float32 only.
+//
+// fp32 accuracy on TF32 tensor cores: every fp32 operand v is split on chip into hi (top 19 bits, exactly a
+// TF32 number) and lo = v - hi; a product a*b is issued as three MMAs  a_hi*b_hi + a_hi*b_lo + a_lo*b_hi
+// accumulated in the same fp32 TMEM accumulator ("3xTF32", error ~2^-21 per product).  passes == 1 issues
+// only a_hi*b_hi (plain TF32, rel. err ~1e-3, opt-in variant DCTN_VARIANT_TC1).
+//
+// Core gradient (dcore[a][n] = sum_p KR1[p][a] * KR2[p][b(n)] * gout[p][o(n)]), reduction over ALL patches:
+//   * CTA tile 128 (a) x 256 (n), one TMEM accumulator (256 columns), K = patches in chunks of 32;
+//   * BOTH operands are generated in shared memory by 8 producer warps from two-level Khatri-Rao tables
+//     (common.cuh) directly in the K-major SWIZZLE_128B layout tcgen05.mma reads — nothing Q^m-sized
+//     ever comes from HBM; only x (n*Q floats per patch) and gout (O floats per patch) are read;
+//   * warp 0 issues the MMAs (one elected thread), tcgen05.commit frees the stage / publishes the accumulator;
+//   * split-K: every CTA reduces at most `per_split` patches, partial tiles go to the workspace and a second
+//     kernel sums them in a fixed order (deterministic; also bounds the length of the tensor-core fp32
+//     accumulation chain, whose rounding is not round-to-nearest).
 #include "common.cuh"
 #include "eps_kernels.h"
-bool tc_supported(const EpsGeom&, int) { return false; }
-size_t tc_workspace_bytes(const EpsGeom&, int) { return 0; }
-int tc_forward(const EpsGeom&, const float*, const float*, float*, void*, int, cudaStream_t) { return dctn_set_error(-2, "tcgen05 family not built"); }
-int tc_backward_core(const EpsGeom&, const float*, const float*, float*, void*, int, cudaStream_t) { return dctn_set_error(-2, "tcgen05 family not built"); }
-int tc_backward_input(const EpsGeom&, const float*, const float*, const float*, float*, void*, int, cudaStream_t) { return dctn_set_error(-2, "tcgen05 family not built"); }
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int BM = 128;          // MMA M (rows of the accumulator = TMEM lanes)
+constexpr int BK = 32;           // K elements per stage (128 bytes per row)
+constexpr int STAGES = 2;
+constexpr int NPROD_WARPS = 8;   // producer warps (warps 1..8); warp 0 issues MMAs
+constexpr int NTHREADS_TC = 32 * (1 + NPROD_WARPS);
+constexpr int DCORE_SEG = 2048;  // max patches reduced into one TMEM accumulator
+
+struct TcDcoreArgs {
+  EpsGeom g;
+  const float* x;
+  const float* gout;
+  float* part;          // [splits][A][N]
+  long long per_split;  // multiple of BK
+  int passes;           // 3 (fp32-accurate) or 1
+};
+
+__device__ __forceinline__ void producer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * NPROD_WARPS) : "memory"); }
+
+// packed digits (one byte each, digit 0 = slowest) of entry e of a group with cnt <= 4 factors
+__device__ __forceinline__ uint32_t pack_digits(int e, int cnt, int Q) {
+  uint32_t packed = 0;
+  for (int t = cnt - 1; t >= 0; --t) {
+    packed |= (uint32_t)(e % Q) << (8 * t);
+    e /= Q;
+  }
+  return packed;
+}
+
+template <int BN>
+struct DcoreSmem {
+  static constexpr uint32_t A_BYTES = BM * BK * 4;   // 16 KB
+  static constexpr uint32_t B_BYTES = BN * BK * 4;   // 32 KB for BN = 256
+  static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr uint32_t OFF_A_HI = 0, OFF_A_LO = A_BYTES, OFF_B_HI = 2 * A_BYTES, OFF_B_LO = 2 * A_BYTES + B_BYTES;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_constant__ TcDcoreArgs a) {
+  using SM = DcoreSmem<BN>;
+  extern __shared__ unsigned char smem_dyn[];
+  const EpsGeom& g = a.g;
+  const int Q = g.Q, O = g.O;
+  const int BLO = g.BL * O;
+  const int TE = g.AH + g.AL + g.BH + BLO;   // table entries per patch
+  const int NX = g.n * Q;
+
+  // ---- carve shared memory (operand stages first, 1024-byte aligned for SWIZZLE_128B)
+  unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+  unsigned char* stages = base;
+  float* tab = (float*)(base + STAGES * SM::STAGE_BYTES);   // [TE][32]
+  float* xs = tab + TE * 32;                                 // [NX][32]
+  float* gs = xs + NX * 32;                                  // [O][32]
+  uint32_t* rowinfo = (uint32_t*)(gs + O * 32);              // [BM + BN]: hi entry | lo entry << 16, 0xFFFFFFFF = padding row
+  uint32_t* digits = rowinfo + BM + BN;                      // [AH + AL + BH + BL]
+  uint64_t* bars = (uint64_t*)(((uintptr_t)(digits + g.AH + g.AL + g.BH + g.BL) + 7) & ~(uintptr_t)7);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 1);
+  const uint32_t bar_full0 = tc::smem_u32(bars), bar_empty0 = bar_full0 + 8 * STAGES, bar_accum = bar_full0 + 16 * STAGES;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int a0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  long long pbeg = (long long)blockIdx.z * a.per_split;
+  long long pend = pbeg + a.per_split;
+  if (pend > g.P) pend = g.P;
+  const int nchunks = (int)((pend - pbeg + BK - 1) / BK);
+
+  // ---- one-time setup
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(bar_full0 + 8 * s, NPROD_WARPS);
+      tc::mbar_init(bar_empty0 + 8 * s, 1);
+    }
+    tc::mbar_init(bar_accum, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 0) tc::tmem_alloc(tc::smem_u32(tmem_slot), BN);
+  // row -> (hi entry, lo entry) and the digit tables
+  for (int r = tid; r < BM + BN; r += NTHREADS_TC) {
+    uint32_t info = 0xFFFFFFFFu;
+    if (r < BM) {
+      int ai = a0 + r;
+      if (ai < g.A) info = (uint32_t)(ai / g.AL) | ((uint32_t)(g.AH + ai % g.AL) << 16);
+    } else {
+      int ni = n0 + (r - BM);
+      if (ni < g.N) info = (uint32_t)(g.AH + g.AL + ni / BLO) | ((uint32_t)(g.AH + g.AL + g.BH + ni % BLO) << 16);
+    }
+    rowinfo[r] = info;
+  }
+  for (int e = tid; e < g.AH + g.AL + g.BH + g.BL; e += NTHREADS_TC) {
+    uint32_t d;
+    if (e < g.AH) d = pack_digits(e, g.a_nh, Q);
+    else if (e < g.AH + g.AL) d = pack_digits(e - g.AH, g.a_nl, Q);
+    else if (e < g.AH + g.AL + g.BH) d = pack_digits(e - g.AH - g.AL, g.b_nh, Q);
+    else d = pack_digits(e - g.AH - g.AL - g.BH, g.b_nl, Q);
+    digits[e] = d;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== MMA issuer ===========================
+    const uint32_t idesc = tc::make_idesc_tf32(BM, BN);
+    for (int c = 0; c < nchunks; ++c) {
+      const int s = c % STAGES;
+      const uint32_t it = (uint32_t)(c / STAGES);
+      tc::mbar_wait(bar_full0 + 8 * s, it & 1);
+      tc::tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sb = tc::smem_u32(stages + s * SM::STAGE_BYTES);
+        const uint64_t da_hi = tc::make_sw128_kmajor_desc(sb + SM::OFF_A_HI);
+        const uint64_t da_lo = tc::make_sw128_kmajor_desc(sb + SM::OFF_A_LO);
+        const uint64_t db_hi = tc::make_sw128_kmajor_desc(sb + SM::OFF_B_HI);
+        const uint64_t db_lo = tc::make_sw128_kmajor_desc(sb + SM::OFF_B_LO);
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          const uint64_t adv = (uint64_t)(k * 2);  // 32 bytes >> 4
+          if (a.passes == 3) {
+            // small terms first, then the dominant one
+            tc::umma_tf32(tmem_acc, da_lo + adv, db_hi + adv, idesc, (c > 0 || k > 0) ? 1u : 0u);
+            tc::umma_tf32(tmem_acc, da_hi + adv, db_lo + adv, idesc, 1u);
+            tc::umma_tf32(tmem_acc, da_hi + adv, db_hi + adv, idesc, 1u);
+          } else {
+            tc::umma_tf32(tmem_acc, da_hi + adv, db_hi + adv, idesc, (c > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        tc::umma_commit(bar_empty0 + 8 * s);            // stage can be refilled once these MMAs have read it
+        if (c == nchunks - 1) tc::umma_commit(bar_accum);  // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // =========================== producers ===========================
+    const int pw = warp - 1;  // 0..7
+    for (int c = 0; c < nchunks; ++c) {
+      const int s = c % STAGES;
+      const uint32_t it = (uint32_t)(c / STAGES);
+      // (1) stage x and gout of this chunk's 32 patches: lane = patch
+      {
+        const long long p = pbeg + (long long)c * BK + lane;
+        const bool ok = p < pend;
+        const long long org = ok ? patch_origin(g, p) : 0;
+        for (int jq = pw; jq < NX; jq += NPROD_WARPS) {
+          int j = jq / Q, q = jq - j * Q;
+          xs[jq * 32 + lane] = ok ? __ldg(&a.x[org + g.foff[j] + q]) : 0.f;
+        }
+        for (int o = pw; o < O; o += NPROD_WARPS) gs[o * 32 + lane] = ok ? __ldg(&a.gout[p * O + o]) : 0.f;
+      }
+      producer_bar_sync();
+      // (2) two-level Khatri-Rao tables, one warp per entry, lane = patch
+      for (int t = pw; t < TE; t += NPROD_WARPS) {
+        int e, j0, cnt;
+        float v = 1.f;
+        if (t < g.AH) { e = t; j0 = 0; cnt = g.a_nh; }
+        else if (t < g.AH + g.AL) { e = t; j0 = g.a_nh; cnt = g.a_nl; }
+        else if (t < g.AH + g.AL + g.BH) { e = t; j0 = g.m; cnt = g.b_nh; }
+        else {
+          int idx = t - (g.AH + g.AL + g.BH);
+          int el = idx / O;
+          v = gs[(idx - el * O) * 32 + lane];
+          e = g.AH + g.AL + g.BH + el; j0 = g.m + g.b_nh; cnt = g.b_nl;
+        }
+        const uint32_t dg = digits[e];
+        for (int u = 0; u < cnt; ++u) v *= xs[((j0 + u) * Q + ((dg >> (8 * u)) & 0xFF)) * 32 + lane];
+        tab[t * 32 + lane] = v;
+      }
+      producer_bar_sync();
+      // (3) wait until the MMAs that read this stage (two chunks ago) are done, then generate the operand tiles
+      tc::mbar_wait(bar_empty0 + 8 * s, (it & 1) ^ 1);
+      unsigned char* st = stages + s * SM::STAGE_BYTES;
+      for (int r = pw; r < BM + BN; r += NPROD_WARPS) {
+        const uint32_t info = rowinfo[r];
+        float v = 0.f;
+        if (info != 0xFFFFFFFFu) v = tab[(info & 0xFFFF) * 32 + lane] * tab[(info >> 16) * 32 + lane];
+        float hi, lo;
+        tc::split_tf32(v, hi, lo);
+        const bool isA = r < BM;
+        const int rr = isA ? r : r - BM;
+        const uint32_t off = tc::sw128_offset(rr, lane);
+        *(float*)(st + (isA ? SM::OFF_A_HI : SM::OFF_B_HI) + off) = hi;
+        if (a.passes == 3) *(float*)(st + (isA ? SM::OFF_A_LO : SM::OFF_B_LO) + off) = lo;
+      }
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(bar_full0 + 8 * s);
+    }
+    // =========================== epilogue: TMEM -> partial tile ===========================
+    tc::mbar_wait(bar_accum, 0);
+    tc::tc_fence_after();
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may access
+    const int half = (warp - 1) >> 2;    // which half of the columns
+    const int arow = a0 + quad * 32 + lane;
+    float* prow = a.part + ((long long)blockIdx.z * g.A + arow) * (long long)g.N;
+    for (int cb = 0; cb < BN / 2; cb += 32) {
+      const int col = half * (BN / 2) + cb;
+      float v[32];
+      tc::tmem_ld32(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)col, v);
+      if (arow < g.A) {
+        const int nb = n0 + col;
+        if (nb + 32 <= g.N && (g.N & 3) == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) *(float4*)(prow + nb + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (nb + i < g.N) prow[nb + i] = v[i];
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_acc, BN);
+}
+
+template <int BN>
+size_t dcore_tc_smem(const EpsGeom& g) {
+  const int BLO = g.BL * g.O;
+  const int TE = g.AH + g.AL + g.BH + BLO;
+  size_t b = 1024 + (size_t)STAGES * DcoreSmem<BN>::STAGE_BYTES + (size_t)(TE + g.n * g.Q + g.O) * 32 * 4 +
+             (size_t)(BM + BN) * 4 + (size_t)(g.AH + g.AL + g.BH + g.BL) * 4 + 8 + (2 * STAGES + 1) * 8 + 16;
+  return b;
+}
+
+constexpr size_t TC_SMEM_LIMIT = 227 * 1024;
+
+inline void dcore_split(const EpsGeom& g, long long* per_split, int* splits) {
+  long long per = DCORE_SEG;
+  if (per > g.P) per = ((g.P + BK - 1) / BK) * BK;
+  *per_split = per;
+  *splits = (int)((g.P + per - 1) / per);
+}
+
+}  // namespace
+
+bool tc_supported(const EpsGeom& g, int kind) {
+  if (kind != 1) return false;  // forward / input-gradient tcgen05 kernels: see tc_forward / tc_backward_input
+  if (g.a_nh > 4 || g.a_nl > 4 || g.b_nh > 4 || g.b_nl > 4) return false;  // packed digit bytes
+  if (g.Q > 255 || g.AH + g.AL + g.BH + g.BL * g.O >= 65535) return false;
+  if (g.A < 64 || g.N < 128) return false;   // tiles would be mostly padding: the CUDA-core family is the better fit
+  if (g.P < 4096) return false;              // tiny reductions are launch-bound either way
+  return dcore_tc_smem<256>(g) <= TC_SMEM_LIMIT;
+}
+
+size_t tc_workspace_bytes(const EpsGeom& g, int kind) {
+  if (kind == 1) {
+    long long per;
+    int splits;
+    dcore_split(g, &per, &splits);
+    return (size_t)splits * g.A * g.N * sizeof(float);
+  }
+  return 0;
+}
+
+int tc_backward_core(const EpsGeom& g, const float* x, const float* gout, float* dcore, void* ws, int passes,
+                     cudaStream_t st) {
+  constexpr int BN = 256;
+  size_t smem = dcore_tc_smem<BN>(g);
+  if (smem > TC_SMEM_LIMIT) return dctn_set_error(-2, "tcgen05 core-gradient kernel needs %zu bytes of shared memory", smem);
+  TcDcoreArgs a{};
+  a.g = g; a.x = x; a.gout = gout; a.part = (float*)ws; a.passes = passes;
+  int splits;
+  dcore_split(g, &a.per_split, &splits);
+  auto k = tc_dcore_kernel<BN>;
+  DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((g.A + BM - 1) / BM, (g.N + BN - 1) / BN, splits);
+  k<<<grid, NTHREADS_TC, smem, st>>>(a);
+  dctn_count_launch();
+  DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  return launch_reduce_partials<float>(a.part, dcore, (long long)g.A * g.N, splits, st);
+}
+
+int tc_forward(const EpsGeom&, const float*, const float*, float*, void*, int, cudaStream_t) {
+  return dctn_set_error(-2, "tcgen05 forward kernel not available for this shape");
+}
+int tc_backward_input(const EpsGeom&, const float*, const float*, const float*, float*, void*, int, cudaStream_t) {
+  return dctn_set_error(-2, "tcgen05 input-gradient kernel not available for this shape");
+}
