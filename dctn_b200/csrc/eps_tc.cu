@@ -11,9 +11,13 @@
 //     (common.cuh) directly in the K-major SWIZZLE_128B layout tcgen05.mma reads — nothing Q^m-sized
 //     ever comes from HBM; only x (n*Q floats per patch) and gout (O floats per patch) are read;
 //   * warp 0 issues the MMAs (one elected thread), tcgen05.commit frees the stage / publishes the accumulator;
-//   * split-K: every CTA reduces at most `per_split` patches, partial tiles go to the workspace and a second
-//     kernel sums them in a fixed order (deterministic; also bounds the length of the tensor-core fp32
-//     accumulation chain, whose rounding is not round-to-nearest).
+//   * the tensor core's fp32 accumulator ROUNDS TOWARD ZERO on every MMA (measured: 768 accumulate steps
+//     shrink the result by 1.5e-5), so the accumulation chain is kept short: the K loop is cut into segments
+//     of SEG_CHUNKS chunks that alternate between two TMEM accumulators (2 x 256 columns = all of TMEM); while
+//     the MMAs of segment i+1 run, the producer warps drain segment i with tcgen05.ld and add it into fp32
+//     REGISTERS (128 per thread, round-to-nearest) — "promotion", ~2e-6 residual bias independent of K;
+//   * split-K: one CTA per (tile, patch range), ~one wave of 148 CTAs; partial tiles go to the workspace and
+//     a second kernel sums them in a fixed order (deterministic).
 #include "common.cuh"
 #include "eps_kernels.h"
 #include "tc_common.cuh"
@@ -25,7 +29,7 @@ constexpr int BK = 32;           // K elements per stage (128 bytes per row)
 constexpr int STAGES = 2;
 constexpr int NPROD_WARPS = 8;   // producer warps (warps 1..8); warp 0 issues MMAs
 constexpr int NTHREADS_TC = 32 * (1 + NPROD_WARPS);
-constexpr int DCORE_SEG = 2048;  // max patches reduced into one TMEM accumulator
+constexpr int SEG_CHUNKS = 8;    // chunks (of BK patches) accumulated in TMEM before promotion to registers
 
 struct TcDcoreArgs {
   EpsGeom g;
@@ -75,8 +79,9 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
   uint32_t* rowinfo = (uint32_t*)(gs + O * 32);              // [BM + BN]: hi entry | lo entry << 16, 0xFFFFFFFF = padding row
   uint32_t* digits = rowinfo + BM + BN;                      // [AH + AL + BH + BL]
   uint64_t* bars = (uint64_t*)(((uintptr_t)(digits + g.AH + g.AL + g.BH + g.BL) + 7) & ~(uintptr_t)7);
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 1);
-  const uint32_t bar_full0 = tc::smem_u32(bars), bar_empty0 = bar_full0 + 8 * STAGES, bar_accum = bar_full0 + 16 * STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+  const uint32_t bar_full0 = tc::smem_u32(bars), bar_empty0 = bar_full0 + 8 * STAGES;
+  const uint32_t bar_accfull0 = bar_full0 + 16 * STAGES, bar_accempty0 = bar_accfull0 + 16;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int a0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -91,10 +96,13 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
       tc::mbar_init(bar_full0 + 8 * s, NPROD_WARPS);
       tc::mbar_init(bar_empty0 + 8 * s, 1);
     }
-    tc::mbar_init(bar_accum, 1);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(bar_accfull0 + 8 * i, 1);
+      tc::mbar_init(bar_accempty0 + 8 * i, NPROD_WARPS);
+    }
     tc::fence_barrier_init();
   }
-  if (warp == 0) tc::tmem_alloc(tc::smem_u32(tmem_slot), BN);
+  if (warp == 0) tc::tmem_alloc(tc::smem_u32(tmem_slot), 2 * BN);
   // row -> (hi entry, lo entry) and the digit tables
   for (int r = tid; r < BM + BN; r += NTHREADS_TC) {
     uint32_t info = 0xFFFFFFFFu;
@@ -118,7 +126,7 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem_acc = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // =========================== MMA issuer ===========================
@@ -126,9 +134,15 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
     for (int c = 0; c < nchunks; ++c) {
       const int s = c % STAGES;
       const uint32_t it = (uint32_t)(c / STAGES);
+      const int seg = c / SEG_CHUNKS, acc = seg & 1;
+      const bool seg_first = (c % SEG_CHUNKS) == 0;
+      const bool seg_last = ((c + 1) % SEG_CHUNKS) == 0 || c == nchunks - 1;
+      // before overwriting an accumulator, its previous use (segment seg-2) must have been drained
+      if (seg_first && seg >= 2) tc::mbar_wait(bar_accempty0 + 8 * acc, (uint32_t)(((seg >> 1) - 1) & 1));
       tc::mbar_wait(bar_full0 + 8 * s, it & 1);
       tc::tc_fence_after();
       if (lane == 0) {
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
         const uint32_t sb = tc::smem_u32(stages + s * SM::STAGE_BYTES);
         const uint64_t da_hi = tc::make_sw128_kmajor_desc(sb + SM::OFF_A_HI);
         const uint64_t da_lo = tc::make_sw128_kmajor_desc(sb + SM::OFF_A_LO);
@@ -137,23 +151,46 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
           const uint64_t adv = (uint64_t)(k * 2);  // 32 bytes >> 4
+          const uint32_t accum = (seg_first && k == 0) ? 0u : 1u;
           if (a.passes == 3) {
             // small terms first, then the dominant one
-            tc::umma_tf32(tmem_acc, da_lo + adv, db_hi + adv, idesc, (c > 0 || k > 0) ? 1u : 0u);
+            tc::umma_tf32(tmem_acc, da_lo + adv, db_hi + adv, idesc, accum);
             tc::umma_tf32(tmem_acc, da_hi + adv, db_lo + adv, idesc, 1u);
             tc::umma_tf32(tmem_acc, da_hi + adv, db_hi + adv, idesc, 1u);
           } else {
-            tc::umma_tf32(tmem_acc, da_hi + adv, db_hi + adv, idesc, (c > 0 || k > 0) ? 1u : 0u);
+            tc::umma_tf32(tmem_acc, da_hi + adv, db_hi + adv, idesc, accum);
           }
         }
-        tc::umma_commit(bar_empty0 + 8 * s);            // stage can be refilled once these MMAs have read it
-        if (c == nchunks - 1) tc::umma_commit(bar_accum);  // accumulator complete
+        tc::umma_commit(bar_empty0 + 8 * s);                       // stage can be refilled once these MMAs have read it
+        if (seg_last) tc::umma_commit(bar_accfull0 + 8 * acc);      // this segment's accumulator is complete
       }
       __syncwarp();
     }
   } else {
     // =========================== producers ===========================
     const int pw = warp - 1;  // 0..7
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may access
+    const int half = (warp - 1) >> 2;    // which half of the accumulator columns this warp promotes
+    float racc[BN / 2];                  // fp32 running sum of this thread's row, BN/2 columns
+#pragma unroll
+    for (int i = 0; i < BN / 2; ++i) racc[i] = 0.f;
+    int next_drain = 0;
+    // promote segment `seg` (complete in TMEM) into the register accumulators, then hand the buffer back
+    auto drain = [&](int seg) {
+      const int acc = seg & 1;
+      tc::mbar_wait(bar_accfull0 + 8 * acc, (uint32_t)((seg >> 1) & 1));
+      tc::tc_fence_after();
+#pragma unroll
+      for (int cb = 0; cb < BN / 2; cb += 32) {
+        float v[32];
+        tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2) + cb), v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) racc[cb + i] += v[i];
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(bar_accempty0 + 8 * acc);
+    };
     for (int c = 0; c < nchunks; ++c) {
       const int s = c % STAGES;
       const uint32_t it = (uint32_t)(c / STAGES);
@@ -205,34 +242,33 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
       tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(bar_full0 + 8 * s);
+      // Having been allowed to refill stage s means the MMAs of chunk c-STAGES are complete; one chunk into a
+      // new segment (c % SEG_CHUNKS == STAGES-1) that covers the whole previous segment: promote it now, while
+      // the tensor core works on the chunks just produced.
+      if ((c % SEG_CHUNKS) == STAGES - 1 && c >= SEG_CHUNKS) drain(next_drain++);
     }
-    // =========================== epilogue: TMEM -> partial tile ===========================
-    tc::mbar_wait(bar_accum, 0);
-    tc::tc_fence_after();
-    const int quad = warp & 3;           // TMEM lane quadrant this warp may access
-    const int half = (warp - 1) >> 2;    // which half of the columns
+    const int last_seg = (nchunks - 1) / SEG_CHUNKS;
+    while (next_drain <= last_seg) drain(next_drain++);
+    // =========================== epilogue: registers -> partial tile ===========================
     const int arow = a0 + quad * 32 + lane;
     float* prow = a.part + ((long long)blockIdx.z * g.A + arow) * (long long)g.N;
-    for (int cb = 0; cb < BN / 2; cb += 32) {
-      const int col = half * (BN / 2) + cb;
-      float v[32];
-      tc::tmem_ld32(tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)col, v);
-      if (arow < g.A) {
-        const int nb = n0 + col;
-        if (nb + 32 <= g.N && (g.N & 3) == 0) {
+    if (arow < g.A) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) *(float4*)(prow + nb + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      for (int cb = 0; cb < BN / 2; cb += 4) {
+        const int nb = n0 + half * (BN / 2) + cb;
+        if (nb + 4 <= g.N && (g.N & 3) == 0) {
+          *(float4*)(prow + nb) = make_float4(racc[cb], racc[cb + 1], racc[cb + 2], racc[cb + 3]);
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (nb + i < g.N) prow[nb + i] = v[i];
+          for (int i = 0; i < 4; ++i)
+            if (nb + i < g.N) prow[nb + i] = racc[cb + i];
         }
       }
     }
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem_acc, BN);
+  if (warp == 0) tc::tmem_dealloc(tmem_base, 2 * BN);
 }
 
 template <int BN>
@@ -240,15 +276,21 @@ size_t dcore_tc_smem(const EpsGeom& g) {
   const int BLO = g.BL * g.O;
   const int TE = g.AH + g.AL + g.BH + BLO;
   size_t b = 1024 + (size_t)STAGES * DcoreSmem<BN>::STAGE_BYTES + (size_t)(TE + g.n * g.Q + g.O) * 32 * 4 +
-             (size_t)(BM + BN) * 4 + (size_t)(g.AH + g.AL + g.BH + g.BL) * 4 + 8 + (2 * STAGES + 1) * 8 + 16;
+             (size_t)(BM + BN) * 4 + (size_t)(g.AH + g.AL + g.BH + g.BL) * 4 + 8 + (2 * STAGES + 4) * 8 + 16;
   return b;
 }
 
 constexpr size_t TC_SMEM_LIMIT = 227 * 1024;
 
-inline void dcore_split(const EpsGeom& g, long long* per_split, int* splits) {
-  long long per = DCORE_SEG;
-  if (per > g.P) per = ((g.P + BK - 1) / BK) * BK;
+inline void dcore_split(const EpsGeom& g, int BN, long long* per_split, int* splits) {
+  // about one wave: one CTA per SM (the kernel uses all of TMEM and ~220 KB of shared memory)
+  long long tiles = (long long)((g.A + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+  long long want = 148 / tiles;
+  if (want < 1) want = 1;
+  long long per = (g.P + want - 1) / want;
+  per = ((per + BK - 1) / BK) * BK;
+  const long long min_per = (long long)BK * SEG_CHUNKS * 4;  // do not split below a few segments
+  if (per < min_per) per = min_per;
   *per_split = per;
   *splits = (int)((g.P + per - 1) / per);
 }
@@ -268,7 +310,7 @@ size_t tc_workspace_bytes(const EpsGeom& g, int kind) {
   if (kind == 1) {
     long long per;
     int splits;
-    dcore_split(g, &per, &splits);
+    dcore_split(g, 256, &per, &splits);
     return (size_t)splits * g.A * g.N * sizeof(float);
   }
   return 0;
@@ -282,7 +324,7 @@ int tc_backward_core(const EpsGeom& g, const float* x, const float* gout, float*
   TcDcoreArgs a{};
   a.g = g; a.x = x; a.gout = gout; a.part = (float*)ws; a.passes = passes;
   int splits;
-  dcore_split(g, &a.per_split, &splits);
+  dcore_split(g, BN, &a.per_split, &splits);
   auto k = tc_dcore_kernel<BN>;
   DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((g.A + BM - 1) / BM, (g.N + BN - 1) / BN, splits);
