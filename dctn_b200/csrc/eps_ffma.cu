@@ -555,6 +555,36 @@ int launch_reduce_partials(const T* part, T* out, long long count, int splits, c
 template int launch_reduce_partials<float>(const float*, float*, long long, int, cudaStream_t);
 template int launch_reduce_partials<double>(const double*, double*, long long, int, cudaStream_t);
 
+// half == 0: factors [0, m) from dKR1 [np][A];  half == 1: factors [m, n) from dKR2 [np][Bn]
+template <typename T>
+int launch_loo(const EpsGeom& g, const T* x, const T* dkr, long long p0, int np, int half, T* dxp, cudaStream_t st) {
+  const int j0 = half ? g.m : 0, cnth = half ? g.b_nh : g.a_nh, cntl = half ? g.b_nl : g.a_nl;
+  const int EH = half ? g.BH : g.AH, EL = half ? g.BL : g.AL;
+  const int nf = cnth + cntl;
+  size_t smem = ((size_t)PT * 2 * (EH + EL) + (size_t)PT * ((nf * g.Q) | 1)) * sizeof(T) + 16;
+  if (smem > SMEM_LIMIT) return dctn_set_error(-2, "leave-one-out kernel needs %zu bytes of shared memory", smem);
+  DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(loo_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  loo_kernel<T><<<(np + PT - 1) / PT, NTHREADS, smem, st>>>(g, x, dkr, p0, np, j0, cnth, EH, cntl, EL, dxp);
+  dctn_count_launch();
+  DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  return 0;
+}
+template int launch_loo<float>(const EpsGeom&, const float*, const float*, long long, int, int, float*, cudaStream_t);
+template int launch_loo<double>(const EpsGeom&, const double*, const double*, long long, int, int, double*, cudaStream_t);
+
+template <typename T>
+int launch_gather_dx(const EpsGeom& g, const T* dxp, T* dx, cudaStream_t st) {
+  long long total = (long long)g.C * g.B * g.H * g.W * g.Q;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gather_dx_kernel<T><<<blocks, 256, 0, st>>>(g, dxp, dx);
+  dctn_count_launch();
+  DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  return 0;
+}
+template int launch_gather_dx<float>(const EpsGeom&, const float*, float*, cudaStream_t);
+template int launch_gather_dx<double>(const EpsGeom&, const double*, double*, cudaStream_t);
+
 template <typename T>
 size_t ffma_workspace_bytes(const EpsGeom& g, int kind) {
   if (kind == 0) {

@@ -13,6 +13,11 @@ template <typename T> int ffma_backward_input(const EpsGeom& g, const T* x, cons
 // out[i] = sum_z part[z*count + i], fixed order (deterministic split-K reduction)
 template <typename T> int launch_reduce_partials(const T* part, T* out, long long count, int splits, cudaStream_t st);
 
+// per-patch leave-one-out contraction dKR -> dxp[p][j][q] (half 0: first m factors, half 1: the rest) and the
+// deterministic gather dxp -> dx
+template <typename T> int launch_loo(const EpsGeom& g, const T* x, const T* dkr, long long p0, int np, int half, T* dxp, cudaStream_t st);
+template <typename T> int launch_gather_dx(const EpsGeom& g, const T* dxp, T* dx, cudaStream_t st);
+
 // ---- streaming thread-per-patch family for tiny cores (eps_direct.cu): HBM-bound shapes
 bool direct_supported(const EpsGeom& g, int dtype);
 template <typename T> int direct_forward(const EpsGeom& g, const T* x, const T* core, T* out, cudaStream_t st);
@@ -21,6 +26,9 @@ template <typename T> int direct_forward(const EpsGeom& g, const T* x, const T* 
 bool tc_supported(const EpsGeom& g, int kind);
 size_t tc_workspace_bytes(const EpsGeom& g, int kind);
 int tc_forward(const EpsGeom& g, const float* x, const float* core, float* out, void* ws, int passes, cudaStream_t st);
+// eps_tc_gemm.cu: forward / input-gradient GEMMs on tcgen05 (A generated on chip, core streamed by bulk copies)
+bool tcg_supported(const EpsGeom& g, int kind);
+size_t tcg_workspace_bytes(const EpsGeom& g, int kind);
 int tc_backward_core(const EpsGeom& g, const float* x, const float* gout, float* dcore, void* ws, int passes, cudaStream_t st);
 int tc_backward_input(const EpsGeom& g, const float* x, const float* core, const float* gout, float* dx, void* ws, int passes, cudaStream_t st);
 

@@ -71,14 +71,15 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
   const int NX = g.n * Q;
 
   // ---- carve shared memory (operand stages first, 1024-byte aligned for SWIZZLE_128B)
-  unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+  unsigned char* base = smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u);  // stays a shared-space pointer
   unsigned char* stages = base;
-  float* tab = (float*)(base + STAGES * SM::STAGE_BYTES);   // [TE][32]
-  float* xs = tab + TE * 32;                                 // [NX][32]
-  float* gs = xs + NX * 32;                                  // [O][32]
-  uint32_t* rowinfo = (uint32_t*)(gs + O * 32);              // [BM + BN]: hi entry | lo entry << 16, 0xFFFFFFFF = padding row
-  uint32_t* digits = rowinfo + BM + BN;                      // [AH + AL + BH + BL]
-  uint64_t* bars = (uint64_t*)(((uintptr_t)(digits + g.AH + g.AL + g.BH + g.BL) + 7) & ~(uintptr_t)7);
+  float* tab = (float*)(base + STAGES * SM::STAGE_BYTES);   // [TE + 1][32]; row TE is all zeros (padding rows)
+  float* xs = tab + (TE + 1) * 32;                           // [NX + 1][32]; row NX is all ones (unused factor slots)
+  float* gs = xs + (NX + 1) * 32;                            // [O + 1][32];  row O is all ones (entries without gout)
+  uint32_t* rowinfo = (uint32_t*)(gs + (O + 1) * 32);        // [BM + BN]: hi entry | lo entry << 16 (TE | TE<<16 = padding row)
+  uint2* emeta = (uint2*)(rowinfo + BM + BN);                // [TE]: {4 xs rows packed, gs row} (8-byte aligned: all sizes above are multiples of 8)
+  int* xoff = (int*)(emeta + TE);                            // [NX]: element offset of (factor j, component q) from the patch origin
+  uint64_t* bars = (uint64_t*)(xoff + ((NX + 1) & ~1));
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
   const uint32_t bar_full0 = tc::smem_u32(bars), bar_empty0 = bar_full0 + 8 * STAGES;
   const uint32_t bar_accfull0 = bar_full0 + 16 * STAGES, bar_accempty0 = bar_accfull0 + 16;
@@ -103,9 +104,9 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
     tc::fence_barrier_init();
   }
   if (warp == 0) tc::tmem_alloc(tc::smem_u32(tmem_slot), 2 * BN);
-  // row -> (hi entry, lo entry) and the digit tables
+  // row -> (hi entry, lo entry); padding rows multiply the all-zero table row
   for (int r = tid; r < BM + BN; r += NTHREADS_TC) {
-    uint32_t info = 0xFFFFFFFFu;
+    uint32_t info = (uint32_t)TE | ((uint32_t)TE << 16);
     if (r < BM) {
       int ai = a0 + r;
       if (ai < g.A) info = (uint32_t)(ai / g.AL) | ((uint32_t)(g.AH + ai % g.AL) << 16);
@@ -115,13 +116,29 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
     }
     rowinfo[r] = info;
   }
-  for (int e = tid; e < g.AH + g.AL + g.BH + g.BL; e += NTHREADS_TC) {
-    uint32_t d;
-    if (e < g.AH) d = pack_digits(e, g.a_nh, Q);
-    else if (e < g.AH + g.AL) d = pack_digits(e - g.AH, g.a_nl, Q);
-    else if (e < g.AH + g.AL + g.BH) d = pack_digits(e - g.AH - g.AL, g.b_nh, Q);
-    else d = pack_digits(e - g.AH - g.AL - g.BH, g.b_nl, Q);
-    digits[e] = d;
+  // table entry -> the (up to 4) xs rows whose product it is, plus its gout row; unused slots point at ones rows
+  for (int t = tid; t < TE; t += NTHREADS_TC) {
+    int e, j0, cnt, grow = O;
+    if (t < g.AH) { e = t; j0 = 0; cnt = g.a_nh; }
+    else if (t < g.AH + g.AL) { e = t - g.AH; j0 = g.a_nh; cnt = g.a_nl; }
+    else if (t < g.AH + g.AL + g.BH) { e = t - g.AH - g.AL; j0 = g.m; cnt = g.b_nh; }
+    else {
+      int idx = t - (g.AH + g.AL + g.BH);
+      e = idx / O; grow = idx - e * O; j0 = g.m + g.b_nh; cnt = g.b_nl;
+    }
+    const uint32_t dg = pack_digits(e, cnt, Q);
+    uint32_t rows = 0;
+    for (int u = 0; u < 4; ++u) {
+      uint32_t row = (u < cnt) ? (uint32_t)((j0 + u) * Q) + ((dg >> (8 * u)) & 0xFF) : (uint32_t)NX;
+      rows |= row << (8 * u);
+    }
+    emeta[t] = make_uint2(rows, (uint32_t)grow);
+  }
+  for (int jq = tid; jq < NX; jq += NTHREADS_TC) xoff[jq] = (int)g.foff[jq / Q] + jq % Q;
+  if (tid < 32) {
+    tab[TE * 32 + tid] = 0.f;
+    xs[NX * 32 + tid] = 1.f;
+    gs[O * 32 + tid] = 1.f;
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -169,12 +186,17 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
   } else {
     // =========================== producers ===========================
     const int pw = warp - 1;  // 0..7
+    const int kq = lane & 7;             // which 4 consecutive patches (16-byte chunk of a K-major row)
+    const int rsub = lane >> 3;          // which of the 4 rows / entries a warp handles per iteration
+    const int r0 = pw * 4 + rsub;        // first row / table entry owned by this thread (then every 32nd)
+    const uint32_t off0 = (uint32_t)(r0 * 128 + ((kq ^ (r0 & 7)) << 4));  // its 16-byte chunk in a swizzled tile
     const int quad = warp & 3;           // TMEM lane quadrant this warp may access
     const int half = (warp - 1) >> 2;    // which half of the accumulator columns this warp promotes
     float racc[BN / 2];                  // fp32 running sum of this thread's row, BN/2 columns
 #pragma unroll
     for (int i = 0; i < BN / 2; ++i) racc[i] = 0.f;
     int next_drain = 0;
+    const unsigned hw = (unsigned)(g.Ho * g.Wo);
     // promote segment `seg` (complete in TMEM) into the register accumulators, then hand the buffer back
     auto drain = [&](int seg) {
       const int acc = seg & 1;
@@ -194,50 +216,77 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
     for (int c = 0; c < nchunks; ++c) {
       const int s = c % STAGES;
       const uint32_t it = (uint32_t)(c / STAGES);
-      // (1) stage x and gout of this chunk's 32 patches: lane = patch
+      // (1) stage x and gout of this chunk's 32 patches: lane = patch (32-bit index math, offsets precomputed)
       {
-        const long long p = pbeg + (long long)c * BK + lane;
-        const bool ok = p < pend;
-        const long long org = ok ? patch_origin(g, p) : 0;
-        for (int jq = pw; jq < NX; jq += NPROD_WARPS) {
-          int j = jq / Q, q = jq - j * Q;
-          xs[jq * 32 + lane] = ok ? __ldg(&a.x[org + g.foff[j] + q]) : 0.f;
-        }
-        for (int o = pw; o < O; o += NPROD_WARPS) gs[o * 32 + lane] = ok ? __ldg(&a.gout[p * O + o]) : 0.f;
+        const unsigned p = (unsigned)pbeg + (unsigned)(c * BK + lane);
+        const bool ok = p < (unsigned)pend;
+        const unsigned pc = ok ? p : 0u;
+        const unsigned b = pc / hw, r = pc - b * hw, h = r / (unsigned)g.Wo, w = r - h * (unsigned)g.Wo;
+        const float* xp = a.x + (size_t)(((b * (unsigned)g.H + h) * (unsigned)g.W + w) * (unsigned)Q);
+        const float* gp = a.gout + (size_t)pc * O;
+#pragma unroll 4
+        for (int jq = pw; jq < NX; jq += NPROD_WARPS) xs[jq * 32 + lane] = ok ? __ldg(xp + xoff[jq]) : 0.f;
+        for (int o = pw; o < O; o += NPROD_WARPS) gs[o * 32 + lane] = ok ? __ldg(gp + o) : 0.f;
       }
       producer_bar_sync();
-      // (2) two-level Khatri-Rao tables, one warp per entry, lane = patch
-      for (int t = pw; t < TE; t += NPROD_WARPS) {
-        int e, j0, cnt;
-        float v = 1.f;
-        if (t < g.AH) { e = t; j0 = 0; cnt = g.a_nh; }
-        else if (t < g.AH + g.AL) { e = t; j0 = g.a_nh; cnt = g.a_nl; }
-        else if (t < g.AH + g.AL + g.BH) { e = t; j0 = g.m; cnt = g.b_nh; }
-        else {
-          int idx = t - (g.AH + g.AL + g.BH);
-          int el = idx / O;
-          v = gs[(idx - el * O) * 32 + lane];
-          e = g.AH + g.AL + g.BH + el; j0 = g.m + g.b_nh; cnt = g.b_nl;
+      // (2) two-level Khatri-Rao tables.  Thread = (entry, 4 consecutive patches): 128-bit shared accesses,
+      //     branch-free (unused factor slots read the all-ones rows); two entries per iteration for ILP.
+      {
+        const float4* xs4 = (const float4*)xs;
+        const float4* gs4 = (const float4*)gs;
+        float4* tab4 = (float4*)tab;
+        auto entry = [&](int t) -> float4 {
+          const uint2 em = emeta[t];
+          float4 v = gs4[em.y * 8 + kq];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 f = xs4[((em.x >> (8 * u)) & 0xFF) * 8 + kq];
+            v.x *= f.x; v.y *= f.y; v.z *= f.z; v.w *= f.w;
+          }
+          return v;
+        };
+        int t = r0;
+        for (; t + 32 < TE; t += 64) {
+          const float4 v0 = entry(t), v1 = entry(t + 32);
+          tab4[t * 8 + kq] = v0;
+          tab4[(t + 32) * 8 + kq] = v1;
         }
-        const uint32_t dg = digits[e];
-        for (int u = 0; u < cnt; ++u) v *= xs[((j0 + u) * Q + ((dg >> (8 * u)) & 0xFF)) * 32 + lane];
-        tab[t * 32 + lane] = v;
+        if (t < TE) tab4[t * 8 + kq] = entry(t);
       }
       producer_bar_sync();
-      // (3) wait until the MMAs that read this stage (two chunks ago) are done, then generate the operand tiles
+      // (3) wait until the MMAs that read this stage (two chunks ago) are done, then generate the operand tiles:
+      //     thread = (row, 4 consecutive patches) -> one 16-byte chunk of the swizzled row, hi and lo parts
       tc::mbar_wait(bar_empty0 + 8 * s, (it & 1) ^ 1);
-      unsigned char* st = stages + s * SM::STAGE_BYTES;
-      for (int r = pw; r < BM + BN; r += NPROD_WARPS) {
-        const uint32_t info = rowinfo[r];
-        float v = 0.f;
-        if (info != 0xFFFFFFFFu) v = tab[(info & 0xFFFF) * 32 + lane] * tab[(info >> 16) * 32 + lane];
-        float hi, lo;
-        tc::split_tf32(v, hi, lo);
-        const bool isA = r < BM;
-        const int rr = isA ? r : r - BM;
-        const uint32_t off = tc::sw128_offset(rr, lane);
-        *(float*)(st + (isA ? SM::OFF_A_HI : SM::OFF_B_HI) + off) = hi;
-        if (a.passes == 3) *(float*)(st + (isA ? SM::OFF_A_LO : SM::OFF_B_LO) + off) = lo;
+      {
+        // Each thread owns the same rows r0 + 32*i in every chunk: row r0 + 32*i keeps r & 7, so the swizzled byte
+        // offset is (off0 + i*4096) and everything below except the table values is loop-invariant.
+        unsigned char* st = stages + s * SM::STAGE_BYTES + off0;
+        const float4* tab4 = (const float4*)tab + kq;
+        const uint32_t* ri = rowinfo + r0;
+        constexpr int NROW = (BM + BN) / 32;
+        static_assert(BM % 32 == 0 && BN % 32 == 0 && NROW % 2 == 0, "row ownership pattern");
+#pragma unroll
+        for (int i = 0; i < NROW; i += 2) {
+          float4 hi[2], lo[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const uint32_t info = ri[(i + u) * 32];
+            const float4 th = tab4[(info & 0xFFFF) * 8], tl = tab4[(info >> 16) * 8];
+            tc::split_tf32(th.x * tl.x, hi[u].x, lo[u].x);
+            tc::split_tf32(th.y * tl.y, hi[u].y, lo[u].y);
+            tc::split_tf32(th.z * tl.z, hi[u].z, lo[u].z);
+            tc::split_tf32(th.w * tl.w, hi[u].w, lo[u].w);
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            constexpr uint32_t A_ROWS = BM / 32;
+            const int ii = i + u;
+            const uint32_t tile_hi = ii < (int)A_ROWS ? SM::OFF_A_HI + ii * 4096u : SM::OFF_B_HI + (ii - A_ROWS) * 4096u;
+            const uint32_t tile_lo = ii < (int)A_ROWS ? SM::OFF_A_LO + ii * 4096u : SM::OFF_B_LO + (ii - A_ROWS) * 4096u;
+            *(float4*)(st + tile_hi) = hi[u];
+            if (a.passes == 3) *(float4*)(st + tile_lo) = lo[u];
+          }
+        }
       }
       tc::fence_proxy_async();
       __syncwarp();
@@ -275,8 +324,8 @@ template <int BN>
 size_t dcore_tc_smem(const EpsGeom& g) {
   const int BLO = g.BL * g.O;
   const int TE = g.AH + g.AL + g.BH + BLO;
-  size_t b = 1024 + (size_t)STAGES * DcoreSmem<BN>::STAGE_BYTES + (size_t)(TE + g.n * g.Q + g.O) * 32 * 4 +
-             (size_t)(BM + BN) * 4 + (size_t)(g.AH + g.AL + g.BH + g.BL) * 4 + 8 + (2 * STAGES + 4) * 8 + 16;
+  size_t b = 1024 + (size_t)STAGES * DcoreSmem<BN>::STAGE_BYTES + (size_t)(TE + g.n * g.Q + g.O + 3) * 32 * 4 +
+             (size_t)(BM + BN) * 4 + 8 + (size_t)TE * 8 + (size_t)(g.n * g.Q + 2) * 4 + (2 * STAGES + 4) * 8 + 16;
   return b;
 }
 
@@ -298,9 +347,10 @@ inline void dcore_split(const EpsGeom& g, int BN, long long* per_split, int* spl
 }  // namespace
 
 bool tc_supported(const EpsGeom& g, int kind) {
-  if (kind != 1) return false;  // forward / input-gradient tcgen05 kernels: see tc_forward / tc_backward_input
+  if (kind != 1) return tcg_supported(g, kind);  // forward / input-gradient GEMMs live in eps_tc_gemm.cu
   if (g.a_nh > 4 || g.a_nl > 4 || g.b_nh > 4 || g.b_nl > 4) return false;  // packed digit bytes
-  if (g.Q > 255 || g.AH + g.AL + g.BH + g.BL * g.O >= 65535) return false;
+  if (g.n * g.Q > 254 || g.O > 254 || g.AH + g.AL + g.BH + g.BL * g.O >= 65535) return false;
+  if (g.P >= (1ll << 31) / (g.Q > g.O ? g.Q : g.O)) return false;  // 32-bit patch index math
   if (g.A < 64 || g.N < 128) return false;   // tiles would be mostly padding: the CUDA-core family is the better fit
   if (g.P < 4096) return false;              // tiny reductions are launch-bound either way
   return dcore_tc_smem<256>(g) <= TC_SMEM_LIMIT;
@@ -313,7 +363,7 @@ size_t tc_workspace_bytes(const EpsGeom& g, int kind) {
     dcore_split(g, 256, &per, &splits);
     return (size_t)splits * g.A * g.N * sizeof(float);
   }
-  return 0;
+  return tcg_workspace_bytes(g, kind);
 }
 
 int tc_backward_core(const EpsGeom& g, const float* x, const float* gout, float* dcore, void* ws, int passes,
@@ -334,9 +384,3 @@ int tc_backward_core(const EpsGeom& g, const float* x, const float* gout, float*
   return launch_reduce_partials<float>(a.part, dcore, (long long)g.A * g.N, splits, st);
 }
 
-int tc_forward(const EpsGeom&, const float*, const float*, float*, void*, int, cudaStream_t) {
-  return dctn_set_error(-2, "tcgen05 forward kernel not available for this shape");
-}
-int tc_backward_input(const EpsGeom&, const float*, const float*, const float*, float*, void*, int, cudaStream_t) {
-  return dctn_set_error(-2, "tcgen05 input-gradient kernel not available for this shape");
-}

@@ -325,7 +325,7 @@ TC_SHAPES = [
     (8, 28, 28, 2, 4, 4),
     (8, 25, 25, 4, 3, 6),
     (9, 27, 26, 3, 3, 5),   # A = 243, N = 405: ragged row and column tiles
-    (40, 14, 13, 2, 3, 24),
+    (30, 16, 15, 2, 4, 3),   # N = 768, odd Q_out
 ]
 
 
@@ -357,3 +357,36 @@ def test_tc_backward_core_full_size_vs_fp64(B, H, W, Q, K, Oq):
     ffma = _raw_call(_lib.WS_BACKWARD_CORE, "ffma", core.to(DEV), x.to(DEV), gout.to(DEV))
     print(f"ffma dcore full-size rel err {rel_err(ffma, want):.3e}")
     assert rel_err(ffma, want) <= 1e-5
+
+
+@pytest.mark.parametrize("variant,tol", [("tc3", 1e-5), ("tc1", 5e-3)])
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_tc_forward_and_input_grad_vs_oracle(shape, variant, tol):
+    """tcgen05 forward (fused KR2 epilogue) and input-gradient (two GEMMs + leave-one-out + gather) vs the oracle."""
+    from dctn_b200 import _lib
+
+    B, H, W, Q, K, Oq = shape
+    x, core, gout = _rand_layer(B, H, W, Q, K, Oq, seed=23)
+    want = O.eps_4step(core.double(), x.double())
+    _, want_dx = O.eps_grads(core.double(), x.double(), gout.double())
+    got = _raw_call(_lib.WS_FORWARD, variant, core.to(DEV), x.to(DEV), gout.to(DEV))
+    assert rel_err(got, want) <= tol
+    got_dx = _raw_call(_lib.WS_BACKWARD_INPUT, variant, core.to(DEV), x.to(DEV), gout.to(DEV))
+    assert rel_err(got_dx, want_dx) <= tol
+
+
+@pytest.mark.parametrize("B,H,W,Q,K,Oq", [(512, 28, 28, 2, 4, 4), (512, 25, 25, 4, 3, 6)])
+def test_tc_forward_and_input_grad_full_size_vs_fp64(B, H, W, Q, K, Oq):
+    """Full config-2 layer sizes: tensor-core forward / input-gradient against our own float64 CUDA-core kernels."""
+    from dctn_b200 import _lib
+
+    x, core, gout = _rand_layer(B, H, W, Q, K, Oq, seed=24)
+    x64, c64, g64 = x.double().to(DEV), core.double().to(DEV), gout.double().to(DEV)
+    want = _raw_call(_lib.WS_FORWARD, "ffma", c64, x64, g64)
+    got = _raw_call(_lib.WS_FORWARD, "tc3", core.to(DEV), x.to(DEV), gout.to(DEV))
+    print(f"tc3 forward full-size rel err {rel_err(got, want):.3e}")
+    assert rel_err(got, want) <= 1e-5
+    want_dx = _raw_call(_lib.WS_BACKWARD_INPUT, "ffma", c64, x64, g64)
+    got_dx = _raw_call(_lib.WS_BACKWARD_INPUT, "tc3", core.to(DEV), x.to(DEV), gout.to(DEV))
+    print(f"tc3 input-grad full-size rel err {rel_err(got_dx, want_dx):.3e}")
+    assert rel_err(got_dx, want_dx) <= 1e-5
