@@ -3,8 +3,10 @@
 //   C[p][c] = sum_k Gen[p][k] * Bop[k][c]            p: 128 patches per CTA (TMEM lanes), c: BN columns per tile
 //
 //   * Gen (Khatri-Rao half, optionally times gout) is GENERATED per stage by 4 producer warps, one patch row per
-//     thread, from two-level tables built once per CTA, straight into the K-major SWIZZLE_128B layout, already
-//     split into TF32 hi / lo parts;
+//     thread (= one TMEM lane), from two-level tables built once per CTA, split into TF32 hi / lo parts and written
+//     with tcgen05.st straight into TENSOR MEMORY: the MMAs read A from TMEM (TS form), so the generated operand
+//     never touches shared memory — shared-memory bandwidth was the measured bottleneck of the SS form
+//     (profiles/r01_gemm_fwd_ss_ncu.txt: smem pipe 91% busy, tensor pipe 51%);
 //   * Bop (the core) is pre-packed once per call by pack_core_kernel into per-(tile, k-chunk) images that are
 //     already split (hi / lo), K-major and swizzled, so that one elected thread streams each stage with two
 //     cp.async.bulk copies (TMA engine, mbarrier complete_tx) — no tensor map needed;
@@ -16,15 +18,27 @@
 //       MODE_FWD   out[p][o]  = sum_b C[p][(o,b)] * KR2[p][b]          (core packed as [a][(o,b)])      dctn/eps.py:19-40
 //       MODE_DKR2  dKR2[p][b] = sum_o C[p][(b,o)] * gout[p][o]         (C = KR1 @ core, never stored)
 //       MODE_STORE dKR1[p][a] = C[p][a]                                (Gen = KR2 x gout, Bop = core^T)
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "eps_kernels.h"
 #include "tc_common.cuh"
+
+// cycle probes for tuning (make NVFLAGS+=-DDCTN_TCG_TIMING, then run with DCTN_TCG_DEBUG=1); compiled out by default
+#ifdef DCTN_TCG_TIMING
+#define TCG_CLK() clock64()
+#else
+#define TCG_CLK() 0ll
+#endif
 
 namespace {
 
 constexpr int GBM = 128;
 constexpr int GBK = 32;
-constexpr int GSTAGES = 2;
+constexpr int ASTAGES = 2;      // A-operand stages in TMEM (2 x (hi + lo) x 32 columns = 128 columns)
+constexpr int MAX_BSTAGES = 4;  // B-operand stages in shared memory (as many as fit)
+constexpr int MAX_BN = 192;     // accumulators: main + small = 2*BN columns, + 128 for A  <= 512 TMEM columns
 constexpr int G_THREADS = 384;  // warp 0: bulk copies, warp 1: MMA, warp 2: TMEM alloc, warps 4-7: producers, warps 8-11: epilogue
 enum { MODE_STORE = 0, MODE_FWD = 1, MODE_DKR2 = 2 };
 constexpr size_t TCG_SMEM_LIMIT = 227 * 1024;
@@ -38,9 +52,12 @@ struct TcGemmArgs {
   int jh0, cnth, KH, cntl, KLb, KL, Kdim, withG;  // generated operand (see GenGemmArgs in eps_ffma.cu)
   int Ncols, ntiles, nk;
   const float* packed;  // [ntiles][nk][2][BN*32]
+  int BN;               // column-tile width: multiple of 16, <= MAX_BN
+  int bstages;          // shared-memory stages for B
   int passes;
   float* out;           // MODE_STORE: [np][ldc]; MODE_FWD: out[P][O] (absolute patches); MODE_DKR2: [np][Bn]
   long long ldc;
+  long long* dbg;       // optional per-CTA cycle counters (DCTN_TCG_DEBUG): 8 per CTA
 };
 
 // ------------------------------------------------------------------------------------------------ core packing
@@ -89,45 +106,51 @@ __global__ void pack_core_kernel(const float* __restrict__ core, float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ the GEMM
-template <int BN>
-struct GSmem {
-  static constexpr uint32_t A_BYTES = GBM * GBK * 4;
-  static constexpr uint32_t B_BYTES = BN * GBK * 4;
-  static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr uint32_t OFF_A_HI = 0, OFF_A_LO = A_BYTES, OFF_B_HI = 2 * A_BYTES, OFF_B_LO = 2 * A_BYTES + B_BYTES;
-};
-
-template <int BN, int MODE>
+template <int MODE>
 __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcGemmArgs a) {
-  using SM = GSmem<BN>;
   extern __shared__ unsigned char smem_dyn[];
   const EpsGeom& g = a.g;
-  const int Q = g.Q, O = g.O;
+  const int Q = g.Q, O = g.O, BN = a.BN, NB = a.bstages;
+  const uint32_t B_BYTES = (uint32_t)BN * GBK * 4;     // one part (hi or lo) of a B stage
+  const uint32_t STAGE_BYTES = 2 * B_BYTES;            // multiple of 1024 (BN % 16 == 0)
   unsigned char* base = smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* stages = base;
-  float* tabKH = (float*)(base + GSTAGES * SM::STAGE_BYTES);  // [KH][128]
-  float* tabKL = tabKH + a.KH * 128;                          // [KL][128]
-  float* tabE = tabKL + a.KL * 128;                           // MODE_FWD: [BH + BL][128]; MODE_DKR2: gout [O][128]
+  float* tabKH = (float*)(base + NB * STAGE_BYTES);    // [KH][128]
+  float* tabKL = tabKH + (a.KH + 1) * 128;             // [KL][128]   (row KH of tabKH is all zeros: padding k)
+  float* tabE = tabKL + a.KL * 128;                    // MODE_FWD: [BH + BL][128]; MODE_DKR2: gout [O][128]
   const int nE = (MODE == MODE_FWD) ? (g.BH + g.BL) : (MODE == MODE_DKR2 ? O : 0);
-  float* outs = tabE + nE * 128;                              // MODE_FWD: [O][128]
-  uint64_t* bars = (uint64_t*)(outs + ((MODE == MODE_FWD) ? O * 128 : 0));
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * GSTAGES + 2);
-  const uint32_t bar_full0 = tc::smem_u32(bars), bar_empty0 = bar_full0 + 8 * GSTAGES;
-  const uint32_t bar_accfull = bar_full0 + 16 * GSTAGES, bar_accempty = bar_accfull + 8;
-  // setup-only scratch aliased onto the (not yet used) operand stages: x [n*Q][128] and gout [O][128]
+  float* outs = tabE + nE * 128;                       // MODE_FWD: [O][128]
+  // index tables that make the inner loops branch-free (every load address is known up front -> full ILP):
+  //   kidx[k]  = kh | kl << 16 for the generated operand (k >= Kdim -> the all-zero row KH of tabKH)
+  //   eidx[..] = MODE_FWD: bh | bl << 16 for b in [0, 2*Bn) (doubled so 32 consecutive b never wrap the table);
+  //              MODE_DKR2: o | last << 8 for the BN columns of a tile
+  uint32_t* kidx = (uint32_t*)(outs + ((MODE == MODE_FWD) ? O * 128 : 0));
+  const int nkidx = a.nk * GBK;
+  uint32_t* eidx = kidx + nkidx;
+  const int neidx = (MODE == MODE_FWD) ? 2 * g.Bn : (MODE == MODE_DKR2 ? ((BN + 31) & ~31) : 0);
+  uint64_t* bars = (uint64_t*)(eidx + ((neidx + 1) & ~1));
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * MAX_BSTAGES + 2 * ASTAGES + 2);
+  const uint32_t bar_fullB0 = tc::smem_u32(bars), bar_emptyB0 = bar_fullB0 + 8 * MAX_BSTAGES;
+  const uint32_t bar_fullA0 = bar_emptyB0 + 8 * MAX_BSTAGES, bar_emptyA0 = bar_fullA0 + 8 * ASTAGES;
+  const uint32_t bar_accfull = bar_emptyA0 + 8 * ASTAGES, bar_accempty = bar_accfull + 8;
+  // setup-only scratch aliased onto the (not yet used) B stages: x [n*Q][128] and gout [O][128]
   float* xs = (float*)stages;
   float* gsx = xs + g.n * Q * 128;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int pl0 = blockIdx.x * GBM;                 // first patch of this CTA, relative to the launch
   const long long pt0 = a.p0 + pl0;                 // absolute
-  constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+  constexpr uint32_t TMEM_COLS = 512;
 
   // ---------------- setup: barriers, TMEM, tables
   if (tid == 0) {
-    for (int s = 0; s < GSTAGES; ++s) {
-      tc::mbar_init(bar_full0 + 8 * s, 4 + 1);   // 4 producer warps + the expect_tx arrive of the copy warp
-      tc::mbar_init(bar_empty0 + 8 * s, 1);      // tcgen05.commit
+    for (int s = 0; s < MAX_BSTAGES; ++s) {
+      tc::mbar_init(bar_fullB0 + 8 * s, 1);      // the expect_tx arrive of the copy warp (+ transaction bytes)
+      tc::mbar_init(bar_emptyB0 + 8 * s, 1);     // tcgen05.commit
+    }
+    for (int s = 0; s < ASTAGES; ++s) {
+      tc::mbar_init(bar_fullA0 + 8 * s, 4);      // 4 producer warps
+      tc::mbar_init(bar_emptyA0 + 8 * s, 1);     // tcgen05.commit
     }
     tc::mbar_init(bar_accfull, 1);
     tc::mbar_init(bar_accempty, 4);              // 4 epilogue warps
@@ -182,104 +205,134 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
     }
     if (MODE == MODE_DKR2)
       for (int idx = tid; idx < O * 128; idx += G_THREADS) tabE[idx] = gsx[idx];
+    if (tid < 128) tabKH[a.KH * 128 + tid] = 0.f;
+    for (int k = tid; k < nkidx; k += G_THREADS)
+      kidx[k] = (k < a.Kdim) ? ((uint32_t)(k / a.KL) | ((uint32_t)(k % a.KL) << 16)) : (uint32_t)a.KH;
+    if (MODE == MODE_FWD)
+      for (int b2 = tid; b2 < 2 * g.Bn; b2 += G_THREADS) {
+        const int b = b2 % g.Bn;
+        eidx[b2] = (uint32_t)(b / g.BL) | ((uint32_t)(b % g.BL) << 16);
+      }
+    if (MODE == MODE_DKR2)
+      for (int c = tid; c < neidx; c += G_THREADS) eidx[c] = (uint32_t)(c % O) | ((c % O == O - 1) ? 0x100u : 0u);
   }
   tc::tc_fence_before();
   __syncthreads();  // tables complete, xs/gsx scratch (aliasing the stages) dead from here on
   tc::tc_fence_after();
   const uint32_t tmem_main = *tmem_slot;
-  const uint32_t tmem_small = tmem_main + BN;
+  const uint32_t tmem_small = tmem_main + (uint32_t)BN;
+  const uint32_t tmem_a0 = tmem_main + 2u * (uint32_t)BN;   // stage s: hi at +64*s, lo at +64*s + 32
   const int total_it = a.ntiles * a.nk;
 
   if (warp == 0) {
     // =========================== bulk-copy issuer (B operand) ===========================
     if (lane == 0) {
-      const uint32_t bytes = SM::B_BYTES * (a.passes == 3 ? 2u : 1u);
+      const uint32_t bytes = B_BYTES * (a.passes == 3 ? 2u : 1u);
+      int s = 0;
+      uint32_t ph = 1;   // parity to wait for on the empty barrier: fresh barriers pass a wait on parity 1
+      const float* src = a.packed;
       for (int i = 0; i < total_it; ++i) {
-        const int s = i % GSTAGES;
-        const uint32_t it = (uint32_t)(i / GSTAGES);
-        tc::mbar_wait(bar_empty0 + 8 * s, (it & 1) ^ 1);
-        const uint32_t sb = tc::smem_u32(stages + s * SM::STAGE_BYTES);
-        const float* src = a.packed + (long long)i * 2 * BN * 32;
-        tc::mbar_arrive_expect_tx(bar_full0 + 8 * s, bytes);
-        tc::bulk_g2s(sb + SM::OFF_B_HI, src, SM::B_BYTES, bar_full0 + 8 * s);
-        if (a.passes == 3) tc::bulk_g2s(sb + SM::OFF_B_LO, src + BN * 32, SM::B_BYTES, bar_full0 + 8 * s);
+        tc::mbar_wait(bar_emptyB0 + 8 * s, ph);
+        const uint32_t sb = tc::smem_u32(stages + s * STAGE_BYTES);
+        tc::mbar_arrive_expect_tx(bar_fullB0 + 8 * s, bytes);
+        tc::bulk_g2s(sb, src, B_BYTES, bar_fullB0 + 8 * s);
+        if (a.passes == 3) tc::bulk_g2s(sb + B_BYTES, src + BN * 32, B_BYTES, bar_fullB0 + 8 * s);
+        src += 2 * BN * 32;
+        if (++s == NB) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     const uint32_t idesc = tc::make_idesc_tf32(GBM, BN);
-    int i = 0;
+    long long dbg_waitA = 0, dbg_waitB = 0, dbg_waitAcc = 0, dbg_start = TCG_CLK();
+    int sa = 0, sb_ = 0;
+    uint32_t pha = 0, phb = 0;     // parities of the full barriers
+    const uint64_t db_base = tc::make_sw128_kmajor_desc(tc::smem_u32(stages));
+    const uint32_t stage_adv = STAGE_BYTES >> 4, part_adv = B_BYTES >> 4;  // descriptor address units (16 bytes)
     for (int t = 0; t < a.ntiles; ++t) {
+      long long ta = TCG_CLK();
       if (t > 0) tc::mbar_wait(bar_accempty, (uint32_t)((t - 1) & 1));  // epilogue has drained the previous tile
+      dbg_waitAcc += TCG_CLK() - ta;
       tc::tc_fence_after();
-      for (int kc = 0; kc < a.nk; ++kc, ++i) {
-        const int s = i % GSTAGES;
-        const uint32_t it = (uint32_t)(i / GSTAGES);
-        tc::mbar_wait(bar_full0 + 8 * s, it & 1);
+      for (int kc = 0; kc < a.nk; ++kc) {
+        long long t0 = TCG_CLK();
+        tc::mbar_wait(bar_fullB0 + 8 * sb_, phb);
+        long long t1 = TCG_CLK();
+        tc::mbar_wait(bar_fullA0 + 8 * sa, pha);
+        long long t2 = TCG_CLK();
+        dbg_waitB += t1 - t0; dbg_waitA += t2 - t1;
         tc::tc_fence_after();
         if (lane == 0) {
-          const uint32_t sb = tc::smem_u32(stages + s * SM::STAGE_BYTES);
-          const uint64_t da_hi = tc::make_sw128_kmajor_desc(sb + SM::OFF_A_HI);
-          const uint64_t da_lo = tc::make_sw128_kmajor_desc(sb + SM::OFF_A_LO);
-          const uint64_t db_hi = tc::make_sw128_kmajor_desc(sb + SM::OFF_B_HI);
-          const uint64_t db_lo = tc::make_sw128_kmajor_desc(sb + SM::OFF_B_LO);
+          const uint64_t db_hi = db_base + (uint64_t)(sb_ * stage_adv);
+          const uint64_t db_lo = db_hi + part_adv;
+          const uint32_t a_hi = tmem_a0 + (uint32_t)(sa * 64), a_lo = a_hi + 32;
 #pragma unroll
           for (int k = 0; k < GBK / 8; ++k) {
-            const uint64_t adv = (uint64_t)(k * 2);
+            const uint64_t adv = (uint64_t)(k * 2);     // 8 fp32 = 32 bytes >> 4 along the K-major smem rows
+            const uint32_t acol = (uint32_t)(k * 8);    // 8 TMEM columns
             const uint32_t first = (kc == 0 && k == 0) ? 0u : 1u;
-            tc::umma_tf32(tmem_main, da_hi + adv, db_hi + adv, idesc, first);
+            tc::umma_tf32_ts(tmem_main, a_hi + acol, db_hi + adv, idesc, first);
             if (a.passes == 3) {
-              tc::umma_tf32(tmem_small, da_hi + adv, db_lo + adv, idesc, first);
-              tc::umma_tf32(tmem_small, da_lo + adv, db_hi + adv, idesc, 1u);
+              tc::umma_tf32_ts(tmem_small, a_hi + acol, db_lo + adv, idesc, first);
+              tc::umma_tf32_ts(tmem_small, a_lo + acol, db_hi + adv, idesc, 1u);
             }
           }
-          tc::umma_commit(bar_empty0 + 8 * s);
+          tc::umma_commit(bar_emptyA0 + 8 * sa);
+          tc::umma_commit(bar_emptyB0 + 8 * sb_);
           if (kc == a.nk - 1) tc::umma_commit(bar_accfull);
         }
         __syncwarp();
+        if (++sa == ASTAGES) { sa = 0; pha ^= 1; }
+        if (++sb_ == NB) { sb_ = 0; phb ^= 1; }
       }
     }
+    if (a.dbg && lane == 0) {
+      long long* d = a.dbg + (long long)blockIdx.x * 8;
+      d[0] = dbg_waitA; d[1] = dbg_waitB; d[2] = dbg_waitAcc; d[3] = TCG_CLK() - dbg_start;
+    }
   } else if (warp >= 4 && warp < 8) {
-    // =========================== A producers: one patch row per thread ===========================
-    const int pr = (warp - 4) * 32 + lane;
+    // =========================== A producers: one patch row (= TMEM lane) per thread ===========================
+    const int pr = (warp & 3) * 32 + lane;
     const float* th = tabKH + pr;
     const float* tl = tabKL + pr;
-    const uint32_t rowoff = (uint32_t)(pr * 128);
-    const int sw = pr & 7;
-    int i = 0;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    int sa = 0;
+    uint32_t phe = 1;   // parity to wait for on the empty barrier
+    long long dbg_pwait = 0, dbg_pst = 0, dbg_pgen = 0, tprev = TCG_CLK();
     for (int t = 0; t < a.ntiles; ++t) {
-      for (int kc = 0; kc < a.nk; ++kc, ++i) {
-        const int s = i % GSTAGES;
-        const uint32_t it = (uint32_t)(i / GSTAGES);
+      for (int kc = 0; kc < a.nk; ++kc) {
         const int k0 = kc * GBK;
-        int kh = k0 / a.KL;
-        int kl = k0 - kh * a.KL;
-        float v[GBK];
+        float hi[GBK], lo[GBK];
+        {
+          uint32_t id[GBK];
+          const uint4* kp = (const uint4*)(kidx + k0);   // warp-uniform, 16-byte aligned
 #pragma unroll
-        for (int j = 0; j < GBK; ++j) {
-          const bool ok = (k0 + j) < a.Kdim;
-          const float hv = th[(ok ? kh : 0) * 128];
-          const float lv = tl[(ok ? kl : 0) * 128];
-          v[j] = ok ? hv * lv : 0.f;
-          if (++kl == a.KL) { kl = 0; ++kh; }
-        }
-        tc::mbar_wait(bar_empty0 + 8 * s, (it & 1) ^ 1);
-        unsigned char* st = stages + s * SM::STAGE_BYTES + rowoff;
+          for (int q4 = 0; q4 < GBK / 4; ++q4) {
+            const uint4 u = kp[q4];
+            id[4 * q4] = u.x; id[4 * q4 + 1] = u.y; id[4 * q4 + 2] = u.z; id[4 * q4 + 3] = u.w;
+          }
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float4 hi, lo;
-          tc::split_tf32(v[4 * c + 0], hi.x, lo.x);
-          tc::split_tf32(v[4 * c + 1], hi.y, lo.y);
-          tc::split_tf32(v[4 * c + 2], hi.z, lo.z);
-          tc::split_tf32(v[4 * c + 3], hi.w, lo.w);
-          const uint32_t off = (uint32_t)((c ^ sw) << 4);
-          *(float4*)(st + SM::OFF_A_HI + off) = hi;
-          if (a.passes == 3) *(float4*)(st + SM::OFF_A_LO + off) = lo;
+          for (int j = 0; j < GBK; ++j) tc::split_tf32(th[(id[j] & 0xFFFF) * 128] * tl[(id[j] >> 16) * 128], hi[j], lo[j]);
         }
-        tc::fence_proxy_async();
+        long long t0 = TCG_CLK();
+        tc::mbar_wait(bar_emptyA0 + 8 * sa, phe);
+        long long t1 = TCG_CLK();
+        tc::tc_fence_after();
+        const uint32_t dst = tmem_a0 + lane_base + (uint32_t)(sa * 64);
+        tc::tmem_st32(dst, hi);
+        if (a.passes == 3) tc::tmem_st32(dst + 32, lo);
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(bar_full0 + 8 * s);
+        if (lane == 0) tc::mbar_arrive(bar_fullA0 + 8 * sa);
+        long long t2 = TCG_CLK();
+        dbg_pwait += t1 - t0; dbg_pst += t2 - t1; dbg_pgen += t0 - tprev; tprev = t2;
+        if (++sa == ASTAGES) { sa = 0; phe ^= 1; }
       }
+    }
+    if (a.dbg && warp == 4 && lane == 0) {
+      long long* d = a.dbg + (long long)blockIdx.x * 8;
+      d[4] = dbg_pwait; d[5] = dbg_pst; d[6] = dbg_pgen;
     }
   } else if (warp >= 8) {
     // =========================== epilogue ===========================
@@ -290,18 +343,20 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     // running state of the fused reductions (all of it warp-uniform except s)
     float s = 0.f;
-    int fo = 0, fb = 0, fbh = 0, fbl = 0;    // MODE_FWD: current o, b, b / BL, b % BL
-    int do_ = 0, db = 0;                     // MODE_DKR2: current o and b
+    int fo = 0, fb = 0;                      // MODE_FWD: current o and b of the next column
+    int db = 0;                              // MODE_DKR2: next b to store
     const float* eH = tabE + pr;
     const float* eL = tabE + g.BH * 128 + pr;
+    long long dbg_epi = 0;
     for (int t = 0; t < a.ntiles; ++t) {
       tc::mbar_wait(bar_accfull, (uint32_t)(t & 1));
+      long long te0 = TCG_CLK();
       tc::tc_fence_after();
       const int n0 = t * BN;
       if (MODE == MODE_FWD) {
-        fo = n0 / g.Bn; fb = n0 - fo * g.Bn; fbh = fb / g.BL; fbl = fb - fbh * g.BL;
+        fo = n0 / g.Bn; fb = n0 - fo * g.Bn;
       } else if (MODE == MODE_DKR2) {
-        do_ = 0; db = n0 / O;  // BN % O == 0 (checked on the host)
+        db = n0 / O;  // BN % O == 0 (checked on the host): every tile starts at o == 0
       }
 #pragma unroll 1
       for (int cb = 0; cb < BN; cb += 32) {
@@ -327,26 +382,50 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
             }
           }
         } else if (MODE == MODE_FWD) {
+          // columns cb..cb+31 are b = fb, fb+1, ... (wrapping to the next o at b == Bn; Bn >= 32: at most one wrap)
+          int nvalid = BN - cb;
+          if (a.Ncols - n0 - cb < nvalid) nvalid = a.Ncols - n0 - cb;
+          if (nvalid > 32) nvalid = 32;
+          const int wrap = g.Bn - fb;          // first column of this batch that belongs to the next o
+          const uint32_t* bi = eidx + fb;      // doubled table: fb + 31 < 2*Bn
+          float kr[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            if (cb + i < BN && n0 + cb + i < a.Ncols) {
-              s = fmaf(v[i], eH[fbh * 128] * eL[fbl * 128], s);
-              ++fb;
-              if (++fbl == g.BL) { fbl = 0; ++fbh; }
-              if (fb == g.Bn) {
-                outs[fo * 128 + pr] += s;
-                s = 0.f; fb = 0; fbh = 0; fbl = 0; ++fo;
-              }
-            }
+            const uint32_t id = bi[i];
+            kr[i] = eH[(id & 0xFFFF) * 128] * eL[(id >> 16) * 128];
+          }
+          float s2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float c = (i < nvalid) ? v[i] * kr[i] : 0.f;
+            if (i < wrap) s += c; else s2 += c;
+          }
+          if (wrap <= nvalid) {
+            outs[fo * 128 + pr] += s;
+            s = s2; ++fo; fb = fb + nvalid - g.Bn;
+          } else {
+            fb += nvalid;
           }
         } else {  // MODE_DKR2
+          const uint4* cp = (const uint4*)(eidx + cb);
+          uint32_t id[32];
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const uint4 u = cp[q4];
+            id[4 * q4] = u.x; id[4 * q4 + 1] = u.y; id[4 * q4 + 2] = u.z; id[4 * q4 + 3] = u.w;
+          }
+          float gv[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) gv[i] = tabE[(id[i] & 0xFF) * 128 + pr];
+          int nvalid = BN - cb;
+          if (a.Ncols - n0 - cb < nvalid) nvalid = a.Ncols - n0 - cb;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            if (cb + i < BN && n0 + cb + i < a.Ncols) {
-              s = fmaf(v[i], tabE[do_ * 128 + pr], s);
-              if (++do_ == O) {
+            if (i < nvalid) {
+              s = fmaf(v[i], gv[i], s);
+              if (id[i] & 0x100u) {
                 if (pvalid) a.out[(long long)pl * g.Bn + db] = s;
-                s = 0.f; do_ = 0; ++db;
+                s = 0.f; ++db;
               }
             }
           }
@@ -359,7 +438,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(bar_accempty);
+      dbg_epi += TCG_CLK() - te0;
     }
+    if (a.dbg && warp == 8 && lane == 0) a.dbg[(long long)blockIdx.x * 8 + 7] = dbg_epi;
     if (MODE == MODE_FWD && pvalid) {
       float* orow = a.out + (pt0 + pr) * O;
       for (int o = 0; o < O; ++o) orow[o] = outs[o * 128 + pr];
@@ -387,32 +468,40 @@ inline GemmShape shape_for(const EpsGeom& g, int mode) {
   return s;
 }
 
-inline size_t gemm_smem(const EpsGeom& g, const GemmShape& s, int mode, int BN) {
+inline size_t gemm_fixed_smem(const EpsGeom& g, const GemmShape& s, int mode) {
   const int nE = (mode == MODE_FWD) ? (g.BH + g.BL) : (mode == MODE_DKR2 ? g.O : 0);
-  size_t stage = 2 * (size_t)GBM * GBK * 4 + 2 * (size_t)BN * GBK * 4;
-  size_t b = 1024 + GSTAGES * stage + (size_t)(s.KH + s.KL + nE + (mode == MODE_FWD ? g.O : 0)) * 128 * 4 + (2 * GSTAGES + 2) * 8 + 16;
-  return b;
+  const size_t nkidx = (size_t)((s.Kdim + GBK - 1) / GBK) * GBK;
+  const size_t neidx = (mode == MODE_FWD) ? 2 * (size_t)g.Bn : (mode == MODE_DKR2 ? (size_t)MAX_BN : 0);
+  return 1024 + (size_t)(s.KH + 1 + s.KL + nE + (mode == MODE_FWD ? g.O : 0)) * 128 * 4 + (nkidx + neidx + 2) * 4 +
+         (2 * MAX_BSTAGES + 2 * ASTAGES + 2) * 8 + 16;
+}
+inline size_t bstage_bytes(int BN) { return 2 * (size_t)BN * GBK * 4; }
+
+// number of shared-memory B stages that fit (0 = does not fit); the setup scratch (x and gout of 128 patches)
+// is aliased onto the stages and must fit too
+inline int pick_bstages(const EpsGeom& g, int mode, int BN) {
+  const GemmShape s = shape_for(g, mode);
+  const size_t fixed = gemm_fixed_smem(g, s, mode);
+  if (fixed >= TCG_SMEM_LIMIT) return 0;
+  int nb = (int)((TCG_SMEM_LIMIT - fixed) / bstage_bytes(BN));
+  if (nb > MAX_BSTAGES) nb = MAX_BSTAGES;
+  if (nb < 2) return 0;
+  if ((size_t)(g.n * g.Q + g.O) * 128 * 4 > nb * bstage_bytes(BN)) return 0;
+  return nb;
 }
 
-// setup scratch (x and gout of 128 patches) is aliased onto the operand stages: it must fit there
-inline bool scratch_fits(const EpsGeom& g, int BN) {
-  size_t stage = 2 * (size_t)GBM * GBK * 4 + 2 * (size_t)BN * GBK * 4;
-  return (size_t)(g.n * g.Q + g.O) * 128 * 4 <= GSTAGES * stage;
-}
-
-// pick the column-tile width: fits shared memory, satisfies the epilogue's alignment, least padding, then widest
+// pick the column-tile width (multiple of 16, <= MAX_BN): satisfies the epilogue's alignment (MODE_DKR2 needs whole
+// (b, o) groups per tile), fits shared memory with >= 2 stages, least padded width, then widest
 inline int pick_bn(const EpsGeom& g, int mode) {
   const GemmShape s = shape_for(g, mode);
   int best = 0;
-  long long best_pad = 0;
-  const int cands[4] = {256, 240, 192, 128};  // 240 = 16*15 serves Q_out = 3, 5, 6, 10, 12, 15, 24 in MODE_DKR2
-  for (int i = 0; i < 4; ++i) {
-    const int bn = cands[i];
+  long long best_cost = 0;
+  for (int bn = MAX_BN; bn >= 64; bn -= 16) {
     if (mode == MODE_DKR2 && bn % g.O != 0) continue;
-    if (gemm_smem(g, s, mode, bn) > TCG_SMEM_LIMIT || !scratch_fits(g, bn)) continue;
-    long long pad = (long long)((s.Ncols + bn - 1) / bn) * bn;
-    if (bn == 128) pad = pad * 5 / 4;  // N=128 MMAs are shared-memory-bandwidth bound: count them as 25% more expensive
-    if (!best || pad < best_pad) { best = bn; best_pad = pad; }
+    if (pick_bstages(g, mode, bn) == 0) continue;
+    long long cost = (long long)((s.Ncols + bn - 1) / bn) * bn;
+    if (bn < 160) cost = cost * 9 / 8;  // narrow tiles: relatively more epilogue / barrier overhead per MMA
+    if (!best || cost < best_cost) { best = bn; best_cost = cost; }
   }
   return best;
 }
@@ -427,14 +516,17 @@ inline long long dx_patch_chunk(const EpsGeom& g) {
   long long target = 96ll << 20;
   long long pc = target / (((long long)g.A + g.Bn) * 4);
   if (pc < 4096) pc = 4096;
-  pc = (pc / 128) * 128;
+  // whole waves: one CTA per 128 patches, 148 CTAs resident at a time
+  const long long wave = 148ll * GBM;
+  if (pc >= wave) pc = (pc / wave) * wave;
+  else pc = (pc / 128) * 128;
   if (pc > g.P) pc = g.P;
   return pc;
 }
 
-template <int BN, int MODE>
+template <int MODE>
 int launch_gemm_inst(const TcGemmArgs& a, size_t smem, cudaStream_t st) {
-  auto k = tc_gemm_kernel<BN, MODE>;
+  auto k = tc_gemm_kernel<MODE>;
   DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k<<<(a.np + GBM - 1) / GBM, G_THREADS, smem, st>>>(a);
   dctn_count_launch();
@@ -449,15 +541,34 @@ int run_gemm(const EpsGeom& g, int mode, int BN, const float* x, const float* go
   a.g = g; a.x = x; a.gout = gout; a.p0 = p0; a.np = np;
   a.jh0 = s.jh0; a.cnth = s.cnth; a.KH = s.KH; a.cntl = s.cntl; a.KLb = s.KLb; a.KL = s.KL; a.Kdim = s.Kdim; a.withG = s.withG;
   a.Ncols = s.Ncols; a.ntiles = (s.Ncols + BN - 1) / BN; a.nk = (s.Kdim + GBK - 1) / GBK;
-  a.packed = packed; a.passes = passes; a.out = out; a.ldc = ldc;
-  const size_t smem = gemm_smem(g, s, mode, BN);
-#define DCTN_GEMM_CASE(bn, md) \
-  if (BN == bn && mode == md) return launch_gemm_inst<bn, md>(a, smem, st);
-  DCTN_GEMM_CASE(256, MODE_STORE) DCTN_GEMM_CASE(240, MODE_STORE) DCTN_GEMM_CASE(192, MODE_STORE) DCTN_GEMM_CASE(128, MODE_STORE)
-  DCTN_GEMM_CASE(256, MODE_FWD) DCTN_GEMM_CASE(240, MODE_FWD) DCTN_GEMM_CASE(192, MODE_FWD) DCTN_GEMM_CASE(128, MODE_FWD)
-  DCTN_GEMM_CASE(256, MODE_DKR2) DCTN_GEMM_CASE(240, MODE_DKR2) DCTN_GEMM_CASE(192, MODE_DKR2) DCTN_GEMM_CASE(128, MODE_DKR2)
-#undef DCTN_GEMM_CASE
-  return dctn_set_error(-2, "tcgen05 GEMM: no kernel instance for BN=%d mode=%d", BN, mode);
+  a.packed = packed; a.BN = BN; a.bstages = pick_bstages(g, mode, BN); a.passes = passes; a.out = out; a.ldc = ldc;
+  a.dbg = nullptr;
+  static long long* dbg_buf = nullptr;
+  const char* dbg_env = getenv("DCTN_TCG_DEBUG");
+  const int ncta = (np + GBM - 1) / GBM;
+  if (dbg_env && ncta <= 4096) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 4096 * 8 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 4096 * 8 * sizeof(long long), st);
+    a.dbg = dbg_buf;
+  }
+  const size_t smem = gemm_fixed_smem(g, s, mode) + a.bstages * bstage_bytes(BN);
+  int rc;
+  if (mode == MODE_STORE) rc = launch_gemm_inst<MODE_STORE>(a, smem, st);
+  else if (mode == MODE_FWD) rc = launch_gemm_inst<MODE_FWD>(a, smem, st);
+  else rc = launch_gemm_inst<MODE_DKR2>(a, smem, st);
+  if (a.dbg && rc == 0) {
+    static long long host[4096 * 8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(host, dbg_buf, (size_t)ncta * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+    double sum[8] = {0};
+    for (int c = 0; c < ncta; ++c) for (int k = 0; k < 8; ++k) sum[k] += (double)host[c * 8 + k];
+    const double nst = (double)a.ntiles * a.nk;
+    fprintf(stderr, "[tcg dbg] mode=%d BN=%d NB=%d ntiles=%d nk=%d per-stage cycles: mma waitA %.0f waitB %.0f waitAcc(per tile) %.0f total %.0f | "
+            "producer wait %.0f st %.0f gen %.0f | epilogue/tile %.0f\n", mode, BN, a.bstages, a.ntiles, a.nk,
+            sum[0] / ncta / nst, sum[1] / ncta / nst, sum[2] / ncta / a.ntiles, sum[3] / ncta / nst,
+            sum[4] / ncta / nst, sum[5] / ncta / nst, sum[6] / ncta / nst, sum[7] / ncta / a.ntiles);
+  }
+  return rc;
 }
 
 int run_pack(const EpsGeom& g, int mode, int BN, const float* core, float* dst, int passes, cudaStream_t st) {
@@ -483,7 +594,7 @@ inline bool common_ok(const EpsGeom& g) {
 
 bool tcg_supported(const EpsGeom& g, int kind) {
   if (!common_ok(g)) return false;
-  if (kind == 0) return pick_bn(g, MODE_FWD) != 0;
+  if (kind == 0) return g.Bn >= 32 && pick_bn(g, MODE_FWD) != 0;
   if (kind == 2) return (g.n - g.m) > 0 && pick_bn(g, MODE_STORE) != 0 && pick_bn(g, MODE_DKR2) != 0;
   return false;
 }
