@@ -1,310 +1,383 @@
-// tcgen05 (5th-gen tensor core) kernel family for the EPS contraction, float32 only.
+// tcgen05 core-gradient kernel of the EPS contraction (float32; 3xTF32 or 1xTF32 arithmetic).
 //
-// fp32 accuracy on TF32 tensor cores: every fp32 operand v is split on chip into hi (top 19 bits, exactly a
-// TF32 number) and lo = v - hi; a product a*b is issued as three MMAs  a_hi*b_hi + a_hi*b_lo + a_lo*b_hi
-// accumulated in the same fp32 TMEM accumulator ("3xTF32", error ~2^-21 per product).  passes == 1 issues
-// only a_hi*b_hi (plain TF32, rel. err ~1e-3, opt-in variant DCTN_VARIANT_TC1).
+//   dcore[a][n] = sum_p KR1[p][a] * KR2[p][b(n)] * gout[p][o(n)]          reduction over ALL patches
 //
-// Core gradient (dcore[a][n] = sum_p KR1[p][a] * KR2[p][b(n)] * gout[p][o(n)]), reduction over ALL patches:
-//   * CTA tile 128 (a) x 256 (n), one TMEM accumulator (256 columns), K = patches in chunks of 32;
-//   * BOTH operands are generated in shared memory by 8 producer warps from two-level Khatri-Rao tables
-//     (common.cuh) directly in the K-major SWIZZLE_128B layout tcgen05.mma reads — nothing Q^m-sized
-//     ever comes from HBM; only x (n*Q floats per patch) and gout (O floats per patch) are read;
-//   * warp 0 issues the MMAs (one elected thread), tcgen05.commit frees the stage / publishes the accumulator;
-//   * the tensor core's fp32 accumulator ROUNDS TOWARD ZERO on every MMA (measured: 768 accumulate steps
-//     shrink the result by 1.5e-5), so the accumulation chain is kept short: the K loop is cut into segments
-//     of SEG_CHUNKS chunks that alternate between two TMEM accumulators (2 x 256 columns = all of TMEM); while
-//     the MMAs of segment i+1 run, the producer warps drain segment i with tcgen05.ld and add it into fp32
-//     REGISTERS (128 per thread, round-to-nearest) — "promotion", ~2e-6 residual bias independent of K;
-//   * split-K: one CTA per (tile, patch range), ~one wave of 148 CTAs; partial tiles go to the workspace and
-//     a second kernel sums them in a fixed order (deterministic).
+//   * CTA tile 128 (a) x 128 (n); the K loop runs over this CTA's patch range in chunks of 64 patches (two
+//     32-wide slabs per pipeline stage, so every barrier round feeds 24 MMAs);
+//   * BOTH operands are generated on chip from the two-level Khatri-Rao tables (common.cuh).  The tables themselves
+//     (AH + AL + BH + BL*O floats per patch, e.g. 192) are computed ONCE per call by build_tables_kernel into an
+//     L2-friendly scratch buffer laid out [chunk of 64 patches][entry][64 (+4 pad)]: every one of the (A/128)*(N/128)
+//     output tiles needs them for the same patches, and rebuilding them per CTA was 60% of the producers' time
+//     (profiles/r01_dcore_phase_cycles.txt).  One elected thread streams the rows a tile needs (4 contiguous ranges)
+//     per chunk with cp.async.bulk (TMA engine, mbarrier complete_tx), double-buffered.  Every producer thread then
+//     generates ONE operand row: its two table-row pointers are loop-invariant, so a row is 16 x LDS.128 + 32
+//     multiplies + the TF32 hi/lo split per slab — no index arithmetic in the loop.
+//     A rows (a) are written with tcgen05.st into TENSOR MEMORY (the MMA reads A from TMEM, TS form); B rows (n) go
+//     to shared memory in the K-major SWIZZLE_128B layout.  Nothing Q^m-sized ever comes from HBM;
+//   * warp 0 issues tcgen05.mma kind::tf32 (M=128, N=128, K=8): hi*hi products into a MAIN accumulator, the two
+//     cross terms into a SMALL one.  The tensor core rounds its fp32 accumulator toward zero on every MMA
+//     (measured: 768 accumulate steps shrink a result by 1.5e-5), so the main chain is also kept short: every
+//     SEG_CHUNKS chunks the producers drain both accumulators with tcgen05.ld and add them into fp32 REGISTERS
+//     (64 per thread, round-to-nearest) — "promotion"; residual bias ~2e-6 independent of the reduction length;
+//   * split-K over patch ranges (about two waves of CTAs); partial tiles go to the workspace and a second kernel
+//     sums them in a fixed order (deterministic).
+// TMEM columns: main 0..127, small 128..255, A stage s at 256 + 128*s (slab0 hi | slab0 lo | slab1 hi | slab1 lo).
 #include "common.cuh"
 #include "eps_kernels.h"
+#include <cstdio>
+#include <cstdlib>
+
 #include "tc_common.cuh"
+
+// cycle probes for tuning (make NVFLAGS+=-DDCTN_TCG_TIMING, run with DCTN_TCG_DEBUG=1); compiled out by default
+#ifdef DCTN_TCG_TIMING
+#define TCD_CLK() clock64()
+#else
+#define TCD_CLK() 0ll
+#endif
 
 namespace {
 
-constexpr int BM = 128;          // MMA M (rows of the accumulator = TMEM lanes)
-constexpr int BK = 32;           // K elements per stage (128 bytes per row)
+constexpr int BM = 128;           // a rows  (= TMEM lanes)
+constexpr int BN = 128;           // n rows of the B operand
+constexpr int CH = 64;            // patches per pipeline stage
+constexpr int SLABS = CH / 32;    // 32-wide K slabs per stage
 constexpr int STAGES = 2;
-constexpr int NPROD_WARPS = 8;   // producer warps (warps 1..8); warp 0 issues MMAs
-constexpr int NTHREADS_TC = 32 * (1 + NPROD_WARPS);
-constexpr int SEG_CHUNKS = 8;    // chunks (of BK patches) accumulated in TMEM before promotion to registers
+constexpr int NPROD_WARPS = 8;    // warps 1..8; warp 0 issues MMAs; warp 9 streams the tables
+constexpr int NTHREADS_TC = 32 * (2 + NPROD_WARPS);
+constexpr int TSTAGES = 2;        // table buffers
+constexpr int SEG_CHUNKS = 12;    // chunks per promotion segment: 12 * 2 slabs * 4 k-steps = 96 roundings of the main chain
+constexpr int TS_ = CH + 4;       // table row stride in floats (272 B: 16-byte aligned, rows 4 banks apart)
+constexpr uint32_t SLAB_BYTES = BN * 32 * 4;           // one part (hi or lo) of one slab of B: 16 KB
+constexpr uint32_t STAGE_BYTES = SLABS * 2 * SLAB_BYTES;  // 64 KB
+constexpr size_t TC_SMEM_LIMIT = 227 * 1024;
 
 struct TcDcoreArgs {
   EpsGeom g;
-  const float* x;
-  const float* gout;
+  const float* tables;  // [ceil(P/64)][ENT][TS_] from build_tables_kernel, ENT = AH + AL + BH + BL*O
   float* part;          // [splits][A][N]
-  long long per_split;  // multiple of BK
+  long long per_split;  // multiple of CH
   int passes;           // 3 (fp32-accurate) or 1
+  long long* dbg;       // optional per-CTA cycle counters (16 per CTA)
 };
 
 __device__ __forceinline__ void producer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * NPROD_WARPS) : "memory"); }
 
-// packed digits (one byte each, digit 0 = slowest) of entry e of a group with cnt <= 4 factors
-__device__ __forceinline__ uint32_t pack_digits(int e, int cnt, int Q) {
-  uint32_t packed = 0;
-  for (int t = cnt - 1; t >= 0; --t) {
-    packed |= (uint32_t)(e % Q) << (8 * t);
-    e /= Q;
-  }
-  return packed;
+// which table entries a tile needs: all of the lo tables, a contiguous range of the hi tables
+struct TileTables {
+  int ah0, nah;   // first needed AH entry and count
+  int bh0, nbh;   // first needed BH entry and count
+  int te;         // total entries: nah + AL + nbh + BL*O
+};
+__host__ __device__ inline TileTables tile_tables(const EpsGeom& g, int a0, int n0) {
+  TileTables t;
+  const int BLO = g.BL * g.O;
+  int a1 = a0 + BM - 1; if (a1 > g.A - 1) a1 = g.A - 1;
+  int n1 = n0 + BN - 1; if (n1 > g.N - 1) n1 = g.N - 1;
+  t.ah0 = a0 / g.AL; t.nah = a1 / g.AL - t.ah0 + 1;
+  t.bh0 = n0 / BLO;  t.nbh = n1 / BLO - t.bh0 + 1;
+  t.te = t.nah + g.AL + t.nbh + BLO;
+  return t;
+}
+// upper bound of TileTables::te over all tiles
+inline int max_tile_entries(const EpsGeom& g) {
+  const int BLO = g.BL * g.O;
+  int nah = (BM + g.AL - 1) / g.AL + 1; if (nah > g.AH) nah = g.AH;
+  int nbh = (BN + BLO - 1) / BLO + 1;   if (nbh > g.BH) nbh = g.BH;
+  return nah + g.AL + nbh + BLO;
 }
 
-template <int BN>
-struct DcoreSmem {
-  static constexpr uint32_t A_BYTES = BM * BK * 4;   // 16 KB
-  static constexpr uint32_t B_BYTES = BN * BK * 4;   // 32 KB for BN = 256
-  static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr uint32_t OFF_A_HI = 0, OFF_A_LO = A_BYTES, OFF_B_HI = 2 * A_BYTES, OFF_B_LO = 2 * A_BYTES + B_BYTES;
-};
-
-template <int BN>
-__global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_constant__ TcDcoreArgs a) {
-  using SM = DcoreSmem<BN>;
-  extern __shared__ unsigned char smem_dyn[];
-  const EpsGeom& g = a.g;
-  const int Q = g.Q, O = g.O;
+// tables[chunk][entry][i] for patch p = chunk*64 + i (zeros past P): entries [0,AH): first-half hi group,
+// [AH, AH+AL): first-half lo group, then [.., +BH): second-half hi group, then BL*O: second-half lo group x gout.
+__global__ void __launch_bounds__(256) build_tables_kernel(EpsGeom g, const float* __restrict__ x,
+                                                           const float* __restrict__ gout, float* __restrict__ tables) {
+  extern __shared__ float bt_smem[];
+  const int Q = g.Q, O = g.O, NX = g.n * Q;
+  float* xs = bt_smem;             // [NX][64]
+  float* gs = xs + NX * CH;        // [O][64]
+  const long long p0 = (long long)blockIdx.x * CH;
+  for (int idx = threadIdx.x; idx < (NX + O) * CH; idx += blockDim.x) {
+    const int i = idx & (CH - 1), r = idx >> 6;
+    const long long p = p0 + i;
+    float v = 0.f;
+    if (p < g.P) v = (r < NX) ? __ldg(&x[patch_origin(g, p) + g.foff[r / Q] + r % Q]) : __ldg(&gout[p * O + (r - NX)]);
+    xs[idx] = v;
+  }
+  __syncthreads();
   const int BLO = g.BL * O;
-  const int TE = g.AH + g.AL + g.BH + BLO;   // table entries per patch
-  const int NX = g.n * Q;
-
-  // ---- carve shared memory (operand stages first, 1024-byte aligned for SWIZZLE_128B)
-  unsigned char* base = smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u);  // stays a shared-space pointer
-  unsigned char* stages = base;
-  float* tab = (float*)(base + STAGES * SM::STAGE_BYTES);   // [TE + 1][32]; row TE is all zeros (padding rows)
-  float* xs = tab + (TE + 1) * 32;                           // [NX + 1][32]; row NX is all ones (unused factor slots)
-  float* gs = xs + (NX + 1) * 32;                            // [O + 1][32];  row O is all ones (entries without gout)
-  uint32_t* rowinfo = (uint32_t*)(gs + (O + 1) * 32);        // [BM + BN]: hi entry | lo entry << 16 (TE | TE<<16 = padding row)
-  uint2* emeta = (uint2*)(rowinfo + BM + BN);                // [TE]: {4 xs rows packed, gs row} (8-byte aligned: all sizes above are multiples of 8)
-  int* xoff = (int*)(emeta + TE);                            // [NX]: element offset of (factor j, component q) from the patch origin
-  uint64_t* bars = (uint64_t*)(xoff + ((NX + 1) & ~1));
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
-  const uint32_t bar_full0 = tc::smem_u32(bars), bar_empty0 = bar_full0 + 8 * STAGES;
-  const uint32_t bar_accfull0 = bar_full0 + 16 * STAGES, bar_accempty0 = bar_accfull0 + 16;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int a0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  long long pbeg = (long long)blockIdx.z * a.per_split;
-  long long pend = pbeg + a.per_split;
-  if (pend > g.P) pend = g.P;
-  const int nchunks = (int)((pend - pbeg + BK - 1) / BK);
-
-  // ---- one-time setup
-  if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      tc::mbar_init(bar_full0 + 8 * s, NPROD_WARPS);
-      tc::mbar_init(bar_empty0 + 8 * s, 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(bar_accfull0 + 8 * i, 1);
-      tc::mbar_init(bar_accempty0 + 8 * i, NPROD_WARPS);
-    }
-    tc::fence_barrier_init();
-  }
-  if (warp == 0) tc::tmem_alloc(tc::smem_u32(tmem_slot), 2 * BN);
-  // row -> (hi entry, lo entry); padding rows multiply the all-zero table row
-  for (int r = tid; r < BM + BN; r += NTHREADS_TC) {
-    uint32_t info = (uint32_t)TE | ((uint32_t)TE << 16);
-    if (r < BM) {
-      int ai = a0 + r;
-      if (ai < g.A) info = (uint32_t)(ai / g.AL) | ((uint32_t)(g.AH + ai % g.AL) << 16);
-    } else {
-      int ni = n0 + (r - BM);
-      if (ni < g.N) info = (uint32_t)(g.AH + g.AL + ni / BLO) | ((uint32_t)(g.AH + g.AL + g.BH + ni % BLO) << 16);
-    }
-    rowinfo[r] = info;
-  }
-  // table entry -> the (up to 4) xs rows whose product it is, plus its gout row; unused slots point at ones rows
-  for (int t = tid; t < TE; t += NTHREADS_TC) {
-    int e, j0, cnt, grow = O;
+  const int ENT = g.AH + g.AL + g.BH + BLO;
+  float* out = tables + (long long)blockIdx.x * ENT * TS_;
+  for (int idx = threadIdx.x; idx < ENT * CH; idx += blockDim.x) {
+    const int i = idx & (CH - 1), t = idx >> 6;
+    int e, j0, cnt;
+    float v = 1.f;
     if (t < g.AH) { e = t; j0 = 0; cnt = g.a_nh; }
     else if (t < g.AH + g.AL) { e = t - g.AH; j0 = g.a_nh; cnt = g.a_nl; }
     else if (t < g.AH + g.AL + g.BH) { e = t - g.AH - g.AL; j0 = g.m; cnt = g.b_nh; }
     else {
-      int idx = t - (g.AH + g.AL + g.BH);
-      e = idx / O; grow = idx - e * O; j0 = g.m + g.b_nh; cnt = g.b_nl;
+      const int k = t - (g.AH + g.AL + g.BH);
+      e = k / O; v = gs[(k - e * O) * CH + i]; j0 = g.m + g.b_nh; cnt = g.b_nl;
     }
-    const uint32_t dg = pack_digits(e, cnt, Q);
-    uint32_t rows = 0;
-    for (int u = 0; u < 4; ++u) {
-      uint32_t row = (u < cnt) ? (uint32_t)((j0 + u) * Q) + ((dg >> (8 * u)) & 0xFF) : (uint32_t)NX;
-      rows |= row << (8 * u);
+    for (int u = cnt - 1; u >= 0; --u) {
+      const int d = e % Q;
+      e /= Q;
+      v *= xs[((j0 + u) * Q + d) * CH + i];
     }
-    emeta[t] = make_uint2(rows, (uint32_t)grow);
+    out[t * TS_ + i] = v;
   }
-  for (int jq = tid; jq < NX; jq += NTHREADS_TC) xoff[jq] = (int)g.foff[jq / Q] + jq % Q;
-  if (tid < 32) {
-    tab[TE * 32 + tid] = 0.f;
-    xs[NX * 32 + tid] = 1.f;
-    gs[O * 32 + tid] = 1.f;
+  // the 4 pad floats of every row are never read by the consumers (rows are read 64 wide) but are copied: define them
+  for (int idx = threadIdx.x; idx < ENT * (TS_ - CH); idx += blockDim.x) out[(idx / (TS_ - CH)) * TS_ + CH + idx % (TS_ - CH)] = 0.f;
+}
+
+__global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_constant__ TcDcoreArgs a) {
+  extern __shared__ unsigned char smem_dyn[];
+  const EpsGeom& g = a.g;
+  const int O = g.O;
+  const int BLO = g.BL * O;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int a0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const TileTables tt = tile_tables(g, a0, n0);
+  const int TE = tt.te;
+
+  // ---- carve shared memory
+  unsigned char* base = smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u);
+  unsigned char* stages = base;                                  // B operand: [STAGES][slab][hi|lo][128 rows x 128 B]
+  float* tabs = (float*)(base + STAGES * STAGE_BYTES);           // [TSTAGES][TE][TS_]  table rows this tile needs
+  float* zrow = tabs + TSTAGES * TE * TS_;                       // [TS_] zeros: padding operand rows multiply this
+  uint64_t* bars = (uint64_t*)(zrow + TS_);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 2 * TSTAGES + 2);
+  const uint32_t bar_fullA0 = tc::smem_u32(bars), bar_fullB0 = bar_fullA0 + 8 * STAGES;
+  const uint32_t bar_empty0 = bar_fullB0 + 8 * STAGES;           // one per stage: frees both the TMEM A stage and the smem B stage
+  const uint32_t bar_tfull0 = bar_empty0 + 8 * STAGES, bar_tempty0 = bar_tfull0 + 8 * TSTAGES;
+  const uint32_t bar_accfull = bar_tempty0 + 8 * TSTAGES, bar_accempty = bar_accfull + 8;
+
+  long long pbeg = (long long)blockIdx.z * a.per_split;
+  long long pend = pbeg + a.per_split;
+  if (pend > g.P) pend = g.P;
+  const int nchunks = (int)((pend - pbeg + CH - 1) / CH);
+
+  // ---- one-time setup
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(bar_fullA0 + 8 * s, 4);   // the 4 warps that write A rows
+      tc::mbar_init(bar_fullB0 + 8 * s, 4);   // the 4 warps that write B rows
+      tc::mbar_init(bar_empty0 + 8 * s, 1);   // tcgen05.commit
+    }
+    for (int s = 0; s < TSTAGES; ++s) {
+      tc::mbar_init(bar_tfull0 + 8 * s, 1);             // expect_tx arrive of the table warp (+ bytes)
+      tc::mbar_init(bar_tempty0 + 8 * s, NPROD_WARPS);  // every producer warp is done reading the buffer
+    }
+    tc::mbar_init(bar_accfull, 1);
+    tc::mbar_init(bar_accempty, NPROD_WARPS);
+    tc::fence_barrier_init();
   }
+  if (warp == 0) tc::tmem_alloc(tc::smem_u32(tmem_slot), 512);
+  for (int i = tid; i < TS_; i += NTHREADS_TC) zrow[i] = 0.f;
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_main = tmem_base, tmem_small = tmem_base + BN, tmem_a0 = tmem_base + 2 * BN;
 
   if (warp == 0) {
     // =========================== MMA issuer ===========================
     const uint32_t idesc = tc::make_idesc_tf32(BM, BN);
+    const uint64_t db_base = tc::make_sw128_kmajor_desc(tc::smem_u32(stages));
+    int s = 0;
+    uint32_t ph = 0;
+    long long dm_acc = 0, dm_b = 0, dm_a = 0, dm_start = TCD_CLK();
     for (int c = 0; c < nchunks; ++c) {
-      const int s = c % STAGES;
-      const uint32_t it = (uint32_t)(c / STAGES);
-      const int seg = c / SEG_CHUNKS, acc = seg & 1;
       const bool seg_first = (c % SEG_CHUNKS) == 0;
       const bool seg_last = ((c + 1) % SEG_CHUNKS) == 0 || c == nchunks - 1;
-      // before overwriting an accumulator, its previous use (segment seg-2) must have been drained
-      if (seg_first && seg >= 2) tc::mbar_wait(bar_accempty0 + 8 * acc, (uint32_t)(((seg >> 1) - 1) & 1));
-      tc::mbar_wait(bar_full0 + 8 * s, it & 1);
+      long long m0 = TCD_CLK();
+      if (seg_first && c > 0) {   // the previous segment must have been promoted before its accumulators are overwritten
+        tc::mbar_wait(bar_accempty, (uint32_t)((c / SEG_CHUNKS - 1) & 1));
+        tc::tc_fence_after();
+      }
+      long long m1 = TCD_CLK();
+      tc::mbar_wait(bar_fullB0 + 8 * s, ph);
+      long long m2 = TCD_CLK();
+      tc::mbar_wait(bar_fullA0 + 8 * s, ph);
+      long long m3 = TCD_CLK();
+      dm_acc += m1 - m0; dm_b += m2 - m1; dm_a += m3 - m2;
       tc::tc_fence_after();
       if (lane == 0) {
-        const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
-        const uint32_t sb = tc::smem_u32(stages + s * SM::STAGE_BYTES);
-        const uint64_t da_hi = tc::make_sw128_kmajor_desc(sb + SM::OFF_A_HI);
-        const uint64_t da_lo = tc::make_sw128_kmajor_desc(sb + SM::OFF_A_LO);
-        const uint64_t db_hi = tc::make_sw128_kmajor_desc(sb + SM::OFF_B_HI);
-        const uint64_t db_lo = tc::make_sw128_kmajor_desc(sb + SM::OFF_B_LO);
 #pragma unroll
-        for (int k = 0; k < BK / 8; ++k) {
-          const uint64_t adv = (uint64_t)(k * 2);  // 32 bytes >> 4
-          const uint32_t accum = (seg_first && k == 0) ? 0u : 1u;
-          if (a.passes == 3) {
-            // small terms first, then the dominant one
-            tc::umma_tf32(tmem_acc, da_lo + adv, db_hi + adv, idesc, accum);
-            tc::umma_tf32(tmem_acc, da_hi + adv, db_lo + adv, idesc, 1u);
-            tc::umma_tf32(tmem_acc, da_hi + adv, db_hi + adv, idesc, 1u);
-          } else {
-            tc::umma_tf32(tmem_acc, da_hi + adv, db_hi + adv, idesc, accum);
+        for (int sl = 0; sl < SLABS; ++sl) {
+          const uint64_t db_hi = db_base + (uint64_t)((s * STAGE_BYTES + sl * 2 * SLAB_BYTES) >> 4);
+          const uint64_t db_lo = db_hi + (SLAB_BYTES >> 4);
+          const uint32_t a_hi = tmem_a0 + (uint32_t)(s * 128 + sl * 64), a_lo = a_hi + 32;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)(k * 2);
+            const uint32_t acol = (uint32_t)(k * 8);
+            const uint32_t first = (seg_first && sl == 0 && k == 0) ? 0u : 1u;
+            tc::umma_tf32_ts(tmem_main, a_hi + acol, db_hi + adv, idesc, first);
+            if (a.passes == 3) {
+              tc::umma_tf32_ts(tmem_small, a_hi + acol, db_lo + adv, idesc, first);
+              tc::umma_tf32_ts(tmem_small, a_lo + acol, db_hi + adv, idesc, 1u);
+            }
           }
         }
-        tc::umma_commit(bar_empty0 + 8 * s);                       // stage can be refilled once these MMAs have read it
-        if (seg_last) tc::umma_commit(bar_accfull0 + 8 * acc);      // this segment's accumulator is complete
+        tc::umma_commit(bar_empty0 + 8 * s);
+        if (seg_last) tc::umma_commit(bar_accfull);
       }
       __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1; }
+    }
+    if (a.dbg && lane == 0) {
+      long long* d = a.dbg + ((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16;
+      d[0] = dm_acc; d[1] = dm_b; d[2] = dm_a; d[3] = TCD_CLK() - dm_start; d[4] = nchunks;
+    }
+  } else if (warp == 1 + NPROD_WARPS) {
+    // =========================== table streamer ===========================
+    if (lane == 0) {
+      const int ENT = g.AH + g.AL + g.BH + BLO;
+      const uint32_t row_b = TS_ * 4;
+      const uint32_t bytes = (uint32_t)TE * row_b;
+      const long long chunk0 = pbeg / CH;     // per_split is a multiple of CH
+      int ts = 0;
+      uint32_t ph = 1;
+      for (int c = 0; c < nchunks; ++c) {
+        tc::mbar_wait(bar_tempty0 + 8 * ts, ph);
+        const float* src = a.tables + (chunk0 + c) * (long long)ENT * TS_;
+        const uint32_t dst = tc::smem_u32(tabs + ts * TE * TS_);
+        const uint32_t bar = bar_tfull0 + 8 * ts;
+        tc::mbar_arrive_expect_tx(bar, bytes);
+        tc::bulk_g2s(dst, src + (long long)tt.ah0 * TS_, (uint32_t)tt.nah * row_b, bar);
+        tc::bulk_g2s(dst + (uint32_t)tt.nah * row_b, src + (long long)g.AH * TS_, (uint32_t)g.AL * row_b, bar);
+        tc::bulk_g2s(dst + (uint32_t)(tt.nah + g.AL) * row_b, src + (long long)(g.AH + g.AL + tt.bh0) * TS_, (uint32_t)tt.nbh * row_b, bar);
+        tc::bulk_g2s(dst + (uint32_t)(tt.nah + g.AL + tt.nbh) * row_b, src + (long long)(g.AH + g.AL + g.BH) * TS_, (uint32_t)BLO * row_b, bar);
+        if (++ts == TSTAGES) { ts = 0; ph ^= 1; }
+      }
     }
   } else {
     // =========================== producers ===========================
-    const int pw = warp - 1;  // 0..7
-    const int kq = lane & 7;             // which 4 consecutive patches (16-byte chunk of a K-major row)
-    const int rsub = lane >> 3;          // which of the 4 rows / entries a warp handles per iteration
-    const int r0 = pw * 4 + rsub;        // first row / table entry owned by this thread (then every 32nd)
-    const uint32_t off0 = (uint32_t)(r0 * 128 + ((kq ^ (r0 & 7)) << 4));  // its 16-byte chunk in a swizzled tile
-    const int quad = warp & 3;           // TMEM lane quadrant this warp may access
-    const int half = (warp - 1) >> 2;    // which half of the accumulator columns this warp promotes
-    float racc[BN / 2];                  // fp32 running sum of this thread's row, BN/2 columns
+    const int pw = warp - 1;                 // 0..7
+    const bool is_a = pw < 4;                // warps 1..4 own the 128 A rows, warps 5..8 the 128 B rows
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+    const int row = is_a ? quad * 32 + lane : (pw - 4) * 32 + lane;
+    // loop-invariant table rows of this thread's operand row (padding rows multiply the all-zero table row)
+    int e_hi = TE, e_lo = TE;
+    if (is_a) {
+      const int ai = a0 + row;
+      if (ai < g.A) { e_hi = ai / g.AL - tt.ah0; e_lo = tt.nah + ai % g.AL; }
+    } else {
+      const int ni = n0 + row;
+      if (ni < g.N) { e_hi = tt.nah + g.AL + (ni / BLO - tt.bh0); e_lo = tt.nah + g.AL + tt.nbh + ni % BLO; }
+    }
+    const float4* th4[TSTAGES];
+    const float4* tl4[TSTAGES];
 #pragma unroll
-    for (int i = 0; i < BN / 2; ++i) racc[i] = 0.f;
+    for (int b = 0; b < TSTAGES; ++b) {
+      th4[b] = (const float4*)(e_hi < TE ? tabs + (b * TE + e_hi) * TS_ : zrow);
+      tl4[b] = (const float4*)(e_lo < TE ? tabs + (b * TE + e_lo) * TS_ : zrow);
+    }
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint32_t brow_off = (uint32_t)(row * 128);
+    const int bsw = row & 7;
+    // promotion: this thread accumulates row (quad*32 + lane), columns [chalf*64, chalf*64 + 64)
+    const int chalf = pw >> 2;
+    float racc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) racc[i] = 0.f;
     int next_drain = 0;
-    const unsigned hw = (unsigned)(g.Ho * g.Wo);
-    // promote segment `seg` (complete in TMEM) into the register accumulators, then hand the buffer back
     auto drain = [&](int seg) {
-      const int acc = seg & 1;
-      tc::mbar_wait(bar_accfull0 + 8 * acc, (uint32_t)((seg >> 1) & 1));
+      tc::mbar_wait(bar_accfull, (uint32_t)(seg & 1));
       tc::tc_fence_after();
 #pragma unroll
-      for (int cb = 0; cb < BN / 2; cb += 32) {
+      for (int cb = 0; cb < 64; cb += 32) {
         float v[32];
-        tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2) + cb), v);
+        tc::tmem_ld32(tmem_main + lane_base + (uint32_t)(chalf * 64 + cb), v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) racc[cb + i] += v[i];
+        if (a.passes == 3) {
+          tc::tmem_ld32(tmem_small + lane_base + (uint32_t)(chalf * 64 + cb), v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) racc[cb + i] += v[i];
+        }
       }
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(bar_accempty0 + 8 * acc);
+      if (lane == 0) tc::mbar_arrive(bar_accempty);
     };
+
+    int s = 0, ts = 0;
+    uint32_t phe = 1;   // parity to wait for on the empty barrier (fresh barriers pass parity 1)
+    uint32_t tph = 0;   // parity of the table-full barrier
+    long long dp[7] = {0, 0, 0, 0, 0, 0, 0};
     for (int c = 0; c < nchunks; ++c) {
-      const int s = c % STAGES;
-      const uint32_t it = (uint32_t)(c / STAGES);
-      // (1) stage x and gout of this chunk's 32 patches: lane = patch (32-bit index math, offsets precomputed)
-      {
-        const unsigned p = (unsigned)pbeg + (unsigned)(c * BK + lane);
-        const bool ok = p < (unsigned)pend;
-        const unsigned pc = ok ? p : 0u;
-        const unsigned b = pc / hw, r = pc - b * hw, h = r / (unsigned)g.Wo, w = r - h * (unsigned)g.Wo;
-        const float* xp = a.x + (size_t)(((b * (unsigned)g.H + h) * (unsigned)g.W + w) * (unsigned)Q);
-        const float* gp = a.gout + (size_t)pc * O;
-#pragma unroll 4
-        for (int jq = pw; jq < NX; jq += NPROD_WARPS) xs[jq * 32 + lane] = ok ? __ldg(xp + xoff[jq]) : 0.f;
-        for (int o = pw; o < O; o += NPROD_WARPS) gs[o * 32 + lane] = ok ? __ldg(gp + o) : 0.f;
-      }
-      producer_bar_sync();
-      // (2) two-level Khatri-Rao tables.  Thread = (entry, 4 consecutive patches): 128-bit shared accesses,
-      //     branch-free (unused factor slots read the all-ones rows); two entries per iteration for ILP.
-      {
-        const float4* xs4 = (const float4*)xs;
-        const float4* gs4 = (const float4*)gs;
-        float4* tab4 = (float4*)tab;
-        auto entry = [&](int t) -> float4 {
-          const uint2 em = emeta[t];
-          float4 v = gs4[em.y * 8 + kq];
+      long long q0 = TCD_CLK();
+      // (1) the table rows of this chunk have landed
+      tc::mbar_wait(bar_tfull0 + 8 * ts, tph);
+      long long q1 = TCD_CLK(), q2 = q1, q3 = q1, q4 = q1;
+      const float4* th = th4[ts];
+      const float4* tl = tl4[ts];
+      // (2) one operand row per thread; wait until the MMAs that read this stage two chunks ago are done
+      tc::mbar_wait(bar_empty0 + 8 * s, phe);
+      long long q5 = TCD_CLK();
+      tc::tc_fence_after();
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float4 f = xs4[((em.x >> (8 * u)) & 0xFF) * 8 + kq];
-            v.x *= f.x; v.y *= f.y; v.z *= f.z; v.w *= f.w;
-          }
-          return v;
-        };
-        int t = r0;
-        for (; t + 32 < TE; t += 64) {
-          const float4 v0 = entry(t), v1 = entry(t + 32);
-          tab4[t * 8 + kq] = v0;
-          tab4[(t + 32) * 8 + kq] = v1;
+      for (int sl = 0; sl < SLABS; ++sl) {
+        float hi[32], lo[32];
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 h4 = th[sl * 8 + q4], l4 = tl[sl * 8 + q4];
+          tc::split_tf32(h4.x * l4.x, hi[4 * q4 + 0], lo[4 * q4 + 0]);
+          tc::split_tf32(h4.y * l4.y, hi[4 * q4 + 1], lo[4 * q4 + 1]);
+          tc::split_tf32(h4.z * l4.z, hi[4 * q4 + 2], lo[4 * q4 + 2]);
+          tc::split_tf32(h4.w * l4.w, hi[4 * q4 + 3], lo[4 * q4 + 3]);
         }
-        if (t < TE) tab4[t * 8 + kq] = entry(t);
-      }
-      producer_bar_sync();
-      // (3) wait until the MMAs that read this stage (two chunks ago) are done, then generate the operand tiles:
-      //     thread = (row, 4 consecutive patches) -> one 16-byte chunk of the swizzled row, hi and lo parts
-      tc::mbar_wait(bar_empty0 + 8 * s, (it & 1) ^ 1);
-      {
-        // Each thread owns the same rows r0 + 32*i in every chunk: row r0 + 32*i keeps r & 7, so the swizzled byte
-        // offset is (off0 + i*4096) and everything below except the table values is loop-invariant.
-        unsigned char* st = stages + s * SM::STAGE_BYTES + off0;
-        const float4* tab4 = (const float4*)tab + kq;
-        const uint32_t* ri = rowinfo + r0;
-        constexpr int NROW = (BM + BN) / 32;
-        static_assert(BM % 32 == 0 && BN % 32 == 0 && NROW % 2 == 0, "row ownership pattern");
+        if (is_a) {
+          const uint32_t dst = tmem_a0 + lane_base + (uint32_t)(s * 128 + sl * 64);
+          tc::tmem_st32(dst, hi);
+          if (a.passes == 3) tc::tmem_st32(dst + 32, lo);
+        } else {
+          unsigned char* st = stages + s * STAGE_BYTES + sl * 2 * SLAB_BYTES + brow_off;
 #pragma unroll
-        for (int i = 0; i < NROW; i += 2) {
-          float4 hi[2], lo[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const uint32_t info = ri[(i + u) * 32];
-            const float4 th = tab4[(info & 0xFFFF) * 8], tl = tab4[(info >> 16) * 8];
-            tc::split_tf32(th.x * tl.x, hi[u].x, lo[u].x);
-            tc::split_tf32(th.y * tl.y, hi[u].y, lo[u].y);
-            tc::split_tf32(th.z * tl.z, hi[u].z, lo[u].z);
-            tc::split_tf32(th.w * tl.w, hi[u].w, lo[u].w);
-          }
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            constexpr uint32_t A_ROWS = BM / 32;
-            const int ii = i + u;
-            const uint32_t tile_hi = ii < (int)A_ROWS ? SM::OFF_A_HI + ii * 4096u : SM::OFF_B_HI + (ii - A_ROWS) * 4096u;
-            const uint32_t tile_lo = ii < (int)A_ROWS ? SM::OFF_A_LO + ii * 4096u : SM::OFF_B_LO + (ii - A_ROWS) * 4096u;
-            *(float4*)(st + tile_hi) = hi[u];
-            if (a.passes == 3) *(float4*)(st + tile_lo) = lo[u];
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const uint32_t off = (uint32_t)((q4 ^ bsw) << 4);
+            *(float4*)(st + off) = make_float4(hi[4 * q4], hi[4 * q4 + 1], hi[4 * q4 + 2], hi[4 * q4 + 3]);
+            if (a.passes == 3)
+              *(float4*)(st + SLAB_BYTES + off) = make_float4(lo[4 * q4], lo[4 * q4 + 1], lo[4 * q4 + 2], lo[4 * q4 + 3]);
           }
         }
       }
-      tc::fence_proxy_async();
+      if (is_a) {
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(bar_fullA0 + 8 * s);
+      } else {
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(bar_fullB0 + 8 * s);
+      }
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(bar_full0 + 8 * s);
-      // Having been allowed to refill stage s means the MMAs of chunk c-STAGES are complete; one chunk into a
-      // new segment (c % SEG_CHUNKS == STAGES-1) that covers the whole previous segment: promote it now, while
-      // the tensor core works on the chunks just produced.
-      if ((c % SEG_CHUNKS) == STAGES - 1 && c >= SEG_CHUNKS) drain(next_drain++);
+      if (lane == 0) tc::mbar_arrive(bar_tempty0 + 8 * ts);   // this warp no longer reads the table buffer
+      if (++ts == TSTAGES) { ts = 0; tph ^= 1; }
+      long long q6 = TCD_CLK();
+      dp[0] += q1 - q0; dp[1] += q2 - q1; dp[2] += q3 - q2; dp[3] += q4 - q3; dp[4] += q5 - q4; dp[5] += q6 - q5;
+      if (++s == STAGES) { s = 0; phe ^= 1; }
+      // the first chunk of a new segment is now queued behind the previous segment: promote that segment while the
+      // tensor core finishes it, so the MMA warp finds work ready the moment the accumulators are handed back
+      if ((c % SEG_CHUNKS) == 0 && c > 0) drain(next_drain++);
+      dp[6] += TCD_CLK() - q6;
+    }
+    if (a.dbg && lane == 0 && (warp == 1 || warp == 5)) {
+      long long* d = a.dbg + ((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (warp == 1 ? 5 : 5);
+      if (warp == 1) for (int i = 0; i < 7; ++i) d[i] = dp[i];
     }
     const int last_seg = (nchunks - 1) / SEG_CHUNKS;
     while (next_drain <= last_seg) drain(next_drain++);
+
     // =========================== epilogue: registers -> partial tile ===========================
     const int arow = a0 + quad * 32 + lane;
-    float* prow = a.part + ((long long)blockIdx.z * g.A + arow) * (long long)g.N;
     if (arow < g.A) {
+      float* prow = a.part + ((long long)blockIdx.z * g.A + arow) * (long long)g.N;
 #pragma unroll
-      for (int cb = 0; cb < BN / 2; cb += 4) {
-        const int nb = n0 + half * (BN / 2) + cb;
+      for (int cb = 0; cb < 64; cb += 4) {
+        const int nb = n0 + chalf * 64 + cb;
         if (nb + 4 <= g.N && (g.N & 3) == 0) {
           *(float4*)(prow + nb) = make_float4(racc[cb], racc[cb + 1], racc[cb + 2], racc[cb + 3]);
         } else {
@@ -317,28 +390,26 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem_base, 2 * BN);
+  if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
 }
 
-template <int BN>
 size_t dcore_tc_smem(const EpsGeom& g) {
-  const int BLO = g.BL * g.O;
-  const int TE = g.AH + g.AL + g.BH + BLO;
-  size_t b = 1024 + (size_t)STAGES * DcoreSmem<BN>::STAGE_BYTES + (size_t)(TE + g.n * g.Q + g.O + 3) * 32 * 4 +
-             (size_t)(BM + BN) * 4 + 8 + (size_t)TE * 8 + (size_t)(g.n * g.Q + 2) * 4 + (2 * STAGES + 4) * 8 + 16;
-  return b;
+  const int TE = max_tile_entries(g);
+  return 1024 + (size_t)STAGES * STAGE_BYTES + (size_t)(TSTAGES * TE + 1) * TS_ * 4 + (3 * STAGES + 2 * TSTAGES + 2) * 8 + 16;
+}
+inline size_t table_floats(const EpsGeom& g) {
+  const long long nchunks = (g.P + CH - 1) / CH;
+  return (size_t)nchunks * (size_t)(g.AH + g.AL + g.BH + g.BL * g.O) * TS_;
 }
 
-constexpr size_t TC_SMEM_LIMIT = 227 * 1024;
-
-inline void dcore_split(const EpsGeom& g, int BN, long long* per_split, int* splits) {
-  // about one wave: one CTA per SM (the kernel uses all of TMEM and ~220 KB of shared memory)
+inline void dcore_split(const EpsGeom& g, long long* per_split, int* splits) {
+  // about two waves of one-CTA-per-SM (the kernel uses all of TMEM and most of shared memory)
   long long tiles = (long long)((g.A + BM - 1) / BM) * ((g.N + BN - 1) / BN);
-  long long want = 148 / tiles;
+  long long want = (2 * 148) / tiles;
   if (want < 1) want = 1;
   long long per = (g.P + want - 1) / want;
-  per = ((per + BK - 1) / BK) * BK;
-  const long long min_per = (long long)BK * SEG_CHUNKS * 4;  // do not split below a few segments
+  per = ((per + CH - 1) / CH) * CH;
+  const long long min_per = (long long)CH * SEG_CHUNKS * 2;  // do not split below a couple of segments
   if (per < min_per) per = min_per;
   *per_split = per;
   *splits = (int)((g.P + per - 1) / per);
@@ -348,39 +419,65 @@ inline void dcore_split(const EpsGeom& g, int BN, long long* per_split, int* spl
 
 bool tc_supported(const EpsGeom& g, int kind) {
   if (kind != 1) return tcg_supported(g, kind);  // forward / input-gradient GEMMs live in eps_tc_gemm.cu
-  if (g.a_nh > 4 || g.a_nl > 4 || g.b_nh > 4 || g.b_nl > 4) return false;  // packed digit bytes
-  if (g.n * g.Q > 254 || g.O > 254 || g.AH + g.AL + g.BH + g.BL * g.O >= 65535) return false;
+  if (g.a_nh > 4 || g.a_nl > 4 || g.b_nh > 4 || g.b_nl > 4) return false;  // 4 factor slots per table entry
   if (g.P >= (1ll << 31) / (g.Q > g.O ? g.Q : g.O)) return false;  // 32-bit patch index math
-  if (g.A < 64 || g.N < 128) return false;   // tiles would be mostly padding: the CUDA-core family is the better fit
+  if (g.A < 64 || g.N < 64) return false;    // tiles would be mostly padding: the CUDA-core family is the better fit
   if (g.P < 4096) return false;              // tiny reductions are launch-bound either way
-  return dcore_tc_smem<256>(g) <= TC_SMEM_LIMIT;
+  return dcore_tc_smem(g) <= TC_SMEM_LIMIT;
 }
 
 size_t tc_workspace_bytes(const EpsGeom& g, int kind) {
   if (kind == 1) {
     long long per;
     int splits;
-    dcore_split(g, 256, &per, &splits);
-    return (size_t)splits * g.A * g.N * sizeof(float);
+    dcore_split(g, &per, &splits);
+    return ((size_t)splits * g.A * g.N + table_floats(g)) * sizeof(float) + 256;
   }
   return tcg_workspace_bytes(g, kind);
 }
 
 int tc_backward_core(const EpsGeom& g, const float* x, const float* gout, float* dcore, void* ws, int passes,
                      cudaStream_t st) {
-  constexpr int BN = 256;
-  size_t smem = dcore_tc_smem<BN>(g);
+  size_t smem = dcore_tc_smem(g);
   if (smem > TC_SMEM_LIMIT) return dctn_set_error(-2, "tcgen05 core-gradient kernel needs %zu bytes of shared memory", smem);
   TcDcoreArgs a{};
-  a.g = g; a.x = x; a.gout = gout; a.part = (float*)ws; a.passes = passes;
+  a.g = g; a.part = (float*)ws; a.passes = passes;
   int splits;
-  dcore_split(g, BN, &a.per_split, &splits);
-  auto k = tc_dcore_kernel<BN>;
-  DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dcore_split(g, &a.per_split, &splits);
+  float* tables = a.part + (((size_t)splits * g.A * g.N + 63) & ~(size_t)63);
+  a.tables = tables;
+  {
+    const size_t bsm = (size_t)(g.n * g.Q + g.O) * CH * sizeof(float);
+    if (bsm > 200 * 1024) return dctn_set_error(-2, "table kernel needs %zu bytes of shared memory", bsm);
+    DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(build_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+    build_tables_kernel<<<(unsigned)((g.P + CH - 1) / CH), 256, bsm, st>>>(g, x, gout, tables);
+    dctn_count_launch();
+    DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  }
+  DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(tc_dcore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((g.A + BM - 1) / BM, (g.N + BN - 1) / BN, splits);
-  k<<<grid, NTHREADS_TC, smem, st>>>(a);
+  a.dbg = nullptr;
+  static long long* dbg_buf = nullptr;
+  const int ncta = (int)(grid.x * grid.y * grid.z);
+  if (getenv("DCTN_TCG_DEBUG") && ncta <= 4096) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 4096 * 16 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 4096 * 16 * sizeof(long long), st);
+    a.dbg = dbg_buf;
+  }
+  tc_dcore_kernel<<<grid, NTHREADS_TC, smem, st>>>(a);
   dctn_count_launch();
   DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  if (a.dbg) {
+    static long long host[4096 * 16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(host, dbg_buf, (size_t)ncta * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+    double sum[16] = {0};
+    for (int c = 0; c < ncta; ++c) for (int k = 0; k < 16; ++k) sum[k] += (double)host[c * 16 + k];
+    const double nch = sum[4];
+    fprintf(stderr, "[dcore dbg] ctas=%d chunks/cta=%.0f per-chunk cycles: mma wait acc %.0f B %.0f A %.0f total %.0f | producer: publish %.0f "
+            "bar1 %.0f prefetch+tables %.0f bar2 %.0f wait-empty %.0f rows+signal %.0f drain %.0f\n", ncta, nch / ncta,
+            sum[0] / nch, sum[1] / nch, sum[2] / nch, sum[3] / nch, sum[5] / nch, sum[6] / nch, sum[7] / nch, sum[8] / nch,
+            sum[9] / nch, sum[10] / nch, sum[11] / nch);
+  }
   return launch_reduce_partials<float>(a.part, dcore, (long long)g.A * g.N, splits, st);
 }
-
