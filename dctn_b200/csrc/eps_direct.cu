@@ -1,7 +1,359 @@
-// Streaming thread-per-patch family — placeholder until the kernels land.
+// Streaming thread-per-patch forward kernel for EPS layers with a tiny core (the HBM-bound regime of SURVEY.md
+// section 8d: K=2 with Q=2..6, K=3 with Q=2; e.g. config 1 and the K=2 rows of the config-3 microbenchmark).
+//
+// One thread = one output patch.  The K*K*C factor vectors are read straight from x (pos2d unfold = index arithmetic;
+// neighbouring threads read neighbouring pixels, so every warp load is one or two fully used cache lines and the
+// overlap between patches is served by L1/L2: x crosses HBM once), the two Khatri-Rao halves are expanded in
+// REGISTERS (template-unrolled, A = Q^MA and Bn = Q^MB values), and the core — transposed once per CTA into shared
+// memory as [o][a][b] — is broadcast to all threads with 128-bit shared loads:
+//     out[p][o] = sum_a kr1[a] * (sum_b kr2[b] * core[a][b][o])
+// No Q^(K*K)-sized intermediate exists anywhere.  Algorithmic bytes per patch: Q floats of x (amortised) + O floats out.
+#include <type_traits>
+
 #include "common.cuh"
 #include "eps_kernels.h"
-bool direct_supported(const EpsGeom&, int) { return false; }
-template <typename T> int direct_forward(const EpsGeom&, const T*, const T*, T*, cudaStream_t) { return dctn_set_error(-2, "direct family not built"); }
+
+namespace {
+
+constexpr int DTHREADS = 128;
+
+template <int Q, int M> struct IPow { static constexpr int v = Q * IPow<Q, M - 1>::v; };
+template <int Q> struct IPow<Q, 0> { static constexpr int v = 1; };
+
+// kr[e] for e in [0, Q^M): product over factors j0..j0+M-1 (factor j0 slowest digit), built in registers
+template <typename T, int Q, int M>
+__device__ __forceinline__ void expand_kr(T (&kr)[IPow<Q, M>::v], const T* __restrict__ x, unsigned org, const EpsGeom& g, int j0) {
+  kr[0] = T(1);
+  int cur = 1;
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    T xv[Q];
+    const T* px = x + org + g.foff[j0 + j];   // element offset is a multiple of Q: Q even -> 2-element vectors are aligned
+    if constexpr (Q % 4 == 0 && sizeof(T) == 4) {
+#pragma unroll
+      for (int q = 0; q < Q; q += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(px + q));
+        xv[q] = v.x; xv[q + 1] = v.y; xv[q + 2] = v.z; xv[q + 3] = v.w;
+      }
+    } else if constexpr (Q % 2 == 0) {
+      using T2 = typename std::conditional<sizeof(T) == 4, float2, double2>::type;
+#pragma unroll
+      for (int q = 0; q < Q; q += 2) {
+        const T2 v = __ldg(reinterpret_cast<const T2*>(px + q));
+        xv[q] = v.x; xv[q + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < Q; ++q) xv[q] = __ldg(px + q);
+    }
+#pragma unroll
+    for (int e = IPow<Q, M>::v / Q - 1; e >= 0; --e) {   // only e < cur is live; later entries are overwritten before use
+      if (e < cur) {
+        const T base = kr[e];
+#pragma unroll
+        for (int q = Q - 1; q >= 0; --q) kr[e * Q + q] = base * xv[q];
+      }
+    }
+    cur *= Q;
+  }
+}
+
+template <typename T, int Q, int MA, int MB>
+__global__ void __launch_bounds__(DTHREADS) direct_fwd_kernel(EpsGeom g, const T* __restrict__ x,
+                                                              const T* __restrict__ core, T* __restrict__ out) {
+  constexpr int A = IPow<Q, MA>::v, BN = IPow<Q, MB>::v;
+  constexpr int V = 16 / sizeof(T);                 // elements per 128-bit shared load
+  constexpr int BNP = (BN + V - 1) / V * V;         // padded b-run
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* cs = reinterpret_cast<T*>(smem_raw);           // [O][A][BNP]
+  const int O = g.O;
+  for (int idx = threadIdx.x; idx < O * A * BNP; idx += DTHREADS) {
+    const int b = idx % BNP, r = idx / BNP, a = r % A, o = r / A;
+    cs[idx] = (b < BN) ? core[((long long)a * BN + b) * O + o] : T(0);
+  }
+  __syncthreads();
+  const unsigned hw = (unsigned)(g.Ho * g.Wo), Wo = (unsigned)g.Wo, P32 = (unsigned)g.P;   // P and |x| < 2^31 (host check)
+  // PPT patches per thread per iteration: all their loads are issued before any arithmetic, so that enough bytes are in
+  // flight per SM to cover HBM latency (B200 needs ~45 KB outstanding per SM for full bandwidth)
+  constexpr int PPT = (A + BNP <= 16) ? 4 : ((A + BNP <= 40) ? 2 : 1);
+  const unsigned stride = gridDim.x * DTHREADS;
+  for (unsigned p0 = blockIdx.x * DTHREADS + threadIdx.x; p0 < P32; p0 += stride * PPT) {
+    T kr1[PPT][A], kr2[PPT][BNP];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const unsigned p = p0 + k * stride;
+      const unsigned pc = p < P32 ? p : p0;          // clamp: computed but not stored
+      const unsigned b = pc / hw, r = pc - b * hw, h = r / Wo, w = r - h * Wo;
+      const unsigned org = ((b * (unsigned)g.H + h) * (unsigned)g.W + w) * Q;
+      expand_kr<T, Q, MA>(kr1[k], x, org, g, 0);
+      T tmp[BN];
+      expand_kr<T, Q, MB>(tmp, x, org, g, MA);
+#pragma unroll
+      for (int i = 0; i < BNP; ++i) kr2[k][i] = (i < BN) ? tmp[i] : T(0);
+    }
+    // two outputs per pass: every core value read from shared memory feeds 2*PPT FMAs; pairs are stored as one vector
+    for (int o = 0; o < O; o += 2) {
+      const bool two = o + 1 < O;
+      const T* c0 = cs + (size_t)o * A * BNP;
+      const T* c1 = two ? c0 + A * BNP : c0;
+      T acc0[PPT], acc1[PPT];
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) acc0[k] = acc1[k] = T(0);
+#pragma unroll
+      for (int a = 0; a < A; ++a) {
+        T t0[PPT], t1[PPT];
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) t0[k] = t1[k] = T(0);
+#pragma unroll
+        for (int bb = 0; bb < BNP; bb += V) {
+          T u[V], v[V];
+          if constexpr (sizeof(T) == 4) {
+            const float4 uu = *reinterpret_cast<const float4*>(c0 + a * BNP + bb);
+            const float4 vv = *reinterpret_cast<const float4*>(c1 + a * BNP + bb);
+            u[0] = uu.x; u[1] = uu.y; u[2] = uu.z; u[3] = uu.w; v[0] = vv.x; v[1] = vv.y; v[2] = vv.z; v[3] = vv.w;
+          } else {
+            const double2 uu = *reinterpret_cast<const double2*>(c0 + a * BNP + bb);
+            const double2 vv = *reinterpret_cast<const double2*>(c1 + a * BNP + bb);
+            u[0] = uu.x; u[1] = uu.y; v[0] = vv.x; v[1] = vv.y;
+          }
+#pragma unroll
+          for (int k = 0; k < PPT; ++k)
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+              t0[k] = fma(kr2[k][bb + i], u[i], t0[k]);
+              t1[k] = fma(kr2[k][bb + i], v[i], t1[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+          acc0[k] = fma(kr1[k][a], t0[k], acc0[k]);
+          acc1[k] = fma(kr1[k][a], t1[k], acc1[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        const unsigned p = p0 + k * stride;
+        if (p < P32) {
+          T* orow = out + (size_t)p * O;
+          if (two && (O & 1) == 0) {
+            using T2 = typename std::conditional<sizeof(T) == 4, float2, double2>::type;
+            T2 v2; v2.x = acc0[k]; v2.y = acc1[k];
+            *reinterpret_cast<T2*>(orow + o) = v2;     // p*O + o is even: aligned
+          } else {
+            orow[o] = acc0[k];
+            if (two) orow[o + 1] = acc1[k];
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K = 2, C = 1 specialisation (the HBM-bound family).  One warp = RH consecutive output rows x up to 31 output columns:
+//   * lane l loads pixel column w0 + l of the RH + 1 input rows ONCE (vector loads, fully coalesced); the right
+//     neighbour of every pixel comes from lane l + 1 by __shfl_down — 1.25 loads per patch instead of 4;
+//   * the outer product of a horizontally adjacent pixel pair, pp[r] = x[r][w] (x) x[r][w+1], is both the first
+//     Khatri-Rao half of output row r and the second half of output row r - 1: computed once, used twice;
+//   * out[r][o] = sum_a pp[r][a] * (sum_b pp[r+1][b] * core[a][b][o]), core broadcast from shared memory, each
+//     128-bit shared load feeding 2 * RH FMAs per lane.
+template <typename T, int Q, int OT>   // OT: compile-time Q_out (2..8), or 0 = runtime (any Q_out, pairs per pass)
+__global__ void __launch_bounds__(DTHREADS) direct_k2_kernel(EpsGeom g, const T* __restrict__ x, const T* __restrict__ core,
+                                                             T* __restrict__ out) {
+  constexpr int RH = 4;
+  constexpr int A = Q * Q;                          // = Bn
+  constexpr int V = 16 / sizeof(T);
+  constexpr int BNP = (A + V - 1) / V * V;
+  constexpr int OC = OT > 0 ? OT : 2;               // outputs computed per pass
+  using T2 = typename std::conditional<sizeof(T) == 4, float2, double2>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* cs = reinterpret_cast<T*>(smem_raw);           // [O][A][BNP]
+  const int O = OT > 0 ? OT : g.O;
+  for (int idx = threadIdx.x; idx < O * A * BNP; idx += DTHREADS) {
+    const int b = idx % BNP, r = idx / BNP, a = r % A, o = r / A;
+    cs[idx] = (b < A) ? core[((long long)a * A + b) * O + o] : T(0);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const unsigned nhb = (unsigned)(g.Ho + RH - 1) / RH;   // row blocks per image
+  const unsigned ntw = (unsigned)(g.Wo + 30) / 31;       // column tiles of 31 outputs (+1 halo lane)
+  const unsigned ntask = (unsigned)g.B * nhb * ntw;
+  const unsigned nwarps = gridDim.x * (DTHREADS / 32);
+  const unsigned xrow = (unsigned)g.W * Q, orow_stride = (unsigned)g.Wo * O;   // 32-bit offsets (host checks the sizes)
+  for (unsigned task = blockIdx.x * (DTHREADS / 32) + (threadIdx.x >> 5); task < ntask; task += nwarps) {
+    const unsigned tw = task % ntw, t2 = task / ntw, hb = t2 % nhb, b = t2 / nhb;
+    const unsigned h0 = hb * RH, wcol = tw * 31 + lane;  // input (and output) column of this lane
+    // (1) this lane's pixel column, RH + 1 rows; out-of-range lanes/rows re-read a valid pixel (value never stored)
+    const unsigned wc = wcol < (unsigned)g.W ? wcol : 0u;
+    const T* px = x + ((b * (unsigned)g.H + h0) * (unsigned)g.W + wc) * Q;
+    T xv[RH + 1][Q];
+#pragma unroll
+    for (int r = 0; r <= RH; ++r) {
+      const T* pr = px + ((h0 + r < (unsigned)g.H) ? r * xrow : 0u);
+      if constexpr (Q % 4 == 0 && sizeof(T) == 4) {
+#pragma unroll
+        for (int q = 0; q < Q; q += 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(pr + q));
+          xv[r][q] = v.x; xv[r][q + 1] = v.y; xv[r][q + 2] = v.z; xv[r][q + 3] = v.w;
+        }
+      } else if constexpr (Q % 2 == 0) {
+#pragma unroll
+        for (int q = 0; q < Q; q += 2) {
+          const T2 v = __ldg(reinterpret_cast<const T2*>(pr + q));
+          xv[r][q] = v.x; xv[r][q + 1] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) xv[r][q] = __ldg(pr + q);
+      }
+    }
+    // (2) pair products with the right neighbour (lane + 1)
+    T pp[RH + 1][BNP];
+#pragma unroll
+    for (int r = 0; r <= RH; ++r) {
+      T xr[Q];
+#pragma unroll
+      for (int q = 0; q < Q; ++q) xr[q] = __shfl_down_sync(0xffffffffu, xv[r][q], 1);
+#pragma unroll
+      for (int i = 0; i < Q; ++i)
+#pragma unroll
+        for (int j = 0; j < Q; ++j) pp[r][i * Q + j] = xv[r][i] * xr[j];
+#pragma unroll
+      for (int i = A; i < BNP; ++i) pp[r][i] = T(0);
+    }
+    // (3) contraction with the core, OC outputs per pass
+    const bool lane_ok = lane < 31 && wcol < (unsigned)g.Wo;
+    T* obase = out + ((b * (unsigned)g.Ho + h0) * (unsigned)g.Wo + (lane_ok ? wcol : 0u)) * O;
+    for (int o = 0; o < O; o += OC) {
+      T acc[OC][RH];
+#pragma unroll
+      for (int c = 0; c < OC; ++c)
+#pragma unroll
+        for (int r = 0; r < RH; ++r) acc[c][r] = T(0);
+#pragma unroll
+      for (int a = 0; a < A; ++a) {
+        T t[OC][RH];
+#pragma unroll
+        for (int c = 0; c < OC; ++c)
+#pragma unroll
+          for (int r = 0; r < RH; ++r) t[c][r] = T(0);
+#pragma unroll
+        for (int bb = 0; bb < BNP; bb += V) {
+#pragma unroll
+          for (int c = 0; c < OC; ++c) {
+            const int oc = (OT > 0 || o + c < O) ? o + c : o;   // runtime-O tail: recompute output o (not stored)
+            T u[V];
+            if constexpr (sizeof(T) == 4) {
+              const float4 uu = *reinterpret_cast<const float4*>(cs + ((size_t)oc * A + a) * BNP + bb);
+              u[0] = uu.x; u[1] = uu.y; u[2] = uu.z; u[3] = uu.w;
+            } else {
+              const double2 uu = *reinterpret_cast<const double2*>(cs + ((size_t)oc * A + a) * BNP + bb);
+              u[0] = uu.x; u[1] = uu.y;
+            }
+#pragma unroll
+            for (int r = 0; r < RH; ++r)
+#pragma unroll
+              for (int i = 0; i < V; ++i) t[c][r] = fma(pp[r + 1][bb + i], u[i], t[c][r]);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < OC; ++c)
+#pragma unroll
+          for (int r = 0; r < RH; ++r) acc[c][r] = fma(pp[r][a], t[c][r], acc[c][r]);
+      }
+#pragma unroll
+      for (int r = 0; r < RH; ++r) {
+        if (lane_ok && h0 + r < (unsigned)g.Ho) {
+          T* orow = obase + r * orow_stride + o;
+          if constexpr (OT > 0 && OT % 2 == 0) {
+#pragma unroll
+            for (int c = 0; c < OC; c += 2) {
+              T2 v2; v2.x = acc[c][r]; v2.y = acc[c + 1][r];
+              *reinterpret_cast<T2*>(orow + c) = v2;          // (patch * O + c) is even: aligned
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < OC; ++c)
+              if (OT > 0 || o + c < O) orow[c] = acc[c][r];
+          }
+        }
+      }
+    }
+  }
+}
+
+template <typename T, int Q, int OT>
+int launch_direct_k2(const EpsGeom& g, const T* x, const T* core, T* out, cudaStream_t st) {
+  constexpr int A = Q * Q;
+  constexpr int V = 16 / sizeof(T);
+  constexpr int BNP = (A + V - 1) / V * V;
+  const size_t smem = (size_t)g.O * A * BNP * sizeof(T);
+  auto k = direct_k2_kernel<T, Q, OT>;
+  DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long ntask = (long long)g.B * ((g.Ho + 3) / 4) * ((g.Wo + 30) / 31);
+  long long blocks = (ntask + DTHREADS / 32 - 1) / (DTHREADS / 32);
+  const long long cap = 148ll * 16;
+  if (blocks > cap) blocks = cap;
+  k<<<(unsigned)blocks, DTHREADS, smem, st>>>(g, x, core, out);
+  dctn_count_launch();
+  DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  return 0;
+}
+template <typename T, int Q>
+int dispatch_direct_k2(const EpsGeom& g, const T* x, const T* core, T* out, cudaStream_t st) {
+  switch (g.O) {
+    case 2: return launch_direct_k2<T, Q, 2>(g, x, core, out, st);
+    case 3: return launch_direct_k2<T, Q, 3>(g, x, core, out, st);
+    case 4: return launch_direct_k2<T, Q, 4>(g, x, core, out, st);
+    case 6: return launch_direct_k2<T, Q, 6>(g, x, core, out, st);
+    default: return launch_direct_k2<T, Q, 0>(g, x, core, out, st);
+  }
+}
+
+struct DirectShape { int Q, MA, MB; };
+constexpr DirectShape kShapes[] = {{2, 2, 2}, {3, 2, 2}, {4, 2, 2}, {5, 2, 2}, {6, 2, 2}, {2, 5, 4}, {2, 1, 1}, {3, 1, 1}, {4, 1, 1}};
+
+template <typename T, int Q, int MA, int MB>
+int launch_direct(const EpsGeom& g, const T* x, const T* core, T* out, cudaStream_t st) {
+  constexpr int A = IPow<Q, MA>::v, BN = IPow<Q, MB>::v;
+  constexpr int V = 16 / sizeof(T);
+  constexpr int BNP = (BN + V - 1) / V * V;
+  const size_t smem = (size_t)g.O * A * BNP * sizeof(T);
+  auto k = direct_fwd_kernel<T, Q, MA, MB>;
+  DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long blocks = (g.P + DTHREADS - 1) / DTHREADS;
+  const long long cap = 148ll * 16;                  // a few CTAs per SM, grid-stride over the rest
+  if (blocks > cap) blocks = cap;
+  k<<<(unsigned)blocks, DTHREADS, smem, st>>>(g, x, core, out);
+  dctn_count_launch();
+  DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+bool direct_supported(const EpsGeom& g, int dtype) {
+  const size_t es = dtype == 0 ? 4 : 8;
+  if ((size_t)g.A * (g.Bn + 4) * g.O * es > 36 * 1024) return false;   // transposed core in shared memory, >= 6 CTAs per SM
+  if (g.P * g.O >= (1ll << 31) || (long long)g.C * g.B * g.H * g.W * g.Q >= (1ll << 31)) return false;  // 32-bit index math
+  for (const DirectShape& s : kShapes)
+    if (s.Q == g.Q && s.MA == g.m && s.MB == g.n - g.m) return true;
+  return false;
+}
+
+template <typename T>
+int direct_forward(const EpsGeom& g, const T* x, const T* core, T* out, cudaStream_t st) {
+  if (g.K == 2 && g.C == 1) {
+    if (g.Q == 2) return dispatch_direct_k2<T, 2>(g, x, core, out, st);
+    if (g.Q == 3) return dispatch_direct_k2<T, 3>(g, x, core, out, st);
+  }
+#define DCTN_DIRECT_CASE(q, ma, mb) \
+  if (g.Q == q && g.m == ma && g.n - g.m == mb) return launch_direct<T, q, ma, mb>(g, x, core, out, st);
+  DCTN_DIRECT_CASE(2, 2, 2) DCTN_DIRECT_CASE(3, 2, 2) DCTN_DIRECT_CASE(4, 2, 2) DCTN_DIRECT_CASE(5, 2, 2)
+  DCTN_DIRECT_CASE(6, 2, 2) DCTN_DIRECT_CASE(2, 5, 4) DCTN_DIRECT_CASE(2, 1, 1) DCTN_DIRECT_CASE(3, 1, 1)
+  DCTN_DIRECT_CASE(4, 1, 1)
+#undef DCTN_DIRECT_CASE
+  return dctn_set_error(-2, "direct forward kernel: no instance for Q=%d with %d+%d factors", g.Q, g.m, g.n - g.m);
+}
 template int direct_forward<float>(const EpsGeom&, const float*, const float*, float*, cudaStream_t);
 template int direct_forward<double>(const EpsGeom&, const double*, const double*, double*, cudaStream_t);
