@@ -1,0 +1,102 @@
+#!/usr/bin/env python
+"""Config 3 (BASELINE.json): EPS layer microbenchmark — K in {2,3,4}, Q_in in {2,3,4}, Q_out in {2..6}, batch 4096 at
+28x28, forward and forward+backward, against the roofline that binds each shape (small_experiments/eps2d_benchmark
+shape and dctn/benchmark.py protocol: randn core and input, both requiring grad, fixed randn out_grad).
+
+Infeasible corners are reported, not run: K=4 with Q_in=4 (core 4^16 x Q_out elements) and
+K=4 with Q_in=3 (3^16-element core, > 0.4 PFLOP per forward at B=4096).  K=3,Q_in=4 runs at --big-batch (default 512).
+
+    python benchmarks/eps_microbench.py [--batch 4096] [--qouts 2,6] [--json out.json]
+"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from dctn_b200 import _lib  # noqa: E402
+from dctn_b200.eps import eps, plan_description  # noqa: E402
+
+
+def peaks():
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+def timeit(fn, flush, iters):
+    fn(); fn()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record(); e.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--big-batch", type=int, default=512, help="batch for K=3,Q=4 (8.7 TFLOP per forward at 4096)")
+    ap.add_argument("--ks", default="2,3,4")
+    ap.add_argument("--qs", default="2,3,4")
+    ap.add_argument("--qouts", default="2,3,4,5,6")
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--json", default="")
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    hbm, bf16, src = peaks()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    rows = []
+    for K in map(int, args.ks.split(",")):
+        for Q in map(int, args.qs.split(",")):
+            for O in map(int, args.qouts.split(",")):
+                D = Q ** (K * K)
+                if K == 4 and Q >= 3:
+                    rows.append(dict(K=K, Q=Q, O=O, skipped="infeasible: core has %d^16 x %d elements" % (Q, O)))
+                    continue
+                B = args.big_batch if D >= 262144 else args.batch
+                torch.manual_seed(0)
+                core = (torch.randn(*(Q,) * (K * K), O, device=dev) * Q ** (-(K * K) / 2)).requires_grad_(True)
+                x = torch.randn(1, B, 28, 28, Q, device=dev).requires_grad_(True)
+                out = eps(core, x)
+                gout = torch.randn_like(out)
+                P = out.numel() // O
+                flops = 2.0 * P * D * O
+
+                def fwd():
+                    with torch.no_grad():
+                        eps(core, x)
+
+                def fwdbwd():
+                    core.grad = None; x.grad = None
+                    eps(core, x).backward(gout)
+
+                l0 = _lib.launch_count()
+                t_f = timeit(fwd, flush, args.iters)
+                t_fb = timeit(fwdbwd, flush, args.iters)
+                assert _lib.launch_count() > l0
+                fbytes = 4.0 * (x.numel() + out.numel() + core.numel())
+                ai = flops / fbytes
+                row = dict(K=K, Q=Q, O=O, B=B, D=D, P=P, fwd_ms=t_f, fwdbwd_ms=t_fb, fwd_tflops=flops / t_f / 1e9,
+                           fwdbwd_tflops=4 * flops / t_fb / 1e9, fwd_gbs=fbytes / t_f / 1e6, ai_flop_per_byte=ai,
+                           bound="hbm" if ai < 11.4 else ("ffma" if ai < 128 else "tensor"),
+                           fwd_frac_hbm=fbytes / t_f / 1e6 / hbm, fwd_frac_bf16=flops / t_f / 1e9 / bf16,
+                           imgs_per_s_fwdbwd=B / t_fb * 1e3, patches_per_s_fwdbwd=P / t_fb * 1e3,
+                           plan=plan_description(core, x))
+                rows.append(row)
+                print(f"K={K} Q={Q} O={O} B={B}: fwd {t_f:8.3f} ms ({row['fwd_tflops']:7.2f} TF/s, {row['fwd_gbs']:7.1f} GB/s, "
+                      f"{row['bound']}-bound)  fwd+bwd {t_fb:8.3f} ms ({row['fwdbwd_tflops']:7.2f} TF/s)", flush=True)
+                del core, x, out, gout
+    if args.json:
+        json.dump(dict(peaks=dict(hbm_gbs=hbm, bf16_tflops=bf16, source=src), rows=rows), open(args.json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -142,10 +142,13 @@ static int pick_family(const dctn_plan_t* pl, const EpsGeom& g, int kind) {
     case DCTN_VARIANT_FFMA: return FAM_FFMA;
     case DCTN_VARIANT_TC3:
     case DCTN_VARIANT_TC1: return tc_supported(g, kind) ? FAM_TC : -1;
-    case DCTN_VARIANT_DIRECT: return (kind == DCTN_WS_FORWARD && direct_supported(g, pl->dtype)) ? FAM_DIRECT : -1;
+    case DCTN_VARIANT_DIRECT:
+      if (kind == DCTN_WS_FORWARD) return direct_supported(g, pl->dtype) ? FAM_DIRECT : -1;
+      return direct_bwd_supported(g, pl->dtype, kind) ? FAM_DIRECT : -1;
     default: break;
   }
   if (kind == DCTN_WS_FORWARD && direct_supported(g, pl->dtype)) return FAM_DIRECT;
+  if (kind != DCTN_WS_FORWARD && direct_bwd_supported(g, pl->dtype, kind)) return FAM_DIRECT;
   if (pl->dtype == DCTN_F32 && tc_supported(g, kind)) return FAM_TC;
   return FAM_FFMA;
 }
@@ -158,6 +161,7 @@ extern "C" size_t dctn_eps_workspace_bytes(const dctn_plan_t* pl, int B, int H, 
   size_t bytes = 0;
   if (fam == FAM_FFMA) bytes = pl->dtype == DCTN_F32 ? ffma_workspace_bytes<float>(g, kind) : ffma_workspace_bytes<double>(g, kind);
   else if (fam == FAM_TC) bytes = tc_workspace_bytes(g, kind);
+  else if (fam == FAM_DIRECT) bytes = direct_workspace_bytes(g, pl->dtype, kind);
   return bytes + 256;  // never zero, so callers can always pass a valid pointer
 }
 
@@ -199,6 +203,9 @@ extern "C" int dctn_eps_backward_core(const dctn_plan_t* pl, const void* x, cons
   cudaStream_t st = (cudaStream_t)stream;
   int fam = pick_family(pl, g, DCTN_WS_BACKWARD_CORE);
   if (fam < 0) return dctn_set_error(DCTN_ERR_UNSUPPORTED, "backward_core: requested kernel variant %d does not support this shape (%s)", pl->variant, pl->desc.c_str());
+  if (fam == FAM_DIRECT)
+    return pl->dtype == DCTN_F32 ? direct_backward<float>(g, 1, (const float*)x, nullptr, (const float*)gout, (float*)dcore, ws, st)
+                                 : direct_backward<double>(g, 1, (const double*)x, nullptr, (const double*)gout, (double*)dcore, ws, st);
   if (fam == FAM_TC)
     return tc_backward_core(g, (const float*)x, (const float*)gout, (float*)dcore, ws, pl->variant == DCTN_VARIANT_TC1 ? 1 : 3, st);
   return pl->dtype == DCTN_F32 ? ffma_backward_core<float>(g, (const float*)x, (const float*)gout, (float*)dcore, ws, st)
@@ -216,6 +223,10 @@ extern "C" int dctn_eps_backward_input(const dctn_plan_t* pl, const void* x, con
   cudaStream_t st = (cudaStream_t)stream;
   int fam = pick_family(pl, g, DCTN_WS_BACKWARD_INPUT);
   if (fam < 0) return dctn_set_error(DCTN_ERR_UNSUPPORTED, "backward_input: requested kernel variant %d does not support this shape (%s)", pl->variant, pl->desc.c_str());
+  if (fam == FAM_DIRECT)
+    return pl->dtype == DCTN_F32
+               ? direct_backward<float>(g, 2, (const float*)x, (const float*)core, (const float*)gout, (float*)dx, ws, st)
+               : direct_backward<double>(g, 2, (const double*)x, (const double*)core, (const double*)gout, (double*)dx, ws, st);
   if (fam == FAM_TC)
     return tc_backward_input(g, (const float*)x, (const float*)core, (const float*)gout, (float*)dx, ws, pl->variant == DCTN_VARIANT_TC1 ? 1 : 3, st);
   return pl->dtype == DCTN_F32

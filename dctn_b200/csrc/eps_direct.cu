@@ -310,6 +310,182 @@ int dispatch_direct_k2(const EpsGeom& g, const T* x, const T* core, T* out, cuda
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Backward for tiny cores (same register-resident Khatri-Rao halves as the forward).
+//
+// Core gradient: dcore[a][b][o] = sum_p kr1[p][a] kr2[p][b] gout[p][o].  Each thread accumulates PPT patches locally
+// per (a, b, o) term, the warp reduces the term with shuffles, lane 0 adds it into this warp's shared-memory copy of
+// dcore; the CTA then writes one partial per CTA and reduce_partials sums them in fixed order (deterministic).
+template <typename T, int Q, int MA, int MB>
+__global__ void __launch_bounds__(DTHREADS) direct_dcore_kernel(EpsGeom g, const T* __restrict__ x, const T* __restrict__ gout,
+                                                                T* __restrict__ part) {
+  constexpr int A = IPow<Q, MA>::v, BN = IPow<Q, MB>::v;
+  constexpr int PPT = (A + BN <= 16) ? 4 : 2;
+  constexpr int NW = DTHREADS / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* acc_s = reinterpret_cast<T*>(smem_raw);        // [NW][A*BN*O]
+  const int O = g.O, DO = A * BN * O;
+  for (int i = threadIdx.x; i < NW * DO; i += DTHREADS) acc_s[i] = T(0);
+  __syncthreads();
+  T* mine = acc_s + (threadIdx.x >> 5) * DO;
+  const int lane = threadIdx.x & 31;
+  const unsigned hw = (unsigned)(g.Ho * g.Wo), Wo = (unsigned)g.Wo, P32 = (unsigned)g.P;
+  const unsigned stride = gridDim.x * DTHREADS;
+  // all lanes of a warp iterate together (p0 differs only by lane), out-of-range patches contribute zeros
+  for (unsigned p0 = blockIdx.x * DTHREADS + (threadIdx.x & ~31u); p0 < P32; p0 += stride * PPT) {
+    T kr1[PPT][A], kr2[PPT][BN];
+    const T* gp[PPT];
+    bool ok[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const unsigned p = p0 + k * stride + lane;
+      ok[k] = p < P32;
+      const unsigned pc = ok[k] ? p : 0u;
+      const unsigned b = pc / hw, r = pc - b * hw, h = r / Wo, w = r - h * Wo;
+      const unsigned org = ((b * (unsigned)g.H + h) * (unsigned)g.W + w) * Q;
+      expand_kr<T, Q, MA>(kr1[k], x, org, g, 0);
+      expand_kr<T, Q, MB>(kr2[k], x, org, g, MA);
+      gp[k] = gout + (size_t)pc * O;
+    }
+    for (int o = 0; o < O; ++o) {
+      T gv[PPT];
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) gv[k] = ok[k] ? __ldg(gp[k] + o) : T(0);
+#pragma unroll
+      for (int a = 0; a < A; ++a) {
+        T ga[PPT];
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) ga[k] = kr1[k][a] * gv[k];
+#pragma unroll
+        for (int b = 0; b < BN; ++b) {
+          T v = T(0);
+#pragma unroll
+          for (int k = 0; k < PPT; ++k) v = fma(ga[k], kr2[k][b], v);
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+          if (lane == 0) mine[(a * BN + b) * O + o] += v;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  T* dst = part + (size_t)blockIdx.x * DO;
+  for (int i = threadIdx.x; i < DO; i += DTHREADS) {
+    T v = T(0);
+#pragma unroll
+    for (int w = 0; w < NW; ++w) v += acc_s[w * DO + i];
+    dst[i] = v;
+  }
+}
+
+// Input gradient, written per patch as dxp[p][j][q] (the shared gather kernel then sums the K*K overlapping patches of
+// every pixel):  G[a][b] = sum_o gout[p][o] core[a][b][o];  W1[a] = sum_b G[a][b] kr2[b];  W2[b] = sum_a G[a][b] kr1[a];
+// d x_j[q] = sum over the entries of its half with digit_j == q of W * (product of the other factors of that half).
+template <typename T, int Q, int M>
+__device__ __forceinline__ void leave_one_out(const T (&w)[IPow<Q, M>::v], const T (&xv)[M][Q], T* __restrict__ dst /*[M][Q]*/) {
+  constexpr int E = IPow<Q, M>::v;
+#pragma unroll
+  for (int t = 0; t < M; ++t) {
+    T acc[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) acc[q] = T(0);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      T v = w[e];
+      int ee = e, dig = 0;
+#pragma unroll
+      for (int u = M - 1; u >= 0; --u) {
+        const int d = ee % Q;
+        ee /= Q;
+        if (u == t) dig = d; else v *= xv[u][d];
+      }
+#pragma unroll
+      for (int q = 0; q < Q; ++q)
+        if (q == dig) acc[q] += v;
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) dst[t * Q + q] = acc[q];
+  }
+}
+
+template <typename T, int Q, int MA, int MB>
+__global__ void __launch_bounds__(DTHREADS) direct_dx_kernel(EpsGeom g, const T* __restrict__ x, const T* __restrict__ core,
+                                                             const T* __restrict__ gout, T* __restrict__ dxp) {
+  constexpr int A = IPow<Q, MA>::v, BN = IPow<Q, MB>::v;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* cs = reinterpret_cast<T*>(smem_raw);           // core as stored: [A][BN][O]
+  const int O = g.O;
+  for (int i = threadIdx.x; i < A * BN * O; i += DTHREADS) cs[i] = core[i];
+  __syncthreads();
+  const unsigned hw = (unsigned)(g.Ho * g.Wo), Wo = (unsigned)g.Wo, P32 = (unsigned)g.P;
+  for (unsigned p = blockIdx.x * DTHREADS + threadIdx.x; p < P32; p += gridDim.x * DTHREADS) {
+    const unsigned b = p / hw, r = p - b * hw, h = r / Wo, w = r - h * Wo;
+    const unsigned org = ((b * (unsigned)g.H + h) * (unsigned)g.W + w) * Q;
+    T xa[MA][Q], xb[MB][Q];
+#pragma unroll
+    for (int j = 0; j < MA; ++j)
+#pragma unroll
+      for (int q = 0; q < Q; ++q) xa[j][q] = __ldg(x + org + g.foff[j] + q);
+#pragma unroll
+    for (int j = 0; j < MB; ++j)
+#pragma unroll
+      for (int q = 0; q < Q; ++q) xb[j][q] = __ldg(x + org + g.foff[MA + j] + q);
+    T kr1[A], kr2[BN];
+    expand_kr<T, Q, MA>(kr1, x, org, g, 0);
+    expand_kr<T, Q, MB>(kr2, x, org, g, MA);
+    T w1[A], w2[BN];
+#pragma unroll
+    for (int i = 0; i < BN; ++i) w2[i] = T(0);
+    const T* gp = gout + (size_t)p * O;
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      T grow[BN];
+#pragma unroll
+      for (int i = 0; i < BN; ++i) grow[i] = T(0);
+      for (int o = 0; o < O; ++o) {
+        const T gv = __ldg(gp + o);
+#pragma unroll
+        for (int i = 0; i < BN; ++i) grow[i] = fma(gv, cs[(a * BN + i) * O + o], grow[i]);
+      }
+      T s1 = T(0);
+#pragma unroll
+      for (int i = 0; i < BN; ++i) {
+        s1 = fma(grow[i], kr2[i], s1);
+        w2[i] = fma(grow[i], kr1[a], w2[i]);
+      }
+      w1[a] = s1;
+    }
+    T* dst = dxp + (size_t)p * (MA + MB) * Q;
+    leave_one_out<T, Q, MA>(w1, xa, dst);
+    leave_one_out<T, Q, MB>(w2, xb, dst + MA * Q);
+  }
+}
+
+template <typename T, int Q, int MA, int MB>
+int launch_direct_bwd(const EpsGeom& g, int kind, const T* x, const T* core, const T* gout, T* result, void* ws, cudaStream_t st) {
+  constexpr int A = IPow<Q, MA>::v, BN = IPow<Q, MB>::v;
+  long long blocks = (g.P + DTHREADS - 1) / DTHREADS;
+  const long long cap = 148ll * 8;
+  if (blocks > cap) blocks = cap;
+  if (kind == 1) {
+    const int DO = A * BN * g.O;
+    const size_t smem = (size_t)(DTHREADS / 32) * DO * sizeof(T);
+    auto k = direct_dcore_kernel<T, Q, MA, MB>;
+    DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)blocks, DTHREADS, smem, st>>>(g, x, gout, (T*)ws);
+    dctn_count_launch();
+    DCTN_CUDA_CHECK_RET(cudaGetLastError());
+    return launch_reduce_partials<T>((const T*)ws, result, DO, (int)blocks, st);
+  }
+  const size_t smem = (size_t)A * BN * g.O * sizeof(T);
+  auto k = direct_dx_kernel<T, Q, MA, MB>;
+  DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<(unsigned)blocks, DTHREADS, smem, st>>>(g, x, core, gout, (T*)ws);
+  dctn_count_launch();
+  DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  return launch_gather_dx<T>(g, (const T*)ws, result, st);
+}
+
 struct DirectShape { int Q, MA, MB; };
 constexpr DirectShape kShapes[] = {{2, 2, 2}, {3, 2, 2}, {4, 2, 2}, {5, 2, 2}, {6, 2, 2}, {2, 5, 4}, {2, 1, 1}, {3, 1, 1}, {4, 1, 1}};
 
@@ -357,3 +533,29 @@ int direct_forward(const EpsGeom& g, const T* x, const T* core, T* out, cudaStre
 }
 template int direct_forward<float>(const EpsGeom&, const float*, const float*, float*, cudaStream_t);
 template int direct_forward<double>(const EpsGeom&, const double*, const double*, double*, cudaStream_t);
+
+// ---- backward entry points (core gradient: kind 1, input gradient: kind 2)
+bool direct_bwd_supported(const EpsGeom& g, int dtype, int kind) {
+  if (!direct_supported(g, dtype)) return false;
+  const long long DO = (long long)g.A * g.Bn * g.O;
+  if (kind == 1) return DO <= 2048;                       // one shuffle-reduction per core element per warp iteration
+  return g.A + g.Bn <= 64 && g.P * g.n * g.Q < (1ll << 31);  // everything of a patch stays in registers
+}
+size_t direct_workspace_bytes(const EpsGeom& g, int dtype, int kind) {
+  const size_t es = dtype == 0 ? 4 : 8;
+  if (kind == 1) return (size_t)148 * 8 * g.A * g.Bn * g.O * es + 256;
+  if (kind == 2) return (size_t)g.P * g.n * g.Q * es + 256;
+  return 256;
+}
+template <typename T>
+int direct_backward(const EpsGeom& g, int kind, const T* x, const T* core, const T* gout, T* result, void* ws, cudaStream_t st) {
+#define DCTN_DIRECT_CASE(q, ma, mb) \
+  if (g.Q == q && g.m == ma && g.n - g.m == mb) return launch_direct_bwd<T, q, ma, mb>(g, kind, x, core, gout, result, ws, st);
+  DCTN_DIRECT_CASE(2, 2, 2) DCTN_DIRECT_CASE(3, 2, 2) DCTN_DIRECT_CASE(4, 2, 2) DCTN_DIRECT_CASE(5, 2, 2)
+  DCTN_DIRECT_CASE(6, 2, 2) DCTN_DIRECT_CASE(2, 5, 4) DCTN_DIRECT_CASE(2, 1, 1) DCTN_DIRECT_CASE(3, 1, 1)
+  DCTN_DIRECT_CASE(4, 1, 1)
+#undef DCTN_DIRECT_CASE
+  return dctn_set_error(-2, "direct backward kernel: no instance for Q=%d with %d+%d factors", g.Q, g.m, g.n - g.m);
+}
+template int direct_backward<float>(const EpsGeom&, int, const float*, const float*, const float*, float*, void*, cudaStream_t);
+template int direct_backward<double>(const EpsGeom&, int, const double*, const double*, const double*, double*, void*, cudaStream_t);

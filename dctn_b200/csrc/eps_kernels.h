@@ -21,6 +21,10 @@ template <typename T> int launch_gather_dx(const EpsGeom& g, const T* dxp, T* dx
 // ---- streaming thread-per-patch family for tiny cores (eps_direct.cu): HBM-bound shapes
 bool direct_supported(const EpsGeom& g, int dtype);
 template <typename T> int direct_forward(const EpsGeom& g, const T* x, const T* core, T* out, cudaStream_t st);
+bool direct_bwd_supported(const EpsGeom& g, int dtype, int kind);
+size_t direct_workspace_bytes(const EpsGeom& g, int dtype, int kind);
+// kind 1: result = dcore (core unused), kind 2: result = dx
+template <typename T> int direct_backward(const EpsGeom& g, int kind, const T* x, const T* core, const T* gout, T* result, void* ws, cudaStream_t st);
 
 // ---- tcgen05 TF32 family (eps_tc.cu): float only, large cores
 bool tc_supported(const EpsGeom& g, int kind);
