@@ -422,6 +422,113 @@ __global__ void __launch_bounds__(NTHREADS) loo_kernel(EpsGeom g, const T* __res
   }
 }
 
+// Shared-memory staged version of loo_kernel: the dKR rows of LPT patches are brought in ONCE with coalesced 128-bit
+// loads (row-major [EH][EL] matrix per patch, stored with an odd row stride so that both the column-wise (Wlo) and the
+// row-wise (Whi) passes are bank-conflict free); everything else is as in loo_kernel.
+constexpr int LPT = 8;  // patches per CTA
+template <typename T>
+__global__ void __launch_bounds__(NTHREADS) loo_staged_kernel(EpsGeom g, const T* __restrict__ x, const T* __restrict__ dkr,
+                                                              long long p0, int np, int j0, int cnth, int EH, int cntl,
+                                                              int EL, T* __restrict__ dxp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int Q = g.Q;
+  const int nf = cnth + cntl;
+  const int xs_stride = (nf * Q) | 1;
+  const int E = EH * EL;
+  const int ELS = EL | 1;                  // padded row stride of the staged matrix
+  T* M = reinterpret_cast<T*>(smem_raw);   // [LPT][EH][ELS]
+  T* tH = M + LPT * EH * ELS;              // [LPT][EH]
+  T* tL = tH + LPT * EH;                   // [LPT][EL]
+  T* wH = tL + LPT * EL;                   // [LPT][EH]
+  T* wL = wH + LPT * EH;                   // [LPT][EL]
+  T* xs = wL + LPT * EL;
+  const int pl0 = blockIdx.x * LPT;
+  const int npl = (np - pl0 < LPT) ? (np - pl0) : LPT;
+  // (1) stage the rows: contiguous npl*E elements of dkr starting at pl0*E
+  {
+    const T* src = dkr + (long long)pl0 * E;
+    const int total = npl * E;
+    constexpr int V = 16 / sizeof(T);
+    if ((E % V) == 0) {
+      for (int i = threadIdx.x * V; i < total; i += NTHREADS * V) {
+        T v[V];
+        if constexpr (sizeof(T) == 4) {
+          const float4 f = *reinterpret_cast<const float4*>(src + i);
+          v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+        } else {
+          const double2 f = *reinterpret_cast<const double2*>(src + i);
+          v[0] = f.x; v[1] = f.y;
+        }
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+          const int e = (i + u) % E, pl = (i + u) / E;
+          M[(pl * EH + e / EL) * ELS + e % EL] = v[u];
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < total; i += NTHREADS) {
+        const int e = i % E, pl = i / E;
+        M[(pl * EH + e / EL) * ELS + e % EL] = src[i];
+      }
+    }
+  }
+  stage_x(xs, xs_stride, x, g, p0 + pl0, LPT, j0, nf);
+  __syncthreads();
+  build_table(tH, EH, 1, xs, xs_stride, 0, cnth, EH, Q, (const T*)nullptr, 1, LPT);
+  build_table(tL, EL, 1, xs, xs_stride, cnth, cntl, EL, Q, (const T*)nullptr, 1, LPT);
+  __syncthreads();
+  for (int item = threadIdx.x; item < LPT * EL; item += NTHREADS) {
+    const int pl = item / EL, el = item - pl * EL;
+    T s = T(0);
+    if (pl < npl) {
+      const T* m = M + pl * EH * ELS + el;
+      const T* th = tH + pl * EH;
+      for (int eh = 0; eh < EH; ++eh) s = fma(m[eh * ELS], th[eh], s);
+    }
+    wL[item] = s;
+  }
+  for (int item = threadIdx.x; item < LPT * EH; item += NTHREADS) {
+    const int pl = item / EH, eh = item - pl * EH;
+    T s = T(0);
+    if (pl < npl) {
+      const T* m = M + (pl * EH + eh) * ELS;
+      const T* tl = tL + pl * EL;
+      for (int el = 0; el < EL; ++el) s = fma(m[el], tl[el], s);
+    }
+    wH[item] = s;
+  }
+  __syncthreads();
+  for (int item = threadIdx.x; item < LPT * nf * Q; item += NTHREADS) {
+    const int pl = item / (nf * Q);
+    const int r = item - pl * nf * Q;
+    const int t = r / Q, q = r - t * Q;
+    if (pl >= npl) continue;
+    const bool in_hi = t < cnth;
+    const int cnt = in_hi ? cnth : cntl;
+    const int tt = in_hi ? t : t - cnth;
+    const int Eg = in_hi ? EH : EL;
+    const T* w = (in_hi ? wH + pl * EH : wL + pl * EL);
+    const T* xr = xs + pl * xs_stride + (in_hi ? 0 : cnth) * Q;
+    int dstride = 1;
+    for (int u = 0; u < cnt - 1 - tt; ++u) dstride *= Q;
+    T s = T(0);
+    const int others = Eg / Q;
+    for (int oe = 0; oe < others; ++oe) {
+      const int lo_part = oe % dstride, hi_part = oe / dstride;
+      const int e = (hi_part * Q + q) * dstride + lo_part;
+      T v = w[e];
+      int ee = e;
+      for (int u = cnt - 1; u >= 0; --u) {
+        const int d = ee % Q;
+        ee /= Q;
+        if (u != tt) v *= xr[u * Q + d];
+      }
+      s += v;
+    }
+    dxp[((p0 + pl0 + pl) * g.n + (j0 + t)) * Q + q] = s;
+  }
+}
+
 // dx[c][b][h][w][q] = sum over the patches that contain pixel (h, w) of dxp[p][j(dh,dw,c)][q]
 template <typename T>
 __global__ void gather_dx_kernel(EpsGeom g, const T* __restrict__ dxp, T* __restrict__ dx) {
@@ -561,6 +668,16 @@ int launch_loo(const EpsGeom& g, const T* x, const T* dkr, long long p0, int np,
   const int j0 = half ? g.m : 0, cnth = half ? g.b_nh : g.a_nh, cntl = half ? g.b_nl : g.a_nl;
   const int EH = half ? g.BH : g.AH, EL = half ? g.BL : g.AL;
   const int nf = cnth + cntl;
+  {
+    const size_t ssm = ((size_t)LPT * EH * (EL | 1) + (size_t)LPT * 2 * (EH + EL) + (size_t)LPT * ((nf * g.Q) | 1)) * sizeof(T) + 16;
+    if (ssm <= 100 * 1024) {   // at least two CTAs per SM
+      DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(loo_staged_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+      loo_staged_kernel<T><<<(np + LPT - 1) / LPT, NTHREADS, ssm, st>>>(g, x, dkr, p0, np, j0, cnth, EH, cntl, EL, dxp);
+      dctn_count_launch();
+      DCTN_CUDA_CHECK_RET(cudaGetLastError());
+      return 0;
+    }
+  }
   size_t smem = ((size_t)PT * 2 * (EH + EL) + (size_t)PT * ((nf * g.Q) | 1)) * sizeof(T) + 16;
   if (smem > SMEM_LIMIT) return dctn_set_error(-2, "leave-one-out kernel needs %zu bytes of shared memory", smem);
   DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(loo_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
