@@ -390,3 +390,81 @@ def test_tc_forward_and_input_grad_full_size_vs_fp64(B, H, W, Q, K, Oq):
     got_dx = _raw_call(_lib.WS_BACKWARD_INPUT, "tc3", core.to(DEV), x.to(DEV), gout.to(DEV))
     print(f"tc3 input-grad full-size rel err {rel_err(got_dx, want_dx):.3e}")
     assert rel_err(got_dx, want_dx) <= 1e-5
+
+
+# ---------------------------------------------------------------- direct (tiny-core) kernels and the host-buffer entry
+DIRECT_SHAPES = [
+    # (C, B, H, W, Q, K, O)
+    (1, 7, 28, 28, 2, 2, 2),    # config-1 layer shape (warp-row kernel, compile-time Q_out)
+    (1, 3, 9, 40, 2, 2, 5),     # W > 32: two column tiles; odd Q_out (runtime path)
+    (1, 2, 6, 7, 3, 2, 6),      # Q = 3
+    (1, 2, 8, 8, 4, 2, 23),     # CIFAR layer-1 shape (generic thread-per-patch kernel)
+    (1, 2, 7, 6, 2, 3, 4),      # K = 3, Q = 2: 5 + 4 factors
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("shape", DIRECT_SHAPES)
+def test_direct_kernels_vs_oracle(shape, dtype):
+    from dctn_b200 import _lib
+
+    C, B, H, W, Q, K, Oq = shape
+    g = torch.Generator().manual_seed(31)
+    n = K * K * C
+    x = (torch.randn(C, B, H, W, Q, dtype=torch.float64, generator=g) * 0.9).to(dtype).double()
+    core = (torch.randn(*(Q,) * n, Oq, dtype=torch.float64, generator=g) * Q ** (-n / 2)).to(dtype).double()
+    gout = torch.randn(B, H - K + 1, W - K + 1, Oq, dtype=torch.float64, generator=g).to(dtype).double()
+    want = O.eps_4step(core, x)
+    want_dcore, want_dx = O.eps_grads(core, x, gout)
+    xd, cd, gd = x.to(DEV, dtype), core.to(DEV, dtype), gout.to(DEV, dtype)
+    tol = TOL[dtype]
+    assert rel_err(_raw_call(_lib.WS_FORWARD, "direct", cd, xd, gd), want) <= tol
+    assert rel_err(_raw_call(_lib.WS_BACKWARD_CORE, "direct", cd, xd, gd), want_dcore) <= tol
+    assert rel_err(_raw_call(_lib.WS_BACKWARD_INPUT, "direct", cd, xd, gd), want_dx) <= tol
+
+
+def test_forward_host_entry():
+    """dctn_eps_forward_host: host buffers in, host buffer out (copies inside), against the oracle."""
+    import ctypes
+
+    from dctn_b200 import _lib
+    from dctn_b200 import eps as E
+
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(1, 4, 9, 8, 2, generator=g)
+    core = torch.randn(*(2,) * 9, 4, generator=g) * 2 ** -4.5
+    want = O.eps_4step(core.double(), x.double())
+    plan = E._plan(1, 3, 2, 4, torch.float32, _lib.VARIANT_AUTO)
+    lib = _lib.lib()
+    nbytes = lib.dctn_eps_forward_host_device_bytes(plan, 4, 9, 8)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    out = torch.empty(4, 7, 6, 4)
+    rc = lib.dctn_eps_forward_host(plan, x.data_ptr(), core.data_ptr(), out.data_ptr(), 4, 9, 8, scratch.data_ptr(), nbytes,
+                                   torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, _lib.last_error()
+    assert rel_err(out, want) <= 1e-5
+    # too small a scratch buffer is reported, not overrun
+    assert lib.dctn_eps_forward_host(plan, x.data_ptr(), core.data_ptr(), out.data_ptr(), 4, 9, 8, scratch.data_ptr(), 16,
+                                     torch.cuda.current_stream().cuda_stream) == -3
+
+
+@pytest.mark.parametrize("specs,Q0,img", [(((2, 6), (2, 24)), 4, 12), (((2, 12), (2, 24)), 4, 10)])
+def test_cifar_shaped_model_vs_oracle(specs, Q0, img):
+    """Config 4 shapes (Q_0 = 4, layers (2,6|12),(2,24)) at a reduced image size: logits and all gradients vs the oracle."""
+    from dctn_b200.eps_plus_linear import EPSesPlusLinear, UnitTheoreticalOutputStd
+
+    torch.manual_seed(51)
+    model = EPSesPlusLinear(specs, UnitTheoreticalOutputStd(), 1.0, torch.device(DEV), torch.float32, image_size=img, Q_0=Q0)
+    x = torch.randn(1, 5, img, img, Q0) * 0.8
+    y = torch.randint(0, 10, (5,))
+    logits = model(x.to(DEV))
+    torch.nn.functional.cross_entropy(logits, y.to(DEV)).backward()
+    cores = [c.detach().double().cpu().requires_grad_(True) for c in model.epses]
+    w = model.linear.weight.detach().double().cpu().requires_grad_(True)
+    b = model.linear.bias.detach().double().cpu().requires_grad_(True)
+    ref = O.eps_plus_linear_forward(cores, w, b, x.double())
+    torch.nn.functional.cross_entropy(ref, y).backward()
+    assert rel_err(logits, ref) <= 1e-5
+    for i, c in enumerate(cores):
+        assert rel_err(model.epses[i].grad, c.grad) <= 1e-5
+    assert rel_err(model.linear.weight.grad, w.grad) <= 1e-5
