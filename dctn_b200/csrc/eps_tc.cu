@@ -58,6 +58,7 @@ struct TcDcoreArgs {
   float* part;          // [splits][A][N]
   long long per_split;  // multiple of CH
   int passes;           // 3 (fp32-accurate) or 1
+  int three;            // 1: B rows are the 3-level product BH * BL * gout (separate BL and gout tables)
   long long* dbg;       // optional per-CTA cycle counters (16 per CTA)
 };
 
@@ -69,28 +70,31 @@ struct TileTables {
   int bh0, nbh;   // first needed BH entry and count
   int te;         // total entries: nah + AL + nbh + BL*O
 };
-__host__ __device__ inline TileTables tile_tables(const EpsGeom& g, int a0, int n0) {
+// number of entries of the last table section: BL*O (lo group x gout, two-level) or BL + O (three-level)
+__host__ __device__ inline int last_section(const EpsGeom& g, int three) { return three ? g.BL + g.O : g.BL * g.O; }
+__host__ __device__ inline TileTables tile_tables(const EpsGeom& g, int a0, int n0, int three) {
   TileTables t;
   const int BLO = g.BL * g.O;
   int a1 = a0 + BM - 1; if (a1 > g.A - 1) a1 = g.A - 1;
   int n1 = n0 + BN - 1; if (n1 > g.N - 1) n1 = g.N - 1;
   t.ah0 = a0 / g.AL; t.nah = a1 / g.AL - t.ah0 + 1;
   t.bh0 = n0 / BLO;  t.nbh = n1 / BLO - t.bh0 + 1;
-  t.te = t.nah + g.AL + t.nbh + BLO;
+  t.te = t.nah + g.AL + t.nbh + last_section(g, three);
   return t;
 }
 // upper bound of TileTables::te over all tiles
-inline int max_tile_entries(const EpsGeom& g) {
+inline int max_tile_entries(const EpsGeom& g, int three) {
   const int BLO = g.BL * g.O;
   int nah = (BM + g.AL - 1) / g.AL + 1; if (nah > g.AH) nah = g.AH;
   int nbh = (BN + BLO - 1) / BLO + 1;   if (nbh > g.BH) nbh = g.BH;
-  return nah + g.AL + nbh + BLO;
+  return nah + g.AL + nbh + last_section(g, three);
 }
 
 // tables[chunk][entry][i] for patch p = chunk*64 + i (zeros past P): entries [0,AH): first-half hi group,
-// [AH, AH+AL): first-half lo group, then [.., +BH): second-half hi group, then BL*O: second-half lo group x gout.
+// [AH, AH+AL): first-half lo group, then [.., +BH): second-half hi group, then either BL*O entries (second-half lo group
+// x gout) or, three-level, BL entries (lo group) followed by O entries (gout).
 __global__ void __launch_bounds__(256) build_tables_kernel(EpsGeom g, const float* __restrict__ x,
-                                                           const float* __restrict__ gout, float* __restrict__ tables) {
+                                                           const float* __restrict__ gout, float* __restrict__ tables, int three) {
   extern __shared__ float bt_smem[];
   const int Q = g.Q, O = g.O, NX = g.n * Q;
   float* xs = bt_smem;             // [NX][64]
@@ -104,8 +108,7 @@ __global__ void __launch_bounds__(256) build_tables_kernel(EpsGeom g, const floa
     xs[idx] = v;
   }
   __syncthreads();
-  const int BLO = g.BL * O;
-  const int ENT = g.AH + g.AL + g.BH + BLO;
+  const int ENT = g.AH + g.AL + g.BH + last_section(g, three);
   float* out = tables + (long long)blockIdx.x * ENT * TS_;
   for (int idx = threadIdx.x; idx < ENT * CH; idx += blockDim.x) {
     const int i = idx & (CH - 1), t = idx >> 6;
@@ -116,7 +119,10 @@ __global__ void __launch_bounds__(256) build_tables_kernel(EpsGeom g, const floa
     else if (t < g.AH + g.AL + g.BH) { e = t - g.AH - g.AL; j0 = g.m; cnt = g.b_nh; }
     else {
       const int k = t - (g.AH + g.AL + g.BH);
-      e = k / O; v = gs[(k - e * O) * CH + i]; j0 = g.m + g.b_nh; cnt = g.b_nl;
+      j0 = g.m + g.b_nh; cnt = g.b_nl;
+      if (!three) { e = k / O; v = gs[(k - e * O) * CH + i]; }     // lo group x gout
+      else if (k < g.BL) { e = k; }                                 // lo group alone
+      else { e = 0; cnt = 0; v = gs[(k - g.BL) * CH + i]; }         // gout row
     }
     for (int u = cnt - 1; u >= 0; --u) {
       const int d = e % Q;
@@ -129,6 +135,7 @@ __global__ void __launch_bounds__(256) build_tables_kernel(EpsGeom g, const floa
   for (int idx = threadIdx.x; idx < ENT * (TS_ - CH); idx += blockDim.x) out[(idx / (TS_ - CH)) * TS_ + CH + idx % (TS_ - CH)] = 0.f;
 }
 
+template <bool THREE>
 __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_constant__ TcDcoreArgs a) {
   extern __shared__ unsigned char smem_dyn[];
   const EpsGeom& g = a.g;
@@ -136,15 +143,17 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
   const int BLO = g.BL * O;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int a0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const TileTables tt = tile_tables(g, a0, n0);
+  const TileTables tt = tile_tables(g, a0, n0, THREE ? 1 : 0);
   const int TE = tt.te;
+  const int LAST = last_section(g, THREE ? 1 : 0);
 
   // ---- carve shared memory
   unsigned char* base = smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* stages = base;                                  // B operand: [STAGES][slab][hi|lo][128 rows x 128 B]
   float* tabs = (float*)(base + STAGES * STAGE_BYTES);           // [TSTAGES][TE][TS_]  table rows this tile needs
   float* zrow = tabs + TSTAGES * TE * TS_;                       // [TS_] zeros: padding operand rows multiply this
-  uint64_t* bars = (uint64_t*)(zrow + TS_);
+  float* onerow = zrow + TS_;                                    // [TS_] ones: third factor of rows that have none
+  uint64_t* bars = (uint64_t*)(onerow + TS_);
   uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 2 * TSTAGES + 2);
   const uint32_t bar_fullA0 = tc::smem_u32(bars), bar_fullB0 = bar_fullA0 + 8 * STAGES;
   const uint32_t bar_empty0 = bar_fullB0 + 8 * STAGES;           // one per stage: frees both the TMEM A stage and the smem B stage
@@ -172,7 +181,7 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
     tc::fence_barrier_init();
   }
   if (warp == 0) tc::tmem_alloc(tc::smem_u32(tmem_slot), 512);
-  for (int i = tid; i < TS_; i += NTHREADS_TC) zrow[i] = 0.f;
+  for (int i = tid; i < TS_; i += NTHREADS_TC) { zrow[i] = 0.f; onerow[i] = 1.f; }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -232,7 +241,7 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
   } else if (warp == 1 + NPROD_WARPS) {
     // =========================== table streamer ===========================
     if (lane == 0) {
-      const int ENT = g.AH + g.AL + g.BH + BLO;
+      const int ENT = g.AH + g.AL + g.BH + LAST;
       const uint32_t row_b = TS_ * 4;
       const uint32_t bytes = (uint32_t)TE * row_b;
       const long long chunk0 = pbeg / CH;     // per_split is a multiple of CH
@@ -247,7 +256,7 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
         tc::bulk_g2s(dst, src + (long long)tt.ah0 * TS_, (uint32_t)tt.nah * row_b, bar);
         tc::bulk_g2s(dst + (uint32_t)tt.nah * row_b, src + (long long)g.AH * TS_, (uint32_t)g.AL * row_b, bar);
         tc::bulk_g2s(dst + (uint32_t)(tt.nah + g.AL) * row_b, src + (long long)(g.AH + g.AL + tt.bh0) * TS_, (uint32_t)tt.nbh * row_b, bar);
-        tc::bulk_g2s(dst + (uint32_t)(tt.nah + g.AL + tt.nbh) * row_b, src + (long long)(g.AH + g.AL + g.BH) * TS_, (uint32_t)BLO * row_b, bar);
+        tc::bulk_g2s(dst + (uint32_t)(tt.nah + g.AL + tt.nbh) * row_b, src + (long long)(g.AH + g.AL + g.BH) * TS_, (uint32_t)LAST * row_b, bar);
         if (++ts == TSTAGES) { ts = 0; ph ^= 1; }
       }
     }
@@ -258,20 +267,27 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
     const int row = is_a ? quad * 32 + lane : (pw - 4) * 32 + lane;
     // loop-invariant table rows of this thread's operand row (padding rows multiply the all-zero table row)
-    int e_hi = TE, e_lo = TE;
+    int e_hi = TE, e_lo = TE, e_g = -1;   // e_g: gout table row (three-level B rows only)
     if (is_a) {
       const int ai = a0 + row;
       if (ai < g.A) { e_hi = ai / g.AL - tt.ah0; e_lo = tt.nah + ai % g.AL; }
     } else {
       const int ni = n0 + row;
-      if (ni < g.N) { e_hi = tt.nah + g.AL + (ni / BLO - tt.bh0); e_lo = tt.nah + g.AL + tt.nbh + ni % BLO; }
+      if (ni < g.N) {
+        const int base = tt.nah + g.AL + tt.nbh, rem = ni % BLO;
+        e_hi = tt.nah + g.AL + (ni / BLO - tt.bh0);
+        if (THREE) { e_lo = base + rem / O; e_g = base + g.BL + rem % O; }
+        else e_lo = base + rem;
+      }
     }
     const float4* th4[TSTAGES];
     const float4* tl4[TSTAGES];
+    const float4* tg4[TSTAGES];
 #pragma unroll
     for (int b = 0; b < TSTAGES; ++b) {
       th4[b] = (const float4*)(e_hi < TE ? tabs + (b * TE + e_hi) * TS_ : zrow);
       tl4[b] = (const float4*)(e_lo < TE ? tabs + (b * TE + e_lo) * TS_ : zrow);
+      tg4[b] = (const float4*)(e_g >= 0 ? tabs + (b * TE + e_g) * TS_ : onerow);
     }
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const uint32_t brow_off = (uint32_t)(row * 128);
@@ -313,6 +329,7 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
       long long q1 = TCD_CLK(), q2 = q1, q3 = q1, q4 = q1;
       const float4* th = th4[ts];
       const float4* tl = tl4[ts];
+      const float4* tg = tg4[ts];
       // (2) one operand row per thread; wait until the MMAs that read this stage two chunks ago are done
       tc::mbar_wait(bar_empty0 + 8 * s, phe);
       long long q5 = TCD_CLK();
@@ -322,7 +339,12 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
         float hi[32], lo[32];
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4) {
-          const float4 h4 = th[sl * 8 + q4], l4 = tl[sl * 8 + q4];
+          float4 h4 = th[sl * 8 + q4];
+          const float4 l4 = tl[sl * 8 + q4];
+          if (THREE) {
+            const float4 g4 = tg[sl * 8 + q4];
+            h4.x *= g4.x; h4.y *= g4.y; h4.z *= g4.z; h4.w *= g4.w;
+          }
           tc::split_tf32(h4.x * l4.x, hi[4 * q4 + 0], lo[4 * q4 + 0]);
           tc::split_tf32(h4.y * l4.y, hi[4 * q4 + 1], lo[4 * q4 + 1]);
           tc::split_tf32(h4.z * l4.z, hi[4 * q4 + 2], lo[4 * q4 + 2]);
@@ -393,13 +415,19 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
   if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
 }
 
-size_t dcore_tc_smem(const EpsGeom& g) {
-  const int TE = max_tile_entries(g);
-  return 1024 + (size_t)STAGES * STAGE_BYTES + (size_t)(TSTAGES * TE + 1) * TS_ * 4 + (3 * STAGES + 2 * TSTAGES + 2) * 8 + 16;
+size_t dcore_tc_smem(const EpsGeom& g, int three) {
+  const int TE = max_tile_entries(g, three);
+  return 1024 + (size_t)STAGES * STAGE_BYTES + (size_t)(TSTAGES * TE + 2) * TS_ * 4 + (3 * STAGES + 2 * TSTAGES + 2) * 8 + 16;
 }
-inline size_t table_floats(const EpsGeom& g) {
+// two-level B rows when their tables fit in shared memory, else three-level; -1: neither fits
+inline int pick_three(const EpsGeom& g) {
+  if (dcore_tc_smem(g, 0) <= TC_SMEM_LIMIT) return 0;
+  if (dcore_tc_smem(g, 1) <= TC_SMEM_LIMIT) return 1;
+  return -1;
+}
+inline size_t table_floats(const EpsGeom& g, int three) {
   const long long nchunks = (g.P + CH - 1) / CH;
-  return (size_t)nchunks * (size_t)(g.AH + g.AL + g.BH + g.BL * g.O) * TS_;
+  return (size_t)nchunks * (size_t)(g.AH + g.AL + g.BH + last_section(g, three)) * TS_;
 }
 
 inline void dcore_split(const EpsGeom& g, long long* per_split, int* splits) {
@@ -423,7 +451,7 @@ bool tc_supported(const EpsGeom& g, int kind) {
   if (g.P >= (1ll << 31) / (g.Q > g.O ? g.Q : g.O)) return false;  // 32-bit patch index math
   if (g.A < 64 || g.N < 64) return false;    // tiles would be mostly padding: the CUDA-core family is the better fit
   if (g.P < 4096) return false;              // tiny reductions are launch-bound either way
-  return dcore_tc_smem(g) <= TC_SMEM_LIMIT;
+  return pick_three(g) >= 0;
 }
 
 size_t tc_workspace_bytes(const EpsGeom& g, int kind) {
@@ -431,17 +459,19 @@ size_t tc_workspace_bytes(const EpsGeom& g, int kind) {
     long long per;
     int splits;
     dcore_split(g, &per, &splits);
-    return ((size_t)splits * g.A * g.N + table_floats(g)) * sizeof(float) + 256;
+    const int three = pick_three(g);
+    return ((size_t)splits * g.A * g.N + table_floats(g, three < 0 ? 0 : three)) * sizeof(float) + 256;
   }
   return tcg_workspace_bytes(g, kind);
 }
 
 int tc_backward_core(const EpsGeom& g, const float* x, const float* gout, float* dcore, void* ws, int passes,
                      cudaStream_t st) {
-  size_t smem = dcore_tc_smem(g);
-  if (smem > TC_SMEM_LIMIT) return dctn_set_error(-2, "tcgen05 core-gradient kernel needs %zu bytes of shared memory", smem);
+  const int three = pick_three(g);
+  if (three < 0) return dctn_set_error(-2, "tcgen05 core-gradient kernel: tables of this shape do not fit in shared memory");
+  const size_t smem = dcore_tc_smem(g, three);
   TcDcoreArgs a{};
-  a.g = g; a.part = (float*)ws; a.passes = passes;
+  a.g = g; a.part = (float*)ws; a.passes = passes; a.three = three;
   int splits;
   dcore_split(g, &a.per_split, &splits);
   float* tables = a.part + (((size_t)splits * g.A * g.N + 63) & ~(size_t)63);
@@ -450,11 +480,12 @@ int tc_backward_core(const EpsGeom& g, const float* x, const float* gout, float*
     const size_t bsm = (size_t)(g.n * g.Q + g.O) * CH * sizeof(float);
     if (bsm > 200 * 1024) return dctn_set_error(-2, "table kernel needs %zu bytes of shared memory", bsm);
     DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(build_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
-    build_tables_kernel<<<(unsigned)((g.P + CH - 1) / CH), 256, bsm, st>>>(g, x, gout, tables);
+    build_tables_kernel<<<(unsigned)((g.P + CH - 1) / CH), 256, bsm, st>>>(g, x, gout, tables, three);
     dctn_count_launch();
     DCTN_CUDA_CHECK_RET(cudaGetLastError());
   }
-  DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(tc_dcore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kern = three ? tc_dcore_kernel<true> : tc_dcore_kernel<false>;
+  DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((g.A + BM - 1) / BM, (g.N + BN - 1) / BN, splits);
   a.dbg = nullptr;
   static long long* dbg_buf = nullptr;
@@ -464,7 +495,7 @@ int tc_backward_core(const EpsGeom& g, const float* x, const float* gout, float*
     cudaMemsetAsync(dbg_buf, 0, 4096 * 16 * sizeof(long long), st);
     a.dbg = dbg_buf;
   }
-  tc_dcore_kernel<<<grid, NTHREADS_TC, smem, st>>>(a);
+  kern<<<grid, NTHREADS_TC, smem, st>>>(a);
   dctn_count_launch();
   DCTN_CUDA_CHECK_RET(cudaGetLastError());
   if (a.dbg) {

@@ -50,6 +50,7 @@ struct TcGemmArgs {
   long long p0;  // first patch handled by this launch
   int np;        // number of patches
   int jh0, cnth, KH, cntl, KLb, KL, Kdim, withG;  // generated operand (see GenGemmArgs in eps_ffma.cu)
+  int three;            // withG only: 1 = three-level product tabKH * tabKL(lo group alone) * gout instead of the folded table
   int Ncols, ntiles, nk;
   const float* packed;  // [ntiles][nk][2][BN*32]
   int BN;               // column-tile width: multiple of 16, <= MAX_BN
@@ -116,8 +117,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
   unsigned char* base = smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* stages = base;
   float* tabKH = (float*)(base + NB * STAGE_BYTES);    // [KH][128]
-  float* tabKL = tabKH + (a.KH + 1) * 128;             // [KL][128]   (row KH of tabKH is all zeros: padding k)
-  float* tabE = tabKL + a.KL * 128;                    // MODE_FWD: [BH + BL][128]; MODE_DKR2: gout [O][128]
+  float* tabKL = tabKH + (a.KH + 1) * 128;             // [KL][128] (row KH of tabKH is all zeros: padding k); three-level: [KLb][128]
+  const int nKL = a.three ? a.KLb : a.KL;
+  float* tabG = tabKL + nKL * 128;                     // three-level only: gout [O][128]
+  float* tabE = tabG + (a.three ? O * 128 : 0);        // MODE_FWD: [BH + BL][128]; MODE_DKR2: gout [O][128]
   const int nE = (MODE == MODE_FWD) ? (g.BH + g.BL) : (MODE == MODE_DKR2 ? O : 0);
   float* outs = tabE + nE * 128;                       // MODE_FWD: [O][128]
   // index tables that make the inner loops branch-free (every load address is known up front -> full ILP):
@@ -187,16 +190,18 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
       return v;
     };
     for (int idx = tid; idx < a.KH * 128; idx += G_THREADS) tabKH[idx] = kr_entry(a.jh0, a.cnth, idx >> 7, idx & 127);
-    for (int idx = tid; idx < a.KL * 128; idx += G_THREADS) {
+    for (int idx = tid; idx < nKL * 128; idx += G_THREADS) {
       const int pr = idx & 127, eo = idx >> 7;
       int e = eo;
       float gv = 1.f;
-      if (a.withG) {
+      if (a.withG && !a.three) {
         e = eo / O;
         gv = gsx[(eo - e * O) * 128 + pr];
       }
       tabKL[idx] = gv * kr_entry(a.jh0 + a.cnth, a.cntl, e, pr);
     }
+    if (a.three)
+      for (int idx = tid; idx < O * 128; idx += G_THREADS) tabG[idx] = gsx[idx];
     if (MODE == MODE_FWD) {
       for (int idx = tid; idx < g.BH * 128; idx += G_THREADS) tabE[idx] = kr_entry(g.m, g.b_nh, idx >> 7, idx & 127);
       for (int idx = tid; idx < g.BL * 128; idx += G_THREADS)
@@ -206,8 +211,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
     if (MODE == MODE_DKR2)
       for (int idx = tid; idx < O * 128; idx += G_THREADS) tabE[idx] = gsx[idx];
     if (tid < 128) tabKH[a.KH * 128 + tid] = 0.f;
-    for (int k = tid; k < nkidx; k += G_THREADS)
-      kidx[k] = (k < a.Kdim) ? ((uint32_t)(k / a.KL) | ((uint32_t)(k % a.KL) << 16)) : (uint32_t)a.KH;
+    for (int k = tid; k < nkidx; k += G_THREADS) {
+      uint32_t id = (uint32_t)a.KH;   // padding k: the all-zero row of tabKH
+      if (k < a.Kdim) {
+        const int kh = k / a.KL, kl = k % a.KL;
+        id = a.three ? ((uint32_t)kh | ((uint32_t)(kl / O) << 10) | ((uint32_t)(kl % O) << 20)) : ((uint32_t)kh | ((uint32_t)kl << 16));
+      }
+      kidx[k] = id;
+    }
     if (MODE == MODE_FWD)
       for (int b2 = tid; b2 < 2 * g.Bn; b2 += G_THREADS) {
         const int b = b2 % g.Bn;
@@ -311,8 +322,15 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
             const uint4 u = kp[q4];
             id[4 * q4] = u.x; id[4 * q4 + 1] = u.y; id[4 * q4 + 2] = u.z; id[4 * q4 + 3] = u.w;
           }
+          if (a.three) {
+            const float* tg = tabG + pr;
 #pragma unroll
-          for (int j = 0; j < GBK; ++j) tc::split_tf32(th[(id[j] & 0xFFFF) * 128] * tl[(id[j] >> 16) * 128], hi[j], lo[j]);
+            for (int j = 0; j < GBK; ++j)
+              tc::split_tf32(th[(id[j] & 0x3FF) * 128] * tl[((id[j] >> 10) & 0x3FF) * 128] * tg[(id[j] >> 20) * 128], hi[j], lo[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < GBK; ++j) tc::split_tf32(th[(id[j] & 0xFFFF) * 128] * tl[(id[j] >> 16) * 128], hi[j], lo[j]);
+          }
         }
         long long t0 = TCG_CLK();
         tc::mbar_wait(bar_emptyA0 + 8 * sa, phe);
@@ -453,7 +471,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
 
 // ------------------------------------------------------------------------------------------------ host side
 struct GemmShape {
-  int jh0, cnth, KH, cntl, KLb, KL, Kdim, withG, Ncols;
+  int jh0, cnth, KH, cntl, KLb, KL, Kdim, withG, Ncols, three;
 };
 
 inline GemmShape shape_for(const EpsGeom& g, int mode) {
@@ -465,22 +483,34 @@ inline GemmShape shape_for(const EpsGeom& g, int mode) {
     s.jh0 = 0; s.cnth = g.a_nh; s.KH = g.AH; s.cntl = g.a_nl; s.KLb = g.AL; s.KL = g.AL; s.Kdim = g.A;
     s.withG = 0; s.Ncols = g.N;
   }
+  s.three = 0;
   return s;
 }
 
 inline size_t gemm_fixed_smem(const EpsGeom& g, const GemmShape& s, int mode) {
   const int nE = (mode == MODE_FWD) ? (g.BH + g.BL) : (mode == MODE_DKR2 ? g.O : 0);
+  const size_t ktab = s.three ? (size_t)(s.KH + 1 + s.KLb + g.O) : (size_t)(s.KH + 1 + s.KL);
   const size_t nkidx = (size_t)((s.Kdim + GBK - 1) / GBK) * GBK;
   const size_t neidx = (mode == MODE_FWD) ? 2 * (size_t)g.Bn : (mode == MODE_DKR2 ? (size_t)MAX_BN : 0);
-  return 1024 + (size_t)(s.KH + 1 + s.KL + nE + (mode == MODE_FWD ? g.O : 0)) * 128 * 4 + (nkidx + neidx + 2) * 4 +
+  return 1024 + (ktab + nE + (mode == MODE_FWD ? g.O : 0)) * 128 * 4 + (nkidx + neidx + 2) * 4 +
          (2 * MAX_BSTAGES + 2 * ASTAGES + 2) * 8 + 16;
 }
 inline size_t bstage_bytes(int BN) { return 2 * (size_t)BN * GBK * 4; }
 
+inline size_t gemm_fixed_smem(const EpsGeom& g, const GemmShape& s, int mode);
+inline size_t bstage_bytes(int BN);
+// two-level generated operand when its tables leave room for at least two 64-column stages, else (gout-folded operand
+// only) the three-level product
+inline GemmShape shape_auto(const EpsGeom& g, int mode) {
+  GemmShape s = shape_for(g, mode);
+  if (s.withG && gemm_fixed_smem(g, s, mode) + 2 * bstage_bytes(64) > TCG_SMEM_LIMIT && s.KH < 1024 && s.KLb < 1024 && g.O < 1024) s.three = 1;
+  return s;
+}
+
 // number of shared-memory B stages that fit (0 = does not fit); the setup scratch (x and gout of 128 patches)
 // is aliased onto the stages and must fit too
 inline int pick_bstages(const EpsGeom& g, int mode, int BN) {
-  const GemmShape s = shape_for(g, mode);
+  const GemmShape s = shape_auto(g, mode);
   const size_t fixed = gemm_fixed_smem(g, s, mode);
   if (fixed >= TCG_SMEM_LIMIT) return 0;
   int nb = (int)((TCG_SMEM_LIMIT - fixed) / bstage_bytes(BN));
@@ -493,7 +523,7 @@ inline int pick_bstages(const EpsGeom& g, int mode, int BN) {
 // pick the column-tile width (multiple of 16, <= MAX_BN): satisfies the epilogue's alignment (MODE_DKR2 needs whole
 // (b, o) groups per tile), fits shared memory with >= 2 stages, least padded width, then widest
 inline int pick_bn(const EpsGeom& g, int mode) {
-  const GemmShape s = shape_for(g, mode);
+  const GemmShape s = shape_auto(g, mode);
   int best = 0;
   long long best_cost = 0;
   for (int bn = MAX_BN; bn >= 64; bn -= 16) {
@@ -507,7 +537,7 @@ inline int pick_bn(const EpsGeom& g, int mode) {
 }
 
 inline size_t packed_floats(const EpsGeom& g, int mode, int BN) {
-  const GemmShape s = shape_for(g, mode);
+  const GemmShape s = shape_auto(g, mode);
   long long ntiles = (s.Ncols + BN - 1) / BN, nk = (s.Kdim + GBK - 1) / GBK;
   return (size_t)(ntiles * nk * 2 * BN * 32);
 }
@@ -536,10 +566,10 @@ int launch_gemm_inst(const TcGemmArgs& a, size_t smem, cudaStream_t st) {
 
 int run_gemm(const EpsGeom& g, int mode, int BN, const float* x, const float* gout, const float* packed, long long p0,
              int np, float* out, long long ldc, int passes, cudaStream_t st) {
-  const GemmShape s = shape_for(g, mode);
+  const GemmShape s = shape_auto(g, mode);
   TcGemmArgs a{};
   a.g = g; a.x = x; a.gout = gout; a.p0 = p0; a.np = np;
-  a.jh0 = s.jh0; a.cnth = s.cnth; a.KH = s.KH; a.cntl = s.cntl; a.KLb = s.KLb; a.KL = s.KL; a.Kdim = s.Kdim; a.withG = s.withG;
+  a.jh0 = s.jh0; a.cnth = s.cnth; a.KH = s.KH; a.cntl = s.cntl; a.KLb = s.KLb; a.KL = s.KL; a.Kdim = s.Kdim; a.withG = s.withG; a.three = s.three;
   a.Ncols = s.Ncols; a.ntiles = (s.Ncols + BN - 1) / BN; a.nk = (s.Kdim + GBK - 1) / GBK;
   a.packed = packed; a.BN = BN; a.bstages = pick_bstages(g, mode, BN); a.passes = passes; a.out = out; a.ldc = ldc;
   a.dbg = nullptr;
@@ -572,7 +602,7 @@ int run_gemm(const EpsGeom& g, int mode, int BN, const float* x, const float* go
 }
 
 int run_pack(const EpsGeom& g, int mode, int BN, const float* core, float* dst, int passes, cudaStream_t st) {
-  const GemmShape s = shape_for(g, mode);
+  const GemmShape s = shape_auto(g, mode);
   const int ntiles = (s.Ncols + BN - 1) / BN, nk = (s.Kdim + GBK - 1) / GBK;
   long long total = (long long)ntiles * nk * BN * 8;
   int blocks = (int)((total + 255) / 256);
