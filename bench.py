@@ -241,11 +241,21 @@ def kernel_rooflines(model, specs, image_size, Q0, batch, dev, flush):
         lib = _lib.lib()
         st = torch.cuda.current_stream().cuda_stream
         ws = [torch.empty(lib.dctn_eps_workspace_bytes(plan, B, H, H, k), dtype=torch.uint8, device=dev) for k in range(3)]
+        nsave = lib.dctn_eps_saved_bytes(plan, B, H, H) if li > 0 else 0
+        use_saved = 0 < nsave <= E._save_limit_bytes          # what EpsFunction does in the training step
+        saved = torch.empty(max(nsave, 1), dtype=torch.uint8, device=dev) if use_saved else None
+        ws_saved = torch.empty(lib.dctn_eps_workspace_bytes(plan, B, H, H, 3), dtype=torch.uint8, device=dev) if use_saved else None
+        if use_saved:
+            fwd = lambda: lib.dctn_eps_forward_train(plan, x.data_ptr(), core.data_ptr(), out.data_ptr(), saved.data_ptr(), nsave, B, H, H, ws[0].data_ptr(), ws[0].numel(), st)
+        else:
+            fwd = lambda: lib.dctn_eps_forward(plan, x.data_ptr(), core.data_ptr(), out.data_ptr(), B, H, H, ws[0].data_ptr(), ws[0].numel(), st)
         calls = {
-            "forward": (lambda: lib.dctn_eps_forward(plan, x.data_ptr(), core.data_ptr(), out.data_ptr(), B, H, H, ws[0].data_ptr(), ws[0].numel(), st), 1),
+            "forward": (fwd, 1),
             "backward_core": (lambda: lib.dctn_eps_backward_core(plan, x.data_ptr(), gout.data_ptr(), dcore.data_ptr(), B, H, H, ws[1].data_ptr(), ws[1].numel(), st), 1),
         }
-        if li > 0:
+        if li > 0 and use_saved:   # one GEMM (dKR1) + a streaming pass over the saved T
+            calls["backward_input"] = (lambda: lib.dctn_eps_backward_input_saved(plan, x.data_ptr(), core.data_ptr(), gout.data_ptr(), saved.data_ptr(), nsave, dx.data_ptr(), B, H, H, ws_saved.data_ptr(), ws_saved.numel(), st), 1)
+        elif li > 0:               # two GEMMs (dKR1, and T recomputed for dKR2)
             calls["backward_input"] = (lambda: lib.dctn_eps_backward_input(plan, x.data_ptr(), core.data_ptr(), gout.data_ptr(), dx.data_ptr(), B, H, H, ws[2].data_ptr(), ws[2].numel(), st), 2)
         es = 4
         xbytes = B * H * H * d["Q"] * es

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libdctn_b200.so")
 F32, F64 = 0, 1
 VARIANT_AUTO, VARIANT_FFMA, VARIANT_TC3, VARIANT_TC1, VARIANT_DIRECT = 0, 1, 2, 3, 4
 VARIANTS = {"auto": 0, "ffma": 1, "tc3": 2, "tc1": 3, "direct": 4}
-WS_FORWARD, WS_BACKWARD_CORE, WS_BACKWARD_INPUT = 0, 1, 2
+WS_FORWARD, WS_BACKWARD_CORE, WS_BACKWARD_INPUT, WS_BACKWARD_INPUT_SAVED = 0, 1, 2, 3
 
 # every symbol include/dctn_b200.h declares: (name, restype, argtypes)
 SYMBOLS = {
@@ -29,6 +29,9 @@ SYMBOLS = {
     "dctn_eps_forward": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p, c_size_t, c_void_p]),
     "dctn_eps_backward_core": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p, c_size_t, c_void_p]),
     "dctn_eps_backward_input": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p, c_size_t, c_void_p]),
+    "dctn_eps_saved_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
+    "dctn_eps_forward_train": (c_int, [c_void_p] * 5 + [c_size_t] + [c_int] * 3 + [c_void_p, c_size_t, c_void_p]),
+    "dctn_eps_backward_input_saved": (c_int, [c_void_p] * 5 + [c_size_t, c_void_p] + [c_int] * 3 + [c_void_p, c_size_t, c_void_p]),
     "dctn_logmatmulexp_forward": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p]),
     "dctn_logmatmulexp_backward": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_void_p]),
     "dctn_eps_forward_host_device_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),

@@ -157,7 +157,8 @@ extern "C" size_t dctn_eps_workspace_bytes(const dctn_plan_t* pl, int B, int H, 
   if (check_call(pl, B, H, W)) return 0;
   EpsGeom g;
   fill_geom(pl, B, H, W, &g);
-  int fam = pick_family(pl, g, kind);
+  int fam = pick_family(pl, g, kind == DCTN_WS_BACKWARD_INPUT_SAVED ? DCTN_WS_BACKWARD_INPUT : kind);
+  if (kind == DCTN_WS_BACKWARD_INPUT_SAVED && fam != FAM_TC) return 256;
   size_t bytes = 0;
   if (fam == FAM_FFMA) bytes = pl->dtype == DCTN_F32 ? ffma_workspace_bytes<float>(g, kind) : ffma_workspace_bytes<double>(g, kind);
   else if (fam == FAM_TC) bytes = tc_workspace_bytes(g, kind);
@@ -232,6 +233,54 @@ extern "C" int dctn_eps_backward_input(const dctn_plan_t* pl, const void* x, con
   return pl->dtype == DCTN_F32
              ? ffma_backward_input<float>(g, (const float*)x, (const float*)core, (const float*)gout, (float*)dx, ws, st)
              : ffma_backward_input<double>(g, (const double*)x, (const double*)core, (const double*)gout, (double*)dx, ws, st);
+}
+
+// ------------------------------------------------------------------------------------------------ training forward
+// Only the tcgen05 GEMM family has an intermediate worth keeping (its forward and the second half of its input
+// gradient are the same GEMM); every other family reports 0 and the caller uses the plain entry points.
+static bool saved_path(const dctn_plan_t* pl, const EpsGeom& g) {
+  return pl->dtype == DCTN_F32 && pick_family(pl, g, DCTN_WS_FORWARD) == FAM_TC &&
+         pick_family(pl, g, DCTN_WS_BACKWARD_INPUT) == FAM_TC && tc_supported(g, DCTN_WS_BACKWARD_INPUT_SAVED);
+}
+
+extern "C" size_t dctn_eps_saved_bytes(const dctn_plan_t* pl, int B, int H, int W) {
+  if (check_call(pl, B, H, W)) return 0;
+  EpsGeom g;
+  fill_geom(pl, B, H, W, &g);
+  return saved_path(pl, g) ? tcg_saved_bytes(g) : 0;
+}
+
+extern "C" int dctn_eps_forward_train(const dctn_plan_t* pl, const void* x, const void* core, void* out, void* saved,
+                                      size_t saved_bytes, int B, int H, int W, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_call(pl, B, H, W);
+  if (rc) return rc;
+  if (!x || !core || !out || !saved) return dctn_set_error(DCTN_ERR_BAD_ARG, "forward_train: null tensor pointer");
+  if ((rc = check_ws(pl, B, H, W, DCTN_WS_FORWARD, ws, ws_bytes))) return rc;
+  EpsGeom g;
+  fill_geom(pl, B, H, W, &g);
+  if (!saved_path(pl, g))
+    return dctn_set_error(DCTN_ERR_UNSUPPORTED, "forward_train: no savable intermediate for this plan/shape (dctn_eps_saved_bytes() == 0): %s", pl->desc.c_str());
+  if (saved_bytes < tcg_saved_bytes(g))
+    return dctn_set_error(DCTN_ERR_WORKSPACE, "forward_train: saved buffer of %zu bytes needed, got %zu", tcg_saved_bytes(g), saved_bytes);
+  return tc_forward(g, (const float*)x, (const float*)core, (float*)out, ws, pl->variant == DCTN_VARIANT_TC1 ? 1 : 3,
+                    (cudaStream_t)stream, (float*)saved);
+}
+
+extern "C" int dctn_eps_backward_input_saved(const dctn_plan_t* pl, const void* x, const void* core, const void* gout,
+                                             const void* saved, size_t saved_bytes, void* dx, int B, int H, int W,
+                                             void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_call(pl, B, H, W);
+  if (rc) return rc;
+  if (!x || !core || !gout || !saved || !dx) return dctn_set_error(DCTN_ERR_BAD_ARG, "backward_input_saved: null tensor pointer");
+  EpsGeom g;
+  fill_geom(pl, B, H, W, &g);
+  if (!saved_path(pl, g))
+    return dctn_set_error(DCTN_ERR_UNSUPPORTED, "backward_input_saved: no savable intermediate for this plan/shape: %s", pl->desc.c_str());
+  if (saved_bytes < tcg_saved_bytes(g))
+    return dctn_set_error(DCTN_ERR_WORKSPACE, "backward_input_saved: saved buffer of %zu bytes needed, got %zu", tcg_saved_bytes(g), saved_bytes);
+  if ((rc = check_ws(pl, B, H, W, DCTN_WS_BACKWARD_INPUT_SAVED, ws, ws_bytes))) return rc;
+  return tc_backward_input_saved(g, (const float*)x, (const float*)core, (const float*)gout, (const float*)saved, (float*)dx,
+                                 ws, pl->variant == DCTN_VARIANT_TC1 ? 1 : 3, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------ logmatmulexp

@@ -29,7 +29,10 @@ template <typename T> int direct_backward(const EpsGeom& g, int kind, const T* x
 // ---- tcgen05 TF32 family (eps_tc.cu): float only, large cores
 bool tc_supported(const EpsGeom& g, int kind);
 size_t tc_workspace_bytes(const EpsGeom& g, int kind);
-int tc_forward(const EpsGeom& g, const float* x, const float* core, float* out, void* ws, int passes, cudaStream_t st);
+// tsave != nullptr: also store the GEMM rows T[P][N] (column order (o, b)) for tc_backward_input_saved
+int tc_forward(const EpsGeom& g, const float* x, const float* core, float* out, void* ws, int passes, cudaStream_t st, float* tsave = nullptr);
+size_t tcg_saved_bytes(const EpsGeom& g);
+int tc_backward_input_saved(const EpsGeom& g, const float* x, const float* core, const float* gout, const float* tsaved, float* dx, void* ws, int passes, cudaStream_t st);
 // eps_tc_gemm.cu: forward / input-gradient GEMMs on tcgen05 (A generated on chip, core streamed by bulk copies)
 bool tcg_supported(const EpsGeom& g, int kind);
 size_t tcg_workspace_bytes(const EpsGeom& g, int kind);

@@ -58,6 +58,7 @@ struct TcGemmArgs {
   int passes;
   float* out;           // MODE_STORE: [np][ldc]; MODE_FWD: out[P][O] (absolute patches); MODE_DKR2: [np][Bn]
   long long ldc;
+  float* tsave;         // MODE_FWD, training: the accumulator rows T[p][(o, b)] are also stored here, [P][Ncols]
   long long* dbg;       // optional per-CTA cycle counters (DCTN_TCG_DEBUG): 8 per CTA
 };
 
@@ -400,6 +401,18 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
             }
           }
         } else if (MODE == MODE_FWD) {
+          if (a.tsave != nullptr && pvalid) {   // keep T for the input gradient (dctn_eps_forward_train)
+            float* trow = a.tsave + (pt0 + pr) * (long long)a.Ncols;
+            const int nb = n0 + cb;
+            if (cb + 32 <= BN && nb + 32 <= a.Ncols && (a.Ncols & 3) == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) *(float4*)(trow + nb + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (cb + i < BN && nb + i < a.Ncols) trow[nb + i] = v[i];
+            }
+          }
           // columns cb..cb+31 are b = fb, fb+1, ... (wrapping to the next o at b == Bn; Bn >= 32: at most one wrap)
           int nvalid = BN - cb;
           if (a.Ncols - n0 - cb < nvalid) nvalid = a.Ncols - n0 - cb;
@@ -542,8 +555,10 @@ inline size_t packed_floats(const EpsGeom& g, int mode, int BN) {
   return (size_t)(ntiles * nk * 2 * BN * 32);
 }
 
+// patches per launch of the input-gradient GEMMs: their outputs dKR1 / dKR2 go through a scratch buffer of at most
+// 2 GiB (HBM write + read at ~6.5 TB/s costs far less than the launch gaps and partial waves of many small chunks)
 inline long long dx_patch_chunk(const EpsGeom& g) {
-  long long target = 96ll << 20;
+  long long target = 2048ll << 20;
   long long pc = target / (((long long)g.A + g.Bn) * 4);
   if (pc < 4096) pc = 4096;
   // whole waves: one CTA per 128 patches, 148 CTAs resident at a time
@@ -565,13 +580,14 @@ int launch_gemm_inst(const TcGemmArgs& a, size_t smem, cudaStream_t st) {
 }
 
 int run_gemm(const EpsGeom& g, int mode, int BN, const float* x, const float* gout, const float* packed, long long p0,
-             int np, float* out, long long ldc, int passes, cudaStream_t st) {
+             int np, float* out, long long ldc, int passes, cudaStream_t st, float* tsave = nullptr) {
   const GemmShape s = shape_auto(g, mode);
   TcGemmArgs a{};
   a.g = g; a.x = x; a.gout = gout; a.p0 = p0; a.np = np;
   a.jh0 = s.jh0; a.cnth = s.cnth; a.KH = s.KH; a.cntl = s.cntl; a.KLb = s.KLb; a.KL = s.KL; a.Kdim = s.Kdim; a.withG = s.withG; a.three = s.three;
   a.Ncols = s.Ncols; a.ntiles = (s.Ncols + BN - 1) / BN; a.nk = (s.Kdim + GBK - 1) / GBK;
   a.packed = packed; a.BN = BN; a.bstages = pick_bstages(g, mode, BN); a.passes = passes; a.out = out; a.ldc = ldc;
+  a.tsave = tsave;
   a.dbg = nullptr;
   static long long* dbg_buf = nullptr;
   const char* dbg_env = getenv("DCTN_TCG_DEBUG");
@@ -626,48 +642,106 @@ bool tcg_supported(const EpsGeom& g, int kind) {
   if (!common_ok(g)) return false;
   if (kind == 0) return g.Bn >= 32 && pick_bn(g, MODE_FWD) != 0;
   if (kind == 2) return (g.n - g.m) > 0 && pick_bn(g, MODE_STORE) != 0 && pick_bn(g, MODE_DKR2) != 0;
+  if (kind == 3) return (g.n - g.m) > 0 && g.Bn >= 32 && pick_bn(g, MODE_FWD) != 0 && pick_bn(g, MODE_STORE) != 0;
   return false;
 }
 
 size_t tcg_workspace_bytes(const EpsGeom& g, int kind) {
   if (kind == 0) return packed_floats(g, MODE_FWD, pick_bn(g, MODE_FWD)) * 4 + 256;
-  if (kind == 2) {
+  if (kind == 2 || kind == 3) {
     const long long pc = dx_patch_chunk(g);
-    size_t f = packed_floats(g, MODE_STORE, pick_bn(g, MODE_STORE)) + packed_floats(g, MODE_DKR2, pick_bn(g, MODE_DKR2)) +
-               (size_t)pc * ((size_t)g.A + g.Bn) + (size_t)g.P * g.n * g.Q;
+    size_t f = packed_floats(g, MODE_STORE, pick_bn(g, MODE_STORE)) + (size_t)pc * ((size_t)g.A + g.Bn) + (size_t)g.P * g.n * g.Q;
+    if (kind == 2) f += packed_floats(g, MODE_DKR2, pick_bn(g, MODE_DKR2));
     return f * 4 + 1024;
   }
   return 0;
 }
 
-int tc_forward(const EpsGeom& g, const float* x, const float* core, float* out, void* ws, int passes, cudaStream_t st) {
+int tc_forward(const EpsGeom& g, const float* x, const float* core, float* out, void* ws, int passes, cudaStream_t st,
+               float* tsave) {
   const int BN = pick_bn(g, MODE_FWD);
   if (!BN) return dctn_set_error(-2, "tcgen05 forward kernel does not support this shape");
   float* packed = (float*)ws;
   int rc = run_pack(g, MODE_FWD, BN, core, packed, passes, st);
   if (rc) return rc;
-  return run_gemm(g, MODE_FWD, BN, x, nullptr, packed, 0, (int)g.P, out, 0, passes, st);
+  return run_gemm(g, MODE_FWD, BN, x, nullptr, packed, 0, (int)g.P, out, 0, passes, st, tsave);
 }
 
-int tc_backward_input(const EpsGeom& g, const float* x, const float* core, const float* gout, float* dx, void* ws,
-                      int passes, cudaStream_t st) {
-  const int BN1 = pick_bn(g, MODE_STORE), BN2 = pick_bn(g, MODE_DKR2);
-  if (!BN1 || !BN2) return dctn_set_error(-2, "tcgen05 input-gradient kernels do not support this shape");
+size_t tcg_saved_bytes(const EpsGeom& g) { return (size_t)g.P * (size_t)g.N * sizeof(float); }
+
+namespace {
+// dKR2[p][b] = sum_o T[p][o*Bn + b] * gout[p][o] from the rows saved by the training forward; one thread per
+// (patch, 4 consecutive b): 128-bit coalesced reads of T (the only large stream: P*N floats, HBM-bound)
+__global__ void __launch_bounds__(256) dkr2_from_saved_kernel(const float* __restrict__ T, const float* __restrict__ gout,
+                                                              float* __restrict__ dkr2, long long p0, int np, int Bn, int O) {
+  const int b4n = Bn >> 2;
+  const long long total = (long long)np * b4n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int pl = (int)(i / b4n), b4 = (int)(i - (long long)pl * b4n);
+    const long long p = p0 + pl;
+    const float4* t = (const float4*)(T + p * (long long)Bn * O) + b4;
+    const float* gr = gout + p * O;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int o = 0; o < O; ++o) {
+      const float4 v = __ldcs(t + (long long)o * b4n);   // streamed once: do not keep in L2
+      const float gv = __ldg(gr + o);
+      s.x = fmaf(v.x, gv, s.x); s.y = fmaf(v.y, gv, s.y); s.z = fmaf(v.z, gv, s.z); s.w = fmaf(v.w, gv, s.w);
+    }
+    *((float4*)(dkr2 + (long long)pl * Bn) + b4) = s;
+  }
+}
+__global__ void __launch_bounds__(256) dkr2_from_saved_scalar_kernel(const float* __restrict__ T, const float* __restrict__ gout,
+                                                                     float* __restrict__ dkr2, long long p0, int np, int Bn, int O) {
+  const long long total = (long long)np * Bn;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int pl = (int)(i / Bn), b = (int)(i - (long long)pl * Bn);
+    const long long p = p0 + pl;
+    const float* t = T + p * (long long)Bn * O + b;
+    float s = 0.f;
+    for (int o = 0; o < O; ++o) s = fmaf(t[(long long)o * Bn], __ldg(gout + p * O + o), s);
+    dkr2[i] = s;
+  }
+}
+}  // namespace
+
+// kind 2: recompute T (two GEMMs); kind 3: T saved by the training forward (one GEMM + one streaming pass over T)
+static int backward_input_impl(const EpsGeom& g, const float* x, const float* core, const float* gout, const float* tsaved,
+                               float* dx, void* ws, int passes, cudaStream_t st) {
+  const int BN1 = pick_bn(g, MODE_STORE), BN2 = tsaved ? 0 : pick_bn(g, MODE_DKR2);
+  if (!BN1 || (!tsaved && !BN2)) return dctn_set_error(-2, "tcgen05 input-gradient kernels do not support this shape");
   const long long pc = dx_patch_chunk(g);
   float* packed1 = (float*)ws;
   float* packed2 = packed1 + ((packed_floats(g, MODE_STORE, BN1) + 63) & ~(size_t)63);
-  float* dkr1 = packed2 + ((packed_floats(g, MODE_DKR2, BN2) + 63) & ~(size_t)63);
+  float* dkr1 = packed2 + (tsaved ? 0 : ((packed_floats(g, MODE_DKR2, BN2) + 63) & ~(size_t)63));
   float* dkr2 = dkr1 + (size_t)pc * g.A;
   float* dxp = dkr2 + (size_t)pc * g.Bn;
   int rc;
   if ((rc = run_pack(g, MODE_STORE, BN1, core, packed1, passes, st))) return rc;
-  if ((rc = run_pack(g, MODE_DKR2, BN2, core, packed2, passes, st))) return rc;
+  if (!tsaved && (rc = run_pack(g, MODE_DKR2, BN2, core, packed2, passes, st))) return rc;
   for (long long p0 = 0; p0 < g.P; p0 += pc) {
     const int np = (int)((g.P - p0 < pc) ? (g.P - p0) : pc);
     if ((rc = run_gemm(g, MODE_STORE, BN1, x, gout, packed1, p0, np, dkr1, g.A, passes, st))) return rc;
     if ((rc = launch_loo<float>(g, x, dkr1, p0, np, 0, dxp, st))) return rc;
-    if ((rc = run_gemm(g, MODE_DKR2, BN2, x, gout, packed2, p0, np, dkr2, g.Bn, passes, st))) return rc;
+    if (tsaved) {
+      const bool vec = (g.Bn & 3) == 0;
+      const long long items = (long long)np * (vec ? g.Bn / 4 : g.Bn);
+      int blocks = (int)((items + 255) / 256);
+      if (blocks > 148 * 16) blocks = 148 * 16;
+      if (vec) dkr2_from_saved_kernel<<<blocks, 256, 0, st>>>(tsaved, gout, dkr2, p0, np, g.Bn, g.O);
+      else dkr2_from_saved_scalar_kernel<<<blocks, 256, 0, st>>>(tsaved, gout, dkr2, p0, np, g.Bn, g.O);
+      dctn_count_launch();
+      DCTN_CUDA_CHECK_RET(cudaGetLastError());
+    } else if ((rc = run_gemm(g, MODE_DKR2, BN2, x, gout, packed2, p0, np, dkr2, g.Bn, passes, st))) return rc;
     if ((rc = launch_loo<float>(g, x, dkr2, p0, np, 1, dxp, st))) return rc;
   }
   return launch_gather_dx<float>(g, dxp, dx, st);
+}
+
+int tc_backward_input(const EpsGeom& g, const float* x, const float* core, const float* gout, float* dx, void* ws,
+                      int passes, cudaStream_t st) {
+  return backward_input_impl(g, x, core, gout, nullptr, dx, ws, passes, st);
+}
+int tc_backward_input_saved(const EpsGeom& g, const float* x, const float* core, const float* gout, const float* tsaved,
+                            float* dx, void* ws, int passes, cudaStream_t st) {
+  return backward_input_impl(g, x, core, gout, tsaved, dx, ws, passes, st);
 }

@@ -22,6 +22,16 @@ from . import _lib
 _DTYPES = {torch.float32: _lib.F32, torch.float64: _lib.F64}
 _default_variant = _lib.VARIANTS.get(os.environ.get("DCTN_B200_VARIANT", "auto").lower(), _lib.VARIANT_AUTO)
 _plans: Dict[Tuple[int, int, int, int, int, int], int] = {}
+# Training forward keeps the forward GEMM's per-patch intermediate T (P x Q_in^floor(n/2) * Q_out floats) for the
+# input gradient when it is at most this many bytes (B200: 180 GB of HBM3e; config 2, B=512: 1.66 GB); larger
+# layers recompute it.  0 disables saving.
+_save_limit_bytes = int(float(os.environ.get("DCTN_B200_SAVE_LIMIT_MB", "16384")) * (1 << 20))
+
+
+def set_save_limit_mb(mb: float) -> None:
+    global _save_limit_bytes
+    _save_limit_bytes = int(mb * (1 << 20))
+
 
 
 def set_default_variant(name: str) -> None:
@@ -76,7 +86,11 @@ def _workspace(plan: int, B: int, H: int, W: int, kind: int, device) -> Tensor:
 
 
 class EpsFunction(torch.autograd.Function):
-    """autograd node of one EPS layer (forward: K1, backward: K2 core-gradient + K3 input-gradient)."""
+    """autograd node of one EPS layer (forward: K1, backward: K2 core-gradient + K3 input-gradient).
+
+    Saves ``(core, input)`` and — only when ``input`` needs a gradient, the kernel family has one, and it fits the
+    save limit — the forward GEMM's intermediate ``T`` (dctn_eps_forward_train), which halves the tensor-core work
+    of the input gradient.  The reference's autograd keeps that tensor and two larger ones (dctn/eps.py:31-40)."""
 
     @staticmethod
     def forward(ctx, core: Tensor, input: Tensor, variant: int) -> Tensor:
@@ -86,14 +100,28 @@ class EpsFunction(torch.autograd.Function):
         x_c = input.detach().contiguous()
         plan = _plan(C, K, Q, O, input.dtype, variant)
         out = torch.empty((B, H - K + 1, W - K + 1, O), dtype=input.dtype, device=input.device)
+        lib = _lib.lib()
+        saved = None
         with torch.cuda.device(input.device):
             ws = _workspace(plan, B, H, W, _lib.WS_FORWARD, input.device)
-            rc = _lib.lib().dctn_eps_forward(
-                plan, x_c.data_ptr(), core_c.data_ptr(), out.data_ptr(), B, H, W, ws.data_ptr(), ws.numel(),
-                torch.cuda.current_stream().cuda_stream,
-            )
-        _lib.check(rc, "dctn_eps_forward")
-        ctx.save_for_backward(core_c, x_c)
+            stream = torch.cuda.current_stream().cuda_stream
+            nsave = lib.dctn_eps_saved_bytes(plan, B, H, W) if ctx.needs_input_grad[1] else 0
+            if 0 < nsave <= _save_limit_bytes:
+                saved = torch.empty(nsave, dtype=torch.uint8, device=input.device)
+                rc = lib.dctn_eps_forward_train(
+                    plan, x_c.data_ptr(), core_c.data_ptr(), out.data_ptr(), saved.data_ptr(), saved.numel(), B, H, W,
+                    ws.data_ptr(), ws.numel(), stream,
+                )
+                _lib.check(rc, "dctn_eps_forward_train")
+            else:
+                rc = lib.dctn_eps_forward(
+                    plan, x_c.data_ptr(), core_c.data_ptr(), out.data_ptr(), B, H, W, ws.data_ptr(), ws.numel(), stream
+                )
+                _lib.check(rc, "dctn_eps_forward")
+        if saved is None:
+            ctx.save_for_backward(core_c, x_c)
+        else:
+            ctx.save_for_backward(core_c, x_c, saved)
         ctx.plan = plan
         ctx.core_shape = core.shape
         return out
@@ -101,7 +129,8 @@ class EpsFunction(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, gout: Tensor):
-        core_c, x_c = ctx.saved_tensors
+        core_c, x_c, *rest = ctx.saved_tensors
+        saved = rest[0] if rest else None
         _, B, H, W, _ = x_c.shape
         gout = gout.contiguous()
         dcore = dx = None
@@ -118,12 +147,20 @@ class EpsFunction(torch.autograd.Function):
                 dcore = dcore.view(ctx.core_shape)
             if ctx.needs_input_grad[1]:
                 dx = torch.empty_like(x_c)
-                ws = _workspace(ctx.plan, B, H, W, _lib.WS_BACKWARD_INPUT, x_c.device)
-                rc = lib.dctn_eps_backward_input(
-                    ctx.plan, x_c.data_ptr(), core_c.data_ptr(), gout.data_ptr(), dx.data_ptr(), B, H, W,
-                    ws.data_ptr(), ws.numel(), stream,
-                )
-                _lib.check(rc, "dctn_eps_backward_input")
+                if saved is not None:
+                    ws = _workspace(ctx.plan, B, H, W, _lib.WS_BACKWARD_INPUT_SAVED, x_c.device)
+                    rc = lib.dctn_eps_backward_input_saved(
+                        ctx.plan, x_c.data_ptr(), core_c.data_ptr(), gout.data_ptr(), saved.data_ptr(), saved.numel(),
+                        dx.data_ptr(), B, H, W, ws.data_ptr(), ws.numel(), stream,
+                    )
+                    _lib.check(rc, "dctn_eps_backward_input_saved")
+                else:
+                    ws = _workspace(ctx.plan, B, H, W, _lib.WS_BACKWARD_INPUT, x_c.device)
+                    rc = lib.dctn_eps_backward_input(
+                        ctx.plan, x_c.data_ptr(), core_c.data_ptr(), gout.data_ptr(), dx.data_ptr(), B, H, W,
+                        ws.data_ptr(), ws.numel(), stream,
+                    )
+                    _lib.check(rc, "dctn_eps_backward_input")
         return dcore, dx, None
 
 

@@ -57,7 +57,8 @@ typedef enum dctn_variant {
 typedef enum dctn_ws_kind {
   DCTN_WS_FORWARD = 0,
   DCTN_WS_BACKWARD_CORE = 1,
-  DCTN_WS_BACKWARD_INPUT = 2
+  DCTN_WS_BACKWARD_INPUT = 2,
+  DCTN_WS_BACKWARD_INPUT_SAVED = 3 /* dctn_eps_backward_input_saved() */
 } dctn_ws_kind;
 
 typedef struct dctn_plan dctn_plan_t; /* opaque, owned by the library's plan cache, never freed by the caller */
@@ -90,6 +91,22 @@ int dctn_eps_backward_core(const dctn_plan_t* plan, const void* x, const void* g
 int dctn_eps_backward_input(const dctn_plan_t* plan, const void* x, const void* core, const void* gout,
                             void* dx, int B, int H, int W, void* workspace, size_t workspace_bytes,
                             void* stream);
+
+/* Training forward: as dctn_eps_forward, and additionally keeps the forward GEMM's per-patch intermediate
+ * T[p][(o, b)] = sum_a KR1[p][a] * core[a][b][o]  (P x Q_in^(n-m) * Q_out elements, n-m = floor(K*K*C/2) factors)
+ * in the caller's `saved` buffer, so that the input gradient does not have to recompute it — the reference's
+ * autograd keeps the same tensor (step 2 of dctn/eps.py:31-40) plus two larger ones.
+ * dctn_eps_saved_bytes() returns the size of `saved`, or 0 when the kernel family serving this plan/shape has no
+ * savable intermediate (then use dctn_eps_forward / dctn_eps_backward_input). */
+size_t dctn_eps_saved_bytes(const dctn_plan_t* plan, int B, int H, int W);
+int dctn_eps_forward_train(const dctn_plan_t* plan, const void* x, const void* core, void* out, void* saved,
+                           size_t saved_bytes, int B, int H, int W, void* workspace, size_t workspace_bytes,
+                           void* stream);
+/* dx from the intermediate saved by dctn_eps_forward_train (same plan, same x, same core).  Workspace kind
+ * DCTN_WS_BACKWARD_INPUT_SAVED. */
+int dctn_eps_backward_input_saved(const dctn_plan_t* plan, const void* x, const void* core, const void* gout,
+                                  const void* saved, size_t saved_bytes, void* dx, int B, int H, int W,
+                                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* out[t,i] = log sum_r exp(log_A[t,r] + log_B[r,i]).  Replaces dctn/logmatmulexp.py:5-14. */
 int dctn_logmatmulexp_forward(const void* log_A, const void* log_B, void* out, int Theta, int R, int I,

@@ -390,6 +390,86 @@ def test_tc_forward_and_input_grad_full_size_vs_fp64(B, H, W, Q, K, Oq):
     got_dx = _raw_call(_lib.WS_BACKWARD_INPUT, "tc3", core.to(DEV), x.to(DEV), gout.to(DEV))
     print(f"tc3 input-grad full-size rel err {rel_err(got_dx, want_dx):.3e}")
     assert rel_err(got_dx, want_dx) <= 1e-5
+    out_s, dx_s = _raw_train_call("tc3", core.to(DEV), x.to(DEV), gout.to(DEV))
+    print(f"tc3 saved-T path full-size rel err: forward {rel_err(out_s, want):.3e}, input-grad {rel_err(dx_s, want_dx):.3e}")
+    assert torch.equal(out_s, got)
+    assert rel_err(dx_s, want_dx) <= 1e-5
+
+
+def _raw_train_call(variant, core, x, gout):
+    """dctn_eps_forward_train + dctn_eps_backward_input_saved through the C ABI; returns (out, dx)."""
+    from dctn_b200 import _lib
+    from dctn_b200 import eps as E
+
+    C, K, Q, Oq = E._infer(core, x)
+    _, B, H, W, _ = x.shape
+    plan = E._plan(C, K, Q, Oq, x.dtype, _lib.VARIANTS[variant])
+    lib = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    nsave = lib.dctn_eps_saved_bytes(plan, B, H, W)
+    assert nsave == x.shape[1] * (H - K + 1) * (W - K + 1) * Q ** (K * K * C // 2) * Oq * 4
+    saved = torch.empty(nsave, dtype=torch.uint8, device=x.device)
+    ws = torch.empty(lib.dctn_eps_workspace_bytes(plan, B, H, W, _lib.WS_FORWARD), dtype=torch.uint8, device=x.device)
+    out = torch.empty(B, H - K + 1, W - K + 1, Oq, dtype=x.dtype, device=x.device)
+    rc = lib.dctn_eps_forward_train(plan, x.data_ptr(), core.data_ptr(), out.data_ptr(), saved.data_ptr(), nsave, B, H, W,
+                                    ws.data_ptr(), ws.numel(), st)
+    assert rc == 0, _lib.last_error()
+    ws2 = torch.empty(lib.dctn_eps_workspace_bytes(plan, B, H, W, _lib.WS_BACKWARD_INPUT_SAVED), dtype=torch.uint8, device=x.device)
+    dx = torch.empty_like(x)
+    rc = lib.dctn_eps_backward_input_saved(plan, x.data_ptr(), core.data_ptr(), gout.data_ptr(), saved.data_ptr(), nsave,
+                                           dx.data_ptr(), B, H, W, ws2.data_ptr(), ws2.numel(), st)
+    assert rc == 0, _lib.last_error()
+    torch.cuda.synchronize()
+    return out, dx
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_tc_saved_intermediate_path_vs_oracle(shape):
+    """Training forward that keeps T + input gradient from the saved T (one GEMM instead of two) vs the oracle."""
+    B, H, W, Q, K, Oq = shape
+    x, core, gout = _rand_layer(B, H, W, Q, K, Oq, seed=25)
+    want = O.eps_4step(core.double(), x.double())
+    _, want_dx = O.eps_grads(core.double(), x.double(), gout.double())
+    out, dx = _raw_train_call("tc3", core.to(DEV), x.to(DEV), gout.to(DEV))
+    assert rel_err(out, want) <= 1e-5
+    assert rel_err(dx, want_dx) <= 1e-5
+
+
+def test_saved_intermediate_entry_points_reject_other_families():
+    """Families without a savable intermediate report 0 bytes and refuse the training entry points (no fallback)."""
+    from dctn_b200 import _lib
+    from dctn_b200 import eps as E
+
+    lib = _lib.lib()
+    plan = E._plan(1, 2, 2, 2, torch.float32, _lib.VARIANT_AUTO)      # direct family
+    assert lib.dctn_eps_saved_bytes(plan, 8, 28, 28) == 0
+    plan64 = E._plan(1, 3, 4, 6, torch.float64, _lib.VARIANT_AUTO)    # float64: CUDA-core family
+    assert lib.dctn_eps_saved_bytes(plan64, 8, 25, 25) == 0
+    buf = torch.empty(1 << 20, dtype=torch.uint8, device=DEV)
+    rc = lib.dctn_eps_forward_train(plan, buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), buf.numel(), 8, 28, 28,
+                                    buf.data_ptr(), buf.numel(), torch.cuda.current_stream().cuda_stream)
+    assert rc == -2 and "no savable intermediate" in _lib.last_error()
+
+
+def test_autograd_saved_and_recompute_paths_agree():
+    """EpsFunction with and without the saved intermediate (save limit 0) gives the same gradients."""
+    from dctn_b200 import eps as E
+
+    x, core, gout = _rand_layer(8, 25, 25, 4, 3, 6, seed=26)
+    res = []
+    for limit in (16384, 0):
+        E.set_save_limit_mb(limit)
+        try:
+            xd = x.to(DEV).requires_grad_(True)
+            cd = core.to(DEV).requires_grad_(True)
+            E.eps(cd, xd).backward(gout.to(DEV))
+            res.append((xd.grad.clone(), cd.grad.clone()))
+        finally:
+            E.set_save_limit_mb(16384)
+    _, want_dx = O.eps_grads(core.double(), x.double(), gout.double())
+    assert rel_err(res[0][0], want_dx) <= 1e-5 and rel_err(res[1][0], want_dx) <= 1e-5
+    assert rel_err(res[0][0], res[1][0]) <= 2e-6
+    assert torch.equal(res[0][1], res[1][1])
 
 
 # ---------------------------------------------------------------- direct (tiny-core) kernels and the host-buffer entry
