@@ -14,8 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdctn_b200.so")
 
 F32, F64 = 0, 1
-VARIANT_AUTO, VARIANT_FFMA, VARIANT_TC3, VARIANT_TC1, VARIANT_DIRECT = 0, 1, 2, 3, 4
-VARIANTS = {"auto": 0, "ffma": 1, "tc3": 2, "tc1": 3, "direct": 4}
+VARIANT_AUTO, VARIANT_FFMA, VARIANT_TC3, VARIANT_TC1, VARIANT_DIRECT, VARIANT_TCH3 = 0, 1, 2, 3, 4, 5
+VARIANTS = {"auto": 0, "ffma": 1, "tc3": 2, "tc1": 3, "direct": 4, "tch3": 5}
 WS_FORWARD, WS_BACKWARD_CORE, WS_BACKWARD_INPUT, WS_BACKWARD_INPUT_SAVED = 0, 1, 2, 3
 
 # every symbol include/dctn_b200.h declares: (name, restype, argtypes)

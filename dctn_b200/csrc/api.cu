@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -83,7 +84,7 @@ extern "C" const dctn_plan_t* dctn_eps_plan_get(int C, int K, int Qin, int Qout,
     dctn_set_error(DCTN_ERR_BAD_ARG, "plan: dtype must be DCTN_F32 or DCTN_F64");
     return nullptr;
   }
-  if (variant < DCTN_VARIANT_AUTO || variant > DCTN_VARIANT_DIRECT) {
+  if (variant < DCTN_VARIANT_AUTO || variant > DCTN_VARIANT_TCH3) {
     dctn_set_error(DCTN_ERR_BAD_ARG, "plan: unknown variant %d", variant);
     return nullptr;
   }
@@ -104,8 +105,8 @@ extern "C" const dctn_plan_t* dctn_eps_plan_get(int C, int K, int Qin, int Qout,
     dctn_set_error(DCTN_ERR_UNSUPPORTED, "plan: core with Qin^(K*K*C) = %d^%d elements is too large", Qin, n);
     return nullptr;
   }
-  if ((variant == DCTN_VARIANT_TC3 || variant == DCTN_VARIANT_TC1) && dtype != DCTN_F32) {
-    dctn_set_error(DCTN_ERR_UNSUPPORTED, "plan: the tcgen05 TF32 variants are float32 only");
+  if ((variant == DCTN_VARIANT_TC3 || variant == DCTN_VARIANT_TC1 || variant == DCTN_VARIANT_TCH3) && dtype != DCTN_F32) {
+    dctn_set_error(DCTN_ERR_UNSUPPORTED, "plan: the tcgen05 tensor-core variants are float32 only");
     return nullptr;
   }
   dctn_plan* pl = new dctn_plan();
@@ -136,11 +137,23 @@ static int check_call(const dctn_plan_t* pl, int B, int H, int W) {
   return 0;
 }
 
+// arithmetic of the tensor-core family (the `passes` argument of the tc_* launchers): 1 / 3 = TF32 passes, 6 = split fp16.
+// AUTO: split fp16 unless DCTN_B200_AUTO_ARITH=tf32.
+static int tc_arith(const dctn_plan_t* pl, int kind) {
+  static const int auto_arith = [] {
+    const char* e = getenv("DCTN_B200_AUTO_ARITH");
+    return (e && strcmp(e, "tf32") == 0) ? 3 : 6;
+  }();
+  int a = pl->variant == DCTN_VARIANT_TC1 ? 1 : pl->variant == DCTN_VARIANT_TC3 ? 3 : pl->variant == DCTN_VARIANT_TCH3 ? 6 : auto_arith;
+  return a;
+}
+
 // which kernel family serves `kind` for this plan/geometry
 static int pick_family(const dctn_plan_t* pl, const EpsGeom& g, int kind) {
   switch (pl->variant) {
     case DCTN_VARIANT_FFMA: return FAM_FFMA;
     case DCTN_VARIANT_TC3:
+    case DCTN_VARIANT_TCH3:
     case DCTN_VARIANT_TC1: return tc_supported(g, kind) ? FAM_TC : -1;
     case DCTN_VARIANT_DIRECT:
       if (kind == DCTN_WS_FORWARD) return direct_supported(g, pl->dtype) ? FAM_DIRECT : -1;
@@ -188,7 +201,7 @@ extern "C" int dctn_eps_forward(const dctn_plan_t* pl, const void* x, const void
     return pl->dtype == DCTN_F32 ? direct_forward<float>(g, (const float*)x, (const float*)core, (float*)out, st)
                                  : direct_forward<double>(g, (const double*)x, (const double*)core, (double*)out, st);
   if (fam == FAM_TC)
-    return tc_forward(g, (const float*)x, (const float*)core, (float*)out, ws, pl->variant == DCTN_VARIANT_TC1 ? 1 : 3, st);
+    return tc_forward(g, (const float*)x, (const float*)core, (float*)out, ws, tc_arith(pl, DCTN_WS_FORWARD), st);
   return pl->dtype == DCTN_F32 ? ffma_forward<float>(g, (const float*)x, (const float*)core, (float*)out, ws, st)
                                : ffma_forward<double>(g, (const double*)x, (const double*)core, (double*)out, ws, st);
 }
@@ -208,7 +221,7 @@ extern "C" int dctn_eps_backward_core(const dctn_plan_t* pl, const void* x, cons
     return pl->dtype == DCTN_F32 ? direct_backward<float>(g, 1, (const float*)x, nullptr, (const float*)gout, (float*)dcore, ws, st)
                                  : direct_backward<double>(g, 1, (const double*)x, nullptr, (const double*)gout, (double*)dcore, ws, st);
   if (fam == FAM_TC)
-    return tc_backward_core(g, (const float*)x, (const float*)gout, (float*)dcore, ws, pl->variant == DCTN_VARIANT_TC1 ? 1 : 3, st);
+    return tc_backward_core(g, (const float*)x, (const float*)gout, (float*)dcore, ws, tc_arith(pl, DCTN_WS_BACKWARD_CORE), st);
   return pl->dtype == DCTN_F32 ? ffma_backward_core<float>(g, (const float*)x, (const float*)gout, (float*)dcore, ws, st)
                                : ffma_backward_core<double>(g, (const double*)x, (const double*)gout, (double*)dcore, ws, st);
 }
@@ -229,7 +242,7 @@ extern "C" int dctn_eps_backward_input(const dctn_plan_t* pl, const void* x, con
                ? direct_backward<float>(g, 2, (const float*)x, (const float*)core, (const float*)gout, (float*)dx, ws, st)
                : direct_backward<double>(g, 2, (const double*)x, (const double*)core, (const double*)gout, (double*)dx, ws, st);
   if (fam == FAM_TC)
-    return tc_backward_input(g, (const float*)x, (const float*)core, (const float*)gout, (float*)dx, ws, pl->variant == DCTN_VARIANT_TC1 ? 1 : 3, st);
+    return tc_backward_input(g, (const float*)x, (const float*)core, (const float*)gout, (float*)dx, ws, tc_arith(pl, DCTN_WS_BACKWARD_INPUT), st);
   return pl->dtype == DCTN_F32
              ? ffma_backward_input<float>(g, (const float*)x, (const float*)core, (const float*)gout, (float*)dx, ws, st)
              : ffma_backward_input<double>(g, (const double*)x, (const double*)core, (const double*)gout, (double*)dx, ws, st);
@@ -262,7 +275,7 @@ extern "C" int dctn_eps_forward_train(const dctn_plan_t* pl, const void* x, cons
     return dctn_set_error(DCTN_ERR_UNSUPPORTED, "forward_train: no savable intermediate for this plan/shape (dctn_eps_saved_bytes() == 0): %s", pl->desc.c_str());
   if (saved_bytes < tcg_saved_bytes(g))
     return dctn_set_error(DCTN_ERR_WORKSPACE, "forward_train: saved buffer of %zu bytes needed, got %zu", tcg_saved_bytes(g), saved_bytes);
-  return tc_forward(g, (const float*)x, (const float*)core, (float*)out, ws, pl->variant == DCTN_VARIANT_TC1 ? 1 : 3,
+  return tc_forward(g, (const float*)x, (const float*)core, (float*)out, ws, tc_arith(pl, DCTN_WS_FORWARD),
                     (cudaStream_t)stream, (float*)saved);
 }
 
@@ -280,7 +293,7 @@ extern "C" int dctn_eps_backward_input_saved(const dctn_plan_t* pl, const void* 
     return dctn_set_error(DCTN_ERR_WORKSPACE, "backward_input_saved: saved buffer of %zu bytes needed, got %zu", tcg_saved_bytes(g), saved_bytes);
   if ((rc = check_ws(pl, B, H, W, DCTN_WS_BACKWARD_INPUT_SAVED, ws, ws_bytes))) return rc;
   return tc_backward_input_saved(g, (const float*)x, (const float*)core, (const float*)gout, (const float*)saved, (float*)dx,
-                                 ws, pl->variant == DCTN_VARIANT_TC1 ? 1 : 3, (cudaStream_t)stream);
+                                 ws, tc_arith(pl, DCTN_WS_BACKWARD_INPUT), (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------ logmatmulexp

@@ -22,10 +22,20 @@
 //   * split-K over patch ranges (about two waves of CTAs); partial tiles go to the workspace and a second kernel
 //     sums them in a fixed order (deterministic).
 // TMEM columns: main 0..127, small 128..255, A stage s at 256 + 128*s (slab0 hi | slab0 lo | slab1 hi | slab1 lo).
+//
+// Split-fp16 arithmetic (F16 = true, the default; see eps_tc_gemm.cu for the number format): kind::f16 MMAs, a 128-byte
+// operand row / 32-column TMEM slab holds 64 patches, so a stage is ONE slab of 64 patches and there are 4 stages.  The
+// reduction runs over patches whose magnitudes differ, so the per-patch power-of-two normalisation cannot be undone
+// after the sum: patch_exp_kernel computes every patch's exponent E_p (sum of the exponents of its factor vectors and
+// of its gout row) and the maximum E_max; build_tables_kernel writes normalised tables and folds 2^(E_p - E_max) <= 1
+// into the second-half hi table.  A patch far below the largest one loses relative precision exactly as its
+// contribution loses weight in the sum.  reduce_partials applies 2^(E_max - 30) (two operand scales of 2^15).
 #include "common.cuh"
 #include "eps_kernels.h"
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
+#include <cuda_fp16.h>
 
 #include "tc_common.cuh"
 
@@ -47,6 +57,9 @@ constexpr int NPROD_WARPS = 8;    // warps 1..8; warp 0 issues MMAs; warp 9 stre
 constexpr int NTHREADS_TC = 32 * (2 + NPROD_WARPS);
 constexpr int TSTAGES = 2;        // table buffers
 constexpr int SEG_CHUNKS = 12;    // chunks per promotion segment: 12 * 2 slabs * 4 k-steps = 96 roundings of the main chain
+constexpr int SEG_CHUNKS_F16 = 24;  // fp16: one slab per chunk -> the same 96 roundings
+constexpr int STAGES_F16 = 4;     // fp16: a stage is one 64-patch slab (32 KB of B, 64 TMEM columns of A)
+constexpr int ARITH_F16X3 = 6;    // value of `passes` selecting the split-fp16 arithmetic
 constexpr int TS_ = CH + 4;       // table row stride in floats (272 B: 16-byte aligned, rows 4 banks apart)
 constexpr uint32_t SLAB_BYTES = BN * 32 * 4;           // one part (hi or lo) of one slab of B: 16 KB
 constexpr uint32_t STAGE_BYTES = SLABS * 2 * SLAB_BYTES;  // 64 KB
@@ -93,12 +106,52 @@ inline int max_tile_entries(const EpsGeom& g, int three) {
 // tables[chunk][entry][i] for patch p = chunk*64 + i (zeros past P): entries [0,AH): first-half hi group,
 // [AH, AH+AL): first-half lo group, then [.., +BH): second-half hi group, then either BL*O entries (second-half lo group
 // x gout) or, three-level, BL entries (lo group) followed by O entries (gout).
+// exponent e with m = f * 2^e, f in [0.5, 1); 0 for m == 0 / inf / nan
+__device__ __forceinline__ int norm_exp(float m) {
+  int e = 0;
+  if (m > 0.f && m < 3.0e38f) frexpf(m, &e);
+  return e;
+}
+__device__ __forceinline__ void split_f16x2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(v0, v1);
+  const float r0 = (v0 - __low2float(h)) * 2048.f, r1 = (v1 - __high2float(h)) * 2048.f;
+  const __half2 l = __floats2half2_rn(r0, r1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// fp16 arithmetic, pass 1: exps[p] = E_p, *emax = max_p E_p (one thread per patch; *emax starts at INT_MIN)
+__global__ void __launch_bounds__(256) patch_exp_kernel(EpsGeom g, const float* __restrict__ x, const float* __restrict__ gout,
+                                                        int* __restrict__ exps, int* __restrict__ emax) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int E = INT_MIN;
+  if (p < g.P) {
+    const long long o0 = patch_origin(g, p);
+    E = 0;
+    for (int j = 0; j < g.n; ++j) {
+      float m = 0.f;
+      for (int q = 0; q < g.Q; ++q) m = fmaxf(m, fabsf(__ldg(&x[o0 + g.foff[j] + q])));
+      E += norm_exp(m);
+    }
+    float m = 0.f;
+    for (int o = 0; o < g.O; ++o) m = fmaxf(m, fabsf(__ldg(&gout[p * g.O + o])));
+    E += norm_exp(m);
+    exps[p] = E;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) E = max(E, __shfl_xor_sync(0xffffffffu, E, o));
+  if ((threadIdx.x & 31) == 0 && E != INT_MIN) atomicMax(emax, E);
+}
+
+template <bool F16>
 __global__ void __launch_bounds__(256) build_tables_kernel(EpsGeom g, const float* __restrict__ x,
-                                                           const float* __restrict__ gout, float* __restrict__ tables, int three) {
+                                                           const float* __restrict__ gout, float* __restrict__ tables, int three,
+                                                           const int* __restrict__ exps, const int* __restrict__ emax) {
   extern __shared__ float bt_smem[];
   const int Q = g.Q, O = g.O, NX = g.n * Q;
   float* xs = bt_smem;             // [NX][64]
   float* gs = xs + NX * CH;        // [O][64]
+  float* wp = gs + O * CH;         // F16: [64] weight 2^(E_p - E_max) of every patch
   const long long p0 = (long long)blockIdx.x * CH;
   for (int idx = threadIdx.x; idx < (NX + O) * CH; idx += blockDim.x) {
     const int i = idx & (CH - 1), r = idx >> 6;
@@ -108,15 +161,33 @@ __global__ void __launch_bounds__(256) build_tables_kernel(EpsGeom g, const floa
     xs[idx] = v;
   }
   __syncthreads();
+  if (F16) {
+    // every factor vector and the gout row of a patch: largest magnitude scaled into [0.5, 1) (exact)
+    for (int idx = threadIdx.x; idx < (g.n + 1) * CH; idx += blockDim.x) {
+      const int i = idx & (CH - 1), j = idx >> 6;
+      float* v = (j < g.n) ? xs + j * Q * CH + i : gs + i;
+      const int cnt = (j < g.n) ? Q : O;
+      float m = 0.f;
+      for (int q = 0; q < cnt; ++q) m = fmaxf(m, fabsf(v[q * CH]));
+      const int e = norm_exp(m);
+      if (e != 0)
+        for (int q = 0; q < cnt; ++q) v[q * CH] = scalbnf(v[q * CH], -e);
+    }
+    if (threadIdx.x < CH) {
+      const long long p = p0 + threadIdx.x;
+      wp[threadIdx.x] = (p < g.P) ? scalbnf(1.f, max(exps[p] - __ldg(emax), -200)) : 0.f;
+    }
+    __syncthreads();
+  }
   const int ENT = g.AH + g.AL + g.BH + last_section(g, three);
   float* out = tables + (long long)blockIdx.x * ENT * TS_;
   for (int idx = threadIdx.x; idx < ENT * CH; idx += blockDim.x) {
     const int i = idx & (CH - 1), t = idx >> 6;
     int e, j0, cnt;
     float v = 1.f;
-    if (t < g.AH) { e = t; j0 = 0; cnt = g.a_nh; }
+    if (t < g.AH) { e = t; j0 = 0; cnt = g.a_nh; if (F16) v = 32768.f; }
     else if (t < g.AH + g.AL) { e = t - g.AH; j0 = g.a_nh; cnt = g.a_nl; }
-    else if (t < g.AH + g.AL + g.BH) { e = t - g.AH - g.AL; j0 = g.m; cnt = g.b_nh; }
+    else if (t < g.AH + g.AL + g.BH) { e = t - g.AH - g.AL; j0 = g.m; cnt = g.b_nh; if (F16) v = 32768.f * wp[i]; }
     else {
       const int k = t - (g.AH + g.AL + g.BH);
       j0 = g.m + g.b_nh; cnt = g.b_nl;
@@ -135,9 +206,28 @@ __global__ void __launch_bounds__(256) build_tables_kernel(EpsGeom g, const floa
   for (int idx = threadIdx.x; idx < ENT * (TS_ - CH); idx += blockDim.x) out[(idx / (TS_ - CH)) * TS_ + CH + idx % (TS_ - CH)] = 0.f;
 }
 
-template <bool THREE>
+// fp16 arithmetic: out[i] = 2^(E_max - 30) * sum_z part[z*count + i]  (fixed order: deterministic)
+__global__ void reduce_partials_scaled_kernel(const float* __restrict__ part, float* __restrict__ out, long long count, int splits,
+                                              const int* __restrict__ emax) {
+  const int k = __ldg(emax) - 30;
+  const float s1 = scalbnf(1.f, k / 2), s2 = scalbnf(1.f, k - k / 2);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[(long long)z * count + i];
+    out[i] = s * s1 * s2;
+  }
+}
+
+template <bool THREE, bool F16>
 __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_constant__ TcDcoreArgs a) {
   extern __shared__ unsigned char smem_dyn[];
+  // per-arithmetic pipeline shape (shadow the TF32 namespace constants)
+  constexpr int SLABS = F16 ? 1 : ::SLABS;                        // 128-byte K slabs per stage: 64 fp16 or 32 tf32 values each
+  constexpr int STAGES = F16 ? STAGES_F16 : ::STAGES;
+  constexpr uint32_t STAGE_BYTES = SLABS * 2 * SLAB_BYTES;        // 32 KB (fp16) / 64 KB (tf32)
+  constexpr int SEG_CHUNKS = F16 ? SEG_CHUNKS_F16 : ::SEG_CHUNKS;
+  constexpr uint32_t A_STAGE_COLS = SLABS * 64;                   // TMEM columns of one A stage (hi | lo per slab)
+  constexpr int MAXST = STAGES_F16;                               // barrier slots are laid out for the larger stage count
   const EpsGeom& g = a.g;
   const int O = g.O;
   const int BLO = g.BL * O;
@@ -154,10 +244,10 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
   float* zrow = tabs + TSTAGES * TE * TS_;                       // [TS_] zeros: padding operand rows multiply this
   float* onerow = zrow + TS_;                                    // [TS_] ones: third factor of rows that have none
   uint64_t* bars = (uint64_t*)(onerow + TS_);
-  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 2 * TSTAGES + 2);
-  const uint32_t bar_fullA0 = tc::smem_u32(bars), bar_fullB0 = bar_fullA0 + 8 * STAGES;
-  const uint32_t bar_empty0 = bar_fullB0 + 8 * STAGES;           // one per stage: frees both the TMEM A stage and the smem B stage
-  const uint32_t bar_tfull0 = bar_empty0 + 8 * STAGES, bar_tempty0 = bar_tfull0 + 8 * TSTAGES;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * MAXST + 2 * TSTAGES + 2);
+  const uint32_t bar_fullA0 = tc::smem_u32(bars), bar_fullB0 = bar_fullA0 + 8 * MAXST;
+  const uint32_t bar_empty0 = bar_fullB0 + 8 * MAXST;            // one per stage: frees both the TMEM A stage and the smem B stage
+  const uint32_t bar_tfull0 = bar_empty0 + 8 * MAXST, bar_tempty0 = bar_tfull0 + 8 * TSTAGES;
   const uint32_t bar_accfull = bar_tempty0 + 8 * TSTAGES, bar_accempty = bar_accfull + 8;
 
   long long pbeg = (long long)blockIdx.z * a.per_split;
@@ -190,7 +280,7 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
 
   if (warp == 0) {
     // =========================== MMA issuer ===========================
-    const uint32_t idesc = tc::make_idesc_tf32(BM, BN);
+    const uint32_t idesc = F16 ? tc::make_idesc_f16(BM, BN) : tc::make_idesc_tf32(BM, BN);
     const uint64_t db_base = tc::make_sw128_kmajor_desc(tc::smem_u32(stages));
     int s = 0;
     uint32_t ph = 0;
@@ -215,16 +305,24 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
         for (int sl = 0; sl < SLABS; ++sl) {
           const uint64_t db_hi = db_base + (uint64_t)((s * STAGE_BYTES + sl * 2 * SLAB_BYTES) >> 4);
           const uint64_t db_lo = db_hi + (SLAB_BYTES >> 4);
-          const uint32_t a_hi = tmem_a0 + (uint32_t)(s * 128 + sl * 64), a_lo = a_hi + 32;
+          const uint32_t a_hi = tmem_a0 + (uint32_t)(s * A_STAGE_COLS + sl * 64), a_lo = a_hi + 32;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < 4; ++k) {                 // 32 bytes of K per row and MMA: 8 x tf32 or 16 x fp16
             const uint64_t adv = (uint64_t)(k * 2);
             const uint32_t acol = (uint32_t)(k * 8);
             const uint32_t first = (seg_first && sl == 0 && k == 0) ? 0u : 1u;
-            tc::umma_tf32_ts(tmem_main, a_hi + acol, db_hi + adv, idesc, first);
-            if (a.passes == 3) {
-              tc::umma_tf32_ts(tmem_small, a_hi + acol, db_lo + adv, idesc, first);
-              tc::umma_tf32_ts(tmem_small, a_lo + acol, db_hi + adv, idesc, 1u);
+            if (F16) {
+              tc::umma_f16_ts(tmem_main, a_hi + acol, db_hi + adv, idesc, first);
+              if (a.passes == 3) {
+                tc::umma_f16_ts(tmem_small, a_hi + acol, db_lo + adv, idesc, first);
+                tc::umma_f16_ts(tmem_small, a_lo + acol, db_hi + adv, idesc, 1u);
+              }
+            } else {
+              tc::umma_tf32_ts(tmem_main, a_hi + acol, db_hi + adv, idesc, first);
+              if (a.passes == 3) {
+                tc::umma_tf32_ts(tmem_small, a_hi + acol, db_lo + adv, idesc, first);
+                tc::umma_tf32_ts(tmem_small, a_lo + acol, db_hi + adv, idesc, 1u);
+              }
             }
           }
         }
@@ -310,7 +408,7 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
         if (a.passes == 3) {
           tc::tmem_ld32(tmem_small + lane_base + (uint32_t)(chalf * 64 + cb), v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) racc[cb + i] += v[i];
+          for (int i = 0; i < 32; ++i) racc[cb + i] = F16 ? fmaf(v[i], 1.f / 2048.f, racc[cb + i]) : racc[cb + i] + v[i];
         }
       }
       tc::tc_fence_before();
@@ -336,32 +434,47 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
       tc::tc_fence_after();
 #pragma unroll
       for (int sl = 0; sl < SLABS; ++sl) {
-        float hi[32], lo[32];
+        uint32_t hi[32], lo[32];   // one slab: 32 tf32 values or 64 packed fp16 values (patch 2i in the low half of word i)
+        if (F16) {
 #pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4) {
-          float4 h4 = th[sl * 8 + q4];
-          const float4 l4 = tl[sl * 8 + q4];
-          if (THREE) {
-            const float4 g4 = tg[sl * 8 + q4];
-            h4.x *= g4.x; h4.y *= g4.y; h4.z *= g4.z; h4.w *= g4.w;
+          for (int q4 = 0; q4 < 16; ++q4) {
+            float4 h4 = th[q4];
+            const float4 l4 = tl[q4];
+            if (THREE) {
+              const float4 g4 = tg[q4];
+              h4.x *= g4.x; h4.y *= g4.y; h4.z *= g4.z; h4.w *= g4.w;
+            }
+            split_f16x2(h4.x * l4.x, h4.y * l4.y, hi[2 * q4], lo[2 * q4]);
+            split_f16x2(h4.z * l4.z, h4.w * l4.w, hi[2 * q4 + 1], lo[2 * q4 + 1]);
           }
-          tc::split_tf32(h4.x * l4.x, hi[4 * q4 + 0], lo[4 * q4 + 0]);
-          tc::split_tf32(h4.y * l4.y, hi[4 * q4 + 1], lo[4 * q4 + 1]);
-          tc::split_tf32(h4.z * l4.z, hi[4 * q4 + 2], lo[4 * q4 + 2]);
-          tc::split_tf32(h4.w * l4.w, hi[4 * q4 + 3], lo[4 * q4 + 3]);
+        } else {
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            float4 h4 = th[sl * 8 + q4];
+            const float4 l4 = tl[sl * 8 + q4];
+            if (THREE) {
+              const float4 g4 = tg[sl * 8 + q4];
+              h4.x *= g4.x; h4.y *= g4.y; h4.z *= g4.z; h4.w *= g4.w;
+            }
+            float fh, fl;
+            tc::split_tf32(h4.x * l4.x, fh, fl); hi[4 * q4 + 0] = __float_as_uint(fh); lo[4 * q4 + 0] = __float_as_uint(fl);
+            tc::split_tf32(h4.y * l4.y, fh, fl); hi[4 * q4 + 1] = __float_as_uint(fh); lo[4 * q4 + 1] = __float_as_uint(fl);
+            tc::split_tf32(h4.z * l4.z, fh, fl); hi[4 * q4 + 2] = __float_as_uint(fh); lo[4 * q4 + 2] = __float_as_uint(fl);
+            tc::split_tf32(h4.w * l4.w, fh, fl); hi[4 * q4 + 3] = __float_as_uint(fh); lo[4 * q4 + 3] = __float_as_uint(fl);
+          }
         }
         if (is_a) {
-          const uint32_t dst = tmem_a0 + lane_base + (uint32_t)(s * 128 + sl * 64);
-          tc::tmem_st32(dst, hi);
-          if (a.passes == 3) tc::tmem_st32(dst + 32, lo);
+          const uint32_t dst = tmem_a0 + lane_base + (uint32_t)(s * A_STAGE_COLS + sl * 64);
+          tc::tmem_st32_u(dst, hi);
+          if (a.passes == 3) tc::tmem_st32_u(dst + 32, lo);
         } else {
           unsigned char* st = stages + s * STAGE_BYTES + sl * 2 * SLAB_BYTES + brow_off;
 #pragma unroll
           for (int q4 = 0; q4 < 8; ++q4) {
             const uint32_t off = (uint32_t)((q4 ^ bsw) << 4);
-            *(float4*)(st + off) = make_float4(hi[4 * q4], hi[4 * q4 + 1], hi[4 * q4 + 2], hi[4 * q4 + 3]);
+            *(uint4*)(st + off) = make_uint4(hi[4 * q4], hi[4 * q4 + 1], hi[4 * q4 + 2], hi[4 * q4 + 3]);
             if (a.passes == 3)
-              *(float4*)(st + SLAB_BYTES + off) = make_float4(lo[4 * q4], lo[4 * q4 + 1], lo[4 * q4 + 2], lo[4 * q4 + 3]);
+              *(uint4*)(st + SLAB_BYTES + off) = make_uint4(lo[4 * q4], lo[4 * q4 + 1], lo[4 * q4 + 2], lo[4 * q4 + 3]);
           }
         }
       }
@@ -417,7 +530,7 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
 
 size_t dcore_tc_smem(const EpsGeom& g, int three) {
   const int TE = max_tile_entries(g, three);
-  return 1024 + (size_t)STAGES * STAGE_BYTES + (size_t)(TSTAGES * TE + 2) * TS_ * 4 + (3 * STAGES + 2 * TSTAGES + 2) * 8 + 16;
+  return 1024 + (size_t)STAGES * STAGE_BYTES + (size_t)(TSTAGES * TE + 2) * TS_ * 4 + (3 * STAGES_F16 + 2 * TSTAGES + 2) * 8 + 16;
 }
 // two-level B rows when their tables fit in shared memory, else three-level; -1: neither fits
 inline int pick_three(const EpsGeom& g) {
@@ -460,7 +573,8 @@ size_t tc_workspace_bytes(const EpsGeom& g, int kind) {
     int splits;
     dcore_split(g, &per, &splits);
     const int three = pick_three(g);
-    return ((size_t)splits * g.A * g.N + table_floats(g, three < 0 ? 0 : three)) * sizeof(float) + 256;
+    // partial tiles, tables, and (fp16 arithmetic) the per-patch exponents + the slot of their maximum
+    return ((size_t)splits * g.A * g.N + 64 + table_floats(g, three < 0 ? 0 : three) + 64 + (size_t)g.P + 64) * sizeof(float) + 256;
   }
   return tcg_workspace_bytes(g, kind);
 }
@@ -474,17 +588,31 @@ int tc_backward_core(const EpsGeom& g, const float* x, const float* gout, float*
   a.g = g; a.part = (float*)ws; a.passes = passes; a.three = three;
   int splits;
   dcore_split(g, &a.per_split, &splits);
+  const bool f16 = passes == ARITH_F16X3;
+  if (f16) a.passes = 3;
   float* tables = a.part + (((size_t)splits * g.A * g.N + 63) & ~(size_t)63);
   a.tables = tables;
+  int* exps = (int*)(tables + ((table_floats(g, three) + 63) & ~(size_t)63));
+  int* emax = exps + ((g.P + 63) & ~63ll);
   {
-    const size_t bsm = (size_t)(g.n * g.Q + g.O) * CH * sizeof(float);
+    const size_t bsm = (size_t)((g.n * g.Q + g.O) * CH + CH) * sizeof(float);
     if (bsm > 200 * 1024) return dctn_set_error(-2, "table kernel needs %zu bytes of shared memory", bsm);
-    DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(build_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
-    build_tables_kernel<<<(unsigned)((g.P + CH - 1) / CH), 256, bsm, st>>>(g, x, gout, tables, three);
+    if (f16) {
+      DCTN_CUDA_CHECK_RET(cudaMemsetAsync(emax, 0x80, sizeof(int), st));   // 0x80808080: below every possible E_p
+      patch_exp_kernel<<<(unsigned)((g.P + 255) / 256), 256, 0, st>>>(g, x, gout, exps, emax);
+      dctn_count_launch();
+      DCTN_CUDA_CHECK_RET(cudaGetLastError());
+      DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(build_tables_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+      build_tables_kernel<true><<<(unsigned)((g.P + CH - 1) / CH), 256, bsm, st>>>(g, x, gout, tables, three, exps, emax);
+    } else {
+      DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(build_tables_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+      build_tables_kernel<false><<<(unsigned)((g.P + CH - 1) / CH), 256, bsm, st>>>(g, x, gout, tables, three, nullptr, nullptr);
+    }
     dctn_count_launch();
     DCTN_CUDA_CHECK_RET(cudaGetLastError());
   }
-  auto kern = three ? tc_dcore_kernel<true> : tc_dcore_kernel<false>;
+  auto kern = f16 ? (three ? tc_dcore_kernel<true, true> : tc_dcore_kernel<false, true>)
+                  : (three ? tc_dcore_kernel<true, false> : tc_dcore_kernel<false, false>);
   DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((g.A + BM - 1) / BM, (g.N + BN - 1) / BN, splits);
   a.dbg = nullptr;
@@ -509,6 +637,15 @@ int tc_backward_core(const EpsGeom& g, const float* x, const float* gout, float*
             "bar1 %.0f prefetch+tables %.0f bar2 %.0f wait-empty %.0f rows+signal %.0f drain %.0f\n", ncta, nch / ncta,
             sum[0] / nch, sum[1] / nch, sum[2] / nch, sum[3] / nch, sum[5] / nch, sum[6] / nch, sum[7] / nch, sum[8] / nch,
             sum[9] / nch, sum[10] / nch, sum[11] / nch);
+  }
+  if (f16) {
+    const long long count = (long long)g.A * g.N;
+    int blocks = (int)((count + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    reduce_partials_scaled_kernel<<<blocks, 256, 0, st>>>(a.part, dcore, count, splits, emax);
+    dctn_count_launch();
+    DCTN_CUDA_CHECK_RET(cudaGetLastError());
+    return 0;
   }
   return launch_reduce_partials<float>(a.part, dcore, (long long)g.A * g.N, splits, st);
 }

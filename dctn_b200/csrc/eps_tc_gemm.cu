@@ -1,4 +1,5 @@
-// tcgen05 GEMMs of the EPS forward and input-gradient passes (float32 in/out, 3xTF32 or 1xTF32 arithmetic).
+// tcgen05 GEMMs of the EPS forward and input-gradient passes (float32 in/out; arithmetic: split fp16 "3xFP16" (default),
+// split TF32 "3xTF32", or single-pass TF32).
 //
 //   C[p][c] = sum_k Gen[p][k] * Bop[k][c]            p: 128 patches per CTA (TMEM lanes), c: BN columns per tile
 //
@@ -18,8 +19,19 @@
 //       MODE_FWD   out[p][o]  = sum_b C[p][(o,b)] * KR2[p][b]          (core packed as [a][(o,b)])      dctn/eps.py:19-40
 //       MODE_DKR2  dKR2[p][b] = sum_o C[p][(b,o)] * gout[p][o]         (C = KR1 @ core, never stored)
 //       MODE_STORE dKR1[p][a] = C[p][a]                                (Gen = KR2 x gout, Bop = core^T)
+//
+// 3xFP16 (F16 = true): every fp32 operand value v is represented as hi + lo * 2^-11 with hi = fp16(v) and
+// lo = fp16((v - hi) * 2^11): 22 significant bits, exactly what the TF32 split gives, but kind::f16 MMAs run at twice the
+// kind::tf32 rate and move half the operand bytes (a 128-byte swizzled row / a 32-column TMEM slab holds 64 K-values
+// instead of 32).  hi*hi goes to the MAIN accumulator, hi*lo + lo*hi (scaled by 2^11) to the SMALL one; the epilogue
+// adds small * 2^-11.  fp16 has a 5-bit exponent, so both operands are range-normalised with exact power-of-two
+// scales that the epilogue undoes: each factor vector x_j (and the gout row) of a patch is scaled to max-abs in
+// [0.5, 1) and the generated Khatri-Rao row by 2^15 (so its largest entry lies in [2^(15-#factors), 2^15)); the core
+// by one global power of two that puts max|core| in [2^14, 2^15).  Entries far below the row / core maximum
+// lose relative (not absolute) precision: |error| <= max(2^-22 |v|, 2^-36) at max = 2^15.
 #include <cstdio>
 #include <cstdlib>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "eps_kernels.h"
@@ -35,7 +47,9 @@
 namespace {
 
 constexpr int GBM = 128;
-constexpr int GBK = 32;
+constexpr int GBK = 32;         // K values per pipeline stage, TF32 (one 128-byte swizzled row = 32 fp32)
+constexpr int GBK16 = 64;       // K values per pipeline stage, FP16 (one 128-byte swizzled row = 64 fp16)
+constexpr int ARITH_F16X3 = 6;  // value of `passes` that selects the split-fp16 arithmetic (1, 3: TF32 passes)
 constexpr int ASTAGES = 2;      // A-operand stages in TMEM (2 x (hi + lo) x 32 columns = 128 columns)
 constexpr int MAX_BSTAGES = 4;  // B-operand stages in shared memory (as many as fit)
 constexpr int MAX_BN = 192;     // accumulators: main + small = 2*BN columns, + 128 for A  <= 512 TMEM columns
@@ -55,7 +69,8 @@ struct TcGemmArgs {
   const float* packed;  // [ntiles][nk][2][BN*32]
   int BN;               // column-tile width: multiple of 16, <= MAX_BN
   int bstages;          // shared-memory stages for B
-  int passes;
+  int passes;           // MMA passes per product: 3 (split) or 1
+  const uint32_t* core_absmax;  // F16: bits of max|core| (written by absmax_kernel), fixes the core's power-of-two scale
   float* out;           // MODE_STORE: [np][ldc]; MODE_FWD: out[P][O] (absolute patches); MODE_DKR2: [np][Bn]
   long long ldc;
   float* tsave;         // MODE_FWD, training: the accumulator rows T[p][(o, b)] are also stored here, [P][Ncols]
@@ -67,9 +82,40 @@ struct TcGemmArgs {
 //   MODE_STORE: element(c, k) = core[c*N + k]           (c = a, k = n)
 //   MODE_DKR2 : element(c, k) = core[k*N + c]           (c = n, k = a)
 //   MODE_FWD  : element(c, k) = core[(k*Bn + b)*O + o]  (c = o*Bn + b, k = a)
+// exponent e with max = f * 2^e, f in [0.5, 1) (0 for max == 0 / inf / nan): the core is scaled by 2^(15 - e)
+__device__ __forceinline__ int core_scale_exp(uint32_t absmax_bits) {
+  const float m = __uint_as_float(absmax_bits);
+  if (!(m > 0.f) || !(m < 3.0e38f)) return 0;
+  int e;
+  frexpf(m, &e);
+  return 15 - e;
+}
+// v -> (fp16(v), fp16((v - fp16(v)) * 2^11)) for two values, packed low half = first value
+__device__ __forceinline__ void split_f16x2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(v0, v1);
+  const float r0 = (v0 - __low2float(h)) * 2048.f, r1 = (v1 - __high2float(h)) * 2048.f;
+  const __half2 l = __floats2half2_rn(r0, r1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__global__ void absmax_kernel(const float* __restrict__ v, long long n, uint32_t* __restrict__ out) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(v[i]));   // fmaxf drops NaNs; an inf core stays inf and disables the scaling
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));   // non-negative floats order like their bit patterns
+}
+
+template <bool F16>
 __global__ void pack_core_kernel(const float* __restrict__ core, float* __restrict__ dst, EpsGeom g, int mode, int BN,
-                                 int Ncols, int Kdim, int ntiles, int nk, int passes) {
-  const long long total = (long long)ntiles * nk * BN * 8;  // one thread per 16-byte chunk (4 consecutive k)
+                                 int Ncols, int Kdim, int ntiles, int nk, int passes, const uint32_t* __restrict__ absmax) {
+  constexpr int KV = F16 ? 8 : 4;      // K values per 16-byte chunk
+  constexpr int KS = F16 ? GBK16 : GBK;
+  const long long total = (long long)ntiles * nk * BN * 8;  // one thread per 16-byte chunk
+  float scale = 1.f;
+  if (F16) scale = scalbnf(1.f, core_scale_exp(*absmax));
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c16 = (int)(i & 7);
     long long r = i >> 3;
@@ -78,11 +124,13 @@ __global__ void pack_core_kernel(const float* __restrict__ core, float* __restri
     const int kc = (int)(r % nk);
     const int tile = (int)(r / nk);
     const int c = tile * BN + rr;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    float v[KV];
+#pragma unroll
+    for (int u = 0; u < KV; ++u) v[u] = 0.f;
     if (c < Ncols) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int k = kc * 32 + c16 * 4 + u;
+      for (int u = 0; u < KV; ++u) {
+        const int k = kc * KS + c16 * KV + u;
         if (k < Kdim) {
           long long idx;
           if (mode == MODE_STORE) idx = (long long)c * g.N + k;
@@ -91,29 +139,40 @@ __global__ void pack_core_kernel(const float* __restrict__ core, float* __restri
             const int o = c / g.Bn, b = c - o * g.Bn;
             idx = ((long long)k * g.Bn + b) * g.O + o;
           }
-          v[u] = __ldg(&core[idx]);
+          v[u] = __ldg(&core[idx]) * scale;
         }
       }
     }
-    float4 hi, lo;
-    tc::split_tf32(v[0], hi.x, lo.x);
-    tc::split_tf32(v[1], hi.y, lo.y);
-    tc::split_tf32(v[2], hi.z, lo.z);
-    tc::split_tf32(v[3], hi.w, lo.w);
     float* tile_base = dst + ((long long)(tile * nk + kc) * 2) * BN * 32;
-    const int off = rr * 32 + ((c16 ^ (rr & 7)) << 2);  // in floats
-    *(float4*)(tile_base + off) = hi;
-    if (passes == 3) *(float4*)(tile_base + BN * 32 + off) = lo;
+    const int off = rr * 32 + ((c16 ^ (rr & 7)) << 2);  // in 4-byte units
+    if (F16) {
+      uint4 hi, lo;
+      split_f16x2(v[0], v[1], hi.x, lo.x);
+      split_f16x2(v[2], v[3], hi.y, lo.y);
+      split_f16x2(v[4 % KV], v[5 % KV], hi.z, lo.z);
+      split_f16x2(v[6 % KV], v[7 % KV], hi.w, lo.w);
+      *(uint4*)(tile_base + off) = hi;
+      if (passes == 3) *(uint4*)(tile_base + BN * 32 + off) = lo;
+    } else {
+      float4 hi, lo;
+      tc::split_tf32(v[0], hi.x, lo.x);
+      tc::split_tf32(v[1], hi.y, lo.y);
+      tc::split_tf32(v[2], hi.z, lo.z);
+      tc::split_tf32(v[3], hi.w, lo.w);
+      *(float4*)(tile_base + off) = hi;
+      if (passes == 3) *(float4*)(tile_base + BN * 32 + off) = lo;
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ the GEMM
-template <int MODE>
+template <int MODE, bool F16>
 __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcGemmArgs a) {
   extern __shared__ unsigned char smem_dyn[];
   const EpsGeom& g = a.g;
+  constexpr int KS = F16 ? GBK16 : GBK;                // K values per pipeline stage
   const int Q = g.Q, O = g.O, BN = a.BN, NB = a.bstages;
-  const uint32_t B_BYTES = (uint32_t)BN * GBK * 4;     // one part (hi or lo) of a B stage
+  const uint32_t B_BYTES = (uint32_t)BN * 128;         // one part (hi or lo) of a B stage: BN rows of 128 bytes
   const uint32_t STAGE_BYTES = 2 * B_BYTES;            // multiple of 1024 (BN % 16 == 0)
   unsigned char* base = smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* stages = base;
@@ -129,10 +188,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
   //   eidx[..] = MODE_FWD: bh | bl << 16 for b in [0, 2*Bn) (doubled so 32 consecutive b never wrap the table);
   //              MODE_DKR2: o | last << 8 for the BN columns of a tile
   uint32_t* kidx = (uint32_t*)(outs + ((MODE == MODE_FWD) ? O * 128 : 0));
-  const int nkidx = a.nk * GBK;
+  const int nkidx = a.nk * KS;
   uint32_t* eidx = kidx + nkidx;
   const int neidx = (MODE == MODE_FWD) ? 2 * g.Bn : (MODE == MODE_DKR2 ? ((BN + 31) & ~31) : 0);
-  uint64_t* bars = (uint64_t*)(eidx + ((neidx + 1) & ~1));
+  // F16: power-of-two exponents of the per-patch normalisation: [0][pr] generated operand, [1][pr] epilogue factors
+  int* rowexp = (int*)(eidx + ((neidx + 1) & ~1));
+  uint64_t* bars = (uint64_t*)(rowexp + 256);
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * MAX_BSTAGES + 2 * ASTAGES + 2);
   const uint32_t bar_fullB0 = tc::smem_u32(bars), bar_emptyB0 = bar_fullB0 + 8 * MAX_BSTAGES;
   const uint32_t bar_fullA0 = bar_emptyB0 + 8 * MAX_BSTAGES, bar_emptyA0 = bar_fullA0 + 8 * ASTAGES;
@@ -140,6 +201,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
   // setup-only scratch aliased onto the (not yet used) B stages: x [n*Q][128] and gout [O][128]
   float* xs = (float*)stages;
   float* gsx = xs + g.n * Q * 128;
+  int* fexp = (int*)(gsx + O * 128);                   // F16 only: [n + 1][128] exponents of the factors and of gout
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int pl0 = blockIdx.x * GBM;                 // first patch of this CTA, relative to the launch
@@ -179,6 +241,38 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
     }
   }
   __syncthreads();
+  if (F16) {
+    // range normalisation for fp16: scale every factor vector (and the gout row) of a patch by a power of two so that
+    // its largest magnitude lies in [0.5, 1); exact, undone by the epilogue through rowexp
+    for (int idx = tid; idx < (g.n + 1) * 128; idx += G_THREADS) {
+      const int pr = idx & 127, j = idx >> 7;
+      const bool isg = j == g.n;
+      if (isg && !(a.withG || MODE == MODE_DKR2)) { fexp[idx] = 0; continue; }
+      float* v = isg ? gsx + pr : xs + j * Q * 128 + pr;
+      const int cnt = isg ? O : Q;
+      float m = 0.f;
+      for (int q = 0; q < cnt; ++q) m = fmaxf(m, fabsf(v[q * 128]));
+      int e = 0;
+      if (m > 0.f && m < 3.0e38f) frexpf(m, &e);
+      // MODE_DKR2 uses gout only in the epilogue (fp32): keep it as is
+      if (isg && !a.withG) e = 0;
+      if (e != 0)
+        for (int q = 0; q < cnt; ++q) v[q * 128] = scalbnf(v[q * 128], -e);
+      fexp[idx] = e;
+    }
+    __syncthreads();
+    if (tid < 128) {
+      int ea = 0, eb = 0;
+      for (int j = 0; j < g.n; ++j) {
+        const bool in_gen = (j >= a.jh0 && j < a.jh0 + a.cnth + a.cntl);
+        if (in_gen) ea += fexp[j * 128 + tid];
+        else eb += fexp[j * 128 + tid];
+      }
+      if (a.withG) ea += fexp[g.n * 128 + tid];
+      rowexp[tid] = ea;
+      rowexp[128 + tid] = eb;
+    }
+  }
   {
     // table entry e of a group of `cnt` factors starting at factor j0: prod_u x[j0+u][digit_u(e)] (digit 0 slowest)
     auto kr_entry = [&](int j0, int cnt, int e, int pr) -> float {
@@ -190,7 +284,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
       }
       return v;
     };
-    for (int idx = tid; idx < a.KH * 128; idx += G_THREADS) tabKH[idx] = kr_entry(a.jh0, a.cnth, idx >> 7, idx & 127);
+    // F16: the generated row carries a factor 2^15 (largest entry in [2^(15 - #factors), 2^15))
+    const float gen_scale = F16 ? 32768.f : 1.f;
+    for (int idx = tid; idx < a.KH * 128; idx += G_THREADS) tabKH[idx] = gen_scale * kr_entry(a.jh0, a.cnth, idx >> 7, idx & 127);
     for (int idx = tid; idx < nKL * 128; idx += G_THREADS) {
       const int pr = idx & 127, eo = idx >> 7;
       int e = eo;
@@ -231,6 +327,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
   tc::tc_fence_before();
   __syncthreads();  // tables complete, xs/gsx scratch (aliasing the stages) dead from here on
   tc::tc_fence_after();
+  // F16: exponent that turns an accumulator value into the true product: patch normalisation, 2^15 of the generated
+  // row and the core's global scale
+  const int core_exp = F16 ? core_scale_exp(__ldg(a.core_absmax)) : 0;
   const uint32_t tmem_main = *tmem_slot;
   const uint32_t tmem_small = tmem_main + (uint32_t)BN;
   const uint32_t tmem_a0 = tmem_main + 2u * (uint32_t)BN;   // stage s: hi at +64*s, lo at +64*s + 32
@@ -255,7 +354,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    const uint32_t idesc = tc::make_idesc_tf32(GBM, BN);
+    const uint32_t idesc = F16 ? tc::make_idesc_f16(GBM, BN) : tc::make_idesc_tf32(GBM, BN);
     long long dbg_waitA = 0, dbg_waitB = 0, dbg_waitAcc = 0, dbg_start = TCG_CLK();
     int sa = 0, sb_ = 0;
     uint32_t pha = 0, phb = 0;     // parities of the full barriers
@@ -279,14 +378,22 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
           const uint64_t db_lo = db_hi + part_adv;
           const uint32_t a_hi = tmem_a0 + (uint32_t)(sa * 64), a_lo = a_hi + 32;
 #pragma unroll
-          for (int k = 0; k < GBK / 8; ++k) {
-            const uint64_t adv = (uint64_t)(k * 2);     // 8 fp32 = 32 bytes >> 4 along the K-major smem rows
+          for (int k = 0; k < 4; ++k) {                 // 4 MMAs of 32 bytes of K per row: 8 x tf32 or 16 x fp16
+            const uint64_t adv = (uint64_t)(k * 2);     // 32 bytes >> 4 along the K-major smem rows
             const uint32_t acol = (uint32_t)(k * 8);    // 8 TMEM columns
             const uint32_t first = (kc == 0 && k == 0) ? 0u : 1u;
-            tc::umma_tf32_ts(tmem_main, a_hi + acol, db_hi + adv, idesc, first);
-            if (a.passes == 3) {
-              tc::umma_tf32_ts(tmem_small, a_hi + acol, db_lo + adv, idesc, first);
-              tc::umma_tf32_ts(tmem_small, a_lo + acol, db_hi + adv, idesc, 1u);
+            if (F16) {
+              tc::umma_f16_ts(tmem_main, a_hi + acol, db_hi + adv, idesc, first);
+              if (a.passes == 3) {
+                tc::umma_f16_ts(tmem_small, a_hi + acol, db_lo + adv, idesc, first);
+                tc::umma_f16_ts(tmem_small, a_lo + acol, db_hi + adv, idesc, 1u);
+              }
+            } else {
+              tc::umma_tf32_ts(tmem_main, a_hi + acol, db_hi + adv, idesc, first);
+              if (a.passes == 3) {
+                tc::umma_tf32_ts(tmem_small, a_hi + acol, db_lo + adv, idesc, first);
+                tc::umma_tf32_ts(tmem_small, a_lo + acol, db_hi + adv, idesc, 1u);
+              }
             }
           }
           tc::umma_commit(bar_emptyA0 + 8 * sa);
@@ -313,9 +420,31 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
     long long dbg_pwait = 0, dbg_pst = 0, dbg_pgen = 0, tprev = TCG_CLK();
     for (int t = 0; t < a.ntiles; ++t) {
       for (int kc = 0; kc < a.nk; ++kc) {
-        const int k0 = kc * GBK;
-        float hi[GBK], lo[GBK];
-        {
+        const int k0 = kc * KS;
+        uint32_t hi[32], lo[32];   // one 32-column TMEM slab each: 32 tf32 values or 64 packed fp16 values
+        if (F16) {
+          const float* tg = tabG + pr;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t id[32];
+            const uint4* kp = (const uint4*)(kidx + k0 + 32 * h);   // warp-uniform, 16-byte aligned
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4) {
+              const uint4 u = kp[q4];
+              id[4 * q4] = u.x; id[4 * q4 + 1] = u.y; id[4 * q4 + 2] = u.z; id[4 * q4 + 3] = u.w;
+            }
+            float v[32];
+            if (a.three) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = th[(id[j] & 0x3FF) * 128] * tl[((id[j] >> 10) & 0x3FF) * 128] * tg[(id[j] >> 20) * 128];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = th[(id[j] & 0xFFFF) * 128] * tl[(id[j] >> 16) * 128];
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) split_f16x2(v[2 * j], v[2 * j + 1], hi[16 * h + j], lo[16 * h + j]);
+          }
+        } else {
           uint32_t id[GBK];
           const uint4* kp = (const uint4*)(kidx + k0);   // warp-uniform, 16-byte aligned
 #pragma unroll
@@ -323,14 +452,20 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
             const uint4 u = kp[q4];
             id[4 * q4] = u.x; id[4 * q4 + 1] = u.y; id[4 * q4 + 2] = u.z; id[4 * q4 + 3] = u.w;
           }
+          float fh, fl;
           if (a.three) {
             const float* tg = tabG + pr;
 #pragma unroll
-            for (int j = 0; j < GBK; ++j)
-              tc::split_tf32(th[(id[j] & 0x3FF) * 128] * tl[((id[j] >> 10) & 0x3FF) * 128] * tg[(id[j] >> 20) * 128], hi[j], lo[j]);
+            for (int j = 0; j < GBK; ++j) {
+              tc::split_tf32(th[(id[j] & 0x3FF) * 128] * tl[((id[j] >> 10) & 0x3FF) * 128] * tg[(id[j] >> 20) * 128], fh, fl);
+              hi[j] = __float_as_uint(fh); lo[j] = __float_as_uint(fl);
+            }
           } else {
 #pragma unroll
-            for (int j = 0; j < GBK; ++j) tc::split_tf32(th[(id[j] & 0xFFFF) * 128] * tl[(id[j] >> 16) * 128], hi[j], lo[j]);
+            for (int j = 0; j < GBK; ++j) {
+              tc::split_tf32(th[(id[j] & 0xFFFF) * 128] * tl[(id[j] >> 16) * 128], fh, fl);
+              hi[j] = __float_as_uint(fh); lo[j] = __float_as_uint(fl);
+            }
           }
         }
         long long t0 = TCG_CLK();
@@ -338,8 +473,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
         long long t1 = TCG_CLK();
         tc::tc_fence_after();
         const uint32_t dst = tmem_a0 + lane_base + (uint32_t)(sa * 64);
-        tc::tmem_st32(dst, hi);
-        if (a.passes == 3) tc::tmem_st32(dst + 32, lo);
+        tc::tmem_st32_u(dst, hi);
+        if (a.passes == 3) tc::tmem_st32_u(dst + 32, lo);
         tc::tmem_st_wait();
         tc::tc_fence_before();
         __syncwarp();
@@ -366,6 +501,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
     int db = 0;                              // MODE_DKR2: next b to store
     const float* eH = tabE + pr;
     const float* eL = tabE + g.BH * 128 + pr;
+    // F16: accumulator -> true value is a multiplication by 2^kexp, applied as two exact factors (|kexp| can exceed 127)
+    float sc1 = 1.f, sc2 = 1.f, fsc1 = 1.f, fsc2 = 1.f;   // sc: generated operand only (T, dKR1, dKR2); fsc: + epilogue factors
+    if (F16) {
+      const int kexp = rowexp[pr] - 15 - core_exp;
+      sc1 = scalbnf(1.f, kexp / 2); sc2 = scalbnf(1.f, kexp - kexp / 2);
+      const int fexp_all = kexp + rowexp[128 + pr];
+      fsc1 = scalbnf(1.f, fexp_all / 2); fsc2 = scalbnf(1.f, fexp_all - fexp_all / 2);
+    }
     long long dbg_epi = 0;
     for (int t = 0; t < a.ntiles; ++t) {
       tc::mbar_wait(bar_accfull, (uint32_t)(t & 1));
@@ -385,9 +528,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
           float w[32];
           tc::tmem_ld32(tmem_small + lane_base + (uint32_t)cb, w);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += w[i];
+          for (int i = 0; i < 32; ++i) v[i] = F16 ? fmaf(w[i], 1.f / 2048.f, v[i]) : v[i] + w[i];
         }
         if (MODE == MODE_STORE) {
+          if (F16) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = v[i] * sc1 * sc2;
+          }
           if (pvalid) {
             float* crow = a.out + (long long)pl * a.ldc;
             const int nb = n0 + cb;
@@ -406,11 +553,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
             const int nb = n0 + cb;
             if (cb + 32 <= BN && nb + 32 <= a.Ncols && (a.Ncols & 3) == 0) {
 #pragma unroll
-              for (int i = 0; i < 32; i += 4) *(float4*)(trow + nb + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              for (int i = 0; i < 32; i += 4)
+                *(float4*)(trow + nb + i) = F16 ? make_float4(v[i] * sc1 * sc2, v[i + 1] * sc1 * sc2, v[i + 2] * sc1 * sc2, v[i + 3] * sc1 * sc2)
+                                                : make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (cb + i < BN && nb + i < a.Ncols) trow[nb + i] = v[i];
+                if (cb + i < BN && nb + i < a.Ncols) trow[nb + i] = F16 ? v[i] * sc1 * sc2 : v[i];
             }
           }
           // columns cb..cb+31 are b = fb, fb+1, ... (wrapping to the next o at b == Bn; Bn >= 32: at most one wrap)
@@ -455,7 +604,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
             if (i < nvalid) {
               s = fmaf(v[i], gv[i], s);
               if (id[i] & 0x100u) {
-                if (pvalid) a.out[(long long)pl * g.Bn + db] = s;
+                if (pvalid) a.out[(long long)pl * g.Bn + db] = F16 ? s * sc1 * sc2 : s;
                 s = 0.f; ++db;
               }
             }
@@ -474,7 +623,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
     if (a.dbg && warp == 8 && lane == 0) a.dbg[(long long)blockIdx.x * 8 + 7] = dbg_epi;
     if (MODE == MODE_FWD && pvalid) {
       float* orow = a.out + (pt0 + pr) * O;
-      for (int o = 0; o < O; ++o) orow[o] = outs[o * 128 + pr];
+      for (int o = 0; o < O; ++o) orow[o] = F16 ? outs[o * 128 + pr] * fsc1 * fsc2 : outs[o * 128 + pr];
     }
   }
   tc::tc_fence_before();
@@ -500,18 +649,18 @@ inline GemmShape shape_for(const EpsGeom& g, int mode) {
   return s;
 }
 
+// the K extent of a stage is 64 (fp16) or 32 (tf32); the index table is sized for the smaller one (the larger table),
+// so that one tile-width choice serves both arithmetics
 inline size_t gemm_fixed_smem(const EpsGeom& g, const GemmShape& s, int mode) {
   const int nE = (mode == MODE_FWD) ? (g.BH + g.BL) : (mode == MODE_DKR2 ? g.O : 0);
   const size_t ktab = s.three ? (size_t)(s.KH + 1 + s.KLb + g.O) : (size_t)(s.KH + 1 + s.KL);
-  const size_t nkidx = (size_t)((s.Kdim + GBK - 1) / GBK) * GBK;
+  const size_t nkidx = (size_t)((s.Kdim + GBK16 - 1) / GBK16) * GBK16;
   const size_t neidx = (mode == MODE_FWD) ? 2 * (size_t)g.Bn : (mode == MODE_DKR2 ? (size_t)MAX_BN : 0);
-  return 1024 + (ktab + nE + (mode == MODE_FWD ? g.O : 0)) * 128 * 4 + (nkidx + neidx + 2) * 4 +
+  return 1024 + (ktab + nE + (mode == MODE_FWD ? g.O : 0)) * 128 * 4 + (nkidx + neidx + 2) * 4 + 256 * 4 +
          (2 * MAX_BSTAGES + 2 * ASTAGES + 2) * 8 + 16;
 }
-inline size_t bstage_bytes(int BN) { return 2 * (size_t)BN * GBK * 4; }
-
-inline size_t gemm_fixed_smem(const EpsGeom& g, const GemmShape& s, int mode);
-inline size_t bstage_bytes(int BN);
+inline size_t bstage_bytes(int BN) { return 2 * (size_t)BN * 128; }   // hi + lo parts, BN rows of 128 bytes
+inline int stage_k(int passes) { return passes == ARITH_F16X3 ? GBK16 : GBK; }
 // two-level generated operand when its tables leave room for at least two 64-column stages, else (gout-folded operand
 // only) the three-level product
 inline GemmShape shape_auto(const EpsGeom& g, int mode) {
@@ -529,7 +678,7 @@ inline int pick_bstages(const EpsGeom& g, int mode, int BN) {
   int nb = (int)((TCG_SMEM_LIMIT - fixed) / bstage_bytes(BN));
   if (nb > MAX_BSTAGES) nb = MAX_BSTAGES;
   if (nb < 2) return 0;
-  if ((size_t)(g.n * g.Q + g.O) * 128 * 4 > nb * bstage_bytes(BN)) return 0;
+  if ((size_t)(g.n * g.Q + g.O + g.n + 1) * 128 * 4 > nb * bstage_bytes(BN)) return 0;   // x, gout, exponents
   return nb;
 }
 
@@ -549,11 +698,13 @@ inline int pick_bn(const EpsGeom& g, int mode) {
   return best;
 }
 
+// size of the packed core image (TF32 layout; the fp16 image is half as large and uses the same buffer)
 inline size_t packed_floats(const EpsGeom& g, int mode, int BN) {
   const GemmShape s = shape_auto(g, mode);
   long long ntiles = (s.Ncols + BN - 1) / BN, nk = (s.Kdim + GBK - 1) / GBK;
   return (size_t)(ntiles * nk * 2 * BN * 32);
 }
+constexpr size_t WS_HEADER = 256;   // first bytes of every workspace: bits of max|core| (fp16 arithmetic)
 
 // patches per launch of the input-gradient GEMMs: their outputs dKR1 / dKR2 go through a scratch buffer of at most
 // 2 GiB (HBM write + read at ~6.5 TB/s costs far less than the launch gaps and partial waves of many small chunks)
@@ -569,9 +720,9 @@ inline long long dx_patch_chunk(const EpsGeom& g) {
   return pc;
 }
 
-template <int MODE>
+template <int MODE, bool F16>
 int launch_gemm_inst(const TcGemmArgs& a, size_t smem, cudaStream_t st) {
-  auto k = tc_gemm_kernel<MODE>;
+  auto k = tc_gemm_kernel<MODE, F16>;
   DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k<<<(a.np + GBM - 1) / GBM, G_THREADS, smem, st>>>(a);
   dctn_count_launch();
@@ -579,14 +730,18 @@ int launch_gemm_inst(const TcGemmArgs& a, size_t smem, cudaStream_t st) {
   return 0;
 }
 
+// `passes`: 1 / 3 = TF32 passes, ARITH_F16X3 = split fp16 (absmax: the slot absmax_kernel filled before run_pack)
 int run_gemm(const EpsGeom& g, int mode, int BN, const float* x, const float* gout, const float* packed, long long p0,
-             int np, float* out, long long ldc, int passes, cudaStream_t st, float* tsave = nullptr) {
+             int np, float* out, long long ldc, int passes, cudaStream_t st, const uint32_t* absmax, float* tsave = nullptr) {
   const GemmShape s = shape_auto(g, mode);
+  const bool f16 = passes == ARITH_F16X3;
+  const int KS = stage_k(passes);
   TcGemmArgs a{};
   a.g = g; a.x = x; a.gout = gout; a.p0 = p0; a.np = np;
   a.jh0 = s.jh0; a.cnth = s.cnth; a.KH = s.KH; a.cntl = s.cntl; a.KLb = s.KLb; a.KL = s.KL; a.Kdim = s.Kdim; a.withG = s.withG; a.three = s.three;
-  a.Ncols = s.Ncols; a.ntiles = (s.Ncols + BN - 1) / BN; a.nk = (s.Kdim + GBK - 1) / GBK;
-  a.packed = packed; a.BN = BN; a.bstages = pick_bstages(g, mode, BN); a.passes = passes; a.out = out; a.ldc = ldc;
+  a.Ncols = s.Ncols; a.ntiles = (s.Ncols + BN - 1) / BN; a.nk = (s.Kdim + KS - 1) / KS;
+  a.packed = packed; a.BN = BN; a.bstages = pick_bstages(g, mode, BN); a.passes = f16 ? 3 : passes; a.out = out; a.ldc = ldc;
+  a.core_absmax = absmax;
   a.tsave = tsave;
   a.dbg = nullptr;
   static long long* dbg_buf = nullptr;
@@ -599,9 +754,9 @@ int run_gemm(const EpsGeom& g, int mode, int BN, const float* x, const float* go
   }
   const size_t smem = gemm_fixed_smem(g, s, mode) + a.bstages * bstage_bytes(BN);
   int rc;
-  if (mode == MODE_STORE) rc = launch_gemm_inst<MODE_STORE>(a, smem, st);
-  else if (mode == MODE_FWD) rc = launch_gemm_inst<MODE_FWD>(a, smem, st);
-  else rc = launch_gemm_inst<MODE_DKR2>(a, smem, st);
+  if (mode == MODE_STORE) rc = f16 ? launch_gemm_inst<MODE_STORE, true>(a, smem, st) : launch_gemm_inst<MODE_STORE, false>(a, smem, st);
+  else if (mode == MODE_FWD) rc = f16 ? launch_gemm_inst<MODE_FWD, true>(a, smem, st) : launch_gemm_inst<MODE_FWD, false>(a, smem, st);
+  else rc = f16 ? launch_gemm_inst<MODE_DKR2, true>(a, smem, st) : launch_gemm_inst<MODE_DKR2, false>(a, smem, st);
   if (a.dbg && rc == 0) {
     static long long host[4096 * 8];
     cudaStreamSynchronize(st);
@@ -617,13 +772,29 @@ int run_gemm(const EpsGeom& g, int mode, int BN, const float* x, const float* go
   return rc;
 }
 
-int run_pack(const EpsGeom& g, int mode, int BN, const float* core, float* dst, int passes, cudaStream_t st) {
+// max|core| -> ws header (fp16 arithmetic only); one call per entry point, before the packs
+int run_absmax(const EpsGeom& g, const float* core, uint32_t* slot, int passes, cudaStream_t st) {
+  if (passes != ARITH_F16X3) return 0;
+  DCTN_CUDA_CHECK_RET(cudaMemsetAsync(slot, 0, sizeof(uint32_t), st));
+  const long long n = (long long)g.A * g.N;
+  int blocks = (int)((n + 1023) / 1024);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  absmax_kernel<<<blocks, 256, 0, st>>>(core, n, slot);
+  dctn_count_launch();
+  DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  return 0;
+}
+
+int run_pack(const EpsGeom& g, int mode, int BN, const float* core, float* dst, int passes, cudaStream_t st, const uint32_t* absmax) {
   const GemmShape s = shape_auto(g, mode);
-  const int ntiles = (s.Ncols + BN - 1) / BN, nk = (s.Kdim + GBK - 1) / GBK;
+  const bool f16 = passes == ARITH_F16X3;
+  const int KS = stage_k(passes);
+  const int ntiles = (s.Ncols + BN - 1) / BN, nk = (s.Kdim + KS - 1) / KS;
   long long total = (long long)ntiles * nk * BN * 8;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  pack_core_kernel<<<blocks, 256, 0, st>>>(core, dst, g, mode, BN, s.Ncols, s.Kdim, ntiles, nk, passes);
+  if (f16) pack_core_kernel<true><<<blocks, 256, 0, st>>>(core, dst, g, mode, BN, s.Ncols, s.Kdim, ntiles, nk, 3, absmax);
+  else pack_core_kernel<false><<<blocks, 256, 0, st>>>(core, dst, g, mode, BN, s.Ncols, s.Kdim, ntiles, nk, passes, absmax);
   dctn_count_launch();
   DCTN_CUDA_CHECK_RET(cudaGetLastError());
   return 0;
@@ -647,12 +818,12 @@ bool tcg_supported(const EpsGeom& g, int kind) {
 }
 
 size_t tcg_workspace_bytes(const EpsGeom& g, int kind) {
-  if (kind == 0) return packed_floats(g, MODE_FWD, pick_bn(g, MODE_FWD)) * 4 + 256;
+  if (kind == 0) return WS_HEADER + packed_floats(g, MODE_FWD, pick_bn(g, MODE_FWD)) * 4 + 256;
   if (kind == 2 || kind == 3) {
     const long long pc = dx_patch_chunk(g);
     size_t f = packed_floats(g, MODE_STORE, pick_bn(g, MODE_STORE)) + (size_t)pc * ((size_t)g.A + g.Bn) + (size_t)g.P * g.n * g.Q;
     if (kind == 2) f += packed_floats(g, MODE_DKR2, pick_bn(g, MODE_DKR2));
-    return f * 4 + 1024;
+    return WS_HEADER + f * 4 + 1024;
   }
   return 0;
 }
@@ -661,10 +832,12 @@ int tc_forward(const EpsGeom& g, const float* x, const float* core, float* out, 
                float* tsave) {
   const int BN = pick_bn(g, MODE_FWD);
   if (!BN) return dctn_set_error(-2, "tcgen05 forward kernel does not support this shape");
-  float* packed = (float*)ws;
-  int rc = run_pack(g, MODE_FWD, BN, core, packed, passes, st);
+  uint32_t* absmax = (uint32_t*)ws;
+  float* packed = (float*)((char*)ws + WS_HEADER);
+  int rc = run_absmax(g, core, absmax, passes, st);
   if (rc) return rc;
-  return run_gemm(g, MODE_FWD, BN, x, nullptr, packed, 0, (int)g.P, out, 0, passes, st, tsave);
+  if ((rc = run_pack(g, MODE_FWD, BN, core, packed, passes, st, absmax))) return rc;
+  return run_gemm(g, MODE_FWD, BN, x, nullptr, packed, 0, (int)g.P, out, 0, passes, st, absmax, tsave);
 }
 
 size_t tcg_saved_bytes(const EpsGeom& g) { return (size_t)g.P * (size_t)g.N * sizeof(float); }
@@ -710,17 +883,19 @@ static int backward_input_impl(const EpsGeom& g, const float* x, const float* co
   const int BN1 = pick_bn(g, MODE_STORE), BN2 = tsaved ? 0 : pick_bn(g, MODE_DKR2);
   if (!BN1 || (!tsaved && !BN2)) return dctn_set_error(-2, "tcgen05 input-gradient kernels do not support this shape");
   const long long pc = dx_patch_chunk(g);
-  float* packed1 = (float*)ws;
+  uint32_t* absmax = (uint32_t*)ws;
+  float* packed1 = (float*)((char*)ws + WS_HEADER);
   float* packed2 = packed1 + ((packed_floats(g, MODE_STORE, BN1) + 63) & ~(size_t)63);
   float* dkr1 = packed2 + (tsaved ? 0 : ((packed_floats(g, MODE_DKR2, BN2) + 63) & ~(size_t)63));
   float* dkr2 = dkr1 + (size_t)pc * g.A;
   float* dxp = dkr2 + (size_t)pc * g.Bn;
   int rc;
-  if ((rc = run_pack(g, MODE_STORE, BN1, core, packed1, passes, st))) return rc;
-  if (!tsaved && (rc = run_pack(g, MODE_DKR2, BN2, core, packed2, passes, st))) return rc;
+  if ((rc = run_absmax(g, core, absmax, passes, st))) return rc;
+  if ((rc = run_pack(g, MODE_STORE, BN1, core, packed1, passes, st, absmax))) return rc;
+  if (!tsaved && (rc = run_pack(g, MODE_DKR2, BN2, core, packed2, passes, st, absmax))) return rc;
   for (long long p0 = 0; p0 < g.P; p0 += pc) {
     const int np = (int)((g.P - p0 < pc) ? (g.P - p0) : pc);
-    if ((rc = run_gemm(g, MODE_STORE, BN1, x, gout, packed1, p0, np, dkr1, g.A, passes, st))) return rc;
+    if ((rc = run_gemm(g, MODE_STORE, BN1, x, gout, packed1, p0, np, dkr1, g.A, passes, st, absmax))) return rc;
     if ((rc = launch_loo<float>(g, x, dkr1, p0, np, 0, dxp, st))) return rc;
     if (tsaved) {
       const bool vec = (g.Bn & 3) == 0;
@@ -731,7 +906,7 @@ static int backward_input_impl(const EpsGeom& g, const float* x, const float* co
       else dkr2_from_saved_scalar_kernel<<<blocks, 256, 0, st>>>(tsaved, gout, dkr2, p0, np, g.Bn, g.O);
       dctn_count_launch();
       DCTN_CUDA_CHECK_RET(cudaGetLastError());
-    } else if ((rc = run_gemm(g, MODE_DKR2, BN2, x, gout, packed2, p0, np, dkr2, g.Bn, passes, st))) return rc;
+    } else if ((rc = run_gemm(g, MODE_DKR2, BN2, x, gout, packed2, p0, np, dkr2, g.Bn, passes, st, absmax))) return rc;
     if ((rc = launch_loo<float>(g, x, dkr2, p0, np, 1, dxp, st))) return rc;
   }
   return launch_gather_dx<float>(g, dxp, dx, st);

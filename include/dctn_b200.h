@@ -51,7 +51,9 @@ typedef enum dctn_variant {
   DCTN_VARIANT_FFMA = 1, /* CUDA-core FMA kernels, exact fp32/fp64 arithmetic, any shape */
   DCTN_VARIANT_TC3 = 2,  /* tcgen05 TF32 tensor cores, 3-pass split (hi*hi + hi*lo + lo*hi): fp32-accurate */
   DCTN_VARIANT_TC1 = 3,  /* tcgen05 TF32 single pass (rel. err ~1e-3), opt-in only */
-  DCTN_VARIANT_DIRECT = 4 /* thread-per-patch streaming kernel for tiny cores (HBM-bound shapes) */
+  DCTN_VARIANT_DIRECT = 4, /* thread-per-patch streaming kernel for tiny cores (HBM-bound shapes) */
+  DCTN_VARIANT_TCH3 = 5  /* tcgen05 FP16 tensor cores, 3-pass split with power-of-two range normalisation: same 22
+                            significant bits per operand as TC3 at twice the MMA rate; what AUTO uses on large cores */
 } dctn_variant;
 
 typedef enum dctn_ws_kind {

@@ -338,6 +338,8 @@ def test_tc_backward_core_vs_oracle(shape):
     want, _ = O.eps_grads(core.double(), x.double(), gout.double())
     got3 = _raw_call(_lib.WS_BACKWARD_CORE, "tc3", core.to(DEV), x.to(DEV), gout.to(DEV))
     assert rel_err(got3, want) <= 1e-5, "3-pass TF32 must be fp32-accurate"
+    goth = _raw_call(_lib.WS_BACKWARD_CORE, "tch3", core.to(DEV), x.to(DEV), gout.to(DEV))
+    assert rel_err(goth, want) <= 1e-5, "3-pass split fp16 must be fp32-accurate"
     got1 = _raw_call(_lib.WS_BACKWARD_CORE, "tc1", core.to(DEV), x.to(DEV), gout.to(DEV))
     assert rel_err(got1, want) <= 5e-3, "single-pass TF32 (opt-in) tolerance"
 
@@ -354,12 +356,15 @@ def test_tc_backward_core_full_size_vs_fp64(B, H, W, Q, K, Oq):
     err = rel_err(got, want)
     print(f"tc3 dcore full-size rel err {err:.3e}")
     assert err <= 1e-5
+    goth = _raw_call(_lib.WS_BACKWARD_CORE, "tch3", core.to(DEV), x.to(DEV), gout.to(DEV))
+    print(f"tch3 dcore full-size rel err {rel_err(goth, want):.3e}")
+    assert rel_err(goth, want) <= 1e-5
     ffma = _raw_call(_lib.WS_BACKWARD_CORE, "ffma", core.to(DEV), x.to(DEV), gout.to(DEV))
     print(f"ffma dcore full-size rel err {rel_err(ffma, want):.3e}")
     assert rel_err(ffma, want) <= 1e-5
 
 
-@pytest.mark.parametrize("variant,tol", [("tc3", 1e-5), ("tc1", 5e-3)])
+@pytest.mark.parametrize("variant,tol", [("tch3", 1e-5), ("tc3", 1e-5), ("tc1", 5e-3)])
 @pytest.mark.parametrize("shape", TC_SHAPES)
 def test_tc_forward_and_input_grad_vs_oracle(shape, variant, tol):
     """tcgen05 forward (fused KR2 epilogue) and input-gradient (two GEMMs + leave-one-out + gather) vs the oracle."""
@@ -394,6 +399,48 @@ def test_tc_forward_and_input_grad_full_size_vs_fp64(B, H, W, Q, K, Oq):
     print(f"tc3 saved-T path full-size rel err: forward {rel_err(out_s, want):.3e}, input-grad {rel_err(dx_s, want_dx):.3e}")
     assert torch.equal(out_s, got)
     assert rel_err(dx_s, want_dx) <= 1e-5
+    # split-fp16 arithmetic (what AUTO uses): same tolerance
+    got_h = _raw_call(_lib.WS_FORWARD, "tch3", core.to(DEV), x.to(DEV), gout.to(DEV))
+    dx_h = _raw_call(_lib.WS_BACKWARD_INPUT, "tch3", core.to(DEV), x.to(DEV), gout.to(DEV))
+    out_hs, dx_hs = _raw_train_call("tch3", core.to(DEV), x.to(DEV), gout.to(DEV))
+    print(f"tch3 full-size rel err: forward {rel_err(got_h, want):.3e}, input-grad {rel_err(dx_h, want_dx):.3e}, saved-T input-grad {rel_err(dx_hs, want_dx):.3e}")
+    assert rel_err(got_h, want) <= 1e-5 and rel_err(dx_h, want_dx) <= 1e-5 and rel_err(dx_hs, want_dx) <= 1e-5
+    assert torch.equal(out_hs, got_h)
+
+
+@pytest.mark.parametrize("core_scale", [1e-12, 1.0, 1e12])
+def test_tch3_range_normalisation(core_scale):
+    """fp16 has a 5-bit exponent: the split-fp16 kernels rescale every factor vector, the gout row and the core by exact
+    powers of two.  Inputs whose magnitude varies over many decades from pixel to pixel (and a core far outside the fp16
+    range) must come out as accurately as with well-scaled data."""
+    from dctn_b200 import _lib
+
+    B, H, W, Q, K, Oq = 8, 25, 25, 4, 3, 6
+    x, core, gout = _rand_layer(B, H, W, Q, K, Oq, seed=27)
+    gen = torch.Generator().manual_seed(28)
+    # per-pixel magnitudes 10^U(-1.5, 1.5): a 3x3 patch product then spans ~27 decades between patches (fp16 covers 12)
+    x = x * (10.0 ** (torch.rand(1, B, H, W, 1, generator=gen) * 3 - 1.5))
+    gout = gout * (10.0 ** (torch.rand(B, H - K + 1, W - K + 1, 1, generator=gen) * 8 - 4))
+    core = core * core_scale
+    want = O.eps_4step(core.double(), x.double())
+    _, want_dx = O.eps_grads(core.double(), x.double(), gout.double())
+    got = _raw_call(_lib.WS_FORWARD, "tch3", core.to(DEV), x.to(DEV), gout.to(DEV))
+    # row-wise check: every patch individually accurate (a Frobenius norm over all patches would hide the small ones)
+    num = (got.double().cpu() - want).flatten(0, 2).norm(dim=1)
+    den = want.flatten(0, 2).norm(dim=1)
+    assert (num / den).max().item() <= 1e-5
+    # core gradient: a sum over patches of very different magnitude — accurate relative to the whole sum
+    want_dc, _ = O.eps_grads(core.double(), x.double(), gout.double())
+    got_dc = _raw_call(_lib.WS_BACKWARD_CORE, "tch3", core.to(DEV), x.to(DEV), gout.to(DEV))
+    assert rel_err(got_dc, want_dc) <= 1e-5
+    got_dx = _raw_call(_lib.WS_BACKWARD_INPUT, "tch3", core.to(DEV), x.to(DEV), gout.to(DEV))
+    out_s, dx_s = _raw_train_call("tch3", core.to(DEV), x.to(DEV), gout.to(DEV))
+    assert torch.equal(out_s, got)
+    for d in (got_dx, dx_s):
+        # dx of a pixel sums over the patches containing it; compare per image
+        num = (d.double().cpu() - want_dx).flatten(2).norm(dim=2)
+        den = want_dx.flatten(2).norm(dim=2)
+        assert (num / den).max().item() <= 1e-5
 
 
 def _raw_train_call(variant, core, x, gout):
@@ -423,14 +470,15 @@ def _raw_train_call(variant, core, x, gout):
     return out, dx
 
 
+@pytest.mark.parametrize("variant", ["tch3", "tc3"])
 @pytest.mark.parametrize("shape", TC_SHAPES)
-def test_tc_saved_intermediate_path_vs_oracle(shape):
+def test_tc_saved_intermediate_path_vs_oracle(shape, variant):
     """Training forward that keeps T + input gradient from the saved T (one GEMM instead of two) vs the oracle."""
     B, H, W, Q, K, Oq = shape
     x, core, gout = _rand_layer(B, H, W, Q, K, Oq, seed=25)
     want = O.eps_4step(core.double(), x.double())
     _, want_dx = O.eps_grads(core.double(), x.double(), gout.double())
-    out, dx = _raw_train_call("tc3", core.to(DEV), x.to(DEV), gout.to(DEV))
+    out, dx = _raw_train_call(variant, core.to(DEV), x.to(DEV), gout.to(DEV))
     assert rel_err(out, want) <= 1e-5
     assert rel_err(dx, want_dx) <= 1e-5
 
