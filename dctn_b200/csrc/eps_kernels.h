@@ -39,6 +39,14 @@ size_t tcg_workspace_bytes(const EpsGeom& g, int kind);
 int tc_backward_core(const EpsGeom& g, const float* x, const float* gout, float* dcore, void* ws, int passes, cudaStream_t st);
 int tc_backward_input(const EpsGeom& g, const float* x, const float* core, const float* gout, float* dx, void* ws, int passes, cudaStream_t st);
 
+// eps_tc_fast.cu: register-table variant of the two GEMMs above for power-of-two Q, split-fp16 arithmetic
+// (mode 0: input-gradient GEMM dKR1, mode 1: forward)
+bool tcfast_supported(const EpsGeom& g, int mode);
+size_t tcfast_packed_floats(const EpsGeom& g, int mode);
+int tcfast_pack(const EpsGeom& g, int mode, const float* core, float* dst, const uint32_t* absmax, cudaStream_t st);
+int tcfast_gemm(const EpsGeom& g, int mode, const float* x, const float* gout, const float* packed, const uint32_t* absmax,
+                long long p0, int np, float* out, long long ldc, float* tsave, cudaStream_t st);
+
 // ---- logmatmulexp (logmatmulexp.cu)
 template <typename T> int lme_forward(const T* A, const T* B, T* out, int Th, int R, int I, cudaStream_t st);
 template <typename T> int lme_backward(const T* A, const T* B, const T* out, const T* gout, T* dA, T* dB, int Th, int R, int I, cudaStream_t st);

@@ -106,19 +106,8 @@ inline int max_tile_entries(const EpsGeom& g, int three) {
 // tables[chunk][entry][i] for patch p = chunk*64 + i (zeros past P): entries [0,AH): first-half hi group,
 // [AH, AH+AL): first-half lo group, then [.., +BH): second-half hi group, then either BL*O entries (second-half lo group
 // x gout) or, three-level, BL entries (lo group) followed by O entries (gout).
-// exponent e with m = f * 2^e, f in [0.5, 1); 0 for m == 0 / inf / nan
-__device__ __forceinline__ int norm_exp(float m) {
-  int e = 0;
-  if (m > 0.f && m < 3.0e38f) frexpf(m, &e);
-  return e;
-}
-__device__ __forceinline__ void split_f16x2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(v0, v1);
-  const float r0 = (v0 - __low2float(h)) * 2048.f, r1 = (v1 - __high2float(h)) * 2048.f;
-  const __half2 l = __floats2half2_rn(r0, r1);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
+using tc::norm_exp;
+using tc::split_f16x2;
 
 // fp16 arithmetic, pass 1: exps[p] = E_p, *emax = max_p E_p (one thread per patch; *emax starts at INT_MIN)
 __global__ void __launch_bounds__(256) patch_exp_kernel(EpsGeom g, const float* __restrict__ x, const float* __restrict__ gout,

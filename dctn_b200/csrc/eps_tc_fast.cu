@@ -1,0 +1,624 @@
+// Register-table variant of the tcgen05 forward / input-gradient GEMMs (split-fp16 arithmetic only), for layers whose
+// in_size Q is a power of two (config 2: Q = 2 and Q = 4).  Same pipeline as eps_tc_gemm.cu:
+//
+//   C[p][c] = sum_k Gen[p][k] * Bop[k][c]       128 patches per CTA = 128 TMEM lanes, column tiles of BN, K in stages of 64
+//
+// What changes is how the generated operand is produced.  The generic kernel looks two table entries up in shared
+// memory for every generated element; with fp16 MMAs (twice the TF32 rate) those 128 LDS per thread and stage made
+// SHARED-MEMORY BANDWIDTH the limiter — measured with the cycle probes: 1665 cycles of generation per stage against
+// 1152 cycles of MMA, the rest of the pipe waiting (profiles/r01_f16_phase_cycles.txt).  Here
+//   * the K index is ordered (e, kl) with kl in [0, KLR), KLR = Q^cl a power of two <= 16 (compile time): the lo-group
+//     values of a thread's patch, TL[KLR], live in REGISTERS for the whole kernel, and a stage of 64 k needs only
+//     64/KLR loads from the hi table (4 for KLR = 16, down from 128);
+//   * for the input gradient the hi table carries the gout factor: e = (o, hi-group entry), i.e. the reduction index is
+//     ordered (o, b) instead of (b, o); the packed core image is built in the same order (K order is free in a GEMM);
+//   * the forward epilogue uses the same trick for KR2[p][b] = EH[b / ELR] * EL[b % ELR]: EL in registers.
+// No index tables, no per-element shared-memory traffic; shared memory is left to the core stages (TMA writes, MMA
+// reads).  Everything else — TS-form MMAs with the A operand in tensor memory, the main/small accumulator pair, the
+// power-of-two range normalisation, bulk-copied pre-packed core — is as in eps_tc_gemm.cu.
+#include <cstdio>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "eps_kernels.h"
+#include "tc_common.cuh"
+
+#ifdef DCTN_TCG_TIMING
+#define TCF_CLK() clock64()
+#else
+#define TCF_CLK() 0ll
+#endif
+
+namespace {
+
+constexpr int FBM = 128;
+constexpr int FKS = 64;          // K values per stage (one 128-byte row of fp16)
+constexpr int F_ASTAGES = 2;     // A stages in TMEM: 2 x (hi 32 + lo 32 columns)
+constexpr int F_MAX_BSTAGES = 4;
+constexpr int F_MAX_BN = 192;    // main + small accumulators (2 * BN) + 128 columns of A <= 512
+constexpr int F_THREADS = 384;   // warp 0: bulk copies, warp 1: MMA, warp 2: TMEM alloc, warps 4-7: producers, warps 8-11: epilogue
+enum { FMODE_STORE = 0, FMODE_FWD = 1 };
+constexpr size_t F_SMEM_LIMIT = 227 * 1024;
+
+struct FastArgs {
+  EpsGeom g;
+  const float* x;
+  const float* gout;
+  long long p0;
+  int np;
+  int jh0, cnth, cntl;   // generated group: hi factors [jh0, jh0+cnth), lo factors [jh0+cnth, jh0+cnth+cntl) -> TL registers
+  int KHE;               // hi-table entries: Q^cnth (forward) or O * Q^cnth (input gradient, entry = o * Q^cnth + e)
+  int withG;
+  int Kdim;              // KHE * KLR
+  int ej0, ecnth, ecntl; // forward epilogue: KR2 hi factors [ej0, ej0+ecnth), lo factors after them -> EL registers
+  int EHE, ELR;          // Q^ecnth, Q^ecntl
+  int Ncols, ntiles, nk, BN, bstages;
+  const float* packed;   // [ntiles][nk][hi|lo][BN rows x 128 bytes], swizzled
+  const uint32_t* core_absmax;
+  float* out;            // FMODE_STORE: [np][ldc]; FMODE_FWD: out[P][O]
+  long long ldc;
+  float* tsave;          // FMODE_FWD: optional T[P][Ncols]
+  long long* dbg;
+};
+
+// ------------------------------------------------------------------------------------------------ core packing
+// dst[((tile*nk + kc)*2 + part) * BN*128 bytes + swizzled(row rr, 16-byte chunk c16)] = 8 consecutive k of core column c
+//   FMODE_FWD  : element(c = o*Bn + b, k = a)        = core[(a*Bn + b)*O + o]
+//   FMODE_STORE: element(c = a, k = o*Bn + b)         = core[a*N + b*O + o]
+__global__ void fast_pack_kernel(const float* __restrict__ core, float* __restrict__ dst, EpsGeom g, int mode, int BN, int Ncols,
+                                 int Kdim, int ntiles, int nk, const uint32_t* __restrict__ absmax) {
+  const long long total = (long long)ntiles * nk * BN * 8;
+  const float scale = scalbnf(1.f, tc::core_scale_exp(*absmax));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c16 = (int)(i & 7);
+    long long r = i >> 3;
+    const int rr = (int)(r % BN);
+    r /= BN;
+    const int kc = (int)(r % nk);
+    const int tile = (int)(r / nk);
+    const int c = tile * BN + rr;
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = 0.f;
+    if (c < Ncols) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = kc * FKS + c16 * 8 + u;
+        if (k < Kdim) {
+          long long idx;
+          if (mode == FMODE_STORE) {
+            const int o = k / g.Bn, b = k - o * g.Bn;
+            idx = (long long)c * g.N + (long long)b * g.O + o;
+          } else {
+            const int o = c / g.Bn, b = c - o * g.Bn;
+            idx = ((long long)k * g.Bn + b) * g.O + o;
+          }
+          v[u] = __ldg(&core[idx]) * scale;
+        }
+      }
+    }
+    uint4 hi, lo;
+    tc::split_f16x2(v[0], v[1], hi.x, lo.x);
+    tc::split_f16x2(v[2], v[3], hi.y, lo.y);
+    tc::split_f16x2(v[4], v[5], hi.z, lo.z);
+    tc::split_f16x2(v[6], v[7], hi.w, lo.w);
+    float* tile_base = dst + ((long long)(tile * nk + kc) * 2) * BN * 32;
+    const int off = rr * 32 + ((c16 ^ (rr & 7)) << 2);  // in 4-byte units
+    *(uint4*)(tile_base + off) = hi;
+    *(uint4*)(tile_base + BN * 32 + off) = lo;
+  }
+}
+
+// product over `cnt` factors starting at j0 of the normalised x values of patch row pr, for table entry e (digit 0 slowest)
+__device__ __forceinline__ float kr_entry(const float* xs, int Q, int j0, int cnt, int e, int pr) {
+  float v = 1.f;
+  for (int u = cnt - 1; u >= 0; --u) {
+    const int d = e % Q;
+    e /= Q;
+    v *= xs[((j0 + u) * Q + d) * 128 + pr];
+  }
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------ the GEMM
+template <int MODE, int KLR>
+__global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid_constant__ FastArgs a) {
+  extern __shared__ unsigned char smem_dyn[];
+  const EpsGeom& g = a.g;
+  const int Q = g.Q, O = g.O, BN = a.BN, NB = a.bstages;
+  constexpr int RUNS = FKS / KLR;                      // hi-table entries per stage
+  const uint32_t B_BYTES = (uint32_t)BN * 128;
+  const uint32_t STAGE_BYTES = 2 * B_BYTES;
+  unsigned char* base = smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u);
+  unsigned char* stages = base;
+  const int nHrows = a.nk * RUNS;                      // >= KHE; the tail rows are zero (K padding)
+  float* tabH = (float*)(base + NB * STAGE_BYTES);     // [nHrows][128]
+  float* tabEH = tabH + nHrows * 128;                  // FMODE_FWD: [EHE][128]
+  float* outs = tabEH + (MODE == FMODE_FWD ? a.EHE * 128 : 0);   // FMODE_FWD: [O][128]
+  int* rowexp = (int*)(outs + (MODE == FMODE_FWD ? O * 128 : 0));  // [2][128]
+  uint64_t* bars = (uint64_t*)(rowexp + 256);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * F_MAX_BSTAGES + 2 * F_ASTAGES + 2);
+  const uint32_t bar_fullB0 = tc::smem_u32(bars), bar_emptyB0 = bar_fullB0 + 8 * F_MAX_BSTAGES;
+  const uint32_t bar_fullA0 = bar_emptyB0 + 8 * F_MAX_BSTAGES, bar_emptyA0 = bar_fullA0 + 8 * F_ASTAGES;
+  const uint32_t bar_accfull = bar_emptyA0 + 8 * F_ASTAGES, bar_accempty = bar_accfull + 8;
+  // setup-only scratch aliased onto the B stages: x [n*Q][128], gout [O][128], exponents [(n+1)][128]
+  float* xs = (float*)stages;
+  float* gsx = xs + g.n * Q * 128;
+  int* fexp = (int*)(gsx + O * 128);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int pl0 = blockIdx.x * FBM;
+  const long long pt0 = a.p0 + pl0;
+
+  // ---------------- setup
+  if (tid == 0) {
+    for (int s = 0; s < F_MAX_BSTAGES; ++s) {
+      tc::mbar_init(bar_fullB0 + 8 * s, 1);
+      tc::mbar_init(bar_emptyB0 + 8 * s, 1);
+    }
+    for (int s = 0; s < F_ASTAGES; ++s) {
+      tc::mbar_init(bar_fullA0 + 8 * s, 4);
+      tc::mbar_init(bar_emptyA0 + 8 * s, 1);
+    }
+    tc::mbar_init(bar_accfull, 1);
+    tc::mbar_init(bar_accempty, 4);
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc(tc::smem_u32(tmem_slot), 512);
+  {
+    const int NX = g.n * Q;
+    for (int idx = tid; idx < NX * 128; idx += F_THREADS) {
+      const int pr = idx & 127, jq = idx >> 7;
+      const long long p = pt0 + pr;
+      float v = 0.f;
+      if (p < g.P) v = __ldg(&a.x[patch_origin(g, p) + g.foff[jq / Q] + jq % Q]);
+      xs[jq * 128 + pr] = v;
+    }
+    if (a.withG)
+      for (int idx = tid; idx < O * 128; idx += F_THREADS) {
+        const int pr = idx & 127, o = idx >> 7;
+        const long long p = pt0 + pr;
+        gsx[o * 128 + pr] = (p < g.P) ? __ldg(&a.gout[p * O + o]) : 0.f;
+      }
+  }
+  __syncthreads();
+  // range normalisation (see eps_tc_gemm.cu): every factor vector and the gout row scaled to max-abs in [0.5, 1)
+  for (int idx = tid; idx < (g.n + 1) * 128; idx += F_THREADS) {
+    const int pr = idx & 127, j = idx >> 7;
+    const bool isg = j == g.n;
+    if (isg && !a.withG) { fexp[idx] = 0; continue; }
+    float* v = isg ? gsx + pr : xs + j * Q * 128 + pr;
+    const int cnt = isg ? O : Q;
+    float m = 0.f;
+    for (int q = 0; q < cnt; ++q) m = fmaxf(m, fabsf(v[q * 128]));
+    const int e = tc::norm_exp(m);
+    if (e != 0)
+      for (int q = 0; q < cnt; ++q) v[q * 128] = scalbnf(v[q * 128], -e);
+    fexp[idx] = e;
+  }
+  __syncthreads();
+  if (tid < 128) {
+    int ea = 0, eb = 0;
+    for (int j = 0; j < g.n; ++j) {
+      const bool in_gen = (j >= a.jh0 && j < a.jh0 + a.cnth + a.cntl);
+      if (in_gen) ea += fexp[j * 128 + tid];
+      else eb += fexp[j * 128 + tid];
+    }
+    if (a.withG) ea += fexp[g.n * 128 + tid];
+    rowexp[tid] = ea;
+    rowexp[128 + tid] = eb;
+  }
+  {
+    // hi table: entry e (forward) or (o, e) (input gradient); carries the 2^15 of the generated row
+    const int KH = a.withG ? a.KHE / O : a.KHE;
+    for (int idx = tid; idx < nHrows * 128; idx += F_THREADS) {
+      const int pr = idx & 127, r = idx >> 7;
+      float v = 0.f;
+      if (r < a.KHE) {
+        const int o = r / KH, e = r - o * KH;
+        v = 32768.f * kr_entry(xs, Q, a.jh0, a.cnth, e, pr);
+        if (a.withG) v *= gsx[o * 128 + pr];
+      }
+      tabH[idx] = v;
+    }
+    if (MODE == FMODE_FWD) {
+      for (int idx = tid; idx < a.EHE * 128; idx += F_THREADS) tabEH[idx] = kr_entry(xs, Q, a.ej0, a.ecnth, idx >> 7, idx & 127);
+      for (int idx = tid; idx < O * 128; idx += F_THREADS) outs[idx] = 0.f;
+    }
+  }
+  // lo-group values of this thread's patch: registers for the rest of the kernel
+  float TL[KLR];
+  float EL[16];
+  {
+    const int pr = (warp & 3) * 32 + lane;
+    if (warp >= 4 && warp < 8) {
+#pragma unroll
+      for (int j = 0; j < KLR; ++j) TL[j] = kr_entry(xs, Q, a.jh0 + a.cnth, a.cntl, j, pr);
+    }
+    if (MODE == FMODE_FWD && warp >= 8) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) EL[j] = (j < a.ELR) ? kr_entry(xs, Q, a.ej0 + a.ecnth, a.ecntl, j, pr) : 0.f;
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();  // tables complete; the scratch aliasing the stages is dead from here on
+  tc::tc_fence_after();
+  const int core_exp = tc::core_scale_exp(__ldg(a.core_absmax));
+  const uint32_t tmem_main = *tmem_slot;
+  const uint32_t tmem_small = tmem_main + (uint32_t)BN;
+  const uint32_t tmem_a0 = tmem_main + 2u * (uint32_t)BN;   // stage s: hi at +64*s, lo at +64*s + 32
+  const int total_it = a.ntiles * a.nk;
+
+  if (warp == 0) {
+    // =========================== bulk-copy issuer (B operand) ===========================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 1;
+      const float* src = a.packed;
+      for (int i = 0; i < total_it; ++i) {
+        tc::mbar_wait(bar_emptyB0 + 8 * s, ph);
+        const uint32_t sb = tc::smem_u32(stages + s * STAGE_BYTES);
+        tc::mbar_arrive_expect_tx(bar_fullB0 + 8 * s, STAGE_BYTES);
+        tc::bulk_g2s(sb, src, STAGE_BYTES, bar_fullB0 + 8 * s);   // hi and lo parts are contiguous
+        src += 2 * BN * 32;
+        if (++s == NB) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    const uint32_t idesc = tc::make_idesc_f16(FBM, BN);
+    long long dbg_waitA = 0, dbg_waitB = 0, dbg_waitAcc = 0, dbg_start = TCF_CLK();
+    int sa = 0, sb_ = 0;
+    uint32_t pha = 0, phb = 0;
+    const uint64_t db_base = tc::make_sw128_kmajor_desc(tc::smem_u32(stages));
+    const uint32_t stage_adv = STAGE_BYTES >> 4, part_adv = B_BYTES >> 4;
+    for (int t = 0; t < a.ntiles; ++t) {
+      long long ta = TCF_CLK();
+      if (t > 0) tc::mbar_wait(bar_accempty, (uint32_t)((t - 1) & 1));
+      dbg_waitAcc += TCF_CLK() - ta;
+      tc::tc_fence_after();
+      for (int kc = 0; kc < a.nk; ++kc) {
+        long long t0 = TCF_CLK();
+        tc::mbar_wait(bar_fullB0 + 8 * sb_, phb);
+        long long t1 = TCF_CLK();
+        tc::mbar_wait(bar_fullA0 + 8 * sa, pha);
+        long long t2 = TCF_CLK();
+        dbg_waitB += t1 - t0; dbg_waitA += t2 - t1;
+        tc::tc_fence_after();
+        if (lane == 0) {
+          const uint64_t db_hi = db_base + (uint64_t)(sb_ * stage_adv);
+          const uint64_t db_lo = db_hi + part_adv;
+          const uint32_t a_hi = tmem_a0 + (uint32_t)(sa * 64), a_lo = a_hi + 32;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)(k * 2);
+            const uint32_t acol = (uint32_t)(k * 8);
+            const uint32_t first = (kc == 0 && k == 0) ? 0u : 1u;
+            tc::umma_f16_ts(tmem_main, a_hi + acol, db_hi + adv, idesc, first);
+            tc::umma_f16_ts(tmem_small, a_hi + acol, db_lo + adv, idesc, first);
+            tc::umma_f16_ts(tmem_small, a_lo + acol, db_hi + adv, idesc, 1u);
+          }
+          tc::umma_commit(bar_emptyA0 + 8 * sa);
+          tc::umma_commit(bar_emptyB0 + 8 * sb_);
+          if (kc == a.nk - 1) tc::umma_commit(bar_accfull);
+        }
+        __syncwarp();
+        if (++sa == F_ASTAGES) { sa = 0; pha ^= 1; }
+        if (++sb_ == NB) { sb_ = 0; phb ^= 1; }
+      }
+    }
+    if (a.dbg && lane == 0) {
+      long long* d = a.dbg + (long long)blockIdx.x * 8;
+      d[0] = dbg_waitA; d[1] = dbg_waitB; d[2] = dbg_waitAcc; d[3] = TCF_CLK() - dbg_start;
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // =========================== A producers: one patch row (= TMEM lane) per thread ===========================
+    const int pr = (warp & 3) * 32 + lane;
+    const float* th = tabH + pr;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    int sa = 0;
+    uint32_t phe = 1;
+    long long dbg_pwait = 0, dbg_pst = 0, dbg_pgen = 0, tprev = TCF_CLK();
+    for (int t = 0; t < a.ntiles; ++t) {
+      const float* thk = th;
+      for (int kc = 0; kc < a.nk; ++kc) {
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int r = 0; r < RUNS; ++r) {
+          const float h = thk[r * 128];
+#pragma unroll
+          for (int j = 0; j < KLR; j += 2)
+            tc::split_f16x2(h * TL[j], h * TL[j + 1], hi[(r * KLR + j) >> 1], lo[(r * KLR + j) >> 1]);
+        }
+        thk += RUNS * 128;
+        long long t0 = TCF_CLK();
+        tc::mbar_wait(bar_emptyA0 + 8 * sa, phe);
+        long long t1 = TCF_CLK();
+        tc::tc_fence_after();
+        const uint32_t dst = tmem_a0 + lane_base + (uint32_t)(sa * 64);
+        tc::tmem_st32_u(dst, hi);
+        tc::tmem_st32_u(dst + 32, lo);
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(bar_fullA0 + 8 * sa);
+        long long t2 = TCF_CLK();
+        dbg_pwait += t1 - t0; dbg_pst += t2 - t1; dbg_pgen += t0 - tprev; tprev = t2;
+        if (++sa == F_ASTAGES) { sa = 0; phe ^= 1; }
+      }
+    }
+    if (a.dbg && warp == 4 && lane == 0) {
+      long long* d = a.dbg + (long long)blockIdx.x * 8;
+      d[4] = dbg_pwait; d[5] = dbg_pst; d[6] = dbg_pgen;
+    }
+  } else if (warp >= 8) {
+    // =========================== epilogue ===========================
+    const int quad = warp & 3;
+    const int pr = quad * 32 + lane;
+    const int pl = pl0 + pr;
+    const bool pvalid = pl < a.np;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    // accumulator -> true value: 2^kexp as two exact factors (|kexp| may exceed 127)
+    const int kexp = rowexp[pr] - 15 - core_exp;
+    const float sc1 = scalbnf(1.f, kexp / 2), sc2 = scalbnf(1.f, kexp - kexp / 2);
+    const int fexp_all = kexp + rowexp[128 + pr];
+    const float fsc1 = scalbnf(1.f, fexp_all / 2), fsc2 = scalbnf(1.f, fexp_all - fexp_all / 2);
+    const float* eH = tabEH + pr;
+    float s = 0.f;
+    int cur_o = 0;
+    long long dbg_epi = 0;
+    for (int t = 0; t < a.ntiles; ++t) {
+      tc::mbar_wait(bar_accfull, (uint32_t)(t & 1));
+      long long te0 = TCF_CLK();
+      tc::tc_fence_after();
+      const int n0 = t * BN;
+#pragma unroll 1
+      for (int cb = 0; cb < BN; cb += 32) {
+        const int nb = n0 + cb;
+        if (nb >= a.Ncols) break;             // Ncols % 32 == 0 (host check): batches are whole or empty
+        float v[32];
+        {
+          float w[32];
+          tc::tmem_ld32(tmem_main + lane_base + (uint32_t)cb, v);
+          tc::tmem_ld32(tmem_small + lane_base + (uint32_t)cb, w);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaf(w[i], 1.f / 2048.f, v[i]);
+        }
+        if (MODE == FMODE_STORE) {
+          if (pvalid) {
+            float* crow = a.out + (long long)pl * a.ldc + nb;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *(float4*)(crow + i) = make_float4(v[i] * sc1 * sc2, v[i + 1] * sc1 * sc2, v[i + 2] * sc1 * sc2, v[i + 3] * sc1 * sc2);
+          }
+        } else {
+          if (a.tsave != nullptr && pvalid) {
+            float* trow = a.tsave + (pt0 + pr) * (long long)a.Ncols + nb;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *(float4*)(trow + i) = make_float4(v[i] * sc1 * sc2, v[i + 1] * sc1 * sc2, v[i + 2] * sc1 * sc2, v[i + 3] * sc1 * sc2);
+          }
+          // 32 columns of one o (Bn % 32 == 0): b = b0 .. b0+31, KR2[b] = EH[b / ELR] * EL[b % ELR]
+          const int o = nb / g.Bn, b0 = nb - o * g.Bn;
+          if (o != cur_o) {
+            outs[cur_o * 128 + pr] += s;
+            s = 0.f;
+            cur_o = o;
+          }
+          const float* ehp = eH + (b0 / a.ELR) * 128;
+          float acc = 0.f;
+          switch (a.ELR) {
+            case 16:
+#pragma unroll
+              for (int r = 0; r < 2; ++r) {
+                const float eh = ehp[r * 128];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc = fmaf(v[r * 16 + j], eh * EL[j], acc);
+              }
+              break;
+            case 8:
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                const float eh = ehp[r * 128];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc = fmaf(v[r * 8 + j], eh * EL[j], acc);
+              }
+              break;
+            case 4:
+#pragma unroll
+              for (int r = 0; r < 8; ++r) {
+                const float eh = ehp[r * 128];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc = fmaf(v[r * 4 + j], eh * EL[j], acc);
+              }
+              break;
+            default:  // 2
+#pragma unroll
+              for (int r = 0; r < 16; ++r) {
+                const float eh = ehp[r * 128];
+                acc = fmaf(v[r * 2], eh * EL[0], acc);
+                acc = fmaf(v[r * 2 + 1], eh * EL[1], acc);
+              }
+              break;
+          }
+          s += acc;
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(bar_accempty);
+      dbg_epi += TCF_CLK() - te0;
+    }
+    if (a.dbg && warp == 8 && lane == 0) a.dbg[(long long)blockIdx.x * 8 + 7] = dbg_epi;
+    if (MODE == FMODE_FWD) {
+      outs[cur_o * 128 + pr] += s;
+      if (pvalid) {
+        float* orow = a.out + (pt0 + pr) * O;
+        for (int o = 0; o < O; ++o) orow[o] = outs[o * 128 + pr] * fsc1 * fsc2;
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tmem_main, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct FastShape {
+  int ok;
+  int jh0, cnth, cntl, KLR, KHE, withG, Kdim, Ncols;
+  int ej0, ecnth, ecntl, EHE, ELR;
+};
+
+inline int ilog_pow2(int q) {  // log2(q) if q is a power of two >= 2, else -1
+  if (q < 2 || (q & (q - 1))) return -1;
+  int l = 0;
+  while ((1 << l) < q) ++l;
+  return l;
+}
+// lo-group size for `cnt` factors of size Q: the most factors with Q^cl <= 16, leaving at least one for the hi group
+inline int lo_count(int Q, int cnt) {
+  const int lq = ilog_pow2(Q);
+  if (lq < 0 || cnt < 2) return 0;
+  int cl = 4 / lq;
+  if (cl > cnt - 1) cl = cnt - 1;
+  return cl;
+}
+
+inline FastShape fast_shape(const EpsGeom& g, int mode) {
+  FastShape s{};
+  const int cntA = g.m, cntB = g.n - g.m;
+  if (mode == FMODE_FWD) {
+    const int cl = lo_count(g.Q, cntA), el = lo_count(g.Q, cntB);
+    if (cl < 1 || el < 1) return s;
+    s.jh0 = 0; s.cntl = cl; s.cnth = cntA - cl; s.KLR = ipow_host(g.Q, cl); s.KHE = ipow_host(g.Q, s.cnth); s.withG = 0;
+    s.Kdim = g.A; s.Ncols = g.N;
+    s.ej0 = g.m; s.ecntl = el; s.ecnth = cntB - el; s.ELR = ipow_host(g.Q, el); s.EHE = ipow_host(g.Q, s.ecnth);
+    if (g.Bn % 32 != 0) return s;     // a 32-column epilogue batch must not straddle two o
+  } else {
+    const int cl = lo_count(g.Q, cntB);
+    if (cl < 1) return s;
+    s.jh0 = g.m; s.cntl = cl; s.cnth = cntB - cl; s.KLR = ipow_host(g.Q, cl); s.KHE = g.O * ipow_host(g.Q, s.cnth); s.withG = 1;
+    s.Kdim = g.N; s.Ncols = g.A;
+    if (g.A % 32 != 0) return s;
+  }
+  if (s.KLR < 2 || s.KLR > 16) return s;
+  s.ok = 1;
+  return s;
+}
+
+inline size_t fast_fixed_smem(const EpsGeom& g, const FastShape& s, int mode) {
+  const size_t nk = (size_t)(s.Kdim + FKS - 1) / FKS;
+  const size_t nH = nk * (FKS / s.KLR);
+  return 1024 + (nH + (mode == FMODE_FWD ? (size_t)s.EHE + g.O : 0)) * 128 * 4 + 256 * 4 +
+         (2 * F_MAX_BSTAGES + 2 * F_ASTAGES + 2) * 8 + 16;
+}
+inline size_t fast_stage_bytes(int BN) { return 2 * (size_t)BN * 128; }
+inline int fast_bstages(const EpsGeom& g, const FastShape& s, int mode, int BN) {
+  const size_t fixed = fast_fixed_smem(g, s, mode);
+  if (fixed >= F_SMEM_LIMIT) return 0;
+  int nb = (int)((F_SMEM_LIMIT - fixed) / fast_stage_bytes(BN));
+  if (nb > F_MAX_BSTAGES) nb = F_MAX_BSTAGES;
+  if (nb < 2) return 0;
+  if ((size_t)(g.n * g.Q + g.O + g.n + 1) * 128 * 4 > nb * fast_stage_bytes(BN)) return 0;   // setup scratch
+  return nb;
+}
+// column-tile width: multiple of 32 (whole epilogue batches), least padded, then widest
+inline int fast_bn(const EpsGeom& g, const FastShape& s, int mode) {
+  int best = 0;
+  long long best_cost = 0;
+  for (int bn = F_MAX_BN; bn >= 64; bn -= 32) {
+    if (fast_bstages(g, s, mode, bn) == 0) continue;
+    long long cost = (long long)((s.Ncols + bn - 1) / bn) * bn;
+    if (bn < 160) cost = cost * 9 / 8;
+    if (!best || cost < best_cost) { best = bn; best_cost = cost; }
+  }
+  return best;
+}
+
+template <int MODE, int KLR>
+int launch_fast(const FastArgs& a, size_t smem, cudaStream_t st) {
+  auto k = tc_gemm_fast_kernel<MODE, KLR>;
+  DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<(a.np + FBM - 1) / FBM, F_THREADS, smem, st>>>(a);
+  dctn_count_launch();
+  DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  return 0;
+}
+template <int MODE>
+int launch_fast_klr(const FastArgs& a, int KLR, size_t smem, cudaStream_t st) {
+  switch (KLR) {
+    case 2: return launch_fast<MODE, 2>(a, smem, st);
+    case 4: return launch_fast<MODE, 4>(a, smem, st);
+    case 8: return launch_fast<MODE, 8>(a, smem, st);
+    case 16: return launch_fast<MODE, 16>(a, smem, st);
+  }
+  return dctn_set_error(-2, "register-table GEMM: no instance for a lo group of %d entries", KLR);
+}
+
+}  // namespace
+
+// mode: 0 = input-gradient GEMM (dKR1), 1 = forward
+bool tcfast_supported(const EpsGeom& g, int mode) {
+  const FastShape s = fast_shape(g, mode);
+  return s.ok && fast_bn(g, s, mode) != 0;
+}
+
+size_t tcfast_packed_floats(const EpsGeom& g, int mode) {
+  const FastShape s = fast_shape(g, mode);
+  if (!s.ok) return 0;
+  const int BN = fast_bn(g, s, mode);
+  if (!BN) return 0;
+  const long long ntiles = (s.Ncols + BN - 1) / BN, nk = (s.Kdim + FKS - 1) / FKS;
+  return (size_t)(ntiles * nk * 2 * BN * 32);
+}
+
+int tcfast_pack(const EpsGeom& g, int mode, const float* core, float* dst, const uint32_t* absmax, cudaStream_t st) {
+  const FastShape s = fast_shape(g, mode);
+  const int BN = fast_bn(g, s, mode);
+  const int ntiles = (s.Ncols + BN - 1) / BN, nk = (s.Kdim + FKS - 1) / FKS;
+  const long long total = (long long)ntiles * nk * BN * 8;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  fast_pack_kernel<<<blocks, 256, 0, st>>>(core, dst, g, mode, BN, s.Ncols, s.Kdim, ntiles, nk, absmax);
+  dctn_count_launch();
+  DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  return 0;
+}
+
+int tcfast_gemm(const EpsGeom& g, int mode, const float* x, const float* gout, const float* packed, const uint32_t* absmax,
+                long long p0, int np, float* out, long long ldc, float* tsave, cudaStream_t st) {
+  const FastShape s = fast_shape(g, mode);
+  const int BN = s.ok ? fast_bn(g, s, mode) : 0;
+  if (!BN) return dctn_set_error(-2, "register-table GEMM does not support this shape");
+  FastArgs a{};
+  a.g = g; a.x = x; a.gout = gout; a.p0 = p0; a.np = np;
+  a.jh0 = s.jh0; a.cnth = s.cnth; a.cntl = s.cntl; a.KHE = s.KHE; a.withG = s.withG; a.Kdim = s.Kdim;
+  a.ej0 = s.ej0; a.ecnth = s.ecnth; a.ecntl = s.ecntl; a.EHE = s.EHE; a.ELR = s.ELR;
+  a.Ncols = s.Ncols; a.ntiles = (s.Ncols + BN - 1) / BN; a.nk = (s.Kdim + FKS - 1) / FKS; a.BN = BN;
+  a.bstages = fast_bstages(g, s, mode, BN);
+  a.packed = packed; a.core_absmax = absmax; a.out = out; a.ldc = ldc; a.tsave = tsave;
+  a.dbg = nullptr;
+  static long long* dbg_buf = nullptr;
+  const int ncta = (np + FBM - 1) / FBM;
+  if (getenv("DCTN_TCG_DEBUG") && ncta <= 4096) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 4096 * 8 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 4096 * 8 * sizeof(long long), st);
+    a.dbg = dbg_buf;
+  }
+  const size_t smem = fast_fixed_smem(g, s, mode) + a.bstages * fast_stage_bytes(BN);
+  int rc = (mode == FMODE_FWD) ? launch_fast_klr<FMODE_FWD>(a, s.KLR, smem, st) : launch_fast_klr<FMODE_STORE>(a, s.KLR, smem, st);
+  if (a.dbg && rc == 0) {
+    static long long host[4096 * 8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(host, dbg_buf, (size_t)ncta * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+    double sum[8] = {0};
+    for (int c = 0; c < ncta; ++c) for (int k = 0; k < 8; ++k) sum[k] += (double)host[c * 8 + k];
+    const double nst = (double)a.ntiles * a.nk;
+    fprintf(stderr, "[tcfast dbg] mode=%d KLR=%d BN=%d NB=%d ntiles=%d nk=%d per-stage cycles: mma waitA %.0f waitB %.0f waitAcc(per tile) %.0f total %.0f | "
+            "producer wait %.0f st %.0f gen %.0f | epilogue/tile %.0f\n", mode, s.KLR, BN, a.bstages, a.ntiles, a.nk,
+            sum[0] / ncta / nst, sum[1] / ncta / nst, sum[2] / ncta / a.ntiles, sum[3] / ncta / nst,
+            sum[4] / ncta / nst, sum[5] / ncta / nst, sum[6] / ncta / nst, sum[7] / ncta / a.ntiles);
+  }
+  return rc;
+}

@@ -82,22 +82,8 @@ struct TcGemmArgs {
 //   MODE_STORE: element(c, k) = core[c*N + k]           (c = a, k = n)
 //   MODE_DKR2 : element(c, k) = core[k*N + c]           (c = n, k = a)
 //   MODE_FWD  : element(c, k) = core[(k*Bn + b)*O + o]  (c = o*Bn + b, k = a)
-// exponent e with max = f * 2^e, f in [0.5, 1) (0 for max == 0 / inf / nan): the core is scaled by 2^(15 - e)
-__device__ __forceinline__ int core_scale_exp(uint32_t absmax_bits) {
-  const float m = __uint_as_float(absmax_bits);
-  if (!(m > 0.f) || !(m < 3.0e38f)) return 0;
-  int e;
-  frexpf(m, &e);
-  return 15 - e;
-}
-// v -> (fp16(v), fp16((v - fp16(v)) * 2^11)) for two values, packed low half = first value
-__device__ __forceinline__ void split_f16x2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(v0, v1);
-  const float r0 = (v0 - __low2float(h)) * 2048.f, r1 = (v1 - __high2float(h)) * 2048.f;
-  const __half2 l = __floats2half2_rn(r0, r1);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
+using tc::core_scale_exp;
+using tc::split_f16x2;
 
 __global__ void absmax_kernel(const float* __restrict__ v, long long n, uint32_t* __restrict__ out) {
   float m = 0.f;
@@ -809,6 +795,14 @@ inline bool common_ok(const EpsGeom& g) {
 
 }  // namespace
 
+// register-table kernels (eps_tc_fast.cu) serve the split-fp16 arithmetic when the shape allows; DCTN_B200_NO_FAST=1
+// forces the generic table-lookup kernels (A/B comparisons, tests of the generic path)
+static bool use_fast(const EpsGeom& g, int fmode, int passes) {
+  if (passes != ARITH_F16X3 || !tcfast_supported(g, fmode)) return false;
+  const char* e = getenv("DCTN_B200_NO_FAST");
+  return !(e && e[0] == '1');
+}
+
 bool tcg_supported(const EpsGeom& g, int kind) {
   if (!common_ok(g)) return false;
   if (kind == 0) return g.Bn >= 32 && pick_bn(g, MODE_FWD) != 0;
@@ -818,10 +812,14 @@ bool tcg_supported(const EpsGeom& g, int kind) {
 }
 
 size_t tcg_workspace_bytes(const EpsGeom& g, int kind) {
-  if (kind == 0) return WS_HEADER + packed_floats(g, MODE_FWD, pick_bn(g, MODE_FWD)) * 4 + 256;
+  if (kind == 0) {
+    size_t pf = packed_floats(g, MODE_FWD, pick_bn(g, MODE_FWD)), ff = tcfast_packed_floats(g, 1);
+    return WS_HEADER + (pf > ff ? pf : ff) * 4 + 256;
+  }
   if (kind == 2 || kind == 3) {
     const long long pc = dx_patch_chunk(g);
-    size_t f = packed_floats(g, MODE_STORE, pick_bn(g, MODE_STORE)) + (size_t)pc * ((size_t)g.A + g.Bn) + (size_t)g.P * g.n * g.Q;
+    size_t p1 = packed_floats(g, MODE_STORE, pick_bn(g, MODE_STORE)), f1 = tcfast_packed_floats(g, 0);
+    size_t f = (p1 > f1 ? p1 : f1) + 64 + (size_t)pc * ((size_t)g.A + g.Bn) + (size_t)g.P * g.n * g.Q;
     if (kind == 2) f += packed_floats(g, MODE_DKR2, pick_bn(g, MODE_DKR2));
     return WS_HEADER + f * 4 + 1024;
   }
@@ -836,6 +834,10 @@ int tc_forward(const EpsGeom& g, const float* x, const float* core, float* out, 
   float* packed = (float*)((char*)ws + WS_HEADER);
   int rc = run_absmax(g, core, absmax, passes, st);
   if (rc) return rc;
+  if (use_fast(g, 1, passes)) {
+    if ((rc = tcfast_pack(g, 1, core, packed, absmax, st))) return rc;
+    return tcfast_gemm(g, 1, x, nullptr, packed, absmax, 0, (int)g.P, out, 0, tsave, st);
+  }
   if ((rc = run_pack(g, MODE_FWD, BN, core, packed, passes, st, absmax))) return rc;
   return run_gemm(g, MODE_FWD, BN, x, nullptr, packed, 0, (int)g.P, out, 0, passes, st, absmax, tsave);
 }
@@ -885,17 +887,24 @@ static int backward_input_impl(const EpsGeom& g, const float* x, const float* co
   const long long pc = dx_patch_chunk(g);
   uint32_t* absmax = (uint32_t*)ws;
   float* packed1 = (float*)((char*)ws + WS_HEADER);
-  float* packed2 = packed1 + ((packed_floats(g, MODE_STORE, BN1) + 63) & ~(size_t)63);
+  const bool fast1 = use_fast(g, 0, passes);
+  size_t pf1 = packed_floats(g, MODE_STORE, BN1);
+  if (tcfast_packed_floats(g, 0) > pf1) pf1 = tcfast_packed_floats(g, 0);
+  float* packed2 = packed1 + ((pf1 + 63) & ~(size_t)63);
   float* dkr1 = packed2 + (tsaved ? 0 : ((packed_floats(g, MODE_DKR2, BN2) + 63) & ~(size_t)63));
   float* dkr2 = dkr1 + (size_t)pc * g.A;
   float* dxp = dkr2 + (size_t)pc * g.Bn;
   int rc;
   if ((rc = run_absmax(g, core, absmax, passes, st))) return rc;
-  if ((rc = run_pack(g, MODE_STORE, BN1, core, packed1, passes, st, absmax))) return rc;
+  if (fast1) rc = tcfast_pack(g, 0, core, packed1, absmax, st);
+  else rc = run_pack(g, MODE_STORE, BN1, core, packed1, passes, st, absmax);
+  if (rc) return rc;
   if (!tsaved && (rc = run_pack(g, MODE_DKR2, BN2, core, packed2, passes, st, absmax))) return rc;
   for (long long p0 = 0; p0 < g.P; p0 += pc) {
     const int np = (int)((g.P - p0 < pc) ? (g.P - p0) : pc);
-    if ((rc = run_gemm(g, MODE_STORE, BN1, x, gout, packed1, p0, np, dkr1, g.A, passes, st, absmax))) return rc;
+    if (fast1) rc = tcfast_gemm(g, 0, x, gout, packed1, absmax, p0, np, dkr1, g.A, nullptr, st);
+    else rc = run_gemm(g, MODE_STORE, BN1, x, gout, packed1, p0, np, dkr1, g.A, passes, st, absmax);
+    if (rc) return rc;
     if ((rc = launch_loo<float>(g, x, dkr1, p0, np, 0, dxp, st))) return rc;
     if (tsaved) {
       const bool vec = (g.Bn & 3) == 0;

@@ -6,6 +6,7 @@
 // (r & 7); groups of 8 rows are 1024 bytes apart (SBO).  One tcgen05.mma kind::tf32 consumes K = 8 elements
 // (32 bytes) per row, so a 32-wide tile is 4 MMA k-steps, each advancing the descriptor start address by 32 B.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -201,6 +202,28 @@ __device__ __forceinline__ uint32_t sw128_offset(int r, int k) {
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
   lo = v - hi;
+}
+
+// ---------------------------------------------------------------- split-fp16 number format
+// v -> (fp16(v), fp16((v - fp16(v)) * 2^11)) for two values, packed with the first value in the low half
+__device__ __forceinline__ void split_f16x2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(v0, v1);
+  const float r0 = (v0 - __low2float(h)) * 2048.f, r1 = (v1 - __high2float(h)) * 2048.f;
+  const __half2 l = __floats2half2_rn(r0, r1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// exponent e with m = f * 2^e, f in [0.5, 1); 0 for m == 0 / inf / nan
+__device__ __forceinline__ int norm_exp(float m) {
+  int e = 0;
+  if (m > 0.f && m < 3.0e38f) frexpf(m, &e);
+  return e;
+}
+// the core is scaled by 2^(15 - norm_exp(max|core|)): largest magnitude in [2^14, 2^15)
+__device__ __forceinline__ int core_scale_exp(uint32_t absmax_bits) {
+  const float m = __uint_as_float(absmax_bits);
+  if (!(m > 0.f) || !(m < 3.0e38f)) return 0;
+  return 15 - norm_exp(m);
 }
 
 }  // namespace tc

@@ -364,10 +364,31 @@ def test_tc_backward_core_full_size_vs_fp64(B, H, W, Q, K, Oq):
     assert rel_err(ffma, want) <= 1e-5
 
 
-@pytest.mark.parametrize("variant,tol", [("tch3", 1e-5), ("tc3", 1e-5), ("tc1", 5e-3)])
+@pytest.fixture
+def generic_tc_kernels(monkeypatch):
+    """Forces the generic table-lookup tcgen05 GEMM kernels instead of the register-table ones (eps_tc_fast.cu)."""
+    monkeypatch.setenv("DCTN_B200_NO_FAST", "1")
+
+
 @pytest.mark.parametrize("shape", TC_SHAPES)
+def test_tch3_generic_kernels_vs_oracle(shape, generic_tc_kernels):
+    from dctn_b200 import _lib
+
+    B, H, W, Q, K, Oq = shape
+    x, core, gout = _rand_layer(B, H, W, Q, K, Oq, seed=29)
+    want = O.eps_4step(core.double(), x.double())
+    _, want_dx = O.eps_grads(core.double(), x.double(), gout.double())
+    assert rel_err(_raw_call(_lib.WS_FORWARD, "tch3", core.to(DEV), x.to(DEV), gout.to(DEV)), want) <= 1e-5
+    assert rel_err(_raw_call(_lib.WS_BACKWARD_INPUT, "tch3", core.to(DEV), x.to(DEV), gout.to(DEV)), want_dx) <= 1e-5
+    out, dx = _raw_train_call("tch3", core.to(DEV), x.to(DEV), gout.to(DEV))
+    assert rel_err(out, want) <= 1e-5 and rel_err(dx, want_dx) <= 1e-5
+
+
+@pytest.mark.parametrize("variant,tol", [("tch3", 1e-5), ("tc3", 1e-5), ("tc1", 5e-3)])
+@pytest.mark.parametrize("shape", TC_SHAPES + [(20, 16, 16, 8, 2, 24), (6, 30, 31, 8, 2, 5), (3, 40, 41, 16, 2, 3)])
 def test_tc_forward_and_input_grad_vs_oracle(shape, variant, tol):
-    """tcgen05 forward (fused KR2 epilogue) and input-gradient (two GEMMs + leave-one-out + gather) vs the oracle."""
+    """tcgen05 forward (fused KR2 epilogue) and input-gradient (two GEMMs + leave-one-out + gather) vs the oracle.
+    The extra shapes exercise the register-table kernels with lo groups of 8 (Q=8, K=2) and 16 (Q=16, K=2) entries."""
     from dctn_b200 import _lib
 
     B, H, W, Q, K, Oq = shape
