@@ -25,7 +25,7 @@ def _model():
     return torch.nn.Sequential(torch.nn.Linear(12, 8), torch.nn.Tanh(), torch.nn.Linear(8, 10)).double()
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, overlap):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -37,7 +37,7 @@ def _worker(rank, world, port, ret):
             with torch.no_grad():
                 for p in model.parameters():
                     p.add_(1.0)
-        reducer = GradAllReducer(model.parameters())
+        reducer = GradAllReducer(model.parameters(), overlap=overlap)
         xs, ys = shard_batch(x, rank, world, dim=1), shard_batch(y, rank, world, dim=0)
         assert xs.shape == (1, 4, 12) and ys.shape == (4,)
         loss = F.cross_entropy(model(xs[0]), ys)
@@ -60,12 +60,16 @@ def _worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-def test_grad_allreduce_matches_single_process():
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("overlap", [False, True])
+def test_grad_allreduce_matches_single_process(overlap):
     world = 2
     port = _free_port()
     with mp.Manager() as manager:
         ret = manager.dict()
-        mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, port, ret, overlap), nprocs=world, join=True)
         grads, params, metrics = ret["grads"], ret["params"], ret["metrics"]
     # single-process reference: full batch, rank-0 parameters
     g = torch.Generator().manual_seed(0)
