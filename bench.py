@@ -158,7 +158,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def cpu_baseline_sample(workload, seconds=20.0):
@@ -412,13 +412,27 @@ def run_ours(args):
             line["roofline"] = kernel_rooflines(model, specs, image_size, Q0, batch, dev, flush)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample(args.workload)
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def _emit(line: dict) -> None:
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner at communicator
+    creation), so main() points fd 1 at stderr for the duration of the run and the result goes to the saved fd."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT, data)
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -227,13 +227,14 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
     }
   }
   // lo-group values of this thread's patch: registers for the rest of the kernel
-  float TL[KLR];
+  tc::f32x2_t TL2[KLR / 2];
   float EL[16];
   {
     const int pr = (warp & 3) * 32 + lane;
     if (warp >= 4 && warp < 8) {
 #pragma unroll
-      for (int j = 0; j < KLR; ++j) TL[j] = kr_entry(xs, Q, a.jh0 + a.cnth, a.cntl, j, pr);
+      for (int j = 0; j < KLR; j += 2)
+        TL2[j / 2] = tc::pack2(kr_entry(xs, Q, a.jh0 + a.cnth, a.cntl, j, pr), kr_entry(xs, Q, a.jh0 + a.cnth, a.cntl, j + 1, pr));
     }
     if (MODE == FMODE_FWD && warp >= 8) {
 #pragma unroll
@@ -326,9 +327,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
 #pragma unroll
         for (int r = 0; r < RUNS; ++r) {
           const float h = thk[r * 128];
+          const tc::f32x2_t h2 = tc::pack2(h, h);
 #pragma unroll
           for (int j = 0; j < KLR; j += 2)
-            tc::split_f16x2(h * TL[j], h * TL[j + 1], hi[(r * KLR + j) >> 1], lo[(r * KLR + j) >> 1]);
+            tc::split_f16x2_p(tc::mul2(h2, TL2[j / 2]), hi[(r * KLR + j) >> 1], lo[(r * KLR + j) >> 1]);
         }
         thk += RUNS * 128;
         long long t0 = TCF_CLK();
