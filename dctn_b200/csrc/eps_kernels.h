@@ -39,6 +39,11 @@ size_t tcg_workspace_bytes(const EpsGeom& g, int kind);
 int tc_backward_core(const EpsGeom& g, const float* x, const float* gout, float* dcore, void* ws, int passes, cudaStream_t st);
 int tc_backward_input(const EpsGeom& g, const float* x, const float* core, const float* gout, float* dx, void* ws, int passes, cudaStream_t st);
 
+// eps_tc_dcore.cu: split-fp16 core gradient (A' = KR1 x second-half hi group generated into TMEM, second-half lo group x
+// gout pre-split once and streamed by bulk copies)
+bool tc16_dcore_supported(const EpsGeom& g);
+size_t tc16_dcore_workspace_bytes(const EpsGeom& g);
+int tc16_backward_core(const EpsGeom& g, const float* x, const float* gout, float* dcore, void* ws, cudaStream_t st);
 // eps_tc_fast.cu: register-table variant of the two GEMMs above for power-of-two Q, split-fp16 arithmetic
 // (mode 0: input-gradient GEMM dKR1, mode 1: forward)
 bool tcfast_supported(const EpsGeom& g, int mode);

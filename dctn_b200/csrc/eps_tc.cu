@@ -1,4 +1,6 @@
-// tcgen05 core-gradient kernel of the EPS contraction (float32; 3xTF32 or 1xTF32 arithmetic).
+// tcgen05 core-gradient kernel of the EPS contraction, split-TF32 arithmetic (float32; 3xTF32 or 1xTF32; variants tc3 / tc1).
+// The default arithmetic, split fp16, has its own kernel in eps_tc_dcore.cu; this one is the validated reference
+// arithmetic it is compared against.
 //
 //   dcore[a][n] = sum_p KR1[p][a] * KR2[p][b(n)] * gout[p][o(n)]          reduction over ALL patches
 //
@@ -22,20 +24,10 @@
 //   * split-K over patch ranges (about two waves of CTAs); partial tiles go to the workspace and a second kernel
 //     sums them in a fixed order (deterministic).
 // TMEM columns: main 0..127, small 128..255, A stage s at 256 + 128*s (slab0 hi | slab0 lo | slab1 hi | slab1 lo).
-//
-// Split-fp16 arithmetic (F16 = true, the default; see eps_tc_gemm.cu for the number format): kind::f16 MMAs, a 128-byte
-// operand row / 32-column TMEM slab holds 64 patches, so a stage is ONE slab of 64 patches and there are 4 stages.  The
-// reduction runs over patches whose magnitudes differ, so the per-patch power-of-two normalisation cannot be undone
-// after the sum: patch_exp_kernel computes every patch's exponent E_p (sum of the exponents of its factor vectors and
-// of its gout row) and the maximum E_max; build_tables_kernel writes normalised tables and folds 2^(E_p - E_max) <= 1
-// into the second-half hi table.  A patch far below the largest one loses relative precision exactly as its
-// contribution loses weight in the sum.  reduce_partials applies 2^(E_max - 30) (two operand scales of 2^15).
 #include "common.cuh"
 #include "eps_kernels.h"
-#include <climits>
 #include <cstdio>
 #include <cstdlib>
-#include <cuda_fp16.h>
 
 #include "tc_common.cuh"
 
@@ -57,9 +49,6 @@ constexpr int NPROD_WARPS = 8;    // warps 1..8; warp 0 issues MMAs; warp 9 stre
 constexpr int NTHREADS_TC = 32 * (2 + NPROD_WARPS);
 constexpr int TSTAGES = 2;        // table buffers
 constexpr int SEG_CHUNKS = 12;    // chunks per promotion segment: 12 * 2 slabs * 4 k-steps = 96 roundings of the main chain
-constexpr int SEG_CHUNKS_F16 = 24;  // fp16: one slab per chunk -> the same 96 roundings
-constexpr int STAGES_F16 = 4;     // fp16: a stage is one 64-patch slab (32 KB of B, 64 TMEM columns of A)
-constexpr int ARITH_F16X3 = 6;    // value of `passes` selecting the split-fp16 arithmetic
 constexpr int TS_ = CH + 4;       // table row stride in floats (272 B: 16-byte aligned, rows 4 banks apart)
 constexpr uint32_t SLAB_BYTES = BN * 32 * 4;           // one part (hi or lo) of one slab of B: 16 KB
 constexpr uint32_t STAGE_BYTES = SLABS * 2 * SLAB_BYTES;  // 64 KB
@@ -106,41 +95,12 @@ inline int max_tile_entries(const EpsGeom& g, int three) {
 // tables[chunk][entry][i] for patch p = chunk*64 + i (zeros past P): entries [0,AH): first-half hi group,
 // [AH, AH+AL): first-half lo group, then [.., +BH): second-half hi group, then either BL*O entries (second-half lo group
 // x gout) or, three-level, BL entries (lo group) followed by O entries (gout).
-using tc::norm_exp;
-using tc::split_f16x2;
-
-// fp16 arithmetic, pass 1: exps[p] = E_p, *emax = max_p E_p (one thread per patch; *emax starts at INT_MIN)
-__global__ void __launch_bounds__(256) patch_exp_kernel(EpsGeom g, const float* __restrict__ x, const float* __restrict__ gout,
-                                                        int* __restrict__ exps, int* __restrict__ emax) {
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  int E = INT_MIN;
-  if (p < g.P) {
-    const long long o0 = patch_origin(g, p);
-    E = 0;
-    for (int j = 0; j < g.n; ++j) {
-      float m = 0.f;
-      for (int q = 0; q < g.Q; ++q) m = fmaxf(m, fabsf(__ldg(&x[o0 + g.foff[j] + q])));
-      E += norm_exp(m);
-    }
-    float m = 0.f;
-    for (int o = 0; o < g.O; ++o) m = fmaxf(m, fabsf(__ldg(&gout[p * g.O + o])));
-    E += norm_exp(m);
-    exps[p] = E;
-  }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) E = max(E, __shfl_xor_sync(0xffffffffu, E, o));
-  if ((threadIdx.x & 31) == 0 && E != INT_MIN) atomicMax(emax, E);
-}
-
-template <bool F16>
 __global__ void __launch_bounds__(256) build_tables_kernel(EpsGeom g, const float* __restrict__ x,
-                                                           const float* __restrict__ gout, float* __restrict__ tables, int three,
-                                                           const int* __restrict__ exps, const int* __restrict__ emax) {
+                                                           const float* __restrict__ gout, float* __restrict__ tables, int three) {
   extern __shared__ float bt_smem[];
   const int Q = g.Q, O = g.O, NX = g.n * Q;
   float* xs = bt_smem;             // [NX][64]
   float* gs = xs + NX * CH;        // [O][64]
-  float* wp = gs + O * CH;         // F16: [64] weight 2^(E_p - E_max) of every patch
   const long long p0 = (long long)blockIdx.x * CH;
   for (int idx = threadIdx.x; idx < (NX + O) * CH; idx += blockDim.x) {
     const int i = idx & (CH - 1), r = idx >> 6;
@@ -150,33 +110,15 @@ __global__ void __launch_bounds__(256) build_tables_kernel(EpsGeom g, const floa
     xs[idx] = v;
   }
   __syncthreads();
-  if (F16) {
-    // every factor vector and the gout row of a patch: largest magnitude scaled into [0.5, 1) (exact)
-    for (int idx = threadIdx.x; idx < (g.n + 1) * CH; idx += blockDim.x) {
-      const int i = idx & (CH - 1), j = idx >> 6;
-      float* v = (j < g.n) ? xs + j * Q * CH + i : gs + i;
-      const int cnt = (j < g.n) ? Q : O;
-      float m = 0.f;
-      for (int q = 0; q < cnt; ++q) m = fmaxf(m, fabsf(v[q * CH]));
-      const int e = norm_exp(m);
-      if (e != 0)
-        for (int q = 0; q < cnt; ++q) v[q * CH] = scalbnf(v[q * CH], -e);
-    }
-    if (threadIdx.x < CH) {
-      const long long p = p0 + threadIdx.x;
-      wp[threadIdx.x] = (p < g.P) ? scalbnf(1.f, max(exps[p] - __ldg(emax), -200)) : 0.f;
-    }
-    __syncthreads();
-  }
   const int ENT = g.AH + g.AL + g.BH + last_section(g, three);
   float* out = tables + (long long)blockIdx.x * ENT * TS_;
   for (int idx = threadIdx.x; idx < ENT * CH; idx += blockDim.x) {
     const int i = idx & (CH - 1), t = idx >> 6;
     int e, j0, cnt;
     float v = 1.f;
-    if (t < g.AH) { e = t; j0 = 0; cnt = g.a_nh; if (F16) v = 32768.f; }
+    if (t < g.AH) { e = t; j0 = 0; cnt = g.a_nh; }
     else if (t < g.AH + g.AL) { e = t - g.AH; j0 = g.a_nh; cnt = g.a_nl; }
-    else if (t < g.AH + g.AL + g.BH) { e = t - g.AH - g.AL; j0 = g.m; cnt = g.b_nh; if (F16) v = 32768.f * wp[i]; }
+    else if (t < g.AH + g.AL + g.BH) { e = t - g.AH - g.AL; j0 = g.m; cnt = g.b_nh; }
     else {
       const int k = t - (g.AH + g.AL + g.BH);
       j0 = g.m + g.b_nh; cnt = g.b_nl;
@@ -195,28 +137,9 @@ __global__ void __launch_bounds__(256) build_tables_kernel(EpsGeom g, const floa
   for (int idx = threadIdx.x; idx < ENT * (TS_ - CH); idx += blockDim.x) out[(idx / (TS_ - CH)) * TS_ + CH + idx % (TS_ - CH)] = 0.f;
 }
 
-// fp16 arithmetic: out[i] = 2^(E_max - 30) * sum_z part[z*count + i]  (fixed order: deterministic)
-__global__ void reduce_partials_scaled_kernel(const float* __restrict__ part, float* __restrict__ out, long long count, int splits,
-                                              const int* __restrict__ emax) {
-  const int k = __ldg(emax) - 30;
-  const float s1 = scalbnf(1.f, k / 2), s2 = scalbnf(1.f, k - k / 2);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += part[(long long)z * count + i];
-    out[i] = s * s1 * s2;
-  }
-}
-
-template <bool THREE, bool F16>
+template <bool THREE>
 __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_constant__ TcDcoreArgs a) {
   extern __shared__ unsigned char smem_dyn[];
-  // per-arithmetic pipeline shape (shadow the TF32 namespace constants)
-  constexpr int SLABS = F16 ? 1 : ::SLABS;                        // 128-byte K slabs per stage: 64 fp16 or 32 tf32 values each
-  constexpr int STAGES = F16 ? STAGES_F16 : ::STAGES;
-  constexpr uint32_t STAGE_BYTES = SLABS * 2 * SLAB_BYTES;        // 32 KB (fp16) / 64 KB (tf32)
-  constexpr int SEG_CHUNKS = F16 ? SEG_CHUNKS_F16 : ::SEG_CHUNKS;
-  constexpr uint32_t A_STAGE_COLS = SLABS * 64;                   // TMEM columns of one A stage (hi | lo per slab)
-  constexpr int MAXST = STAGES_F16;                               // barrier slots are laid out for the larger stage count
   const EpsGeom& g = a.g;
   const int O = g.O;
   const int BLO = g.BL * O;
@@ -233,10 +156,10 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
   float* zrow = tabs + TSTAGES * TE * TS_;                       // [TS_] zeros: padding operand rows multiply this
   float* onerow = zrow + TS_;                                    // [TS_] ones: third factor of rows that have none
   uint64_t* bars = (uint64_t*)(onerow + TS_);
-  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * MAXST + 2 * TSTAGES + 2);
-  const uint32_t bar_fullA0 = tc::smem_u32(bars), bar_fullB0 = bar_fullA0 + 8 * MAXST;
-  const uint32_t bar_empty0 = bar_fullB0 + 8 * MAXST;            // one per stage: frees both the TMEM A stage and the smem B stage
-  const uint32_t bar_tfull0 = bar_empty0 + 8 * MAXST, bar_tempty0 = bar_tfull0 + 8 * TSTAGES;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 2 * TSTAGES + 2);
+  const uint32_t bar_fullA0 = tc::smem_u32(bars), bar_fullB0 = bar_fullA0 + 8 * STAGES;
+  const uint32_t bar_empty0 = bar_fullB0 + 8 * STAGES;           // one per stage: frees both the TMEM A stage and the smem B stage
+  const uint32_t bar_tfull0 = bar_empty0 + 8 * STAGES, bar_tempty0 = bar_tfull0 + 8 * TSTAGES;
   const uint32_t bar_accfull = bar_tempty0 + 8 * TSTAGES, bar_accempty = bar_accfull + 8;
 
   long long pbeg = (long long)blockIdx.z * a.per_split;
@@ -269,7 +192,7 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
 
   if (warp == 0) {
     // =========================== MMA issuer ===========================
-    const uint32_t idesc = F16 ? tc::make_idesc_f16(BM, BN) : tc::make_idesc_tf32(BM, BN);
+    const uint32_t idesc = tc::make_idesc_tf32(BM, BN);
     const uint64_t db_base = tc::make_sw128_kmajor_desc(tc::smem_u32(stages));
     int s = 0;
     uint32_t ph = 0;
@@ -294,24 +217,16 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
         for (int sl = 0; sl < SLABS; ++sl) {
           const uint64_t db_hi = db_base + (uint64_t)((s * STAGE_BYTES + sl * 2 * SLAB_BYTES) >> 4);
           const uint64_t db_lo = db_hi + (SLAB_BYTES >> 4);
-          const uint32_t a_hi = tmem_a0 + (uint32_t)(s * A_STAGE_COLS + sl * 64), a_lo = a_hi + 32;
+          const uint32_t a_hi = tmem_a0 + (uint32_t)(s * 128 + sl * 64), a_lo = a_hi + 32;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {                 // 32 bytes of K per row and MMA: 8 x tf32 or 16 x fp16
+          for (int k = 0; k < 4; ++k) {
             const uint64_t adv = (uint64_t)(k * 2);
             const uint32_t acol = (uint32_t)(k * 8);
             const uint32_t first = (seg_first && sl == 0 && k == 0) ? 0u : 1u;
-            if (F16) {
-              tc::umma_f16_ts(tmem_main, a_hi + acol, db_hi + adv, idesc, first);
-              if (a.passes == 3) {
-                tc::umma_f16_ts(tmem_small, a_hi + acol, db_lo + adv, idesc, first);
-                tc::umma_f16_ts(tmem_small, a_lo + acol, db_hi + adv, idesc, 1u);
-              }
-            } else {
-              tc::umma_tf32_ts(tmem_main, a_hi + acol, db_hi + adv, idesc, first);
-              if (a.passes == 3) {
-                tc::umma_tf32_ts(tmem_small, a_hi + acol, db_lo + adv, idesc, first);
-                tc::umma_tf32_ts(tmem_small, a_lo + acol, db_hi + adv, idesc, 1u);
-              }
+            tc::umma_tf32_ts(tmem_main, a_hi + acol, db_hi + adv, idesc, first);
+            if (a.passes == 3) {
+              tc::umma_tf32_ts(tmem_small, a_hi + acol, db_lo + adv, idesc, first);
+              tc::umma_tf32_ts(tmem_small, a_lo + acol, db_hi + adv, idesc, 1u);
             }
           }
         }
@@ -397,7 +312,7 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
         if (a.passes == 3) {
           tc::tmem_ld32(tmem_small + lane_base + (uint32_t)(chalf * 64 + cb), v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) racc[cb + i] = F16 ? fmaf(v[i], 1.f / 2048.f, racc[cb + i]) : racc[cb + i] + v[i];
+          for (int i = 0; i < 32; ++i) racc[cb + i] += v[i];
         }
       }
       tc::tc_fence_before();
@@ -423,47 +338,32 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
       tc::tc_fence_after();
 #pragma unroll
       for (int sl = 0; sl < SLABS; ++sl) {
-        uint32_t hi[32], lo[32];   // one slab: 32 tf32 values or 64 packed fp16 values (patch 2i in the low half of word i)
-        if (F16) {
+        float hi[32], lo[32];
 #pragma unroll
-          for (int q4 = 0; q4 < 16; ++q4) {
-            float4 h4 = th[q4];
-            const float4 l4 = tl[q4];
-            if (THREE) {
-              const float4 g4 = tg[q4];
-              h4.x *= g4.x; h4.y *= g4.y; h4.z *= g4.z; h4.w *= g4.w;
-            }
-            split_f16x2(h4.x * l4.x, h4.y * l4.y, hi[2 * q4], lo[2 * q4]);
-            split_f16x2(h4.z * l4.z, h4.w * l4.w, hi[2 * q4 + 1], lo[2 * q4 + 1]);
+        for (int q4 = 0; q4 < 8; ++q4) {
+          float4 h4 = th[sl * 8 + q4];
+          const float4 l4 = tl[sl * 8 + q4];
+          if (THREE) {
+            const float4 g4 = tg[sl * 8 + q4];
+            h4.x *= g4.x; h4.y *= g4.y; h4.z *= g4.z; h4.w *= g4.w;
           }
-        } else {
-#pragma unroll
-          for (int q4 = 0; q4 < 8; ++q4) {
-            float4 h4 = th[sl * 8 + q4];
-            const float4 l4 = tl[sl * 8 + q4];
-            if (THREE) {
-              const float4 g4 = tg[sl * 8 + q4];
-              h4.x *= g4.x; h4.y *= g4.y; h4.z *= g4.z; h4.w *= g4.w;
-            }
-            float fh, fl;
-            tc::split_tf32(h4.x * l4.x, fh, fl); hi[4 * q4 + 0] = __float_as_uint(fh); lo[4 * q4 + 0] = __float_as_uint(fl);
-            tc::split_tf32(h4.y * l4.y, fh, fl); hi[4 * q4 + 1] = __float_as_uint(fh); lo[4 * q4 + 1] = __float_as_uint(fl);
-            tc::split_tf32(h4.z * l4.z, fh, fl); hi[4 * q4 + 2] = __float_as_uint(fh); lo[4 * q4 + 2] = __float_as_uint(fl);
-            tc::split_tf32(h4.w * l4.w, fh, fl); hi[4 * q4 + 3] = __float_as_uint(fh); lo[4 * q4 + 3] = __float_as_uint(fl);
-          }
+          tc::split_tf32(h4.x * l4.x, hi[4 * q4 + 0], lo[4 * q4 + 0]);
+          tc::split_tf32(h4.y * l4.y, hi[4 * q4 + 1], lo[4 * q4 + 1]);
+          tc::split_tf32(h4.z * l4.z, hi[4 * q4 + 2], lo[4 * q4 + 2]);
+          tc::split_tf32(h4.w * l4.w, hi[4 * q4 + 3], lo[4 * q4 + 3]);
         }
         if (is_a) {
-          const uint32_t dst = tmem_a0 + lane_base + (uint32_t)(s * A_STAGE_COLS + sl * 64);
-          tc::tmem_st32_u(dst, hi);
-          if (a.passes == 3) tc::tmem_st32_u(dst + 32, lo);
+          const uint32_t dst = tmem_a0 + lane_base + (uint32_t)(s * 128 + sl * 64);
+          tc::tmem_st32(dst, hi);
+          if (a.passes == 3) tc::tmem_st32(dst + 32, lo);
         } else {
           unsigned char* st = stages + s * STAGE_BYTES + sl * 2 * SLAB_BYTES + brow_off;
 #pragma unroll
           for (int q4 = 0; q4 < 8; ++q4) {
             const uint32_t off = (uint32_t)((q4 ^ bsw) << 4);
-            *(uint4*)(st + off) = make_uint4(hi[4 * q4], hi[4 * q4 + 1], hi[4 * q4 + 2], hi[4 * q4 + 3]);
+            *(float4*)(st + off) = make_float4(hi[4 * q4], hi[4 * q4 + 1], hi[4 * q4 + 2], hi[4 * q4 + 3]);
             if (a.passes == 3)
-              *(uint4*)(st + SLAB_BYTES + off) = make_uint4(lo[4 * q4], lo[4 * q4 + 1], lo[4 * q4 + 2], lo[4 * q4 + 3]);
+              *(float4*)(st + SLAB_BYTES + off) = make_float4(lo[4 * q4], lo[4 * q4 + 1], lo[4 * q4 + 2], lo[4 * q4 + 3]);
           }
         }
       }
@@ -517,325 +417,9 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore_kernel(const __grid_c
   if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Split-fp16 core gradient with "patch-owner" B producers (the default core-gradient kernel).
-//
-// With fp16 MMAs a 64-patch chunk is 768 tensor cycles, and the row-per-thread generation above (every thread reads two
-// 256-byte table rows per chunk) made SHARED-MEMORY BANDWIDTH the limiter: 1717 producer cycles per chunk measured
-// (profiles/r01_f16_phase_cycles.txt).  Here
-//   * the B tile is 16 hi-group entries x 8 (lo-group x gout) entries (NBH x NBLO = 128 rows, NBH a template parameter)
-//     instead of 128 consecutive n: the tile needs NBH + NBLO table rows, not ~100, so the table stream per chunk shrinks
-//     from 33 KB to 13 KB;
-//   * a B-producer lane owns TWO PATCHES (one packed fp16 pair) of the chunk, keeps their NBH/4 + NBLO table values in
-//     registers and writes one 32-bit word into each of its warp's 32 rows (the 32 lanes of a warp fill one 128-byte
-//     swizzled row per store: conflict-free).  Table reads of the B side drop from 40 KB to 12 KB per chunk;
-//   * A rows go to tensor memory, one row per thread, as before (a TMEM lane can only be written by its own thread).
-// Output column c of the tile is n = (bh0 + c / NBLO) * BLO + blo0 + c % NBLO; the epilogue scatters accordingly.
-constexpr int TSTAGES16 = 4;   // table buffers (they are small here: latency tolerance instead)
-
-struct Dc16Args {
-  EpsGeom g;
-  const float* tables;  // [ceil(P/64)][ENT][TS_], ENT = AH + AL + BH + BL*O (two-level, fp16-normalised)
-  float* part;          // [splits][A][N]
-  long long per_split;  // multiple of CH
-  int tiles_blo;        // ceil(BL*O / NBLO)
-  long long* dbg;
-};
-
-template <int NBH>
-__global__ void __launch_bounds__(NTHREADS_TC, 1) tc_dcore16_kernel(const __grid_constant__ Dc16Args a) {
-  extern __shared__ unsigned char smem_dyn[];
-  constexpr int NBLO = 128 / NBH;
-  constexpr int BHW = NBH / 4;                    // hi entries per B-producer warp
-  constexpr int STAGES = STAGES_F16;
-  constexpr uint32_t STAGE_BYTES = 2 * SLAB_BYTES;  // hi | lo parts of one 64-patch slab of B: 32 KB
-  constexpr int SEG = SEG_CHUNKS_F16;
-  const EpsGeom& g = a.g;
-  const int BLO = g.BL * g.O;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int a0 = blockIdx.x * BM;
-  const int tbh = blockIdx.y / a.tiles_blo, tblo = blockIdx.y - tbh * a.tiles_blo;
-  const int bh0 = tbh * NBH, blo0 = tblo * NBLO;
-  const int nbh = (g.BH - bh0 < NBH) ? (g.BH - bh0) : NBH;
-  const int nblo = (BLO - blo0 < NBLO) ? (BLO - blo0) : NBLO;
-  int a1 = a0 + BM - 1; if (a1 > g.A - 1) a1 = g.A - 1;
-  const int ah0 = a0 / g.AL, nah = a1 / g.AL - ah0 + 1;
-  // table rows of one buffer: [nah | AL | NBH | NBLO | zero row]; rows past nbh / nblo are never loaded nor read
-  const int rB = nah + g.AL, rL = rB + NBH, rZ = rL + NBLO, TE = rZ + 1;
-
-  unsigned char* base = smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u);
-  unsigned char* stages = base;                                  // [STAGES][hi|lo][128 rows x 128 B]
-  float* tabs = (float*)(base + STAGES * STAGE_BYTES);           // [TSTAGES16][TE][TS_]
-  uint64_t* bars = (uint64_t*)(tabs + TSTAGES16 * TE * TS_);
-  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 2 * TSTAGES16 + 2);
-  const uint32_t bar_fullA0 = tc::smem_u32(bars), bar_fullB0 = bar_fullA0 + 8 * STAGES;
-  const uint32_t bar_empty0 = bar_fullB0 + 8 * STAGES;
-  const uint32_t bar_tfull0 = bar_empty0 + 8 * STAGES, bar_tempty0 = bar_tfull0 + 8 * TSTAGES16;
-  const uint32_t bar_accfull = bar_tempty0 + 8 * TSTAGES16, bar_accempty = bar_accfull + 8;
-
-  long long pbeg = (long long)blockIdx.z * a.per_split;
-  long long pend = pbeg + a.per_split;
-  if (pend > g.P) pend = g.P;
-  const int nchunks = (int)((pend - pbeg + CH - 1) / CH);
-
-  if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      tc::mbar_init(bar_fullA0 + 8 * s, 4);
-      tc::mbar_init(bar_fullB0 + 8 * s, 4);
-      tc::mbar_init(bar_empty0 + 8 * s, 1);
-    }
-    for (int s = 0; s < TSTAGES16; ++s) {
-      tc::mbar_init(bar_tfull0 + 8 * s, 1);
-      tc::mbar_init(bar_tempty0 + 8 * s, NPROD_WARPS);
-    }
-    tc::mbar_init(bar_accfull, 1);
-    tc::mbar_init(bar_accempty, NPROD_WARPS);
-    tc::fence_barrier_init();
-  }
-  if (warp == 0) tc::tmem_alloc(tc::smem_u32(tmem_slot), 512);
-  // zero every buffer once: the zero row (padding A rows) and the B rows past nbh / nblo are never written by the bulk copies
-  for (int i = tid; i < TSTAGES16 * TE * TS_; i += NTHREADS_TC) tabs[i] = 0.f;
-  tc::fence_proxy_async();   // generic-proxy writes before the async-proxy (bulk copy) writes to the same buffers
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_main = tmem_base, tmem_small = tmem_base + BN, tmem_a0 = tmem_base + 2 * BN;   // A stage s: +64*s (hi | lo)
-
-  if (warp == 0) {
-    // =========================== MMA issuer ===========================
-    const uint32_t idesc = tc::make_idesc_f16(BM, BN);
-    const uint64_t db_base = tc::make_sw128_kmajor_desc(tc::smem_u32(stages));
-    int s = 0;
-    uint32_t ph = 0;
-    long long dm_acc = 0, dm_b = 0, dm_a = 0, dm_start = TCD_CLK();
-    for (int c = 0; c < nchunks; ++c) {
-      const bool seg_first = (c % SEG) == 0;
-      const bool seg_last = ((c + 1) % SEG) == 0 || c == nchunks - 1;
-      long long m0 = TCD_CLK();
-      if (seg_first && c > 0) {
-        tc::mbar_wait(bar_accempty, (uint32_t)((c / SEG - 1) & 1));
-        tc::tc_fence_after();
-      }
-      long long m1 = TCD_CLK();
-      tc::mbar_wait(bar_fullB0 + 8 * s, ph);
-      long long m2 = TCD_CLK();
-      tc::mbar_wait(bar_fullA0 + 8 * s, ph);
-      long long m3 = TCD_CLK();
-      dm_acc += m1 - m0; dm_b += m2 - m1; dm_a += m3 - m2;
-      tc::tc_fence_after();
-      if (lane == 0) {
-        const uint64_t db_hi = db_base + (uint64_t)((s * STAGE_BYTES) >> 4);
-        const uint64_t db_lo = db_hi + (SLAB_BYTES >> 4);
-        const uint32_t a_hi = tmem_a0 + (uint32_t)(s * 64), a_lo = a_hi + 32;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t adv = (uint64_t)(k * 2);
-          const uint32_t acol = (uint32_t)(k * 8);
-          const uint32_t first = (seg_first && k == 0) ? 0u : 1u;
-          tc::umma_f16_ts(tmem_main, a_hi + acol, db_hi + adv, idesc, first);
-          tc::umma_f16_ts(tmem_small, a_hi + acol, db_lo + adv, idesc, first);
-          tc::umma_f16_ts(tmem_small, a_lo + acol, db_hi + adv, idesc, 1u);
-        }
-        tc::umma_commit(bar_empty0 + 8 * s);
-        if (seg_last) tc::umma_commit(bar_accfull);
-      }
-      __syncwarp();
-      if (++s == STAGES) { s = 0; ph ^= 1; }
-    }
-    if (a.dbg && lane == 0) {
-      long long* d = a.dbg + ((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16;
-      d[0] = dm_acc; d[1] = dm_b; d[2] = dm_a; d[3] = TCD_CLK() - dm_start; d[4] = nchunks;
-    }
-  } else if (warp == 1 + NPROD_WARPS) {
-    // =========================== table streamer ===========================
-    if (lane == 0) {
-      const int ENT = g.AH + g.AL + g.BH + BLO;
-      const uint32_t row_b = TS_ * 4;
-      const uint32_t bytes = (uint32_t)(nah + g.AL + nbh + nblo) * row_b;
-      const long long chunk0 = pbeg / CH;
-      int ts = 0;
-      uint32_t ph = 1;
-      for (int c = 0; c < nchunks; ++c) {
-        tc::mbar_wait(bar_tempty0 + 8 * ts, ph);
-        const float* src = a.tables + (chunk0 + c) * (long long)ENT * TS_;
-        const uint32_t dst = tc::smem_u32(tabs + ts * TE * TS_);
-        const uint32_t bar = bar_tfull0 + 8 * ts;
-        tc::mbar_arrive_expect_tx(bar, bytes);
-        tc::bulk_g2s(dst, src + (long long)ah0 * TS_, (uint32_t)nah * row_b, bar);
-        tc::bulk_g2s(dst + (uint32_t)nah * row_b, src + (long long)g.AH * TS_, (uint32_t)g.AL * row_b, bar);
-        tc::bulk_g2s(dst + (uint32_t)rB * row_b, src + (long long)(g.AH + g.AL + bh0) * TS_, (uint32_t)nbh * row_b, bar);
-        tc::bulk_g2s(dst + (uint32_t)rL * row_b, src + (long long)(g.AH + g.AL + g.BH + blo0) * TS_, (uint32_t)nblo * row_b, bar);
-        if (++ts == TSTAGES16) { ts = 0; ph ^= 1; }
-      }
-    }
-  } else {
-    // =========================== producers ===========================
-    const int pw = warp - 1;                 // 0..7
-    const bool is_a = pw < 4;                // warps 1..4: A rows (one per thread, into TMEM); warps 5..8: B rows (patch owners)
-    const int quad = warp & 3;
-    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    // A: float offsets (inside a table buffer) of this thread's two table rows; padding rows use the zero row
-    int offH = rZ * TS_, offL = rZ * TS_;
-    if (is_a) {
-      const int ai = a0 + quad * 32 + lane;
-      if (ai < g.A) { offH = (ai / g.AL - ah0) * TS_; offL = (nah + ai % g.AL) * TS_; }
-    }
-    // B: this warp's hi entries [wb*BHW, +BHW) and all NBLO lo entries; the lane owns patches 2*lane, 2*lane+1
-    const int wb = pw - 4;
-    const int offBH = (rB + wb * BHW) * TS_ + 2 * lane, offBL = rL * TS_ + 2 * lane;   // rows past nbh / nblo stay zero
-    // byte offset of this lane's packed word inside row 0 (row r: + r*128, 16-byte chunk index XOR (r & 7))
-    const uint32_t wchunk = (uint32_t)(lane >> 2), wsub = (uint32_t)((lane & 3) << 2);
-
-    const int chalf = pw >> 2;               // promotion: row quad*32 + lane, columns [chalf*64, +64)
-    float racc[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) racc[i] = 0.f;
-    int next_drain = 0;
-    auto drain = [&](int seg) {
-      tc::mbar_wait(bar_accfull, (uint32_t)(seg & 1));
-      tc::tc_fence_after();
-#pragma unroll
-      for (int cb = 0; cb < 64; cb += 32) {
-        float v[32];
-        tc::tmem_ld32(tmem_main + lane_base + (uint32_t)(chalf * 64 + cb), v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) racc[cb + i] += v[i];
-        tc::tmem_ld32(tmem_small + lane_base + (uint32_t)(chalf * 64 + cb), v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) racc[cb + i] = fmaf(v[i], 1.f / 2048.f, racc[cb + i]);
-      }
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(bar_accempty);
-    };
-
-    int s = 0, ts = 0;
-    uint32_t phe = 1, tph = 0;
-    long long dp[4] = {0, 0, 0, 0};
-    for (int c = 0; c < nchunks; ++c) {
-      long long q0 = TCD_CLK();
-      tc::mbar_wait(bar_tfull0 + 8 * ts, tph);
-      long long q1 = TCD_CLK();
-      const float* tb = tabs + ts * TE * TS_;
-      if (is_a) {
-        const float4* th = (const float4*)(tb + offH);
-        const float4* tl = (const float4*)(tb + offL);
-        const uint32_t dst = tmem_a0 + lane_base + (uint32_t)(s * 64);
-        // two halves of 32 patches each (16 packed columns of hi, 16 of lo): keeps 32 registers free for the accumulators
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int q4 = 0; q4 < 8; ++q4) {
-            const float4 h4 = th[hf * 8 + q4], l4 = tl[hf * 8 + q4];
-            tc::split_f16x2_p(tc::mul2(tc::pack2(h4.x, h4.y), tc::pack2(l4.x, l4.y)), hi[2 * q4], lo[2 * q4]);
-            tc::split_f16x2_p(tc::mul2(tc::pack2(h4.z, h4.w), tc::pack2(l4.z, l4.w)), hi[2 * q4 + 1], lo[2 * q4 + 1]);
-          }
-          if (hf == 0) {
-            tc::mbar_wait(bar_empty0 + 8 * s, phe);
-            tc::tc_fence_after();
-          }
-          tc::tmem_st16_u(dst + (uint32_t)(hf * 16), hi);
-          tc::tmem_st16_u(dst + 32 + (uint32_t)(hf * 16), lo);
-        }
-        tc::tmem_st_wait();
-        tc::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(bar_fullA0 + 8 * s);
-      } else {
-        tc::f32x2_t th[BHW], tl[NBLO];
-#pragma unroll
-        for (int i = 0; i < BHW; ++i) th[i] = tc::as_f32x2(*(const float2*)(tb + offBH + i * TS_));
-#pragma unroll
-        for (int j = 0; j < NBLO; ++j) tl[j] = tc::as_f32x2(*(const float2*)(tb + offBL + j * TS_));
-        tc::mbar_wait(bar_empty0 + 8 * s, phe);
-        unsigned char* st = stages + s * STAGE_BYTES + wsub;
-#pragma unroll
-        for (int i = 0; i < BHW; ++i) {
-#pragma unroll
-          for (int j = 0; j < NBLO; ++j) {
-            const int r = (wb * BHW + i) * NBLO + j;
-            uint32_t h, l;
-            tc::split_f16x2_p(tc::mul2(th[i], tl[j]), h, l);
-            const uint32_t off = (uint32_t)(r * 128) + ((wchunk ^ (uint32_t)(r & 7)) << 4);
-            *(uint32_t*)(st + off) = h;
-            *(uint32_t*)(st + SLAB_BYTES + off) = l;
-          }
-        }
-        tc::fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(bar_fullB0 + 8 * s);
-      }
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(bar_tempty0 + 8 * ts);
-      if (++ts == TSTAGES16) { ts = 0; tph ^= 1; }
-      long long q2 = TCD_CLK();
-      if (++s == STAGES) { s = 0; phe ^= 1; }
-      if ((c % SEG) == 0 && c > 0) drain(next_drain++);
-      long long q3 = TCD_CLK();
-      dp[0] += q1 - q0; dp[1] += q2 - q1; dp[2] += q3 - q2;
-    }
-    if (a.dbg && lane == 0 && (warp == 1 || warp == 5)) {
-      long long* d = a.dbg + ((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (warp == 1 ? 5 : 9);
-      for (int i = 0; i < 3; ++i) d[i] = dp[i];
-    }
-    const int last_seg = (nchunks - 1) / SEG;
-    while (next_drain <= last_seg) drain(next_drain++);
-
-    // =========================== epilogue: registers -> partial tile (scattered columns) ===========================
-    const int arow = a0 + quad * 32 + lane;
-    if (arow < g.A) {
-      float* prow = a.part + ((long long)blockIdx.z * g.A + arow) * (long long)g.N;
-#pragma unroll
-      for (int cc = 0; cc < 64; ++cc) {
-        const int c = chalf * 64 + cc;
-        const int bhl = c / NBLO, j = c % NBLO;
-        if (bhl < nbh && j < nblo) prow[(long long)(bh0 + bhl) * BLO + blo0 + j] = racc[cc];
-      }
-    }
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
-}
-
-// B-tile shape NBH x (128 / NBH): least padding, ties to 16 x 8
-inline int pick_nbh(const EpsGeom& g) {
-  const int BLO = g.BL * g.O;
-  int best = 16;
-  long long best_cost = -1;
-  const int cand[4] = {16, 8, 32, 4};
-  for (int i = 0; i < 4; ++i) {
-    const int nbh = cand[i], nblo = 128 / nbh;
-    const long long cost = (long long)((g.BH + nbh - 1) / nbh) * nbh * ((BLO + nblo - 1) / nblo) * nblo;
-    if (best_cost < 0 || cost < best_cost) { best = nbh; best_cost = cost; }
-  }
-  return best;
-}
-inline size_t dcore16_smem(const EpsGeom& g, int nbh) {
-  int nah = (BM + g.AL - 1) / g.AL + 1; if (nah > g.AH) nah = g.AH;
-  const int TE = nah + g.AL + nbh + 128 / nbh + 1;
-  return 1024 + (size_t)STAGES_F16 * 2 * SLAB_BYTES + (size_t)TSTAGES16 * TE * TS_ * 4 + (3 * STAGES_F16 + 2 * TSTAGES16 + 2) * 8 + 16;
-}
-inline void dcore16_split(const EpsGeom& g, int nbh, long long* per_split, int* splits, int* tiles_bh, int* tiles_blo) {
-  const int BLO = g.BL * g.O, nblo = 128 / nbh;
-  *tiles_bh = (g.BH + nbh - 1) / nbh;
-  *tiles_blo = (BLO + nblo - 1) / nblo;
-  const long long tiles = (long long)((g.A + BM - 1) / BM) * *tiles_bh * *tiles_blo;
-  long long want = (2 * 148) / tiles;     // about two waves of one CTA per SM
-  if (want < 1) want = 1;
-  long long per = (g.P + want - 1) / want;
-  per = ((per + CH - 1) / CH) * CH;
-  const long long min_per = (long long)CH * SEG_CHUNKS_F16 * 2;
-  if (per < min_per) per = min_per;
-  *per_split = per;
-  *splits = (int)((g.P + per - 1) / per);
-}
-
 size_t dcore_tc_smem(const EpsGeom& g, int three) {
   const int TE = max_tile_entries(g, three);
-  return 1024 + (size_t)STAGES * STAGE_BYTES + (size_t)(TSTAGES * TE + 2) * TS_ * 4 + (3 * STAGES_F16 + 2 * TSTAGES + 2) * 8 + 16;
+  return 1024 + (size_t)STAGES * STAGE_BYTES + (size_t)(TSTAGES * TE + 2) * TS_ * 4 + (3 * STAGES + 2 * TSTAGES + 2) * 8 + 16;
 }
 // two-level B rows when their tables fit in shared memory, else three-level; -1: neither fits
 inline int pick_three(const EpsGeom& g) {
@@ -869,7 +453,7 @@ bool tc_supported(const EpsGeom& g, int kind) {
   if (g.P >= (1ll << 31) / (g.Q > g.O ? g.Q : g.O)) return false;  // 32-bit patch index math
   if (g.A < 64 || g.N < 64) return false;    // tiles would be mostly padding: the CUDA-core family is the better fit
   if (g.P < 4096) return false;              // tiny reductions are launch-bound either way
-  return pick_three(g) >= 0 && dcore16_smem(g, pick_nbh(g)) <= TC_SMEM_LIMIT;
+  return pick_three(g) >= 0 && tc16_dcore_supported(g);   // both arithmetics serve the same shapes
 }
 
 size_t tc_workspace_bytes(const EpsGeom& g, int kind) {
@@ -878,78 +462,16 @@ size_t tc_workspace_bytes(const EpsGeom& g, int kind) {
     int splits;
     dcore_split(g, &per, &splits);
     const int three = pick_three(g);
-    long long per16;
-    int splits16, tbh, tblo;
-    dcore16_split(g, pick_nbh(g), &per16, &splits16, &tbh, &tblo);
-    if (splits16 > splits) splits = splits16;
-    size_t tf = table_floats(g, three < 0 ? 0 : three), tf0 = table_floats(g, 0);
-    if (tf0 > tf) tf = tf0;
-    // partial tiles, tables, and (fp16 arithmetic) the per-patch exponents + the slot of their maximum
-    return ((size_t)splits * g.A * g.N + 64 + tf + 64 + (size_t)g.P + 64) * sizeof(float) + 256;
+    const size_t tf32 = ((size_t)splits * g.A * g.N + table_floats(g, three < 0 ? 0 : three)) * sizeof(float) + 256;
+    const size_t f16 = tc16_dcore_workspace_bytes(g);
+    return tf32 > f16 ? tf32 : f16;
   }
   return tcg_workspace_bytes(g, kind);
 }
 
-// split-fp16 core gradient: patch exponents -> normalised two-level tables -> tc_dcore16_kernel -> scaled reduction
-static int backward_core_f16(const EpsGeom& g, const float* x, const float* gout, float* dcore, void* ws, cudaStream_t st) {
-  const int nbh = pick_nbh(g);
-  const size_t smem = dcore16_smem(g, nbh);
-  if (smem > TC_SMEM_LIMIT) return dctn_set_error(-2, "tcgen05 core-gradient kernel needs %zu bytes of shared memory", smem);
-  Dc16Args a{};
-  a.g = g; a.part = (float*)ws;
-  int splits, tiles_bh;
-  dcore16_split(g, nbh, &a.per_split, &splits, &tiles_bh, &a.tiles_blo);
-  float* tables = a.part + (((size_t)splits * g.A * g.N + 63) & ~(size_t)63);
-  a.tables = tables;
-  int* exps = (int*)(tables + ((table_floats(g, 0) + 63) & ~(size_t)63));
-  int* emax = exps + ((g.P + 63) & ~63ll);
-  const size_t bsm = (size_t)((g.n * g.Q + g.O) * CH + CH) * sizeof(float);
-  if (bsm > 200 * 1024) return dctn_set_error(-2, "table kernel needs %zu bytes of shared memory", bsm);
-  DCTN_CUDA_CHECK_RET(cudaMemsetAsync(emax, 0x80, sizeof(int), st));   // 0x80808080: below every possible E_p
-  patch_exp_kernel<<<(unsigned)((g.P + 255) / 256), 256, 0, st>>>(g, x, gout, exps, emax);
-  dctn_count_launch();
-  DCTN_CUDA_CHECK_RET(cudaGetLastError());
-  DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(build_tables_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
-  build_tables_kernel<true><<<(unsigned)((g.P + CH - 1) / CH), 256, bsm, st>>>(g, x, gout, tables, 0, exps, emax);
-  dctn_count_launch();
-  DCTN_CUDA_CHECK_RET(cudaGetLastError());
-  auto kern = nbh == 4 ? tc_dcore16_kernel<4> : nbh == 8 ? tc_dcore16_kernel<8> : nbh == 16 ? tc_dcore16_kernel<16> : tc_dcore16_kernel<32>;
-  DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((g.A + BM - 1) / BM, tiles_bh * a.tiles_blo, splits);
-  a.dbg = nullptr;
-  static long long* dbg_buf = nullptr;
-  const int ncta = (int)(grid.x * grid.y * grid.z);
-  if (getenv("DCTN_TCG_DEBUG") && ncta <= 4096) {
-    if (!dbg_buf) cudaMalloc(&dbg_buf, 4096 * 16 * sizeof(long long));
-    cudaMemsetAsync(dbg_buf, 0, 4096 * 16 * sizeof(long long), st);
-    a.dbg = dbg_buf;
-  }
-  kern<<<grid, NTHREADS_TC, smem, st>>>(a);
-  dctn_count_launch();
-  DCTN_CUDA_CHECK_RET(cudaGetLastError());
-  if (a.dbg) {
-    static long long host[4096 * 16];
-    cudaStreamSynchronize(st);
-    cudaMemcpy(host, dbg_buf, (size_t)ncta * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
-    double sum[16] = {0};
-    for (int c = 0; c < ncta; ++c) for (int k = 0; k < 16; ++k) sum[k] += (double)host[c * 16 + k];
-    const double nch = sum[4];
-    fprintf(stderr, "[dcore16 dbg] NBH=%d ctas=%d chunks/cta=%.0f per-chunk cycles: mma wait acc %.0f B %.0f A %.0f total %.0f | A producer: wait-tables %.0f rows %.0f drain %.0f | "
-            "B producer: wait-tables %.0f rows %.0f drain %.0f\n", nbh, ncta, nch / ncta, sum[0] / nch, sum[1] / nch, sum[2] / nch, sum[3] / nch,
-            sum[5] / nch, sum[6] / nch, sum[7] / nch, sum[9] / nch, sum[10] / nch, sum[11] / nch);
-  }
-  const long long count = (long long)g.A * g.N;
-  int blocks = (int)((count + 255) / 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  reduce_partials_scaled_kernel<<<blocks, 256, 0, st>>>(a.part, dcore, count, splits, emax);
-  dctn_count_launch();
-  DCTN_CUDA_CHECK_RET(cudaGetLastError());
-  return 0;
-}
-
 int tc_backward_core(const EpsGeom& g, const float* x, const float* gout, float* dcore, void* ws, int passes,
                      cudaStream_t st) {
-  if (passes == ARITH_F16X3) return backward_core_f16(g, x, gout, dcore, ws, st);
+  if (passes == 6) return tc16_backward_core(g, x, gout, dcore, ws, st);   // split fp16 (eps_tc_dcore.cu)
   const int three = pick_three(g);
   if (three < 0) return dctn_set_error(-2, "tcgen05 core-gradient kernel: tables of this shape do not fit in shared memory");
   const size_t smem = dcore_tc_smem(g, three);
@@ -957,31 +479,17 @@ int tc_backward_core(const EpsGeom& g, const float* x, const float* gout, float*
   a.g = g; a.part = (float*)ws; a.passes = passes; a.three = three;
   int splits;
   dcore_split(g, &a.per_split, &splits);
-  const bool f16 = passes == ARITH_F16X3;
-  if (f16) a.passes = 3;
   float* tables = a.part + (((size_t)splits * g.A * g.N + 63) & ~(size_t)63);
   a.tables = tables;
-  int* exps = (int*)(tables + ((table_floats(g, three) + 63) & ~(size_t)63));
-  int* emax = exps + ((g.P + 63) & ~63ll);
   {
-    const size_t bsm = (size_t)((g.n * g.Q + g.O) * CH + CH) * sizeof(float);
+    const size_t bsm = (size_t)(g.n * g.Q + g.O) * CH * sizeof(float);
     if (bsm > 200 * 1024) return dctn_set_error(-2, "table kernel needs %zu bytes of shared memory", bsm);
-    if (f16) {
-      DCTN_CUDA_CHECK_RET(cudaMemsetAsync(emax, 0x80, sizeof(int), st));   // 0x80808080: below every possible E_p
-      patch_exp_kernel<<<(unsigned)((g.P + 255) / 256), 256, 0, st>>>(g, x, gout, exps, emax);
-      dctn_count_launch();
-      DCTN_CUDA_CHECK_RET(cudaGetLastError());
-      DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(build_tables_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
-      build_tables_kernel<true><<<(unsigned)((g.P + CH - 1) / CH), 256, bsm, st>>>(g, x, gout, tables, three, exps, emax);
-    } else {
-      DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(build_tables_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
-      build_tables_kernel<false><<<(unsigned)((g.P + CH - 1) / CH), 256, bsm, st>>>(g, x, gout, tables, three, nullptr, nullptr);
-    }
+    DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(build_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+    build_tables_kernel<<<(unsigned)((g.P + CH - 1) / CH), 256, bsm, st>>>(g, x, gout, tables, three);
     dctn_count_launch();
     DCTN_CUDA_CHECK_RET(cudaGetLastError());
   }
-  auto kern = f16 ? (three ? tc_dcore_kernel<true, true> : tc_dcore_kernel<false, true>)
-                  : (three ? tc_dcore_kernel<true, false> : tc_dcore_kernel<false, false>);
+  auto kern = three ? tc_dcore_kernel<true> : tc_dcore_kernel<false>;
   DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((g.A + BM - 1) / BM, (g.N + BN - 1) / BN, splits);
   a.dbg = nullptr;
@@ -1006,15 +514,6 @@ int tc_backward_core(const EpsGeom& g, const float* x, const float* gout, float*
             "bar1 %.0f prefetch+tables %.0f bar2 %.0f wait-empty %.0f rows+signal %.0f drain %.0f\n", ncta, nch / ncta,
             sum[0] / nch, sum[1] / nch, sum[2] / nch, sum[3] / nch, sum[5] / nch, sum[6] / nch, sum[7] / nch, sum[8] / nch,
             sum[9] / nch, sum[10] / nch, sum[11] / nch);
-  }
-  if (f16) {
-    const long long count = (long long)g.A * g.N;
-    int blocks = (int)((count + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    reduce_partials_scaled_kernel<<<blocks, 256, 0, st>>>(a.part, dcore, count, splits, emax);
-    dctn_count_launch();
-    DCTN_CUDA_CHECK_RET(cudaGetLastError());
-    return 0;
   }
   return launch_reduce_partials<float>(a.part, dcore, (long long)g.A * g.N, splits, st);
 }
