@@ -15,8 +15,10 @@
 //     mbarrier complete_tx) straight into the B stages: no B generation, no generic-proxy writes, no proxy fences;
 //   * CTA tile: 128 (a) x NT (blo), NT <= 128 columns; grid = a-tiles x BH x blo-tiles x splits of the patch range.
 // Number format and accumulation are those of eps_tc_gemm.cu / eps_tc.cu: v = hi + lo * 2^-11 (22 significant bits),
-// hi*hi into a MAIN TMEM accumulator, the cross terms into a SMALL one, both promoted to fp32 registers every
-// SEG16 chunks (the tensor core rounds its accumulator toward zero).  fp16 range: every factor vector and the gout row
+// hi*hi into a MAIN TMEM accumulator, the cross terms into a SMALL one.  The tensor core rounds its accumulator toward
+// zero, so the main chain is kept short: TWO main accumulators alternate between segments of SEG16 chunks, and while
+// one fills, the producers add the other into fp32 registers ("promotion") — the MMAs never wait for it.  The small
+// accumulator (weight 2^-11) runs through.  fp16 range: every factor vector and the gout row
 // of a patch are scaled to max-abs in [0.5, 1) (exact powers of two); the reduction runs over patches, so the patch
 // scale cannot be undone afterwards: patch_exp_kernel finds E_max = max_p E_p and 2^(E_p - E_max) <= 1 is folded into
 // TBH.  A' and TLO carry 2^15 each; reduce_partials_scaled_kernel applies 2^(E_max - 30).
@@ -38,11 +40,12 @@ namespace {
 
 constexpr int BM = 128;            // a rows = TMEM lanes
 constexpr int CH = 64;             // patches per chunk = one 128-byte fp16 K slab
-constexpr int STAGES = 4;          // pipeline stages: B slab in shared memory, A' slab in tensor memory (64 columns: hi | lo)
+constexpr int MAX_STAGES = 4;      // pipeline stages: B slab in shared memory, A' slab in tensor memory (64 columns: hi | lo);
+                                   // as many as fit next to the three accumulators in the 512 TMEM columns
 constexpr int TSTAGES = 4;         // table buffers
 constexpr int SEG16 = 24;          // chunks per promotion segment: 24 * 4 k-steps = 96 roundings of the main chain
-constexpr int NPROD_WARPS = 8;     // warps 1..8 generate A'; warp 0 issues MMAs; warp 9 streams tables and B
-constexpr int NTHREADS = 32 * (2 + NPROD_WARPS);
+constexpr int NPROD_WARPS = 8;     // warps 1..8 generate A'; warp 0 issues MMAs; warp 9 streams the tables, warp 10 the B slabs
+constexpr int NTHREADS = 32 * (3 + NPROD_WARPS);
 constexpr int TS_ = CH + 4;        // table row stride in floats (272 bytes)
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 
@@ -188,6 +191,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
   extern __shared__ unsigned char smem_dyn[];
   constexpr int NT = 32 * NTH;
   constexpr int NCOL = 16 * NTH;                       // columns promoted by one thread
+  constexpr int STAGES = ((512 - 3 * NT) / 64 < MAX_STAGES) ? (512 - 3 * NT) / 64 : MAX_STAGES;   // 4, 4, 3, 2 for NT = 32..128
   constexpr uint32_t PART_BYTES = NT * 128;            // hi or lo part of one B slab
   constexpr uint32_t STAGE_BYTES = 2 * PART_BYTES;
   const EpsGeom& g = a.g;
@@ -204,11 +208,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
   unsigned char* stages = base;                                  // [STAGES][hi|lo][NT rows x 128 B]
   float* tabs = (float*)(base + STAGES * STAGE_BYTES);           // [TSTAGES][TE][TS_]
   uint64_t* bars = (uint64_t*)(tabs + TSTAGES * TE * TS_);
-  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 2 * TSTAGES + 2);
-  const uint32_t bar_fullA0 = tc::smem_u32(bars), bar_fullB0 = bar_fullA0 + 8 * STAGES;
-  const uint32_t bar_empty0 = bar_fullB0 + 8 * STAGES;           // one per stage: frees the TMEM A' slab and the smem B slab
-  const uint32_t bar_tfull0 = bar_empty0 + 8 * STAGES, bar_tempty0 = bar_tfull0 + 8 * TSTAGES;
-  const uint32_t bar_accfull = bar_tempty0 + 8 * TSTAGES, bar_accempty = bar_accfull + 8;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * MAX_STAGES + 2 * TSTAGES + 4);
+  const uint32_t bar_fullA0 = tc::smem_u32(bars), bar_fullB0 = bar_fullA0 + 8 * MAX_STAGES;
+  const uint32_t bar_empty0 = bar_fullB0 + 8 * MAX_STAGES;       // one per stage: frees the TMEM A' slab and the smem B slab
+  const uint32_t bar_tfull0 = bar_empty0 + 8 * MAX_STAGES, bar_tempty0 = bar_tfull0 + 8 * TSTAGES;
+  const uint32_t bar_accfull0 = bar_tempty0 + 8 * TSTAGES, bar_accempty0 = bar_accfull0 + 16;   // one pair per main accumulator
 
   long long pbeg = (long long)blockIdx.z * a.per_split;
   long long pend = pbeg + a.per_split;
@@ -226,8 +230,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
       tc::mbar_init(bar_tfull0 + 8 * s, 1);
       tc::mbar_init(bar_tempty0 + 8 * s, NPROD_WARPS);
     }
-    tc::mbar_init(bar_accfull, 1);
-    tc::mbar_init(bar_accempty, NPROD_WARPS);
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(bar_accfull0 + 8 * b, 1);
+      tc::mbar_init(bar_accempty0 + 8 * b, NPROD_WARPS);
+    }
     tc::fence_barrier_init();
   }
   if (warp == 0) tc::tmem_alloc(tc::smem_u32(tmem_slot), 512);
@@ -236,7 +242,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_main = tmem_base, tmem_small = tmem_base + NT, tmem_a0 = tmem_base + 256;   // A' stage s: +64*s (hi | lo)
+  // columns: main accumulator 0 | main accumulator 1 | small accumulator | A' stages (64 columns each: hi | lo)
+  const uint32_t tmem_main0 = tmem_base, tmem_small = tmem_base + 2 * NT, tmem_a0 = tmem_base + 3 * NT;
 
   if (warp == 0) {
     // =========================== MMA issuer ===========================
@@ -248,9 +255,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
     for (int c = 0; c < nchunks; ++c) {
       const bool seg_first = (c % SEG16) == 0;
       const bool seg_last = ((c + 1) % SEG16) == 0 || c == nchunks - 1;
+      const int seg = c / SEG16, mb = seg & 1;          // segment and the main accumulator it uses
+      const uint32_t tmem_main = tmem_main0 + (uint32_t)(mb * NT);
       long long m0 = TC16_CLK();
-      if (seg_first && c > 0) {   // the previous segment must have been promoted before its accumulators are overwritten
-        tc::mbar_wait(bar_accempty, (uint32_t)((c / SEG16 - 1) & 1));
+      if (seg_first && seg >= 2) {   // segment seg-2 (same accumulator) must have been promoted before it is overwritten
+        tc::mbar_wait(bar_accempty0 + 8 * mb, (uint32_t)(((seg - 2) >> 1) & 1));
         tc::tc_fence_after();
       }
       long long m1 = TC16_CLK();
@@ -270,11 +279,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
           const uint32_t acol = (uint32_t)(k * 8);
           const uint32_t first = (seg_first && k == 0) ? 0u : 1u;
           tc::umma_f16_ts(tmem_main, a_hi + acol, db_hi + adv, idesc, first);
-          tc::umma_f16_ts(tmem_small, a_hi + acol, db_lo + adv, idesc, first);
+          tc::umma_f16_ts(tmem_small, a_hi + acol, db_lo + adv, idesc, (c == 0 && k == 0) ? 0u : 1u);
           tc::umma_f16_ts(tmem_small, a_lo + acol, db_hi + adv, idesc, 1u);
         }
         tc::umma_commit(bar_empty0 + 8 * s);
-        if (seg_last) tc::umma_commit(bar_accfull);
+        if (seg_last) tc::umma_commit(bar_accfull0 + 8 * mb);
       }
       __syncwarp();
       if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -284,13 +293,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
       d[0] = dm_acc; d[1] = dm_b; d[2] = dm_a; d[3] = TC16_CLK() - dm_start; d[4] = nchunks;
     }
   } else if (warp == 1 + NPROD_WARPS) {
-    // =========================== streamer: tables (for the producers) and B slabs (for the MMAs) ===========================
+    // =========================== table streamer (for the producers) ===========================
     if (lane == 0) {
       const int ENT = g.AH + g.AL + g.BH;
       const uint32_t row_b = TS_ * 4;
       const uint32_t tbytes = (uint32_t)(nah + g.AL + 1) * row_b;
-      int ts = 0, s = 0;
-      uint32_t tph = 1, ph = 1;
+      int ts = 0;
+      uint32_t tph = 1;
       for (int c = 0; c < nchunks; ++c) {
         tc::mbar_wait(bar_tempty0 + 8 * ts, tph);
         const float* src = a.tables + (chunk0 + c) * (long long)ENT * TS_;
@@ -301,6 +310,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
         tc::bulk_g2s(dst + (uint32_t)nah * row_b, src + (long long)g.AH * TS_, (uint32_t)g.AL * row_b, tbar);
         tc::bulk_g2s(dst + (uint32_t)rBH * row_b, src + (long long)(g.AH + g.AL + bh) * TS_, row_b, tbar);
         if (++ts == TSTAGES) { ts = 0; tph ^= 1; }
+      }
+    }
+  } else if (warp == 2 + NPROD_WARPS) {
+    // =========================== B streamer (for the MMAs): the pre-split image, one slab per chunk ===========================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 1;
+      for (int c = 0; c < nchunks; ++c) {
         tc::mbar_wait(bar_empty0 + 8 * s, ph);
         const float* bsrc = a.bimg + ((chunk0 + c) * a.ntile + tile) * (long long)(2 * NT * 32);
         tc::mbar_arrive_expect_tx(bar_fullB0 + 8 * s, STAGE_BYTES);
@@ -325,22 +342,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
 #pragma unroll
     for (int i = 0; i < NCOL; ++i) racc[i] = 0.f;
     int next_drain = 0;
+    const int nseg = (nchunks + SEG16 - 1) / SEG16;
+    // promotion of segment seg: its main accumulator; the last segment also takes the small accumulator (which ran through)
     auto drain = [&](int seg) {
-      tc::mbar_wait(bar_accfull, (uint32_t)(seg & 1));
+      const int mb = seg & 1;
+      tc::mbar_wait(bar_accfull0 + 8 * mb, (uint32_t)((seg >> 1) & 1));
       tc::tc_fence_after();
 #pragma unroll
       for (int cb = 0; cb < NCOL; cb += 16) {
         float v[16];
-        tmem_ld16(tmem_main + lane_base + (uint32_t)(hf * NCOL + cb), v);
+        tmem_ld16(tmem_main0 + lane_base + (uint32_t)(mb * NT + hf * NCOL + cb), v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) racc[cb + i] += v[i];
-        tmem_ld16(tmem_small + lane_base + (uint32_t)(hf * NCOL + cb), v);
+        if (seg == nseg - 1) {
+          tmem_ld16(tmem_small + lane_base + (uint32_t)(hf * NCOL + cb), v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) racc[cb + i] = fmaf(v[i], 1.f / 2048.f, racc[cb + i]);
+          for (int i = 0; i < 16; ++i) racc[cb + i] = fmaf(v[i], 1.f / 2048.f, racc[cb + i]);
+        }
       }
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(bar_accempty);
+      if (lane == 0) tc::mbar_arrive(bar_accempty0 + 8 * mb);
     };
 
     int s = 0, ts = 0;
@@ -377,7 +399,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
       if (lane == 0) tc::mbar_arrive(bar_fullA0 + 8 * s);
       long long q2 = TC16_CLK();
       if (++s == STAGES) { s = 0; phe ^= 1; }
-      if ((c % SEG16) == 0 && c > 0) drain(next_drain++);
+      // segment seg was handed to the tensor core SEG16/2 chunks ago: it has long completed, so this never waits
+      if ((c % SEG16) == SEG16 / 2 && c > SEG16) drain(next_drain++);
       long long q3 = TC16_CLK();
       dp[0] += q1 - q0; dp[1] += q2 - q1; dp[2] += q3 - q2;
     }
@@ -385,8 +408,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
       long long* d = a.dbg + ((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + 5;
       for (int i = 0; i < 3; ++i) d[i] = dp[i];
     }
-    const int last_seg = (nchunks - 1) / SEG16;
-    while (next_drain <= last_seg) drain(next_drain++);
+    while (next_drain < nseg) drain(next_drain++);
 
     // =========================== epilogue: registers -> partial tile ===========================
     const int arow = a0 + quad * 32 + lane;
@@ -423,10 +445,33 @@ inline int pick_nt(const EpsGeom& g) {
   }
   return best;
 }
+// The generated operand A' has A * BH rows and is regenerated for every blo tile, so the work of the producers (the
+// limiter of this kernel) is proportional to BH * ntile.  The split of the second half into hi / lo groups is free here
+// (n = bh * BLO + blo for any split): take the one with the least generation, ties to the larger hi group.
+inline EpsGeom regroup(const EpsGeom& g0) {
+  EpsGeom best = g0;
+  long long best_cost = -1;
+  const int cnt = g0.n - g0.m;
+  for (int nh = cnt; nh >= 0; --nh) {
+    EpsGeom g = g0;
+    g.b_nh = nh; g.b_nl = cnt - nh;
+    const long long BH = ipow_host(g0.Q, nh), BL = ipow_host(g0.Q, cnt - nh);
+    if (BL * g0.O > (1 << 20)) continue;
+    g.BH = (int)BH; g.BL = (int)BL;
+    const int NT = pick_nt(g);
+    // NT = 128 leaves room for only two A' stages in tensor memory and makes the MMAs of a chunk as long as its
+    // generation: measured 1.4x per chunk (config 2, layer 2: 16 x 1 tiles of 96 beat 4 x 3 tiles of 128)
+    const long long cost = BH * ((BL * g0.O + NT - 1) / NT) * (NT == 128 ? 14 : 10);
+    if (best_cost < 0 || cost < best_cost) { best = g; best_cost = cost; }
+  }
+  return best;
+}
+
 inline size_t dcore16_smem(const EpsGeom& g, int NT) {
   int nah = (BM + g.AL - 1) / g.AL + 1; if (nah > g.AH) nah = g.AH;
   const int TE = nah + g.AL + 2;
-  return 1024 + (size_t)STAGES * 2 * NT * 128 + (size_t)TSTAGES * TE * TS_ * 4 + (3 * STAGES + 2 * TSTAGES + 2) * 8 + 16;
+  const int stages = ((512 - 3 * NT) / 64 < MAX_STAGES) ? (512 - 3 * NT) / 64 : MAX_STAGES;
+  return 1024 + (size_t)stages * 2 * NT * 128 + (size_t)TSTAGES * TE * TS_ * 4 + (3 * MAX_STAGES + 2 * TSTAGES + 4) * 8 + 16;
 }
 // split the patch range so that the grid fills whole waves of one CTA per SM
 inline void dcore16_split(const EpsGeom& g, int ntile, long long* per_split, int* splits) {
@@ -454,7 +499,8 @@ inline size_t bimg_words(const EpsGeom& g, int NT, int ntile) { return (size_t)(
 
 }  // namespace
 
-bool tc16_dcore_supported(const EpsGeom& g) {
+bool tc16_dcore_supported(const EpsGeom& g0) {
+  const EpsGeom g = regroup(g0);
   if (g.P >= (1ll << 31) / (g.Q > g.O ? g.Q : g.O)) return false;   // 32-bit patch index math
   if (g.A < 64 || g.N < 64) return false;       // tiles would be mostly padding: the CUDA-core family is the better fit
   if (g.P < 4096) return false;                 // tiny reductions are launch-bound either way
@@ -462,7 +508,8 @@ bool tc16_dcore_supported(const EpsGeom& g) {
   return dcore16_smem(g, pick_nt(g)) <= SMEM_LIMIT;
 }
 
-size_t tc16_dcore_workspace_bytes(const EpsGeom& g) {
+size_t tc16_dcore_workspace_bytes(const EpsGeom& g0) {
+  const EpsGeom g = regroup(g0);
   const int NT = pick_nt(g), ntile = (g.BL * g.O + NT - 1) / NT;
   long long per;
   int splits;
@@ -470,7 +517,8 @@ size_t tc16_dcore_workspace_bytes(const EpsGeom& g) {
   return ((size_t)splits * g.A * g.N + 64 + table_floats(g) + 64 + bimg_words(g, NT, ntile) + 64 + (size_t)g.P + 64 + 64) * 4 + 256;
 }
 
-int tc16_backward_core(const EpsGeom& g, const float* x, const float* gout, float* dcore, void* ws, cudaStream_t st) {
+int tc16_backward_core(const EpsGeom& g0, const float* x, const float* gout, float* dcore, void* ws, cudaStream_t st) {
+  const EpsGeom g = regroup(g0);
   const int NT = pick_nt(g), ntile = (g.BL * g.O + NT - 1) / NT;
   const size_t smem = dcore16_smem(g, NT);
   if (smem > SMEM_LIMIT) return dctn_set_error(-2, "tcgen05 core-gradient kernel needs %zu bytes of shared memory", smem);
