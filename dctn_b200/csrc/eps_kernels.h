@@ -45,7 +45,9 @@ bool tc16_dcore_supported(const EpsGeom& g);
 size_t tc16_dcore_workspace_bytes(const EpsGeom& g);
 int tc16_backward_core(const EpsGeom& g, const float* x, const float* gout, float* dcore, void* ws, cudaStream_t st);
 // eps_tc_fast.cu: register-table variant of the two GEMMs above for power-of-two Q, split-fp16 arithmetic
-// (mode 0: input-gradient GEMM dKR1, mode 1: forward)
+// (mode 0: input-gradient GEMM dKR1, mode 1: forward, mode 2: input-gradient GEMM with the first leave-one-out stage
+// fused: out = W[np][ldc], ldc = tcfast_loo_groups() = hi-group + lo-group entries of the first half)
+int tcfast_loo_groups(const EpsGeom& g, int* cnth, int* EH, int* cntl, int* EL);
 bool tcfast_supported(const EpsGeom& g, int mode);
 size_t tcfast_packed_floats(const EpsGeom& g, int mode);
 int tcfast_pack(const EpsGeom& g, int mode, const float* core, float* dst, const uint32_t* absmax, cudaStream_t st);

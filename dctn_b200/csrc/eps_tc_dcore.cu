@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(256) build_tables16_kernel(EpsGeom g, const fl
   float* xs = bt_smem;             // [NX][64]
   float* gs = xs + NX * CH;        // [O][64]
   float* wp = gs + O * CH;         // [64]
+  float* tlo = wp + CH;            // [BL][64]: second-half lo group, evaluated once and reused for every o
   const long long p0 = (long long)blockIdx.x * CH;
   for (int idx = threadIdx.x; idx < (NX + O) * CH; idx += blockDim.x) {
     const int i = idx & (CH - 1), r = idx >> 6;
@@ -138,6 +139,8 @@ __global__ void __launch_bounds__(256) build_tables16_kernel(EpsGeom g, const fl
     out[t * TS_ + i] = v;
   }
   for (int idx = threadIdx.x; idx < ENT * (TS_ - CH); idx += blockDim.x) out[(idx / (TS_ - CH)) * TS_ + CH + idx % (TS_ - CH)] = 0.f;
+  for (int idx = threadIdx.x; idx < g.BL * CH; idx += blockDim.x) tlo[idx] = 32768.f * group(g.m + g.b_nh, g.b_nl, idx >> 6, idx & (CH - 1));
+  __syncthreads();
   // B image: one item = (row, packed pair of patches)
   const int BLO = g.BL * O;
   uint32_t* img = bimg + (long long)blockIdx.x * ntile * 2 * NT * 32;
@@ -146,8 +149,9 @@ __global__ void __launch_bounds__(256) build_tables16_kernel(EpsGeom g, const fl
     float v0 = 0.f, v1 = 0.f;
     if (row < BLO) {
       const int e = row / O, o = row - e * O;
-      v0 = 32768.f * gs[o * CH + 2 * i2] * group(g.m + g.b_nh, g.b_nl, e, 2 * i2);
-      v1 = 32768.f * gs[o * CH + 2 * i2 + 1] * group(g.m + g.b_nh, g.b_nl, e, 2 * i2 + 1);
+      const float2 t2 = *(const float2*)(tlo + e * CH + 2 * i2), g2 = *(const float2*)(gs + o * CH + 2 * i2);
+      v0 = g2.x * t2.x;
+      v1 = g2.y * t2.y;
     }
     uint32_t hi, lo;
     tc::split_f16x2(v0, v1, hi, lo);
@@ -504,7 +508,7 @@ bool tc16_dcore_supported(const EpsGeom& g0) {
   if (g.P >= (1ll << 31) / (g.Q > g.O ? g.Q : g.O)) return false;   // 32-bit patch index math
   if (g.A < 64 || g.N < 64) return false;       // tiles would be mostly padding: the CUDA-core family is the better fit
   if (g.P < 4096) return false;                 // tiny reductions are launch-bound either way
-  if ((size_t)((g.n * g.Q + g.O) * CH + CH) * sizeof(float) > 200 * 1024) return false;   // table kernel staging
+  if ((size_t)((g.n * g.Q + g.O + g.BL) * CH + CH) * sizeof(float) > 200 * 1024) return false;   // table kernel staging
   return dcore16_smem(g, pick_nt(g)) <= SMEM_LIMIT;
 }
 
@@ -531,7 +535,7 @@ int tc16_backward_core(const EpsGeom& g0, const float* x, const float* gout, flo
   int* exps = (int*)(bimg + ((bimg_words(g, NT, ntile) + 63) & ~(size_t)63));
   int* emax = exps + ((g.P + 63) & ~63ll);
   a.tables = tables; a.bimg = (const float*)bimg;
-  const size_t bsm = (size_t)((g.n * g.Q + g.O) * CH + CH) * sizeof(float);
+  const size_t bsm = (size_t)((g.n * g.Q + g.O + g.BL) * CH + CH) * sizeof(float);
   if (bsm > 200 * 1024) return dctn_set_error(-2, "table kernel needs %zu bytes of shared memory", bsm);
   DCTN_CUDA_CHECK_RET(cudaMemsetAsync(emax, 0x80, sizeof(int), st));   // 0x80808080: below every possible E_p
   patch_exp_kernel<<<(unsigned)((g.P + 255) / 256), 256, 0, st>>>(g, x, gout, exps, emax);

@@ -37,7 +37,12 @@ constexpr int F_ASTAGES = 2;     // A stages in TMEM: 2 x (hi 32 + lo 32 columns
 constexpr int F_MAX_BSTAGES = 4;
 constexpr int F_MAX_BN = 192;    // main + small accumulators (2 * BN) + 128 columns of A <= 512
 constexpr int F_THREADS = 384;   // warp 0: bulk copies, warp 1: MMA, warp 2: TMEM alloc, warps 4-7: producers, warps 8-11: epilogue
-enum { FMODE_STORE = 0, FMODE_FWD = 1 };
+// FMODE_LOO: the input-gradient GEMM with the first stage of the leave-one-out contraction fused into the epilogue:
+// instead of the P x A matrix dKR1 it writes, per patch, W[p] = (Whi[EHE] | Wlo[ELR]),
+//   Whi[eh] = sum_el dKR1[eh*ELR + el] * TL1[el],   Wlo[el] = sum_eh dKR1[eh*ELR + el] * TH1[eh]
+// (TH1 / TL1: hi / lo group tables of the FIRST half).  A 16x smaller output (config 2, layer 2: 80 instead of 1024
+// floats per patch), and the separate pass that re-read dKR1 (1.28 ms) disappears.
+enum { FMODE_STORE = 0, FMODE_FWD = 1, FMODE_LOO = 2 };
 constexpr size_t F_SMEM_LIMIT = 227 * 1024;
 
 struct FastArgs {
@@ -86,7 +91,7 @@ __global__ void fast_pack_kernel(const float* __restrict__ core, float* __restri
         const int k = kc * FKS + c16 * 8 + u;
         if (k < Kdim) {
           long long idx;
-          if (mode == FMODE_STORE) {
+          if (mode != FMODE_FWD) {
             const int o = k / g.Bn, b = k - o * g.Bn;
             idx = (long long)c * g.N + (long long)b * g.O + o;
           } else {
@@ -133,10 +138,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
   unsigned char* stages = base;
   const int nHrows = a.nk * RUNS;                      // >= KHE; the tail rows are zero (K padding)
   float* tabH = (float*)(base + NB * STAGE_BYTES);     // [nHrows][128]
-  float* tabEH = tabH + nHrows * 128;                  // FMODE_FWD: [EHE][128]
-  float* outs = tabEH + (MODE == FMODE_FWD ? a.EHE * 128 : 0);   // FMODE_FWD: [O][128]
-  int* rowexp = (int*)(outs + (MODE == FMODE_FWD ? O * 128 : 0));  // [2][128]
-  uint64_t* bars = (uint64_t*)(rowexp + 256);
+  float* tabEH = tabH + nHrows * 128;                  // FMODE_FWD / FMODE_LOO: [EHE][128] hi-group table of the epilogue's half
+  float* outs = tabEH + (MODE != FMODE_STORE ? a.EHE * 128 : 0);   // FMODE_FWD: [O][128]
+  // exponents of the per-patch normalisation: [0] generated group, [1] all other factors, [2] the epilogue's lo group
+  int* rowexp = (int*)(outs + (MODE == FMODE_FWD ? O * 128 : 0));  // [3][128]
+  uint64_t* bars = (uint64_t*)(rowexp + 384);
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * F_MAX_BSTAGES + 2 * F_ASTAGES + 2);
   const uint32_t bar_fullB0 = tc::smem_u32(bars), bar_emptyB0 = bar_fullB0 + 8 * F_MAX_BSTAGES;
   const uint32_t bar_fullA0 = bar_emptyB0 + 8 * F_MAX_BSTAGES, bar_emptyA0 = bar_fullA0 + 8 * F_ASTAGES;
@@ -198,15 +204,17 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
   }
   __syncthreads();
   if (tid < 128) {
-    int ea = 0, eb = 0;
+    int ea = 0, eb = 0, el = 0;
     for (int j = 0; j < g.n; ++j) {
       const bool in_gen = (j >= a.jh0 && j < a.jh0 + a.cnth + a.cntl);
       if (in_gen) ea += fexp[j * 128 + tid];
       else eb += fexp[j * 128 + tid];
+      if (j >= a.ej0 + a.ecnth && j < a.ej0 + a.ecnth + a.ecntl) el += fexp[j * 128 + tid];
     }
     if (a.withG) ea += fexp[g.n * 128 + tid];
     rowexp[tid] = ea;
     rowexp[128 + tid] = eb;
+    rowexp[256 + tid] = el;
   }
   {
     // hi table: entry e (forward) or (o, e) (input gradient); carries the 2^15 of the generated row
@@ -221,10 +229,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
       }
       tabH[idx] = v;
     }
-    if (MODE == FMODE_FWD) {
+    if (MODE != FMODE_STORE)
       for (int idx = tid; idx < a.EHE * 128; idx += F_THREADS) tabEH[idx] = kr_entry(xs, Q, a.ej0, a.ecnth, idx >> 7, idx & 127);
+    if (MODE == FMODE_FWD)
       for (int idx = tid; idx < O * 128; idx += F_THREADS) outs[idx] = 0.f;
-    }
   }
   // lo-group values of this thread's patch: registers for the rest of the kernel
   tc::f32x2_t TL2[KLR / 2];
@@ -236,7 +244,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
       for (int j = 0; j < KLR; j += 2)
         TL2[j / 2] = tc::pack2(kr_entry(xs, Q, a.jh0 + a.cnth, a.cntl, j, pr), kr_entry(xs, Q, a.jh0 + a.cnth, a.cntl, j + 1, pr));
     }
-    if (MODE == FMODE_FWD && warp >= 8) {
+    if (MODE != FMODE_STORE && warp >= 8) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) EL[j] = (j < a.ELR) ? kr_entry(xs, Q, a.ej0 + a.ecnth, a.ecntl, j, pr) : 0.f;
     }
@@ -368,6 +376,17 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
     const float* eH = tabEH + pr;
     float s = 0.f;
     int cur_o = 0;
+    // FMODE_LOO: the epilogue tables come from the normalised x while W is defined with the raw x: Whi (a sum against the
+    // lo-group table) also undoes the lo group's exponents, Wlo the hi group's (rowexp[1] = first half = hi + lo group)
+    float hsc1 = 1.f, hsc2 = 1.f, lsc1 = 1.f, lsc2 = 1.f;
+    if (MODE == FMODE_LOO) {
+      const int kh = kexp + rowexp[256 + pr], kl = kexp + rowexp[128 + pr] - rowexp[256 + pr];
+      hsc1 = scalbnf(1.f, kh / 2); hsc2 = scalbnf(1.f, kh - kh / 2);
+      lsc1 = scalbnf(1.f, kl / 2); lsc2 = scalbnf(1.f, kl - kl / 2);
+    }
+    float WLO[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) WLO[j] = 0.f;
     long long dbg_epi = 0;
     for (int t = 0; t < a.ntiles; ++t) {
       tc::mbar_wait(bar_accfull, (uint32_t)(t & 1));
@@ -386,7 +405,54 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaf(w[i], 1.f / 2048.f, v[i]);
         }
-        if (MODE == FMODE_STORE) {
+        if (MODE == FMODE_LOO) {
+          // columns nb..nb+31 are a = eh*ELR + el: 32/ELR runs of one eh each
+          float* wrow = a.out + (long long)pl * a.ldc;
+          const int eh0 = nb / a.ELR;
+          const float* ehp = eH + eh0 * 128;
+          switch (a.ELR) {
+            case 16:
+#pragma unroll
+              for (int r = 0; r < 2; ++r) {
+                const float th = ehp[r * 128];
+                float whi = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { whi = fmaf(v[r * 16 + j], EL[j], whi); WLO[j] = fmaf(v[r * 16 + j], th, WLO[j]); }
+                if (pvalid) wrow[eh0 + r] = whi * hsc1 * hsc2;
+              }
+              break;
+            case 8:
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                const float th = ehp[r * 128];
+                float whi = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { whi = fmaf(v[r * 8 + j], EL[j], whi); WLO[j] = fmaf(v[r * 8 + j], th, WLO[j]); }
+                if (pvalid) wrow[eh0 + r] = whi * hsc1 * hsc2;
+              }
+              break;
+            case 4:
+#pragma unroll
+              for (int r = 0; r < 8; ++r) {
+                const float th = ehp[r * 128];
+                float whi = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { whi = fmaf(v[r * 4 + j], EL[j], whi); WLO[j] = fmaf(v[r * 4 + j], th, WLO[j]); }
+                if (pvalid) wrow[eh0 + r] = whi * hsc1 * hsc2;
+              }
+              break;
+            default:  // 2
+#pragma unroll
+              for (int r = 0; r < 16; ++r) {
+                const float th = ehp[r * 128];
+                const float whi = fmaf(v[r * 2], EL[0], v[r * 2 + 1] * EL[1]);
+                WLO[0] = fmaf(v[r * 2], th, WLO[0]);
+                WLO[1] = fmaf(v[r * 2 + 1], th, WLO[1]);
+                if (pvalid) wrow[eh0 + r] = whi * hsc1 * hsc2;
+              }
+              break;
+          }
+        } else if (MODE == FMODE_STORE) {
           if (pvalid) {
             float* crow = a.out + (long long)pl * a.ldc + nb;
 #pragma unroll
@@ -452,6 +518,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
       dbg_epi += TCF_CLK() - te0;
     }
     if (a.dbg && warp == 8 && lane == 0) a.dbg[(long long)blockIdx.x * 8 + 7] = dbg_epi;
+    if (MODE == FMODE_LOO && pvalid) {
+      float* wrow = a.out + (long long)pl * a.ldc + a.EHE;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < a.ELR) wrow[j] = WLO[j] * lsc1 * lsc2;
+    }
     if (MODE == FMODE_FWD) {
       outs[cur_o * 128 + pr] += s;
       if (pvalid) {
@@ -503,6 +575,11 @@ inline FastShape fast_shape(const EpsGeom& g, int mode) {
     s.jh0 = g.m; s.cntl = cl; s.cnth = cntB - cl; s.KLR = ipow_host(g.Q, cl); s.KHE = g.O * ipow_host(g.Q, s.cnth); s.withG = 1;
     s.Kdim = g.N; s.Ncols = g.A;
     if (g.A % 32 != 0) return s;
+    if (mode == FMODE_LOO) {   // epilogue groups of the first half
+      const int el = lo_count(g.Q, cntA);
+      if (el < 1) return s;
+      s.ej0 = 0; s.ecntl = el; s.ecnth = cntA - el; s.ELR = ipow_host(g.Q, el); s.EHE = ipow_host(g.Q, s.ecnth);
+    }
   }
   if (s.KLR < 2 || s.KLR > 16) return s;
   s.ok = 1;
@@ -512,7 +589,7 @@ inline FastShape fast_shape(const EpsGeom& g, int mode) {
 inline size_t fast_fixed_smem(const EpsGeom& g, const FastShape& s, int mode) {
   const size_t nk = (size_t)(s.Kdim + FKS - 1) / FKS;
   const size_t nH = nk * (FKS / s.KLR);
-  return 1024 + (nH + (mode == FMODE_FWD ? (size_t)s.EHE + g.O : 0)) * 128 * 4 + 256 * 4 +
+  return 1024 + (nH + (mode != FMODE_STORE ? (size_t)s.EHE : 0) + (mode == FMODE_FWD ? (size_t)g.O : 0)) * 128 * 4 + 384 * 4 +
          (2 * F_MAX_BSTAGES + 2 * F_ASTAGES + 2) * 8 + 16;
 }
 inline size_t fast_stage_bytes(int BN) { return 2 * (size_t)BN * 128; }
@@ -560,7 +637,14 @@ int launch_fast_klr(const FastArgs& a, int KLR, size_t smem, cudaStream_t st) {
 
 }  // namespace
 
-// mode: 0 = input-gradient GEMM (dKR1), 1 = forward
+// mode: 0 = input-gradient GEMM (dKR1), 1 = forward, 2 = input-gradient GEMM with the fused leave-one-out stage
+// (output W[np][ldc], ldc = tcfast_loo_width(g) = hi-group + lo-group entries of the first half)
+int tcfast_loo_groups(const EpsGeom& g, int* cnth, int* EH, int* cntl, int* EL) {
+  const FastShape s = fast_shape(g, FMODE_LOO);
+  if (!s.ok) return 0;
+  *cnth = s.ecnth; *EH = s.EHE; *cntl = s.ecntl; *EL = s.ELR;
+  return s.EHE + s.ELR;
+}
 bool tcfast_supported(const EpsGeom& g, int mode) {
   const FastShape s = fast_shape(g, mode);
   return s.ok && fast_bn(g, s, mode) != 0;
@@ -609,7 +693,8 @@ int tcfast_gemm(const EpsGeom& g, int mode, const float* x, const float* gout, c
     a.dbg = dbg_buf;
   }
   const size_t smem = fast_fixed_smem(g, s, mode) + a.bstages * fast_stage_bytes(BN);
-  int rc = (mode == FMODE_FWD) ? launch_fast_klr<FMODE_FWD>(a, s.KLR, smem, st) : launch_fast_klr<FMODE_STORE>(a, s.KLR, smem, st);
+  int rc = (mode == FMODE_FWD) ? launch_fast_klr<FMODE_FWD>(a, s.KLR, smem, st)
+         : (mode == FMODE_LOO) ? launch_fast_klr<FMODE_LOO>(a, s.KLR, smem, st) : launch_fast_klr<FMODE_STORE>(a, s.KLR, smem, st);
   if (a.dbg && rc == 0) {
     static long long host[4096 * 8];
     cudaStreamSynchronize(st);

@@ -819,6 +819,7 @@ size_t tcg_workspace_bytes(const EpsGeom& g, int kind) {
   if (kind == 2 || kind == 3) {
     const long long pc = dx_patch_chunk(g);
     size_t p1 = packed_floats(g, MODE_STORE, pick_bn(g, MODE_STORE)), f1 = tcfast_packed_floats(g, 0);
+    if (tcfast_packed_floats(g, 2) > f1) f1 = tcfast_packed_floats(g, 2);
     size_t f = (p1 > f1 ? p1 : f1) + 64 + (size_t)pc * ((size_t)g.A + g.Bn) + (size_t)g.P * g.n * g.Q;
     if (kind == 2) f += packed_floats(g, MODE_DKR2, pick_bn(g, MODE_DKR2));
     return WS_HEADER + f * 4 + 1024;
@@ -877,6 +878,114 @@ __global__ void __launch_bounds__(256) dkr2_from_saved_scalar_kernel(const float
     dkr2[i] = s;
   }
 }
+// Second half from the saved T, leave-one-out stage 1 fused: one warp per patch computes dKR2[b] = sum_o T[p][o*Bn + b] *
+// gout[p][o] (coalesced reads of the only large stream, P*N floats) into shared memory and reduces it against the two
+// group tables:  W2[p] = (Whi[BH] | Wlo[BL]),  Whi[eh] = sum_el dKR2[eh*BL + el] * TL[el],  Wlo[el] = sum_eh dKR2[..] * TH[eh].
+constexpr int LOO2_WARPS = 8;
+__global__ void __launch_bounds__(32 * LOO2_WARPS) loo2_from_saved_kernel(EpsGeom g, const float* __restrict__ x, const float* __restrict__ T,
+                                                                          const float* __restrict__ gout, float* __restrict__ W2,
+                                                                          long long p0, int np) {
+  extern __shared__ float l2_smem[];
+  const int Q = g.Q, O = g.O, Bn = g.Bn, BH = g.BH, BL = g.BL, nf = g.n - g.m;
+  const int BLS = BL | 1;                                   // padded row stride of the dKR2 matrix [BH][BL]
+  const int per_warp = BH * BLS + BH + BL + nf * Q + O;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* dk = l2_smem + warp * per_warp;
+  float* tH = dk + BH * BLS;
+  float* tL = tH + BH;
+  float* xs = tL + BL;
+  float* gs = xs + nf * Q;
+  for (long long pl = (long long)blockIdx.x * LOO2_WARPS + warp; pl < np; pl += (long long)gridDim.x * LOO2_WARPS) {
+    const long long p = p0 + pl;
+    const long long o0 = patch_origin(g, p);
+    for (int i = lane; i < nf * Q; i += 32) xs[i] = __ldg(&x[o0 + g.foff[g.m + i / Q] + i % Q]);
+    for (int o = lane; o < O; o += 32) gs[o] = __ldg(&gout[p * O + o]);
+    __syncwarp();
+    for (int e = lane; e < BH + BL; e += 32) {
+      const bool hi = e < BH;
+      int ee = hi ? e : e - BH;
+      const int j0 = hi ? 0 : g.b_nh, cnt = hi ? g.b_nh : g.b_nl;
+      float v = 1.f;
+      for (int u = cnt - 1; u >= 0; --u) {
+        const int d = ee % Q;
+        ee /= Q;
+        v *= xs[(j0 + u) * Q + d];
+      }
+      tH[e] = v;   // tL follows tH in memory
+    }
+    const float* trow = T + p * (long long)Bn * O;
+    for (int b = lane; b < Bn; b += 32) {
+      float sacc = 0.f;
+      for (int o = 0; o < O; ++o) sacc = fmaf(__ldcs(trow + (long long)o * Bn + b), gs[o], sacc);
+      dk[(b / BL) * BLS + b % BL] = sacc;
+    }
+    __syncwarp();
+    float* wrow = W2 + pl * (long long)(BH + BL);
+    for (int eh = lane; eh < BH; eh += 32) {
+      float sacc = 0.f;
+      for (int el = 0; el < BL; ++el) sacc = fmaf(dk[eh * BLS + el], tL[el], sacc);
+      wrow[eh] = sacc;
+    }
+    for (int el = lane; el < BL; el += 32) {
+      float sacc = 0.f;
+      for (int eh = 0; eh < BH; ++eh) sacc = fmaf(dk[eh * BLS + el], tH[eh], sacc);
+      wrow[BH + el] = sacc;
+    }
+    __syncwarp();
+  }
+}
+
+// Leave-one-out stage 2: from W[p] = (Whi[EH] | Wlo[EL]) of one half to d x_j for the factors j of that half,
+//   d x_j[q] (j at position t of a group with table entries e) = sum_{e: digit_t(e) = q} W[e] * prod_{t' != t} x_{j'}[digit_t'(e)]
+// one thread per (patch, factor, q); dxp[p][j][q]
+__global__ void __launch_bounds__(256) loo_groups_kernel(EpsGeom g, const float* __restrict__ x, const float* __restrict__ W, int ldw,
+                                                         long long p0, int np, int j0, int cnth, int EH, int cntl, int EL,
+                                                         float* __restrict__ dxp) {
+  const int Q = g.Q, nf = cnth + cntl;
+  const long long total = (long long)np * nf * Q;
+  for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += (long long)gridDim.x * blockDim.x) {
+    const long long pl = item / (nf * Q);
+    const int r = (int)(item - pl * nf * Q);
+    const int t = r / Q, q = r - t * Q;
+    const long long p = p0 + pl;
+    const long long o0 = patch_origin(g, p);
+    const bool in_hi = t < cnth;
+    const int cnt = in_hi ? cnth : cntl, tt = in_hi ? t : t - cnth, Eg = in_hi ? EH : EL;
+    const int jb = j0 + (in_hi ? 0 : cnth);
+    const float* w = W + pl * (long long)ldw + (in_hi ? 0 : EH);
+    int dstride = 1;
+    for (int u = 0; u < cnt - 1 - tt; ++u) dstride *= Q;
+    float sacc = 0.f;
+    const int others = Eg / Q;
+    for (int oe = 0; oe < others; ++oe) {
+      const int lo_part = oe % dstride, hi_part = oe / dstride;
+      const int e = (hi_part * Q + q) * dstride + lo_part;
+      float v = w[e];
+      int ee = e;
+      for (int u = cnt - 1; u >= 0; --u) {
+        const int d = ee % Q;
+        ee /= Q;
+        if (u != tt) v *= __ldg(&x[o0 + g.foff[jb + u] + d]);
+      }
+      sacc += v;
+    }
+    dxp[(p * g.n + j0 + t) * Q + q] = sacc;
+  }
+}
+
+inline int launch_loo_groups(const EpsGeom& g, const float* x, const float* W, int ldw, long long p0, int np, int j0, int cnth, int EH,
+                             int cntl, int EL, float* dxp, cudaStream_t st) {
+  const long long total = (long long)np * (cnth + cntl) * g.Q;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  loo_groups_kernel<<<blocks, 256, 0, st>>>(g, x, W, ldw, p0, np, j0, cnth, EH, cntl, EL, dxp);
+  dctn_count_launch();
+  DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  return 0;
+}
+inline size_t loo2_smem(const EpsGeom& g) {
+  return (size_t)LOO2_WARPS * (size_t)(g.BH * (g.BL | 1) + g.BH + g.BL + (g.n - g.m) * g.Q + g.O) * sizeof(float);
+}
 }  // namespace
 
 // kind 2: recompute T (two GEMMs); kind 3: T saved by the training forward (one GEMM + one streaming pass over T)
@@ -890,22 +999,44 @@ static int backward_input_impl(const EpsGeom& g, const float* x, const float* co
   const bool fast1 = use_fast(g, 0, passes);
   size_t pf1 = packed_floats(g, MODE_STORE, BN1);
   if (tcfast_packed_floats(g, 0) > pf1) pf1 = tcfast_packed_floats(g, 0);
+  if (tcfast_packed_floats(g, 2) > pf1) pf1 = tcfast_packed_floats(g, 2);
   float* packed2 = packed1 + ((pf1 + 63) & ~(size_t)63);
   float* dkr1 = packed2 + (tsaved ? 0 : ((packed_floats(g, MODE_DKR2, BN2) + 63) & ~(size_t)63));
   float* dkr2 = dkr1 + (size_t)pc * g.A;
   float* dxp = dkr2 + (size_t)pc * g.Bn;
   int rc;
   if ((rc = run_absmax(g, core, absmax, passes, st))) return rc;
-  if (fast1) rc = tcfast_pack(g, 0, core, packed1, absmax, st);
+  int c1h = 0, E1H = 0, c1l = 0, E1L = 0;
+  const int ldw1 = fast1 ? tcfast_loo_groups(g, &c1h, &E1H, &c1l, &E1L) : 0;
+  const bool fused1 = ldw1 > 0 && tcfast_supported(g, 2);
+  if (fast1) rc = tcfast_pack(g, fused1 ? 2 : 0, core, packed1, absmax, st);
   else rc = run_pack(g, MODE_STORE, BN1, core, packed1, passes, st, absmax);
   if (rc) return rc;
   if (!tsaved && (rc = run_pack(g, MODE_DKR2, BN2, core, packed2, passes, st, absmax))) return rc;
+  // leave-one-out stage 1 fused into the producers of dKR (register-table GEMM epilogue / the pass over the saved T):
+  // only W (hi-group + lo-group sums per patch) goes through memory instead of the P x A and P x Bn matrices
+  const bool fused2 = tsaved != nullptr && loo2_smem(g) <= 96 * 1024;
+  if (fused2) DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(loo2_from_saved_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)loo2_smem(g)));
   for (long long p0 = 0; p0 < g.P; p0 += pc) {
     const int np = (int)((g.P - p0 < pc) ? (g.P - p0) : pc);
-    if (fast1) rc = tcfast_gemm(g, 0, x, gout, packed1, absmax, p0, np, dkr1, g.A, nullptr, st);
-    else rc = run_gemm(g, MODE_STORE, BN1, x, gout, packed1, p0, np, dkr1, g.A, passes, st, absmax);
-    if (rc) return rc;
-    if ((rc = launch_loo<float>(g, x, dkr1, p0, np, 0, dxp, st))) return rc;
+    if (fused1) {
+      if ((rc = tcfast_gemm(g, 2, x, gout, packed1, absmax, p0, np, dkr1, ldw1, nullptr, st))) return rc;
+      if ((rc = launch_loo_groups(g, x, dkr1, ldw1, p0, np, 0, c1h, E1H, c1l, E1L, dxp, st))) return rc;
+    } else {
+      if (fast1) rc = tcfast_gemm(g, 0, x, gout, packed1, absmax, p0, np, dkr1, g.A, nullptr, st);
+      else rc = run_gemm(g, MODE_STORE, BN1, x, gout, packed1, p0, np, dkr1, g.A, passes, st, absmax);
+      if (rc) return rc;
+      if ((rc = launch_loo<float>(g, x, dkr1, p0, np, 0, dxp, st))) return rc;
+    }
+    if (fused2) {
+      int blocks = (np + LOO2_WARPS - 1) / LOO2_WARPS;
+      if (blocks > 148 * 8) blocks = 148 * 8;
+      loo2_from_saved_kernel<<<blocks, 32 * LOO2_WARPS, loo2_smem(g), st>>>(g, x, tsaved, gout, dkr2, p0, np);
+      dctn_count_launch();
+      DCTN_CUDA_CHECK_RET(cudaGetLastError());
+      if ((rc = launch_loo_groups(g, x, dkr2, g.BH + g.BL, p0, np, g.m, g.b_nh, g.BH, g.b_nl, g.BL, dxp, st))) return rc;
+      continue;
+    }
     if (tsaved) {
       const bool vec = (g.Bn & 3) == 0;
       const long long items = (long long)np * (vec ? g.Bn / 4 : g.Bn);
