@@ -273,33 +273,41 @@ def kernel_rooflines(model, specs, image_size, Q0, batch, dev, flush):
             res.append({"kernel": f"eps_{name}[L{li + 1} K={d['K']} Qin={d['Q']} Qout={d['O']}]", "ms": ms, "launches": launches,
                         "tflops": flops / ms / 1e9, "gbs": alg_bytes[name] / ms / 1e6, "flops": flops, "bytes": alg_bytes[name]})
         x = out.unsqueeze(0)
-    # "dominant kernel": the EPS kernels of one step are the tcgen05 GEMM (forward and, in wave-sized chunks, the input
-    # gradient) and the tcgen05 core-gradient kernel.  Take the slowest call that is ONE launch of its main kernel
-    # (forward / backward_core: pack or table pre-kernel + main kernel [+ partial reduce]); the chunked input gradient
-    # launches the same GEMM kernel 2 x ceil(P / 18944) times and is listed in all_kernels.
-    single = [r for r in res if r["launches"] <= 3]
-    top = max(single or res, key=lambda r: r["ms"])
+    # "dominant kernel": the slowest EPS call of the step.  Every call is one main tcgen05 kernel plus small helpers (core
+    # packing / table building / partial reduction / leave-one-out); `launches_per_call` counts them all.
+    top = max(res, key=lambda r: r["ms"])
     ai = top["flops"] / top["bytes"]
-    # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full`
-    # captures of the same kernels and shapes: profiles/ncu_traffic.json {kernel key: bytes}
-    traffic = None
+    # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) and tensor-pipe activity of the call's main
+    # kernel from the committed `ncu --set full` captures of the same kernels and shapes: profiles/ncu_traffic.json
+    traffic = ncu_tensor = ncu_what = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(top["kernel"])
-    if ai >= 128:  # above the TF32 tensor ridge (~128 flop/B): tensor-pipe bound
+            ent = json.load(f).get(top["kernel"])
+        if isinstance(ent, dict):
+            traffic, ncu_tensor, ncu_what = ent.get("traffic"), ent.get("tensor_pipe_active_pct"), ent.get("what")
+        elif ent is not None:
+            traffic = ent
+    f16 = os.environ.get("DCTN_B200_AUTO_ARITH", "") != "tf32" and os.environ.get("DCTN_B200_VARIANT", "auto") in ("auto", "tch3")
+    passes_cost = 3.0 if f16 else 6.0   # MMA passes per product, in units of one bf16/fp16 pass (a TF32 pass costs two)
+    if ai >= 128:  # above the tensor ridge: tensor-pipe bound
         roof = {"bound": "tensor", "achieved": top["tflops"], "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": top["tflops"] / peaks["bf16_tflops"], "traffic": traffic,
-                # what the tensor pipe actually executes: 3 TF32 MMA passes per product, TF32 peak = bf16 peak / 2
-                "tensor_pipe_frac": 3 * top["tflops"] / (peaks["bf16_tflops"] / 2)}
+                # what the tensor pipe actually executes: 3 MMA passes per product
+                "tensor_pipe_frac": passes_cost * top["tflops"] / peaks["bf16_tflops"],
+                "tensor_pipe_active_pct_ncu": ncu_tensor}
     else:
         roof = {"bound": "hbm", "achieved": top["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": top["gbs"] / peaks["hbm_gbs"], "traffic": traffic}
+    arith = ("split fp16 (tcgen05 kind::f16, v = hi + lo * 2^-11, 3 MMA passes hi*hi + hi*lo + lo*hi): the ceiling of `frac` against the "
+             "measured bf16 peak is 1/3" if f16 else
+             "split TF32 (tcgen05 kind::tf32, 3 MMA passes): the ceiling of `frac` against the measured bf16 peak is 1/6")
     roof.update({"kernel": top["kernel"], "ms_per_call": top["ms"], "launches_per_call": top["launches"], "peak_source": peaks["source"],
                  "algorithmic_flops_per_call": top["flops"], "algorithmic_bytes_per_call": top["bytes"],
-                 "note": "fp32-accurate path: tcgen05 kind::tf32 with 3 MMA passes per product (hi*hi + hi*lo + lo*hi), so the "
-                         "ceiling of `frac` against the measured bf16 peak is 1/6; `tensor_pipe_frac` counts the issued TF32 MMA "
-                         "flops against the TF32 peak (bf16 peak / 2); see DESIGN.md section 3.3",
+                 "note": "fp32-accurate path, " + arith + "; `tensor_pipe_frac` counts the issued MMA flops against that peak; "
+                         "`tensor_pipe_active_pct_ncu` is sm__pipe_tensor_cycles_active of the committed ncu capture of the same kernel "
+                         "and shape; see DESIGN.md sections 3 and 6",
+                 "traffic_note": ncu_what,
                  "all_kernels": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items() if k in ("kernel", "ms", "tflops", "gbs", "launches")} for r in res]})
     return roof
 

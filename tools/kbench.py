@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--variants", default="auto")
     ap.add_argument("--batch", type=int, default=512)
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--once", action="store_true", help="one call per (layer, kind, variant) and no timing: for ncu captures")
+    ap.add_argument("--train", action="store_true", help="forward keeps T (dctn_eps_forward_train), input gradient uses it")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     lib = _lib.lib()
@@ -42,20 +44,34 @@ def main():
         dx = torch.empty_like(x)
         P, D = B * Ho * Ho, Q ** n
         for variant in args.variants.split(","):
+            saved = ws3 = None
             plan = E._plan(1, K, Q, O, torch.float32, _lib.VARIANTS[variant])
             for kname in args.kinds.split(","):
                 kind = KINDS[kname]
                 ws = torch.empty(lib.dctn_eps_workspace_bytes(plan, B, H, H, kind), dtype=torch.uint8, device=dev)
                 st = torch.cuda.current_stream().cuda_stream
 
+                nsave = lib.dctn_eps_saved_bytes(plan, B, H, H) if args.train else 0
+                if nsave and saved is None:
+                    saved = torch.empty(nsave, dtype=torch.uint8, device=dev)
+                    ws3 = torch.empty(lib.dctn_eps_workspace_bytes(plan, B, H, H, 3), dtype=torch.uint8, device=dev)
+
                 def call():
                     if kind == 0:
+                        if nsave:
+                            return lib.dctn_eps_forward_train(plan, x.data_ptr(), core.data_ptr(), out.data_ptr(), saved.data_ptr(), nsave, B, H, H, ws.data_ptr(), ws.numel(), st)
                         return lib.dctn_eps_forward(plan, x.data_ptr(), core.data_ptr(), out.data_ptr(), B, H, H, ws.data_ptr(), ws.numel(), st)
                     if kind == 1:
                         return lib.dctn_eps_backward_core(plan, x.data_ptr(), gout.data_ptr(), dcore.data_ptr(), B, H, H, ws.data_ptr(), ws.numel(), st)
+                    if nsave:
+                        return lib.dctn_eps_backward_input_saved(plan, x.data_ptr(), core.data_ptr(), gout.data_ptr(), saved.data_ptr(), nsave, dx.data_ptr(), B, H, H, ws3.data_ptr(), ws3.numel(), st)
                     return lib.dctn_eps_backward_input(plan, x.data_ptr(), core.data_ptr(), gout.data_ptr(), dx.data_ptr(), B, H, H, ws.data_ptr(), ws.numel(), st)
 
                 rc = call()
+                if args.once:
+                    torch.cuda.synchronize()
+                    print(f"{lname} B={B} {kname} {variant}: rc={rc}", flush=True)
+                    continue
                 if rc != 0:
                     print(f"{lname} {kname} {variant}: unsupported ({_lib.last_error()[:80]})")
                     continue
@@ -67,7 +83,7 @@ def main():
                     s.record(); call(); e.record(); e.synchronize()
                     ts.append(s.elapsed_time(e))
                 ms = sum(ts) / len(ts)
-                flops = 2.0 * P * D * O * (2 if kname == "input" else 1)
+                flops = 2.0 * P * D * O * (2 if kname == "input" and not nsave else 1)
                 print(f"{lname} B={B} {kname:5s} {variant:5s}: {ms:8.3f} ms  {flops / ms / 1e9:8.2f} TFLOP/s (algorithmic)  ws={ws.numel() / 2**20:.0f} MiB", flush=True)
 
 
