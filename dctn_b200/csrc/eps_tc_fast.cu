@@ -42,7 +42,10 @@ constexpr int F_THREADS = 384;   // warp 0: bulk copies, warp 1: MMA, warp 2: TM
 //   Whi[eh] = sum_el dKR1[eh*ELR + el] * TL1[el],   Wlo[el] = sum_eh dKR1[eh*ELR + el] * TH1[eh]
 // (TH1 / TL1: hi / lo group tables of the FIRST half).  A 16x smaller output (config 2, layer 2: 80 instead of 1024
 // floats per patch), and the separate pass that re-read dKR1 (1.28 ms) disappears.
-enum { FMODE_STORE = 0, FMODE_FWD = 1, FMODE_LOO = 2 };
+// FMODE_LOOX: the second stage as well — the kernel writes d x_j (dxp[p][j][q]) for the first-half factors directly:
+// each finished Whi[eh] is scattered into per-thread accumulators in shared memory, the lo group is contracted from the
+// Wlo registers at the end; the first-half table comes from products of the (normalised) x kept in shared memory.
+enum { FMODE_STORE = 0, FMODE_FWD = 1, FMODE_LOO = 2, FMODE_LOOX = 3 };
 constexpr size_t F_SMEM_LIMIT = 227 * 1024;
 
 struct FastArgs {
@@ -139,7 +142,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
   const int nHrows = a.nk * RUNS;                      // >= KHE; the tail rows are zero (K padding)
   float* tabH = (float*)(base + NB * STAGE_BYTES);     // [nHrows][128]
   float* tabEH = tabH + nHrows * 128;                  // FMODE_FWD / FMODE_LOO: [EHE][128] hi-group table of the epilogue's half
-  float* outs = tabEH + (MODE != FMODE_STORE ? a.EHE * 128 : 0);   // FMODE_FWD: [O][128]
+  // FMODE_LOOX instead: normalised x of the first half, its exponents, hi-group accumulators, Wlo
+  const int mfirst = a.ecnth + a.ecntl;
+  float* xh = tabEH;                                   // [mfirst*Q][128]
+  int* fe = (int*)(xh + mfirst * Q * 128);             // [mfirst][128]
+  float* dxa = (float*)(fe + mfirst * 128);            // [ecnth*Q][128]
+  float* wlo = dxa + a.ecnth * Q * 128;                // [16][128]
+  const int eregion = (MODE == FMODE_LOOX) ? (mfirst * Q + mfirst + a.ecnth * Q + 16) * 128
+                    : (MODE != FMODE_STORE ? a.EHE * 128 : 0);
+  float* outs = tabEH + eregion;                       // FMODE_FWD: [O][128]
   // exponents of the per-patch normalisation: [0] generated group, [1] all other factors, [2] the epilogue's lo group
   int* rowexp = (int*)(outs + (MODE == FMODE_FWD ? O * 128 : 0));  // [3][128]
   uint64_t* bars = (uint64_t*)(rowexp + 384);
@@ -229,8 +240,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
       }
       tabH[idx] = v;
     }
-    if (MODE != FMODE_STORE)
+    if (MODE == FMODE_FWD || MODE == FMODE_LOO)
       for (int idx = tid; idx < a.EHE * 128; idx += F_THREADS) tabEH[idx] = kr_entry(xs, Q, a.ej0, a.ecnth, idx >> 7, idx & 127);
+    if (MODE == FMODE_LOOX) {
+      for (int idx = tid; idx < mfirst * Q * 128; idx += F_THREADS) xh[idx] = xs[a.ej0 * Q * 128 + idx];
+      for (int idx = tid; idx < mfirst * 128; idx += F_THREADS) fe[idx] = fexp[a.ej0 * 128 + idx];
+      for (int idx = tid; idx < a.ecnth * Q * 128; idx += F_THREADS) dxa[idx] = 0.f;
+    }
     if (MODE == FMODE_FWD)
       for (int idx = tid; idx < O * 128; idx += F_THREADS) outs[idx] = 0.f;
   }
@@ -405,7 +421,71 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaf(w[i], 1.f / 2048.f, v[i]);
         }
-        if (MODE == FMODE_LOO) {
+        if (MODE == FMODE_LOOX) {
+          // columns nb..nb+31 are a = eh*ELR + el: 32/ELR runs of one eh each; Q is a power of two here
+          const int eh0 = nb / a.ELR, lq = 31 - __clz(Q), nrun = 32 / a.ELR;
+          for (int r = 0; r < nrun; ++r) {
+            const int eh = eh0 + r;
+            int dg[4];
+            float xv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              dg[u] = 0; xv[u] = 1.f;
+              if (u < a.ecnth) {
+                dg[u] = (eh >> (lq * (a.ecnth - 1 - u))) & (Q - 1);
+                xv[u] = xh[((u * Q + dg[u]) << 7) + pr];
+              }
+            }
+            const float th = (xv[0] * xv[1]) * (xv[2] * xv[3]);
+            float whi = 0.f;
+            // the run's ELR columns sit at a compile-time offset only for a fixed ELR: select it
+            switch (a.ELR) {
+              case 16:
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr)
+                  if (rr == r) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { whi = fmaf(v[rr * 16 + j], EL[j], whi); WLO[j] = fmaf(v[rr * 16 + j], th, WLO[j]); }
+                  }
+                break;
+              case 8:
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr)
+                  if (rr == r) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { whi = fmaf(v[rr * 8 + j], EL[j], whi); WLO[j] = fmaf(v[rr * 8 + j], th, WLO[j]); }
+                  }
+                break;
+              case 4:
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr)
+                  if (rr == r) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { whi = fmaf(v[rr * 4 + j], EL[j], whi); WLO[j] = fmaf(v[rr * 4 + j], th, WLO[j]); }
+                  }
+                break;
+              default:
+#pragma unroll
+                for (int rr = 0; rr < 16; ++rr)
+                  if (rr == r) {
+                    whi = fmaf(v[rr * 2], EL[0], v[rr * 2 + 1] * EL[1]);
+                    WLO[0] = fmaf(v[rr * 2], th, WLO[0]);
+                    WLO[1] = fmaf(v[rr * 2 + 1], th, WLO[1]);
+                  }
+                break;
+            }
+            // scatter Whi[eh] into the hi-group factor gradients (leave-one-out products of the other hi factors)
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              if (t < a.ecnth) {
+                float prod = 1.f;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (u != t) prod *= xv[u];
+                dxa[((t * Q + dg[t]) << 7) + pr] += whi * prod;
+              }
+          }
+        } else if (MODE == FMODE_LOO) {
           // columns nb..nb+31 are a = eh*ELR + el: 32/ELR runs of one eh each
           float* wrow = a.out + (long long)pl * a.ldc;
           const int eh0 = nb / a.ELR;
@@ -518,6 +598,38 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
       dbg_epi += TCF_CLK() - te0;
     }
     if (a.dbg && warp == 8 && lane == 0) a.dbg[(long long)blockIdx.x * 8 + 7] = dbg_epi;
+    if (MODE == FMODE_LOOX) {
+      const int lq = 31 - __clz(Q);
+      const int kb = kexp + rowexp[128 + pr];            // accumulator exponent + all first-half factor exponents
+      float* drow = a.out + ((pt0 + pr) * g.n + a.ej0) * (long long)Q;
+      // hi group: accumulated on the fly
+      for (int t = 0; t < a.ecnth; ++t) {
+        const int k = kb - fe[t * 128 + pr];
+        const float s1 = scalbnf(1.f, k / 2), s2 = scalbnf(1.f, k - k / 2);
+        if (pvalid)
+          for (int q = 0; q < Q; ++q) drow[t * Q + q] = dxa[((t * Q + q) << 7) + pr] * s1 * s2;
+      }
+      // lo group: from the Wlo registers (through this thread's column of shared memory, for dynamic indexing)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) wlo[j * 128 + pr] = WLO[j];
+      for (int tl = 0; tl < a.ecntl; ++tl) {
+        const int u0 = a.ecnth + tl;
+        const int k = kb - fe[u0 * 128 + pr];
+        const float s1 = scalbnf(1.f, k / 2), s2 = scalbnf(1.f, k - k / 2);
+        const int sh = lq * (a.ecntl - 1 - tl);
+        for (int q = 0; q < Q; ++q) {
+          float acc = 0.f;
+          for (int el = 0; el < a.ELR; ++el) {
+            if (((el >> sh) & (Q - 1)) != q) continue;
+            float vv = wlo[el * 128 + pr];
+            for (int t2 = 0; t2 < a.ecntl; ++t2)
+              if (t2 != tl) vv *= xh[(((a.ecnth + t2) * Q + ((el >> (lq * (a.ecntl - 1 - t2))) & (Q - 1))) << 7) + pr];
+            acc += vv;
+          }
+          if (pvalid) drow[u0 * Q + q] = acc * s1 * s2;
+        }
+      }
+    }
     if (MODE == FMODE_LOO && pvalid) {
       float* wrow = a.out + (long long)pl * a.ldc + a.EHE;
 #pragma unroll
@@ -575,10 +687,11 @@ inline FastShape fast_shape(const EpsGeom& g, int mode) {
     s.jh0 = g.m; s.cntl = cl; s.cnth = cntB - cl; s.KLR = ipow_host(g.Q, cl); s.KHE = g.O * ipow_host(g.Q, s.cnth); s.withG = 1;
     s.Kdim = g.N; s.Ncols = g.A;
     if (g.A % 32 != 0) return s;
-    if (mode == FMODE_LOO) {   // epilogue groups of the first half
+    if (mode == FMODE_LOO || mode == FMODE_LOOX) {   // epilogue groups of the first half
       const int el = lo_count(g.Q, cntA);
       if (el < 1) return s;
       s.ej0 = 0; s.ecntl = el; s.ecnth = cntA - el; s.ELR = ipow_host(g.Q, el); s.EHE = ipow_host(g.Q, s.ecnth);
+      if (mode == FMODE_LOOX && s.ecnth > 4) return s;   // the on-the-fly scatter is unrolled for up to 4 hi factors
     }
   }
   if (s.KLR < 2 || s.KLR > 16) return s;
@@ -589,7 +702,9 @@ inline FastShape fast_shape(const EpsGeom& g, int mode) {
 inline size_t fast_fixed_smem(const EpsGeom& g, const FastShape& s, int mode) {
   const size_t nk = (size_t)(s.Kdim + FKS - 1) / FKS;
   const size_t nH = nk * (FKS / s.KLR);
-  return 1024 + (nH + (mode != FMODE_STORE ? (size_t)s.EHE : 0) + (mode == FMODE_FWD ? (size_t)g.O : 0)) * 128 * 4 + 384 * 4 +
+  const size_t mfirst = (size_t)s.ecnth + s.ecntl;
+  const size_t erows = (mode == FMODE_LOOX) ? mfirst * g.Q + mfirst + (size_t)s.ecnth * g.Q + 16 : (mode != FMODE_STORE ? (size_t)s.EHE : 0);
+  return 1024 + (nH + erows + (mode == FMODE_FWD ? (size_t)g.O : 0)) * 128 * 4 + 384 * 4 +
          (2 * F_MAX_BSTAGES + 2 * F_ASTAGES + 2) * 8 + 16;
 }
 inline size_t fast_stage_bytes(int BN) { return 2 * (size_t)BN * 128; }
@@ -694,7 +809,8 @@ int tcfast_gemm(const EpsGeom& g, int mode, const float* x, const float* gout, c
   }
   const size_t smem = fast_fixed_smem(g, s, mode) + a.bstages * fast_stage_bytes(BN);
   int rc = (mode == FMODE_FWD) ? launch_fast_klr<FMODE_FWD>(a, s.KLR, smem, st)
-         : (mode == FMODE_LOO) ? launch_fast_klr<FMODE_LOO>(a, s.KLR, smem, st) : launch_fast_klr<FMODE_STORE>(a, s.KLR, smem, st);
+         : (mode == FMODE_LOO) ? launch_fast_klr<FMODE_LOO>(a, s.KLR, smem, st)
+         : (mode == FMODE_LOOX) ? launch_fast_klr<FMODE_LOOX>(a, s.KLR, smem, st) : launch_fast_klr<FMODE_STORE>(a, s.KLR, smem, st);
   if (a.dbg && rc == 0) {
     static long long host[4096 * 8];
     cudaStreamSynchronize(st);

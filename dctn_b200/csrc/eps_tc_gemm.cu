@@ -820,6 +820,7 @@ size_t tcg_workspace_bytes(const EpsGeom& g, int kind) {
     const long long pc = dx_patch_chunk(g);
     size_t p1 = packed_floats(g, MODE_STORE, pick_bn(g, MODE_STORE)), f1 = tcfast_packed_floats(g, 0);
     if (tcfast_packed_floats(g, 2) > f1) f1 = tcfast_packed_floats(g, 2);
+    if (tcfast_packed_floats(g, 3) > f1) f1 = tcfast_packed_floats(g, 3);
     size_t f = (p1 > f1 ? p1 : f1) + 64 + (size_t)pc * ((size_t)g.A + g.Bn) + (size_t)g.P * g.n * g.Q;
     if (kind == 2) f += packed_floats(g, MODE_DKR2, pick_bn(g, MODE_DKR2));
     return WS_HEADER + f * 4 + 1024;
@@ -878,22 +879,27 @@ __global__ void __launch_bounds__(256) dkr2_from_saved_scalar_kernel(const float
     dkr2[i] = s;
   }
 }
-// Second half from the saved T, leave-one-out stage 1 fused: one warp per patch computes dKR2[b] = sum_o T[p][o*Bn + b] *
-// gout[p][o] (coalesced reads of the only large stream, P*N floats) into shared memory and reduces it against the two
-// group tables:  W2[p] = (Whi[BH] | Wlo[BL]),  Whi[eh] = sum_el dKR2[eh*BL + el] * TL[el],  Wlo[el] = sum_eh dKR2[..] * TH[eh].
+// Second half of the input gradient from the saved T, complete: one warp per patch
+//   dKR2[b]  = sum_o T[p][o*Bn + b] * gout[p][o]                 (coalesced 128-bit reads of the only large stream)
+//   Whi[eh]  = sum_el dKR2[eh*BL + el] * TL[el],   Wlo[el] = sum_eh dKR2[eh*BL + el] * TH[eh]       (stage 1)
+//   d x_j[q] = sum_{e: digit_t(e) = q} W[e] * prod_{t' != t} x_{j'}[digit_t'(e)]                       (stage 2)
+// everything after the read of T lives in the warp's slice of shared memory; dxp[p][j][q] for the factors j >= m.
 constexpr int LOO2_WARPS = 8;
+template <bool VEC>
 __global__ void __launch_bounds__(32 * LOO2_WARPS) loo2_from_saved_kernel(EpsGeom g, const float* __restrict__ x, const float* __restrict__ T,
-                                                                          const float* __restrict__ gout, float* __restrict__ W2,
+                                                                          const float* __restrict__ gout, float* __restrict__ dxp,
                                                                           long long p0, int np) {
   extern __shared__ float l2_smem[];
   const int Q = g.Q, O = g.O, Bn = g.Bn, BH = g.BH, BL = g.BL, nf = g.n - g.m;
   const int BLS = BL | 1;                                   // padded row stride of the dKR2 matrix [BH][BL]
-  const int per_warp = BH * BLS + BH + BL + nf * Q + O;
+  const int per_warp = BH * BLS + 2 * (BH + BL) + nf * Q + O;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* dk = l2_smem + warp * per_warp;
-  float* tH = dk + BH * BLS;
+  float* tH = dk + BH * BLS;   // [BH] then tL [BL]
   float* tL = tH + BH;
-  float* xs = tL + BL;
+  float* wH = tL + BL;         // [BH] then wL [BL]
+  float* wL = wH + BH;
+  float* xs = wL + BL;
   float* gs = xs + nf * Q;
   for (long long pl = (long long)blockIdx.x * LOO2_WARPS + warp; pl < np; pl += (long long)gridDim.x * LOO2_WARPS) {
     const long long p = p0 + pl;
@@ -911,25 +917,65 @@ __global__ void __launch_bounds__(32 * LOO2_WARPS) loo2_from_saved_kernel(EpsGeo
         ee /= Q;
         v *= xs[(j0 + u) * Q + d];
       }
-      tH[e] = v;   // tL follows tH in memory
+      tH[e] = v;   // tL follows tH
     }
     const float* trow = T + p * (long long)Bn * O;
-    for (int b = lane; b < Bn; b += 32) {
-      float sacc = 0.f;
-      for (int o = 0; o < O; ++o) sacc = fmaf(__ldcs(trow + (long long)o * Bn + b), gs[o], sacc);
-      dk[(b / BL) * BLS + b % BL] = sacc;
+    if (VEC) {     // Bn % 4 == 0 and BL % 4 == 0: four consecutive b stay in one row of the [BH][BL] matrix
+      const int b4n = Bn >> 2;
+      for (int b4 = lane; b4 < b4n; b4 += 32) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 6
+        for (int o = 0; o < O; ++o) {
+          const float4 v = __ldcs((const float4*)(trow + (long long)o * Bn) + b4);
+          const float gv = gs[o];
+          acc.x = fmaf(v.x, gv, acc.x); acc.y = fmaf(v.y, gv, acc.y); acc.z = fmaf(v.z, gv, acc.z); acc.w = fmaf(v.w, gv, acc.w);
+        }
+        const int b = b4 << 2;
+        float* d = dk + (b / BL) * BLS + b % BL;
+        d[0] = acc.x; d[1] = acc.y; d[2] = acc.z; d[3] = acc.w;
+      }
+    } else {
+      for (int b = lane; b < Bn; b += 32) {
+        float sacc = 0.f;
+        for (int o = 0; o < O; ++o) sacc = fmaf(__ldcs(trow + (long long)o * Bn + b), gs[o], sacc);
+        dk[(b / BL) * BLS + b % BL] = sacc;
+      }
     }
     __syncwarp();
-    float* wrow = W2 + pl * (long long)(BH + BL);
     for (int eh = lane; eh < BH; eh += 32) {
       float sacc = 0.f;
       for (int el = 0; el < BL; ++el) sacc = fmaf(dk[eh * BLS + el], tL[el], sacc);
-      wrow[eh] = sacc;
+      wH[eh] = sacc;
     }
     for (int el = lane; el < BL; el += 32) {
       float sacc = 0.f;
       for (int eh = 0; eh < BH; ++eh) sacc = fmaf(dk[eh * BLS + el], tH[eh], sacc);
-      wrow[BH + el] = sacc;
+      wL[el] = sacc;
+    }
+    __syncwarp();
+    for (int item = lane; item < nf * Q; item += 32) {
+      const int t = item / Q, q = item - t * Q;
+      const bool in_hi = t < g.b_nh;
+      const int cnt = in_hi ? g.b_nh : g.b_nl, tt = in_hi ? t : t - g.b_nh, Eg = in_hi ? BH : BL;
+      const float* w = in_hi ? wH : wL;
+      const float* xg = xs + (in_hi ? 0 : g.b_nh) * Q;
+      int dstride = 1;
+      for (int u = 0; u < cnt - 1 - tt; ++u) dstride *= Q;
+      float sacc = 0.f;
+      const int others = Eg / Q;
+      for (int oe = 0; oe < others; ++oe) {
+        const int lo_part = oe % dstride, hi_part = oe / dstride;
+        const int e = (hi_part * Q + q) * dstride + lo_part;
+        float v = w[e];
+        int ee = e;
+        for (int u = cnt - 1; u >= 0; --u) {
+          const int d = ee % Q;
+          ee /= Q;
+          if (u != tt) v *= xg[u * Q + d];
+        }
+        sacc += v;
+      }
+      dxp[(p * g.n + g.m + t) * Q + q] = sacc;
     }
     __syncwarp();
   }
@@ -984,7 +1030,7 @@ inline int launch_loo_groups(const EpsGeom& g, const float* x, const float* W, i
   return 0;
 }
 inline size_t loo2_smem(const EpsGeom& g) {
-  return (size_t)LOO2_WARPS * (size_t)(g.BH * (g.BL | 1) + g.BH + g.BL + (g.n - g.m) * g.Q + g.O) * sizeof(float);
+  return (size_t)LOO2_WARPS * (size_t)(g.BH * (g.BL | 1) + 2 * (g.BH + g.BL) + (g.n - g.m) * g.Q + g.O) * sizeof(float);
 }
 }  // namespace
 
@@ -1000,6 +1046,7 @@ static int backward_input_impl(const EpsGeom& g, const float* x, const float* co
   size_t pf1 = packed_floats(g, MODE_STORE, BN1);
   if (tcfast_packed_floats(g, 0) > pf1) pf1 = tcfast_packed_floats(g, 0);
   if (tcfast_packed_floats(g, 2) > pf1) pf1 = tcfast_packed_floats(g, 2);
+  if (tcfast_packed_floats(g, 3) > pf1) pf1 = tcfast_packed_floats(g, 3);
   float* packed2 = packed1 + ((pf1 + 63) & ~(size_t)63);
   float* dkr1 = packed2 + (tsaved ? 0 : ((packed_floats(g, MODE_DKR2, BN2) + 63) & ~(size_t)63));
   float* dkr2 = dkr1 + (size_t)pc * g.A;
@@ -1008,18 +1055,25 @@ static int backward_input_impl(const EpsGeom& g, const float* x, const float* co
   if ((rc = run_absmax(g, core, absmax, passes, st))) return rc;
   int c1h = 0, E1H = 0, c1l = 0, E1L = 0;
   const int ldw1 = fast1 ? tcfast_loo_groups(g, &c1h, &E1H, &c1l, &E1L) : 0;
-  const bool fused1 = ldw1 > 0 && tcfast_supported(g, 2);
-  if (fast1) rc = tcfast_pack(g, fused1 ? 2 : 0, core, packed1, absmax, st);
+  const bool fused1x = fast1 && tcfast_supported(g, 3);          // both leave-one-out stages inside the GEMM kernel
+  const bool fused1 = !fused1x && ldw1 > 0 && tcfast_supported(g, 2);   // first stage only: W through memory
+  if (fast1) rc = tcfast_pack(g, fused1x ? 3 : fused1 ? 2 : 0, core, packed1, absmax, st);
   else rc = run_pack(g, MODE_STORE, BN1, core, packed1, passes, st, absmax);
   if (rc) return rc;
   if (!tsaved && (rc = run_pack(g, MODE_DKR2, BN2, core, packed2, passes, st, absmax))) return rc;
   // leave-one-out stage 1 fused into the producers of dKR (register-table GEMM epilogue / the pass over the saved T):
   // only W (hi-group + lo-group sums per patch) goes through memory instead of the P x A and P x Bn matrices
   const bool fused2 = tsaved != nullptr && loo2_smem(g) <= 96 * 1024;
-  if (fused2) DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(loo2_from_saved_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)loo2_smem(g)));
+  const bool vec2 = (g.Bn & 3) == 0 && (g.BL & 3) == 0;
+  if (fused2) {
+    if (vec2) DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(loo2_from_saved_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)loo2_smem(g)));
+    else DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(loo2_from_saved_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)loo2_smem(g)));
+  }
   for (long long p0 = 0; p0 < g.P; p0 += pc) {
     const int np = (int)((g.P - p0 < pc) ? (g.P - p0) : pc);
-    if (fused1) {
+    if (fused1x) {
+      if ((rc = tcfast_gemm(g, 3, x, gout, packed1, absmax, p0, np, dxp, 0, nullptr, st))) return rc;
+    } else if (fused1) {
       if ((rc = tcfast_gemm(g, 2, x, gout, packed1, absmax, p0, np, dkr1, ldw1, nullptr, st))) return rc;
       if ((rc = launch_loo_groups(g, x, dkr1, ldw1, p0, np, 0, c1h, E1H, c1l, E1L, dxp, st))) return rc;
     } else {
@@ -1031,10 +1085,10 @@ static int backward_input_impl(const EpsGeom& g, const float* x, const float* co
     if (fused2) {
       int blocks = (np + LOO2_WARPS - 1) / LOO2_WARPS;
       if (blocks > 148 * 8) blocks = 148 * 8;
-      loo2_from_saved_kernel<<<blocks, 32 * LOO2_WARPS, loo2_smem(g), st>>>(g, x, tsaved, gout, dkr2, p0, np);
+      if (vec2) loo2_from_saved_kernel<true><<<blocks, 32 * LOO2_WARPS, loo2_smem(g), st>>>(g, x, tsaved, gout, dxp, p0, np);
+      else loo2_from_saved_kernel<false><<<blocks, 32 * LOO2_WARPS, loo2_smem(g), st>>>(g, x, tsaved, gout, dxp, p0, np);
       dctn_count_launch();
       DCTN_CUDA_CHECK_RET(cudaGetLastError());
-      if ((rc = launch_loo_groups(g, x, dkr2, g.BH + g.BL, p0, np, g.m, g.b_nh, g.BH, g.b_nl, g.BL, dxp, st))) return rc;
       continue;
     }
     if (tsaved) {
