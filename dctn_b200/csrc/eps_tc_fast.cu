@@ -128,6 +128,40 @@ __device__ __forceinline__ float kr_entry(const float* xs, int Q, int j0, int cn
   return v;
 }
 
+// FMODE_LOOX epilogue, one batch of 32 accumulator columns = 32/ELRC runs of ELRC columns (one hi-group entry eh each):
+//   Whi[eh] = sum_j v[run][j] * EL[j]  is scattered at once into the hi-group factor gradients dxa[t][digit_t(eh)] with the
+//   leave-one-out product of the other hi factors;  Wlo[j] += v[run][j] * TH[eh],  TH[eh] = product of all hi factors
+template <int ELRC>
+__device__ __forceinline__ void loox_batch(const float (&v)[32], const float (&EL)[16], float (&WLO)[16], const float* xh, float* dxa,
+                                           int eh0, int ecnth, int Q, int lq, int pr) {
+#pragma unroll
+  for (int r = 0; r < 32 / ELRC; ++r) {
+    const int eh = eh0 + r;
+    int dg[4];
+    float xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      dg[u] = 0; xv[u] = 1.f;
+      if (u < ecnth) {
+        dg[u] = (eh >> (lq * (ecnth - 1 - u))) & (Q - 1);
+        xv[u] = xh[((u * Q + dg[u]) << 7) + pr];
+      }
+    }
+    const float p01 = xv[0] * xv[1], p23 = xv[2] * xv[3];
+    const float th = p01 * p23;
+    float whi = 0.f;
+#pragma unroll
+    for (int j = 0; j < ELRC; ++j) {
+      whi = fmaf(v[r * ELRC + j], EL[j], whi);
+      WLO[j] = fmaf(v[r * ELRC + j], th, WLO[j]);
+    }
+    const float lo3[4] = {xv[1] * p23, xv[0] * p23, p01 * xv[3], p01 * xv[2]};   // leave-one-out products
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (t < ecnth) dxa[((t * Q + dg[t]) << 7) + pr] += whi * lo3[t];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ the GEMM
 template <int MODE, int KLR>
 __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid_constant__ FastArgs a) {
@@ -423,67 +457,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
         }
         if (MODE == FMODE_LOOX) {
           // columns nb..nb+31 are a = eh*ELR + el: 32/ELR runs of one eh each; Q is a power of two here
-          const int eh0 = nb / a.ELR, lq = 31 - __clz(Q), nrun = 32 / a.ELR;
-          for (int r = 0; r < nrun; ++r) {
-            const int eh = eh0 + r;
-            int dg[4];
-            float xv[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              dg[u] = 0; xv[u] = 1.f;
-              if (u < a.ecnth) {
-                dg[u] = (eh >> (lq * (a.ecnth - 1 - u))) & (Q - 1);
-                xv[u] = xh[((u * Q + dg[u]) << 7) + pr];
-              }
-            }
-            const float th = (xv[0] * xv[1]) * (xv[2] * xv[3]);
-            float whi = 0.f;
-            // the run's ELR columns sit at a compile-time offset only for a fixed ELR: select it
-            switch (a.ELR) {
-              case 16:
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr)
-                  if (rr == r) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) { whi = fmaf(v[rr * 16 + j], EL[j], whi); WLO[j] = fmaf(v[rr * 16 + j], th, WLO[j]); }
-                  }
-                break;
-              case 8:
-#pragma unroll
-                for (int rr = 0; rr < 4; ++rr)
-                  if (rr == r) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { whi = fmaf(v[rr * 8 + j], EL[j], whi); WLO[j] = fmaf(v[rr * 8 + j], th, WLO[j]); }
-                  }
-                break;
-              case 4:
-#pragma unroll
-                for (int rr = 0; rr < 8; ++rr)
-                  if (rr == r) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) { whi = fmaf(v[rr * 4 + j], EL[j], whi); WLO[j] = fmaf(v[rr * 4 + j], th, WLO[j]); }
-                  }
-                break;
-              default:
-#pragma unroll
-                for (int rr = 0; rr < 16; ++rr)
-                  if (rr == r) {
-                    whi = fmaf(v[rr * 2], EL[0], v[rr * 2 + 1] * EL[1]);
-                    WLO[0] = fmaf(v[rr * 2], th, WLO[0]);
-                    WLO[1] = fmaf(v[rr * 2 + 1], th, WLO[1]);
-                  }
-                break;
-            }
-            // scatter Whi[eh] into the hi-group factor gradients (leave-one-out products of the other hi factors)
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-              if (t < a.ecnth) {
-                float prod = 1.f;
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                  if (u != t) prod *= xv[u];
-                dxa[((t * Q + dg[t]) << 7) + pr] += whi * prod;
-              }
+          const int eh0 = nb / a.ELR, lq = 31 - __clz(Q);
+          switch (a.ELR) {
+            case 16: loox_batch<16>(v, EL, WLO, xh, dxa, eh0, a.ecnth, Q, lq, pr); break;
+            case 8: loox_batch<8>(v, EL, WLO, xh, dxa, eh0, a.ecnth, Q, lq, pr); break;
+            case 4: loox_batch<4>(v, EL, WLO, xh, dxa, eh0, a.ecnth, Q, lq, pr); break;
+            default: loox_batch<2>(v, EL, WLO, xh, dxa, eh0, a.ecnth, Q, lq, pr); break;
           }
         } else if (MODE == FMODE_LOO) {
           // columns nb..nb+31 are a = eh*ELR + el: 32/ELR runs of one eh each

@@ -921,18 +921,40 @@ __global__ void __launch_bounds__(32 * LOO2_WARPS) loo2_from_saved_kernel(EpsGeo
     }
     const float* trow = T + p * (long long)Bn * O;
     if (VEC) {     // Bn % 4 == 0 and BL % 4 == 0: four consecutive b stay in one row of the [BH][BL] matrix
+      // two chunks of 32 x float4 per pass with all their loads issued first: enough bytes in flight per warp to
+      // keep HBM busy (one warp has only this patch's 6 KB to read)
       const int b4n = Bn >> 2;
-      for (int b4 = lane; b4 < b4n; b4 += 32) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 6
-        for (int o = 0; o < O; ++o) {
-          const float4 v = __ldcs((const float4*)(trow + (long long)o * Bn) + b4);
-          const float gv = gs[o];
-          acc.x = fmaf(v.x, gv, acc.x); acc.y = fmaf(v.y, gv, acc.y); acc.z = fmaf(v.z, gv, acc.z); acc.w = fmaf(v.w, gv, acc.w);
+      for (int b4 = lane; b4 < b4n; b4 += 64) {
+        const bool two = b4 + 32 < b4n;
+        float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+        for (int o0 = 0; o0 < O; o0 += 4) {
+          float4 va[4], vb[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            va[k] = vb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (o0 + k < O) {
+              const float4* src = (const float4*)(trow + (long long)(o0 + k) * Bn) + b4;
+              va[k] = __ldcs(src);
+              if (two) vb[k] = __ldcs(src + 32);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float gv = (o0 + k < O) ? gs[o0 + k] : 0.f;
+            acc0.x = fmaf(va[k].x, gv, acc0.x); acc0.y = fmaf(va[k].y, gv, acc0.y); acc0.z = fmaf(va[k].z, gv, acc0.z); acc0.w = fmaf(va[k].w, gv, acc0.w);
+            acc1.x = fmaf(vb[k].x, gv, acc1.x); acc1.y = fmaf(vb[k].y, gv, acc1.y); acc1.z = fmaf(vb[k].z, gv, acc1.z); acc1.w = fmaf(vb[k].w, gv, acc1.w);
+          }
         }
-        const int b = b4 << 2;
-        float* d = dk + (b / BL) * BLS + b % BL;
-        d[0] = acc.x; d[1] = acc.y; d[2] = acc.z; d[3] = acc.w;
+        {
+          const int b = b4 << 2;
+          float* d = dk + (b / BL) * BLS + b % BL;
+          d[0] = acc0.x; d[1] = acc0.y; d[2] = acc0.z; d[3] = acc0.w;
+        }
+        if (two) {
+          const int b = (b4 + 32) << 2;
+          float* d = dk + (b / BL) * BLS + b % BL;
+          d[0] = acc1.x; d[1] = acc1.y; d[2] = acc1.z; d[3] = acc1.w;
+        }
       }
     } else {
       for (int b = lane; b < Bn; b += 32) {
