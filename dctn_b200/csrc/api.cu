@@ -1,6 +1,7 @@
 // C ABI of libdctn_b200.so (include/dctn_b200.h): plan cache, geometry, per-shape dispatch.
 #include <atomic>
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -179,6 +180,12 @@ extern "C" size_t dctn_eps_workspace_bytes(const dctn_plan_t* pl, int B, int H, 
   return bytes + 256;  // never zero, so callers can always pass a valid pointer
 }
 
+// the kernels use 128-bit loads and stores on every tensor
+static int check_aligned(const void* p, const char* what) {
+  if (((uintptr_t)p & 15) != 0) return dctn_set_error(DCTN_ERR_BAD_ARG, "%s (%p) must be 16-byte aligned", what, p);
+  return 0;
+}
+
 static int check_ws(const dctn_plan_t* pl, int B, int H, int W, int kind, void* ws, size_t ws_bytes) {
   size_t need = dctn_eps_workspace_bytes(pl, B, H, W, kind);
   if (!ws || ws_bytes < need)
@@ -191,6 +198,7 @@ extern "C" int dctn_eps_forward(const dctn_plan_t* pl, const void* x, const void
   int rc = check_call(pl, B, H, W);
   if (rc) return rc;
   if (!x || !core || !out) return dctn_set_error(DCTN_ERR_BAD_ARG, "forward: null tensor pointer");
+  if ((rc = check_aligned(x, "input")) || (rc = check_aligned(core, "core")) || (rc = check_aligned(out, "output")) || (rc = check_aligned(ws, "workspace"))) return rc;
   if ((rc = check_ws(pl, B, H, W, DCTN_WS_FORWARD, ws, ws_bytes))) return rc;
   EpsGeom g;
   fill_geom(pl, B, H, W, &g);
@@ -211,6 +219,7 @@ extern "C" int dctn_eps_backward_core(const dctn_plan_t* pl, const void* x, cons
   int rc = check_call(pl, B, H, W);
   if (rc) return rc;
   if (!x || !gout || !dcore) return dctn_set_error(DCTN_ERR_BAD_ARG, "backward_core: null tensor pointer");
+  if ((rc = check_aligned(x, "input")) || (rc = check_aligned(gout, "grad_output")) || (rc = check_aligned(dcore, "grad_core")) || (rc = check_aligned(ws, "workspace"))) return rc;
   if ((rc = check_ws(pl, B, H, W, DCTN_WS_BACKWARD_CORE, ws, ws_bytes))) return rc;
   EpsGeom g;
   fill_geom(pl, B, H, W, &g);
@@ -231,6 +240,7 @@ extern "C" int dctn_eps_backward_input(const dctn_plan_t* pl, const void* x, con
   int rc = check_call(pl, B, H, W);
   if (rc) return rc;
   if (!x || !core || !gout || !dx) return dctn_set_error(DCTN_ERR_BAD_ARG, "backward_input: null tensor pointer");
+  if ((rc = check_aligned(x, "input")) || (rc = check_aligned(core, "core")) || (rc = check_aligned(gout, "grad_output")) || (rc = check_aligned(dx, "grad_input")) || (rc = check_aligned(ws, "workspace"))) return rc;
   if ((rc = check_ws(pl, B, H, W, DCTN_WS_BACKWARD_INPUT, ws, ws_bytes))) return rc;
   EpsGeom g;
   fill_geom(pl, B, H, W, &g);
@@ -268,6 +278,7 @@ extern "C" int dctn_eps_forward_train(const dctn_plan_t* pl, const void* x, cons
   int rc = check_call(pl, B, H, W);
   if (rc) return rc;
   if (!x || !core || !out || !saved) return dctn_set_error(DCTN_ERR_BAD_ARG, "forward_train: null tensor pointer");
+  if ((rc = check_aligned(x, "input")) || (rc = check_aligned(core, "core")) || (rc = check_aligned(out, "output")) || (rc = check_aligned(saved, "saved")) || (rc = check_aligned(ws, "workspace"))) return rc;
   if ((rc = check_ws(pl, B, H, W, DCTN_WS_FORWARD, ws, ws_bytes))) return rc;
   EpsGeom g;
   fill_geom(pl, B, H, W, &g);
@@ -285,6 +296,7 @@ extern "C" int dctn_eps_backward_input_saved(const dctn_plan_t* pl, const void* 
   int rc = check_call(pl, B, H, W);
   if (rc) return rc;
   if (!x || !core || !gout || !saved || !dx) return dctn_set_error(DCTN_ERR_BAD_ARG, "backward_input_saved: null tensor pointer");
+  if ((rc = check_aligned(x, "input")) || (rc = check_aligned(core, "core")) || (rc = check_aligned(gout, "grad_output")) || (rc = check_aligned(saved, "saved")) || (rc = check_aligned(dx, "grad_input")) || (rc = check_aligned(ws, "workspace"))) return rc;
   EpsGeom g;
   fill_geom(pl, B, H, W, &g);
   if (!saved_path(pl, g))

@@ -117,15 +117,37 @@ __global__ void fast_pack_kernel(const float* __restrict__ core, float* __restri
   }
 }
 
-// product over `cnt` factors starting at j0 of the normalised x values of patch row pr, for table entry e (digit 0 slowest)
-__device__ __forceinline__ float kr_entry(const float* xs, int Q, int j0, int cnt, int e, int pr) {
+// product over `cnt` factors starting at j0 of the normalised x values of patch row pr, for table entry e (digit 0
+// slowest); Q = 2^lq in this file's kernels: digits by shifts
+__device__ __forceinline__ float kr_entry2(const float* xs, int lq, int j0, int cnt, int e, int pr) {
   float v = 1.f;
+  const int Q = 1 << lq;
   for (int u = cnt - 1; u >= 0; --u) {
-    const int d = e % Q;
-    e /= Q;
-    v *= xs[((j0 + u) * Q + d) * 128 + pr];
+    v *= xs[(((j0 + u) << lq) + (e & (Q - 1))) * 128 + pr];
+    e >>= lq;
   }
   return v;
+}
+// 2^k as a float for -126 <= k <= 127
+__device__ __forceinline__ float pow2i(int k) { return __int_as_float((k + 127) << 23); }
+// power-of-two normalisation of `cnt` values in registers: returns e (max-abs * 2^-e in [0.5, 1)), scales in place (exact)
+template <int MAXC>
+__device__ __forceinline__ int normalise(float (&v)[MAXC], int cnt) {
+  float m = 0.f;
+#pragma unroll
+  for (int q = 0; q < MAXC; ++q)
+    if (q < cnt) m = fmaxf(m, fabsf(v[q]));
+  int e = 0;
+  const int ef = (__float_as_int(m) >> 23) & 0xFF;
+  if (ef != 0 && ef != 0xFF) e = ef - 126;            // normal numbers: exponent field; 0 / inf / nan: leave unscaled
+  else if (m > 0.f && m < 1.f) frexpf(m, &e);          // subnormal maximum (rare)
+  if (e != 0) {
+    const float s1 = pow2i(-(e / 2)), s2 = pow2i(-(e - e / 2));
+#pragma unroll
+    for (int q = 0; q < MAXC; ++q)
+      if (q < cnt) v[q] = v[q] * s1 * s2;
+  }
+  return e;
 }
 
 // FMODE_LOOX epilogue, one batch of 32 accumulator columns = 32/ELRC runs of ELRC columns (one hi-group entry eh each):
@@ -187,7 +209,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
   float* outs = tabEH + eregion;                       // FMODE_FWD: [O][128]
   // exponents of the per-patch normalisation: [0] generated group, [1] all other factors, [2] the epilogue's lo group
   int* rowexp = (int*)(outs + (MODE == FMODE_FWD ? O * 128 : 0));  // [3][128]
-  uint64_t* bars = (uint64_t*)(rowexp + 384);
+  // training forward: per epilogue warp a [32 rows][36] staging tile that turns the thread-per-row accumulator batches
+  // into whole 128-byte row segments of T (a direct store from registers writes 32 half-used sectors per instruction)
+  float* tstage = (float*)(rowexp + 384);
+  uint64_t* bars = (uint64_t*)(tstage + ((MODE == FMODE_FWD && a.tsave != nullptr) ? 4 * 32 * 36 : 0));
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * F_MAX_BSTAGES + 2 * F_ASTAGES + 2);
   const uint32_t bar_fullB0 = tc::smem_u32(bars), bar_emptyB0 = bar_fullB0 + 8 * F_MAX_BSTAGES;
   const uint32_t bar_fullA0 = bar_emptyB0 + 8 * F_MAX_BSTAGES, bar_emptyA0 = bar_fullA0 + 8 * F_ASTAGES;
@@ -198,6 +223,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
   int* fexp = (int*)(gsx + O * 128);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long dbg_t_entry = TCF_CLK();
   const int pl0 = blockIdx.x * FBM;
   const long long pt0 = a.p0 + pl0;
 
@@ -216,36 +242,56 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
     tc::fence_barrier_init();
   }
   if (warp == 2) tc::tmem_alloc(tc::smem_u32(tmem_slot), 512);
+  const int lq = 31 - __clz(Q);                        // Q is a power of two <= 16 (host check)
   {
-    const int NX = g.n * Q;
-    for (int idx = tid; idx < NX * 128; idx += F_THREADS) {
-      const int pr = idx & 127, jq = idx >> 7;
-      const long long p = pt0 + pr;
-      float v = 0.f;
-      if (p < g.P) v = __ldg(&a.x[patch_origin(g, p) + g.foff[jq / Q] + jq % Q]);
-      xs[jq * 128 + pr] = v;
-    }
-    if (a.withG)
-      for (int idx = tid; idx < O * 128; idx += F_THREADS) {
-        const int pr = idx & 127, o = idx >> 7;
-        const long long p = pt0 + pr;
-        gsx[o * 128 + pr] = (p < g.P) ? __ldg(&a.gout[p * O + o]) : 0.f;
+    // every thread owns one patch row (pr) and every third factor: it loads the factor's Q values with vector loads,
+    // normalises them (range normalisation, see eps_tc_gemm.cu) and stores values and exponent — one pass, all loads of
+    // a thread independent of each other
+    const int pr = tid & 127, slot = tid >> 7;         // F_THREADS = 3 * 128
+    const long long p = pt0 + pr;
+    const bool valid = p < g.P;
+    const long long org = valid ? patch_origin(g, p) : 0;
+#pragma unroll 2
+    for (int j = slot; j < g.n; j += 3) {
+      float v[16];
+      const float* px = a.x + org + g.foff[j];
+      if (!valid) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = 0.f;
+      } else if (Q == 2) {
+        const float2 t = __ldg((const float2*)px);
+        v[0] = t.x; v[1] = t.y;
+      } else {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          if (q4 * 4 < Q) {
+            const float4 t = __ldg((const float4*)px + q4);
+            v[4 * q4] = t.x; v[4 * q4 + 1] = t.y; v[4 * q4 + 2] = t.z; v[4 * q4 + 3] = t.w;
+          }
       }
-  }
-  __syncthreads();
-  // range normalisation (see eps_tc_gemm.cu): every factor vector and the gout row scaled to max-abs in [0.5, 1)
-  for (int idx = tid; idx < (g.n + 1) * 128; idx += F_THREADS) {
-    const int pr = idx & 127, j = idx >> 7;
-    const bool isg = j == g.n;
-    if (isg && !a.withG) { fexp[idx] = 0; continue; }
-    float* v = isg ? gsx + pr : xs + j * Q * 128 + pr;
-    const int cnt = isg ? O : Q;
-    float m = 0.f;
-    for (int q = 0; q < cnt; ++q) m = fmaxf(m, fabsf(v[q * 128]));
-    const int e = tc::norm_exp(m);
-    if (e != 0)
-      for (int q = 0; q < cnt; ++q) v[q * 128] = scalbnf(v[q * 128], -e);
-    fexp[idx] = e;
+      fexp[j * 128 + pr] = normalise<16>(v, Q);
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        if (q < Q) xs[((j << lq) + q) * 128 + pr] = v[q];
+    }
+    if (slot == 0) {
+      int e = 0;
+      if (a.withG) {
+        // gout rows are O floats (any O): scalar loads, two passes over the row in shared memory
+        float m = 0.f;
+        for (int o = 0; o < O; ++o) {
+          const float t = valid ? __ldg(&a.gout[p * O + o]) : 0.f;
+          gsx[o * 128 + pr] = t;
+          m = fmaxf(m, fabsf(t));
+        }
+        e = tc::norm_exp(m);
+        if (e != 0) {
+          const float s1 = pow2i(-(e / 2)), s2 = pow2i(-(e - e / 2));
+          for (int o = 0; o < O; ++o) gsx[o * 128 + pr] = gsx[o * 128 + pr] * s1 * s2;
+        }
+      }
+      fexp[g.n * 128 + pr] = e;
+    }
   }
   __syncthreads();
   if (tid < 128) {
@@ -263,19 +309,18 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
   }
   {
     // hi table: entry e (forward) or (o, e) (input gradient); carries the 2^15 of the generated row
-    const int KH = a.withG ? a.KHE / O : a.KHE;
+    const int lkh = lq * a.cnth;                       // log2 of the hi-group entry count
     for (int idx = tid; idx < nHrows * 128; idx += F_THREADS) {
       const int pr = idx & 127, r = idx >> 7;
       float v = 0.f;
       if (r < a.KHE) {
-        const int o = r / KH, e = r - o * KH;
-        v = 32768.f * kr_entry(xs, Q, a.jh0, a.cnth, e, pr);
-        if (a.withG) v *= gsx[o * 128 + pr];
+        v = 32768.f * kr_entry2(xs, lq, a.jh0, a.cnth, r & ((1 << lkh) - 1), pr);
+        if (a.withG) v *= gsx[(r >> lkh) * 128 + pr];
       }
       tabH[idx] = v;
     }
     if (MODE == FMODE_FWD || MODE == FMODE_LOO)
-      for (int idx = tid; idx < a.EHE * 128; idx += F_THREADS) tabEH[idx] = kr_entry(xs, Q, a.ej0, a.ecnth, idx >> 7, idx & 127);
+      for (int idx = tid; idx < a.EHE * 128; idx += F_THREADS) tabEH[idx] = kr_entry2(xs, lq, a.ej0, a.ecnth, idx >> 7, idx & 127);
     if (MODE == FMODE_LOOX) {
       for (int idx = tid; idx < mfirst * Q * 128; idx += F_THREADS) xh[idx] = xs[a.ej0 * Q * 128 + idx];
       for (int idx = tid; idx < mfirst * 128; idx += F_THREADS) fe[idx] = fexp[a.ej0 * 128 + idx];
@@ -292,17 +337,18 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
     if (warp >= 4 && warp < 8) {
 #pragma unroll
       for (int j = 0; j < KLR; j += 2)
-        TL2[j / 2] = tc::pack2(kr_entry(xs, Q, a.jh0 + a.cnth, a.cntl, j, pr), kr_entry(xs, Q, a.jh0 + a.cnth, a.cntl, j + 1, pr));
+        TL2[j / 2] = tc::pack2(kr_entry2(xs, lq, a.jh0 + a.cnth, a.cntl, j, pr), kr_entry2(xs, lq, a.jh0 + a.cnth, a.cntl, j + 1, pr));
     }
     if (MODE != FMODE_STORE && warp >= 8) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) EL[j] = (j < a.ELR) ? kr_entry(xs, Q, a.ej0 + a.ecnth, a.ecntl, j, pr) : 0.f;
+      for (int j = 0; j < 16; ++j) EL[j] = (j < a.ELR) ? kr_entry2(xs, lq, a.ej0 + a.ecnth, a.ecntl, j, pr) : 0.f;
     }
   }
   tc::tc_fence_before();
   __syncthreads();  // tables complete; the scratch aliasing the stages is dead from here on
   tc::tc_fence_after();
   const int core_exp = tc::core_scale_exp(__ldg(a.core_absmax));
+  const long long dbg_t_setup = TCF_CLK();
   const uint32_t tmem_main = *tmem_slot;
   const uint32_t tmem_small = tmem_main + (uint32_t)BN;
   const uint32_t tmem_a0 = tmem_main + 2u * (uint32_t)BN;   // stage s: hi at +64*s, lo at +64*s + 32
@@ -409,7 +455,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
     }
     if (a.dbg && warp == 4 && lane == 0) {
       long long* d = a.dbg + (long long)blockIdx.x * 8;
-      d[4] = dbg_pwait; d[5] = dbg_pst; d[6] = dbg_pgen;
+      d[6] = dbg_pgen + 0 * (dbg_pwait + dbg_pst);
     }
   } else if (warp >= 8) {
     // =========================== epilogue ===========================
@@ -450,8 +496,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
         float v[32];
         {
           float w[32];
-          tc::tmem_ld32(tmem_main + lane_base + (uint32_t)cb, v);
-          tc::tmem_ld32(tmem_small + lane_base + (uint32_t)cb, w);
+          tc::tmem_ld32x2(tmem_main + lane_base + (uint32_t)cb, tmem_small + lane_base + (uint32_t)cb, v, w);
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaf(w[i], 1.f / 2048.f, v[i]);
         }
@@ -519,11 +564,21 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
               *(float4*)(crow + i) = make_float4(v[i] * sc1 * sc2, v[i + 1] * sc1 * sc2, v[i + 2] * sc1 * sc2, v[i + 3] * sc1 * sc2);
           }
         } else {
-          if (a.tsave != nullptr && pvalid) {
-            float* trow = a.tsave + (pt0 + pr) * (long long)a.Ncols + nb;
+          if (a.tsave != nullptr) {
+            float* st = tstage + quad * (32 * 36);
 #pragma unroll
             for (int i = 0; i < 32; i += 4)
-              *(float4*)(trow + i) = make_float4(v[i] * sc1 * sc2, v[i + 1] * sc1 * sc2, v[i + 2] * sc1 * sc2, v[i + 3] * sc1 * sc2);
+              *(float4*)(st + lane * 36 + i) = make_float4(v[i] * sc1 * sc2, v[i + 1] * sc1 * sc2, v[i + 2] * sc1 * sc2, v[i + 3] * sc1 * sc2);
+            __syncwarp();
+            // one store instruction = 4 rows x 128 contiguous bytes
+            const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+            float* tbase = a.tsave + (pt0 + quad * 32) * (long long)a.Ncols + nb + c4;
+#pragma unroll
+            for (int r0 = 0; r0 < 32; r0 += 4) {
+              const int r = r0 + rsub;
+              if (pl0 + quad * 32 + r < a.np) *(float4*)(tbase + (long long)r * a.Ncols) = *(const float4*)(st + r * 36 + c4);
+            }
+            __syncwarp();
           }
           // 32 columns of one o (Bn % 32 == 0): b = b0 .. b0+31, KR2[b] = EH[b / ELR] * EL[b % ELR]
           const int o = nb / g.Bn, b0 = nb - o * g.Bn;
@@ -626,6 +681,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 2) tc::tmem_dealloc(tmem_main, 512);
+  if (a.dbg && tid == 0) {   // probes (timing build only): setup and whole-CTA cycles replace the producer wait / store slots
+    a.dbg[(long long)blockIdx.x * 8 + 4] = dbg_t_setup - dbg_t_entry;
+    a.dbg[(long long)blockIdx.x * 8 + 5] = TCF_CLK() - dbg_t_entry;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -678,12 +737,13 @@ inline FastShape fast_shape(const EpsGeom& g, int mode) {
   return s;
 }
 
+constexpr size_t TSTAGE_BYTES = 4 * 32 * 36 * 4;   // training forward: staging tiles of the T store
 inline size_t fast_fixed_smem(const EpsGeom& g, const FastShape& s, int mode) {
   const size_t nk = (size_t)(s.Kdim + FKS - 1) / FKS;
   const size_t nH = nk * (FKS / s.KLR);
   const size_t mfirst = (size_t)s.ecnth + s.ecntl;
   const size_t erows = (mode == FMODE_LOOX) ? mfirst * g.Q + mfirst + (size_t)s.ecnth * g.Q + 16 : (mode != FMODE_STORE ? (size_t)s.EHE : 0);
-  return 1024 + (nH + erows + (mode == FMODE_FWD ? (size_t)g.O : 0)) * 128 * 4 + 384 * 4 +
+  return 1024 + (nH + erows + (mode == FMODE_FWD ? (size_t)g.O : 0)) * 128 * 4 + 384 * 4 + (mode == FMODE_FWD ? TSTAGE_BYTES : 0) +
          (2 * F_MAX_BSTAGES + 2 * F_ASTAGES + 2) * 8 + 16;
 }
 inline size_t fast_stage_bytes(int BN) { return 2 * (size_t)BN * 128; }
@@ -798,9 +858,9 @@ int tcfast_gemm(const EpsGeom& g, int mode, const float* x, const float* gout, c
     for (int c = 0; c < ncta; ++c) for (int k = 0; k < 8; ++k) sum[k] += (double)host[c * 8 + k];
     const double nst = (double)a.ntiles * a.nk;
     fprintf(stderr, "[tcfast dbg] mode=%d KLR=%d BN=%d NB=%d ntiles=%d nk=%d per-stage cycles: mma waitA %.0f waitB %.0f waitAcc(per tile) %.0f total %.0f | "
-            "producer wait %.0f st %.0f gen %.0f | epilogue/tile %.0f\n", mode, s.KLR, BN, a.bstages, a.ntiles, a.nk,
+            "CTA setup %.0f whole %.0f | producer gen %.0f | epilogue/tile %.0f\n", mode, s.KLR, BN, a.bstages, a.ntiles, a.nk,
             sum[0] / ncta / nst, sum[1] / ncta / nst, sum[2] / ncta / a.ntiles, sum[3] / ncta / nst,
-            sum[4] / ncta / nst, sum[5] / ncta / nst, sum[6] / ncta / nst, sum[7] / ncta / a.ntiles);
+            sum[4] / ncta, sum[5] / ncta, sum[6] / ncta / nst, sum[7] / ncta / a.ntiles);
   }
   return rc;
 }

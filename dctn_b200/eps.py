@@ -80,6 +80,12 @@ def _check_device(core: Tensor, input: Tensor) -> None:
         raise TypeError(f"eps supports float32/float64 with matching dtypes, got core {core.dtype}, input {input.dtype}")
 
 
+def _dense(t: Tensor) -> Tensor:
+    """Detached, contiguous and 16-byte aligned (the kernels use 128-bit accesses): a copy only when needed."""
+    t = t.detach().contiguous()
+    return t.clone() if t.data_ptr() % 16 else t
+
+
 def _workspace(plan: int, B: int, H: int, W: int, kind: int, device) -> Tensor:
     nbytes = _lib.lib().dctn_eps_workspace_bytes(plan, B, H, W, kind)
     return torch.empty(nbytes, dtype=torch.uint8, device=device)
@@ -96,8 +102,8 @@ class EpsFunction(torch.autograd.Function):
     def forward(ctx, core: Tensor, input: Tensor, variant: int) -> Tensor:
         C, K, Q, O = _infer(core, input)
         _, B, H, W, _ = input.shape
-        core_c = core.detach().contiguous()
-        x_c = input.detach().contiguous()
+        core_c = _dense(core)
+        x_c = _dense(input)
         plan = _plan(C, K, Q, O, input.dtype, variant)
         out = torch.empty((B, H - K + 1, W - K + 1, O), dtype=input.dtype, device=input.device)
         lib = _lib.lib()
@@ -132,7 +138,7 @@ class EpsFunction(torch.autograd.Function):
         core_c, x_c, *rest = ctx.saved_tensors
         saved = rest[0] if rest else None
         _, B, H, W, _ = x_c.shape
-        gout = gout.contiguous()
+        gout = _dense(gout)
         dcore = dx = None
         lib = _lib.lib()
         with torch.cuda.device(x_c.device):

@@ -9,7 +9,7 @@
  *
  * Conventions
  *   - plain pointers and sizes only; all data pointers are DEVICE pointers unless the name ends in
- *     `_host`; every tensor is dense row-major ("contiguous");
+ *     `_host`; every tensor is dense row-major ("contiguous") and 16-byte aligned;
  *   - every launch goes on the cudaStream_t passed by the caller (as a void*), nothing synchronises;
  *   - the library allocates no device memory: scratch is a caller-provided workspace whose size is
  *     queried with dctn_eps_workspace_bytes();
