@@ -212,7 +212,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
   // training forward: per epilogue warp a [32 rows][36] staging tile that turns the thread-per-row accumulator batches
   // into whole 128-byte row segments of T (a direct store from registers writes 32 half-used sectors per instruction)
   float* tstage = (float*)(rowexp + 384);
-  uint64_t* bars = (uint64_t*)(tstage + ((MODE == FMODE_FWD && a.tsave != nullptr) ? 4 * 32 * 36 : 0));
+  // lo-group tables of the generated operand (rows 0..15) and of the epilogue's half (rows 16..31): built by all threads
+  // with the other tables, copied into registers by the producer / epilogue threads once the setup barrier has passed
+  float* regtab = tstage + ((MODE == FMODE_FWD && a.tsave != nullptr) ? 4 * 32 * 36 : 0);   // [32][128]
+  uint64_t* bars = (uint64_t*)(regtab + 32 * 128);
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * F_MAX_BSTAGES + 2 * F_ASTAGES + 2);
   const uint32_t bar_fullB0 = tc::smem_u32(bars), bar_emptyB0 = bar_fullB0 + 8 * F_MAX_BSTAGES;
   const uint32_t bar_fullA0 = bar_emptyB0 + 8 * F_MAX_BSTAGES, bar_emptyA0 = bar_fullA0 + 8 * F_ASTAGES;
@@ -309,18 +312,48 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
   }
   {
     // hi table: entry e (forward) or (o, e) (input gradient); carries the 2^15 of the generated row
+    // four entries per pass, all loads before the stores (the compiler cannot prove that xs and the tables do not alias)
     const int lkh = lq * a.cnth;                       // log2 of the hi-group entry count
-    for (int idx = tid; idx < nHrows * 128; idx += F_THREADS) {
-      const int pr = idx & 127, r = idx >> 7;
-      float v = 0.f;
-      if (r < a.KHE) {
-        v = 32768.f * kr_entry2(xs, lq, a.jh0, a.cnth, r & ((1 << lkh) - 1), pr);
-        if (a.withG) v *= gsx[(r >> lkh) * 128 + pr];
+    for (int idx0 = tid; idx0 < nHrows * 128; idx0 += 4 * F_THREADS) {
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int idx = idx0 + k * F_THREADS, pr = idx & 127, r = idx >> 7;
+        v[k] = 0.f;
+        if (r < a.KHE) {
+          v[k] = 32768.f * kr_entry2(xs, lq, a.jh0, a.cnth, r & ((1 << lkh) - 1), pr);
+          if (a.withG) v[k] *= gsx[(r >> lkh) * 128 + pr];
+        }
       }
-      tabH[idx] = v;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (idx0 + k * F_THREADS < nHrows * 128) tabH[idx0 + k * F_THREADS] = v[k];
     }
     if (MODE == FMODE_FWD || MODE == FMODE_LOO)
-      for (int idx = tid; idx < a.EHE * 128; idx += F_THREADS) tabEH[idx] = kr_entry2(xs, lq, a.ej0, a.ecnth, idx >> 7, idx & 127);
+      for (int idx0 = tid; idx0 < a.EHE * 128; idx0 += 4 * F_THREADS) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int idx = idx0 + k * F_THREADS;
+          v[k] = (idx < a.EHE * 128) ? kr_entry2(xs, lq, a.ej0, a.ecnth, idx >> 7, idx & 127) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (idx0 + k * F_THREADS < a.EHE * 128) tabEH[idx0 + k * F_THREADS] = v[k];
+      }
+    for (int idx0 = tid; idx0 < 32 * 128; idx0 += 4 * F_THREADS) {
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int idx = idx0 + k * F_THREADS, pr = idx & 127, j = idx >> 7;
+        v[k] = 0.f;
+        if (j < KLR) v[k] = kr_entry2(xs, lq, a.jh0 + a.cnth, a.cntl, j, pr);
+        else if (MODE != FMODE_STORE && j >= 16 && j - 16 < a.ELR) v[k] = kr_entry2(xs, lq, a.ej0 + a.ecnth, a.ecntl, j - 16, pr);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (idx0 + k * F_THREADS < 32 * 128) regtab[idx0 + k * F_THREADS] = v[k];
+    }
     if (MODE == FMODE_LOOX) {
       for (int idx = tid; idx < mfirst * Q * 128; idx += F_THREADS) xh[idx] = xs[a.ej0 * Q * 128 + idx];
       for (int idx = tid; idx < mfirst * 128; idx += F_THREADS) fe[idx] = fexp[a.ej0 * 128 + idx];
@@ -329,6 +362,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
     if (MODE == FMODE_FWD)
       for (int idx = tid; idx < O * 128; idx += F_THREADS) outs[idx] = 0.f;
   }
+  tc::tc_fence_before();
+  __syncthreads();  // tables complete; the scratch aliasing the stages is dead from here on
+  tc::tc_fence_after();
   // lo-group values of this thread's patch: registers for the rest of the kernel
   tc::f32x2_t TL2[KLR / 2];
   float EL[16];
@@ -336,17 +372,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
     const int pr = (warp & 3) * 32 + lane;
     if (warp >= 4 && warp < 8) {
 #pragma unroll
-      for (int j = 0; j < KLR; j += 2)
-        TL2[j / 2] = tc::pack2(kr_entry2(xs, lq, a.jh0 + a.cnth, a.cntl, j, pr), kr_entry2(xs, lq, a.jh0 + a.cnth, a.cntl, j + 1, pr));
+      for (int j = 0; j < KLR; j += 2) TL2[j / 2] = tc::pack2(regtab[j * 128 + pr], regtab[(j + 1) * 128 + pr]);
     }
     if (MODE != FMODE_STORE && warp >= 8) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) EL[j] = (j < a.ELR) ? kr_entry2(xs, lq, a.ej0 + a.ecnth, a.ecntl, j, pr) : 0.f;
+      for (int j = 0; j < 16; ++j) EL[j] = regtab[(16 + j) * 128 + pr];
     }
   }
-  tc::tc_fence_before();
-  __syncthreads();  // tables complete; the scratch aliasing the stages is dead from here on
-  tc::tc_fence_after();
   const int core_exp = tc::core_scale_exp(__ldg(a.core_absmax));
   const long long dbg_t_setup = TCF_CLK();
   const uint32_t tmem_main = *tmem_slot;
@@ -743,7 +775,7 @@ inline size_t fast_fixed_smem(const EpsGeom& g, const FastShape& s, int mode) {
   const size_t nH = nk * (FKS / s.KLR);
   const size_t mfirst = (size_t)s.ecnth + s.ecntl;
   const size_t erows = (mode == FMODE_LOOX) ? mfirst * g.Q + mfirst + (size_t)s.ecnth * g.Q + 16 : (mode != FMODE_STORE ? (size_t)s.EHE : 0);
-  return 1024 + (nH + erows + (mode == FMODE_FWD ? (size_t)g.O : 0)) * 128 * 4 + 384 * 4 + (mode == FMODE_FWD ? TSTAGE_BYTES : 0) +
+  return 1024 + (nH + erows + 32 + (mode == FMODE_FWD ? (size_t)g.O : 0)) * 128 * 4 + 384 * 4 + (mode == FMODE_FWD ? TSTAGE_BYTES : 0) +
          (2 * F_MAX_BSTAGES + 2 * F_ASTAGES + 2) * 8 + 16;
 }
 inline size_t fast_stage_bytes(int BN) { return 2 * (size_t)BN * 128; }
