@@ -96,23 +96,31 @@ __global__ void __launch_bounds__(256) build_tables16_kernel(EpsGeom g, const fl
   float* wp = gs + O * CH;         // [64]
   float* tlo = wp + CH;            // [BL][64]: second-half lo group, evaluated once and reused for every o
   const long long p0 = (long long)blockIdx.x * CH;
-  for (int idx = threadIdx.x; idx < (NX + O) * CH; idx += blockDim.x) {
-    const int i = idx & (CH - 1), r = idx >> 6;
+  const int lq = (Q & (Q - 1)) == 0 ? 31 - __clz(Q) : -1;      // log2(Q) when Q is a power of two: digits by shifts
+  {
+    // a thread owns one patch (i) and every fourth factor / gout row: one patch-origin computation, the Q loads of a
+    // factor issued together, normalisation (exact power-of-two scale, see the header) in the same pass
+    const int i = threadIdx.x & (CH - 1), slot = threadIdx.x >> 6;   // 256 threads = 4 x 64
     const long long p = p0 + i;
-    float v = 0.f;
-    if (p < g.P) v = (r < NX) ? __ldg(&x[patch_origin(g, p) + g.foff[r / Q] + r % Q]) : __ldg(&gout[p * O + (r - NX)]);
-    xs[idx] = v;
-  }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < (g.n + 1) * CH; idx += blockDim.x) {
-    const int i = idx & (CH - 1), j = idx >> 6;
-    float* v = (j < g.n) ? xs + j * Q * CH + i : gs + i;
-    const int cnt = (j < g.n) ? Q : O;
-    float m = 0.f;
-    for (int q = 0; q < cnt; ++q) m = fmaxf(m, fabsf(v[q * CH]));
-    const int e = tc::norm_exp(m);
-    if (e != 0)
-      for (int q = 0; q < cnt; ++q) v[q * CH] = scalbnf(v[q * CH], -e);
+    const bool valid = p < g.P;
+    const long long org = valid ? patch_origin(g, p) : 0;
+    for (int j = slot; j <= g.n; j += 4) {
+      const bool isg = j == g.n;
+      const int cnt = isg ? O : Q;
+      const float* src = isg ? gout + p * O : x + org + g.foff[isg ? 0 : j];
+      float* dst = isg ? gs + i : xs + j * Q * CH + i;
+      float m = 0.f;
+      for (int q = 0; q < cnt; ++q) {
+        const float v = valid ? __ldg(src + q) : 0.f;
+        dst[q * CH] = v;
+        m = fmaxf(m, fabsf(v));
+      }
+      const int e = tc::norm_exp(m);
+      if (e != 0) {
+        const float s1 = __int_as_float((127 - e / 2) << 23), s2 = __int_as_float((127 - (e - e / 2)) << 23);
+        for (int q = 0; q < cnt; ++q) dst[q * CH] = dst[q * CH] * s1 * s2;
+      }
+    }
   }
   if (threadIdx.x < CH) {
     const long long p = p0 + threadIdx.x;
@@ -122,8 +130,9 @@ __global__ void __launch_bounds__(256) build_tables16_kernel(EpsGeom g, const fl
   auto group = [&](int j0, int cnt, int e, int i) -> float {
     float v = 1.f;
     for (int u = cnt - 1; u >= 0; --u) {
-      const int d = e % Q;
-      e /= Q;
+      int d;
+      if (lq >= 0) { d = e & (Q - 1); e >>= lq; }
+      else { d = e % Q; e /= Q; }
       v *= xs[((j0 + u) * Q + d) * CH + i];
     }
     return v;
