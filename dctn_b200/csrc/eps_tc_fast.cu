@@ -33,9 +33,9 @@ namespace {
 
 constexpr int FBM = 128;
 constexpr int FKS = 64;          // K values per stage (one 128-byte row of fp16)
-constexpr int F_ASTAGES = 2;     // A stages in TMEM: 2 x (hi 32 + lo 32 columns)
+constexpr int F_ASTAGES = 3;     // at most: A stages in TMEM of (hi 32 + lo 32 columns); 3 when BN <= 160, else 2
 constexpr int F_MAX_BSTAGES = 4;
-constexpr int F_MAX_BN = 192;    // main + small accumulators (2 * BN) + 128 columns of A <= 512
+constexpr int F_MAX_BN = 192;    // main + small accumulators (2 * BN) + 128 or 192 columns of A <= 512
 constexpr int F_THREADS = 384;   // warp 0: bulk copies, warp 1: MMA, warp 2: TMEM alloc, warps 4-7: producers, warps 8-11: epilogue
 // FMODE_LOO: the input-gradient GEMM with the first stage of the leave-one-out contraction fused into the epilogue:
 // instead of the P x A matrix dKR1 it writes, per patch, W[p] = (Whi[EHE] | Wlo[ELR]),
@@ -385,6 +385,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
   const uint32_t tmem_small = tmem_main + (uint32_t)BN;
   const uint32_t tmem_a0 = tmem_main + 2u * (uint32_t)BN;   // stage s: hi at +64*s, lo at +64*s + 32
   const int total_it = a.ntiles * a.nk;
+  const int NA = (2 * BN + 64 * F_ASTAGES <= 512) ? F_ASTAGES : 2;   // A stages that fit beside the accumulators
 
   if (warp == 0) {
     // =========================== bulk-copy issuer (B operand) ===========================
@@ -440,7 +441,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
           if (kc == a.nk - 1) tc::umma_commit(bar_accfull);
         }
         __syncwarp();
-        if (++sa == F_ASTAGES) { sa = 0; pha ^= 1; }
+        if (++sa == NA) { sa = 0; pha ^= 1; }
         if (++sb_ == NB) { sb_ = 0; phb ^= 1; }
       }
     }
@@ -482,7 +483,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
         if (lane == 0) tc::mbar_arrive(bar_fullA0 + 8 * sa);
         long long t2 = TCF_CLK();
         dbg_pwait += t1 - t0; dbg_pst += t2 - t1; dbg_pgen += t0 - tprev; tprev = t2;
-        if (++sa == F_ASTAGES) { sa = 0; phe ^= 1; }
+        if (++sa == NA) { sa = 0; phe ^= 1; }
       }
     }
     if (a.dbg && warp == 4 && lane == 0) {
