@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 from dctn_b200 import _lib  # noqa: E402
-from dctn_b200.eps import eps, plan_description  # noqa: E402
+from dctn_b200.eps import eps, eps_from_pixels, plan_description  # noqa: E402
 
 
 def peaks():
@@ -90,6 +90,20 @@ def main():
                            fwd_frac_hbm=fbytes / t_f / 1e6 / hbm, fwd_frac_bf16=flops / t_f / 1e9 / bf16,
                            imgs_per_s_fwdbwd=B / t_fb * 1e3, patches_per_s_fwdbwd=P / t_fb * 1e3,
                            plan=plan_description(core, x))
+                if K == 2 and Q == 2:
+                    # feature map fused into the forward (raw pixels in): 1 float per pixel instead of 2 crosses HBM
+                    u = torch.rand(B, 28, 28, device=dev)
+
+                    def fwd_pix():
+                        with torch.no_grad():
+                            eps_from_pixels(core, u, 1.45646)
+
+                    t_p = timeit(fwd_pix, flush, args.iters)
+                    pbytes = 4.0 * (u.numel() + out.numel() + core.numel())
+                    row.update(pixels_fwd_ms=t_p, pixels_fwd_gbs=pbytes / t_p / 1e6, pixels_fwd_frac_hbm=pbytes / t_p / 1e6 / hbm,
+                               pixels_fwd_gbs_as_featurised=fbytes / t_p / 1e6)
+                    print(f"K={K} Q={Q} O={O} B={B}: fwd from raw pixels {t_p:8.3f} ms ({row['pixels_fwd_gbs']:7.1f} GB/s of its own "
+                          f"{pbytes / 1e6:.1f} MB; {fbytes / t_p / 1e6:7.1f} GB/s counted on the featurised input)", flush=True)
                 rows.append(row)
                 print(f"K={K} Q={Q} O={O} B={B}: fwd {t_f:8.3f} ms ({row['fwd_tflops']:7.2f} TF/s, {row['fwd_gbs']:7.1f} GB/s, "
                       f"{row['bound']}-bound)  fwd+bwd {t_fb:8.3f} ms ({row['fwdbwd_tflops']:7.2f} TF/s)", flush=True)

@@ -258,6 +258,23 @@ extern "C" int dctn_eps_backward_input(const dctn_plan_t* pl, const void* x, con
              : ffma_backward_input<double>(g, (const double*)x, (const double*)core, (const double*)gout, (double*)dx, ws, st);
 }
 
+// ------------------------------------------------------------------------------------------------ forward from raw pixels
+extern "C" int dctn_eps_forward_from_pixels(const dctn_plan_t* pl, const void* pixels, double scale, const void* core, void* out,
+                                            int B, int H, int W, void* stream) {
+  int rc = check_call(pl, B, H, W);
+  if (rc) return rc;
+  if (!pixels || !core || !out) return dctn_set_error(DCTN_ERR_BAD_ARG, "forward_from_pixels: null tensor pointer");
+  if ((rc = check_aligned(pixels, "pixels")) || (rc = check_aligned(core, "core")) || (rc = check_aligned(out, "output"))) return rc;
+  EpsGeom g;
+  fill_geom(pl, B, H, W, &g);
+  if (!direct_pixels_supported(g, pl->dtype))
+    return dctn_set_error(DCTN_ERR_UNSUPPORTED, "forward_from_pixels: the fused feature map exists for K=2, C=1, Q_in=2 layers only (%s)", pl->desc.c_str());
+  cudaStream_t st = (cudaStream_t)stream;
+  return pl->dtype == DCTN_F32
+             ? direct_forward_pixels<float>(g, (const float*)pixels, (float)scale, (const float*)core, (float*)out, st)
+             : direct_forward_pixels<double>(g, (const double*)pixels, scale, (const double*)core, (double*)out, st);
+}
+
 // ------------------------------------------------------------------------------------------------ training forward
 // Only the tcgen05 GEMM family has an intermediate worth keeping (its forward and the second half of its input
 // gradient are the same GEMM); every other family reports 0 and the caller uses the plain entry points.

@@ -157,9 +157,12 @@ __global__ void __launch_bounds__(DTHREADS) direct_fwd_kernel(EpsGeom g, const T
 //     Khatri-Rao half of output row r and the second half of output row r - 1: computed once, used twice;
 //   * out[r][o] = sum_a pp[r][a] * (sum_b pp[r+1][b] * core[a][b][o]), core broadcast from shared memory, each
 //     128-bit shared load feeding 2 * RH FMAs per lane.
-template <typename T, int Q, int OT>   // OT: compile-time Q_out (2..8), or 0 = runtime (any Q_out, pairs per pass)
+// PIX (Q = 2 only): x is the raw pixel image (B, H, W) and the feature map of the reference's data loader,
+// phi(u) = scale * (sin^2(pi u / 2), cos^2(pi u / 2))  (dctn/dataset_loading.py:33-36), is evaluated on load: one float
+// per pixel crosses HBM instead of two (dctn_eps_forward_from_pixels).
+template <typename T, int Q, int OT, bool PIX = false>   // OT: compile-time Q_out (2..8), or 0 = runtime (any Q_out, pairs per pass)
 __global__ void __launch_bounds__(DTHREADS) direct_k2_kernel(EpsGeom g, const T* __restrict__ x, const T* __restrict__ core,
-                                                             T* __restrict__ out) {
+                                                             T* __restrict__ out, T phi_scale) {
   constexpr int RH = 4;
   constexpr int A = Q * Q;                          // = Bn
   constexpr int V = 16 / sizeof(T);
@@ -185,12 +188,18 @@ __global__ void __launch_bounds__(DTHREADS) direct_k2_kernel(EpsGeom g, const T*
     const unsigned h0 = hb * RH, wcol = tw * 31 + lane;  // input (and output) column of this lane
     // (1) this lane's pixel column, RH + 1 rows; out-of-range lanes/rows re-read a valid pixel (value never stored)
     const unsigned wc = wcol < (unsigned)g.W ? wcol : 0u;
-    const T* px = x + ((b * (unsigned)g.H + h0) * (unsigned)g.W + wc) * Q;
+    const T* px = x + ((b * (unsigned)g.H + h0) * (unsigned)g.W + wc) * (PIX ? 1 : Q);
     T xv[RH + 1][Q];
 #pragma unroll
     for (int r = 0; r <= RH; ++r) {
-      const T* pr = px + ((h0 + r < (unsigned)g.H) ? r * xrow : 0u);
-      if constexpr (Q % 4 == 0 && sizeof(T) == 4) {
+      const T* pr = px + ((h0 + r < (unsigned)g.H) ? r * (PIX ? (unsigned)g.W : xrow) : 0u);
+      if constexpr (PIX) {
+        const T u = __ldg(pr) * T(0.5);
+        T sn, cs2;
+        if constexpr (sizeof(T) == 4) sincospif(u, &sn, &cs2); else sincospi(u, &sn, &cs2);
+        xv[r][0] = phi_scale * sn * sn;
+        xv[r][Q - 1] = phi_scale * cs2 * cs2;
+      } else if constexpr (Q % 4 == 0 && sizeof(T) == 4) {
 #pragma unroll
         for (int q = 0; q < Q; q += 4) {
           const float4 v = __ldg(reinterpret_cast<const float4*>(pr + q));
@@ -282,19 +291,19 @@ __global__ void __launch_bounds__(DTHREADS) direct_k2_kernel(EpsGeom g, const T*
   }
 }
 
-template <typename T, int Q, int OT>
-int launch_direct_k2(const EpsGeom& g, const T* x, const T* core, T* out, cudaStream_t st) {
+template <typename T, int Q, int OT, bool PIX = false>
+int launch_direct_k2(const EpsGeom& g, const T* x, const T* core, T* out, cudaStream_t st, T phi_scale = T(0)) {
   constexpr int A = Q * Q;
   constexpr int V = 16 / sizeof(T);
   constexpr int BNP = (A + V - 1) / V * V;
   const size_t smem = (size_t)g.O * A * BNP * sizeof(T);
-  auto k = direct_k2_kernel<T, Q, OT>;
+  auto k = direct_k2_kernel<T, Q, OT, PIX>;
   DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long ntask = (long long)g.B * ((g.Ho + 3) / 4) * ((g.Wo + 30) / 31);
   long long blocks = (ntask + DTHREADS / 32 - 1) / (DTHREADS / 32);
   const long long cap = 148ll * 16;
   if (blocks > cap) blocks = cap;
-  k<<<(unsigned)blocks, DTHREADS, smem, st>>>(g, x, core, out);
+  k<<<(unsigned)blocks, DTHREADS, smem, st>>>(g, x, core, out, phi_scale);
   dctn_count_launch();
   DCTN_CUDA_CHECK_RET(cudaGetLastError());
   return 0;
@@ -531,6 +540,19 @@ int direct_forward(const EpsGeom& g, const T* x, const T* core, T* out, cudaStre
 #undef DCTN_DIRECT_CASE
   return dctn_set_error(-2, "direct forward kernel: no instance for Q=%d with %d+%d factors", g.Q, g.m, g.n - g.m);
 }
+// phi fused into the forward (raw pixels in): K = 2, C = 1, Q = 2 — the HBM-bound first layer of config 1
+bool direct_pixels_supported(const EpsGeom& g, int dtype) { return g.K == 2 && g.C == 1 && g.Q == 2 && direct_supported(g, dtype); }
+template <typename T>
+int direct_forward_pixels(const EpsGeom& g, const T* pixels, T scale, const T* core, T* out, cudaStream_t st) {
+  switch (g.O) {
+    case 2: return launch_direct_k2<T, 2, 2, true>(g, pixels, core, out, st, scale);
+    case 4: return launch_direct_k2<T, 2, 4, true>(g, pixels, core, out, st, scale);
+    case 6: return launch_direct_k2<T, 2, 6, true>(g, pixels, core, out, st, scale);
+    default: return launch_direct_k2<T, 2, 0, true>(g, pixels, core, out, st, scale);
+  }
+}
+template int direct_forward_pixels<float>(const EpsGeom&, const float*, float, const float*, float*, cudaStream_t);
+template int direct_forward_pixels<double>(const EpsGeom&, const double*, double, const double*, double*, cudaStream_t);
 template int direct_forward<float>(const EpsGeom&, const float*, const float*, float*, cudaStream_t);
 template int direct_forward<double>(const EpsGeom&, const double*, const double*, double*, cudaStream_t);
 

@@ -21,6 +21,9 @@ template <typename T> int launch_gather_dx(const EpsGeom& g, const T* dxp, T* dx
 // ---- streaming thread-per-patch family for tiny cores (eps_direct.cu): HBM-bound shapes
 bool direct_supported(const EpsGeom& g, int dtype);
 template <typename T> int direct_forward(const EpsGeom& g, const T* x, const T* core, T* out, cudaStream_t st);
+// phi(u) = scale * (sin^2(pi u / 2), cos^2(pi u / 2)) evaluated on load from the raw pixel image (B, H, W): K = 2, C = 1, Q = 2
+bool direct_pixels_supported(const EpsGeom& g, int dtype);
+template <typename T> int direct_forward_pixels(const EpsGeom& g, const T* pixels, T scale, const T* core, T* out, cudaStream_t st);
 bool direct_bwd_supported(const EpsGeom& g, int dtype, int kind);
 size_t direct_workspace_bytes(const EpsGeom& g, int dtype, int kind);
 // kind 1: result = dcore (core unused), kind 2: result = dx

@@ -177,6 +177,66 @@ def eps(core: Tensor, input: Tensor) -> Tensor:
     return EpsFunction.apply(core, input, _default_variant)
 
 
+class EpsFromPixelsFunction(torch.autograd.Function):
+    """First layer on RAW pixels: eps(core, phi(pixels)) with the feature map evaluated inside the kernel
+    (dctn_eps_forward_from_pixels).  Differentiable w.r.t. ``core`` only — pixels are data; the core gradient is the
+    ordinary one on phi(pixels)."""
+
+    @staticmethod
+    def forward(ctx, core: Tensor, pixels: Tensor, scale: float, variant: int) -> Tensor:
+        B, H, W = pixels.shape
+        K = math.isqrt(core.ndim - 1)
+        assert core.shape[:-1] == (2,) * (K * K), "the fused feature map has two components (Q_in = 2, one channel)"
+        core_c, pix_c = _dense(core), _dense(pixels)
+        plan = _plan(1, K, 2, core.shape[-1], pixels.dtype, variant)
+        out = torch.empty((B, H - K + 1, W - K + 1, core.shape[-1]), dtype=pixels.dtype, device=pixels.device)
+        with torch.cuda.device(pixels.device):
+            rc = _lib.lib().dctn_eps_forward_from_pixels(
+                plan, pix_c.data_ptr(), float(scale), core_c.data_ptr(), out.data_ptr(), B, H, W,
+                torch.cuda.current_stream().cuda_stream,
+            )
+        _lib.check(rc, "dctn_eps_forward_from_pixels")
+        ctx.save_for_backward(pix_c)
+        ctx.plan, ctx.scale, ctx.core_shape = plan, float(scale), core.shape
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout: Tensor):
+        (pix_c,) = ctx.saved_tensors
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None
+        B, H, W = pix_c.shape
+        x = phi_sin_cos_squared(pix_c, ctx.scale)
+        gout = _dense(gout)
+        dcore = torch.empty(ctx.core_shape, dtype=pix_c.dtype, device=pix_c.device)
+        with torch.cuda.device(pix_c.device):
+            ws = _workspace(ctx.plan, B, H, W, _lib.WS_BACKWARD_CORE, pix_c.device)
+            rc = _lib.lib().dctn_eps_backward_core(
+                ctx.plan, x.data_ptr(), gout.data_ptr(), dcore.data_ptr(), B, H, W, ws.data_ptr(), ws.numel(),
+                torch.cuda.current_stream().cuda_stream,
+            )
+        _lib.check(rc, "dctn_eps_backward_core")
+        return dcore, None, None, None
+
+
+def phi_sin_cos_squared(pixels: Tensor, scale: float) -> Tensor:
+    """The reference's feature map (dctn/dataset_loading.py:33-36): (B, H, W) pixels in [0, 1] ->
+    (1, B, H, W, 2) = scale * (sin^2(pi u / 2), cos^2(pi u / 2))."""
+    return torch.stack((scale * torch.sin(pixels * (math.pi / 2)) ** 2, scale * torch.cos(pixels * (math.pi / 2)) ** 2), dim=-1)[None]
+
+
+def eps_from_pixels(core: Tensor, pixels: Tensor, scale: float = 1.0) -> Tensor:
+    """``eps(core, phi_sin_cos_squared(pixels, scale))`` with the feature map fused into the kernel: one float per pixel
+    is read instead of two.  Additional entry point (the reference applies phi in its data loader); K = 2, one channel,
+    Q_in = 2 layers with a small core only — other shapes raise."""
+    if not (pixels.is_cuda and core.is_cuda):
+        raise RuntimeError("dctn_b200.eps_from_pixels runs on CUDA tensors only (no CPU fallback)")
+    if pixels.ndim != 3 or pixels.dtype not in _DTYPES or core.dtype != pixels.dtype:
+        raise TypeError("eps_from_pixels: pixels must be (B, H, W) float32/float64 with the core's dtype")
+    return EpsFromPixelsFunction.apply(core, pixels, scale, _default_variant)
+
+
 def eps_one_by_one(core: Tensor, input: Tensor) -> Tensor:
     """Drop-in for dctn/eps.py:43-63.  The reference contracts one aligned factor at a time; the result is
     the same tensor, so this routes to the same fused kernel."""

@@ -110,6 +110,14 @@ int dctn_eps_backward_input_saved(const dctn_plan_t* plan, const void* x, const 
                                   const void* saved, size_t saved_bytes, void* dx, int B, int H, int W,
                                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* First layer fed with RAW pixels: out = eps(core, phi(pixels)), phi(u) = scale * (sin^2(pi u / 2), cos^2(pi u / 2)) —
+ * the feature map the reference applies in its data loader (dctn/dataset_loading.py:33-36; scale = 2 nu,
+ * new_runner.py:358-361) — evaluated inside the kernel, so one float per pixel crosses HBM instead of two.
+ * pixels: (B, H, W) of the plan's dtype.  An ADDITIONAL entry: K = 2, C = 1, Q_in = 2 plans of
+ * the streaming family only (the HBM-bound regime); DCTN_ERR_UNSUPPORTED otherwise.  No workspace. */
+int dctn_eps_forward_from_pixels(const dctn_plan_t* plan, const void* pixels, double scale, const void* core,
+                                 void* out, int B, int H, int W, void* stream);
+
 /* out[t,i] = log sum_r exp(log_A[t,r] + log_B[r,i]).  Replaces dctn/logmatmulexp.py:5-14. */
 int dctn_logmatmulexp_forward(const void* log_A, const void* log_B, void* out, int Theta, int R, int I,
                               int dtype, void* stream);

@@ -579,6 +579,37 @@ def test_direct_kernels_vs_oracle(shape, dtype):
         assert rel_err(got, ref) <= tol
 
 
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("B,H,W,Oq", [(5, 28, 28, 2), (3, 9, 40, 5), (2, 7, 33, 6)])
+def test_eps_from_pixels_vs_oracle(B, H, W, Oq, dtype):
+    """dctn_eps_forward_from_pixels: the feature map of dctn/dataset_loading.py:33-36 fused into the K=2 forward kernel,
+    against the oracle on phi(pixels); the core gradient too."""
+    from dctn_b200 import eps as E
+
+    gen = torch.Generator().manual_seed(41)
+    u = torch.rand(B, H, W, generator=gen, dtype=torch.float64).to(dtype).double()
+    core = (torch.randn(2, 2, 2, 2, Oq, generator=gen, dtype=torch.float64) * 0.25).to(dtype).double()
+    gout = torch.randn(B, H - 1, W - 1, Oq, generator=gen, dtype=torch.float64).to(dtype).double()
+    scale = 1.45646
+    x = O.phi_cos_sin_squared(u, scale / 2)           # the oracle's nu convention: 2 * nu = scale
+    want = O.eps_4step(core, x)
+    want_dcore, _ = O.eps_grads(core, x, gout)
+    cd = core.to(DEV, dtype).requires_grad_(True)
+    out = E.eps_from_pixels(cd, u.to(DEV, dtype), scale)
+    out.backward(gout.to(DEV, dtype))
+    tol = TOL[dtype]
+    assert rel_err(out, want) <= tol
+    assert rel_err(cd.grad, want_dcore) <= tol
+    assert rel_err(E.phi_sin_cos_squared(u.to(DEV, dtype), scale), x) <= tol
+
+
+def test_eps_from_pixels_rejects_other_layers():
+    from dctn_b200 import eps as E
+
+    with pytest.raises(RuntimeError, match="K=2, C=1, Q_in=2"):
+        E.eps_from_pixels(torch.randn(*(2,) * 9, 4, device=DEV), torch.rand(2, 8, 8, device=DEV))
+
+
 def test_forward_host_entry():
     """dctn_eps_forward_host: host buffers in, host buffer out (copies inside), against the oracle."""
     import ctypes
