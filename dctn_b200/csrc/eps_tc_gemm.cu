@@ -210,43 +210,40 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
   }
   if (warp == 2) tc::tmem_alloc(tc::smem_u32(tmem_slot), TMEM_COLS);
   {
-    const int NX = g.n * Q;
-    for (int idx = tid; idx < NX * 128; idx += G_THREADS) {
-      const int pr = idx & 127, jq = idx >> 7;
-      const long long p = pt0 + pr;
-      float v = 0.f;
-      if (p < g.P) v = __ldg(&a.x[patch_origin(g, p) + g.foff[jq / Q] + jq % Q]);
-      xs[jq * 128 + pr] = v;
-    }
-    if (a.withG || MODE == MODE_DKR2) {
-      for (int idx = tid; idx < O * 128; idx += G_THREADS) {
-        const int pr = idx & 127, o = idx >> 7;
-        const long long p = pt0 + pr;
-        gsx[o * 128 + pr] = (p < g.P) ? __ldg(&a.gout[p * O + o]) : 0.f;
+    // a thread owns one patch row (pr) and every third factor (G_THREADS = 3 x 128): ONE patch-origin computation, the Q
+    // loads of a factor issued together and — F16 — its range normalisation in the same pass: the factor vector (and the
+    // gout row) is scaled by a power of two so that its largest magnitude lies in [0.5, 1); exact, undone by the
+    // epilogue through rowexp
+    const int pr = tid & 127, slot = tid >> 7;
+    const long long p = pt0 + pr;
+    const bool valid = p < g.P;
+    const long long org = valid ? patch_origin(g, p) : 0;
+    const bool needg = a.withG || MODE == MODE_DKR2;
+    for (int j = slot; j <= g.n; j += 3) {
+      const bool isg = j == g.n;
+      if (isg && !needg) { if (F16) fexp[j * 128 + pr] = 0; continue; }
+      const int cnt = isg ? O : Q;
+      const float* src = isg ? a.gout + p * O : a.x + org + g.foff[isg ? 0 : j];
+      float* dst = isg ? gsx + pr : xs + j * Q * 128 + pr;
+      float m = 0.f;
+      for (int q = 0; q < cnt; ++q) {
+        const float v = valid ? __ldg(src + q) : 0.f;
+        dst[q * 128] = v;
+        m = fmaxf(m, fabsf(v));
+      }
+      if (F16) {
+        int e = tc::norm_exp(m);
+        if (isg && !a.withG) e = 0;     // MODE_DKR2 uses gout only in the epilogue (fp32): keep it as is
+        if (e != 0) {
+          const float s1 = __int_as_float((127 - e / 2) << 23), s2 = __int_as_float((127 - (e - e / 2)) << 23);
+          for (int q = 0; q < cnt; ++q) dst[q * 128] = dst[q * 128] * s1 * s2;
+        }
+        fexp[j * 128 + pr] = e;
       }
     }
   }
   __syncthreads();
   if (F16) {
-    // range normalisation for fp16: scale every factor vector (and the gout row) of a patch by a power of two so that
-    // its largest magnitude lies in [0.5, 1); exact, undone by the epilogue through rowexp
-    for (int idx = tid; idx < (g.n + 1) * 128; idx += G_THREADS) {
-      const int pr = idx & 127, j = idx >> 7;
-      const bool isg = j == g.n;
-      if (isg && !(a.withG || MODE == MODE_DKR2)) { fexp[idx] = 0; continue; }
-      float* v = isg ? gsx + pr : xs + j * Q * 128 + pr;
-      const int cnt = isg ? O : Q;
-      float m = 0.f;
-      for (int q = 0; q < cnt; ++q) m = fmaxf(m, fabsf(v[q * 128]));
-      int e = 0;
-      if (m > 0.f && m < 3.0e38f) frexpf(m, &e);
-      // MODE_DKR2 uses gout only in the epilogue (fp32): keep it as is
-      if (isg && !a.withG) e = 0;
-      if (e != 0)
-        for (int q = 0; q < cnt; ++q) v[q * 128] = scalbnf(v[q * 128], -e);
-      fexp[idx] = e;
-    }
-    __syncthreads();
     if (tid < 128) {
       int ea = 0, eb = 0;
       for (int j = 0; j < g.n; ++j) {

@@ -364,6 +364,28 @@ def test_tc_backward_core_full_size_vs_fp64(B, H, W, Q, K, Oq):
     assert rel_err(ffma, want) <= 1e-5
 
 
+def test_tc_two_channel_layer_vs_oracle():
+    """C = 2, K = 3, Q = 2: 18 factors per patch (A = 512, Bn = 512).  The first half has 9 factors, more than the fully
+    fused input-gradient epilogue unrolls, so this runs the W path (first leave-one-out stage in the GEMM epilogue,
+    second stage in loo_groups_kernel); also the only tensor-core test with interleaved channels in the factor order."""
+    from dctn_b200 import _lib
+
+    gen = torch.Generator().manual_seed(33)
+    C, B, H, W, Q, K, Oq = 2, 8, 25, 25, 2, 3, 4
+    n = K * K * C
+    x = (torch.rand(C, B, H, W, Q, generator=gen, dtype=torch.float64) * 1.2 + 0.2).float()
+    core = (torch.randn(*(Q,) * n, Oq, generator=gen, dtype=torch.float64) * Q ** (-n / 2)).float()
+    gout = torch.randn(B, H - K + 1, W - K + 1, Oq, generator=gen, dtype=torch.float64).float()
+    want = O.eps_4step(core.double(), x.double())
+    want_dc, want_dx = O.eps_grads(core.double(), x.double(), gout.double())
+    for variant in ("tch3", "tc3"):
+        assert rel_err(_raw_call(_lib.WS_FORWARD, variant, core.to(DEV), x.to(DEV), gout.to(DEV)), want) <= 1e-5
+        assert rel_err(_raw_call(_lib.WS_BACKWARD_CORE, variant, core.to(DEV), x.to(DEV), gout.to(DEV)), want_dc) <= 1e-5
+        assert rel_err(_raw_call(_lib.WS_BACKWARD_INPUT, variant, core.to(DEV), x.to(DEV), gout.to(DEV)), want_dx) <= 1e-5
+        out, dx = _raw_train_call(variant, core.to(DEV), x.to(DEV), gout.to(DEV))
+        assert rel_err(out, want) <= 1e-5 and rel_err(dx, want_dx) <= 1e-5
+
+
 @pytest.fixture
 def generic_tc_kernels(monkeypatch):
     """Forces the generic table-lookup tcgen05 GEMM kernels instead of the register-table ones (eps_tc_fast.cu)."""
