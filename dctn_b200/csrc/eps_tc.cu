@@ -449,7 +449,6 @@ inline void dcore_split(const EpsGeom& g, long long* per_split, int* splits) {
 
 bool tc_supported(const EpsGeom& g, int kind) {
   if (kind != 1) return tcg_supported(g, kind);  // forward / input-gradient GEMMs live in eps_tc_gemm.cu
-  if (g.a_nh > 4 || g.a_nl > 4 || g.b_nh > 4 || g.b_nl > 4) return false;  // 4 factor slots per table entry
   if (g.P >= (1ll << 31) / (g.Q > g.O ? g.Q : g.O)) return false;  // 32-bit patch index math
   if (g.A < 64 || g.N < 64) return false;    // tiles would be mostly padding: the CUDA-core family is the better fit
   if (g.P < 4096) return false;              // tiny reductions are launch-bound either way
