@@ -337,7 +337,7 @@ def run_ours(args):
     torch.manual_seed(0)
     model = EPSesPlusLinear(specs, UnitTheoreticalOutputStd(), 1.0, dev, torch.float32, image_size=image_size, Q_0=Q0)
     model.train()
-    opt = torch.optim.Adam(model.parameters(), lr=1.11e-4)
+    opt = torch.optim.Adam(model.parameters(), lr=1.11e-4, fused=True)   # one kernel for all parameters (same update rule)
     reducer = GradAllReducer(model.parameters())
     nb = 4  # distinct synthetic batches, rotated
     host = [synth_batch(batch, image_size, scale, 1000 + rank * 17 + i, torch.float32, Q0) for i in range(nb)]
