@@ -11,7 +11,7 @@ import threading
 from ctypes import c_char_p, c_int, c_size_t, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdctn_b200.so")
+LIB_PATH = os.environ.get("DCTN_B200_LIB") or os.path.join(_HERE, "libdctn_b200.so")   # override: A/B comparisons of two builds
 
 F32, F64 = 0, 1
 VARIANT_AUTO, VARIANT_FFMA, VARIANT_TC3, VARIANT_TC1, VARIANT_DIRECT, VARIANT_TCH3 = 0, 1, 2, 3, 4, 5

@@ -36,7 +36,10 @@ constexpr int FKS = 64;          // K values per stage (one 128-byte row of fp16
 constexpr int F_ASTAGES = 3;     // at most: A stages in TMEM of (hi 32 + lo 32 columns); 3 when BN <= 160, else 2
 constexpr int F_MAX_BSTAGES = 4;
 constexpr int F_MAX_BN = 192;    // main + small accumulators (2 * BN) + 128 or 192 columns of A <= 512
-constexpr int F_THREADS = 384;   // warp 0: bulk copies, warp 1: MMA, warp 2: TMEM alloc, warps 4-7: producers, warps 8-11: epilogue
+constexpr int F_THREADS = 512;   // warp 0: bulk copies, warp 1: MMA, warp 2: TMEM alloc, warps 4-7: producers, warps 8-15: epilogue
+                                 // (two warps per TMEM lane quadrant, alternating 32-column batches: the epilogue of a tile is
+                                 // not overlapped with the next tile's MMAs, so its length is paid in full)
+constexpr int F_EPI_WARPS = 8;
 // FMODE_LOO: the input-gradient GEMM with the first stage of the leave-one-out contraction fused into the epilogue:
 // instead of the P x A matrix dKR1 it writes, per patch, W[p] = (Whi[EHE] | Wlo[ELR]),
 //   Whi[eh] = sum_el dKR1[eh*ELR + el] * TL1[el],   Wlo[el] = sum_eh dKR1[eh*ELR + el] * TH1[eh]
@@ -203,19 +206,23 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
   float* xh = tabEH;                                   // [mfirst*Q][128]
   int* fe = (int*)(xh + mfirst * Q * 128);             // [mfirst][128]
   float* dxa = (float*)(fe + mfirst * 128);            // [ecnth*Q][128]
-  float* wlo = dxa + a.ecnth * Q * 128;                // [16][128]
-  const int eregion = (MODE == FMODE_LOOX) ? (mfirst * Q + mfirst + a.ecnth * Q + 16) * 128
-                    : (MODE != FMODE_STORE ? a.EHE * 128 : 0);
-  float* outs = tabEH + eregion;                       // FMODE_FWD: [O][128]
+  // (dxa, wlo and outs exist twice: one copy per epilogue half, merged at the end)
+  float* wlo = (MODE == FMODE_LOOX) ? dxa + 2 * a.ecnth * Q * 128 : tabEH + a.EHE * 128;   // [2][16][128] (LOOX), [1][16][128] (LOO)
+  const int eregion = (MODE == FMODE_LOOX) ? (mfirst * Q + mfirst + 2 * a.ecnth * Q + 32) * 128
+                    : (MODE == FMODE_LOO ? (a.EHE + 16) * 128 : (MODE == FMODE_FWD ? a.EHE * 128 : 0));
+  float* outs = tabEH + eregion;                       // FMODE_FWD: [2][O][128]
   // exponents of the per-patch normalisation: [0] generated group, [1] all other factors, [2] the epilogue's lo group
-  int* rowexp = (int*)(outs + (MODE == FMODE_FWD ? O * 128 : 0));  // [3][128]
+  int* rowexp = (int*)(outs + (MODE == FMODE_FWD ? 2 * O * 128 : 0));  // [3][128]
   // training forward: per epilogue warp a [32 rows][36] staging tile that turns the thread-per-row accumulator batches
   // into whole 128-byte row segments of T (a direct store from registers writes 32 half-used sectors per instruction)
+  // training forward: per epilogue warp a [32 rows][20] staging tile (16 columns at a time).  It shares its memory with
+  // regtab, the lo-group tables of the generated operand (rows 0..15) and of the epilogue's half (rows 16..31): those are
+  // built by all threads with the other tables and copied into registers by the producer / epilogue threads right after
+  // the setup barrier (a named barrier separates the copies from the first staging write)
   float* tstage = (float*)(rowexp + 384);
-  // lo-group tables of the generated operand (rows 0..15) and of the epilogue's half (rows 16..31): built by all threads
-  // with the other tables, copied into registers by the producer / epilogue threads once the setup barrier has passed
-  float* regtab = tstage + ((MODE == FMODE_FWD && a.tsave != nullptr) ? 4 * 32 * 36 : 0);   // [32][128]
-  uint64_t* bars = (uint64_t*)(regtab + 32 * 128);
+  float* regtab = tstage;                              // [32][128]
+  constexpr int REGION_FLOATS = (F_EPI_WARPS * 32 * 20 > 32 * 128) ? F_EPI_WARPS * 32 * 20 : 32 * 128;
+  uint64_t* bars = (uint64_t*)(tstage + REGION_FLOATS);
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * F_MAX_BSTAGES + 2 * F_ASTAGES + 2);
   const uint32_t bar_fullB0 = tc::smem_u32(bars), bar_emptyB0 = bar_fullB0 + 8 * F_MAX_BSTAGES;
   const uint32_t bar_fullA0 = bar_emptyB0 + 8 * F_MAX_BSTAGES, bar_emptyA0 = bar_fullA0 + 8 * F_ASTAGES;
@@ -241,7 +248,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
       tc::mbar_init(bar_emptyA0 + 8 * s, 1);
     }
     tc::mbar_init(bar_accfull, 1);
-    tc::mbar_init(bar_accempty, 4);
+    tc::mbar_init(bar_accempty, F_EPI_WARPS);
     tc::fence_barrier_init();
   }
   if (warp == 2) tc::tmem_alloc(tc::smem_u32(tmem_slot), 512);
@@ -250,12 +257,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
     // every thread owns one patch row (pr) and every third factor: it loads the factor's Q values with vector loads,
     // normalises them (range normalisation, see eps_tc_gemm.cu) and stores values and exponent — one pass, all loads of
     // a thread independent of each other
-    const int pr = tid & 127, slot = tid >> 7;         // F_THREADS = 3 * 128
+    const int pr = tid & 127, slot = tid >> 7;         // F_THREADS = 4 * 128
     const long long p = pt0 + pr;
     const bool valid = p < g.P;
     const long long org = valid ? patch_origin(g, p) : 0;
 #pragma unroll 2
-    for (int j = slot; j < g.n; j += 3) {
+    for (int j = slot; j < g.n; j += F_THREADS / 128) {
       float v[16];
       const float* px = a.x + org + g.foff[j];
       if (!valid) {
@@ -357,10 +364,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
     if (MODE == FMODE_LOOX) {
       for (int idx = tid; idx < mfirst * Q * 128; idx += F_THREADS) xh[idx] = xs[a.ej0 * Q * 128 + idx];
       for (int idx = tid; idx < mfirst * 128; idx += F_THREADS) fe[idx] = fexp[a.ej0 * 128 + idx];
-      for (int idx = tid; idx < a.ecnth * Q * 128; idx += F_THREADS) dxa[idx] = 0.f;
+      for (int idx = tid; idx < 2 * a.ecnth * Q * 128; idx += F_THREADS) dxa[idx] = 0.f;
     }
     if (MODE == FMODE_FWD)
-      for (int idx = tid; idx < O * 128; idx += F_THREADS) outs[idx] = 0.f;
+      for (int idx = tid; idx < 2 * O * 128; idx += F_THREADS) outs[idx] = 0.f;
   }
   tc::tc_fence_before();
   __syncthreads();  // tables complete; the scratch aliasing the stages is dead from here on
@@ -379,6 +386,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
       for (int j = 0; j < 16; ++j) EL[j] = regtab[(16 + j) * 128 + pr];
     }
   }
+  if (warp >= 4) asm volatile("bar.sync 2, %0;" ::"n"(32 * (4 + F_EPI_WARPS)) : "memory");   // regtab consumed: tstage may be written
   const int core_exp = tc::core_scale_exp(__ldg(a.core_absmax));
   const long long dbg_t_setup = TCF_CLK();
   const uint32_t tmem_main = *tmem_slot;
@@ -493,10 +501,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
   } else if (warp >= 8) {
     // =========================== epilogue ===========================
     const int quad = warp & 3;
+    const int half = (warp - 8) >> 2;        // which of the two warps of this lane quadrant: takes every other 32-column batch
     const int pr = quad * 32 + lane;
     const int pl = pl0 + pr;
     const bool pvalid = pl < a.np;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    float* outsH = outs + half * O * 128;                 // this half's partial sums (FMODE_FWD)
+    float* dxaH = dxa + half * a.ecnth * Q * 128;         // this half's hi-group accumulators (FMODE_LOOX)
     // accumulator -> true value: 2^kexp as two exact factors (|kexp| may exceed 127)
     const int kexp = rowexp[pr] - 15 - core_exp;
     const float sc1 = scalbnf(1.f, kexp / 2), sc2 = scalbnf(1.f, kexp - kexp / 2);
@@ -526,6 +537,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
       for (int cb = 0; cb < BN; cb += 32) {
         const int nb = n0 + cb;
         if (nb >= a.Ncols) break;             // Ncols % 32 == 0 (host check): batches are whole or empty
+        if (((cb >> 5) & 1) != half) continue;
         float v[32];
         {
           float w[32];
@@ -537,10 +549,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
           // columns nb..nb+31 are a = eh*ELR + el: 32/ELR runs of one eh each; Q is a power of two here
           const int eh0 = nb / a.ELR, lq = 31 - __clz(Q);
           switch (a.ELR) {
-            case 16: loox_batch<16>(v, EL, WLO, xh, dxa, eh0, a.ecnth, Q, lq, pr); break;
-            case 8: loox_batch<8>(v, EL, WLO, xh, dxa, eh0, a.ecnth, Q, lq, pr); break;
-            case 4: loox_batch<4>(v, EL, WLO, xh, dxa, eh0, a.ecnth, Q, lq, pr); break;
-            default: loox_batch<2>(v, EL, WLO, xh, dxa, eh0, a.ecnth, Q, lq, pr); break;
+            case 16: loox_batch<16>(v, EL, WLO, xh, dxaH, eh0, a.ecnth, Q, lq, pr); break;
+            case 8: loox_batch<8>(v, EL, WLO, xh, dxaH, eh0, a.ecnth, Q, lq, pr); break;
+            case 4: loox_batch<4>(v, EL, WLO, xh, dxaH, eh0, a.ecnth, Q, lq, pr); break;
+            default: loox_batch<2>(v, EL, WLO, xh, dxaH, eh0, a.ecnth, Q, lq, pr); break;
           }
         } else if (MODE == FMODE_LOO) {
           // columns nb..nb+31 are a = eh*ELR + el: 32/ELR runs of one eh each
@@ -598,25 +610,29 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
           }
         } else {
           if (a.tsave != nullptr) {
-            float* st = tstage + quad * (32 * 36);
+            float* st = tstage + (warp - 8) * (32 * 20);
+            const int rsub = lane >> 2, c4 = (lane & 3) * 4;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *(float4*)(st + lane * 36 + i) = make_float4(v[i] * sc1 * sc2, v[i + 1] * sc1 * sc2, v[i + 2] * sc1 * sc2, v[i + 3] * sc1 * sc2);
-            __syncwarp();
-            // one store instruction = 4 rows x 128 contiguous bytes
-            const int rsub = lane >> 3, c4 = (lane & 7) * 4;
-            float* tbase = a.tsave + (pt0 + quad * 32) * (long long)a.Ncols + nb + c4;
+            for (int hb = 0; hb < 2; ++hb) {               // 16 columns at a time through the [32][20] tile
 #pragma unroll
-            for (int r0 = 0; r0 < 32; r0 += 4) {
-              const int r = r0 + rsub;
-              if (pl0 + quad * 32 + r < a.np) *(float4*)(tbase + (long long)r * a.Ncols) = *(const float4*)(st + r * 36 + c4);
+              for (int i = 0; i < 16; i += 4)
+                *(float4*)(st + lane * 20 + i) = make_float4(v[16 * hb + i] * sc1 * sc2, v[16 * hb + i + 1] * sc1 * sc2,
+                                                             v[16 * hb + i + 2] * sc1 * sc2, v[16 * hb + i + 3] * sc1 * sc2);
+              __syncwarp();
+              // one store instruction = 8 rows x 64 contiguous bytes
+              float* tbase = a.tsave + (pt0 + quad * 32) * (long long)a.Ncols + nb + 16 * hb + c4;
+#pragma unroll
+              for (int r0 = 0; r0 < 32; r0 += 8) {
+                const int r = r0 + rsub;
+                if (pl0 + quad * 32 + r < a.np) *(float4*)(tbase + (long long)r * a.Ncols) = *(const float4*)(st + r * 20 + c4);
+              }
+              __syncwarp();
             }
-            __syncwarp();
           }
           // 32 columns of one o (Bn % 32 == 0): b = b0 .. b0+31, KR2[b] = EH[b / ELR] * EL[b % ELR]
           const int o = nb / g.Bn, b0 = nb - o * g.Bn;
           if (o != cur_o) {
-            outs[cur_o * 128 + pr] += s;
+            outsH[cur_o * 128 + pr] += s;
             s = 0.f;
             cur_o = o;
           }
@@ -665,7 +681,22 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
       dbg_epi += TCF_CLK() - te0;
     }
     if (a.dbg && warp == 8 && lane == 0) a.dbg[(long long)blockIdx.x * 8 + 7] = dbg_epi;
-    if (MODE == FMODE_LOOX) {
+    // ---- merge the two halves: the second warp of a quadrant parks its partial state in shared memory, the first adds it
+    if (half == 1) {
+      if (MODE == FMODE_FWD) outsH[cur_o * 128 + pr] += s;
+      if (MODE == FMODE_LOO || MODE == FMODE_LOOX) {
+        float* w1 = wlo + (MODE == FMODE_LOOX ? 16 * 128 : 0);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w1[j * 128 + pr] = WLO[j];
+      }
+    }
+    asm volatile("bar.sync 3, %0;" ::"n"(32 * F_EPI_WARPS) : "memory");
+    if (half == 0 && (MODE == FMODE_LOO || MODE == FMODE_LOOX)) {
+      const float* w1 = wlo + (MODE == FMODE_LOOX ? 16 * 128 : 0);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) WLO[j] += w1[j * 128 + pr];
+    }
+    if (MODE == FMODE_LOOX && half == 0) {
       const int lq = 31 - __clz(Q);
       const int kb = kexp + rowexp[128 + pr];            // accumulator exponent + all first-half factor exponents
       float* drow = a.out + ((pt0 + pr) * g.n + a.ej0) * (long long)Q;
@@ -674,7 +705,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
         const int k = kb - fe[t * 128 + pr];
         const float s1 = scalbnf(1.f, k / 2), s2 = scalbnf(1.f, k - k / 2);
         if (pvalid)
-          for (int q = 0; q < Q; ++q) drow[t * Q + q] = dxa[((t * Q + q) << 7) + pr] * s1 * s2;
+          for (int q = 0; q < Q; ++q)
+            drow[t * Q + q] = (dxa[((t * Q + q) << 7) + pr] + dxa[((a.ecnth * Q + t * Q + q) << 7) + pr]) * s1 * s2;
       }
       // lo group: from the Wlo registers (through this thread's column of shared memory, for dynamic indexing)
 #pragma unroll
@@ -697,17 +729,17 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
         }
       }
     }
-    if (MODE == FMODE_LOO && pvalid) {
+    if (MODE == FMODE_LOO && half == 0 && pvalid) {
       float* wrow = a.out + (long long)pl * a.ldc + a.EHE;
 #pragma unroll
       for (int j = 0; j < 16; ++j)
         if (j < a.ELR) wrow[j] = WLO[j] * lsc1 * lsc2;
     }
-    if (MODE == FMODE_FWD) {
+    if (MODE == FMODE_FWD && half == 0) {
       outs[cur_o * 128 + pr] += s;
       if (pvalid) {
         float* orow = a.out + (pt0 + pr) * O;
-        for (int o = 0; o < O; ++o) orow[o] = outs[o * 128 + pr] * fsc1 * fsc2;
+        for (int o = 0; o < O; ++o) orow[o] = (outs[o * 128 + pr] + outs[(O + o) * 128 + pr]) * fsc1 * fsc2;
       }
     }
   }
@@ -770,13 +802,15 @@ inline FastShape fast_shape(const EpsGeom& g, int mode) {
   return s;
 }
 
-constexpr size_t TSTAGE_BYTES = 4 * 32 * 36 * 4;   // training forward: staging tiles of the T store
+// lo-group register tables [32][128], sharing their memory with the staging tiles of the T store [8 warps][32][20]
+constexpr size_t REGION_BYTES = ((size_t)F_EPI_WARPS * 32 * 20 > 32 * 128 ? (size_t)F_EPI_WARPS * 32 * 20 : 32 * 128) * 4;
 inline size_t fast_fixed_smem(const EpsGeom& g, const FastShape& s, int mode) {
   const size_t nk = (size_t)(s.Kdim + FKS - 1) / FKS;
   const size_t nH = nk * (FKS / s.KLR);
   const size_t mfirst = (size_t)s.ecnth + s.ecntl;
-  const size_t erows = (mode == FMODE_LOOX) ? mfirst * g.Q + mfirst + (size_t)s.ecnth * g.Q + 16 : (mode != FMODE_STORE ? (size_t)s.EHE : 0);
-  return 1024 + (nH + erows + 32 + (mode == FMODE_FWD ? (size_t)g.O : 0)) * 128 * 4 + 384 * 4 + (mode == FMODE_FWD ? TSTAGE_BYTES : 0) +
+  const size_t erows = (mode == FMODE_LOOX) ? mfirst * g.Q + mfirst + 2 * (size_t)s.ecnth * g.Q + 32
+                     : (mode == FMODE_LOO ? (size_t)s.EHE + 16 : (mode == FMODE_FWD ? (size_t)s.EHE : 0));
+  return 1024 + (nH + erows + (mode == FMODE_FWD ? 2 * (size_t)g.O : 0)) * 128 * 4 + 384 * 4 + REGION_BYTES +
          (2 * F_MAX_BSTAGES + 2 * F_ASTAGES + 2) * 8 + 16;
 }
 inline size_t fast_stage_bytes(int BN) { return 2 * (size_t)BN * 128; }
