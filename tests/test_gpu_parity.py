@@ -364,6 +364,33 @@ def test_tc_backward_core_full_size_vs_fp64(B, H, W, Q, K, Oq):
     assert rel_err(ffma, want) <= 1e-5
 
 
+def test_tch3_zero_and_sparse_inputs():
+    """Range normalisation must not invent NaNs: all-zero factor vectors (scale exponent 0), all-zero gout rows, whole zero
+    images and a zero core give exact zeros / the oracle's values."""
+    from dctn_b200 import _lib
+
+    B, H, W, Q, K, Oq = 8, 25, 25, 4, 3, 6
+    x, core, gout = _rand_layer(B, H, W, Q, K, Oq, seed=35)
+    gen = torch.Generator().manual_seed(36)
+    x = x * (torch.rand(1, B, H, W, 1, generator=gen) > 0.3)       # 30 % of the pixels have an all-zero feature vector
+    x[:, 3] = 0.0                                                    # one whole image is zero
+    gout = gout * (torch.rand(B, H - K + 1, W - K + 1, 1, generator=gen) > 0.5)
+    want = O.eps_4step(core.double(), x.double())
+    want_dc, want_dx = O.eps_grads(core.double(), x.double(), gout.double())
+    got = _raw_call(_lib.WS_FORWARD, "tch3", core.to(DEV), x.to(DEV), gout.to(DEV))
+    assert torch.isfinite(got).all() and rel_err(got, want) <= 1e-5
+    assert float(got[3].abs().max()) == 0.0
+    got_dc = _raw_call(_lib.WS_BACKWARD_CORE, "tch3", core.to(DEV), x.to(DEV), gout.to(DEV))
+    assert torch.isfinite(got_dc).all() and rel_err(got_dc, want_dc) <= 1e-5
+    out_s, dx_s = _raw_train_call("tch3", core.to(DEV), x.to(DEV), gout.to(DEV))
+    assert torch.isfinite(dx_s).all() and rel_err(dx_s, want_dx) <= 1e-5
+    zero_core = torch.zeros_like(core).to(DEV)
+    z = _raw_call(_lib.WS_FORWARD, "tch3", zero_core, x.to(DEV), gout.to(DEV))
+    assert float(z.abs().max()) == 0.0
+    zg = _raw_call(_lib.WS_BACKWARD_CORE, "tch3", core.to(DEV), x.to(DEV), torch.zeros_like(gout).to(DEV))
+    assert float(zg.abs().max()) == 0.0
+
+
 def test_tc_two_channel_layer_vs_oracle():
     """C = 2, K = 3, Q = 2: 18 factors per patch (A = 512, Bn = 512).  The first half has 9 factors, more than the fully
     fused input-gradient epilogue unrolls, so this runs the W path (first leave-one-out stage in the GEMM epilogue,
