@@ -12,6 +12,7 @@ from . import _lib  # noqa: F401  (does not load the .so until first use)
 __all__ = [
     "align",
     "contraction_path_cache",
+    "conv_sbs_log",
     "eps",
     "eps_plus_linear",
     "epses_composition",

@@ -35,6 +35,8 @@ SYMBOLS = {
     "dctn_eps_forward_from_pixels": (c_int, [c_void_p, c_void_p, ctypes.c_double, c_void_p, c_void_p] + [c_int] * 3 + [c_void_p]),
     "dctn_logmatmulexp_forward": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p]),
     "dctn_logmatmulexp_backward": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_void_p]),
+    "dctn_logmatmulexp_batched_forward": (c_int, [c_void_p] * 3 + [ctypes.c_longlong] + [c_int] * 4 + [c_void_p]),
+    "dctn_logmatmulexp_batched_backward": (c_int, [c_void_p] * 6 + [ctypes.c_longlong] + [c_int] * 4 + [c_void_p]),
     "dctn_eps_forward_host_device_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
     "dctn_eps_forward_host": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p, c_size_t, c_void_p]),
 }

@@ -348,6 +348,31 @@ extern "C" int dctn_logmatmulexp_backward(const void* A, const void* B, const vo
   return dctn_set_error(DCTN_ERR_BAD_ARG, "logmatmulexp: bad dtype %d", dtype);
 }
 
+extern "C" int dctn_logmatmulexp_batched_forward(const void* A, const void* B, void* out, long long batch, int Th, int R,
+                                                 int I, int dtype, void* stream) {
+  if (!A || !B || !out) return dctn_set_error(DCTN_ERR_BAD_ARG, "logmatmulexp_batched: null tensor pointer");
+  if (batch < 1 || Th < 1 || R < 1 || I < 1)
+    return dctn_set_error(DCTN_ERR_BAD_ARG, "logmatmulexp_batched: sizes must be positive (%lld, %d, %d, %d)", batch, Th, R, I);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DCTN_F32) return lme_batched_forward<float>((const float*)A, (const float*)B, (float*)out, batch, Th, R, I, st);
+  if (dtype == DCTN_F64) return lme_batched_forward<double>((const double*)A, (const double*)B, (double*)out, batch, Th, R, I, st);
+  return dctn_set_error(DCTN_ERR_BAD_ARG, "logmatmulexp_batched: bad dtype %d", dtype);
+}
+
+extern "C" int dctn_logmatmulexp_batched_backward(const void* A, const void* B, const void* out, const void* gout,
+                                                  void* dA, void* dB, long long batch, int Th, int R, int I, int dtype,
+                                                  void* stream) {
+  if (!A || !B || !out || !gout) return dctn_set_error(DCTN_ERR_BAD_ARG, "logmatmulexp_batched backward: null tensor pointer");
+  if (batch < 1 || Th < 1 || R < 1 || I < 1)
+    return dctn_set_error(DCTN_ERR_BAD_ARG, "logmatmulexp_batched: sizes must be positive (%lld, %d, %d, %d)", batch, Th, R, I);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DCTN_F32)
+    return lme_batched_backward<float>((const float*)A, (const float*)B, (const float*)out, (const float*)gout, (float*)dA, (float*)dB, batch, Th, R, I, st);
+  if (dtype == DCTN_F64)
+    return lme_batched_backward<double>((const double*)A, (const double*)B, (const double*)out, (const double*)gout, (double*)dA, (double*)dB, batch, Th, R, I, st);
+  return dctn_set_error(DCTN_ERR_BAD_ARG, "logmatmulexp_batched: bad dtype %d", dtype);
+}
+
 // ------------------------------------------------------------------------------------------------ host-buffer entry
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 

@@ -8,6 +8,7 @@
 // Bound: Theta*R*I exponentials on the SFU (MUFU.EX2) pipe, not HBM.
 #include "common.cuh"
 #include "eps_kernels.h"
+#include "../../include/dctn_b200.h"
 
 namespace {
 constexpr int TS = 16;  // 16x16 output tile per CTA, r staged in chunks of 16
@@ -46,9 +47,11 @@ __global__ void __launch_bounds__(TS * TS) lme_fwd_kernel(const T* __restrict__ 
       s = (m == neg_inf<T>()) ? T(0) : s * fexp(m - cm);
       m = cm;
     }
+    const int rc = R - r0;  // valid terms of this chunk (the padding is -inf: exp = 0, not worth an SFU op)
     if (m != neg_inf<T>() && m != -neg_inf<T>()) {
 #pragma unroll
-      for (int r = 0; r < TS; ++r) s += fexp(v[r] - m);
+      for (int r = 0; r < TS; ++r)
+        if (r < rc) s += fexp(v[r] - m);
     } else if (m == -neg_inf<T>()) {
       s = T(1);  // +inf term dominates: result is +inf (log(1) + inf)
     }
@@ -118,6 +121,112 @@ __global__ void __launch_bounds__(TS * TS) lme_bwd_b_kernel(const T* __restrict_
   }
   if (r < R && i < I) dB[(long long)r * I + i] = acc;
 }
+
+// ------------------------------------------------------------------------------------------------ batched, small matrices
+// out[p][t][i] = log sum_r exp(A[p][t][r] + B[p][r][i]),  p < NB: one small product per batch element — the bond
+// matrices of a ConvSBS ring (dctn/conv_sbs.py:258-304 contracts the same ring in linear space), one element per
+// (image, window).  A CTA takes G consecutive batch elements: their A and B blocks are contiguous in HBM, so they are
+// staged into shared memory with 128-bit loads, one thread computes one output from there, and the G*Th*I outputs of
+// the group are again contiguous (coalesced store).  Bound: NB*Th*R*I exponentials (MUFU); HBM traffic is the
+// algorithmic NB*(Th*R + R*I + Th*I) elements.
+template <typename T>
+__device__ __forceinline__ void stage_in(T* __restrict__ dst, const T* __restrict__ src, int n) {
+  constexpr int V = 16 / sizeof(T);
+  if ((n % V) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    const int4* s4 = reinterpret_cast<const int4*>(src);
+    int4* d4 = reinterpret_cast<int4*>(dst);
+    for (int k = threadIdx.x; k < n / V; k += blockDim.x) d4[k] = __ldg(s4 + k);
+  } else {
+    for (int k = threadIdx.x; k < n; k += blockDim.x) dst[k] = __ldg(src + k);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) lme_batched_fwd_kernel(const T* __restrict__ A, const T* __restrict__ B,
+                                                              T* __restrict__ out, long long NB, int Th, int R, int I,
+                                                              int G) {
+  extern __shared__ int4 lme_smem4[];
+  T* As = reinterpret_cast<T*>(lme_smem4);  // [G][Th][R]
+  T* Bs = As + (size_t)G * Th * R;          // [G][R][I]   (G*Th*R is kept a multiple of 4 by the host)
+  const int tr = Th * R, ri = R * I, ti = Th * I;
+  for (long long p0 = (long long)blockIdx.x * G; p0 < NB; p0 += (long long)gridDim.x * G) {
+    const int g = (int)((NB - p0) < G ? (NB - p0) : G);
+    stage_in(As, A + p0 * tr, g * tr);
+    stage_in(Bs, B + p0 * ri, g * ri);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < g * ti; idx += blockDim.x) {
+      const int gi = idx / ti, rem = idx - gi * ti, t = rem / I, i = rem - t * I;
+      const T* a = As + gi * tr + t * R;
+      const T* b = Bs + gi * ri + i;
+      T m = neg_inf<T>();
+      for (int r = 0; r < R; ++r) {
+        T v = a[r] + b[r * I];
+        m = v > m ? v : m;
+      }
+      T res = m;  // -inf (empty sum) and +inf propagate as they are
+      if (m != neg_inf<T>() && m != -neg_inf<T>()) {
+        T s = T(0);
+        for (int r = 0; r < R; ++r) s += fexp(a[r] + b[r * I] - m);
+        res = m + flog(s);
+      }
+      out[p0 * ti + idx] = res;
+    }
+    __syncthreads();
+  }
+}
+
+// dA[p][t][r] = sum_i gout[p][t][i] * exp(A[p][t][r] + B[p][r][i] - out[p][t][i]);  dB likewise, summed over t.
+template <typename T>
+__global__ void __launch_bounds__(256) lme_batched_bwd_kernel(const T* __restrict__ A, const T* __restrict__ B,
+                                                              const T* __restrict__ out, const T* __restrict__ gout,
+                                                              T* __restrict__ dA, T* __restrict__ dB, long long NB,
+                                                              int Th, int R, int I, int G) {
+  extern __shared__ int4 lme_smem4[];
+  const int tr = Th * R, ri = R * I, ti = Th * I;
+  T* As = reinterpret_cast<T*>(lme_smem4);  // every block length G*x is a multiple of 4 elements (host)
+  T* Bs = As + (size_t)G * tr;
+  T* Os = Bs + (size_t)G * ri;
+  T* Gs = Os + (size_t)G * ti;
+  for (long long p0 = (long long)blockIdx.x * G; p0 < NB; p0 += (long long)gridDim.x * G) {
+    const int g = (int)((NB - p0) < G ? (NB - p0) : G);
+    stage_in(As, A + p0 * tr, g * tr);
+    stage_in(Bs, B + p0 * ri, g * ri);
+    stage_in(Os, out + p0 * ti, g * ti);
+    stage_in(Gs, gout + p0 * ti, g * ti);
+    __syncthreads();
+    if (dA) {
+      for (int idx = threadIdx.x; idx < g * tr; idx += blockDim.x) {
+        const int gi = idx / tr, rem = idx - gi * tr, t = rem / R, r = rem - t * R;
+        const T a = As[idx];
+        const T* b = Bs + gi * ri + r * I;
+        const T* o = Os + gi * ti + t * I;
+        const T* gg = Gs + gi * ti + t * I;
+        T acc = T(0);
+        for (int i = 0; i < I; ++i) {
+          T gv = gg[i];
+          if (gv != T(0)) acc += gv * fexp(a + b[i] - o[i]);
+        }
+        dA[p0 * tr + idx] = acc;
+      }
+    }
+    if (dB) {
+      for (int idx = threadIdx.x; idx < g * ri; idx += blockDim.x) {
+        const int gi = idx / ri, rem = idx - gi * ri, r = rem / I, i = rem - r * I;
+        const T b = Bs[idx];
+        const T* a = As + gi * tr + r;
+        const T* o = Os + gi * ti + i;
+        const T* gg = Gs + gi * ti + i;
+        T acc = T(0);
+        for (int t = 0; t < Th; ++t) {
+          T gv = gg[t * I];
+          if (gv != T(0)) acc += gv * fexp(a[t * R] + b - o[t * I]);
+        }
+        dB[p0 * ri + idx] = acc;
+      }
+    }
+    __syncthreads();
+  }
+}
 }  // namespace
 
 template <typename T>
@@ -147,7 +256,70 @@ int lme_backward(const T* A, const T* B, const T* out, const T* gout, T* dA, T* 
   return 0;
 }
 
+
+// Group size: enough batch elements per CTA for ~512 outputs, within the shared-memory budget; G*x multiples of 4.
+static int lme_batched_group(size_t per_elem_bytes, int work_per_elem, long long NB, size_t* smem) {
+  const size_t budget = 96 * 1024;
+  if (per_elem_bytes * 4 > budget) {
+    if (per_elem_bytes > budget) return 0;
+    *smem = per_elem_bytes;  // a single element per CTA: every block starts at the tensor base + multiple of its size
+    return 1;
+  }
+  int G = (512 + work_per_elem - 1) / work_per_elem;
+  G = (G + 3) & ~3;
+  while ((size_t)G * per_elem_bytes > budget) G -= 4;
+  if (G < 4) G = 4;
+  if ((long long)G > NB) G = (int)((NB + 3) & ~3LL);
+  *smem = (size_t)G * per_elem_bytes;
+  return G;
+}
+
+template <typename T>
+int lme_batched_forward(const T* A, const T* B, T* out, long long NB, int Th, int R, int I, cudaStream_t st) {
+  size_t smem = 0;
+  int G = lme_batched_group(sizeof(T) * ((size_t)Th * R + (size_t)R * I), Th * I, NB, &smem);
+  if (G == 0)
+    return dctn_set_error(DCTN_ERR_UNSUPPORTED, "logmatmulexp_batched: a (%d x %d) x (%d x %d) pair does not fit shared memory; use the 2-D entry per element", Th, R, R, I);
+  // G == 1 with odd block sizes: stage_in falls back to scalar loads on its own (alignment test)
+  static bool attr_done[2] = {false, false};
+  if (!attr_done[sizeof(T) == 8]) {
+    DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(lme_batched_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_done[sizeof(T) == 8] = true;
+  }
+  long long groups = (NB + G - 1) / G;
+  int grid = (int)(groups < 148LL * 16 ? groups : 148LL * 16);
+  lme_batched_fwd_kernel<T><<<grid, 256, smem, st>>>(A, B, out, NB, Th, R, I, G);
+  dctn_count_launch();
+  DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+int lme_batched_backward(const T* A, const T* B, const T* out, const T* gout, T* dA, T* dB, long long NB, int Th, int R,
+                         int I, cudaStream_t st) {
+  size_t smem = 0;
+  int work = Th * R > R * I ? Th * R : R * I;
+  int G = lme_batched_group(sizeof(T) * ((size_t)Th * R + (size_t)R * I + 2 * (size_t)Th * I), work, NB, &smem);
+  if (G == 0)
+    return dctn_set_error(DCTN_ERR_UNSUPPORTED, "logmatmulexp_batched backward: a (%d x %d) x (%d x %d) pair does not fit shared memory", Th, R, R, I);
+  static bool attr_done[2] = {false, false};
+  if (!attr_done[sizeof(T) == 8]) {
+    DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(lme_batched_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_done[sizeof(T) == 8] = true;
+  }
+  long long groups = (NB + G - 1) / G;
+  int grid = (int)(groups < 148LL * 16 ? groups : 148LL * 16);
+  lme_batched_bwd_kernel<T><<<grid, 256, smem, st>>>(A, B, out, gout, dA, dB, NB, Th, R, I, G);
+  dctn_count_launch();
+  DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  return 0;
+}
+
 template int lme_forward<float>(const float*, const float*, float*, int, int, int, cudaStream_t);
 template int lme_forward<double>(const double*, const double*, double*, int, int, int, cudaStream_t);
 template int lme_backward<float>(const float*, const float*, const float*, const float*, float*, float*, int, int, int, cudaStream_t);
 template int lme_backward<double>(const double*, const double*, const double*, const double*, double*, double*, int, int, int, cudaStream_t);
+template int lme_batched_forward<float>(const float*, const float*, float*, long long, int, int, int, cudaStream_t);
+template int lme_batched_forward<double>(const double*, const double*, double*, long long, int, int, int, cudaStream_t);
+template int lme_batched_backward<float>(const float*, const float*, const float*, const float*, float*, float*, long long, int, int, int, cudaStream_t);
+template int lme_batched_backward<double>(const double*, const double*, const double*, const double*, double*, double*, long long, int, int, int, cudaStream_t);

@@ -48,6 +48,57 @@ class _LogMatMulExp(torch.autograd.Function):
         return dA, dB
 
 
+class _LogMatMulExpBatched(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, log_A: Tensor, log_B: Tensor) -> Tensor:
+        nb, theta, R = log_A.shape
+        I = log_B.shape[2]
+        a = log_A.detach().contiguous()
+        b = log_B.detach().contiguous()
+        out = torch.empty((nb, theta, I), dtype=a.dtype, device=a.device)
+        with torch.cuda.device(a.device):
+            rc = _lib.lib().dctn_logmatmulexp_batched_forward(
+                a.data_ptr(), b.data_ptr(), out.data_ptr(), nb, theta, R, I, _DTYPES[a.dtype],
+                torch.cuda.current_stream().cuda_stream,
+            )
+        _lib.check(rc, "dctn_logmatmulexp_batched_forward")
+        ctx.save_for_backward(a, b, out)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout: Tensor):
+        a, b, out = ctx.saved_tensors
+        nb, theta, R = a.shape
+        I = b.shape[2]
+        gout = gout.contiguous()
+        dA = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        dB = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(a.device):
+            rc = _lib.lib().dctn_logmatmulexp_batched_backward(
+                a.data_ptr(), b.data_ptr(), out.data_ptr(), gout.data_ptr(),
+                dA.data_ptr() if dA is not None else None, dB.data_ptr() if dB is not None else None,
+                nb, theta, R, I, _DTYPES[a.dtype], torch.cuda.current_stream().cuda_stream,
+            )
+        _lib.check(rc, "dctn_logmatmulexp_batched_backward")
+        return dA, dB
+
+
+def logmatmulexp_batched(log_A: Tensor, log_B: Tensor, /) -> Tensor:
+    """log_A: (..., Theta, R), log_B: (..., R, I) with equal leading dims -> (..., Theta, I), one log-space product
+    per leading index.  ADDITIONAL entry (the reference's logmatmulexp is 2-D only, dctn/logmatmulexp.py:8-10): the
+    ring step of a ConvSBS contraction in log space (dctn/conv_sbs.py:282-303 does it in linear space)."""
+    assert log_A.ndim >= 3 and log_A.ndim == log_B.ndim
+    assert log_A.shape[:-2] == log_B.shape[:-2] and log_A.shape[-1] == log_B.shape[-2]
+    if not (log_A.is_cuda and log_B.is_cuda):
+        raise RuntimeError("dctn_b200.logmatmulexp_batched runs on CUDA tensors only (no CPU fallback)")
+    if log_A.dtype not in _DTYPES or log_A.dtype != log_B.dtype:
+        raise TypeError(f"logmatmulexp_batched supports matching float32/float64 inputs, got {log_A.dtype} and {log_B.dtype}")
+    lead = log_A.shape[:-2]
+    out = _LogMatMulExpBatched.apply(log_A.reshape(-1, *log_A.shape[-2:]), log_B.reshape(-1, *log_B.shape[-2:]))
+    return out.reshape(*lead, log_A.shape[-2], log_B.shape[-1])
+
+
 def logmatmulexp(log_A: Tensor, log_B: Tensor, /) -> Tensor:
     """log_A: Theta x R, log_B: R x I -> (log_A.exp() @ log_B.exp()).log(), stable forward and backward."""
     theta, R = log_A.shape  # ValueError for non 2-D input, like the reference's unpacking

@@ -128,6 +128,16 @@ int dctn_logmatmulexp_forward(const void* log_A, const void* log_B, void* out, i
 int dctn_logmatmulexp_backward(const void* log_A, const void* log_B, const void* out, const void* gout,
                                void* dA, void* dB, int Theta, int R, int I, int dtype, void* stream);
 
+/* Batched small-matrix form: log_A [batch][Theta][R], log_B [batch][R][I] -> out [batch][Theta][I], one product per
+ * batch element.  ADDITIONAL entry: the reference's logmatmulexp asserts 2-D (dctn/logmatmulexp.py:8-10)
+ * and contracts ConvSBS bond-matrix rings in linear space (dctn/conv_sbs.py:258-304); this is that ring step in log
+ * space, one batch element per (image, window).  DCTN_ERR_UNSUPPORTED when one pair exceeds 96 KiB of shared memory. */
+int dctn_logmatmulexp_batched_forward(const void* log_A, const void* log_B, void* out, long long batch, int Theta,
+                                      int R, int I, int dtype, void* stream);
+int dctn_logmatmulexp_batched_backward(const void* log_A, const void* log_B, const void* out, const void* gout,
+                                       void* dA, void* dB, long long batch, int Theta, int R, int I, int dtype,
+                                       void* stream);
+
 /* Host-buffer convenience entry (end-to-end path): copies x and core from HOST memory, runs the
  * forward on `stream`, copies `out` back and synchronises the stream.  All three pointers are host
  * pointers; device scratch of dctn_eps_forward_host_device_bytes() bytes is passed by the caller. */

@@ -172,6 +172,50 @@ def logmatmulexp_grads(log_A: Tensor, log_B: Tensor, gout: Tensor) -> Tuple[Tens
     return a.grad, b.grad
 
 
+def logmatmulexp_batched(log_A: Tensor, log_B: Tensor) -> Tensor:
+    """One dctn/logmatmulexp.py:5-14 product per leading index: (NB, T, R) x (NB, R, I) -> (NB, T, I)."""
+    return torch.logsumexp(log_A.unsqueeze(3) + log_B.unsqueeze(1), dim=2)
+
+
+# ----------------------------------------------------------------------------- ConvSBS (linear and log space)
+def conv_sbs_forward(cores: Sequence[Tensor], positions: Sequence[Tuple[int, int]], x: Tensor) -> Tensor:
+    """dctn/conv_sbs.py:258-304 in LINEAR space.  cores[c]: (O, L, R, Q, ..., Q) (C input dims); x: (C, B, H, W, Q).
+    Per core: bond matrices M_c[b,h,w,o,l,r] (:269-281); then the ring product over bonds, keeping every core's
+    out_quantum dim, traced over the closing bond (:282-303); out dims flattened in core order (:304)."""
+    C, B, H, W, Q = x.shape
+    hs = [p[0] for p in positions]
+    ws = [p[1] for p in positions]
+    Ho, Wo = H - max(hs), W - max(ws)
+    P = B * Ho * Wo
+    T = None  # (P, L0, Otot, R_c)
+    for core, (ph, pw) in zip(cores, positions):
+        O, L, R = core.shape[:3]
+        kr = khatri_rao([x[c][:, ph : ph + Ho, pw : pw + Wo].reshape(P, Q) for c in range(C)])  # (P, Q^C)
+        M = torch.einsum("pi,olri->polr", kr, core.reshape(O, L, R, -1))
+        T = M.permute(0, 2, 1, 3) if T is None else torch.einsum("pxyl,polr->pxyor", T, M).reshape(P, T.shape[1], -1, R)
+    return torch.einsum("pxyx->py", T).reshape(B, Ho, Wo, -1)
+
+
+def conv_sbs_log_forward(log_cores: Sequence[Tensor], positions: Sequence[Tuple[int, int]], log_x: Tensor) -> Tensor:
+    """log(conv_sbs_forward(exp(log_cores), positions, exp(log_x))) computed with logsumexp only."""
+    C, B, H, W, Q = log_x.shape
+    hs = [p[0] for p in positions]
+    ws = [p[1] for p in positions]
+    Ho, Wo = H - max(hs), W - max(ws)
+    P = B * Ho * Wo
+    T = None  # (P, L0*Otot, R_c)
+    L0 = log_cores[0].shape[1]
+    for core, (ph, pw) in zip(log_cores, positions):
+        O, L, R = core.shape[:3]
+        kr = log_x[0][:, ph : ph + Ho, pw : pw + Wo].reshape(P, Q)
+        for c in range(1, C):
+            kr = (kr.unsqueeze(2) + log_x[c][:, ph : ph + Ho, pw : pw + Wo].reshape(P, 1, Q)).reshape(P, -1)
+        M = logmatmulexp(kr, core.reshape(O, L, R, -1).permute(3, 1, 0, 2).reshape(-1, L * O * R)).reshape(P, L, O * R)
+        T = M.reshape(P, L * O, R) if T is None else logmatmulexp_batched(T, M).reshape(P, -1, R)
+    T = T.reshape(P, L0, -1, L0)
+    return torch.logsumexp(torch.diagonal(T, dim1=1, dim2=3), dim=-1).reshape(B, Ho, Wo, -1)
+
+
 # ----------------------------------------------------------------------------- helpers
 def rel_err(a: Tensor, b: Tensor) -> float:
     """Frobenius-relative error ||a-b|| / ||b|| in float64."""

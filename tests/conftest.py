@@ -46,3 +46,11 @@ EPS_GOLDEN_CASES = [
 ]
 LME_GOLDEN_CASES = ["lme_small", "lme_64", "lme_ragged", "lme_scale150"]
 CONVSBS_CASES = ["convsbs_as_eps_perm0", "convsbs_as_eps_perm7", "convsbs_as_eps_perm23"]
+CONVSBS_LOG_CASES = ["convsbs_log_2x2_ring", "convsbs_log_2x2_perm", "convsbs_log_3x3_snake_ring", "convsbs_log_3x3_snake_open"]
+LME_BATCHED_CASES = ["lme_batched_small", "lme_batched_r8", "lme_batched_scale150"]
+
+
+def convsbs_log_case(g):
+    """(log_cores, positions, log_x) of a convsbs_log_* golden file."""
+    n = len(g["outs"])
+    return [g[f"log_core{i}"] for i in range(n)], [tuple(int(v) for v in p) for p in g["positions"]], g["log_x"]

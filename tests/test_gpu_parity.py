@@ -236,6 +236,123 @@ def test_logmatmulexp_chain_and_extremes():
     assert torch.allclose(out, B[0].expand(4, 3), atol=1e-6)
 
 
+# ---------------------------------------------------------------- batched logmatmulexp, ConvSBS in log space (8f-4)
+from conftest import CONVSBS_LOG_CASES, LME_BATCHED_CASES, convsbs_log_case  # noqa: E402
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("name", LME_BATCHED_CASES)
+def test_logmatmulexp_batched_golden(name, dtype):
+    """One reference logmatmulexp call per batch element (dctn/logmatmulexp.py:5-14) vs the batched kernel."""
+    from dctn_b200.logmatmulexp import logmatmulexp_batched
+
+    g = load_golden(name)
+    A = g["log_A"].to(DEV, dtype).requires_grad_(True)
+    B = g["log_B"].to(DEV, dtype).requires_grad_(True)
+    if dtype == torch.float32:  # reference values on the float32-rounded inputs
+        a64, b64 = A.detach().double().cpu().requires_grad_(True), B.detach().double().cpu().requires_grad_(True)
+        want = O.logmatmulexp_batched(a64, b64)
+        want.backward(g["gout"].float().double())
+        want, want_dA, want_dB = want.detach(), a64.grad, b64.grad
+    else:
+        want, want_dA, want_dB = g["out"], g["dA"], g["dB"]
+    out = logmatmulexp_batched(A, B)
+    out.backward(g["gout"].to(DEV, dtype))
+    tol = TOL[dtype]
+    assert out.shape == want.shape and out.dtype == dtype
+    assert rel_err(out, want) <= tol
+    assert rel_err(A.grad, want_dA) <= tol and rel_err(B.grad, want_dB) <= tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("shape", [(1, 1, 1, 1), (1, 3, 5, 7), (5, 2, 40, 3), (1001, 4, 4, 4), (333, 12, 12, 12),
+                                   (3, 70, 9, 33), (2, 1, 64, 1)])
+def test_logmatmulexp_batched_ragged(shape, dtype):
+    """Group tails, sizes that defeat the 128-bit staging, one element per CTA, leading dims, -inf entries."""
+    from dctn_b200.logmatmulexp import logmatmulexp_batched
+
+    NB, T, R, I = shape
+    gen = torch.Generator().manual_seed(1000 + NB + T)
+    A = (3 * torch.randn(NB, T, R, generator=gen, dtype=torch.float64)).to(dtype)
+    B = (3 * torch.randn(NB, R, I, generator=gen, dtype=torch.float64)).to(dtype)
+    if R > 1:
+        A[:, :, 0] = float("-inf")  # log of a zero column: must not produce NaN
+    gout = torch.randn(NB, T, I, generator=gen, dtype=torch.float64).to(dtype)
+    a64, b64 = A.double().requires_grad_(True), B.double().requires_grad_(True)
+    want = O.logmatmulexp_batched(a64, b64)
+    want.backward(gout.double())
+    Ad, Bd = A.to(DEV).requires_grad_(True), B.to(DEV).requires_grad_(True)
+    out = logmatmulexp_batched(Ad, Bd)
+    out.backward(gout.to(DEV))
+    assert torch.isfinite(out).all() and torch.isfinite(Ad.grad).all() and torch.isfinite(Bd.grad).all()
+    assert rel_err(out, want) <= TOL[dtype]
+    assert rel_err(Ad.grad, a64.grad) <= TOL[dtype] and rel_err(Bd.grad, b64.grad) <= TOL[dtype]
+    if NB > 1:  # extra leading dims are flattened
+        out2 = logmatmulexp_batched(Ad.detach().reshape(1, NB, T, R), Bd.detach().reshape(1, NB, R, I))
+        assert out2.shape == (1, NB, T, I) and torch.equal(out2[0], out.detach())
+
+
+def test_logmatmulexp_batched_errors():
+    from dctn_b200.logmatmulexp import logmatmulexp_batched
+
+    with pytest.raises(RuntimeError):  # CPU tensors: no fallback
+        logmatmulexp_batched(torch.zeros(2, 3, 3), torch.zeros(2, 3, 3))
+    with pytest.raises(RuntimeError, match="shared memory"):  # one pair larger than a CTA's shared memory
+        logmatmulexp_batched(torch.zeros(2, 200, 200, device=DEV), torch.zeros(2, 200, 200, device=DEV))
+    with pytest.raises(AssertionError):
+        logmatmulexp_batched(torch.zeros(2, 3, 4, device=DEV), torch.zeros(2, 3, 4, device=DEV))
+
+
+def test_logmatmulexp_batched_full_size_identities():
+    """Config 5 extension size: one 8x8 bond-matrix product per window of a 28x28 image with a 3x3 string, batch 2048."""
+    from dctn_b200.logmatmulexp import logmatmulexp_batched
+
+    NB, r = 2048 * 26 * 26, 8
+    gen = torch.Generator(device=DEV).manual_seed(7)
+    A = 2 * torch.randn(NB, r, r, device=DEV, generator=gen)
+    B = 2 * torch.randn(NB, r, r, device=DEV, generator=gen)
+    out = logmatmulexp_batched(A, B)
+    assert torch.equal(out, logmatmulexp_batched(A, B))  # deterministic
+    eye = torch.full((r, r), float("-inf"), device=DEV)
+    eye.fill_diagonal_(0.0)
+    assert torch.equal(logmatmulexp_batched(A, eye.expand(NB, r, r).contiguous()), A)  # log-identity is neutral
+    shift = torch.randn(NB, 1, 1, device=DEV)
+    assert torch.allclose(logmatmulexp_batched(A + shift, B), out + shift, rtol=0, atol=2e-5)  # shift equivariance
+    # spot-check 4096 elements against the float64 oracle
+    idx = torch.randint(0, NB, (4096,), device=DEV, generator=gen)
+    want = O.logmatmulexp_batched(A[idx].double().cpu(), B[idx].double().cpu())
+    assert rel_err(out[idx], want) <= TOL[torch.float32]
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("name", CONVSBS_LOG_CASES)
+def test_conv_sbs_log_golden(name, dtype):
+    """log of the reference's ConvSBS.forward (dctn/conv_sbs.py:258-304) and gradients w.r.t. log cores / log input."""
+    from dctn_b200.conv_sbs_log import conv_sbs_log_forward
+    from dctn_b200.pos2d import Pos2D
+
+    g = load_golden(name)
+    log_cores, positions, log_x = convsbs_log_case(g)
+    lc = [c.to(DEV, dtype).requires_grad_(True) for c in log_cores]
+    lx = log_x.to(DEV, dtype).requires_grad_(True)
+    if dtype == torch.float32:
+        lc64 = [c.detach().double().cpu().requires_grad_(True) for c in lc]
+        lx64 = lx.detach().double().cpu().requires_grad_(True)
+        want = O.conv_sbs_log_forward(lc64, positions, lx64)
+        want.backward(g["gout"].float().double())
+        want, want_dx, want_dc = want.detach(), lx64.grad, [c.grad for c in lc64]
+    else:
+        want, want_dx, want_dc = g["log_out"], g["dlog_x"], [g[f"dlog_core{i}"] for i in range(len(lc))]
+    out = conv_sbs_log_forward(lc, tuple(Pos2D(*p) for p in positions), lx)
+    out.backward(g["gout"].to(DEV, dtype))
+    tol = TOL[dtype]
+    assert out.shape == want.shape
+    assert rel_err(out, want) <= tol
+    assert rel_err(lx.grad, want_dx) <= tol
+    for got, w in zip(lc, want_dc):
+        assert rel_err(got.grad, w) <= tol
+
+
 # ---------------------------------------------------------------- full BASELINE sizes, oracle-free identities
 FULL_LAYERS = [
     # (name, B, H, W, Q, K, O)  — config 2: layer 1 and layer 2 at batch 512; config 1 at batch 128 (float64)

@@ -99,3 +99,36 @@ def test_oracle_against_live_reference():
     assert torch.allclose(O.eps_4step(core.detach(), x.detach()), out, **TOL)
     dcore, dx = O.eps_grads(core, x, gout)
     assert torch.allclose(dcore, core.grad, **TOL) and torch.allclose(dx, x.grad, **TOL)
+
+
+# ---------------------------------------------------------------- ConvSBS in log space, batched logmatmulexp
+from conftest import CONVSBS_LOG_CASES, LME_BATCHED_CASES, convsbs_log_case  # noqa: E402
+
+
+@pytest.mark.parametrize("name", CONVSBS_LOG_CASES)
+def test_conv_sbs_oracle_linear_and_log(name):
+    """The reference's ConvSBS.forward (dctn/conv_sbs.py:258-304) on positive cores/inputs, its log, and the
+    gradients w.r.t. the LOG cores and LOG input."""
+    g = load_golden(name)
+    log_cores, positions, log_x = convsbs_log_case(g)
+    lin = O.conv_sbs_forward([c.exp() for c in log_cores], positions, log_x.exp())
+    assert torch.allclose(lin.log(), g["log_out"], rtol=1e-10, atol=1e-10)
+    lc = [c.clone().requires_grad_(True) for c in log_cores]
+    lx = log_x.clone().requires_grad_(True)
+    out = O.conv_sbs_log_forward(lc, positions, lx)
+    assert torch.allclose(out, g["log_out"], rtol=1e-10, atol=1e-10)
+    out.backward(g["gout"])
+    assert torch.allclose(lx.grad, g["dlog_x"], rtol=1e-8, atol=1e-10)
+    for i, c in enumerate(lc):
+        assert torch.allclose(c.grad, g[f"dlog_core{i}"], rtol=1e-8, atol=1e-10)
+
+
+@pytest.mark.parametrize("name", LME_BATCHED_CASES)
+def test_logmatmulexp_batched_oracle(name):
+    g = load_golden(name)
+    A = g["log_A"].clone().requires_grad_(True)
+    B = g["log_B"].clone().requires_grad_(True)
+    out = O.logmatmulexp_batched(A, B)
+    assert torch.allclose(out, g["out"], rtol=1e-12, atol=1e-12)
+    out.backward(g["gout"])
+    assert torch.allclose(A.grad, g["dA"], rtol=1e-10, atol=1e-12) and torch.allclose(B.grad, g["dB"], rtol=1e-10, atol=1e-12)
