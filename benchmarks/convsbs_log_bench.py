@@ -67,7 +67,11 @@ def main():
         for m in mats:
             m.requires_grad_(True)
         t_fb = time_cuda(fwdbwd, args.iters)
-        t_rfb = time_cuda(lambda: fwdbwd(ref_lme_batched), max(1, args.iters // 2))
+        try:
+            t_rfb = time_cuda(lambda: fwdbwd(ref_lme_batched), max(1, args.iters // 2))
+        except torch.OutOfMemoryError:  # autograd keeps 8 materialised (NB, r, r, r) tensors
+            t_rfb = None
+            torch.cuda.empty_cache()
         exps_f = (S - 1) * NB * r ** 3
         bytes_f = (S - 1) * NB * 3 * r * r * 4
         row = dict(bond=r, windows=NB, cores=S, dtype="float32", ours_fwd_ms=t_f, ours_fwdbwd_ms=t_fb,

@@ -227,6 +227,126 @@ __global__ void __launch_bounds__(256) lme_batched_bwd_kernel(const T* __restric
     __syncthreads();
   }
 }
+
+// ---- float32, I % 4 == 0: register-tiled variants.  One thread = one row t and four consecutive columns i: the A row is
+// read once for four outputs, B comes in as 128-bit shared-memory loads, the R sums a+b stay in registers between the max
+// pass and the exp pass (R is a template parameter), and exp is one MUFU.EX2 on (v - m) * log2(e).  The difference v - m
+// is formed BEFORE the scaling so that the dominant term is exactly 2^0 (backward recomputes exp(a + b - out) and a
+// forward that is off by one rounding of m*log2(e) would show up there on the scale-150 inputs).
+__device__ __forceinline__ float ex2_approx(float v) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+
+template <int R>
+__global__ void __launch_bounds__(256) lme_batched_fwd_vec_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                                  float* __restrict__ out, long long NB, int Th, int I,
+                                                                  int G) {
+  extern __shared__ int4 lme_smem4[];
+  float* As = reinterpret_cast<float*>(lme_smem4);  // [G][Th][R]
+  float* Bs = As + (size_t)G * Th * R;              // [G][R][I]
+  const int tr = Th * R, ri = R * I, ti = Th * I, I4 = I >> 2, w_per = Th * I4;
+  for (long long p0 = (long long)blockIdx.x * G; p0 < NB; p0 += (long long)gridDim.x * G) {
+    const int g = (int)((NB - p0) < G ? (NB - p0) : G);
+    stage_in(As, A + p0 * tr, g * tr);
+    stage_in(Bs, B + p0 * ri, g * ri);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < g * w_per; idx += blockDim.x) {
+      const int gi = idx / w_per, rem = idx - gi * w_per, t = rem / I4, i4 = rem - t * I4;
+      const float* a = As + gi * tr + t * R;
+      const float4* b = reinterpret_cast<const float4*>(Bs + gi * ri) + i4;
+      float4 v[R];
+      float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float ar = a[r];
+        const float4 br = b[r * I4];
+        v[r] = make_float4(ar + br.x, ar + br.y, ar + br.z, ar + br.w);
+        m.x = fmaxf(m.x, v[r].x); m.y = fmaxf(m.y, v[r].y); m.z = fmaxf(m.z, v[r].z); m.w = fmaxf(m.w, v[r].w);
+      }
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        s.x += ex2_approx((v[r].x - m.x) * kLog2e); s.y += ex2_approx((v[r].y - m.y) * kLog2e);
+        s.z += ex2_approx((v[r].z - m.z) * kLog2e); s.w += ex2_approx((v[r].w - m.w) * kLog2e);
+      }
+      // m = -inf (empty sum) or +inf: v - m is NaN, s is NaN; the result is m itself
+      float4 res;
+      res.x = (fabsf(m.x) == INFINITY) ? m.x : m.x + logf(s.x);
+      res.y = (fabsf(m.y) == INFINITY) ? m.y : m.y + logf(s.y);
+      res.z = (fabsf(m.z) == INFINITY) ? m.z : m.z + logf(s.z);
+      res.w = (fabsf(m.w) == INFINITY) ? m.w : m.w + logf(s.w);
+      reinterpret_cast<float4*>(out + p0 * ti)[idx] = res;  // idx enumerates (gi, t, i4) in memory order
+    }
+    __syncthreads();
+  }
+}
+
+// Backward, float32, I % 4 == 0.  dA: one thread per (t, r), 128-bit loads of the out / gout / B rows; dB: one thread per
+// (r, four columns), walks the rows t.  Same exactness rule: a + b - out first, then the scaling.
+__global__ void __launch_bounds__(256) lme_batched_bwd_vec_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                                  const float* __restrict__ out,
+                                                                  const float* __restrict__ gout, float* __restrict__ dA,
+                                                                  float* __restrict__ dB, long long NB, int Th, int R,
+                                                                  int I, int G) {
+  extern __shared__ int4 lme_smem4[];
+  const int tr = Th * R, ri = R * I, ti = Th * I, I4 = I >> 2;
+  float* As = reinterpret_cast<float*>(lme_smem4);
+  float* Bs = As + (size_t)G * tr;
+  float* Os = Bs + (size_t)G * ri;
+  float* Gs = Os + (size_t)G * ti;
+  for (long long p0 = (long long)blockIdx.x * G; p0 < NB; p0 += (long long)gridDim.x * G) {
+    const int g = (int)((NB - p0) < G ? (NB - p0) : G);
+    stage_in(As, A + p0 * tr, g * tr);
+    stage_in(Bs, B + p0 * ri, g * ri);
+    stage_in(Os, out + p0 * ti, g * ti);
+    stage_in(Gs, gout + p0 * ti, g * ti);
+    __syncthreads();
+    if (dA) {
+      for (int idx = threadIdx.x; idx < g * tr; idx += blockDim.x) {
+        const int gi = idx / tr, rem = idx - gi * tr, t = rem / R, r = rem - t * R;
+        const float a = As[idx];
+        const float4* b = reinterpret_cast<const float4*>(Bs + gi * ri + r * I);
+        const float4* o = reinterpret_cast<const float4*>(Os + gi * ti + t * I);
+        const float4* gg = reinterpret_cast<const float4*>(Gs + gi * ti + t * I);
+        float acc = 0.f;
+#pragma unroll 2
+        for (int i = 0; i < I4; ++i) {
+          const float4 bv = b[i], ov = o[i], gv = gg[i];
+          if (gv.x != 0.f) acc += gv.x * ex2_approx(((a + bv.x) - ov.x) * kLog2e);
+          if (gv.y != 0.f) acc += gv.y * ex2_approx(((a + bv.y) - ov.y) * kLog2e);
+          if (gv.z != 0.f) acc += gv.z * ex2_approx(((a + bv.z) - ov.z) * kLog2e);
+          if (gv.w != 0.f) acc += gv.w * ex2_approx(((a + bv.w) - ov.w) * kLog2e);
+        }
+        dA[p0 * tr + idx] = acc;
+      }
+    }
+    if (dB) {
+      const int w_per = R * I4;
+      for (int idx = threadIdx.x; idx < g * w_per; idx += blockDim.x) {
+        const int gi = idx / w_per, rem = idx - gi * w_per, r = rem / I4, i4 = rem - r * I4;
+        const float4 bv = reinterpret_cast<const float4*>(Bs + gi * ri)[rem];
+        const float* a = As + gi * tr + r;
+        const float4* o = reinterpret_cast<const float4*>(Os + gi * ti) + i4;
+        const float4* gg = reinterpret_cast<const float4*>(Gs + gi * ti) + i4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+        for (int t = 0; t < Th; ++t) {
+          const float av = a[t * R];
+          const float4 ov = o[t * I4], gv = gg[t * I4];
+          if (gv.x != 0.f) acc.x += gv.x * ex2_approx(((av + bv.x) - ov.x) * kLog2e);
+          if (gv.y != 0.f) acc.y += gv.y * ex2_approx(((av + bv.y) - ov.y) * kLog2e);
+          if (gv.z != 0.f) acc.z += gv.z * ex2_approx(((av + bv.z) - ov.z) * kLog2e);
+          if (gv.w != 0.f) acc.w += gv.w * ex2_approx(((av + bv.w) - ov.w) * kLog2e);
+        }
+        reinterpret_cast<float4*>(dB + p0 * ri)[idx] = acc;
+      }
+    }
+    __syncthreads();
+  }
+}
 }  // namespace
 
 template <typename T>
@@ -274,10 +394,39 @@ static int lme_batched_group(size_t per_elem_bytes, int work_per_elem, long long
   return G;
 }
 
+template <int R>
+static int launch_fwd_vec(const float* A, const float* B, float* out, long long NB, int Th, int I, int G, size_t smem,
+                          cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(lme_batched_fwd_vec_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_done = true;
+  }
+  long long groups = (NB + G - 1) / G;
+  int grid = (int)(groups < 148LL * 16 ? groups : 148LL * 16);
+  lme_batched_fwd_vec_kernel<R><<<grid, 256, smem, st>>>(A, B, out, NB, Th, I, G);
+  dctn_count_launch();
+  DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  return 0;
+}
+
+// float32, I % 4 == 0, R <= 16, groups of 4 elements fit: the register-tiled kernels
+static bool lme_vec_ok(size_t elem_size, int R, int I, int G) { return elem_size == 4 && (I & 3) == 0 && R <= 16 && (G & 3) == 0; }
+
 template <typename T>
 int lme_batched_forward(const T* A, const T* B, T* out, long long NB, int Th, int R, int I, cudaStream_t st) {
   size_t smem = 0;
-  int G = lme_batched_group(sizeof(T) * ((size_t)Th * R + (size_t)R * I), Th * I, NB, &smem);
+  int G = lme_batched_group(sizeof(T) * ((size_t)Th * R + (size_t)R * I), (sizeof(T) == 4 && (I & 3) == 0 && R <= 16) ? Th * I / 4 : Th * I, NB, &smem);
+  if (G && lme_vec_ok(sizeof(T), R, I, G)) {
+    const float *a = (const float*)A, *b = (const float*)B;
+    float* o = (float*)out;
+    switch (R) {
+#define LME_CASE(RR) case RR: return launch_fwd_vec<RR>(a, b, o, NB, Th, I, G, smem, st);
+      LME_CASE(1) LME_CASE(2) LME_CASE(3) LME_CASE(4) LME_CASE(5) LME_CASE(6) LME_CASE(7) LME_CASE(8)
+      LME_CASE(9) LME_CASE(10) LME_CASE(11) LME_CASE(12) LME_CASE(13) LME_CASE(14) LME_CASE(15) LME_CASE(16)
+#undef LME_CASE
+    }
+  }
   if (G == 0)
     return dctn_set_error(DCTN_ERR_UNSUPPORTED, "logmatmulexp_batched: a (%d x %d) x (%d x %d) pair does not fit shared memory; use the 2-D entry per element", Th, R, R, I);
   // G == 1 with odd block sizes: stage_in falls back to scalar loads on its own (alignment test)
@@ -309,6 +458,18 @@ int lme_batched_backward(const T* A, const T* B, const T* out, const T* gout, T*
   }
   long long groups = (NB + G - 1) / G;
   int grid = (int)(groups < 148LL * 16 ? groups : 148LL * 16);
+  if (lme_vec_ok(sizeof(T), 1, I, G)) {
+    static bool vec_attr_done = false;
+    if (!vec_attr_done) {
+      DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(lme_batched_bwd_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      vec_attr_done = true;
+    }
+    lme_batched_bwd_vec_kernel<<<grid, 256, smem, st>>>((const float*)A, (const float*)B, (const float*)out, (const float*)gout,
+                                                        (float*)dA, (float*)dB, NB, Th, R, I, G);
+    dctn_count_launch();
+    DCTN_CUDA_CHECK_RET(cudaGetLastError());
+    return 0;
+  }
   lme_batched_bwd_kernel<T><<<grid, 256, smem, st>>>(A, B, out, gout, dA, dB, NB, Th, R, I, G);
   dctn_count_launch();
   DCTN_CUDA_CHECK_RET(cudaGetLastError());

@@ -266,7 +266,7 @@ def test_logmatmulexp_batched_golden(name, dtype):
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 @pytest.mark.parametrize("shape", [(1, 1, 1, 1), (1, 3, 5, 7), (5, 2, 40, 3), (1001, 4, 4, 4), (333, 12, 12, 12),
-                                   (3, 70, 9, 33), (2, 1, 64, 1)])
+                                   (3, 70, 9, 33), (2, 1, 64, 1), (130, 8, 16, 8), (9, 24, 12, 36), (77, 5, 7, 20)])
 def test_logmatmulexp_batched_ragged(shape, dtype):
     """Group tails, sizes that defeat the 128-bit staging, one element per CTA, leading dims, -inf entries."""
     from dctn_b200.logmatmulexp import logmatmulexp_batched
@@ -278,7 +278,7 @@ def test_logmatmulexp_batched_ragged(shape, dtype):
     if R > 1:
         A[:, :, 0] = float("-inf")  # log of a zero column: must not produce NaN
     gout = torch.randn(NB, T, I, generator=gen, dtype=torch.float64).to(dtype)
-    a64, b64 = A.double().requires_grad_(True), B.double().requires_grad_(True)
+    a64, b64 = A.double().clone().requires_grad_(True), B.double().clone().requires_grad_(True)
     want = O.logmatmulexp_batched(a64, b64)
     want.backward(gout.double())
     Ad, Bd = A.to(DEV).requires_grad_(True), B.to(DEV).requires_grad_(True)
