@@ -141,6 +141,23 @@ __device__ __forceinline__ void stage_in(T* __restrict__ dst, const T* __restric
   }
 }
 
+// idx = (gi * NA + a) * NB + b walked in steps of blockDim.x without divisions (the decomposition of a thread's first
+// index does not depend on the group, so it is computed once per kernel; two integer divisions per work item were a
+// quarter of the instructions of the register-tiled forward).
+struct Walk3 {
+  int gi, a, b, sg, sa, sb, NA, NB;
+  __device__ __forceinline__ void init(int idx, int step, int na, int nb) {
+    NA = na; NB = nb;
+    b = idx % nb; int q = idx / nb; a = q % na; gi = q / na;
+    sb = step % nb; q = step / nb; sa = q % na; sg = q / na;
+  }
+  __device__ __forceinline__ void next() {
+    b += sb; if (b >= NB) { b -= NB; ++a; }
+    a += sa; if (a >= NA) { a -= NA; ++gi; }
+    gi += sg;
+  }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(256) lme_batched_fwd_kernel(const T* __restrict__ A, const T* __restrict__ B,
                                                               T* __restrict__ out, long long NB, int Th, int R, int I,
@@ -149,13 +166,16 @@ __global__ void __launch_bounds__(256) lme_batched_fwd_kernel(const T* __restric
   T* As = reinterpret_cast<T*>(lme_smem4);  // [G][Th][R]
   T* Bs = As + (size_t)G * Th * R;          // [G][R][I]   (G*Th*R is kept a multiple of 4 by the host)
   const int tr = Th * R, ri = R * I, ti = Th * I;
+  Walk3 w0;
+  w0.init(threadIdx.x, blockDim.x, Th, I);
   for (long long p0 = (long long)blockIdx.x * G; p0 < NB; p0 += (long long)gridDim.x * G) {
     const int g = (int)((NB - p0) < G ? (NB - p0) : G);
     stage_in(As, A + p0 * tr, g * tr);
     stage_in(Bs, B + p0 * ri, g * ri);
     __syncthreads();
-    for (int idx = threadIdx.x; idx < g * ti; idx += blockDim.x) {
-      const int gi = idx / ti, rem = idx - gi * ti, t = rem / I, i = rem - t * I;
+    Walk3 w = w0;
+    for (int idx = threadIdx.x; idx < g * ti; idx += blockDim.x, w.next()) {
+      const int gi = w.gi, t = w.a, i = w.b;
       const T* a = As + gi * tr + t * R;
       const T* b = Bs + gi * ri + i;
       T m = neg_inf<T>();
@@ -187,6 +207,9 @@ __global__ void __launch_bounds__(256) lme_batched_bwd_kernel(const T* __restric
   T* Bs = As + (size_t)G * tr;
   T* Os = Bs + (size_t)G * ri;
   T* Gs = Os + (size_t)G * ti;
+  Walk3 wa0, wb0;
+  wa0.init(threadIdx.x, blockDim.x, Th, R);
+  wb0.init(threadIdx.x, blockDim.x, R, I);
   for (long long p0 = (long long)blockIdx.x * G; p0 < NB; p0 += (long long)gridDim.x * G) {
     const int g = (int)((NB - p0) < G ? (NB - p0) : G);
     stage_in(As, A + p0 * tr, g * tr);
@@ -195,8 +218,9 @@ __global__ void __launch_bounds__(256) lme_batched_bwd_kernel(const T* __restric
     stage_in(Gs, gout + p0 * ti, g * ti);
     __syncthreads();
     if (dA) {
-      for (int idx = threadIdx.x; idx < g * tr; idx += blockDim.x) {
-        const int gi = idx / tr, rem = idx - gi * tr, t = rem / R, r = rem - t * R;
+      Walk3 w = wa0;
+      for (int idx = threadIdx.x; idx < g * tr; idx += blockDim.x, w.next()) {
+        const int gi = w.gi, t = w.a, r = w.b;
         const T a = As[idx];
         const T* b = Bs + gi * ri + r * I;
         const T* o = Os + gi * ti + t * I;
@@ -210,8 +234,9 @@ __global__ void __launch_bounds__(256) lme_batched_bwd_kernel(const T* __restric
       }
     }
     if (dB) {
-      for (int idx = threadIdx.x; idx < g * ri; idx += blockDim.x) {
-        const int gi = idx / ri, rem = idx - gi * ri, r = rem / I, i = rem - r * I;
+      Walk3 w = wb0;
+      for (int idx = threadIdx.x; idx < g * ri; idx += blockDim.x, w.next()) {
+        const int gi = w.gi, r = w.a, i = w.b;
         const T b = Bs[idx];
         const T* a = As + gi * tr + r;
         const T* o = Os + gi * ti + i;
@@ -238,23 +263,40 @@ __device__ __forceinline__ float ex2_approx(float v) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
   return r;
 }
+__device__ __forceinline__ float lg2_approx(float v) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
 
 template <int R>
-__global__ void __launch_bounds__(256) lme_batched_fwd_vec_kernel(const float* __restrict__ A, const float* __restrict__ B,
+__global__ void __launch_bounds__(256, (R <= 8 ? 5 : (R <= 12 ? 4 : 2))) lme_batched_fwd_vec_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                                   float* __restrict__ out, long long NB, int Th, int I,
                                                                   int G) {
   extern __shared__ int4 lme_smem4[];
   float* As = reinterpret_cast<float*>(lme_smem4);  // [G][Th][R]
   float* Bs = As + (size_t)G * Th * R;              // [G][R][I]
   const int tr = Th * R, ri = R * I, ti = Th * I, I4 = I >> 2, w_per = Th * I4;
+  Walk3 w0;
+  w0.init(threadIdx.x, blockDim.x, Th, I4);
   for (long long p0 = (long long)blockIdx.x * G; p0 < NB; p0 += (long long)gridDim.x * G) {
     const int g = (int)((NB - p0) < G ? (NB - p0) : G);
     stage_in(As, A + p0 * tr, g * tr);
     stage_in(Bs, B + p0 * ri, g * ri);
     __syncthreads();
+    Walk3 w = w0;
     for (int idx = threadIdx.x; idx < g * w_per; idx += blockDim.x) {
-      const int gi = idx / w_per, rem = idx - gi * w_per, t = rem / I4, i4 = rem - t * I4;
+      int gi, t, i4;
+      if constexpr (R <= 8) {   // division-free walk; for larger R its registers cost more than the divisions
+        gi = w.gi; t = w.a; i4 = w.b;
+        w.next();
+      } else {
+        gi = idx / w_per;
+        const int rem = idx - gi * w_per;
+        t = rem / I4; i4 = rem - t * I4;
+      }
       const float* a = As + gi * tr + t * R;
       const float4* b = reinterpret_cast<const float4*>(Bs + gi * ri) + i4;
       float4 v[R];
@@ -274,10 +316,11 @@ __global__ void __launch_bounds__(256) lme_batched_fwd_vec_kernel(const float* _
       }
       // m = -inf (empty sum) or +inf: v - m is NaN, s is NaN; the result is m itself
       float4 res;
-      res.x = (fabsf(m.x) == INFINITY) ? m.x : m.x + logf(s.x);
-      res.y = (fabsf(m.y) == INFINITY) ? m.y : m.y + logf(s.y);
-      res.z = (fabsf(m.z) == INFINITY) ? m.z : m.z + logf(s.z);
-      res.w = (fabsf(m.w) == INFINITY) ? m.w : m.w + logf(s.w);
+      // s is in [1, R]: lg2.approx is good to 2^-22 absolute there
+      res.x = (fabsf(m.x) == INFINITY) ? m.x : fmaf(lg2_approx(s.x), kLn2, m.x);
+      res.y = (fabsf(m.y) == INFINITY) ? m.y : fmaf(lg2_approx(s.y), kLn2, m.y);
+      res.z = (fabsf(m.z) == INFINITY) ? m.z : fmaf(lg2_approx(s.z), kLn2, m.z);
+      res.w = (fabsf(m.w) == INFINITY) ? m.w : fmaf(lg2_approx(s.w), kLn2, m.w);
       reinterpret_cast<float4*>(out + p0 * ti)[idx] = res;  // idx enumerates (gi, t, i4) in memory order
     }
     __syncthreads();
@@ -286,7 +329,7 @@ __global__ void __launch_bounds__(256) lme_batched_fwd_vec_kernel(const float* _
 
 // Backward, float32, I % 4 == 0.  dA: one thread per (t, r), 128-bit loads of the out / gout / B rows; dB: one thread per
 // (r, four columns), walks the rows t.  Same exactness rule: a + b - out first, then the scaling.
-__global__ void __launch_bounds__(256) lme_batched_bwd_vec_kernel(const float* __restrict__ A, const float* __restrict__ B,
+__global__ void __launch_bounds__(256, 6) lme_batched_bwd_vec_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                                   const float* __restrict__ out,
                                                                   const float* __restrict__ gout, float* __restrict__ dA,
                                                                   float* __restrict__ dB, long long NB, int Th, int R,
@@ -297,6 +340,9 @@ __global__ void __launch_bounds__(256) lme_batched_bwd_vec_kernel(const float* _
   float* Bs = As + (size_t)G * tr;
   float* Os = Bs + (size_t)G * ri;
   float* Gs = Os + (size_t)G * ti;
+  Walk3 wa0, wb0;
+  wa0.init(threadIdx.x, blockDim.x, Th, R);
+  wb0.init(threadIdx.x, blockDim.x, R, I4);
   for (long long p0 = (long long)blockIdx.x * G; p0 < NB; p0 += (long long)gridDim.x * G) {
     const int g = (int)((NB - p0) < G ? (NB - p0) : G);
     stage_in(As, A + p0 * tr, g * tr);
@@ -305,8 +351,9 @@ __global__ void __launch_bounds__(256) lme_batched_bwd_vec_kernel(const float* _
     stage_in(Gs, gout + p0 * ti, g * ti);
     __syncthreads();
     if (dA) {
-      for (int idx = threadIdx.x; idx < g * tr; idx += blockDim.x) {
-        const int gi = idx / tr, rem = idx - gi * tr, t = rem / R, r = rem - t * R;
+      Walk3 w = wa0;
+      for (int idx = threadIdx.x; idx < g * tr; idx += blockDim.x, w.next()) {
+        const int gi = w.gi, t = w.a, r = w.b;
         const float a = As[idx];
         const float4* b = reinterpret_cast<const float4*>(Bs + gi * ri + r * I);
         const float4* o = reinterpret_cast<const float4*>(Os + gi * ti + t * I);
@@ -325,8 +372,9 @@ __global__ void __launch_bounds__(256) lme_batched_bwd_vec_kernel(const float* _
     }
     if (dB) {
       const int w_per = R * I4;
-      for (int idx = threadIdx.x; idx < g * w_per; idx += blockDim.x) {
-        const int gi = idx / w_per, rem = idx - gi * w_per, r = rem / I4, i4 = rem - r * I4;
+      Walk3 w = wb0;
+      for (int idx = threadIdx.x; idx < g * w_per; idx += blockDim.x, w.next()) {
+        const int gi = w.gi, r = w.a, i4 = w.b, rem = r * I4 + i4;
         const float4 bv = reinterpret_cast<const float4*>(Bs + gi * ri)[rem];
         const float* a = As + gi * tr + r;
         const float4* o = reinterpret_cast<const float4*>(Os + gi * ti) + i4;
