@@ -8,6 +8,7 @@
 // memory as [o][a][b] — is broadcast to all threads with 128-bit shared loads:
 //     out[p][o] = sum_a kr1[a] * (sum_b kr2[b] * core[a][b][o])
 // No Q^(K*K)-sized intermediate exists anywhere.  Algorithmic bytes per patch: Q floats of x (amortised) + O floats out.
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -387,6 +388,288 @@ __global__ void __launch_bounds__(DTHREADS) direct_dcore_kernel(EpsGeom g, const
   }
 }
 
+// Core gradient, tiled: dcore[a][n] = sum_p kr1[p][a] * GB[p][n],  n = (b, o),  GB[p][n] = kr2[p][b] * gout[p][o] — a GEMM
+// with a tiny M x N output (M = A <= 36, N = Bn*O) and the patches as the reduction axis.  The shuffle kernel above
+// pays 10 instructions per (a, b, o) term per 32..128 patches; here a CTA stages a chunk of PC patches as two tables in
+// shared memory (phase 1: one thread per patch, both Khatri-Rao halves expanded in registers, 128-bit stores), then
+// every thread owns a 4 x 4 register tile of dcore (x TPT) and a SLICE of the chunk's patches (phase 2: two 128-bit
+// shared loads per 16 FMAs).  Tiny cores have fewer tiles than threads, so the CTA's threads are split into NS slices
+// over the patches and the slices are summed in fixed order at the end (deterministic); one partial per CTA.
+constexpr int DC_THREADS = 256;
+
+template <typename T> __device__ __forceinline__ void ld4(const T* p, T (&v)[4]);
+template <> __device__ __forceinline__ void ld4<float>(const float* p, float (&v)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <> __device__ __forceinline__ void ld4<double>(const double* p, double (&v)[4]) {
+  const double2 t0 = *reinterpret_cast<const double2*>(p), t1 = *reinterpret_cast<const double2*>(p + 2);
+  v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y;
+}
+
+template <typename T> __device__ __forceinline__ void st4(T* p, T v0, T v1, T v2, T v3);
+template <> __device__ __forceinline__ void st4<float>(float* p, float v0, float v1, float v2, float v3) {
+  *reinterpret_cast<float4*>(p) = make_float4(v0, v1, v2, v3);
+}
+template <> __device__ __forceinline__ void st4<double>(double* p, double v0, double v1, double v2, double v3) {
+  *reinterpret_cast<double2*>(p) = make_double2(v0, v1);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(v2, v3);
+}
+
+// Table layouts: K1[pl][a] with row stride SA, GB[pl][n] with n = o * BNP + b (BNP = Bn rounded up to 4) and row stride
+// SN; both strides are ODD multiples of four elements, so the one-row-per-lane 128-bit stores of phase 1 and the
+// 128-bit loads of phase 2 are free of bank conflicts.
+template <typename T, int Q, int MA, int MB, int TPT>
+__global__ void __launch_bounds__(DC_THREADS) direct_dcore_tiled_kernel(EpsGeom g, const T* __restrict__ x,
+                                                                        const T* __restrict__ gout, T* __restrict__ part,
+                                                                        int PC, int SA, int SN, int ntiles, int NS) {
+  constexpr int A = IPow<Q, MA>::v, BN = IPow<Q, MB>::v;
+  constexpr int AP = (A + 3) & ~3, BNP = (BN + 3) & ~3;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* K1 = reinterpret_cast<T*>(smem_raw);   // [PC][SA]
+  T* GB = K1 + (size_t)PC * SA;             // [PC][SN]
+  const int O = g.O, N = BN * O, ntn = (O * BNP) >> 2;
+  const int tid = threadIdx.x;
+  // tiles of this thread: tile index runs fastest over threads, then the slice
+  int slice, ta[TPT], tn[TPT];
+  bool live[TPT];
+  if (TPT == 1) {
+    const int t = tid % ntiles;
+    slice = tid / ntiles;
+    live[0] = slice < NS;
+    ta[0] = t / ntn; tn[0] = t - ta[0] * ntn;
+  } else {
+    slice = 0;
+#pragma unroll
+    for (int k = 0; k < TPT; ++k) {
+      const int t = tid + k * DC_THREADS;
+      live[k] = t < ntiles;
+      const int tt = live[k] ? t : 0;
+      ta[k] = tt / ntn; tn[k] = tt - ta[k] * ntn;
+    }
+  }
+  T acc[TPT][4][4];
+#pragma unroll
+  for (int k = 0; k < TPT; ++k)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[k][i][j] = T(0);
+
+  const unsigned hw = (unsigned)(g.Ho * g.Wo), Wo = (unsigned)g.Wo;
+  const long long nchunks = (g.P + PC - 1) / PC;
+  for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    // ---- phase 1: tables of the chunk
+    for (int pl = tid; pl < PC; pl += DC_THREADS) {
+      const long long p = c * PC + pl;
+      T* k1 = K1 + (size_t)pl * SA;
+      T* gb = GB + (size_t)pl * SN;
+      const bool ok = p < g.P;
+      const unsigned pc = ok ? (unsigned)p : 0u;
+      const unsigned b = pc / hw, r = pc - b * hw, h = r / Wo, w = r - h * Wo;
+      const unsigned org = ((b * (unsigned)g.H + h) * (unsigned)g.W + w) * Q;
+      T kr1[AP], kr2[BNP];
+      {
+        T t1[A], t2[BN];
+        expand_kr<T, Q, MA>(t1, x, org, g, 0);
+        expand_kr<T, Q, MB>(t2, x, org, g, MA);
+#pragma unroll
+        for (int a = 0; a < AP; ++a) kr1[a] = (a < A && ok) ? t1[a] : T(0);
+#pragma unroll
+        for (int bb = 0; bb < BNP; ++bb) kr2[bb] = (bb < BN && ok) ? t2[bb] : T(0);
+      }
+#pragma unroll
+      for (int a = 0; a < AP; a += 4) st4<T>(k1 + a, kr1[a], kr1[a + 1], kr1[a + 2], kr1[a + 3]);
+      const T* gp = gout + (size_t)pc * O;
+      for (int o = 0; o < O; ++o) {
+        const T gv = __ldg(gp + o);
+#pragma unroll
+        for (int bb = 0; bb < BNP; bb += 4)
+          st4<T>(gb + o * BNP + bb, kr2[bb] * gv, kr2[bb + 1] * gv, kr2[bb + 2] * gv, kr2[bb + 3] * gv);
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: this thread's slice of the patches into its register tiles
+    if (TPT > 1 || live[0]) {
+#pragma unroll 2
+      for (int pl = slice; pl < PC; pl += NS) {
+#pragma unroll
+        for (int k = 0; k < TPT; ++k) {
+          if (TPT > 1 && !live[k]) continue;
+          T av[4], nv[4];
+          ld4<T>(K1 + (size_t)pl * SA + 4 * ta[k], av);
+          ld4<T>(GB + (size_t)pl * SN + 4 * tn[k], nv);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[k][i][j] = fma(av[i], nv[j], acc[k][i][j]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- slices -> one partial per CTA (fixed summation order); dcore is stored [a][b][o]
+  const int NPs = O * BNP;
+  T* red = reinterpret_cast<T*>(smem_raw);  // [NS][AP][NPs]
+#pragma unroll
+  for (int k = 0; k < TPT; ++k) {
+    if (!live[k]) continue;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[((size_t)slice * AP + 4 * ta[k] + i) * NPs + 4 * tn[k] + j] = acc[k][i][j];
+  }
+  __syncthreads();
+  T* dst = part + (size_t)blockIdx.x * A * N;
+  for (int i = tid; i < A * N; i += DC_THREADS) {
+    const int a = i / N, rem = i - a * N, bb = rem / O, o = rem - bb * O;
+    T v = T(0);
+    for (int sidx = 0; sidx < NS; ++sidx) v += red[((size_t)sidx * AP + a) * NPs + o * BNP + bb];
+    dst[i] = v;
+  }
+}
+
+// returns 1 when the tiled kernel was launched, 0 when the shape does not fit it, < 0 on error
+template <typename T, int Q, int MA, int MB>
+int try_launch_dcore_tiled(const EpsGeom& g, const T* x, const T* gout, T* part, int* blocks_out, cudaStream_t st) {
+  constexpr int A = IPow<Q, MA>::v, BN = IPow<Q, MB>::v;
+  constexpr int AP = (A + 3) & ~3, BNP = (BN + 3) & ~3;
+  const int NP = g.O * BNP;
+  const int ntiles = (AP >> 2) * (NP >> 2);
+  if (ntiles > 2 * DC_THREADS) return 0;
+  const int TPT = ntiles > DC_THREADS ? 2 : 1;
+  const int NS = TPT == 1 ? DC_THREADS / ntiles : 1;
+  const int SA = ((AP >> 2) & 1) ? AP : AP + 4, SN = ((NP >> 2) & 1) ? NP : NP + 4;   // odd multiples of 4
+  int PC = 256;
+  while (PC > 64 && (size_t)PC * (SA + SN) * sizeof(T) > 64 * 1024) PC >>= 1;
+  size_t smem = (size_t)PC * (SA + SN) * sizeof(T);
+  const size_t red = (size_t)NS * AP * NP * sizeof(T);
+  if (red > smem) smem = red;
+  if (smem > 160 * 1024) return 0;
+  const long long nchunks = (g.P + PC - 1) / PC;
+  const int per_sm = smem > 100 * 1024 ? 1 : smem > 70 * 1024 ? 2 : smem > 50 * 1024 ? 3 : 4;
+  long long blocks = 148ll * per_sm;
+  if (blocks > nchunks) blocks = nchunks;
+  auto k1 = direct_dcore_tiled_kernel<T, Q, MA, MB, 1>;
+  auto k2 = direct_dcore_tiled_kernel<T, Q, MA, MB, 2>;
+  auto k = TPT == 1 ? k1 : k2;
+  DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<(unsigned)blocks, DC_THREADS, smem, st>>>(g, x, gout, part, PC, SA, SN, ntiles, NS);
+  dctn_count_launch();
+  DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  *blocks_out = (int)blocks;
+  return 1;
+}
+
+// Core gradient for the smallest cores (A * Bn * O <= 96, i.e. K = 2, Q = 2, O <= 6 — config 1 and the HBM-bound rows
+// of the config-3 grid): every thread keeps a FULL private copy of dcore in registers and streams its patches through
+// it — no shared memory, no barrier and no shuffle in the loop; the copies are summed once at the end (shuffles inside
+// the warp, shared memory across the warps, one partial per CTA, all in fixed order).
+template <typename T, int Q, int MA, int MB, int O>
+__global__ void __launch_bounds__(DTHREADS) direct_dcore_reg_kernel(EpsGeom g, const T* __restrict__ x,
+                                                                    const T* __restrict__ gout, T* __restrict__ part) {
+  constexpr int A = IPow<Q, MA>::v, BN = IPow<Q, MB>::v, DO = A * BN * O, NW = DTHREADS / 32;
+  __shared__ T red[NW][DO];
+  T acc[A * BN][O];
+#pragma unroll
+  for (int e = 0; e < A * BN; ++e)
+#pragma unroll
+    for (int o = 0; o < O; ++o) acc[e][o] = T(0);
+  const unsigned hw = (unsigned)(g.Ho * g.Wo), Wo = (unsigned)g.Wo, P32 = (unsigned)g.P;
+  const unsigned stride = gridDim.x * DTHREADS;
+  for (unsigned p = blockIdx.x * DTHREADS + threadIdx.x; p < P32; p += stride) {
+    const unsigned b = p / hw, r = p - b * hw, h = r / Wo, w = r - h * Wo;
+    const unsigned org = ((b * (unsigned)g.H + h) * (unsigned)g.W + w) * Q;
+    T kr1[A], kr2[BN], gv[O];
+    expand_kr<T, Q, MA>(kr1, x, org, g, 0);
+    expand_kr<T, Q, MB>(kr2, x, org, g, MA);
+#pragma unroll
+    for (int o = 0; o < O; ++o) gv[o] = __ldg(gout + (size_t)p * O + o);
+#pragma unroll
+    for (int a = 0; a < A; ++a)
+#pragma unroll
+      for (int bb = 0; bb < BN; ++bb) {
+        const T kk = kr1[a] * kr2[bb];
+#pragma unroll
+        for (int o = 0; o < O; ++o) acc[a * BN + bb][o] = fma(kk, gv[o], acc[a * BN + bb][o]);
+      }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int e = 0; e < A * BN; ++e)
+#pragma unroll
+    for (int o = 0; o < O; ++o) {
+      T v = acc[e][o];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == 0) red[warp][e * O + o] = v;
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < DO; i += DTHREADS) {
+    T v = T(0);
+#pragma unroll
+    for (int w = 0; w < NW; ++w) v += red[w][i];
+    part[(size_t)blockIdx.x * DO + i] = v;
+  }
+}
+
+template <typename T, int Q, int MA, int MB, int O>
+int launch_dcore_reg(const EpsGeom& g, const T* x, const T* gout, T* part, int* blocks_out, cudaStream_t st) {
+  long long blocks = (g.P + DTHREADS - 1) / DTHREADS;
+  if (blocks > 148ll * 8) blocks = 148ll * 8;
+  direct_dcore_reg_kernel<T, Q, MA, MB, O><<<(unsigned)blocks, DTHREADS, 0, st>>>(g, x, gout, part);
+  dctn_count_launch();
+  DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  *blocks_out = (int)blocks;
+  return 1;
+}
+template <typename T, int Q, int MA, int MB>
+int try_launch_dcore_reg(const EpsGeom& g, const T* x, const T* gout, T* part, int* blocks_out, cudaStream_t st) {
+  constexpr int AB = IPow<Q, MA>::v * IPow<Q, MB>::v;
+  if constexpr (AB <= 16) {
+    switch (g.O) {
+      case 1: return launch_dcore_reg<T, Q, MA, MB, 1>(g, x, gout, part, blocks_out, st);
+      case 2: return launch_dcore_reg<T, Q, MA, MB, 2>(g, x, gout, part, blocks_out, st);
+      case 3: return launch_dcore_reg<T, Q, MA, MB, 3>(g, x, gout, part, blocks_out, st);
+      case 4: return launch_dcore_reg<T, Q, MA, MB, 4>(g, x, gout, part, blocks_out, st);
+      case 5: return launch_dcore_reg<T, Q, MA, MB, 5>(g, x, gout, part, blocks_out, st);
+      case 6: return launch_dcore_reg<T, Q, MA, MB, 6>(g, x, gout, part, blocks_out, st);
+      default: return 0;
+    }
+  }
+  return 0;
+}
+
+// out[i] = sum_z part[z * count + i] for MANY partials of a SMALL tensor (one partial per CTA of the kernels above):
+// the generic reduce_partials_kernel walks the partials serially per output (1184 dependent-latency loads for a
+// 32-element core: 80 us, more than the gradient itself).  Here a CTA of 1024 threads takes 32 outputs x 32 slices of
+// the partials (coalesced over the outputs), then sums the slices through shared memory — fixed order, deterministic.
+template <typename T>
+__global__ void __launch_bounds__(1024) reduce_partials_wide_kernel(const T* __restrict__ part, T* __restrict__ out,
+                                                                    int count, int splits) {
+  __shared__ T red[32][33];
+  const int il = threadIdx.x & 31, zs = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + il;
+  T v = T(0);
+  if (i < count)
+    for (int z = zs; z < splits; z += 32) v += part[(size_t)z * count + i];
+  red[zs][il] = v;
+  __syncthreads();
+  if (zs == 0 && i < count) {
+    T t = T(0);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += red[k][il];
+    out[i] = t;
+  }
+}
+template <typename T>
+int launch_reduce_partials_wide(const T* part, T* out, int count, int splits, cudaStream_t st) {
+  reduce_partials_wide_kernel<T><<<(count + 31) / 32, 1024, 0, st>>>(part, out, count, splits);
+  dctn_count_launch();
+  DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  return 0;
+}
+
 // Input gradient, written per patch as dxp[p][j][q] (the shared gather kernel then sums the K*K overlapping patches of
 // every pixel):  G[a][b] = sum_o gout[p][o] core[a][b][o];  W1[a] = sum_b G[a][b] kr2[b];  W2[b] = sum_a G[a][b] kr1[a];
 // d x_j[q] = sum over the entries of its half with digit_j == q of W * (product of the other factors of that half).
@@ -478,13 +761,20 @@ int launch_direct_bwd(const EpsGeom& g, int kind, const T* x, const T* core, con
   if (blocks > cap) blocks = cap;
   if (kind == 1) {
     const int DO = A * BN * g.O;
+    if (!getenv("DCTN_B200_DCORE_SHUFFLE")) {   // A/B switch: the older warp-shuffle kernel
+      int nb = 0;
+      int rc = try_launch_dcore_reg<T, Q, MA, MB>(g, x, gout, (T*)ws, &nb, st);
+      if (rc == 0) rc = try_launch_dcore_tiled<T, Q, MA, MB>(g, x, gout, (T*)ws, &nb, st);
+      if (rc < 0) return rc;
+      if (rc == 1) return launch_reduce_partials_wide<T>((const T*)ws, result, DO, nb, st);
+    }
     const size_t smem = (size_t)(DTHREADS / 32) * DO * sizeof(T);
     auto k = direct_dcore_kernel<T, Q, MA, MB>;
     DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<(unsigned)blocks, DTHREADS, smem, st>>>(g, x, gout, (T*)ws);
     dctn_count_launch();
     DCTN_CUDA_CHECK_RET(cudaGetLastError());
-    return launch_reduce_partials<T>((const T*)ws, result, DO, (int)blocks, st);
+    return launch_reduce_partials_wide<T>((const T*)ws, result, DO, (int)blocks, st);
   }
   const size_t smem = (size_t)A * BN * g.O * sizeof(T);
   auto k = direct_dx_kernel<T, Q, MA, MB>;
@@ -560,7 +850,13 @@ template int direct_forward<double>(const EpsGeom&, const double*, const double*
 bool direct_bwd_supported(const EpsGeom& g, int dtype, int kind) {
   if (!direct_supported(g, dtype)) return false;
   const long long DO = (long long)g.A * g.Bn * g.O;
-  if (kind == 1) return DO <= 2048;                       // one shuffle-reduction per core element per warp iteration
+  if (kind == 1) {
+    if (DO <= 2048) return true;                          // (fallback) one shuffle-reduction per core element per warp iteration
+    // the tiled kernel: at most 512 register tiles of 4 x 4 and 64 patches of tables within 160 KiB (try_launch_dcore_tiled)
+    const int AP = (g.A + 3) & ~3, NP = g.O * ((g.Bn + 3) & ~3);
+    const size_t es = dtype == 0 ? 4 : 8;
+    return (AP >> 2) * (NP >> 2) <= 512 && (size_t)64 * (AP + NP + 8) * es <= 160 * 1024 && (size_t)AP * NP * es <= 160 * 1024;
+  }
   return g.A + g.Bn <= 64 && g.P * g.n * g.Q < (1ll << 31);  // everything of a patch stays in registers
 }
 size_t direct_workspace_bytes(const EpsGeom& g, int dtype, int kind) {
