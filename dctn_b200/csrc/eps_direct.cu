@@ -674,7 +674,8 @@ int launch_reduce_partials_wide(const T* part, T* out, int count, int splits, cu
 // every pixel):  G[a][b] = sum_o gout[p][o] core[a][b][o];  W1[a] = sum_b G[a][b] kr2[b];  W2[b] = sum_a G[a][b] kr1[a];
 // d x_j[q] = sum over the entries of its half with digit_j == q of W * (product of the other factors of that half).
 template <typename T, int Q, int M>
-__device__ __forceinline__ void leave_one_out(const T (&w)[IPow<Q, M>::v], const T (&xv)[M][Q], T* __restrict__ dst /*[M][Q]*/) {
+__device__ __forceinline__ void leave_one_out(const T (&w)[IPow<Q, M>::v], const T (&xv)[M][Q], T* __restrict__ dst /*[M][Q]*/,
+                                              int ds = 1 /* element stride of dst */) {
   constexpr int E = IPow<Q, M>::v;
 #pragma unroll
   for (int t = 0; t < M; ++t) {
@@ -696,8 +697,51 @@ __device__ __forceinline__ void leave_one_out(const T (&w)[IPow<Q, M>::v], const
         if (q == dig) acc[q] += v;
     }
 #pragma unroll
-    for (int q = 0; q < Q; ++q) dst[t * Q + q] = acc[q];
+    for (int q = 0; q < Q; ++q) dst[(t * Q + q) * ds] = acc[q];
   }
+}
+
+// everything of one patch in registers; writes d x_j[q] of the patch's n factors to dst[(j*Q + q) * ds]
+template <typename T, int Q, int MA, int MB>
+__device__ __forceinline__ void patch_dx(const EpsGeom& g, const T* __restrict__ x, const T* cs /* core [A][BN][O], shared */,
+                                         const T* __restrict__ gp /* gout row */, unsigned org, T* __restrict__ dst, int ds) {
+  constexpr int A = IPow<Q, MA>::v, BN = IPow<Q, MB>::v;
+  const int O = g.O;
+  T xa[MA][Q], xb[MB][Q];
+#pragma unroll
+  for (int j = 0; j < MA; ++j)
+#pragma unroll
+    for (int q = 0; q < Q; ++q) xa[j][q] = __ldg(x + org + g.foff[j] + q);
+#pragma unroll
+  for (int j = 0; j < MB; ++j)
+#pragma unroll
+    for (int q = 0; q < Q; ++q) xb[j][q] = __ldg(x + org + g.foff[MA + j] + q);
+  T kr1[A], kr2[BN];
+  expand_kr<T, Q, MA>(kr1, x, org, g, 0);
+  expand_kr<T, Q, MB>(kr2, x, org, g, MA);
+  T w1[A], w2[BN];
+#pragma unroll
+  for (int i = 0; i < BN; ++i) w2[i] = T(0);
+#pragma unroll
+  for (int a = 0; a < A; ++a) {
+    T grow[BN];
+#pragma unroll
+    for (int i = 0; i < BN; ++i) grow[i] = T(0);
+    for (int o = 0; o < O; ++o) {
+      const T gv = __ldg(gp + o);
+#pragma unroll
+      for (int i = 0; i < BN; ++i) grow[i] = fma(gv, cs[(a * BN + i) * O + o], grow[i]);
+    }
+    T s1 = T(0);
+#pragma unroll
+    for (int i = 0; i < BN; ++i) {
+      s1 = fma(grow[i], kr2[i], s1);
+      w2[i] = fma(grow[i], kr1[a], w2[i]);
+    }
+    w1[a] = s1;
+  }
+  leave_one_out<T, Q, MA>(w1, xa, dst, ds);
+  leave_one_out<T, Q, MB>(w2, xb, dst + MA * Q * ds, ds);
 }
 
 template <typename T, int Q, int MA, int MB>
@@ -713,43 +757,50 @@ __global__ void __launch_bounds__(DTHREADS) direct_dx_kernel(EpsGeom g, const T*
   for (unsigned p = blockIdx.x * DTHREADS + threadIdx.x; p < P32; p += gridDim.x * DTHREADS) {
     const unsigned b = p / hw, r = p - b * hw, h = r / Wo, w = r - h * Wo;
     const unsigned org = ((b * (unsigned)g.H + h) * (unsigned)g.W + w) * Q;
-    T xa[MA][Q], xb[MB][Q];
-#pragma unroll
-    for (int j = 0; j < MA; ++j)
-#pragma unroll
-      for (int q = 0; q < Q; ++q) xa[j][q] = __ldg(x + org + g.foff[j] + q);
-#pragma unroll
-    for (int j = 0; j < MB; ++j)
-#pragma unroll
-      for (int q = 0; q < Q; ++q) xb[j][q] = __ldg(x + org + g.foff[MA + j] + q);
-    T kr1[A], kr2[BN];
-    expand_kr<T, Q, MA>(kr1, x, org, g, 0);
-    expand_kr<T, Q, MB>(kr2, x, org, g, MA);
-    T w1[A], w2[BN];
-#pragma unroll
-    for (int i = 0; i < BN; ++i) w2[i] = T(0);
-    const T* gp = gout + (size_t)p * O;
-#pragma unroll
-    for (int a = 0; a < A; ++a) {
-      T grow[BN];
-#pragma unroll
-      for (int i = 0; i < BN; ++i) grow[i] = T(0);
-      for (int o = 0; o < O; ++o) {
-        const T gv = __ldg(gp + o);
-#pragma unroll
-        for (int i = 0; i < BN; ++i) grow[i] = fma(gv, cs[(a * BN + i) * O + o], grow[i]);
+    patch_dx<T, Q, MA, MB>(g, x, cs, gout + (size_t)p * O, org, dxp + (size_t)p * (MA + MB) * Q, 1);
+  }
+}
+
+// Input gradient, FUSED per image: one CTA owns image b — its Ho*Wo patches write their per-factor contributions into
+// shared memory ([j*Q + q][patch], odd row stride), and after one barrier the same CTA sums, for every pixel of the
+// image, the <= K*K patches that contain it (fixed order) and stores dx coalesced.  The P x n x Q intermediate of the
+// two-kernel path (dxp: written and re-read through HBM, 190 MB of the 265 MB it moves on the config-1 shape at
+// B = 4096) never leaves the SM; HBM traffic is x + gout + dx.
+constexpr int DXI_THREADS = 256;
+template <typename T, int Q, int MA, int MB>
+__global__ void __launch_bounds__(DXI_THREADS) direct_dx_image_kernel(EpsGeom g, const T* __restrict__ x,
+                                                                      const T* __restrict__ core, const T* __restrict__ gout,
+                                                                      T* __restrict__ dx, int NPP) {
+  constexpr int A = IPow<Q, MA>::v, BN = IPow<Q, MB>::v, NF = MA + MB;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* cs = reinterpret_cast<T*>(smem_raw);           // core [A][BN][O]
+  const int O = g.O;
+  T* dxs = cs + ((A * BN * O + 3) & ~3);            // [NF*Q][NPP]
+  for (int i = threadIdx.x; i < A * BN * O; i += DXI_THREADS) cs[i] = core[i];
+  __syncthreads();
+  const int b = blockIdx.x, Wo = g.Wo, npatch = g.Ho * g.Wo;
+  for (int pl = threadIdx.x; pl < npatch; pl += DXI_THREADS) {
+    const int h = pl / Wo, w = pl - h * Wo;
+    const unsigned org = (((unsigned)b * (unsigned)g.H + h) * (unsigned)g.W + w) * Q;
+    patch_dx<T, Q, MA, MB>(g, x, cs, gout + ((size_t)b * npatch + pl) * O, org, dxs + pl, NPP);
+  }
+  __syncthreads();
+  const int per_c = g.H * g.W * Q, K = g.K, C = g.C;
+  for (int idx = threadIdx.x; idx < C * per_c; idx += DXI_THREADS) {
+    const int c = idx / per_c, rem = idx - c * per_c;
+    const int q = rem % Q, hw = rem / Q, w = hw % g.W, h = hw / g.W;
+    T sacc = T(0);
+    for (int dh = 0; dh < K; ++dh) {
+      const int ph = h - dh;
+      if (ph < 0 || ph >= g.Ho) continue;
+      for (int dw = 0; dw < K; ++dw) {
+        const int pw = w - dw;
+        if (pw < 0 || pw >= Wo) continue;
+        const int j = (dh * K + dw) * C + c;
+        sacc += dxs[(j * Q + q) * NPP + ph * Wo + pw];
       }
-      T s1 = T(0);
-#pragma unroll
-      for (int i = 0; i < BN; ++i) {
-        s1 = fma(grow[i], kr2[i], s1);
-        w2[i] = fma(grow[i], kr1[a], w2[i]);
-      }
-      w1[a] = s1;
     }
-    T* dst = dxp + (size_t)p * (MA + MB) * Q;
-    leave_one_out<T, Q, MA>(w1, xa, dst);
-    leave_one_out<T, Q, MB>(w2, xb, dst + MA * Q);
+    dx[((size_t)c * g.B + b) * per_c + rem] = sacc;
   }
 }
 
@@ -775,6 +826,19 @@ int launch_direct_bwd(const EpsGeom& g, int kind, const T* x, const T* core, con
     dctn_count_launch();
     DCTN_CUDA_CHECK_RET(cudaGetLastError());
     return launch_reduce_partials_wide<T>((const T*)ws, result, DO, (int)blocks, st);
+  }
+  {
+    const int npatch = g.Ho * g.Wo, NPP = npatch | 1;
+    const size_t fsm = ((size_t)((A * BN * g.O + 3) & ~3) + (size_t)(MA + MB) * Q * NPP) * sizeof(T);
+    // A + BN > 32 (K = 3, Q = 2): the per-patch registers leave too few 256-thread CTAs per SM, the two-kernel path wins
+    if (fsm <= 200 * 1024 && A + BN <= 32 && !getenv("DCTN_B200_DX_UNFUSED")) {   // env: A/B switch
+      auto kf = direct_dx_image_kernel<T, Q, MA, MB>;
+      DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+      kf<<<(unsigned)g.B, DXI_THREADS, fsm, st>>>(g, x, core, gout, result, NPP);
+      dctn_count_launch();
+      DCTN_CUDA_CHECK_RET(cudaGetLastError());
+      return 0;
+    }
   }
   const size_t smem = (size_t)A * BN * g.O * sizeof(T);
   auto k = direct_dx_kernel<T, Q, MA, MB>;
