@@ -577,9 +577,15 @@ __global__ void __launch_bounds__(DTHREADS) direct_dcore_reg_kernel(EpsGeom g, c
     for (int o = 0; o < O; ++o) acc[e][o] = T(0);
   const unsigned hw = (unsigned)(g.Ho * g.Wo), Wo = (unsigned)g.Wo, P32 = (unsigned)g.P;
   const unsigned stride = gridDim.x * DTHREADS;
-  for (unsigned p = blockIdx.x * DTHREADS + threadIdx.x; p < P32; p += stride) {
-    const unsigned b = p / hw, r = p - b * hw, h = r / Wo, w = r - h * Wo;
+  // (b, h, w) of the thread's patch advance by the decomposed grid stride: no divisions in the loop
+  const unsigned pfirst = blockIdx.x * DTHREADS + threadIdx.x;
+  unsigned b = pfirst / hw, h = (pfirst - b * hw) / Wo, w = pfirst - b * hw - h * Wo;
+  const unsigned sb = stride / hw, sh = (stride - sb * hw) / Wo, sw = stride - sb * hw - sh * Wo, Ho = (unsigned)g.Ho;
+  for (unsigned p = pfirst; p < P32; p += stride) {
     const unsigned org = ((b * (unsigned)g.H + h) * (unsigned)g.W + w) * Q;
+    w += sw; if (w >= Wo) { w -= Wo; ++h; }
+    h += sh; if (h >= Ho) { h -= Ho; ++b; }
+    b += sb;
     T kr1[A], kr2[BN], gv[O];
     expand_kr<T, Q, MA>(kr1, x, org, g, 0);
     expand_kr<T, Q, MB>(kr2, x, org, g, MA);
@@ -785,23 +791,39 @@ __global__ void __launch_bounds__(DXI_THREADS) direct_dx_image_kernel(EpsGeom g,
     patch_dx<T, Q, MA, MB>(g, x, cs, gout + ((size_t)b * npatch + pl) * O, org, dxs + pl, NPP);
   }
   __syncthreads();
-  const int per_c = g.H * g.W * Q, K = g.K, C = g.C;
-  for (int idx = threadIdx.x; idx < C * per_c; idx += DXI_THREADS) {
-    const int c = idx / per_c, rem = idx - c * per_c;
-    const int q = rem % Q, hw = rem / Q, w = hw % g.W, h = hw / g.W;
-    T sacc = T(0);
-    for (int dh = 0; dh < K; ++dh) {
-      const int ph = h - dh;
-      if (ph < 0 || ph >= g.Ho) continue;
-      for (int dw = 0; dw < K; ++dw) {
-        const int pw = w - dw;
-        if (pw < 0 || pw >= Wo) continue;
-        const int j = (dh * K + dw) * C + c;
-        sacc += dxs[(j * Q + q) * NPP + ph * Wo + pw];
+  // gather: one thread per pixel (all Q values), warps over the rows of the C planes, lanes over the columns — no
+  // divisions, the Q results of a pixel stored together
+  const int per_c = g.H * g.W * Q, K = g.K, C = g.C, W = g.W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int row = warp; row < C * g.H; row += DXI_THREADS / 32) {
+    const int c = row / g.H, h = row - c * g.H;
+    T* drow = dx + ((size_t)c * g.B + b) * per_c + (size_t)h * W * Q;
+    for (int w = lane; w < W; w += 32) {
+      T sacc[Q];
+#pragma unroll
+      for (int q = 0; q < Q; ++q) sacc[q] = T(0);
+      for (int dh = 0; dh < K; ++dh) {
+        const int ph = h - dh;
+        if (ph < 0 || ph >= g.Ho) continue;
+        for (int dw = 0; dw < K; ++dw) {
+          const int pw = w - dw;
+          if (pw < 0 || pw >= Wo) continue;
+          const T* src = dxs + (size_t)((dh * K + dw) * C + c) * Q * NPP + ph * Wo + pw;
+#pragma unroll
+          for (int q = 0; q < Q; ++q) sacc[q] += src[q * NPP];
+        }
       }
+#pragma unroll
+      for (int q = 0; q < Q; ++q) drow[w * Q + q] = sacc[q];
     }
-    dx[((size_t)c * g.B + b) * per_c + rem] = sacc;
   }
+}
+
+// The per-image fused input gradient needs the image's per-patch contributions in shared memory.  A + Bn > 32 (K = 3,
+// Q = 2): the per-patch registers leave too few 256-thread CTAs per SM, the two-kernel path wins (measured).
+static bool dx_fused_fits(const EpsGeom& g, size_t es) {
+  const size_t fsm = ((size_t)((g.A * g.Bn * g.O + 3) & ~3) + (size_t)g.n * g.Q * ((g.Ho * g.Wo) | 1)) * es;
+  return fsm <= 200 * 1024 && g.A + g.Bn <= 32 && !getenv("DCTN_B200_DX_UNFUSED");   // env: A/B switch to the two-kernel path
 }
 
 template <typename T, int Q, int MA, int MB>
@@ -827,11 +849,10 @@ int launch_direct_bwd(const EpsGeom& g, int kind, const T* x, const T* core, con
     DCTN_CUDA_CHECK_RET(cudaGetLastError());
     return launch_reduce_partials_wide<T>((const T*)ws, result, DO, (int)blocks, st);
   }
-  {
+  if (dx_fused_fits(g, sizeof(T))) {
     const int npatch = g.Ho * g.Wo, NPP = npatch | 1;
     const size_t fsm = ((size_t)((A * BN * g.O + 3) & ~3) + (size_t)(MA + MB) * Q * NPP) * sizeof(T);
-    // A + BN > 32 (K = 3, Q = 2): the per-patch registers leave too few 256-thread CTAs per SM, the two-kernel path wins
-    if (fsm <= 200 * 1024 && A + BN <= 32 && !getenv("DCTN_B200_DX_UNFUSED")) {   // env: A/B switch
+    {
       auto kf = direct_dx_image_kernel<T, Q, MA, MB>;
       DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
       kf<<<(unsigned)g.B, DXI_THREADS, fsm, st>>>(g, x, core, gout, result, NPP);
@@ -926,7 +947,7 @@ bool direct_bwd_supported(const EpsGeom& g, int dtype, int kind) {
 size_t direct_workspace_bytes(const EpsGeom& g, int dtype, int kind) {
   const size_t es = dtype == 0 ? 4 : 8;
   if (kind == 1) return (size_t)148 * 8 * g.A * g.Bn * g.O * es + 256;
-  if (kind == 2) return (size_t)g.P * g.n * g.Q * es + 256;
+  if (kind == 2) return dx_fused_fits(g, es) ? 256 : (size_t)g.P * g.n * g.Q * es + 256;
   return 256;
 }
 template <typename T>
