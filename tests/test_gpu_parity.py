@@ -715,6 +715,14 @@ DIRECT_SHAPES = [
     (1, 2, 6, 7, 3, 2, 6),      # Q = 3
     (1, 2, 8, 8, 4, 2, 23),     # CIFAR layer-1 shape (generic thread-per-patch kernel)
     (1, 2, 7, 6, 2, 3, 4),      # K = 3, Q = 2: 5 + 4 factors
+    # larger patch counts: many chunks / slices of the tiled core gradient, many CTAs of the per-image input gradient
+    (1, 40, 28, 28, 4, 2, 6),   # K = 2, Q = 4: 96 register tiles, 2 patch slices
+    (1, 30, 20, 21, 6, 2, 4),   # Q = 6: 324 tiles = two tiles per thread; non-square image
+    (1, 24, 14, 15, 2, 3, 6),   # K = 3, Q = 2, O = 6: 3072-element core (tiled kernel only); two-kernel input gradient
+    (1, 33, 28, 28, 3, 2, 5),   # Q = 3: Bn = 9 padded to 12, odd Q_out
+    (1, 64, 28, 28, 2, 2, 6),   # register-resident core gradient with 96 accumulators
+    (1, 50, 12, 13, 5, 2, 3),   # Q = 5: A = Bn = 25 padded to 28
+    (2, 9, 10, 11, 3, 1, 4),    # two channels, K = 1: channel planes in the per-image gather
 ]
 
 
