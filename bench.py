@@ -128,6 +128,17 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 when it is unset, which would pin the CPU arm to one core at N > 1: the
+    reference arm / cpu_baseline use every core this process may run on, at every N."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def run_reference(args):
     """The reference's own CPU implementation of the path: the oracle port of dctn/eps.py:19-40 (explicit
     4-step einsum path) stacked as dctn/eps_plus_linear.py:138-147, autograd backward, Adam — PyTorch CPU ops
@@ -139,7 +150,7 @@ def run_reference(args):
     from oracle import eps_oracle as O
 
     specs, image_size, Q0, _, scale = WORKLOADS[args.workload]
-    threads = torch.get_num_threads()
+    threads = use_all_host_threads()
     dtype = torch.float32
     torch.manual_seed(0)
     cores = [torch.nn.Parameter(c) for c in
@@ -192,7 +203,7 @@ def cpu_baseline_sample(workload, seconds=20.0):
     from oracle import eps_oracle as O
 
     specs, image_size, Q0, _, scale = WORKLOADS[workload]
-    threads = torch.get_num_threads()
+    threads = use_all_host_threads()
     torch.manual_seed(0)
     qs = [Q0] + [o for _, o in specs[:-1]]
     cores = [((q ** (-(K * K) / 2)) * torch.randn(*(q,) * (K * K), o)).requires_grad_(True) for (K, o), q in zip(specs, qs)]
