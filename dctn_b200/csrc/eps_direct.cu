@@ -422,22 +422,29 @@ template <> __device__ __forceinline__ void st4<double>(double* p, double v0, do
 template <typename T, int Q, int MA, int MB, int TPT>
 __global__ void __launch_bounds__(DC_THREADS) direct_dcore_tiled_kernel(EpsGeom g, const T* __restrict__ x,
                                                                         const T* __restrict__ gout, T* __restrict__ part,
-                                                                        int PC, int SA, int SN, int ntiles, int NS) {
+                                                                        int PC, int SA, int SN, int ntn_group, int NS) {
   constexpr int A = IPow<Q, MA>::v, BN = IPow<Q, MB>::v;
   constexpr int AP = (A + 3) & ~3, BNP = (BN + 3) & ~3;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* K1 = reinterpret_cast<T*>(smem_raw);   // [PC][SA]
-  T* GB = K1 + (size_t)PC * SA;             // [PC][SN]
-  const int O = g.O, N = BN * O, ntn = (O * BNP) >> 2;
+  T* GB = K1 + (size_t)PC * SA;             // [PC][SN]: the column tiles [tn0, tn0 + ntn) of this CTA's group only
+  const int O = g.O, N = BN * O;
+  // blockIdx.y = group of 4-wide column tiles (cores with more than 512 tiles are cut along n; every group sees all
+  // patches and writes its own columns of the CTA's partial)
+  const int tn0 = blockIdx.y * ntn_group;
+  const int ntn = min(ntn_group, ((O * BNP) >> 2) - tn0);
+  const int ntiles = (AP >> 2) * ntn;
   const int tid = threadIdx.x;
   // tiles of this thread: tile index runs fastest over threads, then the slice
   int slice, ta[TPT], tn[TPT];
   bool live[TPT];
   if (TPT == 1) {
-    const int t = tid % ntiles;
-    slice = tid / ntiles;
-    live[0] = slice < NS;
-    ta[0] = t / ntn; tn[0] = t - ta[0] * ntn;
+    const int tmax = (AP >> 2) * ntn_group;   // the slice split is that of a full group
+    const int t = tid % tmax;
+    slice = tid / tmax;
+    live[0] = slice < NS && t < ntiles;
+    const int tt = live[0] ? t : 0;
+    ta[0] = tt / ntn; tn[0] = tt - ta[0] * ntn;
   } else {
     slice = 0;
 #pragma unroll
@@ -484,8 +491,10 @@ __global__ void __launch_bounds__(DC_THREADS) direct_dcore_tiled_kernel(EpsGeom 
       for (int o = 0; o < O; ++o) {
         const T gv = __ldg(gp + o);
 #pragma unroll
-        for (int bb = 0; bb < BNP; bb += 4)
-          st4<T>(gb + o * BNP + bb, kr2[bb] * gv, kr2[bb + 1] * gv, kr2[bb + 2] * gv, kr2[bb + 3] * gv);
+        for (int bb = 0; bb < BNP; bb += 4) {
+          const int ct = ((o * BNP + bb) >> 2) - tn0;   // column tile inside this group?
+          if (ct >= 0 && ct < ntn) st4<T>(gb + 4 * ct, kr2[bb] * gv, kr2[bb + 1] * gv, kr2[bb + 2] * gv, kr2[bb + 3] * gv);
+        }
       }
     }
     __syncthreads();
@@ -509,7 +518,7 @@ __global__ void __launch_bounds__(DC_THREADS) direct_dcore_tiled_kernel(EpsGeom 
     __syncthreads();
   }
   // ---- slices -> one partial per CTA (fixed summation order); dcore is stored [a][b][o]
-  const int NPs = O * BNP;
+  const int NPs = 4 * ntn;
   T* red = reinterpret_cast<T*>(smem_raw);  // [NS][AP][NPs]
 #pragma unroll
   for (int k = 0; k < TPT; ++k) {
@@ -521,12 +530,30 @@ __global__ void __launch_bounds__(DC_THREADS) direct_dcore_tiled_kernel(EpsGeom 
   }
   __syncthreads();
   T* dst = part + (size_t)blockIdx.x * A * N;
-  for (int i = tid; i < A * N; i += DC_THREADS) {
-    const int a = i / N, rem = i - a * N, bb = rem / O, o = rem - bb * O;
+  for (int i = tid; i < A * NPs; i += DC_THREADS) {
+    const int a = i / NPs, nl = i - a * NPs, n = 4 * tn0 + nl, o = n / BNP, bb = n - o * BNP;
+    if (bb >= BN) continue;   // padding column
     T v = T(0);
-    for (int sidx = 0; sidx < NS; ++sidx) v += red[((size_t)sidx * AP + a) * NPs + o * BNP + bb];
-    dst[i] = v;
+    for (int sidx = 0; sidx < NS; ++sidx) v += red[((size_t)sidx * AP + a) * NPs + nl];
+    dst[a * N + bb * O + o] = v;
   }
+}
+
+// cut the column tiles into groups of at most 512 register tiles (two per thread)
+static void dcore_tiled_groups(int AP, int NP, int* ngroups, int* ntn_group) {
+  const int nta = AP >> 2, ntn = NP >> 2;
+  int per = (2 * DC_THREADS) / nta;            // column tiles per group
+  if (per < 1) per = 1;
+  if (per > ntn) per = ntn;
+  *ngroups = (ntn + per - 1) / per;
+  *ntn_group = (ntn + *ngroups - 1) / *ngroups;   // balanced groups
+}
+static bool dcore_tiled_fits(int A, int Bn, int O, size_t es) {
+  const int AP = (A + 3) & ~3, NP = O * ((Bn + 3) & ~3);
+  if ((AP >> 2) > 2 * DC_THREADS) return false;
+  int ngroups, ntn_group;
+  dcore_tiled_groups(AP, NP, &ngroups, &ntn_group);
+  return ngroups <= 64 && (size_t)64 * (AP + 4 * ntn_group + 8) * es <= 160 * 1024 && (size_t)AP * 4 * ntn_group * es <= 160 * 1024;
 }
 
 // returns 1 when the tiled kernel was launched, 0 when the shape does not fit it, < 0 on error
@@ -534,27 +561,30 @@ template <typename T, int Q, int MA, int MB>
 int try_launch_dcore_tiled(const EpsGeom& g, const T* x, const T* gout, T* part, int* blocks_out, cudaStream_t st) {
   constexpr int A = IPow<Q, MA>::v, BN = IPow<Q, MB>::v;
   constexpr int AP = (A + 3) & ~3, BNP = (BN + 3) & ~3;
-  const int NP = g.O * BNP;
-  const int ntiles = (AP >> 2) * (NP >> 2);
-  if (ntiles > 2 * DC_THREADS) return 0;
+  const int NP = g.O * BNP, ntn_all = NP >> 2;
+  int ngroups, ntn_group;
+  dcore_tiled_groups(AP, NP, &ngroups, &ntn_group);
+  const int ntiles = (AP >> 2) * ntn_group;            // tiles of a full group, <= 512
   const int TPT = ntiles > DC_THREADS ? 2 : 1;
   const int NS = TPT == 1 ? DC_THREADS / ntiles : 1;
-  const int SA = ((AP >> 2) & 1) ? AP : AP + 4, SN = ((NP >> 2) & 1) ? NP : NP + 4;   // odd multiples of 4
+  const int NPg = 4 * ntn_group;
+  const int SA = ((AP >> 2) & 1) ? AP : AP + 4, SN = (ntn_group & 1) ? NPg : NPg + 4;   // odd multiples of 4
   int PC = 256;
   while (PC > 64 && (size_t)PC * (SA + SN) * sizeof(T) > 64 * 1024) PC >>= 1;
   size_t smem = (size_t)PC * (SA + SN) * sizeof(T);
-  const size_t red = (size_t)NS * AP * NP * sizeof(T);
+  const size_t red = (size_t)NS * AP * NPg * sizeof(T);
   if (red > smem) smem = red;
   if (smem > 160 * 1024) return 0;
+  (void)ntn_all;
   const long long nchunks = (g.P + PC - 1) / PC;
   const int per_sm = smem > 100 * 1024 ? 1 : smem > 70 * 1024 ? 2 : smem > 50 * 1024 ? 3 : 4;
-  long long blocks = 148ll * per_sm;
+  long long blocks = (148ll * per_sm + ngroups - 1) / ngroups;   // partials = blocks; the grid is blocks x ngroups
   if (blocks > nchunks) blocks = nchunks;
   auto k1 = direct_dcore_tiled_kernel<T, Q, MA, MB, 1>;
   auto k2 = direct_dcore_tiled_kernel<T, Q, MA, MB, 2>;
   auto k = TPT == 1 ? k1 : k2;
   DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<(unsigned)blocks, DC_THREADS, smem, st>>>(g, x, gout, part, PC, SA, SN, ntiles, NS);
+  k<<<dim3((unsigned)blocks, (unsigned)ngroups), DC_THREADS, smem, st>>>(g, x, gout, part, PC, SA, SN, ntn_group, NS);
   dctn_count_launch();
   DCTN_CUDA_CHECK_RET(cudaGetLastError());
   *blocks_out = (int)blocks;
@@ -932,21 +962,26 @@ template int direct_forward<float>(const EpsGeom&, const float*, const float*, f
 template int direct_forward<double>(const EpsGeom&, const double*, const double*, double*, cudaStream_t);
 
 // ---- backward entry points (core gradient: kind 1, input gradient: kind 2)
+static bool direct_shape_known(const EpsGeom& g) {
+  if (g.P * g.O >= (1ll << 31) || (long long)g.C * g.B * g.H * g.W * g.Q >= (1ll << 31)) return false;  // 32-bit index math
+  for (const DirectShape& s : kShapes)
+    if (s.Q == g.Q && s.MA == g.m && s.MB == g.n - g.m) return true;
+  return false;
+}
 bool direct_bwd_supported(const EpsGeom& g, int dtype, int kind) {
-  if (!direct_supported(g, dtype)) return false;
   const long long DO = (long long)g.A * g.Bn * g.O;
   if (kind == 1) {
-    if (DO <= 2048) return true;                          // (fallback) one shuffle-reduction per core element per warp iteration
-    // the tiled kernel: at most 512 register tiles of 4 x 4 and 64 patches of tables within 160 KiB (try_launch_dcore_tiled)
-    const int AP = (g.A + 3) & ~3, NP = g.O * ((g.Bn + 3) & ~3);
-    const size_t es = dtype == 0 ? 4 : 8;
-    return (AP >> 2) * (NP >> 2) <= 512 && (size_t)64 * (AP + NP + 8) * es <= 160 * 1024 && (size_t)AP * NP * es <= 160 * 1024;
+    // the tiled core gradient does not keep the core on chip: any Q_out whose tables fit (e.g. CIFAR (2, 6 -> 24))
+    if (!direct_shape_known(g)) return false;
+    if (!getenv("DCTN_B200_DCORE_SHUFFLE") && dcore_tiled_fits(g.A, g.Bn, g.O, dtype == 0 ? 4 : 8)) return true;
+    return direct_supported(g, dtype) && DO <= 2048;      // (fallback) one shuffle-reduction per core element per warp iteration
   }
+  if (!direct_supported(g, dtype)) return false;
   return g.A + g.Bn <= 64 && g.P * g.n * g.Q < (1ll << 31);  // everything of a patch stays in registers
 }
 size_t direct_workspace_bytes(const EpsGeom& g, int dtype, int kind) {
   const size_t es = dtype == 0 ? 4 : 8;
-  if (kind == 1) return (size_t)148 * 8 * g.A * g.Bn * g.O * es + 256;
+  if (kind == 1) return (size_t)148 * 8 * g.A * g.Bn * g.O * es + 256;   // one partial per CTA (x) of the core-gradient kernels
   if (kind == 2) return dx_fused_fits(g, es) ? 256 : (size_t)g.P * g.n * g.Q * es + 256;
   return 256;
 }

@@ -723,6 +723,8 @@ DIRECT_SHAPES = [
     (1, 64, 28, 28, 2, 2, 6),   # register-resident core gradient with 96 accumulators
     (1, 50, 12, 13, 5, 2, 3),   # Q = 5: A = Bn = 25 padded to 28
     (2, 9, 10, 11, 3, 1, 4),    # two channels, K = 1: channel planes in the per-image gather
+    (1, 6, 16, 17, 6, 2, 24),   # CIFAR (2, 6 -> 24) layer: core gradient cut into 4 groups of column tiles
+    (1, 5, 12, 12, 4, 2, 23),   # CIFAR layer 1 with Q_out = 23: odd Q_out across group boundaries
 ]
 
 
