@@ -102,6 +102,24 @@ extern "C" const dctn_plan_t* dctn_eps_plan_get(int C, int K, int Qin, int Qout,
   int m = (n + 1) / 2;  // the reference's split, dctn/eps.py:25-27
   long long A, Bn;
   const long long LIM = 1ll << 30;
+  // The split is free (core[a][b][o] is one flat [Q^n][O] array for every m).  Mid-sized cores whose halves are too
+  // narrow for the 128-row tensor-core tiles (A = Q^m < 64, e.g. CIFAR (2, 6 -> 24): A = Bn = 36) get a lopsided split
+  // that is wide enough (A' >= 64 and N' = Q^(n-m') * O >= 64) instead of the CUDA-core kernels.  DCTN_B200_SPLIT_M forces m.
+  if (dtype == DCTN_F32 && (variant == DCTN_VARIANT_AUTO || variant == DCTN_VARIANT_TCH3 || variant == DCTN_VARIANT_TC3 || variant == DCTN_VARIANT_TC1)) {
+    long long a0, b0, d0;
+    if (pow_fits(Qin, m, LIM, &a0) && pow_fits(Qin, n - m, LIM, &b0) && pow_fits(Qin, n, LIM, &d0) && d0 >= 1024 &&
+        (a0 < 64 || b0 * Qout < 64)) {
+      for (int mm = 1; mm < n; ++mm) {
+        long long a1, b1;
+        if (!pow_fits(Qin, mm, LIM, &a1) || !pow_fits(Qin, n - mm, LIM, &b1)) continue;
+        if (a1 >= 64 && b1 * Qout >= 64 && a1 <= 4096) { m = mm; break; }
+      }
+    }
+  }
+  if (const char* e = getenv("DCTN_B200_SPLIT_M")) {
+    const int mm = atoi(e);
+    if (mm >= 1 && mm < n) m = mm;
+  }
   if (!pow_fits(Qin, m, LIM, &A) || !pow_fits(Qin, n - m, LIM, &Bn) || Bn * Qout > LIM || A * Bn * Qout >= (1ll << 31)) {
     dctn_set_error(DCTN_ERR_UNSUPPORTED, "plan: core with Qin^(K*K*C) = %d^%d elements is too large", Qin, n);
     return nullptr;

@@ -707,6 +707,26 @@ def test_autograd_saved_and_recompute_paths_agree():
     assert torch.equal(res[0][1], res[1][1])
 
 
+def test_lopsided_split_for_mid_sized_core():
+    """CIFAR (2, 6 -> 24), layer 2: the reference's split (dctn/eps.py:25-27) gives A = Bn = 36, too narrow for the 128-row
+    tensor-core tiles; the plan takes m = 3 (A = 216, N = 144) so that both gradients run on tcgen05.  Same results."""
+    from dctn_b200 import _lib
+    from dctn_b200.eps import plan_description
+
+    B, H, W, Q, K, Oq = 16, 20, 21, 6, 2, 24
+    x, core, gout = _rand_layer(B, H, W, Q, K, Oq, seed=29)
+    assert "split m=3 (A=216, Bn=6, N=144" in plan_description(core, x)
+    assert "split m=2" in plan_description(core.double(), x.double())   # float64 keeps the reference's split
+    want = O.eps_4step(core.double(), x.double())
+    want_dcore, want_dx = O.eps_grads(core.double(), x.double(), gout.double())
+    cd, xd, gd = core.to(DEV), x.to(DEV), gout.to(DEV)
+    assert rel_err(_raw_call(_lib.WS_FORWARD, "auto", cd, xd, gd), want) <= 1e-5
+    assert rel_err(_raw_call(_lib.WS_BACKWARD_CORE, "auto", cd, xd, gd), want_dcore) <= 1e-5
+    assert rel_err(_raw_call(_lib.WS_BACKWARD_INPUT, "auto", cd, xd, gd), want_dx) <= 1e-5
+    out, dcore, dx = _eps_fwd_bwd(core.double(), x.double(), gout.double(), torch.float32)   # autograd path (saved T or not)
+    assert rel_err(out, want) <= 1e-5 and rel_err(dcore, want_dcore) <= 1e-5 and rel_err(dx, want_dx) <= 1e-5
+
+
 # ---------------------------------------------------------------- direct (tiny-core) kernels and the host-buffer entry
 DIRECT_SHAPES = [
     # (C, B, H, W, Q, K, O)
