@@ -737,9 +737,21 @@ __device__ __forceinline__ void leave_one_out(const T (&w)[IPow<Q, M>::v], const
   }
 }
 
+// The input-gradient kernels keep the core TRANSPOSED in shared memory, [o][a][BNP] (Bn padded to a multiple of four):
+// for a fixed (o, a) the Bn values a thread needs are contiguous, so they arrive as broadcast 128-bit loads instead of
+// one strided 32-bit load (plus its address arithmetic) per FMA.
+template <typename T, int Q, int MB> struct DxCoreLayout { static constexpr int BNP = (IPow<Q, MB>::v + 3) & ~3; };
+template <typename T, int A, int BN, int BNP>
+__device__ __forceinline__ void stage_core_transposed(T* cs, const T* __restrict__ core, int O, int nthreads) {
+  for (int idx = threadIdx.x; idx < O * A * BNP; idx += nthreads) {
+    const int b = idx % BNP, r = idx / BNP, a = r % A, o = r / A;
+    cs[idx] = (b < BN) ? core[((size_t)a * BN + b) * O + o] : T(0);
+  }
+}
+
 // everything of one patch in registers; writes d x_j[q] of the patch's n factors to dst[(j*Q + q) * ds]
 template <typename T, int Q, int MA, int MB>
-__device__ __forceinline__ void patch_dx(const EpsGeom& g, const T* __restrict__ x, const T* cs /* core [A][BN][O], shared */,
+__device__ __forceinline__ void patch_dx(const EpsGeom& g, const T* __restrict__ x, const T* cs /* core [O][A][BNP], shared */,
                                          const T* __restrict__ gp /* gout row */, unsigned org, T* __restrict__ dst, int ds) {
   constexpr int A = IPow<Q, MA>::v, BN = IPow<Q, MB>::v;
   const int O = g.O;
@@ -758,15 +770,22 @@ __device__ __forceinline__ void patch_dx(const EpsGeom& g, const T* __restrict__
   T w1[A], w2[BN];
 #pragma unroll
   for (int i = 0; i < BN; ++i) w2[i] = T(0);
+  constexpr int BNP = DxCoreLayout<T, Q, MB>::BNP;
 #pragma unroll
   for (int a = 0; a < A; ++a) {
-    T grow[BN];
+    T grow[BNP];
 #pragma unroll
-    for (int i = 0; i < BN; ++i) grow[i] = T(0);
-    for (int o = 0; o < O; ++o) {
+    for (int i = 0; i < BNP; ++i) grow[i] = T(0);
+    const T* ca = cs + a * BNP;
+    for (int o = 0; o < O; ++o) {           // core row (o, a): 128-bit broadcast loads, one per four FMAs
       const T gv = __ldg(gp + o);
 #pragma unroll
-      for (int i = 0; i < BN; ++i) grow[i] = fma(gv, cs[(a * BN + i) * O + o], grow[i]);
+      for (int i = 0; i < BNP; i += 4) {
+        T u[4];
+        ld4<T>(ca + (size_t)o * (A * BNP) + i, u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) grow[i + k] = fma(gv, u[k], grow[i + k]);
+      }
     }
     T s1 = T(0);
 #pragma unroll
@@ -785,9 +804,9 @@ __global__ void __launch_bounds__(DTHREADS) direct_dx_kernel(EpsGeom g, const T*
                                                              const T* __restrict__ gout, T* __restrict__ dxp) {
   constexpr int A = IPow<Q, MA>::v, BN = IPow<Q, MB>::v;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* cs = reinterpret_cast<T*>(smem_raw);           // core as stored: [A][BN][O]
+  T* cs = reinterpret_cast<T*>(smem_raw);           // core transposed: [O][A][BNP]
   const int O = g.O;
-  for (int i = threadIdx.x; i < A * BN * O; i += DTHREADS) cs[i] = core[i];
+  stage_core_transposed<T, A, BN, DxCoreLayout<T, Q, MB>::BNP>(cs, core, O, DTHREADS);
   __syncthreads();
   const unsigned hw = (unsigned)(g.Ho * g.Wo), Wo = (unsigned)g.Wo, P32 = (unsigned)g.P;
   for (unsigned p = blockIdx.x * DTHREADS + threadIdx.x; p < P32; p += gridDim.x * DTHREADS) {
@@ -809,10 +828,11 @@ __global__ void __launch_bounds__(DXI_THREADS) direct_dx_image_kernel(EpsGeom g,
                                                                       T* __restrict__ dx, int NPP) {
   constexpr int A = IPow<Q, MA>::v, BN = IPow<Q, MB>::v, NF = MA + MB;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* cs = reinterpret_cast<T*>(smem_raw);           // core [A][BN][O]
+  T* cs = reinterpret_cast<T*>(smem_raw);           // core transposed: [O][A][BNP]
   const int O = g.O;
-  T* dxs = cs + ((A * BN * O + 3) & ~3);            // [NF*Q][NPP]
-  for (int i = threadIdx.x; i < A * BN * O; i += DXI_THREADS) cs[i] = core[i];
+  constexpr int BNP = DxCoreLayout<T, Q, MB>::BNP;
+  T* dxs = cs + (size_t)O * A * BNP;                // [NF*Q][NPP]
+  stage_core_transposed<T, A, BN, BNP>(cs, core, O, DXI_THREADS);
   __syncthreads();
   const int b = blockIdx.x, Wo = g.Wo, npatch = g.Ho * g.Wo;
   for (int pl = threadIdx.x; pl < npatch; pl += DXI_THREADS) {
@@ -852,7 +872,7 @@ __global__ void __launch_bounds__(DXI_THREADS) direct_dx_image_kernel(EpsGeom g,
 // The per-image fused input gradient needs the image's per-patch contributions in shared memory.  A + Bn > 32 (K = 3,
 // Q = 2): the per-patch registers leave too few 256-thread CTAs per SM, the two-kernel path wins (measured).
 static bool dx_fused_fits(const EpsGeom& g, size_t es) {
-  const size_t fsm = ((size_t)((g.A * g.Bn * g.O + 3) & ~3) + (size_t)g.n * g.Q * ((g.Ho * g.Wo) | 1)) * es;
+  const size_t fsm = ((size_t)g.O * g.A * ((g.Bn + 3) & ~3) + (size_t)g.n * g.Q * ((g.Ho * g.Wo) | 1)) * es;
   return fsm <= 200 * 1024 && g.A + g.Bn <= 32 && !getenv("DCTN_B200_DX_UNFUSED");   // env: A/B switch to the two-kernel path
 }
 
@@ -881,7 +901,7 @@ int launch_direct_bwd(const EpsGeom& g, int kind, const T* x, const T* core, con
   }
   if (dx_fused_fits(g, sizeof(T))) {
     const int npatch = g.Ho * g.Wo, NPP = npatch | 1;
-    const size_t fsm = ((size_t)((A * BN * g.O + 3) & ~3) + (size_t)(MA + MB) * Q * NPP) * sizeof(T);
+    const size_t fsm = ((size_t)g.O * A * ((BN + 3) & ~3) + (size_t)(MA + MB) * Q * NPP) * sizeof(T);
     {
       auto kf = direct_dx_image_kernel<T, Q, MA, MB>;
       DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
@@ -891,7 +911,7 @@ int launch_direct_bwd(const EpsGeom& g, int kind, const T* x, const T* core, con
       return 0;
     }
   }
-  const size_t smem = (size_t)A * BN * g.O * sizeof(T);
+  const size_t smem = (size_t)g.O * A * ((BN + 3) & ~3) * sizeof(T);
   auto k = direct_dx_kernel<T, Q, MA, MB>;
   DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k<<<(unsigned)blocks, DTHREADS, smem, st>>>(g, x, core, gout, (T*)ws);
