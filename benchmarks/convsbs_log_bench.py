@@ -44,6 +44,7 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--cpu-windows", type=int, default=0, help="also time the reference formulation on this many windows on the host")
     ap.add_argument("--json", default="")
+    ap.add_argument("--full", action="store_true", help="also time conv_sbs_log_forward end to end (bond matrices from log x and log cores + ring) on a 3x3 snake string")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     NB, S = args.batch * 26 * 26, args.cores
@@ -92,6 +93,57 @@ def main():
         print(json.dumps(row), flush=True)
         del mats, og
         torch.cuda.empty_cache()
+    if args.full:
+        # BASELINE config 5 as worded: 28x28 synthetic input, batch 2048, through the public entry.  3x3 snake string, Q = 2,
+        # C = 1, one output core (O = 4), closed ring; the linear-space reference formulation (dctn/conv_sbs.py:258-304
+        # restated with einsum) on the same GPU beside it.
+        from dctn_b200.conv_sbs_log import conv_sbs_log_forward
+        from dctn_b200.pos2d import Pos2D
+
+        snake = [(0, 0), (0, 1), (0, 2), (1, 2), (1, 1), (1, 0), (2, 0), (2, 1), (2, 2)]
+        for r in map(int, args.bonds.split(",")):
+            torch.manual_seed(1)
+            outs = [1, 1, 1, 1, 4, 1, 1, 1, 1]
+            log_cores = [(0.3 * torch.randn(o, r, r, 2, device=dev)).requires_grad_(True) for o in outs]
+            log_x = (0.5 * torch.randn(1, args.batch, 28, 28, 2, device=dev)).requires_grad_(True)
+            pos = tuple(Pos2D(*p) for p in snake)
+
+            def lin_forward():
+                x = log_x.exp()
+                T = None
+                P = args.batch * 26 * 26
+                for core, (ph, pw) in zip(log_cores, snake):
+                    M = torch.einsum("pi,olri->polr", x[0][:, ph:ph + 26, pw:pw + 26].reshape(P, 2), core.exp())
+                    T = M.permute(0, 2, 1, 3) if T is None else torch.einsum("pxyl,polr->pxyor", T, M).reshape(P, T.shape[1], -1, M.shape[3])
+                return torch.einsum("pxyx->py", T).log()
+
+            def f_ours():
+                with torch.no_grad():
+                    return conv_sbs_log_forward(log_cores, pos, log_x)
+
+            def fb_ours():
+                for t in log_cores + [log_x]:
+                    t.grad = None
+                conv_sbs_log_forward(log_cores, pos, log_x).sum().backward()
+
+            def f_lin():
+                with torch.no_grad():
+                    return lin_forward()
+
+            def fb_lin():
+                for t in log_cores + [log_x]:
+                    t.grad = None
+                lin_forward().sum().backward()
+
+            err = (f_ours().reshape(-1, 4) - f_lin()).abs().max().item()
+            row = dict(kind="conv_sbs_log_forward 3x3 snake", bond=r, batch=args.batch, image=28, windows=NB,
+                       ours_fwd_ms=time_cuda(f_ours, args.iters), ours_fwdbwd_ms=time_cuda(fb_ours, args.iters),
+                       linear_space_einsum_gpu_fwd_ms=time_cuda(f_lin, args.iters),
+                       linear_space_einsum_gpu_fwdbwd_ms=time_cuda(fb_lin, args.iters), max_abs_diff_vs_linear_space=err)
+            rows.append(row)
+            print(json.dumps(row), flush=True)
+            del log_cores, log_x
+            torch.cuda.empty_cache()
     if args.json:
         json.dump(rows, open(args.json, "w"), indent=1)
 

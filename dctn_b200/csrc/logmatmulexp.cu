@@ -27,7 +27,9 @@ __global__ void __launch_bounds__(TS * TS) lme_fwd_kernel(const T* __restrict__ 
   __shared__ T As[TS][TS + 1];  // [t][r]
   __shared__ T Bs[TS][TS + 1];  // [r][i]
   const int tx = threadIdx.x % TS, ty = threadIdx.x / TS;
-  const int t = blockIdx.y * TS + ty, i = blockIdx.x * TS + tx;
+  // linear grid (Theta can exceed the 65535-block limit of grid.y: one row per ConvSBS window)
+  const unsigned nbx = (unsigned)(I + TS - 1) / TS, bx = blockIdx.x % nbx, by = blockIdx.x / nbx;
+  const int t = by * TS + ty, i = bx * TS + tx;
   T m = neg_inf<T>(), s = T(0);
   for (int r0 = 0; r0 < R; r0 += TS) {
     int ra = r0 + tx, rb = r0 + ty;
@@ -69,7 +71,8 @@ __global__ void __launch_bounds__(TS * TS) lme_bwd_a_kernel(const T* __restrict_
   __shared__ T Gs[TS][TS + 1];  // gout[t][i]
   __shared__ T Bs[TS][TS + 1];  // B[r][i]
   const int tx = threadIdx.x % TS, ty = threadIdx.x / TS;
-  const int t = blockIdx.y * TS + ty, r = blockIdx.x * TS + tx;
+  const unsigned nbx = (unsigned)(R + TS - 1) / TS, bx = blockIdx.x % nbx, by = blockIdx.x / nbx;
+  const int t = by * TS + ty, r = bx * TS + tx;
   const T a = (t < Th && r < R) ? A[(long long)t * R + r] : T(0);
   T acc = T(0);
   for (int i0 = 0; i0 < I; i0 += TS) {
@@ -77,7 +80,7 @@ __global__ void __launch_bounds__(TS * TS) lme_bwd_a_kernel(const T* __restrict_
     bool ok = (t < Th && ii < I);
     Os[ty][tx] = ok ? out[(long long)t * I + ii] : T(0);
     Gs[ty][tx] = ok ? gout[(long long)t * I + ii] : T(0);
-    int rb = blockIdx.x * TS + ty;
+    int rb = bx * TS + ty;
     Bs[ty][tx] = (rb < R && ii < I) ? B[(long long)rb * I + ii] : neg_inf<T>();
     __syncthreads();
 #pragma unroll
@@ -100,7 +103,8 @@ __global__ void __launch_bounds__(TS * TS) lme_bwd_b_kernel(const T* __restrict_
   __shared__ T Gs[TS][TS + 1];  // gout[t][i]
   __shared__ T As[TS][TS + 1];  // A[t][r]
   const int tx = threadIdx.x % TS, ty = threadIdx.x / TS;
-  const int r = blockIdx.y * TS + ty, i = blockIdx.x * TS + tx;
+  const unsigned nbx = (unsigned)(I + TS - 1) / TS, bx = blockIdx.x % nbx, by = blockIdx.x / nbx;
+  const int r = by * TS + ty, i = bx * TS + tx;
   const T b = (r < R && i < I) ? B[(long long)r * I + i] : T(0);
   T acc = T(0);
   for (int t0 = 0; t0 < Th; t0 += TS) {
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(TS * TS) lme_bwd_b_kernel(const T* __restrict_
     bool ok = (tt < Th && i < I);
     Os[ty][tx] = ok ? out[(long long)tt * I + i] : T(0);
     Gs[ty][tx] = ok ? gout[(long long)tt * I + i] : T(0);
-    int ra = blockIdx.y * TS + tx;
+    int ra = by * TS + tx;
     As[ty][tx] = (tt < Th && ra < R) ? A[(long long)tt * R + ra] : neg_inf<T>();
     __syncthreads();
 #pragma unroll
@@ -399,8 +403,9 @@ __global__ void __launch_bounds__(256, 6) lme_batched_bwd_vec_kernel(const float
 
 template <typename T>
 int lme_forward(const T* A, const T* B, T* out, int Th, int R, int I, cudaStream_t st) {
-  dim3 grid((I + TS - 1) / TS, (Th + TS - 1) / TS);
-  lme_fwd_kernel<T><<<grid, TS * TS, 0, st>>>(A, B, out, Th, R, I);
+  const long long nblk = (long long)((I + TS - 1) / TS) * ((Th + TS - 1) / TS);
+  if (nblk >= (1ll << 31)) return dctn_set_error(DCTN_ERR_UNSUPPORTED, "logmatmulexp: %lld output tiles exceed the grid limit", nblk);
+  lme_fwd_kernel<T><<<(unsigned)nblk, TS * TS, 0, st>>>(A, B, out, Th, R, I);
   dctn_count_launch();
   DCTN_CUDA_CHECK_RET(cudaGetLastError());
   return 0;
@@ -410,14 +415,15 @@ template <typename T>
 int lme_backward(const T* A, const T* B, const T* out, const T* gout, T* dA, T* dB, int Th, int R, int I,
                  cudaStream_t st) {
   if (dA) {
-    dim3 grid((R + TS - 1) / TS, (Th + TS - 1) / TS);
-    lme_bwd_a_kernel<T><<<grid, TS * TS, 0, st>>>(A, B, out, gout, dA, Th, R, I);
+    const long long nblk = (long long)((R + TS - 1) / TS) * ((Th + TS - 1) / TS);
+    if (nblk >= (1ll << 31)) return dctn_set_error(DCTN_ERR_UNSUPPORTED, "logmatmulexp backward: %lld tiles exceed the grid limit", nblk);
+    lme_bwd_a_kernel<T><<<(unsigned)nblk, TS * TS, 0, st>>>(A, B, out, gout, dA, Th, R, I);
     dctn_count_launch();
     DCTN_CUDA_CHECK_RET(cudaGetLastError());
   }
   if (dB) {
-    dim3 grid((I + TS - 1) / TS, (R + TS - 1) / TS);
-    lme_bwd_b_kernel<T><<<grid, TS * TS, 0, st>>>(A, B, out, gout, dB, Th, R, I);
+    const long long nblk = (long long)((I + TS - 1) / TS) * ((R + TS - 1) / TS);
+    lme_bwd_b_kernel<T><<<(unsigned)nblk, TS * TS, 0, st>>>(A, B, out, gout, dB, Th, R, I);
     dctn_count_launch();
     DCTN_CUDA_CHECK_RET(cudaGetLastError());
   }

@@ -12,6 +12,45 @@ from . import _lib
 _DTYPES = {torch.float32: _lib.F32, torch.float64: _lib.F64}
 
 
+# dB of a TALL product (Theta = one row per ConvSBS window, R and I small) is a reduction over Theta that the 2-D backward
+# kernel walks serially with R*I/256 CTAs.  Such products are cut into chunks of rows and handed to the batched kernel
+# (one chunk per batch element, log_B repeated): it yields dA directly and one dB partial per chunk, summed in fixed order.
+_TALL_THETA = 16384
+
+
+def _tall_chunk(R: int, I: int, es: int) -> int:
+    """Rows per chunk so that one chunk fits the batched backward kernel's shared memory (96 KiB)."""
+    budget = 90 * 1024 // es - R * I
+    return max(0, min(128, budget // (R + 2 * I)))
+
+
+def _tall_backward(a: Tensor, b: Tensor, out: Tensor, gout: Tensor, need_dA: bool):
+    theta, R = a.shape
+    I = b.shape[1]
+    tc = _tall_chunk(R, I, a.element_size())
+    nchunk = (theta + tc - 1) // tc
+    pad = nchunk * tc - theta
+
+    def chunks(t, width):
+        if pad:  # padding rows carry gout = 0: they add nothing to dB and their dA rows are dropped
+            t = torch.cat([t, t.new_zeros(pad, width)])
+        return t.reshape(nchunk, tc, width)
+
+    a3, o3, g3 = chunks(a, R), chunks(out, I), chunks(gout, I)
+    b3 = b.unsqueeze(0).expand(nchunk, R, I).contiguous()
+    dA3 = torch.empty_like(a3) if need_dA else None
+    dB3 = torch.empty_like(b3)
+    with torch.cuda.device(a.device):
+        rc = _lib.lib().dctn_logmatmulexp_batched_backward(
+            a3.data_ptr(), b3.data_ptr(), o3.data_ptr(), g3.data_ptr(),
+            dA3.data_ptr() if need_dA else None, dB3.data_ptr(), nchunk, tc, R, I, _DTYPES[a.dtype],
+            torch.cuda.current_stream().cuda_stream,
+        )
+    _lib.check(rc, "dctn_logmatmulexp_batched_backward (tall product)")
+    dA = dA3.reshape(-1, R)[:theta] if need_dA else None
+    return dA, dB3.sum(dim=0)
+
+
 class _LogMatMulExp(torch.autograd.Function):
     @staticmethod
     def forward(ctx, log_A: Tensor, log_B: Tensor) -> Tensor:
@@ -36,6 +75,8 @@ class _LogMatMulExp(torch.autograd.Function):
         theta, R = a.shape
         I = b.shape[1]
         gout = gout.contiguous()
+        if theta >= _TALL_THETA and ctx.needs_input_grad[1] and _tall_chunk(R, I, a.element_size()) >= 16:
+            return _tall_backward(a, b, out, gout, ctx.needs_input_grad[0])
         dA = torch.empty_like(a) if ctx.needs_input_grad[0] else None
         dB = torch.empty_like(b) if ctx.needs_input_grad[1] else None
         with torch.cuda.device(a.device):

@@ -325,6 +325,30 @@ def test_logmatmulexp_batched_full_size_identities():
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("shape", [(70001, 2, 64), (20000, 4, 24), (100000, 9, 5)])
+def test_logmatmulexp_tall_product(shape, dtype):
+    """One row per ConvSBS window: Theta beyond the 65535-block grid.y limit, dB as a chunked reduction over Theta."""
+    from dctn_b200.logmatmulexp import logmatmulexp
+
+    T, R, I = shape
+    gen = torch.Generator().manual_seed(77)
+    A = torch.randn(T, R, generator=gen, dtype=torch.float64).to(dtype)
+    B = torch.randn(R, I, generator=gen, dtype=torch.float64).to(dtype)
+    gout = torch.randn(T, I, generator=gen, dtype=torch.float64).to(dtype)
+    a64, b64 = A.double().clone().requires_grad_(True), B.double().clone().requires_grad_(True)
+    want = O.logmatmulexp(a64, b64)
+    want.backward(gout.double())
+    Ad, Bd = A.to(DEV).requires_grad_(True), B.to(DEV).requires_grad_(True)
+    out = logmatmulexp(Ad, Bd)
+    out.backward(gout.to(DEV))
+    assert rel_err(out, want) <= TOL[dtype]
+    assert rel_err(Ad.grad, a64.grad) <= TOL[dtype] and rel_err(Bd.grad, b64.grad) <= TOL[dtype]
+    Bd.grad = None
+    logmatmulexp(Ad.detach(), Bd).backward(gout.to(DEV))   # dB only
+    assert rel_err(Bd.grad, b64.grad) <= TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 @pytest.mark.parametrize("name", CONVSBS_LOG_CASES)
 def test_conv_sbs_log_golden(name, dtype):
     """log of the reference's ConvSBS.forward (dctn/conv_sbs.py:258-304) and gradients w.r.t. log cores / log input."""
