@@ -561,7 +561,7 @@ template <typename T, int Q, int MA, int MB>
 int try_launch_dcore_tiled(const EpsGeom& g, const T* x, const T* gout, T* part, int* blocks_out, cudaStream_t st) {
   constexpr int A = IPow<Q, MA>::v, BN = IPow<Q, MB>::v;
   constexpr int AP = (A + 3) & ~3, BNP = (BN + 3) & ~3;
-  const int NP = g.O * BNP, ntn_all = NP >> 2;
+  const int NP = g.O * BNP;
   int ngroups, ntn_group;
   dcore_tiled_groups(AP, NP, &ngroups, &ntn_group);
   const int ntiles = (AP >> 2) * ntn_group;            // tiles of a full group, <= 512
@@ -575,7 +575,6 @@ int try_launch_dcore_tiled(const EpsGeom& g, const T* x, const T* gout, T* part,
   const size_t red = (size_t)NS * AP * NPg * sizeof(T);
   if (red > smem) smem = red;
   if (smem > 160 * 1024) return 0;
-  (void)ntn_all;
   const long long nchunks = (g.P + PC - 1) / PC;
   const int per_sm = smem > 100 * 1024 ? 1 : smem > 70 * 1024 ? 2 : smem > 50 * 1024 ? 3 : 4;
   long long blocks = (148ll * per_sm + ngroups - 1) / ngroups;   // partials = blocks; the grid is blocks x ngroups
