@@ -570,7 +570,7 @@ int try_launch_dcore_tiled(const EpsGeom& g, const T* x, const T* gout, T* part,
   const int NPg = 4 * ntn_group;
   const int SA = ((AP >> 2) & 1) ? AP : AP + 4, SN = (ntn_group & 1) ? NPg : NPg + 4;   // odd multiples of 4
   int PC = 256;
-  while (PC > 64 && (size_t)PC * (SA + SN) * sizeof(T) > 64 * 1024) PC >>= 1;
+  while (PC > 64 && (size_t)PC * (SA + SN) * sizeof(T) > 72 * 1024) PC >>= 1;
   size_t smem = (size_t)PC * (SA + SN) * sizeof(T);
   const size_t red = (size_t)NS * AP * NPg * sizeof(T);
   if (red > smem) smem = red;
