@@ -16,7 +16,8 @@ LIB_PATH = os.environ.get("DCTN_B200_LIB") or os.path.join(_HERE, "libdctn_b200.
 F32, F64 = 0, 1
 VARIANT_AUTO, VARIANT_FFMA, VARIANT_TC3, VARIANT_TC1, VARIANT_DIRECT, VARIANT_TCH3 = 0, 1, 2, 3, 4, 5
 VARIANTS = {"auto": 0, "ffma": 1, "tc3": 2, "tc1": 3, "direct": 4, "tch3": 5}
-WS_FORWARD, WS_BACKWARD_CORE, WS_BACKWARD_INPUT, WS_BACKWARD_INPUT_SAVED = 0, 1, 2, 3
+WS_FORWARD, WS_BACKWARD_CORE, WS_BACKWARD_INPUT, WS_BACKWARD_INPUT_SAVED, WS_FORWARD_STATS = 0, 1, 2, 3, 4
+FAMILY_CUDA_CORE, FAMILY_TCGEN05, FAMILY_STREAMING = 1, 2, 4
 
 # every symbol include/dctn_b200.h declares: (name, restype, argtypes)
 SYMBOLS = {
@@ -25,6 +26,7 @@ SYMBOLS = {
     "dctn_launch_count": (c_ulonglong, []),
     "dctn_eps_plan_get": (c_void_p, [c_int] * 6),
     "dctn_eps_plan_describe": (c_char_p, [c_void_p]),
+    "dctn_eps_kernel_family": (c_int, [c_void_p, c_int, c_int, c_int, c_int]),
     "dctn_eps_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int, c_int]),
     "dctn_eps_forward": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p, c_size_t, c_void_p]),
     "dctn_eps_backward_core": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p, c_size_t, c_void_p]),
@@ -32,6 +34,9 @@ SYMBOLS = {
     "dctn_eps_saved_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
     "dctn_eps_forward_train": (c_int, [c_void_p] * 5 + [c_size_t] + [c_int] * 3 + [c_void_p, c_size_t, c_void_p]),
     "dctn_eps_backward_input_saved": (c_int, [c_void_p] * 5 + [c_size_t, c_void_p] + [c_int] * 3 + [c_void_p, c_size_t, c_void_p]),
+    "dctn_eps_forward_stats": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p, c_size_t, c_void_p]),
+    "dctn_window_stats_workspace_bytes": (c_size_t, [c_int] * 4),
+    "dctn_window_stats": (c_int, [c_void_p] + [c_int] * 7 + [c_void_p, c_void_p, c_size_t, c_void_p]),
     "dctn_eps_forward_from_pixels": (c_int, [c_void_p, c_void_p, ctypes.c_double, c_void_p, c_void_p] + [c_int] * 3 + [c_void_p]),
     "dctn_logmatmulexp_forward": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p]),
     "dctn_logmatmulexp_backward": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_void_p]),

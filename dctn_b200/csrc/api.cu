@@ -185,10 +185,25 @@ static int pick_family(const dctn_plan_t* pl, const EpsGeom& g, int kind) {
   return FAM_FFMA;
 }
 
+// which kernel family serves call `kind` at this size: 1 = CUDA-core (FFMA/DFMA), 2 = tcgen05 tensor-core, 4 = streaming
+// small-core; negative status when the plan's forced variant does not support the shape
+extern "C" int dctn_eps_kernel_family(const dctn_plan_t* pl, int B, int H, int W, int kind) {
+  int rc = check_call(pl, B, H, W);
+  if (rc) return rc;
+  if (kind < DCTN_WS_FORWARD || kind > DCTN_WS_BACKWARD_INPUT_SAVED) return dctn_set_error(DCTN_ERR_BAD_ARG, "kernel_family: unknown call kind %d", kind);
+  EpsGeom g;
+  fill_geom(pl, B, H, W, &g);
+  int fam = pick_family(pl, g, kind == DCTN_WS_BACKWARD_INPUT_SAVED ? DCTN_WS_BACKWARD_INPUT : kind);
+  if (fam < 0) return dctn_set_error(DCTN_ERR_UNSUPPORTED, "kernel_family: variant %d does not support this shape (%s)", pl->variant, pl->desc.c_str());
+  return fam;
+}
+
 extern "C" size_t dctn_eps_workspace_bytes(const dctn_plan_t* pl, int B, int H, int W, int kind) {
   if (check_call(pl, B, H, W)) return 0;
   EpsGeom g;
   fill_geom(pl, B, H, W, &g);
+  if (kind == DCTN_WS_FORWARD_STATS)   // the forward's workspace followed by the per-block partial sums
+    return ((dctn_eps_workspace_bytes(pl, B, H, W, DCTN_WS_FORWARD) + 255) & ~(size_t)255) + value_stats_workspace_bytes();
   int fam = pick_family(pl, g, kind == DCTN_WS_BACKWARD_INPUT_SAVED ? DCTN_WS_BACKWARD_INPUT : kind);
   if (kind == DCTN_WS_BACKWARD_INPUT_SAVED && fam != FAM_TC) return 256;
   size_t bytes = 0;
@@ -274,6 +289,42 @@ extern "C" int dctn_eps_backward_input(const dctn_plan_t* pl, const void* x, con
   return pl->dtype == DCTN_F32
              ? ffma_backward_input<float>(g, (const float*)x, (const float*)core, (const float*)gout, (float*)dx, ws, st)
              : ffma_backward_input<double>(g, (const double*)x, (const double*)core, (const double*)gout, (double*)dx, ws, st);
+}
+
+// ------------------------------------------------------------------------------------------------ statistics
+// forward + (sum, sum of squares) of its output accumulated into stats[0..1] (device doubles): the reduction of the
+// empirical-std initialisation (dctn/eps.py:163-181) slice by slice, no concatenated output, no second pass from HBM
+extern "C" int dctn_eps_forward_stats(const dctn_plan_t* pl, const void* x, const void* core, void* out, double* stats,
+                                      int B, int H, int W, void* ws, size_t ws_bytes, void* stream) {
+  if (!stats) return dctn_set_error(DCTN_ERR_BAD_ARG, "forward_stats: null stats pointer");
+  int rc = check_call(pl, B, H, W);
+  if (rc) return rc;
+  if ((rc = check_ws(pl, B, H, W, DCTN_WS_FORWARD_STATS, ws, ws_bytes))) return rc;
+  const size_t fwd_bytes = (dctn_eps_workspace_bytes(pl, B, H, W, DCTN_WS_FORWARD) + 255) & ~(size_t)255;
+  rc = dctn_eps_forward(pl, x, core, out, B, H, W, ws, fwd_bytes, stream);
+  if (rc) return rc;
+  const long long n = (long long)B * (H - pl->K + 1) * (W - pl->K + 1) * pl->O;
+  void* part = (char*)ws + fwd_bytes;
+  return pl->dtype == DCTN_F32 ? launch_value_stats<float>((const float*)out, n, stats, part, (cudaStream_t)stream)
+                               : launch_value_stats<double>((const double*)out, n, stats, part, (cudaStream_t)stream);
+}
+
+extern "C" size_t dctn_window_stats_workspace_bytes(int C, int B, int H, int W) {
+  if (C < 1 || B < 1 || H < 1 || W < 1) return 0;
+  return window_stats_workspace_bytes(C, B, H, W) + 256;
+}
+
+extern "C" int dctn_window_stats(const void* x, int C, int B, int H, int W, int Q, int K, int dtype, double* stats, void* ws,
+                                 size_t ws_bytes, void* stream) {
+  if (!x || !stats) return dctn_set_error(DCTN_ERR_BAD_ARG, "window_stats: null pointer");
+  if (C < 1 || B < 1 || Q < 1 || K < 1 || H < K || W < K)
+    return dctn_set_error(DCTN_ERR_BAD_ARG, "window_stats: bad sizes C=%d B=%d H=%d W=%d Q=%d K=%d", C, B, H, W, Q, K);
+  if (!ws || ws_bytes < dctn_window_stats_workspace_bytes(C, B, H, W) || ((uintptr_t)ws & 15))
+    return dctn_set_error(DCTN_ERR_WORKSPACE, "window_stats: 16-byte aligned workspace of %zu bytes needed, got %zu", dctn_window_stats_workspace_bytes(C, B, H, W), ws_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DCTN_F32) return launch_window_stats<float>((const float*)x, C, B, H, W, Q, K, stats, ws, st);
+  if (dtype == DCTN_F64) return launch_window_stats<double>((const double*)x, C, B, H, W, Q, K, stats, ws, st);
+  return dctn_set_error(DCTN_ERR_BAD_ARG, "window_stats: bad dtype %d", dtype);
 }
 
 // ------------------------------------------------------------------------------------------------ forward from raw pixels

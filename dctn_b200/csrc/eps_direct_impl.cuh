@@ -8,6 +8,10 @@
 // memory as [o][a][b] — is broadcast to all threads with 128-bit shared loads:
 //     out[p][o] = sum_a kr1[a] * (sum_b kr2[b] * core[a][b][o])
 // No Q^(K*K)-sized intermediate exists anywhere.  Algorithmic bytes per patch: Q floats of x (amortised) + O floats out.
+//
+// This file is the implementation shared by four translation units (eps_direct_{fwd,bwd}_{f32,f64}.cu): each defines
+// DCTN_DIRECT_PART and includes it, so that the ~190 kernel instantiations compile in parallel (one TU took 7 minutes).
+//   part 1 / 2: forward entry points, float / double        part 3 / 4: backward entry points, float / double
 #include <cstdlib>
 #include <type_traits>
 
@@ -941,6 +945,7 @@ int launch_direct(const EpsGeom& g, const T* x, const T* core, T* out, cudaStrea
 
 }  // namespace
 
+#if DCTN_DIRECT_PART == 1
 bool direct_supported(const EpsGeom& g, int dtype) {
   const size_t es = dtype == 0 ? 4 : 8;
   if ((size_t)g.A * (g.Bn + 4) * g.O * es > 36 * 1024) return false;   // transposed core in shared memory, >= 6 CTAs per SM
@@ -950,6 +955,8 @@ bool direct_supported(const EpsGeom& g, int dtype) {
   return false;
 }
 
+#endif
+#if DCTN_DIRECT_PART == 1 || DCTN_DIRECT_PART == 2
 template <typename T>
 int direct_forward(const EpsGeom& g, const T* x, const T* core, T* out, cudaStream_t st) {
   if (g.K == 2 && g.C == 1) {
@@ -965,7 +972,9 @@ int direct_forward(const EpsGeom& g, const T* x, const T* core, T* out, cudaStre
   return dctn_set_error(-2, "direct forward kernel: no instance for Q=%d with %d+%d factors", g.Q, g.m, g.n - g.m);
 }
 // phi fused into the forward (raw pixels in): K = 2, C = 1, Q = 2 — the HBM-bound first layer of config 1
+#if DCTN_DIRECT_PART == 1
 bool direct_pixels_supported(const EpsGeom& g, int dtype) { return g.K == 2 && g.C == 1 && g.Q == 2 && direct_supported(g, dtype); }
+#endif
 template <typename T>
 int direct_forward_pixels(const EpsGeom& g, const T* pixels, T scale, const T* core, T* out, cudaStream_t st) {
   switch (g.O) {
@@ -975,12 +984,17 @@ int direct_forward_pixels(const EpsGeom& g, const T* pixels, T scale, const T* c
     default: return launch_direct_k2<T, 2, 0, true>(g, pixels, core, out, st, scale);
   }
 }
+#if DCTN_DIRECT_PART == 1
 template int direct_forward_pixels<float>(const EpsGeom&, const float*, float, const float*, float*, cudaStream_t);
-template int direct_forward_pixels<double>(const EpsGeom&, const double*, double, const double*, double*, cudaStream_t);
 template int direct_forward<float>(const EpsGeom&, const float*, const float*, float*, cudaStream_t);
+#else
+template int direct_forward_pixels<double>(const EpsGeom&, const double*, double, const double*, double*, cudaStream_t);
 template int direct_forward<double>(const EpsGeom&, const double*, const double*, double*, cudaStream_t);
+#endif
+#endif  // forward parts
 
 // ---- backward entry points (core gradient: kind 1, input gradient: kind 2)
+#if DCTN_DIRECT_PART == 3
 static bool direct_shape_known(const EpsGeom& g) {
   if (g.P * g.O >= (1ll << 31) || (long long)g.C * g.B * g.H * g.W * g.Q >= (1ll << 31)) return false;  // 32-bit index math
   for (const DirectShape& s : kShapes)
@@ -1004,6 +1018,8 @@ size_t direct_workspace_bytes(const EpsGeom& g, int dtype, int kind) {
   if (kind == 2) return dx_fused_fits(g, es) ? 256 : (size_t)g.P * g.n * g.Q * es + 256;
   return 256;
 }
+#endif
+#if DCTN_DIRECT_PART == 3 || DCTN_DIRECT_PART == 4
 template <typename T>
 int direct_backward(const EpsGeom& g, int kind, const T* x, const T* core, const T* gout, T* result, void* ws, cudaStream_t st) {
 #define DCTN_DIRECT_CASE(q, ma, mb) \
@@ -1014,5 +1030,9 @@ int direct_backward(const EpsGeom& g, int kind, const T* x, const T* core, const
 #undef DCTN_DIRECT_CASE
   return dctn_set_error(-2, "direct backward kernel: no instance for Q=%d with %d+%d factors", g.Q, g.m, g.n - g.m);
 }
+#if DCTN_DIRECT_PART == 3
 template int direct_backward<float>(const EpsGeom&, int, const float*, const float*, const float*, float*, void*, cudaStream_t);
+#else
 template int direct_backward<double>(const EpsGeom&, int, const double*, const double*, const double*, double*, void*, cudaStream_t);
+#endif
+#endif  // backward parts

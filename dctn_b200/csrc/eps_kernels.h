@@ -63,3 +63,9 @@ template <typename T> int lme_backward(const T* A, const T* B, const T* out, con
 // batched small matrices: A [NB][Th][R], B [NB][R][I] -> out [NB][Th][I] (ConvSBS bond-matrix rings in log space)
 template <typename T> int lme_batched_forward(const T* A, const T* B, T* out, long long NB, int Th, int R, int I, cudaStream_t st);
 template <typename T> int lme_batched_backward(const T* A, const T* B, const T* out, const T* gout, T* dA, T* dB, long long NB, int Th, int R, int I, cudaStream_t st);
+
+// ---- statistics (stats.cu): (sum, sum of squares) accumulated in double INTO stats[0..1]
+size_t value_stats_workspace_bytes();
+template <typename T> int launch_value_stats(const T* v, long long n, double* stats, void* ws, cudaStream_t st);
+size_t window_stats_workspace_bytes(int C, int B, int H, int W);
+template <typename T> int launch_window_stats(const T* x, int C, int B, int H, int W, int Q, int K, double* stats, void* ws, cudaStream_t st);

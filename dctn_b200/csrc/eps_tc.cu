@@ -492,6 +492,7 @@ int tc_backward_core(const EpsGeom& g, const float* x, const float* gout, float*
   DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((g.A + BM - 1) / BM, (g.N + BN - 1) / BN, splits);
   a.dbg = nullptr;
+#ifdef DCTN_TCG_TIMING   // cycle probes: timing builds only (allocates, synchronises, not thread-safe)
   static long long* dbg_buf = nullptr;
   const int ncta = (int)(grid.x * grid.y * grid.z);
   if (getenv("DCTN_TCG_DEBUG") && ncta <= 4096) {
@@ -499,9 +500,11 @@ int tc_backward_core(const EpsGeom& g, const float* x, const float* gout, float*
     cudaMemsetAsync(dbg_buf, 0, 4096 * 16 * sizeof(long long), st);
     a.dbg = dbg_buf;
   }
+#endif
   kern<<<grid, NTHREADS_TC, smem, st>>>(a);
   dctn_count_launch();
   DCTN_CUDA_CHECK_RET(cudaGetLastError());
+#ifdef DCTN_TCG_TIMING
   if (a.dbg) {
     static long long host[4096 * 16];
     cudaStreamSynchronize(st);
@@ -514,5 +517,6 @@ int tc_backward_core(const EpsGeom& g, const float* x, const float* gout, float*
             sum[0] / nch, sum[1] / nch, sum[2] / nch, sum[3] / nch, sum[5] / nch, sum[6] / nch, sum[7] / nch, sum[8] / nch,
             sum[9] / nch, sum[10] / nch, sum[11] / nch);
   }
+#endif
   return launch_reduce_partials<float>(a.part, dcore, (long long)g.A * g.N, splits, st);
 }

@@ -558,6 +558,7 @@ int tc16_backward_core(const EpsGeom& g0, const float* x, const float* gout, flo
   DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((g.A + BM - 1) / BM, g.BH * ntile, splits);
   a.dbg = nullptr;
+#ifdef DCTN_TCG_TIMING   // cycle probes: timing builds only (allocates, synchronises, not thread-safe)
   static long long* dbg_buf = nullptr;
   const long long ncta = (long long)grid.x * grid.y * grid.z;
   if (getenv("DCTN_TCG_DEBUG") && ncta <= 4096) {
@@ -565,9 +566,11 @@ int tc16_backward_core(const EpsGeom& g0, const float* x, const float* gout, flo
     cudaMemsetAsync(dbg_buf, 0, 4096 * 16 * sizeof(long long), st);
     a.dbg = dbg_buf;
   }
+#endif
   kern<<<grid, NTHREADS, smem, st>>>(a);
   dctn_count_launch();
   DCTN_CUDA_CHECK_RET(cudaGetLastError());
+#ifdef DCTN_TCG_TIMING
   if (a.dbg) {
     static long long host[4096 * 16];
     cudaStreamSynchronize(st);
@@ -578,6 +581,7 @@ int tc16_backward_core(const EpsGeom& g0, const float* x, const float* gout, flo
     fprintf(stderr, "[dcore16 dbg] NT=%d ctas=%lld splits=%d chunks/cta=%.0f per-chunk cycles: mma wait acc %.0f B %.0f A %.0f total %.0f | producer: wait-tables %.0f rows %.0f drain %.0f\n",
             NT, ncta, splits, nch / ncta, sum[0] / nch, sum[1] / nch, sum[2] / nch, sum[3] / nch, sum[5] / nch, sum[6] / nch, sum[7] / nch);
   }
+#endif
   const long long count = (long long)g.A * g.N;
   int blocks = (int)((count + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;

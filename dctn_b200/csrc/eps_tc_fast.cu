@@ -906,6 +906,7 @@ int tcfast_gemm(const EpsGeom& g, int mode, const float* x, const float* gout, c
   a.bstages = fast_bstages(g, s, mode, BN);
   a.packed = packed; a.core_absmax = absmax; a.out = out; a.ldc = ldc; a.tsave = tsave;
   a.dbg = nullptr;
+#ifdef DCTN_TCG_TIMING   // cycle probes: timing builds only (allocates, synchronises, not thread-safe)
   static long long* dbg_buf = nullptr;
   const int ncta = (np + FBM - 1) / FBM;
   if (getenv("DCTN_TCG_DEBUG") && ncta <= 4096) {
@@ -913,10 +914,12 @@ int tcfast_gemm(const EpsGeom& g, int mode, const float* x, const float* gout, c
     cudaMemsetAsync(dbg_buf, 0, 4096 * 8 * sizeof(long long), st);
     a.dbg = dbg_buf;
   }
+#endif
   const size_t smem = fast_fixed_smem(g, s, mode) + a.bstages * fast_stage_bytes(BN);
   int rc = (mode == FMODE_FWD) ? launch_fast_klr<FMODE_FWD>(a, s.KLR, smem, st)
          : (mode == FMODE_LOO) ? launch_fast_klr<FMODE_LOO>(a, s.KLR, smem, st)
          : (mode == FMODE_LOOX) ? launch_fast_klr<FMODE_LOOX>(a, s.KLR, smem, st) : launch_fast_klr<FMODE_STORE>(a, s.KLR, smem, st);
+#ifdef DCTN_TCG_TIMING
   if (a.dbg && rc == 0) {
     static long long host[4096 * 8];
     cudaStreamSynchronize(st);
@@ -929,5 +932,6 @@ int tcfast_gemm(const EpsGeom& g, int mode, const float* x, const float* gout, c
             sum[0] / ncta / nst, sum[1] / ncta / nst, sum[2] / ncta / a.ntiles, sum[3] / ncta / nst,
             sum[4] / ncta, sum[5] / ncta, sum[6] / ncta / nst, sum[7] / ncta / a.ntiles);
   }
+#endif
   return rc;
 }

@@ -727,6 +727,7 @@ int run_gemm(const EpsGeom& g, int mode, int BN, const float* x, const float* go
   a.core_absmax = absmax;
   a.tsave = tsave;
   a.dbg = nullptr;
+#ifdef DCTN_TCG_TIMING   // cycle probes: timing builds only (allocates, synchronises, not thread-safe)
   static long long* dbg_buf = nullptr;
   const char* dbg_env = getenv("DCTN_TCG_DEBUG");
   const int ncta = (np + GBM - 1) / GBM;
@@ -735,11 +736,13 @@ int run_gemm(const EpsGeom& g, int mode, int BN, const float* x, const float* go
     cudaMemsetAsync(dbg_buf, 0, 4096 * 8 * sizeof(long long), st);
     a.dbg = dbg_buf;
   }
+#endif
   const size_t smem = gemm_fixed_smem(g, s, mode) + a.bstages * bstage_bytes(BN);
   int rc;
   if (mode == MODE_STORE) rc = f16 ? launch_gemm_inst<MODE_STORE, true>(a, smem, st) : launch_gemm_inst<MODE_STORE, false>(a, smem, st);
   else if (mode == MODE_FWD) rc = f16 ? launch_gemm_inst<MODE_FWD, true>(a, smem, st) : launch_gemm_inst<MODE_FWD, false>(a, smem, st);
   else rc = f16 ? launch_gemm_inst<MODE_DKR2, true>(a, smem, st) : launch_gemm_inst<MODE_DKR2, false>(a, smem, st);
+#ifdef DCTN_TCG_TIMING
   if (a.dbg && rc == 0) {
     static long long host[4096 * 8];
     cudaStreamSynchronize(st);
@@ -752,6 +755,7 @@ int run_gemm(const EpsGeom& g, int mode, int BN, const float* x, const float* go
             sum[0] / ncta / nst, sum[1] / ncta / nst, sum[2] / ncta / a.ntiles, sum[3] / ncta / nst,
             sum[4] / ncta / nst, sum[5] / ncta / nst, sum[6] / ncta / nst, sum[7] / ncta / a.ntiles);
   }
+#endif
   return rc;
 }
 

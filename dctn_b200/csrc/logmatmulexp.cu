@@ -451,11 +451,8 @@ static int lme_batched_group(size_t per_elem_bytes, int work_per_elem, long long
 template <int R>
 static int launch_fwd_vec(const float* A, const float* B, float* out, long long NB, int Th, int I, int G, size_t smem,
                           cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(lme_batched_fwd_vec_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_done = true;
-  }
+  // per device/context attribute: set on every launch (a process-wide flag would cover only the first GPU used)
+  DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(lme_batched_fwd_vec_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   long long groups = (NB + G - 1) / G;
   int grid = (int)(groups < 148LL * 16 ? groups : 148LL * 16);
   lme_batched_fwd_vec_kernel<R><<<grid, 256, smem, st>>>(A, B, out, NB, Th, I, G);
@@ -484,11 +481,7 @@ int lme_batched_forward(const T* A, const T* B, T* out, long long NB, int Th, in
   if (G == 0)
     return dctn_set_error(DCTN_ERR_UNSUPPORTED, "logmatmulexp_batched: a (%d x %d) x (%d x %d) pair does not fit shared memory; use the 2-D entry per element", Th, R, R, I);
   // G == 1 with odd block sizes: stage_in falls back to scalar loads on its own (alignment test)
-  static bool attr_done[2] = {false, false};
-  if (!attr_done[sizeof(T) == 8]) {
-    DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(lme_batched_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_done[sizeof(T) == 8] = true;
-  }
+  DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(lme_batched_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   long long groups = (NB + G - 1) / G;
   int grid = (int)(groups < 148LL * 16 ? groups : 148LL * 16);
   lme_batched_fwd_kernel<T><<<grid, 256, smem, st>>>(A, B, out, NB, Th, R, I, G);
@@ -505,19 +498,11 @@ int lme_batched_backward(const T* A, const T* B, const T* out, const T* gout, T*
   int G = lme_batched_group(sizeof(T) * ((size_t)Th * R + (size_t)R * I + 2 * (size_t)Th * I), work, NB, &smem);
   if (G == 0)
     return dctn_set_error(DCTN_ERR_UNSUPPORTED, "logmatmulexp_batched backward: a (%d x %d) x (%d x %d) pair does not fit shared memory", Th, R, R, I);
-  static bool attr_done[2] = {false, false};
-  if (!attr_done[sizeof(T) == 8]) {
-    DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(lme_batched_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_done[sizeof(T) == 8] = true;
-  }
+  DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(lme_batched_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   long long groups = (NB + G - 1) / G;
   int grid = (int)(groups < 148LL * 16 ? groups : 148LL * 16);
   if (lme_vec_ok(sizeof(T), 1, I, G)) {
-    static bool vec_attr_done = false;
-    if (!vec_attr_done) {
-      DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(lme_batched_bwd_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      vec_attr_done = true;
-    }
+    DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(lme_batched_bwd_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     lme_batched_bwd_vec_kernel<<<grid, 256, smem, st>>>((const float*)A, (const float*)B, (const float*)out, (const float*)gout,
                                                         (float*)dA, (float*)dB, NB, Th, R, I, G);
     dctn_count_launch();

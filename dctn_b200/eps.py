@@ -60,6 +60,16 @@ def plan_description(core: Tensor, input: Tensor) -> str:
     return _lib.lib().dctn_eps_plan_describe(_plan(C, K, Q, O, input.dtype, _default_variant)).decode()
 
 
+def kernel_families(core: Tensor, input: Tensor) -> Dict[str, int]:
+    """Which kernel family (``_lib.FAMILY_*``) serves the forward, core-gradient and input-gradient calls of this
+    layer at this input size under the current default variant (dctn_eps_kernel_family)."""
+    C, K, Q, O = _infer(core, input)
+    _, B, H, W, _ = input.shape
+    plan = _plan(C, K, Q, O, input.dtype, _default_variant)
+    kinds = {"forward": _lib.WS_FORWARD, "backward_core": _lib.WS_BACKWARD_CORE, "backward_input": _lib.WS_BACKWARD_INPUT}
+    return {name: _lib.lib().dctn_eps_kernel_family(plan, B, H, W, kind) for name, kind in kinds.items()}
+
+
 def _infer(core: Tensor, input: Tensor) -> Tuple[int, int, int, int]:
     """Shape contract of dctn/eps.py:20-23 (AssertionError on mismatch, like the reference)."""
     num_channels, batch_size, height, width, in_size = input.shape
@@ -305,19 +315,67 @@ def make_eps_unit_theoretical_output_std(
     return std * torch.randn(*shape, dtype=dtype).to(device)
 
 
+@torch.no_grad()
+def transform_in_slices_with_stats(eps_core: Tensor, x: Tensor, batch_size: int) -> Tuple[Tensor, Tensor]:
+    """transform_in_slices that also returns the float64 pair (sum, sum of squares) of the whole output, reduced on the
+    GPU right after each slice's forward (dctn_eps_forward_stats): every slice writes straight into its part of ONE
+    preallocated output, so there is no torch.cat and no separate pass for the statistics."""
+    assert is_eps(eps_core)
+    _check_device(eps_core, x)
+    C, K, Q, O = _infer(eps_core, x)
+    _, N, H, W, _ = x.shape
+    core_c = _dense(eps_core)
+    plan = _plan(C, K, Q, O, x.dtype, _default_variant)
+    out = torch.empty((N, H - K + 1, W - K + 1, O), dtype=x.dtype, device=x.device)
+    stats = torch.zeros(2, dtype=torch.float64, device=x.device)
+    lib = _lib.lib()
+    with torch.cuda.device(x.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        ws = None
+        for b0 in range(0, N, batch_size):
+            piece = _dense(x[:, b0 : b0 + batch_size])
+            B = piece.shape[1]
+            need = lib.dctn_eps_workspace_bytes(plan, B, H, W, _lib.WS_FORWARD_STATS)
+            if ws is None or ws.numel() < need:
+                ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+            dst = out[b0 : b0 + B]
+            aligned = dst.data_ptr() % 16 == 0        # the kernels store 128 bits at a time
+            tmp = dst if aligned else torch.empty_like(dst)
+            rc = lib.dctn_eps_forward_stats(
+                plan, piece.data_ptr(), core_c.data_ptr(), tmp.data_ptr(), stats.data_ptr(), B, H, W,
+                ws.data_ptr(), ws.numel(), stream,
+            )
+            _lib.check(rc, "dctn_eps_forward_stats")
+            if not aligned:
+                dst.copy_(tmp)
+    return out.unsqueeze(0), stats
+
+
+def _empirical_std_core_and_output(
+    kernel_size: int, out_size: int, input: Tensor, device: torch.device, dtype: torch.dtype, batch_size: int
+) -> Tuple[Tensor, Tensor]:
+    """The core of make_eps_unit_empirical_output_std and its output on `input`.  The contraction is linear in the core, so
+    the output of the rescaled core is the unscaled output times the same factor: ONE pass over the dataset instead of the
+    reference's two (dctn/eps.py:176 and dctn/epses_composition.py:103)."""
+    num_channels, dataset_size, height, width, in_size = input.shape
+    core = torch.randn(*(in_size,) * (kernel_size ** 2 * num_channels), out_size, dtype=dtype).to(device)
+    output, stats = transform_in_slices_with_stats(core, input.to(device, dtype), batch_size)
+    n = output.numel()
+    mean = stats[0] / n
+    inv_std = ((stats[1] / n - mean * mean) ** -0.5).to(dtype)      # biased std, as output.std(unbiased=False)
+    logger = logging.getLogger(f"{__name__}.make_eps_unit_empirical_output_std")
+    logger.info(f"Multiplying the output of randn by {inv_std:.30e}")
+    core *= inv_std
+    output *= inv_std
+    logger.info(f"Initialized an EPS with empirical std = {core.std(unbiased=False):.30e}")
+    return core, output
+
+
 def make_eps_unit_empirical_output_std(
     kernel_size: int, out_size: int, input: Tensor, device: torch.device, dtype: torch.dtype, batch_size: int
 ) -> Tensor:
     """randn core rescaled so that its output on `input` has unit (biased) std (dctn/eps.py:163-181)."""
-    num_channels, dataset_size, height, width, in_size = input.shape
-    core = torch.randn(*(in_size,) * (kernel_size ** 2 * num_channels), out_size, dtype=dtype).to(device)
-    output = transform_in_slices(core, input.to(device, dtype), batch_size)
-    inv_std = output.std(unbiased=False) ** -1
-    logger = logging.getLogger(f"{__name__}.make_eps_unit_empirical_output_std")
-    logger.info(f"Multiplying the output of randn by {inv_std:.30e}")
-    core *= inv_std
-    logger.info(f"Initialized an EPS with empirical std = {core.std(unbiased=False):.30e}")
-    return core
+    return _empirical_std_core_and_output(kernel_size, out_size, input, device, dtype, batch_size)[0]
 
 
 class EPS(nn.Module):

@@ -16,6 +16,7 @@ import torch.nn.functional as F
 from torch import Tensor
 
 from . import eps, epses_composition
+from .align import make_windows
 from .eps import EPS  # noqa: F401  (re-exported like the reference)
 from .utils import (  # noqa: F401
     FromFileInitialization,
@@ -121,8 +122,8 @@ class EPSesPlusLinear(nn.Module):
 
     @torch.no_grad()
     def log_intermediate_reps_stats(self, x: Tensor, batch_size: int = 128) -> None:
-        """Logs mean/std of every intermediate representation in eval mode
-        (dctn/eps_plus_linear.py:161-196, without the rank-one window statistics, which are out of scope)."""
+        """Logs mean/std of every intermediate representation and of its K x K windows in eval mode
+        (dctn/eps_plus_linear.py:161-196; same log lines)."""
         logger = getLogger(f"{__name__}.EPSesPlusLinear.log_intermediate_reps_stats")
         logger.info("Logging intermediate reps stats as if self.training == False")
 
@@ -130,10 +131,20 @@ class EPSesPlusLinear(nn.Module):
             mu, sigma = t.mean(), t.std(unbiased=False)
             logger.info(f"{name}: μ={mu:.7e}, σ={sigma:.7e}, μ**2+σ**2={mu**2+sigma**2:.7e}, shape={tuple(t.shape)}")
 
+        def log_windows(windows, name: str) -> None:
+            mu, sigma = windows.mean_over_batch(), windows.std_over_batch(unbiased=False)
+            logger.info(
+                f"{name}: μ={mu:.7e}, σ={sigma:.7e}, μ**2+σ**2={mu**2+sigma**2:.7e}, "
+                f"batch_shape={windows.batch_shape}, "
+                f"num_factors={windows.num_factors}, "
+                f"num_coordinates_in_one_factor={windows.num_coordinates_in_one_factor}"
+            )
+
         for n, core in enumerate(self.epses):
             log_one(x, f"x_{n}")
             kernel_size = math.isqrt(core.ndim - 1)
             assert kernel_size ** 2 == core.ndim - 1
+            log_windows(make_windows(x, kernel_size), f"w_{n}")
             x = eps.transform_in_slices(core, x, batch_size)
         x = x.squeeze(0).flatten(start_dim=1)
         log_one(x, f"x_{len(self.epses)}")

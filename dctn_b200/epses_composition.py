@@ -72,8 +72,7 @@ def make_epses_composition_unit_empirical_output_std(
     of the CUDA forward kernel."""
     cores = []
     for kernel_size, out_size in epses_specs:
-        core = eps.make_eps_unit_empirical_output_std(kernel_size, out_size, input, device, dtype, batch_size)
-        input = eps.transform_in_slices(core, input.to(device, dtype), batch_size)
+        core, input = eps._empirical_std_core_and_output(kernel_size, out_size, input, device, dtype, batch_size)
         cores.append(core)
     return tuple(cores)
 

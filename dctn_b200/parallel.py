@@ -5,9 +5,8 @@ training_configurations/get_adequate_results_with_cifar10_rgb/lr_gridsearch.py:6
 the batch axis (dim 1 of the (C, B, H, W, Q) input): patches of different images are independent in the
 forward and in the input gradient; only the parameter gradients (cores + linear, 7.5 MB at config 2) are sums
 over the batch.  So: one process per GPU, parameters replicated, each rank runs the unchanged single-GPU
-kernels on its B/world images, and ONE collective per step — an NCCL all-reduce over a flat bucket of all
-parameter gradients, issued after the backward pass — averages the gradients (``F.cross_entropy`` averages over
-the local batch, dctn/training.py:78).  No activation crosses GPUs.
+kernels on its B/world images, and the only collective is the average of the parameter gradients
+(``F.cross_entropy`` averages over the local batch, dctn/training.py:78).  No activation crosses GPUs.
 
 Works with any torch.distributed backend (``nccl`` on GPUs, ``gloo`` in the CPU tests).
 """
@@ -29,69 +28,145 @@ def shard_batch(x: Tensor, rank: int, world_size: int, dim: int = 1) -> Tensor:
     return x.narrow(dim, rank * per, per)
 
 
-class GradAllReducer:
-    """Averages parameter gradients across ranks.  Call :meth:`wait` after ``backward()`` and before
-    ``optimizer.step()``.
+def _is_nccl(group) -> bool:
+    try:
+        return dist.get_backend(group) == "nccl"
+    except Exception:
+        return False
 
-    Default (``overlap=False``): ONE all-reduce over a flat bucket holding every gradient (7.5 MB at config 2, ~20 us on
-    NVLink 5) issued when the backward pass is complete.  The EPS kernels are persistent-style — one CTA per SM, all of the
-    SM's shared memory and tensor memory — so a collective launched *during* backward cannot co-reside with them: its
-    CTAs wait for SMs, then hold them while spinning on the peers, and every following one-wave kernel launch turns
-    into two waves.  Measured at N=2: 27.2 ms/step with per-parameter all-reduces overlapped from the gradient hooks
-    against 21.0 ms at N=1; the flat bucket after backward removes that.
-    ``overlap=True`` keeps the hook-driven variant (one async all-reduce per parameter as soon as its gradient is
-    accumulated) for models whose kernels leave SMs free."""
+
+class GradAllReducer:
+    """Averages parameter gradients across ranks.  Call :meth:`zero_grad` before ``backward()`` and :meth:`wait` after
+    it, before ``optimizer.step()``.
+
+    Layout: ONE flat bucket holds every gradient, in a FIXED layout over all parameters that require a gradient (the same
+    on every rank, whatever subset of gradients a step produces), and every ``p.grad`` is a VIEW into it — autograd
+    accumulates straight into the bucket, so the collective needs no gather / scatter copies.  A parameter that received
+    no gradient in a step contributes zeros (its view was zeroed by :meth:`zero_grad`).
+
+    ``overlap=False`` (default): one all-reduce (average) over the whole bucket when the backward pass is complete.
+    ``overlap=True``: the bucket is cut in two at ``params[:early]`` / the rest, in the ORDER GRADIENTS BECOME READY
+    (pass the parameters last-layer first: linear, last EPS core, ..., first EPS core).  The early part — everything but
+    the first layer's core — is all-reduced asynchronously from the gradient hook of its last parameter while the first
+    layer's core gradient is still being computed; :meth:`wait` reduces the remainder and joins.  Use it with a
+    CTA-limited NCCL communicator (:func:`make_comm_group`): the EPS kernels occupy every SM with one CTA, so the
+    collective's CTAs take over SMs as EPS CTAs retire, and a handful of them costs a few percent of the SMs for the
+    ~50 us of the transfer instead of stalling whole waves."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None,
-                 broadcast_from: int = 0, overlap: bool = False):
+                 broadcast_from: int = 0, overlap: bool = False, early: Optional[int] = None):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        assert self.params, "no parameter requires a gradient"
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.overlap = overlap
-        self._pending = []
+        self.overlap = overlap and self.world > 1
         self._handles = []
-        self._flat: Optional[Tensor] = None
+        self._work = []
+        self._flat = None
+        if self.world == 1:      # nothing to reduce: gradients stay ordinary tensors
+            return
+        first = self.params[0]
+        assert all(p.dtype == first.dtype and p.device == first.device for p in self.params), \
+            "all parameters must share dtype and device (one flat bucket)"
+        self._sizes = [p.numel() for p in self.params]
+        # 128-byte aligned slots so that every view satisfies the kernels' 16-byte alignment
+        es = first.element_size()
+        align = max(1, 128 // es)
+        self._offsets, off = [], 0
+        for n in self._sizes:
+            self._offsets.append(off)
+            off += (n + align - 1) // align * align
+        self._flat = torch.zeros(off, dtype=first.dtype, device=first.device)
+        self._views = [self._flat[o:o + n].view_as(p) for o, n, p in zip(self._offsets, self._sizes, self.params)]
+        self._early = len(self.params) - 1 if early is None else early
+        self._early = max(0, min(self._early, len(self.params)))
+        self._cut = self._offsets[self._early] if self._early < len(self.params) else off
+        self._avg = _is_nccl(group) if self.world > 1 else False
         if self.world > 1:
             for p in self.params:  # replicas start identical
                 dist.broadcast(p.data, src=broadcast_from, group=group)
-            if overlap:
-                for p in self.params:
-                    self._handles.append(p.register_post_accumulate_grad_hook(self._on_grad_ready))
+            if self.overlap and self._early > 0:
+                trigger = self.params[self._early - 1]
+                self._handles.append(trigger.register_post_accumulate_grad_hook(self._on_early_ready))
+        self.zero_grad()
 
-    def _on_grad_ready(self, p: torch.nn.Parameter) -> None:
-        # pre-scale so that the SUM all-reduce yields the mean (cross_entropy averages over the local batch)
-        p.grad.div_(self.world)
-        work = dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self._pending.append(work)
+    # -- gradients live in the bucket
+    def zero_grad(self) -> None:
+        """Zeroes the bucket (one memset) and (re)attaches every ``p.grad`` to its view.  Replaces
+        ``optimizer.zero_grad()``, whose default ``set_to_none=True`` would detach the gradients from the bucket."""
+        if self.world == 1:
+            for p in self.params:
+                p.grad = None
+            return
+        self._flat.zero_()
+        for p, v in zip(self.params, self._views):
+            if p.grad is not v:
+                p.grad = v
+
+    def _attached(self) -> bool:
+        return all(p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v in zip(self.params, self._views))
+
+    def _reattach(self) -> None:
+        """A caller used optimizer.zero_grad(set_to_none=True) (or autograd replaced a gradient tensor): copy what exists
+        into the fixed layout — missing gradients stay zero — so every rank still reduces the same buffer."""
+        self._flat.zero_()
+        for p, v in zip(self.params, self._views):
+            if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad)
+            p.grad = v
+
+    def _reduce(self, t: Tensor, async_op: bool):
+        if self._avg:
+            return dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group, async_op=async_op)
+        t.div_(self.world)   # SUM of pre-scaled gradients = mean over ranks (gloo has no AVG)
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
+
+    def _on_early_ready(self, _p: torch.nn.Parameter) -> None:
+        # hooks fire in backward order: everything in params[:early] is accumulated when the last of them is
+        if self._attached():
+            self._work.append(self._reduce(self._flat[: self._cut], async_op=True))
 
     def wait(self) -> None:
         if self.world == 1:
             return
         if self.overlap:
-            for work in self._pending:
-                work.wait()
-            self._pending.clear()
+            # ALWAYS the same two collectives in the same order on every rank ([:cut], then [cut:]), whether or not this
+            # rank's hook fired (a rank whose trigger parameter got no gradient this step must not fall out of step)
+            if not self._work:
+                if not self._attached():
+                    self._reattach()
+                if self._cut > 0:
+                    self._work.append(self._reduce(self._flat[: self._cut], async_op=True))
+            if self._cut < self._flat.numel():
+                self._work.append(self._reduce(self._flat[self._cut:], async_op=True))
+            for w in self._work:
+                w.wait()
+            self._work.clear()
             return
-        grads = [p.grad for p in self.params if p.grad is not None]
-        if not grads:
-            return
-        n = sum(g.numel() for g in grads)
-        if self._flat is None or self._flat.numel() != n or self._flat.device != grads[0].device or self._flat.dtype != grads[0].dtype:
-            self._flat = torch.empty(n, dtype=grads[0].dtype, device=grads[0].device)
-        views = []
-        off = 0
-        for g in grads:
-            views.append(self._flat[off:off + g.numel()].view_as(g))
-            off += g.numel()
-        torch._foreach_copy_(views, grads)
-        self._flat.div_(self.world)   # SUM of pre-scaled gradients = mean over ranks
-        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.group)
-        torch._foreach_copy_(grads, views)
+        if not self._attached():
+            self._reattach()
+        self._reduce(self._flat, async_op=False)
+
+    @property
+    def flat_grad(self) -> Tensor:
+        return self._flat
 
     def remove(self) -> None:
         for h in self._handles:
             h.remove()
         self._handles.clear()
+
+
+def make_comm_group(max_ctas: int = 4):
+    """A second NCCL communicator over all ranks whose kernels use at most ``max_ctas`` CTAs (ncclConfig_t.maxCTAs), for
+    collectives that run WHILE the EPS kernels hold the SMs (GradAllReducer(overlap=True)).  Returns None when the
+    backend is not NCCL."""
+    if not dist.is_initialized() or dist.get_backend() != "nccl":
+        return None
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.config.max_ctas = max_ctas
+    opts.config.min_ctas = 1
+    return dist.new_group(backend="nccl", pg_options=opts)
 
 
 def seed_core_dropout(seed: int, step: int, device: torch.device) -> None:

@@ -60,7 +60,8 @@ typedef enum dctn_ws_kind {
   DCTN_WS_FORWARD = 0,
   DCTN_WS_BACKWARD_CORE = 1,
   DCTN_WS_BACKWARD_INPUT = 2,
-  DCTN_WS_BACKWARD_INPUT_SAVED = 3 /* dctn_eps_backward_input_saved() */
+  DCTN_WS_BACKWARD_INPUT_SAVED = 3, /* dctn_eps_backward_input_saved() */
+  DCTN_WS_FORWARD_STATS = 4         /* dctn_eps_forward_stats() */
 } dctn_ws_kind;
 
 typedef struct dctn_plan dctn_plan_t; /* opaque, owned by the library's plan cache, never freed by the caller */
@@ -74,6 +75,12 @@ const dctn_plan_t* dctn_eps_plan_get(int C, int K, int Qin, int Qout, int dtype,
 
 /* Human-readable description of the plan (split, tile shapes, kernel family); static storage per plan. */
 const char* dctn_eps_plan_describe(const dctn_plan_t* plan);
+
+/* Which kernel family the library's per-shape dispatch uses for call `kind` (a dctn_ws_kind) at this size:
+ * DCTN_FAMILY_*; a negative dctn_status when the plan's forced variant cannot serve the shape.  Diagnostic: tests and
+ * benchmarks assert with it that the tcgen05 kernels, not a CUDA-core path, served a call. */
+typedef enum dctn_family { DCTN_FAMILY_CUDA_CORE = 1, DCTN_FAMILY_TCGEN05 = 2, DCTN_FAMILY_STREAMING = 4 } dctn_family;
+int dctn_eps_kernel_family(const dctn_plan_t* plan, int B, int H, int W, int kind);
 
 /* Scratch bytes needed by the call `kind` on a (C,B,H,W,Qin) input. */
 size_t dctn_eps_workspace_bytes(const dctn_plan_t* plan, int B, int H, int W, int kind);
@@ -109,6 +116,21 @@ int dctn_eps_forward_train(const dctn_plan_t* plan, const void* x, const void* c
 int dctn_eps_backward_input_saved(const dctn_plan_t* plan, const void* x, const void* core, const void* gout,
                                   const void* saved, size_t saved_bytes, void* dx, int B, int H, int W,
                                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* Forward plus statistics: as dctn_eps_forward, and (sum, sum of squares) of `out` are ADDED in double precision to the
+ * device-resident pair stats[0..1] (zero it before the first slice).  Replaces the `torch.cat` + `output.std()` pass of
+ * make_eps_unit_empirical_output_std (dctn/eps.py:163-181, slices from transform_in_slices dctn/eps.py:126-137): the
+ * biased variance is stats[1]/n - (stats[0]/n)^2.  Workspace kind DCTN_WS_FORWARD_STATS.  Deterministic. */
+int dctn_eps_forward_stats(const dctn_plan_t* plan, const void* x, const void* core, void* out, double* stats,
+                           int B, int H, int W, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Statistics of all K x K windows of x (C, B, H, W, Q) seen as rank-one tensors of K*K*C factors, without expanding
+ * them: stats[0] += sum over windows of prod_j sum_q x_j[q], stats[1] += sum over windows of prod_j sum_q x_j[q]^2.
+ * Replaces make_windows (dctn/align.py:49-61) + RankOneTensorsBatch.sum_over_batch / squared_fro_norm_over_batch
+ * (dctn/rank_one_tensor.py:53-98) as used by log_intermediate_reps_stats (dctn/eps_plus_linear.py:176-186). */
+size_t dctn_window_stats_workspace_bytes(int C, int B, int H, int W);
+int dctn_window_stats(const void* x, int C, int B, int H, int W, int Q, int K, int dtype, double* stats,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* First layer fed with RAW pixels: out = eps(core, phi(pixels)), phi(u) = scale * (sin^2(pi u / 2), cos^2(pi u / 2)) —
  * the feature map the reference applies in its data loader (dctn/dataset_loading.py:33-36; scale = 2 nu,

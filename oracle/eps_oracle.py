@@ -128,6 +128,45 @@ def phi_cos_sin_squared(u: Tensor, nu: float = 1.0) -> Tensor:
     return torch.stack((s, c), dim=-1).unsqueeze(0)
 
 
+# ----------------------------------------------------------------------------- statistics / empirical-std init
+def window_stats(x: Tensor, kernel_size: int) -> Tuple[Tensor, Tensor, int, int]:
+    """make_windows (dctn/align.py:49-61) + RankOneTensorsBatch (dctn/rank_one_tensor.py:53-98): for every K x K window
+    seen as a rank-one tensor of K*K*C factors, returns (sum of all elements of all windows, squared Frobenius norm of
+    the whole batch, number of windows, elements per window) via the rank-one identities (no expansion)."""
+    views = align_views(x, kernel_size)                       # K*K*C views (B, H', W', Q)
+    sums = torch.stack([v.sum(dim=-1) for v in views]).prod(dim=0)
+    sqn = torch.stack([(v ** 2).sum(dim=-1) for v in views]).prod(dim=0)
+    return sums.sum(), sqn.sum(), sums.numel(), x.shape[-1] ** len(views)
+
+
+def window_mean_var(x: Tensor, kernel_size: int, unbiased: bool = True) -> Tuple[Tensor, Tensor]:
+    """mean_over_batch / var_over_batch of dctn/rank_one_tensor.py:66-106."""
+    total, sqn, ntensors, ncoord = window_stats(x, kernel_size)
+    nelement = ntensors * ncoord
+    mean = total / nelement
+    divisor = nelement - 1 if unbiased else nelement
+    return mean, sqn / divisor - 2 * total / divisor * mean + nelement / divisor * mean ** 2
+
+
+def transform_in_slices(core: Tensor, x: Tensor, batch_size: int) -> Tensor:
+    """dctn/eps.py:126-137."""
+    return torch.cat([eps_4step(core, piece) for piece in x.split(batch_size, dim=1)]).unsqueeze(0)
+
+
+def empirical_std_cores(specs: Sequence[Tuple[int, int]], x: Tensor, batch_size: int) -> List[Tensor]:
+    """dctn/epses_composition.py:91-105 over dctn/eps.py:163-181: every layer's randn core (drawn from torch's global
+    generator, in layer order, on the CPU — as the reference does) divided by the biased std of its output on the current
+    representation of x, which is then pushed through the rescaled core."""
+    cores = []
+    for kernel_size, out_size in specs:
+        C, _, _, _, Q = x.shape
+        core = torch.randn(*(Q,) * (kernel_size ** 2 * C), out_size, dtype=x.dtype)
+        core = core * transform_in_slices(core, x, batch_size).std(unbiased=False) ** -1
+        x = transform_in_slices(core, x, batch_size)
+        cores.append(core)
+    return cores
+
+
 # ----------------------------------------------------------------------------- regulariser
 def contract_on_input_dims(a: Tensor, b: Tensor) -> Tensor:
     """dctn/eps.py:106-112."""

@@ -30,7 +30,8 @@ def load_golden(name):
     import torch
 
     data = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
-    return {k: torch.from_numpy(data[k]) for k in data.files}
+    # numeric arrays as tensors; string arrays (log lines, names) stay numpy
+    return {k: (torch.from_numpy(data[k]) if data[k].dtype.kind in "fiub" else data[k]) for k in data.files}
 
 
 EPS_GOLDEN_CASES = [
@@ -47,6 +48,7 @@ EPS_GOLDEN_CASES = [
 LME_GOLDEN_CASES = ["lme_small", "lme_64", "lme_ragged", "lme_scale150"]
 CONVSBS_CASES = ["convsbs_as_eps_perm0", "convsbs_as_eps_perm7", "convsbs_as_eps_perm23"]
 CONVSBS_LOG_CASES = ["convsbs_log_2x2_ring", "convsbs_log_2x2_perm", "convsbs_log_3x3_snake_ring", "convsbs_log_3x3_snake_open"]
+WINDOW_STATS_CASES = ["stats_windows_c1_k3", "stats_windows_c2_k2", "stats_windows_c1_k4_ragged"]
 LME_BATCHED_CASES = ["lme_batched_small", "lme_batched_r8", "lme_batched_scale150"]
 
 

@@ -7,7 +7,7 @@ from functools import reduce
 import pytest
 import torch
 
-from conftest import CONVSBS_CASES, EPS_GOLDEN_CASES, LME_GOLDEN_CASES, load_golden
+from conftest import CONVSBS_CASES, EPS_GOLDEN_CASES, LME_GOLDEN_CASES, WINDOW_STATS_CASES, load_golden
 from oracle import eps_oracle as O
 
 TOL = dict(rtol=1e-12, atol=1e-12)
@@ -132,3 +132,48 @@ def test_logmatmulexp_batched_oracle(name):
     assert torch.allclose(out, g["out"], rtol=1e-12, atol=1e-12)
     out.backward(g["gout"])
     assert torch.allclose(A.grad, g["dA"], rtol=1e-10, atol=1e-12) and torch.allclose(B.grad, g["dB"], rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", WINDOW_STATS_CASES)
+def test_window_stats(name):
+    """make_windows + RankOneTensorsBatch statistics of the reference (tests/golden/make_golden_stats.py)."""
+    g = load_golden(name)
+    K = int(g["kernel_size"])
+    total, sqn, ntensors, ncoord = O.window_stats(g["x"], K)
+    assert ntensors == int(g["ntensors"]) and ncoord == int(g["ncoordinates"])
+    assert torch.allclose(total, g["sum"], rtol=1e-12) and torch.allclose(sqn, g["sqnorm"], rtol=1e-12)
+    mean, var_u = O.window_mean_var(g["x"], K, True)
+    assert torch.allclose(mean, g["mean"], rtol=1e-12) and torch.allclose(var_u, g["var_unbiased"], rtol=1e-10)
+    assert torch.allclose(O.window_mean_var(g["x"], K, False)[1], g["var_biased"], rtol=1e-10)
+    # std_over_batch(unbiased=False) of the reference ignores its argument (dctn/rank_one_tensor.py:108-110)
+    assert torch.allclose(var_u ** 0.5, g["std"], rtol=1e-10)
+
+
+def test_empirical_std_init():
+    """UnitEmpiricalOutputStd cores of the reference under a fixed seed, and unit output std per layer."""
+    g = load_golden("stats_empirical_init")
+    torch.manual_seed(int(g["seed"]))
+    cores = O.empirical_std_cores(((2, 3), (2, 4)), g["x"], int(g["batch_size"]))
+    assert torch.allclose(cores[0], g["core0"], rtol=1e-11, atol=1e-13)
+    assert torch.allclose(cores[1], g["core1"], rtol=1e-11, atol=1e-13)
+    assert torch.allclose(g["out_stds"], torch.ones(2, dtype=torch.float64), rtol=1e-10)
+
+
+def test_intermediate_reps_log_numbers():
+    """(mu, sigma) of every line log_intermediate_reps_stats writes (dctn/eps_plus_linear.py:161-196)."""
+    g = load_golden("stats_log_lines")
+    x, got = g["x"], []
+    for core in (g["core0"], g["core1"]):
+        got.append((x.mean(), x.std(unbiased=False)))
+        K = 2
+        mean, var = O.window_mean_var(x, K, True)
+        got.append((mean, var ** 0.5))
+        x = O.transform_in_slices(core, x, 4)
+    flat = x.squeeze(0).flatten(start_dim=1)
+    got.append((flat.mean(), flat.std(unbiased=False)))
+    for t in (flat @ g["weight"].T, flat @ g["weight"].T + g["bias"]):
+        got.append((t.mean(), t.std(unbiased=False)))
+    mus = torch.stack([m for m, _ in got])
+    sigmas = torch.stack([s for _, s in got])
+    # the golden numbers were parsed from the log lines: 8 significant digits
+    assert torch.allclose(mus, g["mus"], rtol=2e-7, atol=1e-12) and torch.allclose(sigmas, g["sigmas"], rtol=2e-7)

@@ -37,13 +37,32 @@ def _worker(rank, world, port, ret, overlap):
             with torch.no_grad():
                 for p in model.parameters():
                     p.add_(1.0)
-        reducer = GradAllReducer(model.parameters(), overlap=overlap)
+        # overlap: parameters in the order their gradients become ready (last layer first)
+        plist = list(model.parameters())
+        reducer = GradAllReducer(plist[::-1] if overlap else plist, overlap=overlap)
         xs, ys = shard_batch(x, rank, world, dim=1), shard_batch(y, rank, world, dim=0)
         assert xs.shape == (1, 4, 12) and ys.shape == (4,)
-        loss = F.cross_entropy(model(xs[0]), ys)
-        loss.backward()
-        reducer.wait()
+        for step in range(2):   # second step: zero_grad() must restore a clean bucket
+            reducer.zero_grad()
+            assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(reducer.params, reducer._views))
+            loss = F.cross_entropy(model(xs[0]), ys)
+            loss.backward()
+            reducer.wait()
         grads = [p.grad.clone() for p in model.parameters()]
+        # a caller that detaches the gradients (optimizer.zero_grad(set_to_none=True)) and a parameter without a gradient
+        # on ONE rank only: the fixed bucket layout keeps the ranks in step, the missing gradient counts as zero
+        for p in model.parameters():
+            p.grad = None
+        out = model(xs[0])
+        if rank == 0:
+            F.cross_entropy(out, ys).backward()
+        else:
+            model[2].weight.requires_grad_(False)
+            F.cross_entropy(out.detach() @ torch.eye(10, dtype=torch.float64) + model[2].bias, ys).backward()   # bias only
+            model[2].weight.requires_grad_(True)
+        reducer.wait()
+        if rank == 0:
+            ret["partial"] = [p.grad.clone() for p in model.parameters()]
         # identical dropout masks on every rank
         seed_core_dropout(123, 5, torch.device("cpu"))
         mask = torch.bernoulli(torch.full((16,), 0.5))
@@ -70,7 +89,7 @@ def test_grad_allreduce_matches_single_process(overlap):
     with mp.Manager() as manager:
         ret = manager.dict()
         mp.spawn(_worker, args=(world, port, ret, overlap), nprocs=world, join=True)
-        grads, params, metrics = ret["grads"], ret["params"], ret["metrics"]
+        grads, params, metrics, partial = ret["grads"], ret["params"], ret["metrics"], ret["partial"]
     # single-process reference: full batch, rank-0 parameters
     g = torch.Generator().manual_seed(0)
     x = torch.randn(1, 8, 12, generator=g, dtype=torch.float64)
@@ -82,6 +101,12 @@ def test_grad_allreduce_matches_single_process(overlap):
     for p, gr in zip(model.parameters(), grads):
         assert torch.allclose(p.grad, gr, rtol=1e-12, atol=1e-14)
     assert metrics == ((4 + 8) / 8.0, (0 + 2) / 8.0)
+    # rank 1 contributed a gradient for the last bias only: every other averaged gradient is half of rank 0's
+    model.zero_grad(set_to_none=True)
+    F.cross_entropy(model(x[0, :4]), y[:4]).backward()
+    for i, (p, gr) in enumerate(zip(model.parameters(), partial)):
+        if i < 3:
+            assert torch.allclose(p.grad / 2, gr, rtol=1e-12, atol=1e-14)
 
 
 def test_shard_batch_requires_divisibility():
