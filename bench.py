@@ -36,7 +36,29 @@ WORKLOADS = {
     "cifar_2_6__2_24": (((2, 6), (2, 24)), 32, 4, 64, 1.0),
     "cifar_2_12__2_24": (((2, 12), (2, 24)), 32, 4, 64, 1.0),
     "cifar_2_23__2_24": (((2, 23), (2, 24)), 32, 4, 64, 1.0),
+    # config 4, three layers: (4,4),(3,12),(2,24) of three_epses_on_fashionmnist.py:16 at 28x28 and adapted to the 32x32
+    # grayscale CIFAR input of README.org:87-88 (Q_0 = 2: a K = 4 first layer on Q_0 = 4 would need a 4^16-element core)
+    "three_eps": (((4, 4), (3, 12), (2, 24)), 28, 2, 64, 1.45646),
+    "three_eps_32": (((4, 4), (3, 12), (2, 24)), 32, 2, 64, 1.45646),
 }
+# reference arm / cpu_baseline: FIXED images per CPU step (a bounded sample of the workload's batch; the same number on
+# every run, so the figure is reproducible), sized so that 25 steps stay within a few minutes on 8-16 host cores
+SAMPLE_BATCH = {"cfg2": 32, "cfg1": 128, "one_eps": 32, "cifar_2_6__2_24": 32, "cifar_2_12__2_24": 16, "cifar_2_23__2_24": 4,
+                "three_eps": 8, "three_eps_32": 8}
+# workloads whose step is a chain of short kernels: the captured (CUDA graph) step is the default
+GRAPH_DEFAULT = {"cfg1", "one_eps", "cifar_2_6__2_24"}
+
+
+def workload_config(workload, batch, world, step_desc):
+    """The `config` object of the JSON line — identical keys and values for our arm and the reference arm."""
+    specs, image_size, Q0, default_batch, _ = WORKLOADS[workload]
+    return {"workload": workload, "epses_specs": specs, "image_size": image_size, "Q_0": Q0, "per_gpu_batch": batch or default_batch,
+            "global_batch": (batch or default_batch) * world, "parallelism": f"dp{world}", "step": step_desc,
+            "l2": "GPU arm: 256 MiB memset between timed steps (untimed), per-step CUDA-event times summed; CPU reference arm: not applicable",
+            "sample_batch": SAMPLE_BATCH[workload]}
+
+
+STEP_DESC = "fwd+cross_entropy+bwd+grad_allreduce+adam"
 
 
 def synth_batch(batch, image_size, scale, seed, dtype, Q0=2):
@@ -167,13 +189,11 @@ def run_reference(args):
         opt.step()
         return loss
 
-    # size the per-step sample so that the whole run stays within ~150 s
-    x1, y1 = synth_batch(2, image_size, scale, 1, dtype, Q0)
-    t0 = time.perf_counter(); step(x1, y1); t_probe = (time.perf_counter() - t0) / 2  # s per image
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    sb = args.sample_batch or int(max(1, min(32, budget / max(t_probe, 1e-6))))
+    # FIXED per-step sample (no probe: the first call includes one-off warm-up cost and made the size, hence the
+    # figure, vary from run to run)
+    sb = args.sample_batch or SAMPLE_BATCH[args.workload]
     x, y = synth_batch(sb, image_size, scale, 2, dtype, Q0)
-    for _ in range(args.warmup):
+    for _ in range(max(1, args.warmup)):
         step(x, y)
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -182,16 +202,17 @@ def run_reference(args):
     ms = dt / args.steps * 1e3
     value = sb * args.steps / dt
     dims = layer_dims(specs, image_size, Q0, sb)
+    config = workload_config(args.workload, args.batch, args.gpus, STEP_DESC)
+    config["sample_batch"] = sb
     line = {
         "impl": "reference", "metric": "eps_train_images_per_s", "value": value, "unit": "img/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "epses_specs": specs, "image_size": image_size, "per_gpu_batch": WORKLOADS[args.workload][3],
-                   "step": "fwd+cross_entropy+bwd+adam"},
+        "config": config,
         "patches_per_s": sum(d["P"] for d in dims) * args.steps / dt,
         "cpu_baseline": {"value": value, "unit": "img/s", "cores": threads, "kind": "port",
-                         "sample": f"batch {sb} per step (full workload batch {WORKLOADS[args.workload][3]}), {args.steps} timed steps, "
-                                   f"torch CPU einsum path, os.cpu_count()={os.cpu_count()}"},
+                         "sample": f"batch {sb} per step (fixed sample of the workload batch {config['per_gpu_batch']}), {args.steps} timed steps "
+                                   f"after {max(1, args.warmup)} warm-up, torch CPU einsum path (oracle port of dctn/eps.py:19-40), os.cpu_count()={os.cpu_count()}"},
         "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -216,18 +237,17 @@ def cpu_baseline_sample(workload, seconds=20.0):
             t.grad = None
         F.cross_entropy(O.eps_plus_linear_forward(cores, w, b, x), y).backward()
 
-    x1, y1 = synth_batch(2, image_size, scale, 1, torch.float32, Q0)
-    t0 = time.perf_counter(); step(x1, y1); per_img = (time.perf_counter() - t0) / 2
-    sb = int(max(1, min(32, seconds / 3.0 / max(per_img, 1e-6))))
+    sb = SAMPLE_BATCH[workload]
     x, y = synth_batch(sb, image_size, scale, 2, torch.float32, Q0)
     step(x, y)  # warm-up
     t0 = time.perf_counter()
-    n = 2
-    for _ in range(n):
+    n = 0
+    while n < 2 or (time.perf_counter() - t0 < seconds / 2 and n < 50):
         step(x, y)
+        n += 1
     dt = time.perf_counter() - t0
     return {"value": sb * n / dt, "unit": "img/s", "cores": threads, "kind": "port",
-            "sample": f"fwd+bwd of the same model at batch {sb} (full batch {WORKLOADS[workload][3]}), {n} timed steps after 1 warm-up, "
+            "sample": f"fwd+bwd of the same model at a fixed batch of {sb} (workload batch {WORKLOADS[workload][3]}), {n} timed steps after 1 warm-up, "
                       f"oracle port of the reference's 4-step einsum path on torch CPU, os.cpu_count()={os.cpu_count()}"}
 
 
@@ -352,12 +372,38 @@ def kernel_rooflines(model, specs, image_size, Q0, batch, dev, flush):
     return roof
 
 
+def dp_self_check(model, reducer, batch, image_size, scale, Q0, dev, rank, world):
+    """N >= 2: the gradients GradAllReducer leaves on every rank after one sharded step (mean over ranks of the
+    per-shard mean-loss gradients) against ONE rank's gradients on the concatenated batch.  Returns the largest
+    Frobenius-relative error over the parameters (rank 0; None elsewhere)."""
+    import torch.distributed as dist
+
+    shards = [synth_batch(batch, image_size, scale, 5000 + r, torch.float32, Q0) for r in range(world)]
+    x, y = shards[rank]
+    reducer.zero_grad()
+    F.cross_entropy(model(x.to(dev)), y.to(dev)).backward()
+    reducer.wait()
+    sharded = [p.grad.detach().clone() for p in reducer.params]
+    err = None
+    if rank == 0:
+        for p in reducer.params:
+            p.grad = None
+        xa = torch.cat([sx for sx, _ in shards], dim=1).to(dev)
+        ya = torch.cat([sy for _, sy in shards]).to(dev)
+        F.cross_entropy(model(xa), ya).backward()
+        err = max(((a - p.grad).norm() / p.grad.norm()).item() for a, p in zip(sharded, reducer.params))
+    dist.barrier()
+    reducer.zero_grad()
+    return err
+
+
 def run_ours(args):
     import torch.distributed as dist
 
     from dctn_b200 import _lib
     from dctn_b200.eps_plus_linear import EPSesPlusLinear, UnitTheoreticalOutputStd
-    from dctn_b200.parallel import GradAllReducer
+    from dctn_b200.parallel import GradAllReducer, make_comm_group
+    from dctn_b200.train_step import TrainStep
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -371,24 +417,31 @@ def run_ours(args):
 
     specs, image_size, Q0, default_batch, scale = WORKLOADS[args.workload]
     batch = args.batch or default_batch
+    if args.strong:      # strong scaling: the GLOBAL batch is fixed, each rank takes 1/N of it
+        assert batch % world == 0, f"global batch {batch} not divisible by {world} ranks"
+        batch //= world
+    use_graph = args.graph == "on" or (args.graph == "auto" and args.workload in GRAPH_DEFAULT)
     torch.manual_seed(0)
     model = EPSesPlusLinear(specs, UnitTheoreticalOutputStd(), 1.0, dev, torch.float32, image_size=image_size, Q_0=Q0)
     model.train()
-    opt = torch.optim.Adam(model.parameters(), lr=1.11e-4, fused=True)   # one kernel for all parameters (same update rule)
-    reducer = GradAllReducer(model.parameters())
+    # one kernel for all parameters (same update rule); capturable: the step count lives on the device (graph capture)
+    opt = torch.optim.Adam(model.parameters(), lr=1.11e-4, fused=True, capturable=use_graph)
+    # gradients become ready last layer first: linear, last core, ..., first core
+    ready_order = list(model.linear.parameters()) + list(model.epses)[::-1]
+    comm = make_comm_group(args.comm_ctas) if (world > 1 and args.overlap) else None
+    reducer = GradAllReducer(ready_order, group=comm, overlap=args.overlap) if world > 1 else None
     nb = 4  # distinct synthetic batches, rotated
     host = [synth_batch(batch, image_size, scale, 1000 + rank * 17 + i, torch.float32, Q0) for i in range(nb)]
     host = [(x.pin_memory(), y.pin_memory()) for x, y in host]
     resident = [(x.to(dev), y.to(dev)) for x, y in host]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    loss_host = torch.zeros(nb, dtype=torch.float32).pin_memory()
 
-    def step(x, y):
-        opt.zero_grad(set_to_none=True)
-        loss = F.cross_entropy(model(x), y)
-        loss.backward()
-        reducer.wait()
-        opt.step()
-        return loss
+    dp_err = None
+    if world > 1 and args.check_dp:
+        dp_err = dp_self_check(model, reducer, batch, image_size, scale, Q0, dev, rank, world)
+
+    step = TrainStep(model, opt, resident[0][0], resident[0][1], reducer=reducer, graph=use_graph, warmup=3)
 
     def barrier():
         if world > 1:
@@ -396,24 +449,27 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed(nsteps, e2e):
-        """Sum of per-step device times (CUDA events on the launching stream); L2 flushed (untimed) before each step."""
+        """Sum of per-step device times (CUDA events on the launching stream); L2 flushed (untimed) before each step.
+        e2e: the step's batch comes from pinned host memory and its loss is copied back to pinned host memory, both
+        inside the timed region."""
         total_ms = 0.0
-        last = None
         for i in range(nsteps):
             flush.zero_()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             if e2e:
                 hx, hy = host[i % nb]
-                x, y = hx.to(dev, non_blocking=True), hy.to(dev, non_blocking=True)
-                last = step(x, y).item()  # device -> host read of the step's result
+                if use_graph:       # straight into the graph's static input buffers
+                    loss = step(hx, hy)
+                else:
+                    loss = step(hx.to(dev, non_blocking=True), hy.to(dev, non_blocking=True))
+                loss_host[i % nb].copy_(loss.detach(), non_blocking=True)   # device -> host read of the step's result
             else:
-                x, y = resident[i % nb]
-                last = step(x, y)
+                step(*resident[i % nb])
             e.record()
             e.synchronize()
             total_ms += s.elapsed_time(e)
-        return total_ms, last
+        return total_ms, float(loss_host[(nsteps - 1) % nb]) if e2e else None
 
     for i in range(max(args.warmup, 3)):
         step(*resident[i % nb])
@@ -423,7 +479,7 @@ def run_ours(args):
         sampler.start()
     l0 = _lib.launch_count()
     wall0 = time.perf_counter()
-    ms_total, last = timed(args.steps, e2e=False)
+    ms_total, _ = timed(args.steps, e2e=False)
     barrier()
     wall = time.perf_counter() - wall0
     launches = _lib.launch_count() - l0
@@ -441,21 +497,29 @@ def run_ours(args):
         imgs = batch * world * args.steps
         value = imgs / (ms_total / 1e3)
         hx, hy = host[0]
+        if use_graph:    # replays launch no kernels from the host: count the kernels of ONE eager step of the same model
+            l1 = _lib.launch_count()
+            step._eager(*resident[0])
+            torch.cuda.synchronize()
+            launches = (_lib.launch_count() - l1) * args.steps
+        config = workload_config(args.workload, batch, world, STEP_DESC)
+        run_info = {"variant": os.environ.get("DCTN_B200_VARIANT", "auto"), "cuda_graph": use_graph,
+                    "grad_allreduce": ("overlapped, %d-CTA communicator" % args.comm_ctas) if (world > 1 and args.overlap) else "one flat bucket after backward",
+                    "wall_s_incl_flush": round(wall, 4)}
         line = {
             "metric": "eps_train_images_per_s", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.strong else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "epses_specs": specs, "image_size": image_size, "per_gpu_batch": batch,
-                       "global_batch": batch * world, "parallelism": f"dp{world}", "step": "fwd+cross_entropy+bwd+grad_allreduce+adam",
-                       "variant": os.environ.get("DCTN_B200_VARIANT", "auto"),
-                       "l2": "256 MiB memset between timed steps (untimed); per-step CUDA-event times summed",
-                       "wall_s_incl_flush": round(wall, 4)},
+            "config": config, "run": run_info,
             "patches_per_s": sum(d["P"] for d in dims) * world * args.steps / (ms_total / 1e3),
             "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "img/s", "h2d_bytes_per_step": hx.numel() * hx.element_size() + hy.numel() * hy.element_size(),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": last_loss},
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        if dp_err is not None:
+            line["dp_check"] = {"max_rel_err_sharded_vs_full_batch": dp_err, "ranks": world, "tolerance": 1e-5, "ok": dp_err <= 1e-5}
         if world == 1 or args.roofline:
             line["roofline"] = kernel_rooflines(model, specs, image_size, Q0, batch, dev, flush)
         if world == 1 and not args.no_cpu_baseline:
@@ -488,8 +552,14 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg2")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
-    ap.add_argument("--sample-batch", type=int, default=0, help="reference arm: images per step (default: sized to ~150 s total)")
+    ap.add_argument("--sample-batch", type=int, default=0, help="reference arm: images per CPU step (default: the workload's fixed SAMPLE_BATCH)")
     ap.add_argument("--roofline", action="store_true", help="also time the kernels in isolation when N>1")
+    ap.add_argument("--graph", choices=["auto", "on", "off"], default="auto",
+                    help="capture the training step in a CUDA graph (auto: the launch-bound workloads cfg1 / one_eps / cifar_2_6__2_24)")
+    ap.add_argument("--overlap", action="store_true", help="N>1: all-reduce everything but the first core while the first core's gradient is computed")
+    ap.add_argument("--comm-ctas", type=int, default=4, help="CTA limit of the NCCL communicator used with --overlap")
+    ap.add_argument("--check-dp", action="store_true", help="N>1: verify averaged sharded gradients against one rank on the concatenated batch")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: --batch (default: the workload's) is the GLOBAL batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

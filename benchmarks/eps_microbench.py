@@ -4,7 +4,7 @@
 shape and dctn/benchmark.py protocol: randn core and input, both requiring grad, fixed randn out_grad).
 
 Infeasible corners are reported, not run: K=4 with Q_in=4 (core 4^16 x Q_out elements) and
-K=4 with Q_in=3 (3^16-element core, > 0.4 PFLOP per forward at B=4096).  K=3,Q_in=4 runs at --big-batch (default 512).
+K=4 with Q_in=3 (3^16-element core, > 0.4 PFLOP per forward at B=4096).  K=3,Q_in=4 (2.9-8.7 TFLOP per forward) runs at --big-batch (default 4096, like every other row).
 
     python benchmarks/eps_microbench.py [--batch 4096] [--qouts 2,6] [--json out.json]
 """
@@ -43,7 +43,7 @@ def timeit(fn, flush, iters):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=4096)
-    ap.add_argument("--big-batch", type=int, default=512, help="batch for K=3,Q=4 (8.7 TFLOP per forward at 4096)")
+    ap.add_argument("--big-batch", type=int, default=4096, help="batch for K=3,Q=4 (8.7 TFLOP per forward at 4096: the largest feasible point of the grid)")
     ap.add_argument("--ks", default="2,3,4")
     ap.add_argument("--qs", default="2,3,4")
     ap.add_argument("--qouts", default="2,3,4,5,6")

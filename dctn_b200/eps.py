@@ -123,7 +123,13 @@ class EpsFunction(torch.autograd.Function):
             stream = torch.cuda.current_stream().cuda_stream
             nsave = lib.dctn_eps_saved_bytes(plan, B, H, W) if ctx.needs_input_grad[1] else 0
             if 0 < nsave <= _save_limit_bytes:
-                saved = torch.empty(nsave, dtype=torch.uint8, device=input.device)
+                # T is a convenience (it halves the tensor-core work of the input gradient), never a requirement: when
+                # the device cannot hold it next to the workspaces, fall back to the recompute path
+                try:
+                    saved = torch.empty(nsave, dtype=torch.uint8, device=input.device)
+                except torch.cuda.OutOfMemoryError:
+                    saved = None
+            if saved is not None:
                 rc = lib.dctn_eps_forward_train(
                     plan, x_c.data_ptr(), core_c.data_ptr(), out.data_ptr(), saved.data_ptr(), saved.numel(), B, H, W,
                     ws.data_ptr(), ws.numel(), stream,
