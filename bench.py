@@ -49,6 +49,14 @@ SAMPLE_BATCH = {"cfg2": 32, "cfg1": 128, "one_eps": 32, "cifar_2_6__2_24": 32, "
 GRAPH_DEFAULT = {"cfg1", "one_eps", "cifar_2_6__2_24"}
 
 
+# config 5 (BASELINE.json configs[4]): log-space contraction workloads — not EPS models, own metric and step
+#   cfg5_chain   : reduce(logmatmulexp, 6 N x N matrices), forward + backward with out_grad = ones, N = 256, float32 —
+#                  the protocol of small_experiments/logmatmulexp_benchmark/benchmark.py:21-52
+#   cfg5_convsbs : conv_sbs_log_forward of a 3x3 snake ConvSBS ring (bond 4, Q = 2, one output core with 4 outputs) on a
+#                  28x28 input, batch 2048, forward + backward ("28x28 synthetic input, batch 2048")
+CFG5 = {"cfg5_chain": dict(N=256, nmat=6, sample=1), "cfg5_convsbs": dict(batch=2048, bond=4, sample=16)}
+
+
 def workload_config(workload, batch, world, step_desc):
     """The `config` object of the JSON line — identical keys and values for our arm and the reference arm."""
     specs, image_size, Q0, default_batch, _ = WORKLOADS[workload]
@@ -530,6 +538,228 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ config 5
+def cfg5_inputs(workload, batch, seed, device):
+    """Seeded inputs of a config-5 step (leaf tensors that require a gradient) and the function of them that is timed."""
+    gen = torch.Generator().manual_seed(seed)
+    if workload == "cfg5_chain":
+        N, nmat = CFG5[workload]["N"], CFG5[workload]["nmat"]
+        return [torch.randn(N, N, generator=gen).to(device).requires_grad_(True) for _ in range(nmat)]
+    bond = CFG5[workload]["bond"]
+    u = torch.rand(batch, 28, 28, generator=gen)
+    log_x = torch.log(torch.stack((torch.sin(u * math.pi / 2) ** 2, torch.cos(u * math.pi / 2) ** 2), dim=-1).clamp_min(1e-6))[None]
+    cores = []
+    for c in range(9):   # 3x3 snake: one output core (4 outputs) in the middle, bond `bond` everywhere
+        cores.append((torch.randn(4 if c == 4 else 1, bond, bond, 2, generator=gen) * 0.5).to(device).requires_grad_(True))
+    return [log_x.to(device).requires_grad_(True)] + cores
+
+
+SNAKE_3x3 = ((0, 0), (0, 1), (0, 2), (1, 2), (1, 1), (1, 0), (2, 0), (2, 1), (2, 2))
+
+
+def cfg5_fn(workload, ours):
+    """The forward function of a config-5 step: our CUDA path, or the reference formulation (dctn/logmatmulexp.py:5-14:
+    materialised broadcast sum + torch.logsumexp; dctn/conv_sbs.py:258-304 in linear space) for the CPU arm."""
+    from functools import reduce
+
+    if workload == "cfg5_chain":
+        if ours:
+            from dctn_b200.logmatmulexp import logmatmulexp
+            return lambda ts: reduce(logmatmulexp, ts)
+        from oracle import eps_oracle as O
+        return lambda ts: reduce(O.logmatmulexp, ts)
+    if ours:
+        from dctn_b200.conv_sbs_log import conv_sbs_log_forward
+        from dctn_b200.pos2d import Pos2D
+        pos = tuple(Pos2D(h, w) for h, w in SNAKE_3x3)
+        return lambda ts: conv_sbs_log_forward(ts[1:], pos, ts[0])
+    from oracle import eps_oracle as O
+    return lambda ts: O.conv_sbs_log_forward(ts[1:], SNAKE_3x3, ts[0])
+
+
+def cfg5_units(workload, batch):
+    if workload == "cfg5_chain":
+        return 1, "logmatmulexp_chain_fwdbwd_per_s", "chains/s"
+    return batch, "convsbs_log_fwdbwd_images_per_s", "img/s"
+
+
+def run_cfg5(args):
+    """Config 5 through the bench contract: one step = forward + backward of the workload's function.  The step is captured
+    in a CUDA graph (it is a chain of short kernels; --graph off for the eager figure); `e2e` copies the step's inputs from
+    pinned host memory and reads the scalar sum of the result back."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    spec = CFG5[args.workload]
+    batch = args.batch or spec.get("batch", 1)
+    units, metric, unit = cfg5_units(args.workload, batch)
+    config = {"workload": args.workload, **{k: v for k, v in spec.items() if k != "sample"}, "per_gpu_batch": batch, "parallelism": f"replicas{world}",
+              "step": "fwd+bwd", "l2": "GPU arm: 256 MiB memset between timed steps (untimed), per-step CUDA-event times summed; CPU reference arm: not applicable",
+              "sample_batch": spec["sample"]}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        threads = use_all_host_threads()
+        sb = spec["sample"] if args.workload == "cfg5_convsbs" else 1
+        ts = cfg5_inputs(args.workload, sb, 7, torch.device("cpu"))
+        fn = cfg5_fn(args.workload, ours=False)
+
+        def step():
+            for t in ts:
+                t.grad = None
+            out = fn(ts)
+            out.backward(torch.ones_like(out))
+
+        for _ in range(max(1, args.warmup)):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = time.perf_counter() - t0
+        value = (sb if args.workload == "cfg5_convsbs" else 1) * args.steps / dt
+        _emit({"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": config,
+               "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port",
+                                "sample": f"{sb} image(s) / chain per step, {args.steps} timed steps, reference formulation on torch CPU, os.cpu_count()={os.cpu_count()}"},
+               "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+        return
+
+    from dctn_b200 import _lib
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    use_graph = args.graph != "off"
+    ts = cfg5_inputs(args.workload, batch, 100 + rank, dev)
+    host = [[t.detach().cpu().pin_memory() for t in cfg5_inputs(args.workload, batch, 200 + rank + i, torch.device("cpu"))] for i in range(2)]
+    fn = cfg5_fn(args.workload, ours=True)
+    result = torch.zeros((), device=dev)
+    result_host = torch.zeros(()).pin_memory()
+
+    def eager():
+        for t in ts:
+            t.grad = None
+        out = fn(ts)
+        out.backward(torch.ones_like(out))
+        result.copy_(out.detach().sum())
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            eager()
+    torch.cuda.current_stream().wait_stream(side)
+    l0 = _lib.launch_count()
+    eager()
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - l0
+    graph = None
+    if use_graph:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            eager()
+    step = graph.replay if graph is not None else eager
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed(nsteps, e2e):
+        total = 0.0
+        for i in range(nsteps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            if e2e:
+                with torch.no_grad():
+                    for t, h in zip(ts, host[i % 2]):
+                        t.copy_(h, non_blocking=True)
+            step()
+            if e2e:
+                result_host.copy_(result, non_blocking=True)
+            e.record()
+            e.synchronize()
+            total += s.elapsed_time(e)
+        return total
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_total = timed(args.steps, False)
+    ms_e2e = timed(args.steps, True)
+    clocks = sampler.stop() if sampler else None
+    tt = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = tt.tolist()
+    if rank == 0:
+        h2d = sum(h.numel() * h.element_size() for h in host[0])
+        line = {"metric": metric, "value": units * world * args.steps / (ms_total / 1e3), "unit": unit, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config, "run": {"cuda_graph": use_graph},
+                "e2e": {"value": units * world * args.steps / (ms_e2e / 1e3), "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e / args.steps, "last_result": float(result_host)},
+                "gpu_launches": launches_per_step * args.steps, "clocks": clocks}
+        if world == 1:
+            line["roofline"] = cfg5_roofline(args.workload, batch, ts, fn, flush)
+            if not args.no_cpu_baseline:
+                threads = use_all_host_threads()
+                sb = spec["sample"] if args.workload == "cfg5_convsbs" else 1
+                cts = cfg5_inputs(args.workload, sb, 7, torch.device("cpu"))
+                cfn = cfg5_fn(args.workload, ours=False)
+
+                def cstep():
+                    for t in cts:
+                        t.grad = None
+                    out = cfn(cts)
+                    out.backward(torch.ones_like(out))
+
+                cstep()
+                t0 = time.perf_counter()
+                n = 0
+                while n < 2 or (time.perf_counter() - t0 < 10.0 and n < 50):
+                    cstep()
+                    n += 1
+                dt = time.perf_counter() - t0
+                line["cpu_baseline"] = {"value": (sb if args.workload == "cfg5_convsbs" else 1) * n / dt, "unit": unit, "cores": threads, "kind": "port",
+                                        "sample": f"{sb} image(s) / chain per step, {n} timed steps, reference formulation (materialised broadcast sum + logsumexp) on torch CPU"}
+        _emit(line)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cfg5_roofline(workload, batch, ts, fn, flush):
+    """Dominant kernel of the step timed alone (CUDA events, L2 flushed).  cfg5_chain: ONE logmatmulexp forward product
+    (lme_tile_fwd_kernel): 2*N^3 flops of fp32 FMA + 2*N^2 exponentials over 3*N^2*4 algorithmic bytes — at N = 256 a
+    64-CTA kernel of a few microseconds, latency-bound; reported against the HBM peak as the contract asks for a byte or
+    tensor roofline, with the FMA rate beside it.  cfg5_convsbs: the batched ring product (lme_batched_fwd_vec_kernel)."""
+    peaks = measured_peaks()
+    if workload == "cfg5_chain":
+        from dctn_b200.logmatmulexp import logmatmulexp
+        a, b = ts[0].detach(), ts[1].detach()
+        N = a.shape[0]
+        ms = time_op(lambda: logmatmulexp(a, b), flush, iters=10)
+        alg_bytes, flops = 3.0 * N * N * 4, 2.0 * N ** 3
+        return {"bound": "hbm", "achieved": alg_bytes / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": alg_bytes / ms / 1e6 / peaks["hbm_gbs"],
+                "traffic": None, "kernel": f"lme_tile_fwd_kernel<float> N={N}", "ms_per_call": ms, "peak_source": peaks["source"],
+                "algorithmic_bytes_per_call": alg_bytes, "fp32_fma_tflops": flops / ms / 1e9, "exponentials_per_call": 2 * N * N,
+                "note": "latency-bound: 64 CTAs, ~1 us of work; the event time includes the Python call (ctypes, two torch.empty); the "
+                        "per-element formulation of the reference needs N^3 = 16.8 M exponentials here, this one 2 N^2 = 131 K plus an fp32 matrix product"}
+    from dctn_b200.logmatmulexp import logmatmulexp_batched
+    bond = CFG5[workload]["bond"]
+    NB = batch * 26 * 26
+    A = torch.randn(NB, bond, bond, device=ts[0].device)
+    Bm = torch.randn(NB, bond, bond, device=ts[0].device)
+    ms = time_op(lambda: logmatmulexp_batched(A, Bm), flush, iters=5)
+    alg_bytes = 3.0 * NB * bond * bond * 4
+    return {"bound": "hbm", "achieved": alg_bytes / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": alg_bytes / ms / 1e6 / peaks["hbm_gbs"],
+            "traffic": None, "kernel": f"lme_batched_fwd_vec_kernel<{bond}> batch={NB}", "ms_per_call": ms, "peak_source": peaks["source"],
+            "algorithmic_bytes_per_call": alg_bytes, "exponentials_per_s": NB * bond ** 3 / ms * 1e3}
+
+
 def _emit(line: dict) -> None:
     """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner at communicator
     creation), so main() points fd 1 at stderr for the duration of the run and the result goes to the saved fd."""
@@ -550,7 +780,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg2")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS) + sorted(CFG5), default="cfg2")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--sample-batch", type=int, default=0, help="reference arm: images per CPU step (default: the workload's fixed SAMPLE_BATCH)")
     ap.add_argument("--roofline", action="store_true", help="also time the kernels in isolation when N>1")
@@ -562,7 +792,9 @@ def main():
     ap.add_argument("--strong", action="store_true", help="strong scaling: --batch (default: the workload's) is the GLOBAL batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload in CFG5:
+        run_cfg5(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

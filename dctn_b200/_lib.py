@@ -40,6 +40,9 @@ SYMBOLS = {
     "dctn_eps_forward_from_pixels": (c_int, [c_void_p, c_void_p, ctypes.c_double, c_void_p, c_void_p] + [c_int] * 3 + [c_void_p]),
     "dctn_logmatmulexp_forward": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p]),
     "dctn_logmatmulexp_backward": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_void_p]),
+    "dctn_logmatmulexp_workspace_bytes": (c_size_t, [c_int] * 4),
+    "dctn_logmatmulexp_forward_ws": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p, c_size_t, c_void_p]),
+    "dctn_logmatmulexp_backward_ws": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_void_p, c_size_t, c_void_p]),
     "dctn_logmatmulexp_batched_forward": (c_int, [c_void_p] * 3 + [ctypes.c_longlong] + [c_int] * 4 + [c_void_p]),
     "dctn_logmatmulexp_batched_backward": (c_int, [c_void_p] * 6 + [ctypes.c_longlong] + [c_int] * 4 + [c_void_p]),
     "dctn_eps_forward_host_device_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
@@ -67,6 +70,8 @@ def lib() -> ctypes.CDLL:
                     )
                 handle = ctypes.CDLL(LIB_PATH)
                 for name, (restype, argtypes) in SYMBOLS.items():
+                    if os.environ.get("DCTN_B200_LIB") and not hasattr(handle, name):
+                        continue  # A/B runs against an OLDER build (tools/kbench.py): it may predate newer entry points
                     fn = getattr(handle, name)  # AttributeError if the .so lacks a declared symbol
                     fn.restype = restype
                     fn.argtypes = argtypes

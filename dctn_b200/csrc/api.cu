@@ -417,11 +417,43 @@ extern "C" int dctn_logmatmulexp_backward(const void* A, const void* B, const vo
   return dctn_set_error(DCTN_ERR_BAD_ARG, "logmatmulexp: bad dtype %d", dtype);
 }
 
+// one-kernel-per-product path (csrc/logmatmulexp_tile.cu); 0 bytes = shape not served, use the entries above
+extern "C" size_t dctn_logmatmulexp_workspace_bytes(int Th, int R, int I, int dtype) {
+  if (Th < 1 || R < 1 || I < 1) return 0;
+  if (dtype == DCTN_F32) return lme_tile_supported<float>(Th, R, I) ? lme_tile_workspace_bytes(Th, I, 4) : 0;
+  if (dtype == DCTN_F64) return lme_tile_supported<double>(Th, R, I) ? lme_tile_workspace_bytes(Th, I, 8) : 0;
+  return 0;
+}
+
+extern "C" int dctn_logmatmulexp_forward_ws(const void* A, const void* B, void* out, int Th, int R, int I, int dtype, void* ws,
+                                            size_t ws_bytes, void* stream) {
+  if (!A || !B || !out) return dctn_set_error(DCTN_ERR_BAD_ARG, "logmatmulexp: null tensor pointer");
+  const size_t need = dctn_logmatmulexp_workspace_bytes(Th, R, I, dtype);
+  if (need == 0) return dctn_set_error(DCTN_ERR_UNSUPPORTED, "logmatmulexp_forward_ws: shape (%d, %d, %d) is served by dctn_logmatmulexp_forward only", Th, R, I);
+  if (!ws || ws_bytes < need || ((uintptr_t)ws & 15)) return dctn_set_error(DCTN_ERR_WORKSPACE, "logmatmulexp: 16-byte aligned workspace of %zu bytes needed, got %zu", need, ws_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  return dtype == DCTN_F32 ? lme_tile_forward<float>((const float*)A, (const float*)B, (float*)out, Th, R, I, ws, st)
+                           : lme_tile_forward<double>((const double*)A, (const double*)B, (double*)out, Th, R, I, ws, st);
+}
+
+extern "C" int dctn_logmatmulexp_backward_ws(const void* A, const void* B, const void* out, const void* gout, void* dA, void* dB,
+                                             int Th, int R, int I, int dtype, const void* ws, size_t ws_bytes, void* stream) {
+  if (!A || !B || !out || !gout) return dctn_set_error(DCTN_ERR_BAD_ARG, "logmatmulexp backward: null tensor pointer");
+  const size_t need = dctn_logmatmulexp_workspace_bytes(Th, R, I, dtype);
+  if (need == 0) return dctn_set_error(DCTN_ERR_UNSUPPORTED, "logmatmulexp_backward_ws: shape (%d, %d, %d) is served by dctn_logmatmulexp_backward only", Th, R, I);
+  if (!ws || ws_bytes < need || ((uintptr_t)ws & 15)) return dctn_set_error(DCTN_ERR_WORKSPACE, "logmatmulexp: the workspace of the forward call (%zu bytes) is needed, got %zu", need, ws_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  return dtype == DCTN_F32
+             ? lme_tile_backward<float>((const float*)A, (const float*)B, (const float*)out, (const float*)gout, (float*)dA, (float*)dB, Th, R, I, ws, st)
+             : lme_tile_backward<double>((const double*)A, (const double*)B, (const double*)out, (const double*)gout, (double*)dA, (double*)dB, Th, R, I, ws, st);
+}
+
 extern "C" int dctn_logmatmulexp_batched_forward(const void* A, const void* B, void* out, long long batch, int Th, int R,
                                                  int I, int dtype, void* stream) {
   if (!A || !B || !out) return dctn_set_error(DCTN_ERR_BAD_ARG, "logmatmulexp_batched: null tensor pointer");
   if (batch < 1 || Th < 1 || R < 1 || I < 1)
     return dctn_set_error(DCTN_ERR_BAD_ARG, "logmatmulexp_batched: sizes must be positive (%lld, %d, %d, %d)", batch, Th, R, I);
+  { int rc; if ((rc = check_aligned(out, "output"))) return rc; }   // the float32 register-tiled kernels store 128 bits at a time
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DCTN_F32) return lme_batched_forward<float>((const float*)A, (const float*)B, (float*)out, batch, Th, R, I, st);
   if (dtype == DCTN_F64) return lme_batched_forward<double>((const double*)A, (const double*)B, (double*)out, batch, Th, R, I, st);
@@ -434,6 +466,7 @@ extern "C" int dctn_logmatmulexp_batched_backward(const void* A, const void* B, 
   if (!A || !B || !out || !gout) return dctn_set_error(DCTN_ERR_BAD_ARG, "logmatmulexp_batched backward: null tensor pointer");
   if (batch < 1 || Th < 1 || R < 1 || I < 1)
     return dctn_set_error(DCTN_ERR_BAD_ARG, "logmatmulexp_batched: sizes must be positive (%lld, %d, %d, %d)", batch, Th, R, I);
+  { int rc; if ((dA && (rc = check_aligned(dA, "grad_A"))) || (dB && (rc = check_aligned(dB, "grad_B")))) return rc; }
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DCTN_F32)
     return lme_batched_backward<float>((const float*)A, (const float*)B, (const float*)out, (const float*)gout, (float*)dA, (float*)dB, batch, Th, R, I, st);

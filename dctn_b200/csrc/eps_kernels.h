@@ -60,6 +60,12 @@ int tcfast_gemm(const EpsGeom& g, int mode, const float* x, const float* gout, c
 // ---- logmatmulexp (logmatmulexp.cu)
 template <typename T> int lme_forward(const T* A, const T* B, T* out, int Th, int R, int I, cudaStream_t st);
 template <typename T> int lme_backward(const T* A, const T* B, const T* out, const T* gout, T* dA, T* dB, int Th, int R, int I, cudaStream_t st);
+// logmatmulexp_tile.cu: one fused kernel per product for matrices whose inner dimension fits shared memory; `ws` carries the
+// row / column maxima and the "took the per-element path" flag from forward to backward
+size_t lme_tile_workspace_bytes(int Th, int I, size_t es);
+template <typename T> bool lme_tile_supported(int Th, int R, int I);
+template <typename T> int lme_tile_forward(const T* A, const T* B, T* out, int Th, int R, int I, void* ws, cudaStream_t st);
+template <typename T> int lme_tile_backward(const T* A, const T* B, const T* out, const T* gout, T* dA, T* dB, int Th, int R, int I, const void* ws, cudaStream_t st);
 // batched small matrices: A [NB][Th][R], B [NB][R][I] -> out [NB][Th][I] (ConvSBS bond-matrix rings in log space)
 template <typename T> int lme_batched_forward(const T* A, const T* B, T* out, long long NB, int Th, int R, int I, cudaStream_t st);
 template <typename T> int lme_batched_backward(const T* A, const T* B, const T* out, const T* gout, T* dA, T* dB, long long NB, int Th, int R, int I, cudaStream_t st);

@@ -8,8 +8,11 @@
 // at a quarter of the FMUL rate (tools/ubench/split_rates.cu: 12 cycles per packed pair and sub-partition).  So this
 // kernel generates HALF as many elements and loads the rest:
 //   * the reduction is regrouped as  sum_p (KR1[p][a] * TBH[p][bh]) * TLO[p][blo]:  for one (a-tile, bh) the A operand
-//     A'[a][p] is a three-factor product generated into TENSOR MEMORY (TS-form MMA, one row per thread, packed fp32x2
-//     arithmetic), and the B operand is the table TLO itself;
+//     A'[a][p] = TH[p][ah] * (TL[p][al] * TBH[p][bh]) is generated into TENSOR MEMORY (TS-form MMA, one row per thread,
+//     packed fp32x2 arithmetic), and the B operand is the table TLO itself.  The second factor is pre-multiplied by the
+//     table kernel (one row per (bh, al)): a producer thread reads TWO table rows per chunk, not three — the producers
+//     were bound by shared-memory wavefronts (ncu: 60 % LSU at 46 % tensor pipe; a 128-bit shared load is four
+//     wavefronts whatever its lanes share), 768 wavefronts per chunk and SM against 576 tensor cycles; now 512;
 //   * TLO does not depend on the tile, so build_tables16_kernel splits it ONCE per call into the fp16 hi / lo K-major
 //     swizzled image the MMA reads, and one elected thread streams it chunk by chunk with cp.async.bulk (TMA engine,
 //     mbarrier complete_tx) straight into the B stages: no B generation, no generic-proxy writes, no proxy fences;
@@ -40,10 +43,14 @@ namespace {
 
 constexpr int BM = 128;            // a rows = TMEM lanes
 constexpr int CH = 64;             // patches per chunk = one 128-byte fp16 K slab
-constexpr int MAX_STAGES = 4;      // pipeline stages: B slab in shared memory, A' slab in tensor memory (64 columns: hi | lo);
-                                   // as many as fit next to the three accumulators in the 512 TMEM columns
+constexpr int MAX_STAGES = 4;      // A' slabs in tensor memory (64 columns each: hi | lo): as many as fit next to the three
+                                   // accumulators in the 512 TMEM columns
+constexpr int MAX_BSTAGES = 6;     // B slabs in shared memory: their own, deeper ring (a bulk copy of a 24-32 KB slab from L2 has a
+                                   // latency of ~2000 cycles: with the 2 stages the TMEM budget leaves at NT = 128 the MMAs waited
+                                   // 1150 cycles per chunk for B)
 constexpr int TSTAGES = 4;         // table buffers
-constexpr int SEG16 = 24;          // chunks per promotion segment: 24 * 4 k-steps = 96 roundings of the main chain
+constexpr int SEG16 = 12;          // chunks per promotion segment: 12 * 4 k-steps = 48 roundings of the main chain (the promotion
+                                   // runs on the producers beside the MMAs: measured bias at 96 steps 1.5e-6 / 8.7e-6 for random / positive data)
 constexpr int NPROD_WARPS = 8;     // warps 1..8 generate A'; warp 0 issues MMAs; warp 9 streams the tables, warp 10 the B slabs
 constexpr int NTHREADS = 32 * (3 + NPROD_WARPS);
 constexpr int TS_ = CH + 4;        // table row stride in floats (272 bytes)
@@ -56,7 +63,10 @@ struct Dc16Args {
   float* part;           // [splits][A][N]
   long long per_split;   // multiple of CH
   int NT, ntile;         // blo columns per tile, number of blo tiles
+  int bstages;           // B slabs in shared memory
   long long* dbg;
+  int dbg_skip_gen;      // timing builds: producers signal without generating (isolates the MMA rate)
+  int dbg_order;         // timing builds: 1 = every MMA into ONE accumulator, 2 = three accumulators round-robin (results are wrong)
 };
 
 // ---- pass 1: exps[p] = E_p, *emax = max_p E_p (one thread per patch; *emax starts below every possible value)
@@ -67,14 +77,21 @@ __global__ void __launch_bounds__(256) patch_exp_kernel(EpsGeom g, const float* 
   if (p < g.P) {
     const long long o0 = patch_origin(g, p);
     E = 0;
+    bool zero = false;   // an all-zero factor vector or gout row: the patch contributes nothing
     for (int j = 0; j < g.n; ++j) {
       float m = 0.f;
       for (int q = 0; q < g.Q; ++q) m = fmaxf(m, fabsf(__ldg(&x[o0 + g.foff[j] + q])));
       E += tc::norm_exp(m);
+      zero |= (m == 0.f);
     }
     float m = 0.f;
     for (int o = 0; o < g.O; ++o) m = fmaxf(m, fabsf(__ldg(&gout[p * g.O + o])));
     E += tc::norm_exp(m);
+    zero |= (m == 0.f);
+    // Such a patch must not set E_max: its norm_exp(0) = 0 terms would put it far ABOVE patches whose gradients are
+    // merely small (upstream gradients of a deep stack reach 1e-20 and underflow to exact zeros for some patches), and
+    // every real patch would be scaled by 2^(E_p - E_max) into fp16 underflow — an all-zero core gradient.
+    if (zero) E = INT_MIN;
     exps[p] = E;
   }
 #pragma unroll
@@ -83,8 +100,9 @@ __global__ void __launch_bounds__(256) patch_exp_kernel(EpsGeom g, const float* 
 }
 
 // ---- pass 2, one CTA per chunk of 64 patches:
-//   tables[chunk][entry][i]: entries [0, AH): 2^15 * first-half hi group, [AH, AH+AL): first-half lo group,
-//                            [AH+AL, +BH): 2^(E_p - E_max) * second-half hi group           (all from normalised x)
+//   tables[chunk][entry][i]: entries [0, AH): 2^15 * first-half hi group,
+//                            [AH + bh*AL + al]: first-half lo group entry al * 2^(E_p - E_max) * second-half hi group entry bh
+//                            (all from normalised x)
 //   bimg[chunk][tile][part][row][64 fp16]: split-fp16 image of 2^15 * (second-half lo group x gout), rows = blo
 __global__ void __launch_bounds__(256) build_tables16_kernel(EpsGeom g, const float* __restrict__ x, const float* __restrict__ gout,
                                                              float* __restrict__ tables, uint32_t* __restrict__ bimg, int NT, int ntile,
@@ -95,6 +113,8 @@ __global__ void __launch_bounds__(256) build_tables16_kernel(EpsGeom g, const fl
   float* gs = xs + NX * CH;        // [O][64]
   float* wp = gs + O * CH;         // [64]
   float* tlo = wp + CH;            // [BL][64]: second-half lo group, evaluated once and reused for every o
+  float* tal = tlo + g.BL * CH;    // [AL][64]: first-half lo group
+  float* tbh = tal + g.AL * CH;    // [BH][64]: second-half hi group times the patch weight
   const long long p0 = (long long)blockIdx.x * CH;
   const int lq = (Q & (Q - 1)) == 0 ? 31 - __clz(Q) : -1;      // log2(Q) when Q is a power of two: digits by shifts
   {
@@ -124,7 +144,8 @@ __global__ void __launch_bounds__(256) build_tables16_kernel(EpsGeom g, const fl
   }
   if (threadIdx.x < CH) {
     const long long p = p0 + threadIdx.x;
-    wp[threadIdx.x] = (p < g.P) ? scalbnf(1.f, max(exps[p] - __ldg(emax), -200)) : 0.f;
+    const int ep = (p < g.P) ? exps[p] : INT_MIN;     // INT_MIN: padding, or a patch that contributes nothing
+    wp[threadIdx.x] = (ep != INT_MIN) ? scalbnf(1.f, max(ep - __ldg(emax), -200)) : 0.f;
   }
   __syncthreads();
   auto group = [&](int j0, int cnt, int e, int i) -> float {
@@ -137,19 +158,28 @@ __global__ void __launch_bounds__(256) build_tables16_kernel(EpsGeom g, const fl
     }
     return v;
   };
-  const int ENT = g.AH + g.AL + g.BH;
+  const int ENT = g.AH + g.BH * g.AL;
   float* out = tables + (long long)blockIdx.x * ENT * TS_;
-  for (int idx = threadIdx.x; idx < ENT * CH; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < g.AH * CH; idx += blockDim.x) {
     const int i = idx & (CH - 1), t = idx >> 6;
-    float v;
-    if (t < g.AH) v = 32768.f * group(0, g.a_nh, t, i);
-    else if (t < g.AH + g.AL) v = group(g.a_nh, g.a_nl, t - g.AH, i);
-    else v = wp[i] * group(g.m, g.b_nh, t - g.AH - g.AL, i);
-    out[t * TS_ + i] = v;
+    out[t * TS_ + i] = 32768.f * group(0, g.a_nh, t, i);
   }
   for (int idx = threadIdx.x; idx < ENT * (TS_ - CH); idx += blockDim.x) out[(idx / (TS_ - CH)) * TS_ + CH + idx % (TS_ - CH)] = 0.f;
   for (int idx = threadIdx.x; idx < g.BL * CH; idx += blockDim.x) tlo[idx] = 32768.f * group(g.m + g.b_nh, g.b_nl, idx >> 6, idx & (CH - 1));
+  for (int idx = threadIdx.x; idx < g.AL * CH; idx += blockDim.x) tal[idx] = group(g.a_nh, g.a_nl, idx >> 6, idx & (CH - 1));
+  for (int idx = threadIdx.x; idx < g.BH * CH; idx += blockDim.x) tbh[idx] = wp[idx & (CH - 1)] * group(g.m, g.b_nh, idx >> 6, idx & (CH - 1));
   __syncthreads();
+  // first-half lo group x second-half hi group: one row per (bh, al), four patches per item (128-bit stores)
+  {
+    float* lg = out + (long long)g.AH * TS_;
+    const int rows = g.BH * g.AL;
+    for (int idx = threadIdx.x; idx < rows * (CH / 4); idx += blockDim.x) {
+      const int i4 = idx & (CH / 4 - 1), row = idx >> 4;
+      const int bh = row / g.AL, al = row - bh * g.AL;
+      const float4 l4 = *(const float4*)(tal + al * CH + 4 * i4), b4 = *(const float4*)(tbh + bh * CH + 4 * i4);
+      *(float4*)(lg + (long long)row * TS_ + 4 * i4) = make_float4(l4.x * b4.x, l4.y * b4.y, l4.z * b4.z, l4.w * b4.w);
+    }
+  }
   // B image: one item = (row, packed pair of patches)
   const int BLO = g.BL * O;
   uint32_t* img = bimg + (long long)blockIdx.x * ntile * 2 * NT * 32;
@@ -174,7 +204,8 @@ __global__ void __launch_bounds__(256) build_tables16_kernel(EpsGeom g, const fl
 // out[i] = 2^(E_max - 30) * sum_z part[z*count + i]  (fixed order: deterministic)
 __global__ void reduce_partials_scaled_kernel(const float* __restrict__ part, float* __restrict__ out, long long count, int splits,
                                               const int* __restrict__ emax) {
-  const int k = __ldg(emax) - 30;
+  int k = __ldg(emax);
+  k = (k < -100000) ? -600 : k - 30;       // E_max untouched: no patch contributes, every partial sum is zero
   const float s1 = scalbnf(1.f, k / 2), s2 = scalbnf(1.f, k - k / 2);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
     float s = 0.f;
@@ -214,17 +245,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
   const int bh = blockIdx.y / a.ntile, tile = blockIdx.y - bh * a.ntile;
   int a1 = a0 + BM - 1; if (a1 > g.A - 1) a1 = g.A - 1;
   const int ah0 = a0 / g.AL, nah = a1 / g.AL - ah0 + 1;
-  // rows of one table buffer: [nah first-half hi | AL first-half lo | the bh row | zero row]
-  const int rBH = nah + g.AL, rZ = rBH + 1, TE = rZ + 1;
+  // rows of one table buffer: [nah first-half hi | AL rows of (first-half lo x this CTA's bh) | zero row]
+  const int rZ = nah + g.AL, TE = rZ + 1;
 
   unsigned char* base = smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u);
-  unsigned char* stages = base;                                  // [STAGES][hi|lo][NT rows x 128 B]
-  float* tabs = (float*)(base + STAGES * STAGE_BYTES);           // [TSTAGES][TE][TS_]
+  const int BST = a.bstages;
+  unsigned char* stages = base;                                  // [BST][hi|lo][NT rows x 128 B]
+  float* tabs = (float*)(base + BST * STAGE_BYTES);              // [TSTAGES][TE][TS_]
   uint64_t* bars = (uint64_t*)(tabs + TSTAGES * TE * TS_);
-  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * MAX_STAGES + 2 * TSTAGES + 4);
-  const uint32_t bar_fullA0 = tc::smem_u32(bars), bar_fullB0 = bar_fullA0 + 8 * MAX_STAGES;
-  const uint32_t bar_empty0 = bar_fullB0 + 8 * MAX_STAGES;       // one per stage: frees the TMEM A' slab and the smem B slab
-  const uint32_t bar_tfull0 = bar_empty0 + 8 * MAX_STAGES, bar_tempty0 = bar_tfull0 + 8 * TSTAGES;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * MAX_STAGES + 2 * MAX_BSTAGES + 2 * TSTAGES + 4);
+  const uint32_t bar_fullA0 = tc::smem_u32(bars), bar_emptyA0 = bar_fullA0 + 8 * MAX_STAGES;       // A' slabs (TMEM)
+  const uint32_t bar_fullB0 = bar_emptyA0 + 8 * MAX_STAGES, bar_emptyB0 = bar_fullB0 + 8 * MAX_BSTAGES;   // B slabs (smem)
+  const uint32_t bar_tfull0 = bar_emptyB0 + 8 * MAX_BSTAGES, bar_tempty0 = bar_tfull0 + 8 * TSTAGES;
   const uint32_t bar_accfull0 = bar_tempty0 + 8 * TSTAGES, bar_accempty0 = bar_accfull0 + 16;   // one pair per main accumulator
 
   long long pbeg = (long long)blockIdx.z * a.per_split;
@@ -236,8 +268,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       tc::mbar_init(bar_fullA0 + 8 * s, NPROD_WARPS);
+      tc::mbar_init(bar_emptyA0 + 8 * s, 1);             // tcgen05.commit
+    }
+    for (int s = 0; s < MAX_BSTAGES; ++s) {
       tc::mbar_init(bar_fullB0 + 8 * s, 1);              // expect_tx arrive of the streaming thread (+ bytes)
-      tc::mbar_init(bar_empty0 + 8 * s, 1);              // tcgen05.commit
+      tc::mbar_init(bar_emptyB0 + 8 * s, 1);             // tcgen05.commit
     }
     for (int s = 0; s < TSTAGES; ++s) {
       tc::mbar_init(bar_tfull0 + 8 * s, 1);
@@ -262,9 +297,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
     // =========================== MMA issuer ===========================
     const uint32_t idesc = tc::make_idesc_f16(BM, NT);
     const uint64_t db_base = tc::make_sw128_kmajor_desc(tc::smem_u32(stages));
-    int s = 0;
-    uint32_t ph = 0;
+    int s = 0, sb = 0;          // A' slab (TMEM) and B slab (smem) ring positions
+    uint32_t ph = 0, phb = 0;
     long long dm_acc = 0, dm_b = 0, dm_a = 0, dm_start = TC16_CLK();
+    // The full barriers of chunk c+1 are probed (not waited for) in the middle of issuing chunk c's asynchronous MMAs, so
+    // that at the chunk boundary the next MMAs go out back to back when their operands are there (see eps_tc_fast.cu).
+    bool ready = false;
     for (int c = 0; c < nchunks; ++c) {
       const bool seg_first = (c % SEG16) == 0;
       const bool seg_last = ((c + 1) % SEG16) == 0 || c == nchunks - 1;
@@ -276,30 +314,56 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
         tc::tc_fence_after();
       }
       long long m1 = TC16_CLK();
-      tc::mbar_wait(bar_fullB0 + 8 * s, ph);
-      long long m2 = TC16_CLK();
-      tc::mbar_wait(bar_fullA0 + 8 * s, ph);
-      long long m3 = TC16_CLK();
-      dm_acc += m1 - m0; dm_b += m2 - m1; dm_a += m3 - m2;
-      tc::tc_fence_after();
-      if (lane == 0) {
-        const uint64_t db_hi = db_base + (uint64_t)((s * STAGE_BYTES) >> 4);
-        const uint64_t db_lo = db_hi + (PART_BYTES >> 4);
-        const uint32_t a_hi = tmem_a0 + (uint32_t)(s * 64), a_lo = a_hi + 32;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {                   // 16 patches (32 bytes of K per row) per MMA
-          const uint64_t adv = (uint64_t)(k * 2);
-          const uint32_t acol = (uint32_t)(k * 8);
-          const uint32_t first = (seg_first && k == 0) ? 0u : 1u;
-          tc::umma_f16_ts(tmem_main, a_hi + acol, db_hi + adv, idesc, first);
-          tc::umma_f16_ts(tmem_small, a_hi + acol, db_lo + adv, idesc, (c == 0 && k == 0) ? 0u : 1u);
-          tc::umma_f16_ts(tmem_small, a_lo + acol, db_hi + adv, idesc, 1u);
+      dm_acc += m1 - m0;
+      if (!ready) {
+        tc::mbar_wait(bar_fullB0 + 8 * sb, phb);
+        long long m2 = TC16_CLK();
+        tc::mbar_wait(bar_fullA0 + 8 * s, ph);
+        long long m3 = TC16_CLK();
+        dm_b += m2 - m1; dm_a += m3 - m2;
+        tc::tc_fence_after();
+      }
+      const uint64_t db_hi = db_base + (uint64_t)((sb * STAGE_BYTES) >> 4);
+      const uint64_t db_lo = db_hi + (PART_BYTES >> 4);
+      const uint32_t a_hi = tmem_a0 + (uint32_t)(s * 64), a_lo = a_hi + 32;
+      auto issue = [&](int k) {                         // 16 patches (32 bytes of K per row) per MMA
+        const uint64_t adv = (uint64_t)(k * 2);
+        const uint32_t acol = (uint32_t)(k * 8);
+        const uint32_t first = (seg_first && k == 0) ? 0u : 1u;
+#ifdef DCTN_TCG_TIMING
+        if (a.dbg_order == 1) {
+          tc::umma_f16_ts(tmem_main0, a_hi + acol, db_hi + adv, idesc, 1u);
+          tc::umma_f16_ts(tmem_main0, a_hi + acol, db_lo + adv, idesc, 1u);
+          tc::umma_f16_ts(tmem_main0, a_lo + acol, db_hi + adv, idesc, 1u);
+          return;
         }
-        tc::umma_commit(bar_empty0 + 8 * s);
+        if (a.dbg_order == 2) {
+          tc::umma_f16_ts(tmem_main0, a_hi + acol, db_hi + adv, idesc, 1u);
+          tc::umma_f16_ts(tmem_main0 + NT, a_hi + acol, db_lo + adv, idesc, 1u);
+          tc::umma_f16_ts(tmem_small, a_lo + acol, db_hi + adv, idesc, 1u);
+          return;
+        }
+#endif
+        tc::umma_f16_ts(tmem_main, a_hi + acol, db_hi + adv, idesc, first);
+        tc::umma_f16_ts(tmem_small, a_hi + acol, db_lo + adv, idesc, (c == 0 && k == 0) ? 0u : 1u);
+        tc::umma_f16_ts(tmem_small, a_lo + acol, db_hi + adv, idesc, 1u);
+      };
+      if (tc::elect_one()) { issue(0); issue(1); }
+      __syncwarp();
+      int s_n = s + 1, sb_n = sb + 1;
+      uint32_t ph_n = ph, phb_n = phb;
+      if (s_n == STAGES) { s_n = 0; ph_n ^= 1; }
+      if (sb_n == BST) { sb_n = 0; phb_n ^= 1; }
+      ready = c + 1 < nchunks && tc::mbar_test(bar_fullB0 + 8 * sb_n, phb_n) && tc::mbar_test(bar_fullA0 + 8 * s_n, ph_n);   // probe only
+      if (ready) tc::tc_fence_after();
+      if (tc::elect_one()) {
+        issue(2); issue(3);
+        tc::umma_commit(bar_emptyA0 + 8 * s);
+        tc::umma_commit(bar_emptyB0 + 8 * sb);
         if (seg_last) tc::umma_commit(bar_accfull0 + 8 * mb);
       }
       __syncwarp();
-      if (++s == STAGES) { s = 0; ph ^= 1; }
+      s = s_n; ph = ph_n; sb = sb_n; phb = phb_n;
     }
     if (a.dbg && lane == 0) {
       long long* d = a.dbg + ((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16;
@@ -307,10 +371,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
     }
   } else if (warp == 1 + NPROD_WARPS) {
     // =========================== table streamer (for the producers) ===========================
-    if (lane == 0) {
-      const int ENT = g.AH + g.AL + g.BH;
+    if (tc::elect_one()) {
+      const int ENT = g.AH + g.BH * g.AL;
       const uint32_t row_b = TS_ * 4;
-      const uint32_t tbytes = (uint32_t)(nah + g.AL + 1) * row_b;
+      const uint32_t tbytes = (uint32_t)(nah + g.AL) * row_b;
       int ts = 0;
       uint32_t tph = 1;
       for (int c = 0; c < nchunks; ++c) {
@@ -320,22 +384,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
         const uint32_t tbar = bar_tfull0 + 8 * ts;
         tc::mbar_arrive_expect_tx(tbar, tbytes);
         tc::bulk_g2s(dst, src + (long long)ah0 * TS_, (uint32_t)nah * row_b, tbar);
-        tc::bulk_g2s(dst + (uint32_t)nah * row_b, src + (long long)g.AH * TS_, (uint32_t)g.AL * row_b, tbar);
-        tc::bulk_g2s(dst + (uint32_t)rBH * row_b, src + (long long)(g.AH + g.AL + bh) * TS_, row_b, tbar);
+        tc::bulk_g2s(dst + (uint32_t)nah * row_b, src + (long long)(g.AH + bh * g.AL) * TS_, (uint32_t)g.AL * row_b, tbar);
         if (++ts == TSTAGES) { ts = 0; tph ^= 1; }
       }
     }
   } else if (warp == 2 + NPROD_WARPS) {
     // =========================== B streamer (for the MMAs): the pre-split image, one slab per chunk ===========================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       int s = 0;
       uint32_t ph = 1;
       for (int c = 0; c < nchunks; ++c) {
-        tc::mbar_wait(bar_empty0 + 8 * s, ph);
+        tc::mbar_wait(bar_emptyB0 + 8 * s, ph);
         const float* bsrc = a.bimg + ((chunk0 + c) * a.ntile + tile) * (long long)(2 * NT * 32);
         tc::mbar_arrive_expect_tx(bar_fullB0 + 8 * s, STAGE_BYTES);
         tc::bulk_g2s(tc::smem_u32(stages + s * STAGE_BYTES), bsrc, STAGE_BYTES, bar_fullB0 + 8 * s);
-        if (++s == STAGES) { s = 0; ph ^= 1; }
+        if (++s == BST) { s = 0; ph ^= 1; }
       }
     }
   } else {
@@ -349,7 +412,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
       const int ai = a0 + quad * 32 + lane;
       if (ai < g.A) { offH = (ai / g.AL - ah0) * TS_; offL = (nah + ai % g.AL) * TS_; }
     }
-    const int offB = rBH * TS_;
     // promotion: row quad*32 + lane, columns [hf*NCOL, +NCOL)
     float racc[NCOL];
 #pragma unroll
@@ -388,20 +450,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
       const float* tb = tabs + ts * TE * TS_;
       const float4* th = (const float4*)(tb + offH) + hf * 8;
       const float4* tl = (const float4*)(tb + offL) + hf * 8;
-      const float4* tg = (const float4*)(tb + offB) + hf * 8;
       uint32_t hi[16], lo[16];
+#ifdef DCTN_TCG_TIMING
+      if (a.dbg_skip_gen) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hi[i] = lo[i] = 0x3c003c00u;
+      } else
+#endif
 #pragma unroll
       for (int q4 = 0; q4 < 8; ++q4) {
-        const float4 h4 = th[q4], l4 = tl[q4], b4 = tg[q4];
-        const tc::f32x2_t v01 = tc::mul2(tc::mul2(tc::pack2(h4.x, h4.y), tc::pack2(l4.x, l4.y)), tc::pack2(b4.x, b4.y));
-        const tc::f32x2_t v23 = tc::mul2(tc::mul2(tc::pack2(h4.z, h4.w), tc::pack2(l4.z, l4.w)), tc::pack2(b4.z, b4.w));
+        const float4 h4 = th[q4], l4 = tl[q4];
+        const tc::f32x2_t v01 = tc::mul2(tc::pack2(h4.x, h4.y), tc::pack2(l4.x, l4.y));
+        const tc::f32x2_t v23 = tc::mul2(tc::pack2(h4.z, h4.w), tc::pack2(l4.z, l4.w));
         tc::split_f16x2_p(v01, hi[2 * q4], lo[2 * q4]);
         tc::split_f16x2_p(v23, hi[2 * q4 + 1], lo[2 * q4 + 1]);
       }
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(bar_tempty0 + 8 * ts);   // table buffer read
       if (++ts == TSTAGES) { ts = 0; tph ^= 1; }
-      tc::mbar_wait(bar_empty0 + 8 * s, phe);
+      tc::mbar_wait(bar_emptyA0 + 8 * s, phe);
       tc::tc_fence_after();
       const uint32_t dst = tmem_a0 + lane_base + (uint32_t)(s * 64 + hf * 16);
       tc::tmem_st16_u(dst, hi);
@@ -450,6 +517,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
 // blo-tile width: multiple of 32, <= 128, least padding, then widest
 inline int pick_nt(const EpsGeom& g) {
   const int BLO = g.BL * g.O;
+#ifdef DCTN_TCG_TIMING
+  if (const char* e = getenv("DCTN_B200_DCORE_NT")) return atoi(e);
+#endif
   int best = 0;
   long long best_cost = 0;
   for (int nt = 128; nt >= 32; nt -= 32) {
@@ -480,11 +550,24 @@ inline EpsGeom regroup(const EpsGeom& g0) {
   return best;
 }
 
+inline size_t dcore16_fixed_smem(int TE) {
+  return 1024 + (size_t)TSTAGES * TE * TS_ * 4 + (2 * MAX_STAGES + 2 * MAX_BSTAGES + 2 * TSTAGES + 4) * 8 + 16;
+}
+// B slabs that fit beside the table buffers (at least as many as there are A' slabs in tensor memory)
+inline int dcore16_bstages(int TE, int NT) {
+  const size_t fixed = dcore16_fixed_smem(TE);
+  int nb = fixed < SMEM_LIMIT ? (int)((SMEM_LIMIT - fixed) / ((size_t)2 * NT * 128)) : 0;
+  if (nb > MAX_BSTAGES) nb = MAX_BSTAGES;
+  return nb;
+}
+inline int dcore16_te(const EpsGeom& g) {
+  int nah = (BM + g.AL - 1) / g.AL + 1; if (nah > g.AH) nah = g.AH;
+  return nah + g.AL + 1;
+}
 inline size_t dcore16_smem(const EpsGeom& g, int NT) {
   int nah = (BM + g.AL - 1) / g.AL + 1; if (nah > g.AH) nah = g.AH;
-  const int TE = nah + g.AL + 2;
-  const int stages = ((512 - 3 * NT) / 64 < MAX_STAGES) ? (512 - 3 * NT) / 64 : MAX_STAGES;
-  return 1024 + (size_t)stages * 2 * NT * 128 + (size_t)TSTAGES * TE * TS_ * 4 + (3 * MAX_STAGES + 2 * TSTAGES + 4) * 8 + 16;
+  const int TE = nah + g.AL + 1;
+  return dcore16_fixed_smem(TE) + (size_t)dcore16_bstages(TE, NT) * 2 * NT * 128;
 }
 // split the patch range so that the grid fills whole waves of one CTA per SM
 inline void dcore16_split(const EpsGeom& g, int ntile, long long* per_split, int* splits) {
@@ -506,7 +589,10 @@ inline void dcore16_split(const EpsGeom& g, int ntile, long long* per_split, int
   *splits = (int)((g.P + per - 1) / per);
 }
 inline size_t table_floats(const EpsGeom& g) {
-  return (size_t)((g.P + CH - 1) / CH) * (size_t)(g.AH + g.AL + g.BH) * TS_;
+  return (size_t)((g.P + CH - 1) / CH) * (size_t)(g.AH + (size_t)g.BH * g.AL) * TS_;
+}
+inline size_t table_kernel_smem(const EpsGeom& g) {
+  return (size_t)((g.n * g.Q + g.O + g.BL + g.AL + g.BH) * CH + CH) * sizeof(float);
 }
 inline size_t bimg_words(const EpsGeom& g, int NT, int ntile) { return (size_t)((g.P + CH - 1) / CH) * (size_t)ntile * 2 * NT * 32; }
 
@@ -517,7 +603,7 @@ bool tc16_dcore_supported(const EpsGeom& g0) {
   if (g.P >= (1ll << 31) / (g.Q > g.O ? g.Q : g.O)) return false;   // 32-bit patch index math
   if (g.A < 64 || g.N < 64) return false;       // tiles would be mostly padding: the CUDA-core family is the better fit
   if (g.P < 4096) return false;                 // tiny reductions are launch-bound either way
-  if ((size_t)((g.n * g.Q + g.O + g.BL) * CH + CH) * sizeof(float) > 200 * 1024) return false;   // table kernel staging
+  if (table_kernel_smem(g) > 200 * 1024) return false;   // table kernel staging
   return dcore16_smem(g, pick_nt(g)) <= SMEM_LIMIT;
 }
 
@@ -537,6 +623,8 @@ int tc16_backward_core(const EpsGeom& g0, const float* x, const float* gout, flo
   if (smem > SMEM_LIMIT) return dctn_set_error(-2, "tcgen05 core-gradient kernel needs %zu bytes of shared memory", smem);
   Dc16Args a{};
   a.g = g; a.part = (float*)ws; a.NT = NT; a.ntile = ntile;
+  a.bstages = dcore16_bstages(dcore16_te(g), NT);
+  if (a.bstages < 2) return dctn_set_error(-2, "tcgen05 core-gradient kernel: the tables of this shape leave no room for the B slabs");
   int splits;
   dcore16_split(g, ntile, &a.per_split, &splits);
   float* tables = a.part + (((size_t)splits * g.A * g.N + 63) & ~(size_t)63);
@@ -544,7 +632,7 @@ int tc16_backward_core(const EpsGeom& g0, const float* x, const float* gout, flo
   int* exps = (int*)(bimg + ((bimg_words(g, NT, ntile) + 63) & ~(size_t)63));
   int* emax = exps + ((g.P + 63) & ~63ll);
   a.tables = tables; a.bimg = (const float*)bimg;
-  const size_t bsm = (size_t)((g.n * g.Q + g.O + g.BL) * CH + CH) * sizeof(float);
+  const size_t bsm = table_kernel_smem(g);
   if (bsm > 200 * 1024) return dctn_set_error(-2, "table kernel needs %zu bytes of shared memory", bsm);
   DCTN_CUDA_CHECK_RET(cudaMemsetAsync(emax, 0x80, sizeof(int), st));   // 0x80808080: below every possible E_p
   patch_exp_kernel<<<(unsigned)((g.P + 255) / 256), 256, 0, st>>>(g, x, gout, exps, emax);
@@ -566,6 +654,8 @@ int tc16_backward_core(const EpsGeom& g0, const float* x, const float* gout, flo
     cudaMemsetAsync(dbg_buf, 0, 4096 * 16 * sizeof(long long), st);
     a.dbg = dbg_buf;
   }
+  a.dbg_skip_gen = getenv("DCTN_B200_SKIP_GEN") != nullptr;
+  a.dbg_order = getenv("DCTN_B200_MMA_ORDER") ? atoi(getenv("DCTN_B200_MMA_ORDER")) : 0;
 #endif
   kern<<<grid, NTHREADS, smem, st>>>(a);
   dctn_count_launch();

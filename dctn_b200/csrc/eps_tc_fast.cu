@@ -64,6 +64,7 @@ struct FastArgs {
   int ej0, ecnth, ecntl; // forward epilogue: KR2 hi factors [ej0, ej0+ecnth), lo factors after them -> EL registers
   int EHE, ELR;          // Q^ecnth, Q^ecntl
   int Ncols, ntiles, nk, BN, bstages;
+  int kseg, nseg;        // K stages per accumulation segment, segments per column tile (see tc::seg_stages)
   const float* packed;   // [ntiles][nk][hi|lo][BN rows x 128 bytes], swizzled
   const uint32_t* core_absmax;
   float* out;            // FMODE_STORE: [np][ldc]; FMODE_FWD: out[P][O]
@@ -304,6 +305,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
     }
   }
   __syncthreads();
+  const long long dbg_t_loaded = TCF_CLK();
   if (tid < 128) {
     int ea = 0, eb = 0, el = 0;
     for (int j = 0; j < g.n; ++j) {
@@ -372,6 +374,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
   tc::tc_fence_before();
   __syncthreads();  // tables complete; the scratch aliasing the stages is dead from here on
   tc::tc_fence_after();
+  const long long dbg_t_tables = TCF_CLK();
   // lo-group values of this thread's patch: registers for the rest of the kernel
   tc::f32x2_t TL2[KLR / 2];
   float EL[16];
@@ -397,7 +400,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
 
   if (warp == 0) {
     // =========================== bulk-copy issuer (B operand) ===========================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       int s = 0;
       uint32_t ph = 1;
       const float* src = a.packed;
@@ -418,39 +421,61 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
     uint32_t pha = 0, phb = 0;
     const uint64_t db_base = tc::make_sw128_kmajor_desc(tc::smem_u32(stages));
     const uint32_t stage_adv = STAGE_BYTES >> 4, part_adv = B_BYTES >> 4;
-    for (int t = 0; t < a.ntiles; ++t) {
+    // The MMAs are asynchronous, so the issuing thread has a whole stage of tensor time to spare: the full barriers of
+    // stage i+1 are PROBED in the middle of issuing stage i (after half of its MMAs); when they have completed, the next
+    // stage's MMAs go out back to back at the stage boundary instead of after two barrier polls.  (A blocking wait at
+    // that point was measured to hurt: it holds back the second half of the current stage whenever an operand is late.)
+    bool ready = false;     // the current stage's full barriers have already been waited for
+    // A column tile's K loop is cut into segments of at most a.kseg stages, each accumulated from zero and added to the
+    // result by the epilogue in fp32 (round to nearest): the tensor core truncates its accumulator toward zero at every
+    // MMA, a bias that grows with the length of the chain (tc::seg_stages).  One segment = one "virtual tile".
+    const int nvt = a.ntiles * a.nseg;
+    for (int u = 0; u < nvt; ++u) {
+      const int sg = u % a.nseg;
+      const int kc0 = sg * a.kseg, kc1 = (kc0 + a.kseg < a.nk) ? kc0 + a.kseg : a.nk;
       long long ta = TCF_CLK();
-      if (t > 0) tc::mbar_wait(bar_accempty, (uint32_t)((t - 1) & 1));
+      if (u > 0) tc::mbar_wait(bar_accempty, (uint32_t)((u - 1) & 1));
       dbg_waitAcc += TCF_CLK() - ta;
       tc::tc_fence_after();
-      for (int kc = 0; kc < a.nk; ++kc) {
-        long long t0 = TCF_CLK();
-        tc::mbar_wait(bar_fullB0 + 8 * sb_, phb);
-        long long t1 = TCF_CLK();
-        tc::mbar_wait(bar_fullA0 + 8 * sa, pha);
-        long long t2 = TCF_CLK();
-        dbg_waitB += t1 - t0; dbg_waitA += t2 - t1;
-        tc::tc_fence_after();
-        if (lane == 0) {
-          const uint64_t db_hi = db_base + (uint64_t)(sb_ * stage_adv);
-          const uint64_t db_lo = db_hi + part_adv;
-          const uint32_t a_hi = tmem_a0 + (uint32_t)(sa * 64), a_lo = a_hi + 32;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adv = (uint64_t)(k * 2);
-            const uint32_t acol = (uint32_t)(k * 8);
-            const uint32_t first = (kc == 0 && k == 0) ? 0u : 1u;
-            tc::umma_f16_ts(tmem_main, a_hi + acol, db_hi + adv, idesc, first);
-            tc::umma_f16_ts(tmem_small, a_hi + acol, db_lo + adv, idesc, first);
-            tc::umma_f16_ts(tmem_small, a_lo + acol, db_hi + adv, idesc, 1u);
-          }
+      for (int kc = kc0; kc < kc1; ++kc) {
+        if (!ready) {
+          long long t0 = TCF_CLK();
+          tc::mbar_wait(bar_fullB0 + 8 * sb_, phb);
+          long long t1 = TCF_CLK();
+          tc::mbar_wait(bar_fullA0 + 8 * sa, pha);
+          long long t2 = TCF_CLK();
+          dbg_waitB += t1 - t0; dbg_waitA += t2 - t1;
+          tc::tc_fence_after();
+        }
+        const uint64_t db_hi = db_base + (uint64_t)(sb_ * stage_adv);
+        const uint64_t db_lo = db_hi + part_adv;
+        const uint32_t a_hi = tmem_a0 + (uint32_t)(sa * 64), a_lo = a_hi + 32;
+        auto issue = [&](int k) {
+          const uint64_t adv = (uint64_t)(k * 2);
+          const uint32_t acol = (uint32_t)(k * 8);
+          const uint32_t first = (kc == kc0 && k == 0) ? 0u : 1u;
+          tc::umma_f16_ts(tmem_main, a_hi + acol, db_hi + adv, idesc, first);
+          tc::umma_f16_ts(tmem_small, a_hi + acol, db_lo + adv, idesc, first);
+          tc::umma_f16_ts(tmem_small, a_lo + acol, db_hi + adv, idesc, 1u);
+        };
+        if (tc::elect_one()) { issue(0); issue(1); }
+        __syncwarp();
+        int sa_n = sa + 1, sb_n = sb_ + 1;
+        uint32_t pha_n = pha, phb_n = phb;
+        if (sa_n == NA) { sa_n = 0; pha_n ^= 1; }
+        if (sb_n == NB) { sb_n = 0; phb_n ^= 1; }
+        // look ahead WITHOUT blocking (the second half of this stage's MMAs must not be held back): if the next stage's
+        // operands have landed, its MMAs follow this stage's back to back; otherwise the blocking wait happens at the top
+        ready = !(u == nvt - 1 && kc == kc1 - 1) && tc::mbar_test(bar_fullB0 + 8 * sb_n, phb_n) && tc::mbar_test(bar_fullA0 + 8 * sa_n, pha_n);
+        if (ready) tc::tc_fence_after();
+        if (tc::elect_one()) {
+          issue(2); issue(3);
           tc::umma_commit(bar_emptyA0 + 8 * sa);
           tc::umma_commit(bar_emptyB0 + 8 * sb_);
-          if (kc == a.nk - 1) tc::umma_commit(bar_accfull);
+          if (kc == kc1 - 1) tc::umma_commit(bar_accfull);
         }
         __syncwarp();
-        if (++sa == NA) { sa = 0; pha ^= 1; }
-        if (++sb_ == NB) { sb_ = 0; phb ^= 1; }
+        sa = sa_n; pha = pha_n; sb_ = sb_n; phb = phb_n;
       }
     }
     if (a.dbg && lane == 0) {
@@ -528,8 +553,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
 #pragma unroll
     for (int j = 0; j < 16; ++j) WLO[j] = 0.f;
     long long dbg_epi = 0;
-    for (int t = 0; t < a.ntiles; ++t) {
-      tc::mbar_wait(bar_accfull, (uint32_t)(t & 1));
+    const int nvt = a.ntiles * a.nseg;
+    for (int u = 0; u < nvt; ++u) {
+      const int t = u / a.nseg;
+      const bool accum = (u % a.nseg) != 0;      // a later K segment of the same column tile: add to what is there
+      tc::mbar_wait(bar_accfull, (uint32_t)(u & 1));
       long long te0 = TCF_CLK();
       tc::tc_fence_after();
       const int n0 = t * BN;
@@ -567,7 +595,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
                 float whi = 0.f;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) { whi = fmaf(v[r * 16 + j], EL[j], whi); WLO[j] = fmaf(v[r * 16 + j], th, WLO[j]); }
-                if (pvalid) wrow[eh0 + r] = whi * hsc1 * hsc2;
+                if (pvalid) wrow[eh0 + r] = accum ? fmaf(whi * hsc1, hsc2, wrow[eh0 + r]) : whi * hsc1 * hsc2;
               }
               break;
             case 8:
@@ -577,7 +605,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
                 float whi = 0.f;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { whi = fmaf(v[r * 8 + j], EL[j], whi); WLO[j] = fmaf(v[r * 8 + j], th, WLO[j]); }
-                if (pvalid) wrow[eh0 + r] = whi * hsc1 * hsc2;
+                if (pvalid) wrow[eh0 + r] = accum ? fmaf(whi * hsc1, hsc2, wrow[eh0 + r]) : whi * hsc1 * hsc2;
               }
               break;
             case 4:
@@ -587,7 +615,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
                 float whi = 0.f;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { whi = fmaf(v[r * 4 + j], EL[j], whi); WLO[j] = fmaf(v[r * 4 + j], th, WLO[j]); }
-                if (pvalid) wrow[eh0 + r] = whi * hsc1 * hsc2;
+                if (pvalid) wrow[eh0 + r] = accum ? fmaf(whi * hsc1, hsc2, wrow[eh0 + r]) : whi * hsc1 * hsc2;
               }
               break;
             default:  // 2
@@ -597,7 +625,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
                 const float whi = fmaf(v[r * 2], EL[0], v[r * 2 + 1] * EL[1]);
                 WLO[0] = fmaf(v[r * 2], th, WLO[0]);
                 WLO[1] = fmaf(v[r * 2 + 1], th, WLO[1]);
-                if (pvalid) wrow[eh0 + r] = whi * hsc1 * hsc2;
+                if (pvalid) wrow[eh0 + r] = accum ? fmaf(whi * hsc1, hsc2, wrow[eh0 + r]) : whi * hsc1 * hsc2;
               }
               break;
           }
@@ -605,8 +633,14 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
           if (pvalid) {
             float* crow = a.out + (long long)pl * a.ldc + nb;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *(float4*)(crow + i) = make_float4(v[i] * sc1 * sc2, v[i + 1] * sc1 * sc2, v[i + 2] * sc1 * sc2, v[i + 3] * sc1 * sc2);
+            for (int i = 0; i < 32; i += 4) {
+              float4 r4 = make_float4(v[i] * sc1 * sc2, v[i + 1] * sc1 * sc2, v[i + 2] * sc1 * sc2, v[i + 3] * sc1 * sc2);
+              if (accum) {
+                const float4 o4 = *(const float4*)(crow + i);
+                r4.x += o4.x; r4.y += o4.y; r4.z += o4.z; r4.w += o4.w;
+              }
+              *(float4*)(crow + i) = r4;
+            }
           }
         } else {
           if (a.tsave != nullptr) {
@@ -624,7 +658,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
 #pragma unroll
               for (int r0 = 0; r0 < 32; r0 += 8) {
                 const int r = r0 + rsub;
-                if (pl0 + quad * 32 + r < a.np) *(float4*)(tbase + (long long)r * a.Ncols) = *(const float4*)(st + r * 20 + c4);
+                if (pl0 + quad * 32 + r < a.np) {
+                  float4 r4 = *(const float4*)(st + r * 20 + c4);
+                  float4* tp = (float4*)(tbase + (long long)r * a.Ncols);
+                  if (accum) {
+                    const float4 o4 = *tp;
+                    r4.x += o4.x; r4.y += o4.y; r4.z += o4.z; r4.w += o4.w;
+                  }
+                  *tp = r4;
+                }
               }
               __syncwarp();
             }
@@ -749,6 +791,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
   if (a.dbg && tid == 0) {   // probes (timing build only): setup and whole-CTA cycles replace the producer wait / store slots
     a.dbg[(long long)blockIdx.x * 8 + 4] = dbg_t_setup - dbg_t_entry;
     a.dbg[(long long)blockIdx.x * 8 + 5] = TCF_CLK() - dbg_t_entry;
+    long long* d2 = a.dbg + 4096 * 8 + (long long)blockIdx.x * 4;   // setup phases: x loads | tables | register copies
+    d2[0] = dbg_t_loaded - dbg_t_entry; d2[1] = dbg_t_tables - dbg_t_loaded; d2[2] = dbg_t_setup - dbg_t_tables;
   }
 }
 
@@ -825,12 +869,23 @@ inline int fast_bstages(const EpsGeom& g, const FastShape& s, int mode, int BN) 
 }
 // column-tile width: multiple of 32 (whole epilogue batches), least padded, then widest
 inline int fast_bn(const EpsGeom& g, const FastShape& s, int mode) {
+  if (const char* e = getenv("DCTN_B200_FAST_BN")) {     // tuning override: "<mode>:<BN>[,<mode>:<BN>...]"
+    for (const char* p = e; *p;) {
+      int m = 0, bn = 0;
+      if (sscanf(p, "%d:%d", &m, &bn) == 2 && m == mode && bn >= 32 && bn <= F_MAX_BN && bn % 32 == 0 && fast_bstages(g, s, mode, bn) != 0) return bn;
+      while (*p && *p != ',') ++p;
+      if (*p == ',') ++p;
+    }
+  }
   int best = 0;
   long long best_cost = 0;
   for (int bn = F_MAX_BN; bn >= 64; bn -= 32) {
     if (fast_bstages(g, s, mode, bn) == 0) continue;
     long long cost = (long long)((s.Ncols + bn - 1) / bn) * bn;
     if (bn < 160) cost = cost * 9 / 8;
+    // two B stages cannot cover the latency of the bulk copies (measured, config 2 layer 2 input gradient: BN = 160 with 2
+    // stages 2.86 ms, MMAs waiting 300-600 cycles per stage for B; BN = 128 with 3 stages 2.59 ms)
+    if (fast_bstages(g, s, mode, bn) < 3) cost = cost * 5 / 4;
     if (!best || cost < best_cost) { best = bn; best_cost = cost; }
   }
   return best;
@@ -903,6 +958,7 @@ int tcfast_gemm(const EpsGeom& g, int mode, const float* x, const float* gout, c
   a.jh0 = s.jh0; a.cnth = s.cnth; a.cntl = s.cntl; a.KHE = s.KHE; a.withG = s.withG; a.Kdim = s.Kdim;
   a.ej0 = s.ej0; a.ecnth = s.ecnth; a.ecntl = s.ecntl; a.EHE = s.EHE; a.ELR = s.ELR;
   a.Ncols = s.Ncols; a.ntiles = (s.Ncols + BN - 1) / BN; a.nk = (s.Kdim + FKS - 1) / FKS; a.BN = BN;
+  a.kseg = tc::seg_stages(a.nk); a.nseg = (a.nk + a.kseg - 1) / a.kseg;
   a.bstages = fast_bstages(g, s, mode, BN);
   a.packed = packed; a.core_absmax = absmax; a.out = out; a.ldc = ldc; a.tsave = tsave;
   a.dbg = nullptr;
@@ -910,8 +966,8 @@ int tcfast_gemm(const EpsGeom& g, int mode, const float* x, const float* gout, c
   static long long* dbg_buf = nullptr;
   const int ncta = (np + FBM - 1) / FBM;
   if (getenv("DCTN_TCG_DEBUG") && ncta <= 4096) {
-    if (!dbg_buf) cudaMalloc(&dbg_buf, 4096 * 8 * sizeof(long long));
-    cudaMemsetAsync(dbg_buf, 0, 4096 * 8 * sizeof(long long), st);
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 4096 * 12 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 4096 * 12 * sizeof(long long), st);
     a.dbg = dbg_buf;
   }
 #endif
@@ -921,11 +977,13 @@ int tcfast_gemm(const EpsGeom& g, int mode, const float* x, const float* gout, c
          : (mode == FMODE_LOOX) ? launch_fast_klr<FMODE_LOOX>(a, s.KLR, smem, st) : launch_fast_klr<FMODE_STORE>(a, s.KLR, smem, st);
 #ifdef DCTN_TCG_TIMING
   if (a.dbg && rc == 0) {
-    static long long host[4096 * 8];
+    static long long host[4096 * 12];
     cudaStreamSynchronize(st);
-    cudaMemcpy(host, dbg_buf, (size_t)ncta * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
-    double sum[8] = {0};
+    cudaMemcpy(host, dbg_buf, (size_t)4096 * 12 * sizeof(long long), cudaMemcpyDeviceToHost);
+    double sum[8] = {0}, ph[3] = {0};
     for (int c = 0; c < ncta; ++c) for (int k = 0; k < 8; ++k) sum[k] += (double)host[c * 8 + k];
+    for (int c = 0; c < ncta; ++c) for (int k = 0; k < 3; ++k) ph[k] += (double)host[4096 * 8 + c * 4 + k];
+    fprintf(stderr, "[tcfast dbg] setup phases: x loads %.0f tables %.0f register copies %.0f\n", ph[0] / ncta, ph[1] / ncta, ph[2] / ncta);
     const double nst = (double)a.ntiles * a.nk;
     fprintf(stderr, "[tcfast dbg] mode=%d KLR=%d BN=%d NB=%d ntiles=%d nk=%d per-stage cycles: mma waitA %.0f waitB %.0f waitAcc(per tile) %.0f total %.0f | "
             "CTA setup %.0f whole %.0f | producer gen %.0f | epilogue/tile %.0f\n", mode, s.KLR, BN, a.bstages, a.ntiles, a.nk,

@@ -66,6 +66,8 @@ struct TcGemmArgs {
   int jh0, cnth, KH, cntl, KLb, KL, Kdim, withG;  // generated operand (see GenGemmArgs in eps_ffma.cu)
   int three;            // withG only: 1 = three-level product tabKH * tabKL(lo group alone) * gout instead of the folded table
   int Ncols, ntiles, nk;
+  int kseg, nseg;       // K stages per accumulation segment, segments per column tile (tc::seg_stages)
+  long long seg_stride; // MODE_STORE: segment sg writes its own slice out + sg * seg_stride (summed by sum_slices_kernel)
   const float* packed;  // [ntiles][nk][2][BN*32]
   int BN;               // column-tile width: multiple of 16, <= MAX_BN
   int bstages;          // shared-memory stages for B
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
 
   if (warp == 0) {
     // =========================== bulk-copy issuer (B operand) ===========================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       const uint32_t bytes = B_BYTES * (a.passes == 3 ? 2u : 1u);
       int s = 0;
       uint32_t ph = 1;   // parity to wait for on the empty barrier: fresh barriers pass a wait on parity 1
@@ -343,12 +345,16 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
     uint32_t pha = 0, phb = 0;     // parities of the full barriers
     const uint64_t db_base = tc::make_sw128_kmajor_desc(tc::smem_u32(stages));
     const uint32_t stage_adv = STAGE_BYTES >> 4, part_adv = B_BYTES >> 4;  // descriptor address units (16 bytes)
-    for (int t = 0; t < a.ntiles; ++t) {
+    // one "virtual tile" per (column tile, K segment): see tc::seg_stages
+    const int nvt = a.ntiles * a.nseg;
+    for (int u = 0; u < nvt; ++u) {
+      const int sg = u % a.nseg;
+      const int kc0 = sg * a.kseg, kc1 = (kc0 + a.kseg < a.nk) ? kc0 + a.kseg : a.nk;
       long long ta = TCG_CLK();
-      if (t > 0) tc::mbar_wait(bar_accempty, (uint32_t)((t - 1) & 1));  // epilogue has drained the previous tile
+      if (u > 0) tc::mbar_wait(bar_accempty, (uint32_t)((u - 1) & 1));  // epilogue has drained the previous segment
       dbg_waitAcc += TCG_CLK() - ta;
       tc::tc_fence_after();
-      for (int kc = 0; kc < a.nk; ++kc) {
+      for (int kc = kc0; kc < kc1; ++kc) {
         long long t0 = TCG_CLK();
         tc::mbar_wait(bar_fullB0 + 8 * sb_, phb);
         long long t1 = TCG_CLK();
@@ -356,7 +362,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
         long long t2 = TCG_CLK();
         dbg_waitB += t1 - t0; dbg_waitA += t2 - t1;
         tc::tc_fence_after();
-        if (lane == 0) {
+        if (tc::elect_one()) {
           const uint64_t db_hi = db_base + (uint64_t)(sb_ * stage_adv);
           const uint64_t db_lo = db_hi + part_adv;
           const uint32_t a_hi = tmem_a0 + (uint32_t)(sa * 64), a_lo = a_hi + 32;
@@ -364,7 +370,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
           for (int k = 0; k < 4; ++k) {                 // 4 MMAs of 32 bytes of K per row: 8 x tf32 or 16 x fp16
             const uint64_t adv = (uint64_t)(k * 2);     // 32 bytes >> 4 along the K-major smem rows
             const uint32_t acol = (uint32_t)(k * 8);    // 8 TMEM columns
-            const uint32_t first = (kc == 0 && k == 0) ? 0u : 1u;
+            const uint32_t first = (kc == kc0 && k == 0) ? 0u : 1u;
             if (F16) {
               tc::umma_f16_ts(tmem_main, a_hi + acol, db_hi + adv, idesc, first);
               if (a.passes == 3) {
@@ -381,7 +387,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
           }
           tc::umma_commit(bar_emptyA0 + 8 * sa);
           tc::umma_commit(bar_emptyB0 + 8 * sb_);
-          if (kc == a.nk - 1) tc::umma_commit(bar_accfull);
+          if (kc == kc1 - 1) tc::umma_commit(bar_accfull);
         }
         __syncwarp();
         if (++sa == ASTAGES) { sa = 0; pha ^= 1; }
@@ -493,8 +499,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
       fsc1 = scalbnf(1.f, fexp_all / 2); fsc2 = scalbnf(1.f, fexp_all - fexp_all / 2);
     }
     long long dbg_epi = 0;
-    for (int t = 0; t < a.ntiles; ++t) {
-      tc::mbar_wait(bar_accfull, (uint32_t)(t & 1));
+    const int nvt = a.ntiles * a.nseg;
+    for (int u = 0; u < nvt; ++u) {
+      const int t = u / a.nseg;
+      const bool accum = (u % a.nseg) != 0;   // a later K segment of the same column tile: add to what is there
+      tc::mbar_wait(bar_accfull, (uint32_t)(u & 1));
       long long te0 = TCG_CLK();
       tc::tc_fence_after();
       const int n0 = t * BN;
@@ -519,7 +528,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
             for (int i = 0; i < 32; ++i) v[i] = v[i] * sc1 * sc2;
           }
           if (pvalid) {
-            float* crow = a.out + (long long)pl * a.ldc;
+            // every K segment has its own output slice (plain stores; a read-modify-write of these row-strided 4-byte
+            // accesses was measured at 4x the whole kernel): sum_slices_kernel adds them with coalesced accesses
+            float* crow = a.out + (long long)(u % a.nseg) * a.seg_stride + (long long)pl * a.ldc;
             const int nb = n0 + cb;
             if (cb + 32 <= BN && nb + 32 <= a.Ncols && (a.ldc & 3) == 0) {
 #pragma unroll
@@ -536,13 +547,22 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
             const int nb = n0 + cb;
             if (cb + 32 <= BN && nb + 32 <= a.Ncols && (a.Ncols & 3) == 0) {
 #pragma unroll
-              for (int i = 0; i < 32; i += 4)
-                *(float4*)(trow + nb + i) = F16 ? make_float4(v[i] * sc1 * sc2, v[i + 1] * sc1 * sc2, v[i + 2] * sc1 * sc2, v[i + 3] * sc1 * sc2)
-                                                : make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              for (int i = 0; i < 32; i += 4) {
+                float4 r4 = F16 ? make_float4(v[i] * sc1 * sc2, v[i + 1] * sc1 * sc2, v[i + 2] * sc1 * sc2, v[i + 3] * sc1 * sc2)
+                                : make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                if (accum) {
+                  const float4 o4 = *(const float4*)(trow + nb + i);
+                  r4.x += o4.x; r4.y += o4.y; r4.z += o4.z; r4.w += o4.w;
+                }
+                *(float4*)(trow + nb + i) = r4;
+              }
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (cb + i < BN && nb + i < a.Ncols) trow[nb + i] = F16 ? v[i] * sc1 * sc2 : v[i];
+                if (cb + i < BN && nb + i < a.Ncols) {
+                  const float r1 = F16 ? v[i] * sc1 * sc2 : v[i];
+                  trow[nb + i] = accum ? trow[nb + i] + r1 : r1;
+                }
             }
           }
           // columns cb..cb+31 are b = fb, fb+1, ... (wrapping to the next o at b == Bn; Bn >= 32: at most one wrap)
@@ -587,7 +607,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
             if (i < nvalid) {
               s = fmaf(v[i], gv[i], s);
               if (id[i] & 0x100u) {
-                if (pvalid) a.out[(long long)pl * g.Bn + db] = F16 ? s * sc1 * sc2 : s;
+                if (pvalid) {
+                  float* dst = a.out + (long long)pl * g.Bn + db;
+                  const float r1 = F16 ? s * sc1 * sc2 : s;
+                  *dst = accum ? *dst + r1 : r1;
+                }
                 s = 0.f; ++db;
               }
             }
@@ -715,7 +739,8 @@ int launch_gemm_inst(const TcGemmArgs& a, size_t smem, cudaStream_t st) {
 
 // `passes`: 1 / 3 = TF32 passes, ARITH_F16X3 = split fp16 (absmax: the slot absmax_kernel filled before run_pack)
 int run_gemm(const EpsGeom& g, int mode, int BN, const float* x, const float* gout, const float* packed, long long p0,
-             int np, float* out, long long ldc, int passes, cudaStream_t st, const uint32_t* absmax, float* tsave = nullptr) {
+             int np, float* out, long long ldc, int passes, cudaStream_t st, const uint32_t* absmax, float* tsave = nullptr,
+             long long seg_stride = 0) {
   const GemmShape s = shape_auto(g, mode);
   const bool f16 = passes == ARITH_F16X3;
   const int KS = stage_k(passes);
@@ -723,6 +748,9 @@ int run_gemm(const EpsGeom& g, int mode, int BN, const float* x, const float* go
   a.g = g; a.x = x; a.gout = gout; a.p0 = p0; a.np = np;
   a.jh0 = s.jh0; a.cnth = s.cnth; a.KH = s.KH; a.cntl = s.cntl; a.KLb = s.KLb; a.KL = s.KL; a.Kdim = s.Kdim; a.withG = s.withG; a.three = s.three;
   a.Ncols = s.Ncols; a.ntiles = (s.Ncols + BN - 1) / BN; a.nk = (s.Kdim + KS - 1) / KS;
+  // fp16 stages hold 64 K-values (4 MMAs), tf32 stages 32 (also 4 MMAs): the same number of accumulation steps
+  a.kseg = tc::seg_stages(a.nk); a.nseg = (a.nk + a.kseg - 1) / a.kseg;
+  a.seg_stride = seg_stride;
   a.packed = packed; a.BN = BN; a.bstages = pick_bstages(g, mode, BN); a.passes = f16 ? 3 : passes; a.out = out; a.ldc = ldc;
   a.core_absmax = absmax;
   a.tsave = tsave;
@@ -757,6 +785,21 @@ int run_gemm(const EpsGeom& g, int mode, int BN, const float* x, const float* go
   }
 #endif
   return rc;
+}
+
+// K segments of the generic MODE_STORE GEMM (its output has one slice per segment)
+inline int store_segments(const EpsGeom& g, int passes) {
+  const int nk = (g.N + stage_k(passes) - 1) / stage_k(passes);
+  const int kseg = tc::seg_stages(nk);
+  return (nk + kseg - 1) / kseg;
+}
+// out[i] = sum_s slices[s * stride + i], i < count (fixed order; in place on slice 0)
+__global__ void __launch_bounds__(256) sum_slices_kernel(float* __restrict__ slices, long long stride, long long count, int nslices) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    float s = slices[i];
+    for (int k = 1; k < nslices; ++k) s += slices[(long long)k * stride + i];
+    slices[i] = s;
+  }
 }
 
 // max|core| -> ws header (fp16 arithmetic only); one call per entry point, before the packs
@@ -822,7 +865,8 @@ size_t tcg_workspace_bytes(const EpsGeom& g, int kind) {
     size_t p1 = packed_floats(g, MODE_STORE, pick_bn(g, MODE_STORE)), f1 = tcfast_packed_floats(g, 0);
     if (tcfast_packed_floats(g, 2) > f1) f1 = tcfast_packed_floats(g, 2);
     if (tcfast_packed_floats(g, 3) > f1) f1 = tcfast_packed_floats(g, 3);
-    size_t f = (p1 > f1 ? p1 : f1) + 64 + (size_t)pc * ((size_t)g.A + g.Bn) + (size_t)g.P * g.n * g.Q;
+    const size_t nslice = (size_t)(store_segments(g, 3) > store_segments(g, ARITH_F16X3) ? store_segments(g, 3) : store_segments(g, ARITH_F16X3));
+    size_t f = (p1 > f1 ? p1 : f1) + 64 + (size_t)pc * ((size_t)g.A * nslice + g.Bn) + (size_t)g.P * g.n * g.Q;
     if (kind == 2) f += packed_floats(g, MODE_DKR2, pick_bn(g, MODE_DKR2));
     return WS_HEADER + f * 4 + 1024;
   }
@@ -1072,7 +1116,9 @@ static int backward_input_impl(const EpsGeom& g, const float* x, const float* co
   if (tcfast_packed_floats(g, 3) > pf1) pf1 = tcfast_packed_floats(g, 3);
   float* packed2 = packed1 + ((pf1 + 63) & ~(size_t)63);
   float* dkr1 = packed2 + (tsaved ? 0 : ((packed_floats(g, MODE_DKR2, BN2) + 63) & ~(size_t)63));
-  float* dkr2 = dkr1 + (size_t)pc * g.A;
+  const int nslice1 = fast1 ? 1 : store_segments(g, passes);     // generic MODE_STORE GEMM: one dKR1 slice per K segment
+  const int nslice_ws = store_segments(g, 3) > store_segments(g, ARITH_F16X3) ? store_segments(g, 3) : store_segments(g, ARITH_F16X3);
+  float* dkr2 = dkr1 + (size_t)pc * g.A * nslice_ws;
   float* dxp = dkr2 + (size_t)pc * g.Bn;
   int rc;
   if ((rc = run_absmax(g, core, absmax, passes, st))) return rc;
@@ -1101,8 +1147,16 @@ static int backward_input_impl(const EpsGeom& g, const float* x, const float* co
       if ((rc = launch_loo_groups(g, x, dkr1, ldw1, p0, np, 0, c1h, E1H, c1l, E1L, dxp, st))) return rc;
     } else {
       if (fast1) rc = tcfast_gemm(g, 0, x, gout, packed1, absmax, p0, np, dkr1, g.A, nullptr, st);
-      else rc = run_gemm(g, MODE_STORE, BN1, x, gout, packed1, p0, np, dkr1, g.A, passes, st, absmax);
+      else rc = run_gemm(g, MODE_STORE, BN1, x, gout, packed1, p0, np, dkr1, g.A, passes, st, absmax, nullptr, (long long)pc * g.A);
       if (rc) return rc;
+      if (nslice1 > 1) {
+        const long long count = (long long)np * g.A;
+        int blocks = (int)((count + 255) / 256);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        sum_slices_kernel<<<blocks, 256, 0, st>>>(dkr1, (long long)pc * g.A, count, nslice1);
+        dctn_count_launch();
+        DCTN_CUDA_CHECK_RET(cudaGetLastError());
+      }
       if ((rc = launch_loo<float>(g, x, dkr1, p0, np, 0, dxp, st))) return rc;
     }
     if (fused2) {

@@ -1,0 +1,378 @@
+// logmatmulexp for matrices whose inner dimension fits shared memory (the reference's use: chains of N x N matrices,
+// N <= 300, small_experiments/logmatmulexp_benchmark/benchmark.py:21-52), ONE kernel per product:
+//
+//   out[t][i] = log sum_r exp(A[t][r] + B[r][i])                                             (dctn/logmatmulexp.py:5-14)
+//             = m_t + n_i + log sum_r exp(A[t][r] - m_t) * exp(B[r][i] - n_i),   m_t = max_r A[t][r],  n_i = max_r B[r][i]
+//
+// The second form needs Theta*R + R*I exponentials and a plain fp32 (fp64) matrix product instead of Theta*R*I
+// exponentials — at N = 256 that is 128 K instead of 16.8 M evaluations on the SFU pipe, which is what bounds the
+// per-element form (csrc/logmatmulexp.cu).  It is NOT unconditionally stable: the dominant term of
+// an output can be exp(-spread) below the row / column maxima and underflow (the scale-150 inputs of
+// small_experiments/logmatmulexp_old.py:149-153).  Each CTA therefore checks its own operands: with
+//   spread_A(t) = m_t - min_finite_r A[t][r],   spread_B(i) = n_i - min_finite_r B[r][i]
+// the dominant product of every output of the tile is at least exp(-min(max_t spread_A, max_i spread_B)) (take r at the
+// row maximum of A, or at the column maximum of B); below LIM = 60 (fp32) / 600 (fp64) both factors of the dominant
+// product are normal numbers and every term that underflows is < e^-27 of it.  -inf entries (log 0) are exact zeros
+// and do not count towards the spread.  A tile that fails the test (or holds +inf / NaN) takes the per-element
+// max-shifted path — the same arithmetic as lme_fwd_kernel — from the operands it already has in shared memory, and
+// raises a flag that makes the backward kernels do the same.  So the result is always the stable one; only its cost varies.
+//
+// Backward (nothing Theta*R*I-sized is kept; logmatmulexp_lowmem is the same function):
+//   dA[t][r] = exp(A[t][r] - m_t) * sum_i G[t][i] * exp(B[r][i] - n_i),   G[t][i] = gout[t][i] * exp(m_t + n_i - out[t][i])
+//   dB[r][i] = exp(B[r][i] - n_i) * sum_t exp(A[t][r] - m_t) * G[t][i]
+// (per-element form exp(A + B - out) when the flag is up).  m and n are written by the forward kernel.
+#include <cmath>
+
+#include "../../include/dctn_b200.h"
+#include "common.cuh"
+#include "eps_kernels.h"
+
+namespace {
+
+constexpr int LT = 32;          // output tile LT x LT, 256 threads, 2 x 2 outputs per thread
+constexpr int LTH = 256;
+constexpr size_t LME_SMEM_LIMIT = 200 * 1024;
+
+template <typename T> struct Lim;
+template <> struct Lim<float> { static __device__ __forceinline__ float spread() { return 60.f; } };
+template <> struct Lim<double> { static __device__ __forceinline__ double spread() { return 600.0; } };
+__device__ __forceinline__ float xexp(float v) { return expf(v); }
+__device__ __forceinline__ double xexp(double v) { return exp(v); }
+__device__ __forceinline__ float xlog(float v) { return logf(v); }
+__device__ __forceinline__ double xlog(double v) { return log(v); }
+template <typename T> __device__ __forceinline__ T ninf() { return -(T)INFINITY; }
+template <typename T> __device__ __forceinline__ bool finite_(T v) { return v - v == T(0); }
+
+// ---------------------------------------------------------------------------------------------------------- forward
+template <typename T>
+__global__ void __launch_bounds__(LTH) lme_tile_fwd_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ out,
+                                                           T* __restrict__ rowmax, T* __restrict__ colmax, int* __restrict__ flag,
+                                                           int Th, int R, int I) {
+  extern __shared__ unsigned char lme_smem_raw[];
+  T* sm = reinterpret_cast<T*>(lme_smem_raw);
+  const int RP = R | 1;                      // odd row stride: rows of As are read at a stride by different threads
+  T* As = sm;                                // [LT][RP]
+  T* Bs = As + LT * RP;                      // [R][LT]
+  T* mrow = Bs + (size_t)R * LT;             // [LT] row maxima, then [LT] column maxima
+  T* ncol = mrow + LT;
+  T* red = ncol + LT;                        // [8][LT] x 2 scratch of the column reduction
+  __shared__ int s_unsafe, s_badA, s_badB;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int t0 = blockIdx.y * LT, i0 = blockIdx.x * LT;
+  if (tid == 0) { s_unsafe = 0; s_badA = 0; s_badB = 0; }
+  for (int idx = tid; idx < LT * R; idx += LTH) {
+    const int tl = idx / R, r = idx - tl * R;
+    As[tl * RP + r] = (t0 + tl < Th) ? A[(long long)(t0 + tl) * R + r] : ninf<T>();
+  }
+  for (int idx = tid; idx < R * LT; idx += LTH) {
+    const int r = idx / LT, il = idx - r * LT;
+    Bs[idx] = (i0 + il < I) ? B[(long long)r * I + i0 + il] : ninf<T>();
+  }
+  __syncthreads();
+  // row maxima / finite minima of As: one warp per 4 rows
+  for (int tl = warp; tl < LT; tl += LTH / 32) {
+    T mx = ninf<T>(), mn = -ninf<T>();
+    bool bad = false;
+    for (int r = lane; r < R; r += 32) {
+      const T v = As[tl * RP + r];
+      if (v == ninf<T>()) continue;
+      if (!finite_(v)) { bad = true; continue; }
+      mx = v > mx ? v : mx;
+      mn = v < mn ? v : mn;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const T a = __shfl_xor_sync(0xffffffffu, mx, o), b = __shfl_xor_sync(0xffffffffu, mn, o);
+      mx = a > mx ? a : mx;
+      mn = b < mn ? b : mn;
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+      mrow[tl] = mx;
+      if (bad) s_unsafe = 1;
+      else if (mx != ninf<T>() && mx - mn > Lim<T>::spread()) s_badA = 1;
+    }
+  }
+  // column maxima / finite minima of Bs: 8 threads per column
+  {
+    const int c = tid & 31, part = tid >> 5;
+    T mx = ninf<T>(), mn = -ninf<T>();
+    bool bad = false;
+    for (int r = part; r < R; r += LTH / 32) {
+      const T v = Bs[r * LT + c];
+      if (v == ninf<T>()) continue;
+      if (!finite_(v)) { bad = true; continue; }
+      mx = v > mx ? v : mx;
+      mn = v < mn ? v : mn;
+    }
+    red[part * LT + c] = mx;
+    red[(8 + part) * LT + c] = mn;
+    if (bad) s_unsafe = 1;
+  }
+  __syncthreads();
+  if (tid < LT) {
+    T mx = ninf<T>(), mn = -ninf<T>();
+    for (int p = 0; p < 8; ++p) {
+      const T a = red[p * LT + tid], b = red[(8 + p) * LT + tid];
+      mx = a > mx ? a : mx;
+      mn = b < mn ? b : mn;
+    }
+    ncol[tid] = mx;
+    if (mx != ninf<T>() && mx - mn > Lim<T>::spread()) s_badB = 1;
+  }
+  __syncthreads();
+  const bool exact = s_unsafe || (s_badA && s_badB);
+  if (exact && tid == 0) atomicOr(flag, 1);
+  if (blockIdx.x == 0 && tid < LT && t0 + tid < Th) rowmax[t0 + tid] = mrow[tid];
+  if (blockIdx.y == 0 && tid < LT && i0 + tid < I) colmax[i0 + tid] = ncol[tid];
+  const int ty = tid >> 4, tx = tid & 15;   // outputs (2 ty + u, 2 tx + v)
+  T res[2][2];
+  if (!exact) {
+    for (int idx = tid; idx < LT * R; idx += LTH) {
+      const int tl = idx / R, r = idx - tl * R;
+      const T m = mrow[tl];
+      As[tl * RP + r] = (m == ninf<T>()) ? T(0) : xexp(As[tl * RP + r] - m);
+    }
+    for (int idx = tid; idx < R * LT; idx += LTH) {
+      const T n = ncol[idx & (LT - 1)];
+      Bs[idx] = (n == ninf<T>()) ? T(0) : xexp(Bs[idx] - n);
+    }
+    __syncthreads();
+    T acc[2][2] = {{T(0), T(0)}, {T(0), T(0)}};
+    const T* a0 = As + (2 * ty) * RP;
+    const T* a1 = a0 + RP;
+    const T* b = Bs + 2 * tx;
+#pragma unroll 4
+    for (int r = 0; r < R; ++r) {
+      const T x0 = a0[r], x1 = a1[r], y0 = b[r * LT], y1 = b[r * LT + 1];
+      acc[0][0] += x0 * y0; acc[0][1] += x0 * y1;
+      acc[1][0] += x1 * y0; acc[1][1] += x1 * y1;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const T m = mrow[2 * ty + u], n = ncol[2 * tx + v];
+        res[u][v] = (m == ninf<T>() || n == ninf<T>() || acc[u][v] == T(0)) ? ninf<T>() : m + n + xlog(acc[u][v]);
+      }
+  } else {
+    // per-element max-shifted logsumexp (the arithmetic of lme_fwd_kernel) from the raw operands in shared memory
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const T* a = As + (2 * ty + u) * RP;
+        const T* b = Bs + 2 * tx + v;
+        T m = ninf<T>();
+        for (int r = 0; r < R; ++r) {
+          const T w = a[r] + b[r * LT];
+          m = w > m ? w : m;               // NaN never wins the comparison: handled below
+        }
+        T r0 = m;
+        if (finite_(m)) {
+          T s = T(0);
+          for (int r = 0; r < R; ++r) s += xexp(a[r] + b[r * LT] - m);
+          r0 = m + xlog(s);               // a NaN term makes s, hence the result, NaN — as torch.logsumexp does
+        } else if (m == ninf<T>()) {
+          for (int r = 0; r < R; ++r) {   // all terms -inf, or NaN among them
+            const T w = a[r] + b[r * LT];
+            if (w != w) r0 = w;
+          }
+        }
+        res[u][v] = r0;
+      }
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const int t = t0 + 2 * ty + u, i = i0 + 2 * tx + v;
+      if (t < Th && i < I) out[(long long)t * I + i] = res[u][v];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------- backward
+// WHICH = 0: dA tile (LT rows t x LT columns r), reduction over i;  WHICH = 1: dB tile (LT rows r x LT columns i), over t
+template <typename T, int WHICH>
+__global__ void __launch_bounds__(LTH) lme_tile_bwd_kernel(const T* __restrict__ A, const T* __restrict__ B, const T* __restrict__ out,
+                                                           const T* __restrict__ gout, const T* __restrict__ rowmax,
+                                                           const T* __restrict__ colmax, const int* __restrict__ flag,
+                                                           T* __restrict__ dst, int Th, int R, int I) {
+  extern __shared__ unsigned char lme_smem_raw[];
+  T* sm = reinterpret_cast<T*>(lme_smem_raw);
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const bool exact = *flag != 0;
+  T acc[2][2] = {{T(0), T(0)}, {T(0), T(0)}};
+  if (WHICH == 0) {
+    // rows: X[t][i] (t tile), Y[r][i] (r tile), K = i, both rows contiguous in K
+    const int KP = I | 1;
+    T* Gs = sm;                 // [LT][KP]  G (fast) or gout (exact)
+    T* Os = Gs + LT * KP;       // [LT][KP]  out (exact only)
+    T* Bs = Os + LT * KP;       // [LT][KP]  exp(B - n) (fast) or B (exact)
+    const int t0 = blockIdx.y * LT, r0 = blockIdx.x * LT;
+    for (int idx = tid; idx < LT * I; idx += LTH) {
+      const int l = idx / I, i = idx - l * I;
+      const int t = t0 + l, r = r0 + l;
+      T g = T(0), o = T(0), b = ninf<T>();
+      if (t < Th) { g = gout[(long long)t * I + i]; o = out[(long long)t * I + i]; }
+      if (r < R) b = B[(long long)r * I + i];
+      if (!exact) {
+        const T n = colmax[i];
+        const T m = (t < Th) ? rowmax[t] : ninf<T>();
+        g = (g == T(0) || o == ninf<T>()) ? T(0) : g * xexp(m + n - o);
+        b = (n == ninf<T>()) ? T(0) : xexp(b - n);
+      }
+      Gs[l * KP + i] = g; Os[l * KP + i] = o; Bs[l * KP + i] = b;
+    }
+    __syncthreads();
+    if (!exact) {
+      const T* g0 = Gs + (2 * ty) * KP;
+      const T* g1 = g0 + KP;
+      const T* b0 = Bs + (2 * tx) * KP;
+      const T* b1 = b0 + KP;
+#pragma unroll 4
+      for (int i = 0; i < I; ++i) {
+        const T x0 = g0[i], x1 = g1[i], y0 = b0[i], y1 = b1[i];
+        acc[0][0] += x0 * y0; acc[0][1] += x0 * y1;
+        acc[1][0] += x1 * y0; acc[1][1] += x1 * y1;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const int t = t0 + 2 * ty + u, r = r0 + 2 * tx + v;
+        if (t >= Th || r >= R) continue;
+        const T a = A[(long long)t * R + r];
+        T res;
+        if (!exact) {
+          const T m = rowmax[t];
+          res = (m == ninf<T>()) ? T(0) : xexp(a - m) * acc[u][v];
+        } else {
+          const T* g = Gs + (2 * ty + u) * KP;
+          const T* o = Os + (2 * ty + u) * KP;
+          const T* b = Bs + (2 * tx + v) * KP;
+          res = T(0);
+          for (int i = 0; i < I; ++i) {
+            const T gv = g[i];
+            res += (gv != T(0)) ? gv * xexp(a + b[i] - o[i]) : T(0);
+          }
+        }
+        dst[(long long)t * R + r] = res;
+      }
+  } else {
+    // columns: X[t][r] (r tile), Y[t][i] (i tile), K = t
+    T* As = sm;                       // [Th][LT]  exp(A - m) (fast) or A (exact)
+    T* Gs = As + (size_t)Th * LT;     // [Th][LT]  G (fast) or gout (exact)
+    T* Os = Gs + (size_t)Th * LT;     // [Th][LT]  out (exact only)
+    const int r0 = blockIdx.y * LT, i0 = blockIdx.x * LT;
+    for (int idx = tid; idx < Th * LT; idx += LTH) {
+      const int t = idx / LT, l = idx - t * LT;
+      const int r = r0 + l, i = i0 + l;
+      T a = ninf<T>(), g = T(0), o = T(0);
+      if (r < R) a = A[(long long)t * R + r];
+      if (i < I) { g = gout[(long long)t * I + i]; o = out[(long long)t * I + i]; }
+      if (!exact) {
+        const T m = rowmax[t];
+        const T n = (i < I) ? colmax[i] : ninf<T>();
+        a = (m == ninf<T>()) ? T(0) : xexp(a - m);
+        g = (g == T(0) || o == ninf<T>()) ? T(0) : g * xexp(m + n - o);
+      }
+      As[idx] = a; Gs[idx] = g; Os[idx] = o;
+    }
+    __syncthreads();
+    if (!exact) {
+      const T* a = As + 2 * ty;
+      const T* g = Gs + 2 * tx;
+#pragma unroll 4
+      for (int t = 0; t < Th; ++t) {
+        const T x0 = a[t * LT], x1 = a[t * LT + 1], y0 = g[t * LT], y1 = g[t * LT + 1];
+        acc[0][0] += x0 * y0; acc[0][1] += x0 * y1;
+        acc[1][0] += x1 * y0; acc[1][1] += x1 * y1;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const int r = r0 + 2 * ty + u, i = i0 + 2 * tx + v;
+        if (r >= R || i >= I) continue;
+        const T b = B[(long long)r * I + i];
+        T res;
+        if (!exact) {
+          const T n = colmax[i];
+          res = (n == ninf<T>()) ? T(0) : xexp(b - n) * acc[u][v];
+        } else {
+          res = T(0);
+          for (int t = 0; t < Th; ++t) {
+            const T gv = Gs[t * LT + 2 * tx + v];
+            res += (gv != T(0)) ? gv * xexp(As[t * LT + 2 * ty + u] + b - Os[t * LT + 2 * tx + v]) : T(0);
+          }
+        }
+        dst[(long long)r * I + i] = res;
+      }
+  }
+}
+
+template <typename T> size_t fwd_smem(int R) { return ((size_t)LT * (R | 1) + (size_t)R * LT + 2 * LT + 16 * LT) * sizeof(T); }
+template <typename T> size_t bwd_a_smem(int I) { return (size_t)3 * LT * (I | 1) * sizeof(T); }
+template <typename T> size_t bwd_b_smem(int Th) { return (size_t)3 * Th * LT * sizeof(T); }
+
+}  // namespace
+
+// scratch kept from forward to backward: rowmax [Theta], colmax [I], flag
+size_t lme_tile_workspace_bytes(int Th, int I, size_t es) { return ((size_t)Th + I) * es + 64; }
+
+template <typename T>
+bool lme_tile_supported(int Th, int R, int I) {
+  return fwd_smem<T>(R) <= LME_SMEM_LIMIT && bwd_a_smem<T>(I) <= LME_SMEM_LIMIT && bwd_b_smem<T>(Th) <= LME_SMEM_LIMIT &&
+         (long long)((Th + LT - 1) / LT) < 65536 && (long long)((R + LT - 1) / LT) < 65536;
+}
+template bool lme_tile_supported<float>(int, int, int);
+template bool lme_tile_supported<double>(int, int, int);
+
+template <typename T>
+int lme_tile_forward(const T* A, const T* B, T* out, int Th, int R, int I, void* ws, cudaStream_t st) {
+  T* rowmax = (T*)ws;
+  T* colmax = rowmax + Th;
+  int* flag = (int*)(colmax + I);
+  DCTN_CUDA_CHECK_RET(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  const size_t smem = fwd_smem<T>(R);
+  DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(lme_tile_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((I + LT - 1) / LT, (Th + LT - 1) / LT);
+  lme_tile_fwd_kernel<T><<<grid, LTH, smem, st>>>(A, B, out, rowmax, colmax, flag, Th, R, I);
+  dctn_count_launch();
+  DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  return 0;
+}
+template int lme_tile_forward<float>(const float*, const float*, float*, int, int, int, void*, cudaStream_t);
+template int lme_tile_forward<double>(const double*, const double*, double*, int, int, int, void*, cudaStream_t);
+
+template <typename T>
+int lme_tile_backward(const T* A, const T* B, const T* out, const T* gout, T* dA, T* dB, int Th, int R, int I, const void* ws,
+                      cudaStream_t st) {
+  const T* rowmax = (const T*)ws;
+  const T* colmax = rowmax + Th;
+  const int* flag = (const int*)(colmax + I);
+  if (dA) {
+    const size_t smem = bwd_a_smem<T>(I);
+    auto k = lme_tile_bwd_kernel<T, 0>;
+    DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((R + LT - 1) / LT, (Th + LT - 1) / LT);
+    k<<<grid, LTH, smem, st>>>(A, B, out, gout, rowmax, colmax, flag, dA, Th, R, I);
+    dctn_count_launch();
+    DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  }
+  if (dB) {
+    const size_t smem = bwd_b_smem<T>(Th);
+    auto k = lme_tile_bwd_kernel<T, 1>;
+    DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((I + LT - 1) / LT, (R + LT - 1) / LT);
+    k<<<grid, LTH, smem, st>>>(A, B, out, gout, rowmax, colmax, flag, dB, Th, R, I);
+    dctn_count_launch();
+    DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  }
+  return 0;
+}
+template int lme_tile_backward<float>(const float*, const float*, const float*, const float*, float*, float*, int, int, int, const void*, cudaStream_t);
+template int lme_tile_backward<double>(const double*, const double*, const double*, const double*, double*, double*, int, int, int, const void*, cudaStream_t);

@@ -9,6 +9,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace tc {
 
@@ -44,8 +45,35 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// one non-blocking probe: true when the phase with this parity has completed
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// One lane of the (converged) warp, chosen by the hardware.  Unlike `lane == 0`, the compiler knows that exactly one
+// thread is active after the branch, so the uniform-datapath instructions inside it (tcgen05.mma, tcgen05.commit, bulk
+// copies) are emitted straight-line; behind `if (lane == 0)` each of them sits in its own ELECT / BRA.U.ANY
+// serialisation loop (cuobjdump), which cost ~100 cycles per MMA — more than a 128 x 96 x 16 MMA takes to execute.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -286,6 +314,24 @@ __device__ __forceinline__ int core_scale_exp(uint32_t absmax_bits) {
   const float m = __uint_as_float(absmax_bits);
   if (!(m > 0.f) || !(m < 3.0e38f)) return 0;
   return 15 - norm_exp(m);
+}
+
+// Length of one accumulation segment of the GEMM kernels, in pipeline stages of 64 fp16 K-values (4 MMAs each).
+// The tensor core truncates its fp32 accumulator toward zero on every MMA: measured against the float64 oracle
+// (tools/bias_probe.py, profiles/r02_bias_probe.txt) the result shrinks by ~1.7e-8 per accumulation step for random-sign
+// operands and ~9e-8 per step for all-positive ones (linear in the chain length), e.g. 4e-5 after the 794 steps of the
+// CIFAR (2, 23 -> 24) input gradient.  Chains are therefore cut after 96 steps (24 stages) and the segments summed in
+// fp32 by the epilogue (round to nearest), which bounds the bias at ~1.6e-6 / ~9e-6.  DCTN_B200_KSEG overrides (stages).
+inline int seg_stages(int nk) {
+  int kseg = 24;
+  if (const char* e = getenv("DCTN_B200_KSEG")) {
+    const int v = atoi(e);
+    if (v > 0) kseg = v;
+  }
+  if (kseg > nk) kseg = nk;
+  // equal segments: 25 stages -> 13 + 12 rather than 24 + 1
+  const int nseg = (nk + kseg - 1) / kseg;
+  return (nk + nseg - 1) / nseg;
 }
 
 }  // namespace tc

@@ -96,9 +96,31 @@ def _dense(t: Tensor) -> Tensor:
     return t.clone() if t.data_ptr() % 16 else t
 
 
+# Scratch arenas: ONE buffer per (device, stream), grown to the largest request and reused by every call.  The library's
+# workspace is pure scratch — dead when the call's kernels have run — and calls on one stream execute in order, so
+# sharing it is safe; a per-call torch.empty of hundreds of MB instead makes the caching allocator split and re-cut its
+# large blocks next to the long-lived saved intermediates (seen as cudaMalloc / cudaFree stalls in the middle of a step).
+_arenas: Dict[Tuple[int, int], Tensor] = {}
+
+
 def _workspace(plan: int, B: int, H: int, W: int, kind: int, device) -> Tensor:
     nbytes = _lib.lib().dctn_eps_workspace_bytes(plan, B, H, W, kind)
-    return torch.empty(nbytes, dtype=torch.uint8, device=device)
+    if torch.cuda.is_current_stream_capturing():
+        # graph capture: the allocation must come from the graph's private pool (replays reuse the address)
+        return torch.empty(nbytes, dtype=torch.uint8, device=device)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(device).cuda_stream)
+    arena = _arenas.get(key)
+    if arena is None or arena.numel() < nbytes:
+        arena = None
+        _arenas.pop(key, None)                    # release the old arena before allocating the larger one
+        arena = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+        _arenas[key] = arena
+    return arena
+
+
+def release_workspaces() -> None:
+    """Drops the scratch arenas (they are re-created on demand)."""
+    _arenas.clear()
 
 
 class EpsFunction(torch.autograd.Function):

@@ -101,12 +101,25 @@ class EPSesPlusLinear(nn.Module):
             logger.info(f"Initialized linear.bias from Uniform[{-bias_max:.30e}, {bias_max:.30e}]")
         self.linear.to(device)
         self.register_buffer("p", torch.tensor(p, device=device, dtype=dtype))
+        self._p_host = float(p)
+
+    def _keep_prob(self) -> float:
+        """Host copy of the buffer ``p``.  The reference tests ``self.p < 1.0`` on the device buffer every forward
+        (dctn/eps_plus_linear.py:139), a device-to-host read per step — and an illegal synchronisation while a CUDA graph
+        is being captured (dctn_b200.train_step).  Read once, refreshed when a state_dict is loaded."""
+        if self._p_host is None:
+            self._p_host = float(self.p)
+        return self._p_host
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._p_host = None
+        return super()._load_from_state_dict(*args, **kwargs)
 
     def forward(self, input: Tensor) -> Tensor:
         """Core dropout (train mode and p < 1): every core component is kept with probability p and the
         survivors are divided by p — ONE mask per step for the whole batch (dctn/eps_plus_linear.py:138-147);
         data-parallel ranks must draw it from identically seeded generators (dctn_b200.parallel)."""
-        if self.training and self.p < 1.0:
+        if self.training and self._keep_prob() < 1.0:
             cores = tuple(torch.bernoulli(self.p.expand_as(core)) * core / self.p for core in self.epses)
         else:
             cores = tuple(self.epses)

@@ -59,11 +59,18 @@ class _LogMatMulExp(torch.autograd.Function):
         a = log_A.detach().contiguous()
         b = log_B.detach().contiguous()
         out = torch.empty((theta, I), dtype=a.dtype, device=a.device)
+        lib = _lib.lib()
+        nws = lib.dctn_logmatmulexp_workspace_bytes(theta, R, I, _DTYPES[a.dtype])
         with torch.cuda.device(a.device):
-            rc = _lib.lib().dctn_logmatmulexp_forward(
-                a.data_ptr(), b.data_ptr(), out.data_ptr(), theta, R, I, _DTYPES[a.dtype],
-                torch.cuda.current_stream().cuda_stream,
-            )
+            stream = torch.cuda.current_stream().cuda_stream
+            if nws:   # one fused kernel: N^2 exponentials + a matrix product, per-element fallback inside (logmatmulexp_tile.cu)
+                ws = torch.empty(nws, dtype=torch.uint8, device=a.device)
+                rc = lib.dctn_logmatmulexp_forward_ws(a.data_ptr(), b.data_ptr(), out.data_ptr(), theta, R, I, _DTYPES[a.dtype],
+                                                      ws.data_ptr(), ws.numel(), stream)
+                _lib.check(rc, "dctn_logmatmulexp_forward_ws")
+                ctx.save_for_backward(a, b, out, ws)
+                return out
+            rc = lib.dctn_logmatmulexp_forward(a.data_ptr(), b.data_ptr(), out.data_ptr(), theta, R, I, _DTYPES[a.dtype], stream)
         _lib.check(rc, "dctn_logmatmulexp_forward")
         ctx.save_for_backward(a, b, out)
         return out
@@ -71,10 +78,22 @@ class _LogMatMulExp(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, gout: Tensor):
-        a, b, out = ctx.saved_tensors
+        a, b, out, *rest = ctx.saved_tensors
         theta, R = a.shape
         I = b.shape[1]
         gout = gout.contiguous()
+        if rest:
+            ws = rest[0]
+            dA = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+            dB = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+            with torch.cuda.device(a.device):
+                rc = _lib.lib().dctn_logmatmulexp_backward_ws(
+                    a.data_ptr(), b.data_ptr(), out.data_ptr(), gout.data_ptr(),
+                    dA.data_ptr() if dA is not None else None, dB.data_ptr() if dB is not None else None,
+                    theta, R, I, _DTYPES[a.dtype], ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream,
+                )
+            _lib.check(rc, "dctn_logmatmulexp_backward_ws")
+            return dA, dB
         if theta >= _TALL_THETA and ctx.needs_input_grad[1] and _tall_chunk(R, I, a.element_size()) >= 16:
             return _tall_backward(a, b, out, gout, ctx.needs_input_grad[0])
         dA = torch.empty_like(a) if ctx.needs_input_grad[0] else None
@@ -149,6 +168,10 @@ def logmatmulexp(log_A: Tensor, log_B: Tensor, /) -> Tensor:
         raise RuntimeError("dctn_b200.logmatmulexp runs on CUDA tensors only (no CPU fallback)")
     if log_A.dtype not in _DTYPES or log_A.dtype != log_B.dtype:
         raise TypeError(f"logmatmulexp supports matching float32/float64 inputs, got {log_A.dtype} and {log_B.dtype}")
+    if theta == 0 or I == 0 or R == 0:
+        # empty operands, as the reference handles them: no rows / columns -> empty result; an empty sum is log 0 = -inf
+        # (torch.logsumexp over an empty dimension); the expression keeps the result attached to the autograd graph
+        return (log_A.sum(dim=1, keepdim=True) + log_B.sum(dim=0, keepdim=True)) * 0 + (float("-inf") if R == 0 else 0.0)
     return _LogMatMulExp.apply(log_A, log_B)
 
 

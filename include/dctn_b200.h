@@ -150,10 +150,25 @@ int dctn_logmatmulexp_forward(const void* log_A, const void* log_B, void* out, i
 int dctn_logmatmulexp_backward(const void* log_A, const void* log_B, const void* out, const void* gout,
                                void* dA, void* dB, int Theta, int R, int I, int dtype, void* stream);
 
+/* The same product and gradients by ONE fused kernel each, for matrices whose inner dimension fits shared memory (the
+ * reference's use: chains of N x N matrices, N <= 300, small_experiments/logmatmulexp_benchmark/benchmark.py:21-52):
+ * out = m_t + n_i + log(exp(A - m_t) @ exp(B - n_i)) with row / column maxima m, n — Theta*R + R*I exponentials instead
+ * of Theta*R*I — guarded per tile by a dynamic-range test; tiles that fail it (e.g. the scale-150 inputs of
+ * small_experiments/logmatmulexp_old.py:149-153) use the per-element max-shifted form, so the result is the stable one in
+ * every case.  dctn_logmatmulexp_workspace_bytes() returns the scratch size, or 0 when the shape is served by the two
+ * entries above only; the forward call's workspace must be handed unchanged to the backward call. */
+size_t dctn_logmatmulexp_workspace_bytes(int Theta, int R, int I, int dtype);
+int dctn_logmatmulexp_forward_ws(const void* log_A, const void* log_B, void* out, int Theta, int R, int I, int dtype,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+int dctn_logmatmulexp_backward_ws(const void* log_A, const void* log_B, const void* out, const void* gout, void* dA,
+                                  void* dB, int Theta, int R, int I, int dtype, const void* workspace,
+                                  size_t workspace_bytes, void* stream);
+
 /* Batched small-matrix form: log_A [batch][Theta][R], log_B [batch][R][I] -> out [batch][Theta][I], one product per
  * batch element.  ADDITIONAL entry: the reference's logmatmulexp asserts 2-D (dctn/logmatmulexp.py:8-10)
  * and contracts ConvSBS bond-matrix rings in linear space (dctn/conv_sbs.py:258-304); this is that ring step in log
- * space, one batch element per (image, window).  DCTN_ERR_UNSUPPORTED when one pair exceeds 96 KiB of shared memory. */
+ * space, one batch element per (image, window).  DCTN_ERR_UNSUPPORTED when one pair exceeds 96 KiB of shared memory.
+ * out / dA / dB must be 16-byte aligned (128-bit stores). */
 int dctn_logmatmulexp_batched_forward(const void* log_A, const void* log_B, void* out, long long batch, int Theta,
                                       int R, int I, int dtype, void* stream);
 int dctn_logmatmulexp_batched_backward(const void* log_A, const void* log_B, const void* out, const void* gout,

@@ -72,19 +72,61 @@ def test_cfg2_model_on_tcgen05_vs_oracle():
     assert fams[0]["forward"] == _lib.FAMILY_TCGEN05 and fams[0]["backward_core"] == _lib.FAMILY_TCGEN05, fams
     assert all(f == _lib.FAMILY_TCGEN05 for f in fams[1].values()), fams
     assert launches >= 10
-    assert all(v <= 1e-5 for v in errs.values()), errs
+    assert all(v <= 1e-5 for v in errs.values()), str(errs)
+
+
+def _isolated_layer_errors(model, x, y):
+    """Every layer of `model` run ALONE on the float64 oracle's own inputs and upstream gradients (rounded to float32):
+    {(layer, 'out' | 'dcore' | 'dx'): Frobenius-relative error}.  This is the per-kernel accuracy, free of the errors the
+    earlier layers feed in."""
+    from dctn_b200.eps import eps
+
+    B = x.shape[1]
+    cores = [c.detach().double().cpu().requires_grad_(True) for c in model.epses]
+    w = model.linear.weight.detach().double().cpu()
+    b = model.linear.bias.detach().double().cpu()
+    inters = [x.detach().double().cpu().requires_grad_(True)]
+    for c in cores:
+        nxt = O.eps_4step(c, inters[-1]).unsqueeze(0)
+        nxt.retain_grad()
+        inters.append(nxt)
+    F.cross_entropy(inters[-1].squeeze(0).reshape(B, -1) @ w.T + b, y.cpu()).backward()
+    errs = {}
+    for li, c in enumerate(cores):
+        c32, x32, g32 = c.detach().float(), inters[li].detach().float(), inters[li + 1].grad.squeeze(0).float()
+        cd, xd = c32.to(DEV).requires_grad_(True), x32.to(DEV).requires_grad_(True)
+        out = eps(cd, xd)
+        out.backward(g32.to(DEV))
+        want = O.eps_4step(c32.double(), x32.double())
+        wdc, wdx = O.eps_grads(c32.double(), x32.double(), g32.double())
+        errs[(li, "out")], errs[(li, "dcore")], errs[(li, "dx")] = rel_err(out, want), rel_err(cd.grad, wdc), rel_err(xd.grad, wdx)
+    return errs
 
 
 def test_three_layer_model_vs_oracle():
     """Config 4's 3-layer spec (4,4),(3,12),(2,24) (three_epses_on_fashionmnist.py:16) at image 28, B = 9:
-    layer 2 is K=3, Q=4 -> 12 and layer 3 is K=2, Q=12 -> 24, all on the tcgen05 family."""
+    layer 2 is K=3, Q=4 -> 12 and layer 3 is K=2, Q=12 -> 24, all on the tcgen05 family.
+
+    Tolerances.  Every layer IN ISOLATION (oracle inputs, oracle upstream gradients) must meet 1e-5 on output and both
+    gradients.  End to end a stack of multilinear layers amplifies whatever error a layer makes: the output of layer 1
+    enters layer 2 as K*K = 9 factors and layer 3 as 4 more, so a systematic relative error e1 of layer 1 arrives at
+    the logits as up to 36 * e1 (the reference's own float32 arithmetic is at 3e-6 on this model for the same reason,
+    tools/diag_layers.py).  The tensor core's truncating accumulator makes our per-layer errors (0.3 - 1.3e-6)
+    systematic, so the end-to-end gradients get 5e-5; the logits — dominated here by the bias, the 3-layer output is
+    1e-16 with this initialisation — keep 1e-5.  Upstream gradients reach 1e-20 and flush to exact zeros for some
+    patches: the core gradient of layer 1 must survive that (regression test for the E_max poisoning bug)."""
     from dctn_b200 import _lib
 
     model, x, errs, _ = _model_vs_oracle(((4, 4), (3, 12), (2, 24)), 2, 28, 9, seed=102, input_scale=1.45646, positive=True)
     fams = _layer_families(model, x)
     assert all(f["forward"] == _lib.FAMILY_TCGEN05 and f["backward_core"] == _lib.FAMILY_TCGEN05 for f in fams), fams
     assert fams[1]["backward_input"] == _lib.FAMILY_TCGEN05 and fams[2]["backward_input"] == _lib.FAMILY_TCGEN05, fams
-    assert all(v <= 1e-5 for v in errs.values()), errs
+    assert errs["logits"] <= 1e-5 and errs["dbias"] <= 1e-5, str(errs)
+    assert all(v <= 5e-5 for v in errs.values()), str(errs)
+    torch.manual_seed(102 + 1)
+    y = torch.randint(0, 10, (x.shape[1],))
+    iso = _isolated_layer_errors(model, x, y)
+    assert all(v <= 1e-5 for v in iso.values()), str(iso)
 
 
 @pytest.mark.parametrize("Q1", [12, 23])
@@ -98,7 +140,7 @@ def test_cifar_models_on_tcgen05_vs_oracle(Q1):
     model, x, errs, _ = _model_vs_oracle(((2, Q1), (2, 24)), 4, 32, 5, seed=103 + Q1, input_scale=0.8)
     fams = _layer_families(model, x)
     assert all(f == _lib.FAMILY_TCGEN05 for f in fams[1].values()), fams
-    assert all(v <= 1e-5 for v in errs.values()), errs
+    assert all(v <= 1e-5 for v in errs.values()), str(errs)
     # the same step with and without the saved intermediate T (recompute path of the input gradient)
     model.zero_grad(set_to_none=True)
     old = E._save_limit_bytes
