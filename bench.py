@@ -544,7 +544,8 @@ def cfg5_inputs(workload, batch, seed, device):
     gen = torch.Generator().manual_seed(seed)
     if workload == "cfg5_chain":
         N, nmat = CFG5[workload]["N"], CFG5[workload]["nmat"]
-        return [torch.randn(N, N, generator=gen).to(device).requires_grad_(True) for _ in range(nmat)]
+        # as the reference's benchmark: only the first matrix requires a gradient (benchmark.py:38-40)
+        return [torch.randn(N, N, generator=gen).to(device).requires_grad_(i == 0) for i in range(nmat)]
     bond = CFG5[workload]["bond"]
     u = torch.rand(batch, 28, 28, generator=gen)
     log_x = torch.log(torch.stack((torch.sin(u * math.pi / 2) ** 2, torch.cos(u * math.pi / 2) ** 2), dim=-1).clamp_min(1e-6))[None]

@@ -51,7 +51,12 @@ constexpr int MAX_BSTAGES = 6;     // B slabs in shared memory: their own, deepe
 constexpr int TSTAGES = 4;         // table buffers
 constexpr int SEG16 = 12;          // chunks per promotion segment: 12 * 4 k-steps = 48 roundings of the main chain (the promotion
                                    // runs on the producers beside the MMAs: measured bias at 96 steps 1.5e-6 / 8.7e-6 for random / positive data)
-constexpr int NPROD_WARPS = 8;     // warps 1..8 generate A'; warp 0 issues MMAs; warp 9 streams the tables, warp 10 the B slabs
+constexpr int NPROD_WARPS = 16;    // warps 1..16 generate A' (4 per TMEM lane quadrant, 16 patches of the chunk each); warp 0 issues MMAs;
+                                   // warp 17 streams the tables, warp 18 the B slabs.  Sixteen, not eight: a producer's chunk is a chain
+                                   // of barrier wait -> table loads -> conversion chain -> tcgen05.st -> arrive, and with two warps per
+                                   // sub-partition that latency was exposed (cycle probes: 1100 cycles per chunk against 840 of MMA)
+constexpr int PPQ = NPROD_WARPS / 4;   // producer warps per lane quadrant = parts of the chunk's patch range
+constexpr int PPW = CH / PPQ;          // patches of a chunk per producer warp
 constexpr int NTHREADS = 32 * (3 + NPROD_WARPS);
 constexpr int TS_ = CH + 4;        // table row stride in floats (272 bytes)
 constexpr size_t SMEM_LIMIT = 227 * 1024;
@@ -229,12 +234,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// NTH = NT / 32: accumulator columns per thread = 16 * NTH (compile time: the promotion registers)
+// 32 lanes x 8 consecutive fp32 columns of tensor memory
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// NTH = NT / 32: accumulator columns per thread = NT / PPQ (compile time: the promotion registers)
 template <int NTH>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_constant__ Dc16Args a) {
   extern __shared__ unsigned char smem_dyn[];
   constexpr int NT = 32 * NTH;
-  constexpr int NCOL = 16 * NTH;                       // columns promoted by one thread
+  constexpr int NCOL = NT / PPQ;                       // accumulator columns promoted by one thread
   constexpr int STAGES = ((512 - 3 * NT) / 64 < MAX_STAGES) ? (512 - 3 * NT) / 64 : MAX_STAGES;   // 4, 4, 3, 2 for NT = 32..128
   constexpr uint32_t PART_BYTES = NT * 128;            // hi or lo part of one B slab
   constexpr uint32_t STAGE_BYTES = 2 * PART_BYTES;
@@ -405,7 +423,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
     // =========================== producers: A' rows into tensor memory ===========================
     const int pw = warp - 1;                 // 0..7
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
-    const int hf = pw >> 2;                  // which 32-patch half of the chunk this thread generates
+    const int hf = pw >> 2;                  // which PPW-patch part of the chunk this thread generates
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     int offH = rZ * TS_, offL = rZ * TS_;    // float offsets inside a table buffer; padding rows use the zero row
     {
@@ -424,15 +442,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
       tc::mbar_wait(bar_accfull0 + 8 * mb, (uint32_t)((seg >> 1) & 1));
       tc::tc_fence_after();
 #pragma unroll
-      for (int cb = 0; cb < NCOL; cb += 16) {
-        float v[16];
-        tmem_ld16(tmem_main0 + lane_base + (uint32_t)(mb * NT + hf * NCOL + cb), v);
+      for (int cb = 0; cb < NCOL; cb += 8) {
+        float v[8];
+        tmem_ld8(tmem_main0 + lane_base + (uint32_t)(mb * NT + hf * NCOL + cb), v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) racc[cb + i] += v[i];
+        for (int i = 0; i < 8; ++i) racc[cb + i] += v[i];
         if (seg == nseg - 1) {
-          tmem_ld16(tmem_small + lane_base + (uint32_t)(hf * NCOL + cb), v);
+          tmem_ld8(tmem_small + lane_base + (uint32_t)(hf * NCOL + cb), v);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) racc[cb + i] = fmaf(v[i], 1.f / 2048.f, racc[cb + i]);
+          for (int i = 0; i < 8; ++i) racc[cb + i] = fmaf(v[i], 1.f / 2048.f, racc[cb + i]);
         }
       }
       tc::tc_fence_before();
@@ -448,17 +466,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
       tc::mbar_wait(bar_tfull0 + 8 * ts, tph);
       long long q1 = TC16_CLK();
       const float* tb = tabs + ts * TE * TS_;
-      const float4* th = (const float4*)(tb + offH) + hf * 8;
-      const float4* tl = (const float4*)(tb + offL) + hf * 8;
-      uint32_t hi[16], lo[16];
+      const float4* th = (const float4*)(tb + offH) + hf * (PPW / 4);
+      const float4* tl = (const float4*)(tb + offL) + hf * (PPW / 4);
+      uint32_t hi[PPW / 2], lo[PPW / 2];
 #ifdef DCTN_TCG_TIMING
       if (a.dbg_skip_gen) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) hi[i] = lo[i] = 0x3c003c00u;
+        for (int i = 0; i < PPW / 2; ++i) hi[i] = lo[i] = 0x3c003c00u;
       } else
 #endif
 #pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4) {
+      for (int q4 = 0; q4 < PPW / 4; ++q4) {
         const float4 h4 = th[q4], l4 = tl[q4];
         const tc::f32x2_t v01 = tc::mul2(tc::pack2(h4.x, h4.y), tc::pack2(l4.x, l4.y));
         const tc::f32x2_t v23 = tc::mul2(tc::pack2(h4.z, h4.w), tc::pack2(l4.z, l4.w));
@@ -470,9 +488,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
       if (++ts == TSTAGES) { ts = 0; tph ^= 1; }
       tc::mbar_wait(bar_emptyA0 + 8 * s, phe);
       tc::tc_fence_after();
-      const uint32_t dst = tmem_a0 + lane_base + (uint32_t)(s * 64 + hf * 16);
-      tc::tmem_st16_u(dst, hi);
-      tc::tmem_st16_u(dst + 32, lo);
+      const uint32_t dst = tmem_a0 + lane_base + (uint32_t)(s * 64 + hf * (PPW / 2));
+      tc::tmem_st8_u(dst, hi);
+      tc::tmem_st8_u(dst + 32, lo);
       tc::tmem_st_wait();
       tc::tc_fence_before();
       __syncwarp();
@@ -517,9 +535,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_dcore16_kernel(const __grid_co
 // blo-tile width: multiple of 32, <= 128, least padding, then widest
 inline int pick_nt(const EpsGeom& g) {
   const int BLO = g.BL * g.O;
-#ifdef DCTN_TCG_TIMING
-  if (const char* e = getenv("DCTN_B200_DCORE_NT")) return atoi(e);
-#endif
+  if (const char* e = getenv("DCTN_B200_DCORE_NT")) {   // tuning override
+    const int nt = atoi(e);
+    if (nt == 32 || nt == 64 || nt == 96 || nt == 128) return nt;
+  }
   int best = 0;
   long long best_cost = 0;
   for (int nt = 128; nt >= 32; nt -= 32) {
@@ -535,7 +554,10 @@ inline EpsGeom regroup(const EpsGeom& g0) {
   EpsGeom best = g0;
   long long best_cost = -1;
   const int cnt = g0.n - g0.m;
+  int force_nh = -1;
+  if (const char* e = getenv("DCTN_B200_DCORE_BNH")) force_nh = atoi(e);   // tuning override: hi-group size of the second half
   for (int nh = cnt; nh >= 0; --nh) {
+    if (force_nh >= 0 && force_nh <= cnt && nh != force_nh) continue;
     EpsGeom g = g0;
     g.b_nh = nh; g.b_nl = cnt - nh;
     const long long BH = ipow_host(g0.Q, nh), BL = ipow_host(g0.Q, cnt - nh);
@@ -544,7 +566,12 @@ inline EpsGeom regroup(const EpsGeom& g0) {
     const int NT = pick_nt(g);
     // NT = 128 leaves room for only two A' stages in tensor memory and makes the MMAs of a chunk as long as its
     // generation: measured 1.4x per chunk (config 2, layer 2: 16 x 1 tiles of 96 beat 4 x 3 tiles of 128)
-    const long long cost = BH * ((BL * g0.O + NT - 1) / NT) * (NT == 128 ? 14 : 10);
+    // Both the generation and (the A' operand is read from tensor memory at ~70 cycles per MMA, which hides N <= 128)
+    // the MMA time are proportional to the number of (bh, tile) pairs: wide tiles win.  NT = 128 leaves only two A'
+    // slabs in tensor memory: measured 7 % faster than 16 x 96 at 12 x 128 (config 2, layer 2), not 25 %.
+    const long long ntile = (BL * g0.O + NT - 1) / NT;
+    if ((g0.P + CH - 1) / CH * ntile * 2 * NT * 128 > (640ll << 20)) continue;      // pre-split B image (workspace) cap
+    const long long cost = BH * ntile * (NT == 128 ? 12 : 10);
     if (best_cost < 0 || cost < best_cost) { best = g; best_cost = cost; }
   }
   return best;

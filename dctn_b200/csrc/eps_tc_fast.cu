@@ -132,6 +132,30 @@ __device__ __forceinline__ float kr_entry2(const float* xs, int lq, int j0, int 
   }
   return v;
 }
+// Group table by levels: level L holds, for every patch row, the products of the group's first L factors (digit 0
+// slowest), E0 * Q^L entries; level 0 is `scale` (times g0[t] when the group is led by the gout factor).  The levels
+// ping-pong between `dst` and `tmp` so that the last one lands in dst: one multiplication per entry and level instead
+// of a full product per entry (the per-entry form took 14 k of a CTA's ~20 k setup cycles).  All threads of the CTA.
+__device__ __forceinline__ void build_levels(float* dst, float* tmp, const float* xs, int lq, int j0, int cnt, const float* g0,
+                                             int E0, float scale, int tid) {
+  __syncthreads();                                   // the previous table's last level has been read out of tmp
+  float* cur = (cnt & 1) ? tmp : dst;
+  for (int idx = tid; idx < E0 * 128; idx += F_THREADS) cur[idx] = g0 ? scale * g0[idx] : scale;
+  int E = E0;
+  const int qm = (1 << lq) - 1;
+  for (int L = 0; L < cnt; ++L) {
+    __syncthreads();
+    float* nxt = (cur == dst) ? tmp : dst;
+    const float* xf = xs + (((j0 + L) << lq) << 7);
+    const int En = E << lq;
+    for (int idx = tid; idx < En * 128; idx += F_THREADS) {
+      const int pr = idx & 127, t = idx >> 7;
+      nxt[idx] = cur[((t >> lq) << 7) + pr] * xf[((t & qm) << 7) + pr];
+    }
+    cur = nxt;
+    E = En;
+  }
+}
 // 2^k as a float for -126 <= k <= 127
 __device__ __forceinline__ float pow2i(int k) { return __int_as_float((k + 127) << 23); }
 // power-of-two normalisation of `cnt` values in registers: returns e (max-abs * 2^-e in [0.5, 1)), scales in place (exact)
@@ -262,28 +286,54 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
     const long long p = pt0 + pr;
     const bool valid = p < g.P;
     const long long org = valid ? patch_origin(g, p) : 0;
-#pragma unroll 2
-    for (int j = slot; j < g.n; j += F_THREADS / 128) {
-      float v[16];
-      const float* px = a.x + org + g.foff[j];
-      if (!valid) {
+    if (Q <= 4) {
+      // up to four factors per round, every load of the round issued before the first use (one DRAM round trip per
+      // round instead of one per factor: the loads were 5-8 k cycles of the setup)
+      for (int j0 = slot; j0 < g.n; j0 += 4 * (F_THREADS / 128)) {
+        float4 t[4];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = 0.f;
-      } else if (Q == 2) {
-        const float2 t = __ldg((const float2*)px);
-        v[0] = t.x; v[1] = t.y;
-      } else {
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4)
-          if (q4 * 4 < Q) {
-            const float4 t = __ldg((const float4*)px + q4);
-            v[4 * q4] = t.x; v[4 * q4 + 1] = t.y; v[4 * q4 + 2] = t.z; v[4 * q4 + 3] = t.w;
+        for (int k = 0; k < 4; ++k) {
+          const int j = j0 + k * (F_THREADS / 128);
+          t[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid && j < g.n) {
+            const float* px = a.x + org + g.foff[j];
+            if (Q == 2) { const float2 u = __ldg((const float2*)px); t[k].x = u.x; t[k].y = u.y; }
+            else t[k] = __ldg((const float4*)px);
           }
-      }
-      fexp[j * 128 + pr] = normalise<16>(v, Q);
+        }
 #pragma unroll
-      for (int q = 0; q < 16; ++q)
-        if (q < Q) xs[((j << lq) + q) * 128 + pr] = v[q];
+        for (int k = 0; k < 4; ++k) {
+          const int j = j0 + k * (F_THREADS / 128);
+          if (j < g.n) {
+            float v[4] = {t[k].x, t[k].y, t[k].z, t[k].w};
+            fexp[j * 128 + pr] = normalise<4>(v, Q);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (q < Q) xs[((j << lq) + q) * 128 + pr] = v[q];
+          }
+        }
+      }
+    } else {
+#pragma unroll 2
+      for (int j = slot; j < g.n; j += F_THREADS / 128) {
+        float v[16];
+        const float* px = a.x + org + g.foff[j];
+        if (!valid) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = 0.f;
+        } else {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            if (q4 * 4 < Q) {
+              const float4 t = __ldg((const float4*)px + q4);
+              v[4 * q4] = t.x; v[4 * q4 + 1] = t.y; v[4 * q4 + 2] = t.z; v[4 * q4 + 3] = t.w;
+            }
+        }
+        fexp[j * 128 + pr] = normalise<16>(v, Q);
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          if (q < Q) xs[((j << lq) + q) * 128 + pr] = v[q];
+      }
     }
     if (slot == 0) {
       int e = 0;
@@ -320,49 +370,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
     rowexp[256 + tid] = el;
   }
   {
-    // hi table: entry e (forward) or (o, e) (input gradient); carries the 2^15 of the generated row
-    // four entries per pass, all loads before the stores (the compiler cannot prove that xs and the tables do not alias)
-    const int lkh = lq * a.cnth;                       // log2 of the hi-group entry count
-    for (int idx0 = tid; idx0 < nHrows * 128; idx0 += 4 * F_THREADS) {
-      float v[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int idx = idx0 + k * F_THREADS, pr = idx & 127, r = idx >> 7;
-        v[k] = 0.f;
-        if (r < a.KHE) {
-          v[k] = 32768.f * kr_entry2(xs, lq, a.jh0, a.cnth, r & ((1 << lkh) - 1), pr);
-          if (a.withG) v[k] *= gsx[(r >> lkh) * 128 + pr];
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (idx0 + k * F_THREADS < nHrows * 128) tabH[idx0 + k * F_THREADS] = v[k];
-    }
-    if (MODE == FMODE_FWD || MODE == FMODE_LOO)
-      for (int idx0 = tid; idx0 < a.EHE * 128; idx0 += 4 * F_THREADS) {
-        float v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int idx = idx0 + k * F_THREADS;
-          v[k] = (idx < a.EHE * 128) ? kr_entry2(xs, lq, a.ej0, a.ecnth, idx >> 7, idx & 127) : 0.f;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (idx0 + k * F_THREADS < a.EHE * 128) tabEH[idx0 + k * F_THREADS] = v[k];
-      }
-    for (int idx0 = tid; idx0 < 32 * 128; idx0 += 4 * F_THREADS) {
-      float v[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int idx = idx0 + k * F_THREADS, pr = idx & 127, j = idx >> 7;
-        v[k] = 0.f;
-        if (j < KLR) v[k] = kr_entry2(xs, lq, a.jh0 + a.cnth, a.cntl, j, pr);
-        else if (MODE != FMODE_STORE && j >= 16 && j - 16 < a.ELR) v[k] = kr_entry2(xs, lq, a.ej0 + a.ecnth, a.ecntl, j - 16, pr);
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (idx0 + k * F_THREADS < 32 * 128) regtab[idx0 + k * F_THREADS] = v[k];
-    }
+    // zero rows: K padding of the hi table, unused rows of the lo-group tables
+    for (int idx = tid + a.KHE * 128; idx < nHrows * 128; idx += F_THREADS) tabH[idx] = 0.f;
+    for (int idx = tid; idx < 32 * 128; idx += F_THREADS) regtab[idx] = 0.f;
+    float* ytmp = (float*)(fexp + (g.n + 1) * 128);     // level scratch, in the (still unused) B stages like xs
+    // hi table: entry e (forward) or (o, e) (input gradient: the gout factor leads); carries the 2^15 of the generated row
+    build_levels(tabH, ytmp, xs, lq, a.jh0, a.cnth, a.withG ? gsx : nullptr, a.withG ? O : 1, 32768.f, tid);
+    if (MODE == FMODE_FWD || MODE == FMODE_LOO) build_levels(tabEH, ytmp, xs, lq, a.ej0, a.ecnth, nullptr, 1, 1.f, tid);
+    build_levels(regtab, ytmp, xs, lq, a.jh0 + a.cnth, a.cntl, nullptr, 1, 1.f, tid);                       // rows [0, KLR)
+    if (MODE != FMODE_STORE) build_levels(regtab + 16 * 128, ytmp, xs, lq, a.ej0 + a.ecnth, a.ecntl, nullptr, 1, 1.f, tid);   // rows [16, 16 + ELR)
     if (MODE == FMODE_LOOX) {
       for (int idx = tid; idx < mfirst * Q * 128; idx += F_THREADS) xh[idx] = xs[a.ej0 * Q * 128 + idx];
       for (int idx = tid; idx < mfirst * 128; idx += F_THREADS) fe[idx] = fexp[a.ej0 * 128 + idx];
@@ -864,7 +880,10 @@ inline int fast_bstages(const EpsGeom& g, const FastShape& s, int mode, int BN) 
   int nb = (int)((F_SMEM_LIMIT - fixed) / fast_stage_bytes(BN));
   if (nb > F_MAX_BSTAGES) nb = F_MAX_BSTAGES;
   if (nb < 2) return 0;
-  if ((size_t)(g.n * g.Q + g.O + g.n + 1) * 128 * 4 > nb * fast_stage_bytes(BN)) return 0;   // setup scratch
+  // setup scratch aliased onto the stages: x, gout, exponents and the level buffer of the table builder
+  size_t ymax = (size_t)s.KHE > (size_t)s.EHE ? (size_t)s.KHE : (size_t)s.EHE;
+  if (ymax < 16) ymax = 16;
+  if ((size_t)(g.n * g.Q + g.O + g.n + 1 + ymax / g.Q + 1) * 128 * 4 > nb * fast_stage_bytes(BN)) return 0;
   return nb;
 }
 // column-tile width: multiple of 32 (whole epilogue batches), least padded, then widest

@@ -53,7 +53,9 @@ constexpr int ARITH_F16X3 = 6;  // value of `passes` that selects the split-fp16
 constexpr int ASTAGES = 2;      // A-operand stages in TMEM (2 x (hi + lo) x 32 columns = 128 columns)
 constexpr int MAX_BSTAGES = 4;  // B-operand stages in shared memory (as many as fit)
 constexpr int MAX_BN = 192;     // accumulators: main + small = 2*BN columns, + 128 for A  <= 512 TMEM columns
-constexpr int G_THREADS = 384;  // warp 0: bulk copies, warp 1: MMA, warp 2: TMEM alloc, warps 4-7: producers, warps 8-11: epilogue
+constexpr int G_THREADS = 512;  // warp 0: bulk copies, warp 1: MMA, warp 2: TMEM alloc, warps 4-7 and 12-15: producers (each half of a
+                                // stage's K range: the two table look-ups per generated element made four producer warps the
+                                // limiter, 1600-1900 cycles per stage against 1152 of MMA), warps 8-11: epilogue
 enum { MODE_STORE = 0, MODE_FWD = 1, MODE_DKR2 = 2 };
 constexpr size_t TCG_SMEM_LIMIT = 227 * 1024;
 
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
       tc::mbar_init(bar_emptyB0 + 8 * s, 1);     // tcgen05.commit
     }
     for (int s = 0; s < ASTAGES; ++s) {
-      tc::mbar_init(bar_fullA0 + 8 * s, 4);      // 4 producer warps
+      tc::mbar_init(bar_fullA0 + 8 * s, 8);      // 8 producer warps
       tc::mbar_init(bar_emptyA0 + 8 * s, 1);     // tcgen05.commit
     }
     tc::mbar_init(bar_accfull, 1);
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
   }
   if (warp == 2) tc::tmem_alloc(tc::smem_u32(tmem_slot), TMEM_COLS);
   {
-    // a thread owns one patch row (pr) and every third factor (G_THREADS = 3 x 128): ONE patch-origin computation, the Q
+    // a thread owns one patch row (pr) and every fourth factor (G_THREADS = 4 x 128): ONE patch-origin computation, the Q
     // loads of a factor issued together and — F16 — its range normalisation in the same pass: the factor vector (and the
     // gout row) is scaled by a power of two so that its largest magnitude lies in [0.5, 1); exact, undone by the
     // epilogue through rowexp
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
     const bool valid = p < g.P;
     const long long org = valid ? patch_origin(g, p) : 0;
     const bool needg = a.withG || MODE == MODE_DKR2;
-    for (int j = slot; j <= g.n; j += 3) {
+    for (int j = slot; j <= g.n; j += G_THREADS / 128) {
       const bool isg = j == g.n;
       if (isg && !needg) { if (F16) fexp[j * 128 + pr] = 0; continue; }
       const int cnt = isg ? O : Q;
@@ -398,8 +400,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
       long long* d = a.dbg + (long long)blockIdx.x * 8;
       d[0] = dbg_waitA; d[1] = dbg_waitB; d[2] = dbg_waitAcc; d[3] = TCG_CLK() - dbg_start;
     }
-  } else if (warp >= 4 && warp < 8) {
-    // =========================== A producers: one patch row (= TMEM lane) per thread ===========================
+  } else if ((warp >= 4 && warp < 8) || warp >= 12) {
+    // =========================== A producers: one patch row (= TMEM lane) and one half of the stage per thread ===========================
+    const int ph_ = warp >= 12 ? 1 : 0;        // which half of the stage's K range
     const int pr = (warp & 3) * 32 + lane;
     const float* th = tabKH + pr;
     const float* tl = tabKL + pr;
@@ -410,11 +413,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
     for (int t = 0; t < a.ntiles; ++t) {
       for (int kc = 0; kc < a.nk; ++kc) {
         const int k0 = kc * KS;
-        uint32_t hi[32], lo[32];   // one 32-column TMEM slab each: 32 tf32 values or 64 packed fp16 values
+        uint32_t hi[16], lo[16];   // this half of a 32-column TMEM slab: 16 tf32 values or 32 packed fp16 values
         if (F16) {
           const float* tg = tabG + pr;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          {
+            const int h = ph_;
             uint32_t id[32];
             const uint4* kp = (const uint4*)(kidx + k0 + 32 * h);   // warp-uniform, 16-byte aligned
 #pragma unroll
@@ -431,13 +434,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
               for (int j = 0; j < 32; ++j) v[j] = th[(id[j] & 0xFFFF) * 128] * tl[(id[j] >> 16) * 128];
             }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) split_f16x2(v[2 * j], v[2 * j + 1], hi[16 * h + j], lo[16 * h + j]);
+            for (int j = 0; j < 16; ++j) split_f16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
           }
         } else {
-          uint32_t id[GBK];
-          const uint4* kp = (const uint4*)(kidx + k0);   // warp-uniform, 16-byte aligned
+          uint32_t id[GBK / 2];
+          const uint4* kp = (const uint4*)(kidx + k0 + (GBK / 2) * ph_);   // warp-uniform, 16-byte aligned
 #pragma unroll
-          for (int q4 = 0; q4 < GBK / 4; ++q4) {
+          for (int q4 = 0; q4 < GBK / 8; ++q4) {
             const uint4 u = kp[q4];
             id[4 * q4] = u.x; id[4 * q4 + 1] = u.y; id[4 * q4 + 2] = u.z; id[4 * q4 + 3] = u.w;
           }
@@ -445,13 +448,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
           if (a.three) {
             const float* tg = tabG + pr;
 #pragma unroll
-            for (int j = 0; j < GBK; ++j) {
+            for (int j = 0; j < GBK / 2; ++j) {
               tc::split_tf32(th[(id[j] & 0x3FF) * 128] * tl[((id[j] >> 10) & 0x3FF) * 128] * tg[(id[j] >> 20) * 128], fh, fl);
               hi[j] = __float_as_uint(fh); lo[j] = __float_as_uint(fl);
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < GBK; ++j) {
+            for (int j = 0; j < GBK / 2; ++j) {
               tc::split_tf32(th[(id[j] & 0xFFFF) * 128] * tl[(id[j] >> 16) * 128], fh, fl);
               hi[j] = __float_as_uint(fh); lo[j] = __float_as_uint(fl);
             }
@@ -461,9 +464,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
         tc::mbar_wait(bar_emptyA0 + 8 * sa, phe);
         long long t1 = TCG_CLK();
         tc::tc_fence_after();
-        const uint32_t dst = tmem_a0 + lane_base + (uint32_t)(sa * 64);
-        tc::tmem_st32_u(dst, hi);
-        if (a.passes == 3) tc::tmem_st32_u(dst + 32, lo);
+        const uint32_t dst = tmem_a0 + lane_base + (uint32_t)(sa * 64 + 16 * ph_);
+        tc::tmem_st16_u(dst, hi);
+        if (a.passes == 3) tc::tmem_st16_u(dst + 32, lo);
         tc::tmem_st_wait();
         tc::tc_fence_before();
         __syncwarp();
@@ -477,7 +480,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
       long long* d = a.dbg + (long long)blockIdx.x * 8;
       d[4] = dbg_pwait; d[5] = dbg_pst; d[6] = dbg_pgen;
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 12) {
     // =========================== epilogue ===========================
     const int quad = warp & 3;
     const int pr = quad * 32 + lane;
