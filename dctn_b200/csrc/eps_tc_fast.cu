@@ -65,6 +65,8 @@ struct FastArgs {
   int EHE, ELR;          // Q^ecnth, Q^ecntl
   int Ncols, ntiles, nk, BN, bstages;
   int kseg, nseg;        // K stages per accumulation segment, segments per column tile (see tc::seg_stages)
+  int dbuf;              // 1: two MAIN accumulators alternate between (virtual) tiles, the small one is parked (see the epilogue)
+  int region_floats;     // size of the staging / register-table / parking region
   const float* packed;   // [ntiles][nk][hi|lo][BN rows x 128 bytes], swizzled
   const uint32_t* core_absmax;
   float* out;            // FMODE_STORE: [np][ldc]; FMODE_FWD: out[P][O]
@@ -247,11 +249,18 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
   float* tstage = (float*)(rowexp + 384);
   float* regtab = tstage;                              // [32][128]
   constexpr int REGION_FLOATS = (F_EPI_WARPS * 32 * 20 > 32 * 128) ? F_EPI_WARPS * 32 * 20 : 32 * 128;
-  uint64_t* bars = (uint64_t*)(tstage + REGION_FLOATS);
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * F_MAX_BSTAGES + 2 * F_ASTAGES + 2);
+  // parking area of the small accumulator (double-buffered mode): [8 epilogue warps][32 words][32 lanes] of packed bf16
+  // pairs.  The training forward keeps its staging tiles, so the area follows them; the other modes use the region only
+  // for the register tables during the setup, and the area overlays it.
+  uint32_t* park = (uint32_t*)((MODE == FMODE_FWD) ? tstage + REGION_FLOATS : tstage);
+  uint64_t* bars = (uint64_t*)(tstage + a.region_floats);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * F_MAX_BSTAGES + 2 * F_ASTAGES + 6);
   const uint32_t bar_fullB0 = tc::smem_u32(bars), bar_emptyB0 = bar_fullB0 + 8 * F_MAX_BSTAGES;
   const uint32_t bar_fullA0 = bar_emptyB0 + 8 * F_MAX_BSTAGES, bar_emptyA0 = bar_fullA0 + 8 * F_ASTAGES;
-  const uint32_t bar_accfull = bar_emptyA0 + 8 * F_ASTAGES, bar_accempty = bar_accfull + 8;
+  // accumulators: accfull[b] (MMAs of a tile in main accumulator b are complete), mainempty[b] (its epilogue is done),
+  // smallempty (the small accumulator has been parked).  Single-buffered mode uses accfull[0] / mainempty[0] only.
+  const uint32_t bar_accfull0 = bar_emptyA0 + 8 * F_ASTAGES, bar_mainempty0 = bar_accfull0 + 16, bar_smallempty = bar_mainempty0 + 16;
+  const bool DB = a.dbuf != 0;
   // setup-only scratch aliased onto the B stages: x [n*Q][128], gout [O][128], exponents [(n+1)][128]
   float* xs = (float*)stages;
   float* gsx = xs + g.n * Q * 128;
@@ -272,8 +281,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
       tc::mbar_init(bar_fullA0 + 8 * s, 4);
       tc::mbar_init(bar_emptyA0 + 8 * s, 1);
     }
-    tc::mbar_init(bar_accfull, 1);
-    tc::mbar_init(bar_accempty, F_EPI_WARPS);
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(bar_accfull0 + 8 * b, 1);
+      tc::mbar_init(bar_mainempty0 + 8 * b, F_EPI_WARPS);
+    }
+    tc::mbar_init(bar_smallempty, F_EPI_WARPS);
     tc::fence_barrier_init();
   }
   if (warp == 2) tc::tmem_alloc(tc::smem_u32(tmem_slot), 512);
@@ -408,11 +420,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
   if (warp >= 4) asm volatile("bar.sync 2, %0;" ::"n"(32 * (4 + F_EPI_WARPS)) : "memory");   // regtab consumed: tstage may be written
   const int core_exp = tc::core_scale_exp(__ldg(a.core_absmax));
   const long long dbg_t_setup = TCF_CLK();
-  const uint32_t tmem_main = *tmem_slot;
-  const uint32_t tmem_small = tmem_main + (uint32_t)BN;
-  const uint32_t tmem_a0 = tmem_main + 2u * (uint32_t)BN;   // stage s: hi at +64*s, lo at +64*s + 32
+  // tensor memory: main accumulator(s) | small accumulator | A stages
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t nacc = DB ? 3u : 2u;
+  const uint32_t tmem_small = tmem_base + (nacc - 1u) * (uint32_t)BN;
+  const uint32_t tmem_a0 = tmem_base + nacc * (uint32_t)BN;   // stage s: hi at +64*s, lo at +64*s + 32
   const int total_it = a.ntiles * a.nk;
-  const int NA = (2 * BN + 64 * F_ASTAGES <= 512) ? F_ASTAGES : 2;   // A stages that fit beside the accumulators
+  const int NA = ((int)nacc * BN + 64 * F_ASTAGES <= 512) ? F_ASTAGES : 2;   // A stages that fit beside the accumulators
 
   if (warp == 0) {
     // =========================== bulk-copy issuer (B operand) ===========================
@@ -449,8 +463,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
     for (int u = 0; u < nvt; ++u) {
       const int sg = u % a.nseg;
       const int kc0 = sg * a.kseg, kc1 = (kc0 + a.kseg < a.nk) ? kc0 + a.kseg : a.nk;
+      const int mb = DB ? (u & 1) : 0;
+      const uint32_t tmem_main = tmem_base + (uint32_t)(mb * BN);
       long long ta = TCF_CLK();
-      if (u > 0) tc::mbar_wait(bar_accempty, (uint32_t)((u - 1) & 1));
+      if (!DB) {
+        if (u > 0) tc::mbar_wait(bar_mainempty0, (uint32_t)((u - 1) & 1));
+      } else {
+        if (u > 0) tc::mbar_wait(bar_smallempty, (uint32_t)((u - 1) & 1));                       // the previous tile's small part is parked
+        if (u >= 2) tc::mbar_wait(bar_mainempty0 + 8 * mb, (uint32_t)(((u - 2) >> 1) & 1));      // tile u-2 has left this main accumulator
+      }
       dbg_waitAcc += TCF_CLK() - ta;
       tc::tc_fence_after();
       for (int kc = kc0; kc < kc1; ++kc) {
@@ -488,7 +509,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
           issue(2); issue(3);
           tc::umma_commit(bar_emptyA0 + 8 * sa);
           tc::umma_commit(bar_emptyB0 + 8 * sb_);
-          if (kc == kc1 - 1) tc::umma_commit(bar_accfull);
+          if (kc == kc1 - 1) tc::umma_commit(bar_accfull0 + 8 * mb);
         }
         __syncwarp();
         sa = sa_n; pha = pha_n; sb_ = sb_n; phb = phb_n;
@@ -573,17 +594,44 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
     for (int u = 0; u < nvt; ++u) {
       const int t = u / a.nseg;
       const bool accum = (u % a.nseg) != 0;      // a later K segment of the same column tile: add to what is there
-      tc::mbar_wait(bar_accfull, (uint32_t)(u & 1));
+      const int mb = DB ? (u & 1) : 0;
+      const uint32_t tmem_main = tmem_base + (uint32_t)(mb * BN);
+      tc::mbar_wait(bar_accfull0 + 8 * mb, (uint32_t)(DB ? ((u >> 1) & 1) : (u & 1)));
       long long te0 = TCF_CLK();
       tc::tc_fence_after();
       const int n0 = t * BN;
+      uint32_t* mypark = park + (warp - 8) * (32 * 32) + lane;
+      if (DB) {
+        // Park the small accumulator: its columns of this warp go to shared memory as bf16 pairs (it carries the cross
+        // terms, weight 2^-11: bf16 keeps 2^-20 of the result) and the accumulator is handed back at once — the next
+        // tile's MMAs (into the OTHER main accumulator) run while this epilogue works through the main one.
+#pragma unroll 1
+        for (int cb = 32 * half; cb < BN; cb += 64) {
+          if (n0 + cb >= a.Ncols) break;
+          float w[32];
+          tc::tmem_ld32(tmem_small + lane_base + (uint32_t)cb, w);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) mypark[((cb >> 6) * 16 + i) * 32] = tc::pack_bf16x2(w[2 * i], w[2 * i + 1]);
+        }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(bar_smallempty);
+      }
 #pragma unroll 1
       for (int cb = 0; cb < BN; cb += 32) {
         const int nb = n0 + cb;
         if (nb >= a.Ncols) break;             // Ncols % 32 == 0 (host check): batches are whole or empty
         if (((cb >> 5) & 1) != half) continue;
         float v[32];
-        {
+        if (DB) {
+          tc::tmem_ld32(tmem_main + lane_base + (uint32_t)cb, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint32_t pw = mypark[((cb >> 6) * 16 + i) * 32];
+            v[2 * i] = fmaf(__uint_as_float(pw << 16), 1.f / 2048.f, v[2 * i]);
+            v[2 * i + 1] = fmaf(__uint_as_float(pw & 0xFFFF0000u), 1.f / 2048.f, v[2 * i + 1]);
+          }
+        } else {
           float w[32];
           tc::tmem_ld32x2(tmem_main + lane_base + (uint32_t)cb, tmem_small + lane_base + (uint32_t)cb, v, w);
 #pragma unroll
@@ -735,7 +783,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
       }
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(bar_accempty);
+      if (lane == 0) tc::mbar_arrive(bar_mainempty0 + 8 * mb);
       dbg_epi += TCF_CLK() - te0;
     }
     if (a.dbg && warp == 8 && lane == 0) a.dbg[(long long)blockIdx.x * 8 + 7] = dbg_epi;
@@ -803,7 +851,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_gemm_fast_kernel(const __grid
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 2) tc::tmem_dealloc(tmem_main, 512);
+  if (warp == 2) tc::tmem_dealloc(tmem_base, 512);
   if (a.dbg && tid == 0) {   // probes (timing build only): setup and whole-CTA cycles replace the producer wait / store slots
     a.dbg[(long long)blockIdx.x * 8 + 4] = dbg_t_setup - dbg_t_entry;
     a.dbg[(long long)blockIdx.x * 8 + 5] = TCF_CLK() - dbg_t_entry;
@@ -864,18 +912,23 @@ inline FastShape fast_shape(const EpsGeom& g, int mode) {
 
 // lo-group register tables [32][128], sharing their memory with the staging tiles of the T store [8 warps][32][20]
 constexpr size_t REGION_BYTES = ((size_t)F_EPI_WARPS * 32 * 20 > 32 * 128 ? (size_t)F_EPI_WARPS * 32 * 20 : 32 * 128) * 4;
-inline size_t fast_fixed_smem(const EpsGeom& g, const FastShape& s, int mode) {
+constexpr size_t PARK_BYTES = (size_t)F_EPI_WARPS * 32 * 32 * 4;   // double-buffered mode: the parked small accumulator
+inline size_t fast_region_bytes(int mode, int dbuf) {
+  if (!dbuf) return REGION_BYTES;
+  return mode == FMODE_FWD ? REGION_BYTES + PARK_BYTES : (REGION_BYTES > PARK_BYTES ? REGION_BYTES : PARK_BYTES);
+}
+inline size_t fast_fixed_smem(const EpsGeom& g, const FastShape& s, int mode, int dbuf = 0) {
   const size_t nk = (size_t)(s.Kdim + FKS - 1) / FKS;
   const size_t nH = nk * (FKS / s.KLR);
   const size_t mfirst = (size_t)s.ecnth + s.ecntl;
   const size_t erows = (mode == FMODE_LOOX) ? mfirst * g.Q + mfirst + 2 * (size_t)s.ecnth * g.Q + 32
                      : (mode == FMODE_LOO ? (size_t)s.EHE + 16 : (mode == FMODE_FWD ? (size_t)s.EHE : 0));
-  return 1024 + (nH + erows + (mode == FMODE_FWD ? 2 * (size_t)g.O : 0)) * 128 * 4 + 384 * 4 + REGION_BYTES +
-         (2 * F_MAX_BSTAGES + 2 * F_ASTAGES + 2) * 8 + 16;
+  return 1024 + (nH + erows + (mode == FMODE_FWD ? 2 * (size_t)g.O : 0)) * 128 * 4 + 384 * 4 + fast_region_bytes(mode, dbuf) +
+         (2 * F_MAX_BSTAGES + 2 * F_ASTAGES + 6) * 8 + 16;
 }
 inline size_t fast_stage_bytes(int BN) { return 2 * (size_t)BN * 128; }
-inline int fast_bstages(const EpsGeom& g, const FastShape& s, int mode, int BN) {
-  const size_t fixed = fast_fixed_smem(g, s, mode);
+inline int fast_bstages(const EpsGeom& g, const FastShape& s, int mode, int BN, int dbuf = 0) {
+  const size_t fixed = fast_fixed_smem(g, s, mode, dbuf);
   if (fixed >= F_SMEM_LIMIT) return 0;
   int nb = (int)((F_SMEM_LIMIT - fixed) / fast_stage_bytes(BN));
   if (nb > F_MAX_BSTAGES) nb = F_MAX_BSTAGES;
@@ -910,6 +963,25 @@ inline int fast_bn(const EpsGeom& g, const FastShape& s, int mode) {
   return best;
 }
 
+// Tile configuration: column-tile width and whether two main accumulators alternate (BN <= 128: 3 BN + 128 columns of
+// tensor memory).  Double buffering hides the epilogue behind the next tile's MMAs — single-buffered, the MMAs waited
+// 3-7 k cycles per tile for it (12-27 % of the kernel) — and is taken whenever it fits with three B stages.
+struct FastCfg { int BN, dbuf, nb; };
+inline FastCfg fast_cfg(const EpsGeom& g, const FastShape& s, int mode) {
+  FastCfg c{fast_bn(g, s, mode), 0, 0};
+  if (!c.BN) return c;
+  c.nb = fast_bstages(g, s, mode, c.BN);
+  static const int want = [] { const char* e = getenv("DCTN_B200_FAST_DBUF"); return e ? atoi(e) : 1; }();
+  if (want) {
+    for (int bn = 128; bn >= 64; bn -= 32) {
+      if ((s.Ncols + bn - 1) / bn * bn > (s.Ncols + 127) / 128 * 128 + 32 && bn < 128) continue;   // narrower only when it pads less
+      const int nb = fast_bstages(g, s, mode, bn, 1);
+      if (nb >= 3) { c.BN = bn; c.dbuf = 1; c.nb = nb; break; }
+    }
+  }
+  return c;
+}
+
 template <int MODE, int KLR>
 int launch_fast(const FastArgs& a, size_t smem, cudaStream_t st) {
   auto k = tc_gemm_fast_kernel<MODE, KLR>;
@@ -942,13 +1014,13 @@ int tcfast_loo_groups(const EpsGeom& g, int* cnth, int* EH, int* cntl, int* EL) 
 }
 bool tcfast_supported(const EpsGeom& g, int mode) {
   const FastShape s = fast_shape(g, mode);
-  return s.ok && fast_bn(g, s, mode) != 0;
+  return s.ok && fast_cfg(g, s, mode).BN != 0;
 }
 
 size_t tcfast_packed_floats(const EpsGeom& g, int mode) {
   const FastShape s = fast_shape(g, mode);
   if (!s.ok) return 0;
-  const int BN = fast_bn(g, s, mode);
+  const int BN = fast_cfg(g, s, mode).BN;
   if (!BN) return 0;
   const long long ntiles = (s.Ncols + BN - 1) / BN, nk = (s.Kdim + FKS - 1) / FKS;
   return (size_t)(ntiles * nk * 2 * BN * 32);
@@ -956,7 +1028,7 @@ size_t tcfast_packed_floats(const EpsGeom& g, int mode) {
 
 int tcfast_pack(const EpsGeom& g, int mode, const float* core, float* dst, const uint32_t* absmax, cudaStream_t st) {
   const FastShape s = fast_shape(g, mode);
-  const int BN = fast_bn(g, s, mode);
+  const int BN = fast_cfg(g, s, mode).BN;
   const int ntiles = (s.Ncols + BN - 1) / BN, nk = (s.Kdim + FKS - 1) / FKS;
   const long long total = (long long)ntiles * nk * BN * 8;
   int blocks = (int)((total + 255) / 256);
@@ -970,7 +1042,8 @@ int tcfast_pack(const EpsGeom& g, int mode, const float* core, float* dst, const
 int tcfast_gemm(const EpsGeom& g, int mode, const float* x, const float* gout, const float* packed, const uint32_t* absmax,
                 long long p0, int np, float* out, long long ldc, float* tsave, cudaStream_t st) {
   const FastShape s = fast_shape(g, mode);
-  const int BN = s.ok ? fast_bn(g, s, mode) : 0;
+  const FastCfg cfg = s.ok ? fast_cfg(g, s, mode) : FastCfg{0, 0, 0};
+  const int BN = cfg.BN;
   if (!BN) return dctn_set_error(-2, "register-table GEMM does not support this shape");
   FastArgs a{};
   a.g = g; a.x = x; a.gout = gout; a.p0 = p0; a.np = np;
@@ -978,7 +1051,9 @@ int tcfast_gemm(const EpsGeom& g, int mode, const float* x, const float* gout, c
   a.ej0 = s.ej0; a.ecnth = s.ecnth; a.ecntl = s.ecntl; a.EHE = s.EHE; a.ELR = s.ELR;
   a.Ncols = s.Ncols; a.ntiles = (s.Ncols + BN - 1) / BN; a.nk = (s.Kdim + FKS - 1) / FKS; a.BN = BN;
   a.kseg = tc::seg_stages(a.nk); a.nseg = (a.nk + a.kseg - 1) / a.kseg;
-  a.bstages = fast_bstages(g, s, mode, BN);
+  a.bstages = cfg.nb;
+  a.dbuf = cfg.dbuf;
+  a.region_floats = (int)(fast_region_bytes(mode, cfg.dbuf) / 4);
   a.packed = packed; a.core_absmax = absmax; a.out = out; a.ldc = ldc; a.tsave = tsave;
   a.dbg = nullptr;
 #ifdef DCTN_TCG_TIMING   // cycle probes: timing builds only (allocates, synchronises, not thread-safe)
@@ -990,7 +1065,7 @@ int tcfast_gemm(const EpsGeom& g, int mode, const float* x, const float* gout, c
     a.dbg = dbg_buf;
   }
 #endif
-  const size_t smem = fast_fixed_smem(g, s, mode) + a.bstages * fast_stage_bytes(BN);
+  const size_t smem = fast_fixed_smem(g, s, mode, cfg.dbuf) + a.bstages * fast_stage_bytes(BN);
   int rc = (mode == FMODE_FWD) ? launch_fast_klr<FMODE_FWD>(a, s.KLR, smem, st)
          : (mode == FMODE_LOO) ? launch_fast_klr<FMODE_LOO>(a, s.KLR, smem, st)
          : (mode == FMODE_LOOX) ? launch_fast_klr<FMODE_LOOX>(a, s.KLR, smem, st) : launch_fast_klr<FMODE_STORE>(a, s.KLR, smem, st);

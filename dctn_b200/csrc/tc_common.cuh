@@ -310,6 +310,12 @@ __device__ __forceinline__ void split_f16x2_p(f32x2_t v, uint32_t& hi, uint32_t&
 __device__ __forceinline__ void split_f16x2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
   split_f16x2_p(pack2(v0, v1), hi, lo);
 }
+// two fp32 -> packed bf16 pair (round to nearest), `lo` in the low half
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 // exponent e with m = f * 2^e, f in [0.5, 1); 0 for m == 0 / inf / nan
 __device__ __forceinline__ int norm_exp(float m) {
   int e = 0;
