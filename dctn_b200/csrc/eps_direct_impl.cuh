@@ -959,6 +959,8 @@ bool direct_supported(const EpsGeom& g, int dtype) {
 #if DCTN_DIRECT_PART == 1 || DCTN_DIRECT_PART == 2
 template <typename T>
 int direct_forward(const EpsGeom& g, const T* x, const T* core, T* out, cudaStream_t st) {
+  if constexpr (std::is_same<T, float>::value)
+    if (stream_k2q2_enabled() && stream_k2q2_supported(g, 0)) return stream_k2q2_forward(g, x, core, out, st);
   if (g.K == 2 && g.C == 1) {
     if (g.Q == 2) return dispatch_direct_k2<T, 2>(g, x, core, out, st);
     if (g.Q == 3) return dispatch_direct_k2<T, 3>(g, x, core, out, st);
@@ -977,6 +979,8 @@ bool direct_pixels_supported(const EpsGeom& g, int dtype) { return g.K == 2 && g
 #endif
 template <typename T>
 int direct_forward_pixels(const EpsGeom& g, const T* pixels, T scale, const T* core, T* out, cudaStream_t st) {
+  if constexpr (std::is_same<T, float>::value)
+    if (stream_k2q2_enabled() && stream_k2q2_supported(g, 0)) return stream_k2q2_forward_pixels(g, pixels, scale, core, out, st);
   switch (g.O) {
     case 2: return launch_direct_k2<T, 2, 2, true>(g, pixels, core, out, st, scale);
     case 4: return launch_direct_k2<T, 2, 4, true>(g, pixels, core, out, st, scale);

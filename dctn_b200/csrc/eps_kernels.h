@@ -24,6 +24,11 @@ template <typename T> int direct_forward(const EpsGeom& g, const T* x, const T* 
 // phi(u) = scale * (sin^2(pi u / 2), cos^2(pi u / 2)) evaluated on load from the raw pixel image (B, H, W): K = 2, C = 1, Q = 2
 bool direct_pixels_supported(const EpsGeom& g, int dtype);
 template <typename T> int direct_forward_pixels(const EpsGeom& g, const T* pixels, T scale, const T* core, T* out, cudaStream_t st);
+// eps_stream_k2q2.cu: K = 2, C = 1, Q_in = 2, float32 — the HBM-bound corner (one task per warp, packed fp32x2 arithmetic)
+bool stream_k2q2_supported(const EpsGeom& g, int dtype);
+bool stream_k2q2_enabled();   // DCTN_B200_STREAM=0 falls back to the generic small-core kernels (A/B measurements)
+int stream_k2q2_forward(const EpsGeom& g, const float* x, const float* core, float* out, cudaStream_t st);
+int stream_k2q2_forward_pixels(const EpsGeom& g, const float* pixels, float scale, const float* core, float* out, cudaStream_t st);
 bool direct_bwd_supported(const EpsGeom& g, int dtype, int kind);
 size_t direct_workspace_bytes(const EpsGeom& g, int dtype, int kind);
 // kind 1: result = dcore (core unused), kind 2: result = dx

@@ -875,3 +875,37 @@ def test_cifar_shaped_model_vs_oracle(specs, Q0, img):
     for i, c in enumerate(cores):
         assert rel_err(model.epses[i].grad, c.grad) <= 1e-5
     assert rel_err(model.linear.weight.grad, w.grad) <= 1e-5
+
+
+# (B, H, W, Q_out): the streaming K=2, Q_in=2 float32 kernels (csrc/eps_stream_k2q2.cu) — one warp per block of 9 or 4 output
+# rows x 31 columns: full and ragged row blocks, several column tiles, odd Q_out, one and several output pairs, 2 x 2 images
+STREAM_SHAPES = [(5, 28, 28, 2), (3, 28, 28, 3), (2, 28, 28, 4), (2, 28, 28, 5), (2, 28, 28, 6), (2, 28, 28, 8), (2, 28, 28, 1),
+                 (3, 11, 40, 3), (2, 5, 70, 5), (4, 2, 2, 2), (2, 46, 33, 2), (2, 47, 64, 4), (1, 30, 32, 7), (7, 10, 19, 6)]
+
+
+@pytest.mark.parametrize("shape", STREAM_SHAPES)
+def test_stream_k2q2_vs_oracle(shape):
+    """Forward (featurised and raw-pixel entry) and both gradients of the K=2, Q_in=2 float32 family against the oracle
+    (dctn/eps.py:19-40); pixels outside [0, 1] exercise the period reduction of the fused feature map."""
+    from dctn_b200 import eps as E
+
+    B, H, W, Oq = shape
+    g = torch.Generator().manual_seed(1000 + B + 7 * H + 31 * W + Oq)
+    x = torch.randn(1, B, H, W, 2, dtype=torch.float64, generator=g).float().double()
+    core = (torch.randn(2, 2, 2, 2, Oq, dtype=torch.float64, generator=g) * 0.25).float().double()
+    gout = torch.randn(B, H - 1, W - 1, Oq, dtype=torch.float64, generator=g).float().double()
+    want = O.eps_4step(core, x)
+    want_dcore, want_dx = O.eps_grads(core, x, gout)
+    out, dcore, dx = _eps_fwd_bwd(core, x, gout, torch.float32)
+    assert out.shape == want.shape
+    assert rel_err(out, want) <= 1e-5
+    assert (out.double().cpu() - want).abs().max() <= 1e-5 * want.abs().max()     # element-wise: no patch is skipped
+    assert rel_err(dcore, want_dcore) <= 1e-5
+    assert rel_err(dx, want_dx) <= 1e-5
+    u = (torch.rand(B, H, W, generator=g, dtype=torch.float64) * 5 - 2).float().double()
+    u[0, 0, 0] = 0.0; u[0, -1, -1] = 1.0
+    xp = O.phi_cos_sin_squared(u, 1.45646 / 2)
+    wantp = O.eps_4step(core, xp)
+    outp = E.eps_from_pixels(core.to(DEV, torch.float32), u.to(DEV, torch.float32), 1.45646)
+    assert rel_err(outp, wantp) <= 1e-5
+    assert (outp.double().cpu() - wantp).abs().max() <= 2e-5 * wantp.abs().max()
