@@ -40,6 +40,65 @@ def timeit(fn, flush, iters):
     return ts[len(ts) // 2]
 
 
+def steady_time(fns, rep=3):
+    """Device time per launch in steady state: `fns` are the same call on ROTATING buffer sets (together larger than the
+    126 MB L2, so every launch reads its input from HBM and its output is written back while the next ones run), all
+    captured in one CUDA graph (no host latency between launches), CUDA events around a replay.  A single launch between
+    two events is quantised to 1.024 us and carries ~5.7 us of fixed cost on these boxes (a 50 MB device copy reads
+    14.3 us that way, 9.7 us this way), which is most of a 10 us kernel."""
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for f in fns:
+            f()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(rep):
+                for f in fns:
+                    f()
+    torch.cuda.synchronize()
+    g.replay(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(7):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); g.replay(); b.record(); b.synchronize(); ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2] / (rep * len(fns))
+
+
+def steady_rows(core, x, gout, K, Q, O, B):
+    """forward / core gradient / input gradient of one layer through the C ABI on rotating buffers (ms per call)"""
+    lib = _lib.lib()
+    nbytes = 4 * (2 * x.numel() + gout.numel())
+    nset = max(3, int(400e6 // nbytes) + 1)
+    xs = [torch.randn_like(x) for _ in range(nset)]
+    gs = [torch.randn_like(gout) for _ in range(nset)]
+    outs = [torch.empty_like(gout) for _ in range(nset)]
+    dxs = [torch.empty_like(x) for _ in range(nset)]
+    dcore = torch.empty_like(core)
+    from dctn_b200.eps import _plan
+    plan = _plan(1, K, Q, O, torch.float32, _lib.VARIANTS["auto"])
+    wsb = max(lib.dctn_eps_workspace_bytes(plan, B, 28, 28, k) for k in (_lib.WS_FORWARD, _lib.WS_BACKWARD_CORE, _lib.WS_BACKWARD_INPUT))
+    ws = torch.empty(max(wsb, 256), dtype=torch.uint8, device=x.device)
+
+    def stream():
+        return torch.cuda.current_stream().cuda_stream
+
+    def f_fwd(xi, oi):
+        assert lib.dctn_eps_forward(plan, xi.data_ptr(), core.data_ptr(), oi.data_ptr(), B, 28, 28, ws.data_ptr(), ws.numel(), stream()) == 0
+
+    def f_dcore(xi, gi):
+        assert lib.dctn_eps_backward_core(plan, xi.data_ptr(), gi.data_ptr(), dcore.data_ptr(), B, 28, 28, ws.data_ptr(), ws.numel(), stream()) == 0
+
+    def f_dx(xi, gi, di):
+        assert lib.dctn_eps_backward_input(plan, xi.data_ptr(), core.data_ptr(), gi.data_ptr(), di.data_ptr(), B, 28, 28, ws.data_ptr(), ws.numel(), stream()) == 0
+
+    t_f = steady_time([lambda a=a, b=b: f_fwd(a, b) for a, b in zip(xs, outs)])
+    t_c = steady_time([lambda a=a, b=b: f_dcore(a, b) for a, b in zip(xs, gs)])
+    t_x = steady_time([lambda a=a, b=b, c=c: f_dx(a, b, c) for a, b, c in zip(xs, gs, dxs)])
+    return t_f, t_c, t_x
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=4096)
@@ -90,6 +149,18 @@ def main():
                            fwd_frac_hbm=fbytes / t_f / 1e6 / hbm, fwd_frac_bf16=flops / t_f / 1e9 / bf16,
                            imgs_per_s_fwdbwd=B / t_fb * 1e3, patches_per_s_fwdbwd=P / t_fb * 1e3,
                            plan=plan_description(core, x))
+                if K == 2 and D * O <= 4096 and core.dtype == torch.float32:
+                    # HBM- / CUDA-core-bound rows: microsecond kernels, timed in steady state on rotating buffers
+                    s_f, s_c, s_x = steady_rows(core.detach(), x.detach(), gout, K, Q, O, B)
+                    cbytes = 4.0 * (x.numel() + out.numel() + core.numel())
+                    xbytes = 4.0 * (2 * x.numel() + out.numel() + core.numel())
+                    row.update(steady=dict(fwd_ms=s_f, fwd_gbs=fbytes / s_f / 1e6, fwd_frac_hbm=fbytes / s_f / 1e6 / hbm,
+                                           dcore_ms=s_c, dcore_gbs=cbytes / s_c / 1e6, dcore_frac_hbm=cbytes / s_c / 1e6 / hbm,
+                                           dx_ms=s_x, dx_gbs=xbytes / s_x / 1e6, dx_frac_hbm=xbytes / s_x / 1e6 / hbm,
+                                           method="rotating buffers > L2, one CUDA graph per round, events around a replay"))
+                    print(f"K={K} Q={Q} O={O} B={B}: steady state  fwd {s_f * 1e3:6.1f} us ({fbytes / s_f / 1e6 / hbm * 100:4.1f} % HBM)  "
+                          f"core grad {s_c * 1e3:6.1f} us ({cbytes / s_c / 1e6 / hbm * 100:4.1f} %)  input grad {s_x * 1e3:6.1f} us "
+                          f"({xbytes / s_x / 1e6 / hbm * 100:4.1f} %)", flush=True)
                 if K == 2 and Q == 2:
                     # feature map fused into the forward (raw pixels in): 1 float per pixel instead of 2 crosses HBM
                     u = torch.rand(B, 28, 28, device=dev)

@@ -1026,6 +1026,8 @@ size_t direct_workspace_bytes(const EpsGeom& g, int dtype, int kind) {
 #if DCTN_DIRECT_PART == 3 || DCTN_DIRECT_PART == 4
 template <typename T>
 int direct_backward(const EpsGeom& g, int kind, const T* x, const T* core, const T* gout, T* result, void* ws, cudaStream_t st) {
+  if constexpr (std::is_same<T, float>::value)
+    if (stream_k2q2_enabled() && stream_k2q2_bwd_supported(g, 0, kind)) return stream_k2q2_backward(g, kind, x, core, gout, result, ws, st);
 #define DCTN_DIRECT_CASE(q, ma, mb) \
   if (g.Q == q && g.m == ma && g.n - g.m == mb) return launch_direct_bwd<T, q, ma, mb>(g, kind, x, core, gout, result, ws, st);
   DCTN_DIRECT_CASE(2, 2, 2) DCTN_DIRECT_CASE(3, 2, 2) DCTN_DIRECT_CASE(4, 2, 2) DCTN_DIRECT_CASE(5, 2, 2)

@@ -28,6 +28,8 @@ template <typename T> int direct_forward_pixels(const EpsGeom& g, const T* pixel
 bool stream_k2q2_supported(const EpsGeom& g, int dtype);
 bool stream_k2q2_enabled();   // DCTN_B200_STREAM=0 falls back to the generic small-core kernels (A/B measurements)
 int stream_k2q2_forward(const EpsGeom& g, const float* x, const float* core, float* out, cudaStream_t st);
+bool stream_k2q2_bwd_supported(const EpsGeom& g, int dtype, int kind);
+int stream_k2q2_backward(const EpsGeom& g, int kind, const float* x, const float* core, const float* gout, float* result, void* ws, cudaStream_t st);
 int stream_k2q2_forward_pixels(const EpsGeom& g, const float* pixels, float scale, const float* core, float* out, cudaStream_t st);
 bool direct_bwd_supported(const EpsGeom& g, int dtype, int kind);
 size_t direct_workspace_bytes(const EpsGeom& g, int dtype, int kind);

@@ -218,8 +218,7 @@ int launch_stream_fwd(const EpsGeom& g, const float* x, const float* core, float
     grid.y = (unsigned)g.B / z; grid.z = z;
     if (grid.y > 65535 || grid.z > 65535) return dctn_set_error(-2, "streaming forward: batch %d does not fit the grid", g.B);
   }
-  static const int pf_env = [] { const char* e = getenv("DCTN_B200_STREAM_PF"); return e ? atoi(e) : 1024; }();
-  const unsigned pf_dist = (unsigned)pf_env;
+  const unsigned pf_dist = 1024;   // images ahead (~ the resident CTAs of the whole GPU); 0 / 2048 / 4096 measured within 4 %
   stream_k2q2_fwd_kernel<OP, RH, PIX><<<grid, 32 * wpc, 0, st>>>(x, core, out, g.H, g.W, g.O, nhb, tpi, pf_dist, scale);
   dctn_count_launch();
   DCTN_CUDA_CHECK_RET(cudaGetLastError());
@@ -230,9 +229,8 @@ int launch_stream_fwd(const EpsGeom& g, const float* x, const float* core, float
 // 9 rows) and still fits the registers for one or two output pairs; three and four pairs take 4 rows
 template <bool PIX>
 int dispatch_stream_fwd(const EpsGeom& g, const float* x, const float* core, float* out, float scale, cudaStream_t st) {
-  static const int rh_env = [] { const char* e = getenv("DCTN_B200_STREAM_RH"); return e ? atoi(e) : 0; }();
   const int op = (g.O + 1) / 2;
-  const bool tall = rh_env ? rh_env > 4 : (g.Ho % 9 == 0 || g.Ho >= 45);
+  const bool tall = g.Ho % 9 == 0 || g.Ho >= 45;
   switch (op) {
     case 1: return tall ? launch_stream_fwd<1, 9, PIX>(g, x, core, out, scale, st) : launch_stream_fwd<1, 4, PIX>(g, x, core, out, scale, st);
     case 2: return tall ? launch_stream_fwd<2, 9, PIX>(g, x, core, out, scale, st) : launch_stream_fwd<2, 4, PIX>(g, x, core, out, scale, st);
@@ -240,6 +238,321 @@ int dispatch_stream_fwd(const EpsGeom& g, const float* x, const float* core, flo
     case 4: return launch_stream_fwd<4, 4, PIX>(g, x, core, out, scale, st);
     default: return dctn_set_error(-2, "streaming forward: Q_out = %d not instantiated", g.O);
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Core gradient: dcore[a][b][o] = sum_p pp_top[p][a] * pp_bot[p][b] * gout[p][o]  (49.6 MB in at B = 4096, Q_out = 2, 128
+// bytes out).  Same warp-row structure as the forward (lane = column, RH rows, pair products shared between vertically
+// adjacent patches); persistent warps keep a PRIVATE copy of dcore in registers as pairs over o — per patch and output pair
+// 4 FMUL2 (u[b] = pp_bot[b] * g) + 16 FFMA2 (acc[a][b] += pp_top[a] * u[b]) — and reduce it once at the end: shuffles within
+// the warp, shared memory across the CTA's warps, one partial per CTA, summed in fixed order by stream_reduce_kernel.
+template <int OT, int RH>
+__global__ void __launch_bounds__(SK_THREADS) stream_k2q2_dcore_kernel(const float* __restrict__ x, const float* __restrict__ gout,
+                                                                        float* __restrict__ part, int H, int W,
+                                                                        unsigned nhb, unsigned ntw, unsigned nimg, unsigned pf_tasks) {
+  constexpr int OP = (OT + 1) / 2;
+  constexpr int O = OT;
+  __shared__ float red[SK_THREADS / 32][32 * OP];
+  __shared__ float red_t[(SK_THREADS / 32) * 32 * OP * 33];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned Ho = H - 1, Wo = W - 1, tpi = nhb * ntw, uO = (unsigned)O;
+  f32x2_t acc[16][OP];
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+#pragma unroll
+    for (int op = 0; op < OP; ++op) acc[i][op] = pack2(0.f, 0.f);
+  // task t = image * tpi + tl; this warp walks t = t0, t0 + NWT, ...: (image, tl) advance by the quotient / remainder of
+  // NWT / tpi with one carry — no division in the loop
+  const unsigned nwt = gridDim.x * (SK_THREADS / 32), t0 = blockIdx.x * (SK_THREADS / 32) + warp;
+  const unsigned dimg = nwt / tpi, dtl = nwt - dimg * tpi;
+  unsigned b = t0 / tpi, tl = t0 - b * tpi;
+  const unsigned xbytes = (unsigned)H * (unsigned)W * 8u, gbytes = Ho * Wo * uO * 4u;
+  for (; b < nimg; b += dimg, tl += dtl) {
+    if (tl >= tpi) { tl -= tpi; if (++b >= nimg) break; }
+    unsigned hb = tl, tw = 0;
+    if (ntw != 1) { tw = tl / nhb; hb = tl - tw * nhb; }
+    const unsigned h0 = hb * RH, wcol = tw * 31 + lane;
+    const unsigned wc = wcol < (unsigned)W ? wcol : (unsigned)W - 1u;
+    const float2* px = reinterpret_cast<const float2*>(x) + (size_t)((b * (unsigned)H + h0) * (unsigned)W + wc);
+    const bool full = h0 + RH <= Ho;
+    float xv[RH + 1][2];
+    const bool colok = lane < 31 && wcol < Wo;
+    const float* pg = gout + (size_t)((b * Ho + h0) * Wo + (colok ? wcol : 0u)) * uO;
+    float gv[RH][2 * OP];
+    if (full) {
+#pragma unroll
+      for (int r = 0; r <= RH; ++r) {
+        const float2 v = __ldg(px + (unsigned)r * (unsigned)W);
+        xv[r][0] = v.x; xv[r][1] = v.y;
+      }
+#pragma unroll
+      for (int r = 0; r < RH; ++r) {
+        const float* q = pg + (unsigned)r * Wo * uO;
+        if constexpr (O % 2 == 0) {
+#pragma unroll
+          for (int o = 0; o < O; o += 2) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(q + o));
+            gv[r][o] = v.x; gv[r][o + 1] = v.y;
+          }
+        } else {
+#pragma unroll
+          for (int o = 0; o < 2 * OP; ++o) gv[r][o] = o < O ? __ldg(q + o) : 0.f;
+        }
+      }
+    } else {
+      const unsigned rows_in = (unsigned)H - h0;
+#pragma unroll
+      for (int r = 0; r <= RH; ++r) {
+        const float2 v = __ldg(px + ((unsigned)r < rows_in ? (unsigned)r * (unsigned)W : 0u));
+        xv[r][0] = v.x; xv[r][1] = v.y;
+      }
+#pragma unroll
+      for (int r = 0; r < RH; ++r) {
+        const bool rok = h0 + r < Ho;
+        const float* q = pg + (rok ? (unsigned)r * Wo * uO : 0u);
+#pragma unroll
+        for (int o = 0; o < 2 * OP; ++o) gv[r][o] = (o < O && rok) ? __ldg(q + (o < O ? o : 0)) : 0.f;
+      }
+    }
+    if (pf_tasks) {
+      // L2 prefetch for the task this warp runs `pf_tasks` iterations from now: the tpi tasks of an image cover its x and
+      // gout (two contiguous runs) with one 128-byte line per lane and pass
+      unsigned bp = b + pf_tasks * dimg, tlp = tl + pf_tasks * dtl;
+      while (tlp >= tpi) { tlp -= tpi; ++bp; }
+      if (bp < nimg) {
+        const char* xb = reinterpret_cast<const char*>(x) + (size_t)bp * xbytes;
+        const char* gb = reinterpret_cast<const char*>(gout) + (size_t)bp * gbytes;
+        for (unsigned off = (tlp * 32 + lane) * 128u; off < xbytes + gbytes; off += tpi * 32 * 128u) {
+          const char* ptr = off < xbytes ? xb + off : gb + (off - xbytes);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+        }
+      }
+    }
+    f32x2_t pp[RH + 1][4];
+#pragma unroll
+    for (int r = 0; r <= RH; ++r) {
+      const float r0 = __shfl_down_sync(0xffffffffu, xv[r][0], 1), r1 = __shfl_down_sync(0xffffffffu, xv[r][1], 1);
+      const float p00 = xv[r][0] * r0, p01 = xv[r][0] * r1, p10 = xv[r][1] * r0, p11 = xv[r][1] * r1;
+      pp[r][0] = pack2(p00, p00); pp[r][1] = pack2(p01, p01); pp[r][2] = pack2(p10, p10); pp[r][3] = pack2(p11, p11);
+    }
+#pragma unroll
+    for (int r = 0; r < RH; ++r) {
+#pragma unroll
+      for (int op = 0; op < OP; ++op) {
+        // patches outside the image (halo lane, columns past the row) contribute zero
+        const f32x2_t g2 = colok ? pack2(gv[r][2 * op], gv[r][2 * op + 1]) : pack2(0.f, 0.f);
+        f32x2_t u[4];
+#pragma unroll
+        for (int bq = 0; bq < 4; ++bq) u[bq] = mul2(pp[r + 1][bq], g2);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int bq = 0; bq < 4; ++bq) acc[a * 4 + bq][op] = fma2(pp[r][a], u[bq], acc[a * 4 + bq][op]);
+      }
+    }
+  }
+  // reduction through shared memory (a shuffle tree behind this loop costs ~1300 instructions per warp — every SHFL sits
+  // in a WARPSYNC / ENDCOLLECTIVE pair — a third of the whole kernel): lane l of every warp adds up value l of its warp's 32
+  // lanes (row stride 33: conflict-free both ways), then the CTA's warps are summed, all in fixed order
+  float* tr = red_t + warp * (32 * OP * 33);
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+#pragma unroll
+    for (int op = 0; op < OP; ++op) {
+      const float2 v = unpack2(acc[i][op]);
+      tr[((i * OP + op) * 2) * 33 + lane] = v.x;
+      tr[((i * OP + op) * 2 + 1) * 33 + lane] = v.y;
+    }
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < OP; ++h) {
+    const float* row = tr + (h * 32 + lane) * 33;
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v += row[k];
+    red[warp][h * 32 + lane] = v;
+  }
+  __syncthreads();
+  for (unsigned idx = threadIdx.x; idx < 16u * uO; idx += SK_THREADS) {
+    const unsigned ab = idx / uO, o = idx - ab * uO;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < SK_THREADS / 32; ++w) v += red[w][(ab * OP + (o >> 1)) * 2 + (o & 1)];
+    part[(size_t)blockIdx.x * 16u * uO + idx] = v;
+  }
+}
+
+// out[i] = sum_z part[z * count + i], z in fixed order: 32 outputs x 32 slices of z per CTA
+__global__ void __launch_bounds__(1024) stream_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int count, int splits) {
+  __shared__ float red[32][33];
+  const int il = threadIdx.x & 31, zs = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + il;
+  float v = 0.f;
+  if (i < count)
+    for (int z = zs; z < splits; z += 32) v += part[(size_t)z * count + i];
+  red[zs][il] = v;
+  __syncthreads();
+  if (zs == 0 && i < count) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += red[k][il];
+    out[i] = t;
+  }
+}
+
+template <int OT, int RH>
+int launch_stream_dcore(const EpsGeom& g, const float* x, const float* gout, float* dcore, float* part, cudaStream_t st) {
+  constexpr int OP = (OT + 1) / 2;
+  const unsigned nhb = (unsigned)(g.Ho + RH - 1) / RH, ntw = (unsigned)(g.Wo + 30) / 31;
+  const long long ntask = (long long)g.B * nhb * ntw;
+  if (ntask >= (1ll << 31)) return dctn_set_error(-2, "streaming core gradient: too many tasks");
+  long long blocks = (ntask + SK_THREADS / 32 - 1) / (SK_THREADS / 32);
+  const long long cap = 148ll * (OP == 1 ? (RH > 4 ? 4 : 5) : 3);   // resident CTAs per SM at this kernel's register count
+  if (blocks > cap) blocks = cap;
+  stream_k2q2_dcore_kernel<OT, RH><<<(unsigned)blocks, SK_THREADS, 0, st>>>(x, gout, part, g.H, g.W, nhb, ntw, (unsigned)g.B, 1u);
+  dctn_count_launch();
+  DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  const int count = 16 * g.O;
+  stream_reduce_kernel<<<(count + 31) / 32, 1024, 0, st>>>(part, dcore, count, (int)blocks);
+  dctn_count_launch();
+  DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Input gradient (x 25.7 MB + gout 23.9 MB in, dx 25.7 MB out at B = 4096, Q_out = 2).  One warp = RH pixel rows x 30 pixel
+// columns of dx; lane l owns pixel column w0 - 1 + l and the patch whose top-left pixel that is, lanes 0 and 31 are halos.
+// The warp walks down its RH + 1 patch rows; per patch
+//     M[a][b] = sum_o core[a][b][o] g[o]         (pairs over b: 8 Q_out FFMA2, core broadcast from shared memory)
+//     dB[b]   = sum_a M[a][b] pp_top[a]           dA[a] = sum_b M[a][b] pp_bot[b]
+//     d x1 = dA . x2,  d x2 = dA . x1,  d x3 = dB . x4,  d x4 = dB . x3      (the leave-one-out products of each pair)
+// and a pixel's gradient is the sum over its <= 4 patches: two of them are this lane's own (this patch row and the one
+// above), the other two come from the lane to the left by one shuffle — every pixel is written once, no atomics, no
+// per-patch intermediate in HBM.  The patch row above the block and the left halo column are recomputed by the neighbours.
+template <int OT, int RH>
+__global__ void __launch_bounds__(SK_THREADS) stream_k2q2_dx_kernel(const float* __restrict__ x, const float* __restrict__ core,
+                                                                     const float* __restrict__ gout, float* __restrict__ dx,
+                                                                     int H, int W, unsigned nqb, unsigned tpi) {
+  __shared__ __align__(16) float2 cs[OT * 4 * 2];   // [o][a][b pair]
+  const int lane = threadIdx.x & 31;
+  const unsigned tl = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const bool live = tl < tpi;
+  const unsigned tk = live ? tl : 0u;
+  unsigned qb = tk, tw = 0;
+  if (tpi != nqb) { tw = tk / nqb; qb = tk - tw * nqb; }
+  const unsigned b = blockIdx.z * gridDim.y + blockIdx.y;
+  const int Ho = H - 1, Wo = W - 1;
+  const int q0 = (int)(qb * RH), wl = (int)(tw * 30) - 1 + lane;         // first pixel row of the block, this lane's column
+  const bool colx = wl >= 0 && wl < W, colp = wl >= 0 && wl < Wo;
+  // x rows q0 - 1 .. q0 + RH (zeros outside the image), gout rows q0 - 1 .. q0 + RH - 1 (zeros outside)
+  float xv[RH + 2][2];
+  const float2* px = reinterpret_cast<const float2*>(x) + ((size_t)b * H * W + (colx ? wl : 0));
+#pragma unroll
+  for (int i = 0; i <= RH + 1; ++i) {
+    const int row = q0 - 1 + i;
+    float2 v = make_float2(0.f, 0.f);
+    if (colx && row >= 0 && row < H) v = __ldg(px + row * W);
+    xv[i][0] = v.x; xv[i][1] = v.y;
+  }
+  float gv[RH + 1][OT];
+  const float* pg = gout + ((size_t)b * Ho * Wo + (colp ? wl : 0)) * OT;
+#pragma unroll
+  for (int j = 0; j <= RH; ++j) {
+    const int pr = q0 - 1 + j;
+    const bool ok = colp && pr >= 0 && pr < Ho;
+    const float* q = pg + (ok ? pr * Wo * OT : 0);
+    if constexpr (OT % 2 == 0) {
+#pragma unroll
+      for (int o = 0; o < OT; o += 2) {
+        const float2 v = ok ? __ldg(reinterpret_cast<const float2*>(q + o)) : make_float2(0.f, 0.f);
+        gv[j][o] = v.x; gv[j][o + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int o = 0; o < OT; ++o) gv[j][o] = ok ? __ldg(q + o) : 0.f;
+    }
+  }
+  for (int idx = threadIdx.x; idx < OT * 8; idx += blockDim.x) {
+    const int bp = idx & 1, a = (idx >> 1) & 3, o = idx >> 3;
+    cs[idx] = make_float2(__ldg(core + (a * 4 + 2 * bp) * OT + o), __ldg(core + (a * 4 + 2 * bp + 1) * OT + o));
+  }
+  // right neighbours
+  float xr[RH + 2][2];
+#pragma unroll
+  for (int i = 0; i <= RH + 1; ++i) {
+    xr[i][0] = __shfl_down_sync(0xffffffffu, xv[i][0], 1);
+    xr[i][1] = __shfl_down_sync(0xffffffffu, xv[i][1], 1);
+  }
+  __syncthreads();
+  float own[2] = {0.f, 0.f}, tor[2] = {0.f, 0.f};     // running sums of the pixel row being completed: own column / for lane + 1
+  float* pd = dx + ((size_t)b * H * W + (colx ? wl : 0)) * 2;
+  const bool store = live && lane >= 1 && lane <= 30 && colx;
+#pragma unroll
+  for (int j = 0; j <= RH; ++j) {
+    // patch row j: top pixels = x row j, bottom pixels = x row j + 1
+    const float t00 = xv[j][0] * xr[j][0], t01 = xv[j][0] * xr[j][1], t10 = xv[j][1] * xr[j][0], t11 = xv[j][1] * xr[j][1];
+    const float b00 = xv[j + 1][0] * xr[j + 1][0], b01 = xv[j + 1][0] * xr[j + 1][1];
+    const float b10 = xv[j + 1][1] * xr[j + 1][0], b11 = xv[j + 1][1] * xr[j + 1][1];
+    const f32x2_t tdup[4] = {pack2(t00, t00), pack2(t01, t01), pack2(t10, t10), pack2(t11, t11)};
+    const f32x2_t bot[2] = {pack2(b00, b01), pack2(b10, b11)};
+    f32x2_t M[4][2];
+#pragma unroll
+    for (int o = 0; o < OT; ++o) {
+      const f32x2_t gd = pack2(gv[j][o], gv[j][o]);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const ulonglong2 c = *reinterpret_cast<const ulonglong2*>(cs + (o * 4 + a) * 2);
+        M[a][0] = (o == 0) ? mul2(c.x, gd) : fma2(c.x, gd, M[a][0]);
+        M[a][1] = (o == 0) ? mul2(c.y, gd) : fma2(c.y, gd, M[a][1]);
+      }
+    }
+    f32x2_t dB2[2];
+    float dA[4];
+#pragma unroll
+    for (int bp = 0; bp < 2; ++bp) {
+      dB2[bp] = mul2(M[0][bp], tdup[0]);
+#pragma unroll
+      for (int a = 1; a < 4; ++a) dB2[bp] = fma2(M[a][bp], tdup[a], dB2[bp]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const float2 v = unpack2(fma2(M[a][1], bot[1], mul2(M[a][0], bot[0])));
+      dA[a] = v.x + v.y;
+    }
+    const float2 dB01 = unpack2(dB2[0]), dB23 = unpack2(dB2[1]);
+    // pixel row j (x1: own column, x2: lane + 1) is complete after this patch row
+    own[0] += dA[0] * xr[j][0] + dA[1] * xr[j][1];
+    own[1] += dA[2] * xr[j][0] + dA[3] * xr[j][1];
+    tor[0] += dA[0] * xv[j][0] + dA[2] * xv[j][1];
+    tor[1] += dA[1] * xv[j][0] + dA[3] * xv[j][1];
+    const float left0 = __shfl_up_sync(0xffffffffu, tor[0], 1), left1 = __shfl_up_sync(0xffffffffu, tor[1], 1);
+    const int row = q0 - 1 + j;
+    if (j >= 1 && store && row < H) *reinterpret_cast<float2*>(pd + (size_t)row * W * 2) = make_float2(own[0] + left0, own[1] + left1);
+    // pixel row j + 1 (x3: own column, x4: lane + 1) starts with this patch row's contribution
+    own[0] = dB01.x * xr[j + 1][0] + dB01.y * xr[j + 1][1];
+    own[1] = dB23.x * xr[j + 1][0] + dB23.y * xr[j + 1][1];
+    tor[0] = dB01.x * xv[j + 1][0] + dB23.x * xv[j + 1][1];
+    tor[1] = dB01.y * xv[j + 1][0] + dB23.y * xv[j + 1][1];
+  }
+}
+
+template <int OT>
+int launch_stream_dx(const EpsGeom& g, const float* x, const float* core, const float* gout, float* dx, cudaStream_t st) {
+  constexpr int RH = 7;
+  const unsigned nqb = (unsigned)(g.H + RH - 1) / RH, ntw = (unsigned)(g.W + 29) / 30;
+  const unsigned tpi = nqb * ntw;
+  const unsigned wpc = tpi < 4 ? tpi : 4;
+  dim3 grid((tpi + wpc - 1) / wpc, (unsigned)g.B, 1);
+  if (g.B > 65535) {
+    unsigned z = (unsigned)((g.B + 65534) / 65535);
+    while (g.B % z) ++z;
+    grid.y = (unsigned)g.B / z; grid.z = z;
+    if (grid.y > 65535 || grid.z > 65535) return dctn_set_error(-2, "streaming input gradient: batch %d does not fit the grid", g.B);
+  }
+  stream_k2q2_dx_kernel<OT, RH><<<grid, 32 * wpc, 0, st>>>(x, core, gout, dx, g.H, g.W, nqb, tpi);
+  dctn_count_launch();
+  DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  return 0;
 }
 
 }  // namespace
@@ -257,4 +570,32 @@ int stream_k2q2_forward(const EpsGeom& g, const float* x, const float* core, flo
 }
 int stream_k2q2_forward_pixels(const EpsGeom& g, const float* pixels, float scale, const float* core, float* out, cudaStream_t st) {
   return dispatch_stream_fwd<true>(g, pixels, core, out, scale, st);
+}
+
+// kind 1: core gradient (Q_out <= 4: the private copy of dcore must fit the registers), kind 2: input gradient (Q_out <= 6)
+bool stream_k2q2_bwd_supported(const EpsGeom& g, int dtype, int kind) {
+  if (!stream_k2q2_supported(g, dtype)) return false;
+  return kind == 1 ? g.O <= 4 : g.O <= 6;
+}
+int stream_k2q2_backward(const EpsGeom& g, int kind, const float* x, const float* core, const float* gout, float* result, void* ws,
+                         cudaStream_t st) {
+  if (kind == 1) {
+    const bool tall = g.Ho % 9 == 0;     // 9-row tasks: 15.1 us against 17.2 us with 4-row tasks (B = 4096, 28 x 28, Q_out = 2)
+    float* part = (float*)ws;
+    switch (g.O) {
+      case 1: return tall ? launch_stream_dcore<1, 9>(g, x, gout, result, part, st) : launch_stream_dcore<1, 4>(g, x, gout, result, part, st);
+      case 2: return tall ? launch_stream_dcore<2, 9>(g, x, gout, result, part, st) : launch_stream_dcore<2, 4>(g, x, gout, result, part, st);
+      case 3: return launch_stream_dcore<3, 4>(g, x, gout, result, part, st);
+      default: return launch_stream_dcore<4, 4>(g, x, gout, result, part, st);
+    }
+  }
+  switch (g.O) {
+    case 1: return launch_stream_dx<1>(g, x, core, gout, result, st);
+    case 2: return launch_stream_dx<2>(g, x, core, gout, result, st);
+    case 3: return launch_stream_dx<3>(g, x, core, gout, result, st);
+    case 4: return launch_stream_dx<4>(g, x, core, gout, result, st);
+    case 5: return launch_stream_dx<5>(g, x, core, gout, result, st);
+    case 6: return launch_stream_dx<6>(g, x, core, gout, result, st);
+    default: return dctn_set_error(-2, "streaming input gradient: Q_out = %d not instantiated", g.O);
+  }
 }

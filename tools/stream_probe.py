@@ -47,6 +47,23 @@ for Oq in ([2, 6] if once else [2, 3, 4, 5, 6]):
         for f in (lambda: E.eps(core, xs[0]), lambda: E.eps_from_pixels(core, us[0], 1.45646), lambda: E.eps(c, x).backward(gout)):
             flush.zero_(); f()
         torch.cuda.synchronize(); continue
+    from dctn_b200 import _lib
+    lib = _lib.lib()
+    plan = E._plan(1, 2, 2, Oq, torch.float32, _lib.VARIANTS["auto"])
+    gouts = [torch.randn_like(out) for _ in range(NSET)]
+    dcore = torch.empty_like(core); dxs = [torch.empty_like(x) for x in xs]
+    wsb = max(lib.dctn_eps_workspace_bytes(plan, B, 28, 28, k) for k in (_lib.WS_BACKWARD_CORE, _lib.WS_BACKWARD_INPUT))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    def f_dcore(x, g):
+        st = torch.cuda.current_stream().cuda_stream
+        assert lib.dctn_eps_backward_core(plan, x.data_ptr(), g.data_ptr(), dcore.data_ptr(), B, 28, 28, ws.data_ptr(), ws.numel(), st) == 0
+    def f_dx(x, g, d):
+        st = torch.cuda.current_stream().cuda_stream
+        assert lib.dctn_eps_backward_input(plan, x.data_ptr(), core.data_ptr(), g.data_ptr(), d.data_ptr(), B, 28, 28, ws.data_ptr(), ws.numel(), st) == 0
+    tdc = graph_time([lambda x=x, g=g: f_dcore(x, g) for x, g in zip(xs, gouts)])
+    tdx = graph_time([lambda x=x, g=g, d=d: f_dx(x, g, d) for x, g, d in zip(xs, gouts, dxs)])
+    nbd = xs[0].numel() * 4 + out.numel() * 4; nbx = 2 * xs[0].numel() * 4 + out.numel() * 4
+    print(f"O={Oq}: core gradient {tdc:6.2f} us ({nbd / tdc / 1e3:6.0f} GB/s = {nbd / tdc / 1e3 / 65.466:4.1f} %)   input gradient {tdx:6.2f} us ({nbx / tdx / 1e3:6.0f} GB/s = {nbx / tdx / 1e3 / 65.466:4.1f} %)", flush=True)
     with torch.no_grad():
         tf = graph_time([lambda x=x: E.eps(core, x) for x in xs])
         tp = graph_time([lambda u=u: E.eps_from_pixels(core, u, 1.45646) for u in us])
