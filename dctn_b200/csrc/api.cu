@@ -115,6 +115,13 @@ extern "C" const dctn_plan_t* dctn_eps_plan_get(int C, int K, int Qin, int Qout,
         if (a1 >= 64 && b1 * Qout >= 64 && a1 <= 4096) { m = mm; break; }
       }
     }
+    // Four-factor layers (K = 2, one channel) whose Q_in is not a power of two run on the table-lookup GEMM kernels, where
+    // the forward epilogue (Q_in^(n-m) * Q_out columns per patch) and the saved intermediate T (as many floats per patch)
+    // dominate: three factors in the first half leave Q_in * Q_out columns instead of Q_in^2 * Q_out.  CIFAR (2, 12 -> 24)
+    // at B = 64: forward 0.87 -> 0.51 ms, core gradient 0.33 -> 0.27, input gradient 0.82 -> 1.03; T 796 -> 66 MB.
+    if (n == 4 && (Qin & (Qin - 1)) != 0 && pow_fits(Qin, 3, 4096, &a0) && pow_fits(Qin, n, LIM, &d0) && d0 >= 1024 && a0 >= 64 &&
+        (long long)Qin * Qout >= 64)
+      m = 3;
   }
   if (const char* e = getenv("DCTN_B200_SPLIT_M")) {
     const int mm = atoi(e);

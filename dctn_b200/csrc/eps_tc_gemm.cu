@@ -175,12 +175,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
   float* outs = tabE + nE * 128;                       // MODE_FWD: [O][128]
   // index tables that make the inner loops branch-free (every load address is known up front -> full ILP):
   //   kidx[k]  = kh | kl << 16 for the generated operand (k >= Kdim -> the all-zero row KH of tabKH)
-  //   eidx[..] = MODE_FWD: bh | bl << 16 for b in [0, 2*Bn) (doubled so 32 consecutive b never wrap the table);
+  //   eidx[..] = MODE_FWD: bh | bl << 16 for b2 in [0, Bn + max(Bn, 32)), b = b2 % Bn (32 consecutive b never leave the table);
   //              MODE_DKR2: o | last << 8 for the BN columns of a tile
   uint32_t* kidx = (uint32_t*)(outs + ((MODE == MODE_FWD) ? O * 128 : 0));
   const int nkidx = a.nk * KS;
   uint32_t* eidx = kidx + nkidx;
-  const int neidx = (MODE == MODE_FWD) ? 2 * g.Bn : (MODE == MODE_DKR2 ? ((BN + 31) & ~31) : 0);
+  const int neidx = (MODE == MODE_FWD) ? g.Bn + (g.Bn > 32 ? g.Bn : 32) : (MODE == MODE_DKR2 ? ((BN + 31) & ~31) : 0);
   // F16: power-of-two exponents of the per-patch normalisation: [0][pr] generated operand, [1][pr] epilogue factors
   int* rowexp = (int*)(eidx + ((neidx + 1) & ~1));
   uint64_t* bars = (uint64_t*)(rowexp + 256);
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
       kidx[k] = id;
     }
     if (MODE == MODE_FWD)
-      for (int b2 = tid; b2 < 2 * g.Bn; b2 += G_THREADS) {
+      for (int b2 = tid; b2 < neidx; b2 += G_THREADS) {
         const int b = b2 % g.Bn;
         eidx[b2] = (uint32_t)(b / g.BL) | ((uint32_t)(b % g.BL) << 16);
       }
@@ -580,17 +580,32 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
             const uint32_t id = bi[i];
             kr[i] = eH[(id & 0xFFFF) * 128] * eL[(id >> 16) * 128];
           }
-          float s2 = 0.f;
+          if (g.Bn >= 32) {
+            float s2 = 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float c = (i < nvalid) ? v[i] * kr[i] : 0.f;
-            if (i < wrap) s += c; else s2 += c;
-          }
-          if (wrap <= nvalid) {
-            outs[fo * 128 + pr] += s;
-            s = s2; ++fo; fb = fb + nvalid - g.Bn;
+            for (int i = 0; i < 32; ++i) {
+              const float c = (i < nvalid) ? v[i] * kr[i] : 0.f;
+              if (i < wrap) s += c; else s2 += c;
+            }
+            if (wrap <= nvalid) {
+              outs[fo * 128 + pr] += s;
+              s = s2; ++fo; fb = fb + nvalid - g.Bn;
+            } else {
+              fb += nvalid;
+            }
           } else {
-            fb += nvalid;
+            // narrow second half (lopsided split, e.g. one factor: Bn = Q_in): several outputs per batch of 32 columns;
+            // the run boundaries are warp-uniform
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (i < nvalid) {
+                s = fmaf(v[i], kr[i], s);
+                if (++fb == g.Bn) {
+                  outs[fo * 128 + pr] += s;
+                  s = 0.f; fb = 0; ++fo;
+                }
+              }
+            }
           }
         } else {  // MODE_DKR2
           const uint4* cp = (const uint4*)(eidx + cb);
@@ -665,7 +680,7 @@ inline size_t gemm_fixed_smem(const EpsGeom& g, const GemmShape& s, int mode) {
   const int nE = (mode == MODE_FWD) ? (g.BH + g.BL) : (mode == MODE_DKR2 ? g.O : 0);
   const size_t ktab = s.three ? (size_t)(s.KH + 1 + s.KLb + g.O) : (size_t)(s.KH + 1 + s.KL);
   const size_t nkidx = (size_t)((s.Kdim + GBK16 - 1) / GBK16) * GBK16;
-  const size_t neidx = (mode == MODE_FWD) ? 2 * (size_t)g.Bn : (mode == MODE_DKR2 ? (size_t)MAX_BN : 0);
+  const size_t neidx = (mode == MODE_FWD) ? (size_t)g.Bn + (g.Bn > 32 ? g.Bn : 32) : (mode == MODE_DKR2 ? (size_t)MAX_BN : 0);
   return 1024 + (ktab + nE + (mode == MODE_FWD ? g.O : 0)) * 128 * 4 + (nkidx + neidx + 2) * 4 + 256 * 4 +
          (2 * MAX_BSTAGES + 2 * ASTAGES + 2) * 8 + 16;
 }
@@ -852,9 +867,9 @@ static bool use_fast(const EpsGeom& g, int fmode, int passes) {
 
 bool tcg_supported(const EpsGeom& g, int kind) {
   if (!common_ok(g)) return false;
-  if (kind == 0) return g.Bn >= 32 && pick_bn(g, MODE_FWD) != 0;
+  if (kind == 0) return pick_bn(g, MODE_FWD) != 0;
   if (kind == 2) return (g.n - g.m) > 0 && pick_bn(g, MODE_STORE) != 0 && pick_bn(g, MODE_DKR2) != 0;
-  if (kind == 3) return (g.n - g.m) > 0 && g.Bn >= 32 && pick_bn(g, MODE_FWD) != 0 && pick_bn(g, MODE_STORE) != 0;
+  if (kind == 3) return (g.n - g.m) > 0 && pick_bn(g, MODE_FWD) != 0 && pick_bn(g, MODE_STORE) != 0;
   return false;
 }
 

@@ -12,7 +12,7 @@ from dctn_b200 import _lib  # noqa: E402
 from dctn_b200 import eps as E  # noqa: E402
 
 LAYERS = {  # name: (H, Q, K, O)
-    "L1": (28, 2, 4, 4), "L2": (25, 4, 3, 6), "cfg1": (28, 2, 2, 2), "c23": (31, 23, 2, 24), "c6": (31, 6, 2, 24),
+    "L1": (28, 2, 4, 4), "L2": (25, 4, 3, 6), "cfg1": (28, 2, 2, 2), "c23": (31, 23, 2, 24), "c12": (31, 12, 2, 24), "c6": (31, 6, 2, 24),
     "k3q3": (28, 3, 3, 6), "k2q4": (28, 4, 2, 6), "k3q2": (28, 2, 3, 6), "k2q2o6": (28, 2, 2, 6), "k2q3": (28, 3, 2, 6),
 }
 KINDS = {"fwd": _lib.WS_FORWARD, "core": _lib.WS_BACKWARD_CORE, "input": _lib.WS_BACKWARD_INPUT}
