@@ -500,16 +500,17 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e = t.tolist()
 
+    if use_graph:    # replays launch no kernels from the host: count the kernels of ONE eager step of the same model
+        l1 = _lib.launch_count()      # (every rank runs it: the eager step contains the gradient all-reduce)
+        step._eager(*resident[0])
+        torch.cuda.synchronize()
+        launches = (_lib.launch_count() - l1) * args.steps
+
     if rank == 0:
         dims = layer_dims(specs, image_size, Q0, batch)
         imgs = batch * world * args.steps
         value = imgs / (ms_total / 1e3)
         hx, hy = host[0]
-        if use_graph:    # replays launch no kernels from the host: count the kernels of ONE eager step of the same model
-            l1 = _lib.launch_count()
-            step._eager(*resident[0])
-            torch.cuda.synchronize()
-            launches = (_lib.launch_count() - l1) * args.steps
         config = workload_config(args.workload, batch, world, STEP_DESC)
         run_info = {"variant": os.environ.get("DCTN_B200_VARIANT", "auto"), "cuda_graph": use_graph,
                     "grad_allreduce": ("overlapped, %d-CTA communicator" % args.comm_ctas) if (world > 1 and args.overlap) else "one flat bucket after backward",

@@ -65,8 +65,9 @@ struct TcGemmArgs {
   const float* gout;
   long long p0;  // first patch handled by this launch
   int np;        // number of patches
-  int jh0, cnth, KH, cntl, KLb, KL, Kdim, withG;  // generated operand (see GenGemmArgs in eps_ffma.cu)
-  int three;            // withG only: 1 = three-level product tabKH * tabKL(lo group alone) * gout instead of the folded table
+  // generated operand (struct GemmShape below): nf factors from jh0 (times gout if withG); value(h, r) =
+  // tabKH[kh(h)] * tabKL[kl(h)] * tabR[r] with K ordered [r / RB][h][r % RB] (padded: h to Hpad, r to GP)
+  int jh0, nf, withG, cnth, KH, cntl, KLb, cr, G, GP, RB, H, Hpad, Kp;
   int Ncols, ntiles, nk;
   int kseg, nseg;       // K stages per accumulation segment, segments per column tile (tc::seg_stages)
   long long seg_stride; // MODE_STORE: segment sg writes its own slice out + sg * seg_stride (summed by sum_slices_kernel)
@@ -98,9 +99,21 @@ __global__ void absmax_kernel(const float* __restrict__ v, long long n, uint32_t
   if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));   // non-negative floats order like their bit patterns
 }
 
+// K order of the generated operand (GemmShape): packed position k' -> true k, or -1 for a padding row
+struct KOrder {
+  int H, Hpad, G, RB, Kp;
+};
+__device__ __forceinline__ int korder_true_k(const KOrder& ko, int kp) {
+  if (kp >= ko.Kp) return -1;
+  const int sec = ko.Hpad * ko.RB;
+  const int ob = kp / sec, rem = kp - ob * sec;
+  const int h = rem / ko.RB, r = ob * ko.RB + (rem - h * ko.RB);
+  return (h < ko.H && r < ko.G) ? h * ko.G + r : -1;
+}
+
 template <bool F16>
 __global__ void pack_core_kernel(const float* __restrict__ core, float* __restrict__ dst, EpsGeom g, int mode, int BN,
-                                 int Ncols, int Kdim, int ntiles, int nk, int passes, const uint32_t* __restrict__ absmax) {
+                                 int Ncols, KOrder ko, int ntiles, int nk, int passes, const uint32_t* __restrict__ absmax) {
   constexpr int KV = F16 ? 8 : 4;      // K values per 16-byte chunk
   constexpr int KS = F16 ? GBK16 : GBK;
   const long long total = (long long)ntiles * nk * BN * 8;  // one thread per 16-byte chunk
@@ -120,8 +133,8 @@ __global__ void pack_core_kernel(const float* __restrict__ core, float* __restri
     if (c < Ncols) {
 #pragma unroll
       for (int u = 0; u < KV; ++u) {
-        const int k = kc * KS + c16 * KV + u;
-        if (k < Kdim) {
+        const int k = korder_true_k(ko, kc * KS + c16 * KV + u);
+        if (k >= 0) {
           long long idx;
           if (mode == MODE_STORE) idx = (long long)c * g.N + k;
           else if (mode == MODE_DKR2) idx = (long long)k * g.N + c;
@@ -156,6 +169,66 @@ __global__ void pack_core_kernel(const float* __restrict__ core, float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ the GEMM
+// Epilogue store of a 32-row x 32-column block whose rows live one per lane (v = this lane's row): staged through a
+// [32][36] shared-memory tile so that a store instruction writes whole row segments (4 rows x 128 contiguous bytes, or one
+// row x 128 bytes when the destination is not 16-byte aligned) instead of 32 rows x 16 (or 4) bytes — the row-strided
+// form costs one L1 wavefront per row and instruction and made the epilogue the longest phase of the CIFAR shapes.
+// dst0: row 0, first column of the block; values are multiplied by s1 * s2; accum: add to what is there.
+__device__ __forceinline__ void store_tile(float* st, const float (&v)[32], float s1, float s2, float* dst0, long long ld,
+                                           int nrows, int ncols, bool accum, int lane) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4)
+    *(float4*)(st + lane * 36 + i) = make_float4(v[i] * s1 * s2, v[i + 1] * s1 * s2, v[i + 2] * s1 * s2, v[i + 3] * s1 * s2);
+  __syncwarp();
+  if (ncols == 32 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(dst0) & 15) == 0) {
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+    for (int r0 = 0; r0 < 32; r0 += 4) {
+      const int r = r0 + rsub;
+      if (r < nrows) {
+        float4 x4 = *(const float4*)(st + r * 36 + c4);
+        float4* p = (float4*)(dst0 + (long long)r * ld + c4);
+        if (accum) {
+          const float4 o4 = *p;
+          x4.x += o4.x; x4.y += o4.y; x4.z += o4.z; x4.w += o4.w;
+        }
+        *p = x4;
+      }
+    }
+  } else {
+    float* p = dst0 + lane;
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r, p += ld) {
+      if (r < nrows && lane < ncols) {
+        const float x1 = st[r * 36 + lane];
+        *p = accum ? *p + x1 : x1;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// NV consecutive values of the generated operand of one patch row, from packed K position kp0 (a multiple of NV; NV
+// divides 32, so the run stays inside one register-group section): the RB register-group values of the section are
+// loaded once, then every table value (two loads) yields RB products
+template <int NV, int RB>
+__device__ __forceinline__ void gen_values(float (&v)[NV], int kp0, int Hpad, const uint32_t* __restrict__ hidx,
+                                           const float* __restrict__ th, const float* __restrict__ tl, const float* __restrict__ tr) {
+  const int sec = Hpad * RB;
+  const int ob = kp0 / sec;
+  const int h0 = (kp0 - ob * sec) / RB;
+  float rg[RB];
+#pragma unroll
+  for (int r = 0; r < RB; ++r) rg[r] = tr[(ob * RB + r) * 128];
+#pragma unroll
+  for (int i = 0; i < NV / RB; ++i) {
+    const uint32_t id = hidx[h0 + i];
+    const float hv = th[(id & 0xFFFF) * 128] * tl[(id >> 16) * 128];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) v[i * RB + r] = hv * rg[r];
+  }
+}
+
 template <int MODE, bool F16>
 __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcGemmArgs a) {
   extern __shared__ unsigned char smem_dyn[];
@@ -166,24 +239,23 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
   const uint32_t STAGE_BYTES = 2 * B_BYTES;            // multiple of 1024 (BN % 16 == 0)
   unsigned char* base = smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* stages = base;
-  float* tabKH = (float*)(base + NB * STAGE_BYTES);    // [KH][128]
-  float* tabKL = tabKH + (a.KH + 1) * 128;             // [KL][128] (row KH of tabKH is all zeros: padding k); three-level: [KLb][128]
-  const int nKL = a.three ? a.KLb : a.KL;
-  float* tabG = tabKL + nKL * 128;                     // three-level only: gout [O][128]
-  float* tabE = tabG + (a.three ? O * 128 : 0);        // MODE_FWD: [BH + BL][128]; MODE_DKR2: gout [O][128]
+  float* tabKH = (float*)(base + NB * STAGE_BYTES);    // [KH + 1][128] (row KH is all zeros: padding h)
+  float* tabKL = tabKH + (a.KH + 1) * 128;             // [KLb][128]
+  float* tabR = tabKL + a.KLb * 128;                   // [GP][128] register group (rows >= G are zero)
+  float* tabE = tabR + a.GP * 128;                     // MODE_FWD: [BH + BL][128]; MODE_DKR2: gout [O][128]
   const int nE = (MODE == MODE_FWD) ? (g.BH + g.BL) : (MODE == MODE_DKR2 ? O : 0);
   float* outs = tabE + nE * 128;                       // MODE_FWD: [O][128]
   // index tables that make the inner loops branch-free (every load address is known up front -> full ILP):
-  //   kidx[k]  = kh | kl << 16 for the generated operand (k >= Kdim -> the all-zero row KH of tabKH)
+  //   hidx[h]  = kh | kl << 16 for the table part of the generated operand (h >= H -> the all-zero row KH of tabKH)
   //   eidx[..] = MODE_FWD: bh | bl << 16 for b2 in [0, Bn + max(Bn, 32)), b = b2 % Bn (32 consecutive b never leave the table);
   //              MODE_DKR2: o | last << 8 for the BN columns of a tile
-  uint32_t* kidx = (uint32_t*)(outs + ((MODE == MODE_FWD) ? O * 128 : 0));
-  const int nkidx = a.nk * KS;
-  uint32_t* eidx = kidx + nkidx;
+  uint32_t* hidx = (uint32_t*)(outs + ((MODE == MODE_FWD) ? O * 128 : 0));
+  uint32_t* eidx = hidx + a.Hpad;
   const int neidx = (MODE == MODE_FWD) ? g.Bn + (g.Bn > 32 ? g.Bn : 32) : (MODE == MODE_DKR2 ? ((BN + 31) & ~31) : 0);
   // F16: power-of-two exponents of the per-patch normalisation: [0][pr] generated operand, [1][pr] epilogue factors
-  int* rowexp = (int*)(eidx + ((neidx + 1) & ~1));
-  uint64_t* bars = (uint64_t*)(rowexp + 256);
+  int* rowexp = (int*)(eidx + ((neidx + 3) & ~3));       // 16-byte aligned (Hpad % 4 == 0): tstage is accessed as float4
+  float* tstage = (float*)(rowexp + 256);              // MODE_STORE / MODE_FWD: [4 epilogue warps][32][36] (store_tile)
+  uint64_t* bars = (uint64_t*)(tstage + ((MODE == MODE_DKR2) ? 0 : 4 * 32 * 36));
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * MAX_BSTAGES + 2 * ASTAGES + 2);
   const uint32_t bar_fullB0 = tc::smem_u32(bars), bar_emptyB0 = bar_fullB0 + 8 * MAX_BSTAGES;
   const uint32_t bar_fullA0 = bar_emptyB0 + 8 * MAX_BSTAGES, bar_emptyA0 = bar_fullA0 + 8 * ASTAGES;
@@ -251,7 +323,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
     if (tid < 128) {
       int ea = 0, eb = 0;
       for (int j = 0; j < g.n; ++j) {
-        const bool in_gen = (j >= a.jh0 && j < a.jh0 + a.cnth + a.cntl);
+        const bool in_gen = (j >= a.jh0 && j < a.jh0 + a.nf);
         if (in_gen) ea += fexp[j * 128 + tid];
         else eb += fexp[j * 128 + tid];
       }
@@ -274,18 +346,21 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
     // F16: the generated row carries a factor 2^15 (largest entry in [2^(15 - #factors), 2^15))
     const float gen_scale = F16 ? 32768.f : 1.f;
     for (int idx = tid; idx < a.KH * 128; idx += G_THREADS) tabKH[idx] = gen_scale * kr_entry(a.jh0, a.cnth, idx >> 7, idx & 127);
-    for (int idx = tid; idx < nKL * 128; idx += G_THREADS) {
-      const int pr = idx & 127, eo = idx >> 7;
-      int e = eo;
-      float gv = 1.f;
-      if (a.withG && !a.three) {
-        e = eo / O;
-        gv = gsx[(eo - e * O) * 128 + pr];
+    for (int idx = tid; idx < a.KLb * 128; idx += G_THREADS) tabKL[idx] = kr_entry(a.jh0 + a.cnth, a.cntl, idx >> 7, idx & 127);
+    for (int idx = tid; idx < a.GP * 128; idx += G_THREADS) {
+      const int pr = idx & 127, r = idx >> 7;
+      float v = 0.f;
+      if (r < a.G) {
+        int e = r;
+        float gv = 1.f;
+        if (a.withG) {
+          e = r / O;
+          gv = gsx[(r - e * O) * 128 + pr];
+        }
+        v = gv * kr_entry(a.jh0 + a.cnth + a.cntl, a.cr, e, pr);
       }
-      tabKL[idx] = gv * kr_entry(a.jh0 + a.cnth, a.cntl, e, pr);
+      tabR[idx] = v;
     }
-    if (a.three)
-      for (int idx = tid; idx < O * 128; idx += G_THREADS) tabG[idx] = gsx[idx];
     if (MODE == MODE_FWD) {
       for (int idx = tid; idx < g.BH * 128; idx += G_THREADS) tabE[idx] = kr_entry(g.m, g.b_nh, idx >> 7, idx & 127);
       for (int idx = tid; idx < g.BL * 128; idx += G_THREADS)
@@ -295,14 +370,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
     if (MODE == MODE_DKR2)
       for (int idx = tid; idx < O * 128; idx += G_THREADS) tabE[idx] = gsx[idx];
     if (tid < 128) tabKH[a.KH * 128 + tid] = 0.f;
-    for (int k = tid; k < nkidx; k += G_THREADS) {
-      uint32_t id = (uint32_t)a.KH;   // padding k: the all-zero row of tabKH
-      if (k < a.Kdim) {
-        const int kh = k / a.KL, kl = k % a.KL;
-        id = a.three ? ((uint32_t)kh | ((uint32_t)(kl / O) << 10) | ((uint32_t)(kl % O) << 20)) : ((uint32_t)kh | ((uint32_t)kl << 16));
-      }
-      kidx[k] = id;
-    }
+    for (int h = tid; h < a.Hpad; h += G_THREADS)
+      hidx[h] = (h < a.H) ? ((uint32_t)(h / a.KLb) | ((uint32_t)(h % a.KLb) << 16)) : (uint32_t)a.KH;
     if (MODE == MODE_FWD)
       for (int b2 = tid; b2 < neidx; b2 += G_THREADS) {
         const int b = b2 % g.Bn;
@@ -406,58 +475,33 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
     const int pr = (warp & 3) * 32 + lane;
     const float* th = tabKH + pr;
     const float* tl = tabKL + pr;
+    const float* tr = tabR + pr;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     int sa = 0;
     uint32_t phe = 1;   // parity to wait for on the empty barrier
     long long dbg_pwait = 0, dbg_pst = 0, dbg_pgen = 0, tprev = TCG_CLK();
     for (int t = 0; t < a.ntiles; ++t) {
       for (int kc = 0; kc < a.nk; ++kc) {
-        const int k0 = kc * KS;
         uint32_t hi[16], lo[16];   // this half of a 32-column TMEM slab: 16 tf32 values or 32 packed fp16 values
-        if (F16) {
-          const float* tg = tabG + pr;
-          {
-            const int h = ph_;
-            uint32_t id[32];
-            const uint4* kp = (const uint4*)(kidx + k0 + 32 * h);   // warp-uniform, 16-byte aligned
-#pragma unroll
-            for (int q4 = 0; q4 < 8; ++q4) {
-              const uint4 u = kp[q4];
-              id[4 * q4] = u.x; id[4 * q4 + 1] = u.y; id[4 * q4 + 2] = u.z; id[4 * q4 + 3] = u.w;
-            }
-            float v[32];
-            if (a.three) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = th[(id[j] & 0x3FF) * 128] * tl[((id[j] >> 10) & 0x3FF) * 128] * tg[(id[j] >> 20) * 128];
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = th[(id[j] & 0xFFFF) * 128] * tl[(id[j] >> 16) * 128];
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) split_f16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-          }
+        constexpr int NV = KS / 2;  // generated values per thread and stage
+        float v[NV];
+        const int kp0 = kc * KS + NV * ph_;
+        if (kp0 < a.Kp) {
+          if (a.RB == 8) gen_values<NV, 8>(v, kp0, a.Hpad, hidx, th, tl, tr);
+          else gen_values<NV, 4>(v, kp0, a.Hpad, hidx, th, tl, tr);
         } else {
-          uint32_t id[GBK / 2];
-          const uint4* kp = (const uint4*)(kidx + k0 + (GBK / 2) * ph_);   // warp-uniform, 16-byte aligned
 #pragma unroll
-          for (int q4 = 0; q4 < GBK / 8; ++q4) {
-            const uint4 u = kp[q4];
-            id[4 * q4] = u.x; id[4 * q4 + 1] = u.y; id[4 * q4 + 2] = u.z; id[4 * q4 + 3] = u.w;
-          }
-          float fh, fl;
-          if (a.three) {
-            const float* tg = tabG + pr;
+          for (int j = 0; j < NV; ++j) v[j] = 0.f;
+        }
+        if (F16) {
 #pragma unroll
-            for (int j = 0; j < GBK / 2; ++j) {
-              tc::split_tf32(th[(id[j] & 0x3FF) * 128] * tl[((id[j] >> 10) & 0x3FF) * 128] * tg[(id[j] >> 20) * 128], fh, fl);
-              hi[j] = __float_as_uint(fh); lo[j] = __float_as_uint(fl);
-            }
-          } else {
+          for (int j = 0; j < 16; ++j) split_f16x2(v[(2 * j) % NV], v[(2 * j + 1) % NV], hi[j], lo[j]);
+        } else {
 #pragma unroll
-            for (int j = 0; j < GBK / 2; ++j) {
-              tc::split_tf32(th[(id[j] & 0xFFFF) * 128] * tl[(id[j] >> 16) * 128], fh, fl);
-              hi[j] = __float_as_uint(fh); lo[j] = __float_as_uint(fl);
-            }
+          for (int j = 0; j < 16; ++j) {
+            float fh, fl;
+            tc::split_tf32(v[j % NV], fh, fl);
+            hi[j] = __float_as_uint(fh); lo[j] = __float_as_uint(fl);
           }
         }
         long long t0 = TCG_CLK();
@@ -517,6 +561,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
       }
 #pragma unroll 1
       for (int cb = 0; cb < BN; cb += 32) {
+        if (n0 + cb >= a.Ncols) break;   // padding columns of the last tile (warp-uniform): nothing to reduce or store
         float v[32];
         tc::tmem_ld32(tmem_main + lane_base + (uint32_t)cb, v);
         if (a.passes == 3) {
@@ -526,47 +571,23 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
           for (int i = 0; i < 32; ++i) v[i] = F16 ? fmaf(w[i], 1.f / 2048.f, v[i]) : v[i] + w[i];
         }
         if (MODE == MODE_STORE) {
-          if (F16) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = v[i] * sc1 * sc2;
-          }
-          if (pvalid) {
-            // every K segment has its own output slice (plain stores; a read-modify-write of these row-strided 4-byte
-            // accesses was measured at 4x the whole kernel): sum_slices_kernel adds them with coalesced accesses
-            float* crow = a.out + (long long)(u % a.nseg) * a.seg_stride + (long long)pl * a.ldc;
-            const int nb = n0 + cb;
-            if (cb + 32 <= BN && nb + 32 <= a.Ncols && (a.ldc & 3) == 0) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) *(float4*)(crow + nb + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (cb + i < BN && nb + i < a.Ncols) crow[nb + i] = v[i];
-            }
-          }
+          // every K segment has its own output slice (plain stores; a read-modify-write of the slice was measured at 4x
+          // the whole kernel): sum_slices_kernel adds them with coalesced accesses
+          const int row0 = pl0 + quad * 32;
+          int ncols = a.Ncols - n0 - cb;
+          if (BN - cb < ncols) ncols = BN - cb;
+          if (ncols > 32) ncols = 32;
+          store_tile(tstage + quad * (32 * 36), v, F16 ? sc1 : 1.f, F16 ? sc2 : 1.f,
+                     a.out + (long long)(u % a.nseg) * a.seg_stride + (long long)row0 * a.ldc + n0 + cb, a.ldc, a.np - row0, ncols,
+                     false, lane);
         } else if (MODE == MODE_FWD) {
-          if (a.tsave != nullptr && pvalid) {   // keep T for the input gradient (dctn_eps_forward_train)
-            float* trow = a.tsave + (pt0 + pr) * (long long)a.Ncols;
-            const int nb = n0 + cb;
-            if (cb + 32 <= BN && nb + 32 <= a.Ncols && (a.Ncols & 3) == 0) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                float4 r4 = F16 ? make_float4(v[i] * sc1 * sc2, v[i + 1] * sc1 * sc2, v[i + 2] * sc1 * sc2, v[i + 3] * sc1 * sc2)
-                                : make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                if (accum) {
-                  const float4 o4 = *(const float4*)(trow + nb + i);
-                  r4.x += o4.x; r4.y += o4.y; r4.z += o4.z; r4.w += o4.w;
-                }
-                *(float4*)(trow + nb + i) = r4;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (cb + i < BN && nb + i < a.Ncols) {
-                  const float r1 = F16 ? v[i] * sc1 * sc2 : v[i];
-                  trow[nb + i] = accum ? trow[nb + i] + r1 : r1;
-                }
-            }
+          if (a.tsave != nullptr) {   // keep T for the input gradient (dctn_eps_forward_train)
+            const int row0 = pl0 + quad * 32;
+            int ncols = a.Ncols - n0 - cb;
+            if (BN - cb < ncols) ncols = BN - cb;
+            if (ncols > 32) ncols = 32;
+            store_tile(tstage + quad * (32 * 36), v, F16 ? sc1 : 1.f, F16 ? sc2 : 1.f,
+                       a.tsave + (pt0 + quad * 32) * (long long)a.Ncols + n0 + cb, a.Ncols, a.np - row0, ncols, accum, lane);
           }
           // columns cb..cb+31 are b = fb, fb+1, ... (wrapping to the next o at b == Bn; Bn >= 32: at most one wrap)
           int nvalid = BN - cb;
@@ -658,41 +679,60 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
 
 // ------------------------------------------------------------------------------------------------ host side
 struct GemmShape {
-  int jh0, cnth, KH, cntl, KLb, KL, Kdim, withG, Ncols, three;
+  int jh0, nf, withG, Ncols, Kdim;   // generated operand: factors [jh0, jh0 + nf) (times gout if withG); true K extent
+  // K order of the generated operand and of the packed core: k' = (ob * Hpad + h) * RB + rl, where
+  //   r = ob * RB + rl < G indexes the REGISTER GROUP — the fastest-varying `cr` factors of the operand (times gout):
+  //       a producer thread holds the RB values tabR[ob*RB ..] of its patch in registers for a whole section `ob`,
+  //   h < H indexes the remaining factors, split into two table groups: value = tabKH[h / KLb] * tabKL[h % KLb].
+  // A generated element costs one multiplication (plus 2 shared-memory loads per RB elements) instead of two or three
+  // loads; the price is padding (h to Hpad, r to GP: those rows of the packed core are zero).
+  int cr, G, GP, RB, cnth, KH, cntl, KLb, H, Hpad, Kp;
 };
+
+inline int ipow_i(int b, int e) { int r = 1; while (e-- > 0) r *= b; return r; }
 
 inline GemmShape shape_for(const EpsGeom& g, int mode) {
   GemmShape s{};
   if (mode == MODE_STORE) {  // Gen = KR2 x gout over k = (b, o); columns = a
-    s.jh0 = g.m; s.cnth = g.b_nh; s.KH = g.BH; s.cntl = g.b_nl; s.KLb = g.BL; s.KL = g.BL * g.O; s.Kdim = g.N;
-    s.withG = 1; s.Ncols = g.A;
+    s.jh0 = g.m; s.nf = g.n - g.m; s.Kdim = g.N; s.withG = 1; s.Ncols = g.A;
   } else {                   // Gen = KR1 over k = a; columns = n
-    s.jh0 = 0; s.cnth = g.a_nh; s.KH = g.AH; s.cntl = g.a_nl; s.KLb = g.AL; s.KL = g.AL; s.Kdim = g.A;
-    s.withG = 0; s.Ncols = g.N;
+    s.jh0 = 0; s.nf = g.m; s.Kdim = g.A; s.withG = 0; s.Ncols = g.N;
   }
-  s.three = 0;
+  // register group: the choice with the least padded K; ties: wider blocks, then the larger group (smaller tables)
+  long long best = -1;
+  for (int cr = 0; cr <= s.nf; ++cr) {
+    const long long G = (long long)ipow_i(g.Q, cr) * (s.withG ? g.O : 1);
+    if (G > 64) break;
+    const int H = ipow_i(g.Q, s.nf - cr);
+    for (int RB = 8; RB >= 4; RB -= 4) {
+      const int GP = ((int)G + RB - 1) / RB * RB, hq = 32 / RB, Hpad = (H + hq - 1) / hq * hq;
+      const long long cost = (long long)GP * Hpad;
+      if (best < 0 || cost < best || (cost == best && (RB > s.RB || (RB == s.RB && cr > s.cr)))) {
+        best = cost; s.cr = cr; s.G = (int)G; s.GP = GP; s.RB = RB; s.H = H; s.Hpad = Hpad;
+      }
+    }
+  }
+  if (best < 0) {   // gout alone wider than 64 values: register blocks over gout only
+    s.cr = 0; s.G = g.O; s.RB = 8; s.GP = (g.O + 7) / 8 * 8; s.H = ipow_i(g.Q, s.nf); s.Hpad = (s.H + 3) / 4 * 4;
+  }
+  const int nrem = s.nf - s.cr;
+  s.cntl = nrem / 2; s.cnth = nrem - s.cntl;
+  s.KH = ipow_i(g.Q, s.cnth); s.KLb = ipow_i(g.Q, s.cntl);
+  s.Kp = s.GP * s.Hpad;      // multiple of 32
   return s;
 }
 
-// the K extent of a stage is 64 (fp16) or 32 (tf32); the index table is sized for the smaller one (the larger table),
-// so that one tile-width choice serves both arithmetics
+// the K extent of a stage is 64 (fp16) or 32 (tf32); one tile-width choice serves both arithmetics
 inline size_t gemm_fixed_smem(const EpsGeom& g, const GemmShape& s, int mode) {
   const int nE = (mode == MODE_FWD) ? (g.BH + g.BL) : (mode == MODE_DKR2 ? g.O : 0);
-  const size_t ktab = s.three ? (size_t)(s.KH + 1 + s.KLb + g.O) : (size_t)(s.KH + 1 + s.KL);
-  const size_t nkidx = (size_t)((s.Kdim + GBK16 - 1) / GBK16) * GBK16;
+  const size_t ktab = (size_t)(s.KH + 1 + s.KLb + s.GP);
   const size_t neidx = (mode == MODE_FWD) ? (size_t)g.Bn + (g.Bn > 32 ? g.Bn : 32) : (mode == MODE_DKR2 ? (size_t)MAX_BN : 0);
-  return 1024 + (ktab + nE + (mode == MODE_FWD ? g.O : 0)) * 128 * 4 + (nkidx + neidx + 2) * 4 + 256 * 4 +
-         (2 * MAX_BSTAGES + 2 * ASTAGES + 2) * 8 + 16;
+  return 1024 + (ktab + nE + (mode == MODE_FWD ? g.O : 0)) * 128 * 4 + ((size_t)s.Hpad + neidx + 4) * 4 + 256 * 4 +
+         (mode == MODE_DKR2 ? 0 : 4 * 32 * 36 * 4) + (2 * MAX_BSTAGES + 2 * ASTAGES + 2) * 8 + 16;
 }
 inline size_t bstage_bytes(int BN) { return 2 * (size_t)BN * 128; }   // hi + lo parts, BN rows of 128 bytes
 inline int stage_k(int passes) { return passes == ARITH_F16X3 ? GBK16 : GBK; }
-// two-level generated operand when its tables leave room for at least two 64-column stages, else (gout-folded operand
-// only) the three-level product
-inline GemmShape shape_auto(const EpsGeom& g, int mode) {
-  GemmShape s = shape_for(g, mode);
-  if (s.withG && gemm_fixed_smem(g, s, mode) + 2 * bstage_bytes(64) > TCG_SMEM_LIMIT && s.KH < 1024 && s.KLb < 1024 && g.O < 1024) s.three = 1;
-  return s;
-}
+inline GemmShape shape_auto(const EpsGeom& g, int mode) { return shape_for(g, mode); }
 
 // number of shared-memory B stages that fit (0 = does not fit); the setup scratch (x and gout of 128 patches)
 // is aliased onto the stages and must fit too
@@ -702,6 +742,10 @@ inline int pick_bstages(const EpsGeom& g, int mode, int BN) {
   if (fixed >= TCG_SMEM_LIMIT) return 0;
   int nb = (int)((TCG_SMEM_LIMIT - fixed) / bstage_bytes(BN));
   if (nb > MAX_BSTAGES) nb = MAX_BSTAGES;
+  if (const char* e = getenv("DCTN_B200_MAX_BSTAGES")) {   // experiments only
+    const int v = atoi(e);
+    if (v >= 2 && nb > v) nb = v;
+  }
   if (nb < 2) return 0;
   if ((size_t)(g.n * g.Q + g.O + g.n + 1) * 128 * 4 > nb * bstage_bytes(BN)) return 0;   // x, gout, exponents
   return nb;
@@ -726,7 +770,7 @@ inline int pick_bn(const EpsGeom& g, int mode) {
 // size of the packed core image (TF32 layout; the fp16 image is half as large and uses the same buffer)
 inline size_t packed_floats(const EpsGeom& g, int mode, int BN) {
   const GemmShape s = shape_auto(g, mode);
-  long long ntiles = (s.Ncols + BN - 1) / BN, nk = (s.Kdim + GBK - 1) / GBK;
+  long long ntiles = (s.Ncols + BN - 1) / BN, nk = (s.Kp + GBK - 1) / GBK;
   return (size_t)(ntiles * nk * 2 * BN * 32);
 }
 constexpr size_t WS_HEADER = 256;   // first bytes of every workspace: bits of max|core| (fp16 arithmetic)
@@ -764,8 +808,9 @@ int run_gemm(const EpsGeom& g, int mode, int BN, const float* x, const float* go
   const int KS = stage_k(passes);
   TcGemmArgs a{};
   a.g = g; a.x = x; a.gout = gout; a.p0 = p0; a.np = np;
-  a.jh0 = s.jh0; a.cnth = s.cnth; a.KH = s.KH; a.cntl = s.cntl; a.KLb = s.KLb; a.KL = s.KL; a.Kdim = s.Kdim; a.withG = s.withG; a.three = s.three;
-  a.Ncols = s.Ncols; a.ntiles = (s.Ncols + BN - 1) / BN; a.nk = (s.Kdim + KS - 1) / KS;
+  a.jh0 = s.jh0; a.nf = s.nf; a.withG = s.withG; a.cnth = s.cnth; a.KH = s.KH; a.cntl = s.cntl; a.KLb = s.KLb;
+  a.cr = s.cr; a.G = s.G; a.GP = s.GP; a.RB = s.RB; a.H = s.H; a.Hpad = s.Hpad; a.Kp = s.Kp;
+  a.Ncols = s.Ncols; a.ntiles = (s.Ncols + BN - 1) / BN; a.nk = (s.Kp + KS - 1) / KS;
   // fp16 stages hold 64 K-values (4 MMAs), tf32 stages 32 (also 4 MMAs): the same number of accumulation steps
   a.kseg = tc::seg_stages(a.nk); a.nseg = (a.nk + a.kseg - 1) / a.kseg;
   a.seg_stride = seg_stride;
@@ -784,6 +829,10 @@ int run_gemm(const EpsGeom& g, int mode, int BN, const float* x, const float* go
   }
 #endif
   const size_t smem = gemm_fixed_smem(g, s, mode) + a.bstages * bstage_bytes(BN);
+  if (getenv("DCTN_DEBUG_SHAPE"))
+    fprintf(stderr, "[tcg shape] mode=%d BN=%d NB=%d smem=%zu nf=%d cr=%d G=%d GP=%d RB=%d H=%d Hpad=%d KH=%d KLb=%d Kp=%d nk=%d ntiles=%d kseg=%d\n",
+            mode, BN, a.bstages, smem, a.nf, a.cr, a.G, a.GP, a.RB, a.H, a.Hpad, a.KH, a.KLb, a.Kp, a.nk, a.ntiles, a.kseg);
+  if (getenv("DCTN_DEBUG_SKIP_GEMM")) return 0;
   int rc;
   if (mode == MODE_STORE) rc = f16 ? launch_gemm_inst<MODE_STORE, true>(a, smem, st) : launch_gemm_inst<MODE_STORE, false>(a, smem, st);
   else if (mode == MODE_FWD) rc = f16 ? launch_gemm_inst<MODE_FWD, true>(a, smem, st) : launch_gemm_inst<MODE_FWD, false>(a, smem, st);
@@ -807,7 +856,7 @@ int run_gemm(const EpsGeom& g, int mode, int BN, const float* x, const float* go
 
 // K segments of the generic MODE_STORE GEMM (its output has one slice per segment)
 inline int store_segments(const EpsGeom& g, int passes) {
-  const int nk = (g.N + stage_k(passes) - 1) / stage_k(passes);
+  const int nk = (shape_auto(g, MODE_STORE).Kp + stage_k(passes) - 1) / stage_k(passes);
   const int kseg = tc::seg_stages(nk);
   return (nk + kseg - 1) / kseg;
 }
@@ -837,12 +886,13 @@ int run_pack(const EpsGeom& g, int mode, int BN, const float* core, float* dst, 
   const GemmShape s = shape_auto(g, mode);
   const bool f16 = passes == ARITH_F16X3;
   const int KS = stage_k(passes);
-  const int ntiles = (s.Ncols + BN - 1) / BN, nk = (s.Kdim + KS - 1) / KS;
+  const int ntiles = (s.Ncols + BN - 1) / BN, nk = (s.Kp + KS - 1) / KS;
   long long total = (long long)ntiles * nk * BN * 8;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  if (f16) pack_core_kernel<true><<<blocks, 256, 0, st>>>(core, dst, g, mode, BN, s.Ncols, s.Kdim, ntiles, nk, 3, absmax);
-  else pack_core_kernel<false><<<blocks, 256, 0, st>>>(core, dst, g, mode, BN, s.Ncols, s.Kdim, ntiles, nk, passes, absmax);
+  const KOrder ko{s.H, s.Hpad, s.G, s.RB, s.Kp};
+  if (f16) pack_core_kernel<true><<<blocks, 256, 0, st>>>(core, dst, g, mode, BN, s.Ncols, ko, ntiles, nk, 3, absmax);
+  else pack_core_kernel<false><<<blocks, 256, 0, st>>>(core, dst, g, mode, BN, s.Ncols, ko, ntiles, nk, passes, absmax);
   dctn_count_launch();
   DCTN_CUDA_CHECK_RET(cudaGetLastError());
   return 0;
