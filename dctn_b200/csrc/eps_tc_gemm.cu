@@ -53,9 +53,12 @@ constexpr int ARITH_F16X3 = 6;  // value of `passes` that selects the split-fp16
 constexpr int ASTAGES = 2;      // A-operand stages in TMEM (2 x (hi + lo) x 32 columns = 128 columns)
 constexpr int MAX_BSTAGES = 4;  // B-operand stages in shared memory (as many as fit)
 constexpr int MAX_BN = 192;     // accumulators: main + small = 2*BN columns, + 128 for A  <= 512 TMEM columns
-constexpr int G_THREADS = 512;  // warp 0: bulk copies, warp 1: MMA, warp 2: TMEM alloc, warps 4-7 and 12-15: producers (each half of a
-                                // stage's K range: the two table look-ups per generated element made four producer warps the
-                                // limiter, 1600-1900 cycles per stage against 1152 of MMA), warps 8-11: epilogue
+constexpr int G_THREADS = 640;  // warp 0: bulk copies, warp 1: MMA, warp 2: TMEM alloc, warps 4-7 and 12-15: producers (each half of a
+                                // stage's K range), warps 8-11 and 16-19: epilogue (two warps per TMEM lane quadrant, alternating
+                                // 32-column batches: the epilogue of a tile is not overlapped with the next tile's MMAs — one
+                                // accumulator set — so its length is paid in full, and one warp per scheduler runs its ~1000
+                                // dependent instructions per batch at half the rate two warps reach)
+constexpr int G_EPI_WARPS = 8;
 enum { MODE_STORE = 0, MODE_FWD = 1, MODE_DKR2 = 2 };
 constexpr size_t TCG_SMEM_LIMIT = 227 * 1024;
 
@@ -70,6 +73,7 @@ struct TcGemmArgs {
   int jh0, nf, withG, cnth, KH, cntl, KLb, cr, G, GP, RB, H, Hpad, Kp;
   int Ncols, ntiles, nk;
   int kseg, nseg;       // K stages per accumulation segment, segments per column tile (tc::seg_stages)
+  int dbuf;             // 1: two accumulator sets (BN <= 96) alternate between virtual tiles: the epilogue of one overlaps the MMAs of the next
   long long seg_stride; // MODE_STORE: segment sg writes its own slice out + sg * seg_stride (summed by sum_slices_kernel)
   const float* packed;  // [ntiles][nk][2][BN*32]
   int BN;               // column-tile width: multiple of 16, <= MAX_BN
@@ -169,43 +173,51 @@ __global__ void pack_core_kernel(const float* __restrict__ core, float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ the GEMM
-// Epilogue store of a 32-row x 32-column block whose rows live one per lane (v = this lane's row): staged through a
-// [32][36] shared-memory tile so that a store instruction writes whole row segments (4 rows x 128 contiguous bytes, or one
-// row x 128 bytes when the destination is not 16-byte aligned) instead of 32 rows x 16 (or 4) bytes — the row-strided
-// form costs one L1 wavefront per row and instruction and made the epilogue the longest phase of the CIFAR shapes.
+// Epilogue store of a 32-row x 32-column block whose rows live one per lane (v = this lane's row): staged, 16 columns at
+// a time, through a [32][20] shared-memory tile so that a store instruction writes whole row segments (8 rows x 64
+// contiguous bytes, or 2 rows x 64 bytes when the destination is not 16-byte aligned) instead of 32 rows x 16 (or 4)
+// bytes — the row-strided form costs one L1 wavefront per row and instruction (measured: 4.2k cycles per batch for the
+// odd-pitched dKR1 of the CIFAR (2, 23 -> 24) layer, 0.6k this way).
 // dst0: row 0, first column of the block; values are multiplied by s1 * s2; accum: add to what is there.
+constexpr int TST_FLOATS = 32 * 20;
 __device__ __forceinline__ void store_tile(float* st, const float (&v)[32], float s1, float s2, float* dst0, long long ld,
                                            int nrows, int ncols, bool accum, int lane) {
+  const bool vec = ncols == 32 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(dst0) & 15) == 0;
 #pragma unroll
-  for (int i = 0; i < 32; i += 4)
-    *(float4*)(st + lane * 36 + i) = make_float4(v[i] * s1 * s2, v[i + 1] * s1 * s2, v[i + 2] * s1 * s2, v[i + 3] * s1 * s2);
-  __syncwarp();
-  if (ncols == 32 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(dst0) & 15) == 0) {
-    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+  for (int hb = 0; hb < 2; ++hb) {
 #pragma unroll
-    for (int r0 = 0; r0 < 32; r0 += 4) {
-      const int r = r0 + rsub;
-      if (r < nrows) {
-        float4 x4 = *(const float4*)(st + r * 36 + c4);
-        float4* p = (float4*)(dst0 + (long long)r * ld + c4);
-        if (accum) {
-          const float4 o4 = *p;
-          x4.x += o4.x; x4.y += o4.y; x4.z += o4.z; x4.w += o4.w;
+    for (int i = 0; i < 16; i += 4)
+      *(float4*)(st + lane * 20 + i) = make_float4(v[16 * hb + i] * s1 * s2, v[16 * hb + i + 1] * s1 * s2,
+                                                   v[16 * hb + i + 2] * s1 * s2, v[16 * hb + i + 3] * s1 * s2);
+    __syncwarp();
+    if (vec) {
+      const int rsub = lane >> 2, c4 = (lane & 3) * 4;
+#pragma unroll
+      for (int r0 = 0; r0 < 32; r0 += 8) {
+        const int r = r0 + rsub;
+        if (r < nrows) {
+          float4 x4 = *(const float4*)(st + r * 20 + c4);
+          float4* p = (float4*)(dst0 + (long long)r * ld + 16 * hb + c4);
+          if (accum) {
+            const float4 o4 = *p;
+            x4.x += o4.x; x4.y += o4.y; x4.z += o4.z; x4.w += o4.w;
+          }
+          *p = x4;
         }
-        *p = x4;
       }
-    }
-  } else {
-    float* p = dst0 + lane;
+    } else {
+      const int rsub = lane >> 4, c = lane & 15;
+      float* p = dst0 + (long long)rsub * ld + 16 * hb + c;
 #pragma unroll 4
-    for (int r = 0; r < 32; ++r, p += ld) {
-      if (r < nrows && lane < ncols) {
-        const float x1 = st[r * 36 + lane];
-        *p = accum ? *p + x1 : x1;
+      for (int r0 = 0; r0 < 32; r0 += 2, p += 2 * ld) {
+        if (r0 + rsub < nrows && 16 * hb + c < ncols) {
+          const float x1 = st[(r0 + rsub) * 20 + c];
+          *p = accum ? *p + x1 : x1;
+        }
       }
     }
+    __syncwarp();
   }
-  __syncwarp();
 }
 
 // NV consecutive values of the generated operand of one patch row, from packed K position kp0 (a multiple of NV; NV
@@ -244,22 +256,22 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
   float* tabR = tabKL + a.KLb * 128;                   // [GP][128] register group (rows >= G are zero)
   float* tabE = tabR + a.GP * 128;                     // MODE_FWD: [BH + BL][128]; MODE_DKR2: gout [O][128]
   const int nE = (MODE == MODE_FWD) ? (g.BH + g.BL) : (MODE == MODE_DKR2 ? O : 0);
-  float* outs = tabE + nE * 128;                       // MODE_FWD: [O][128]
+  float* outs = tabE + nE * 128;                       // MODE_FWD: [2 epilogue groups][O][128]
   // index tables that make the inner loops branch-free (every load address is known up front -> full ILP):
   //   hidx[h]  = kh | kl << 16 for the table part of the generated operand (h >= H -> the all-zero row KH of tabKH)
   //   eidx[..] = MODE_FWD: bh | bl << 16 for b2 in [0, Bn + max(Bn, 32)), b = b2 % Bn (32 consecutive b never leave the table);
   //              MODE_DKR2: o | last << 8 for the BN columns of a tile
-  uint32_t* hidx = (uint32_t*)(outs + ((MODE == MODE_FWD) ? O * 128 : 0));
+  uint32_t* hidx = (uint32_t*)(outs + ((MODE == MODE_FWD) ? 2 * O * 128 : 0));
   uint32_t* eidx = hidx + a.Hpad;
   const int neidx = (MODE == MODE_FWD) ? g.Bn + (g.Bn > 32 ? g.Bn : 32) : (MODE == MODE_DKR2 ? ((BN + 31) & ~31) : 0);
   // F16: power-of-two exponents of the per-patch normalisation: [0][pr] generated operand, [1][pr] epilogue factors
   int* rowexp = (int*)(eidx + ((neidx + 3) & ~3));       // 16-byte aligned (Hpad % 4 == 0): tstage is accessed as float4
-  float* tstage = (float*)(rowexp + 256);              // MODE_STORE / MODE_FWD: [4 epilogue warps][32][36] (store_tile)
-  uint64_t* bars = (uint64_t*)(tstage + ((MODE == MODE_DKR2) ? 0 : 4 * 32 * 36));
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * MAX_BSTAGES + 2 * ASTAGES + 2);
+  float* tstage = (float*)(rowexp + 256);              // MODE_STORE / MODE_FWD: [8 epilogue warps][32][20] (store_tile)
+  uint64_t* bars = (uint64_t*)(tstage + ((MODE == MODE_DKR2) ? 0 : G_EPI_WARPS * TST_FLOATS));
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * MAX_BSTAGES + 2 * ASTAGES + 4);
   const uint32_t bar_fullB0 = tc::smem_u32(bars), bar_emptyB0 = bar_fullB0 + 8 * MAX_BSTAGES;
   const uint32_t bar_fullA0 = bar_emptyB0 + 8 * MAX_BSTAGES, bar_emptyA0 = bar_fullA0 + 8 * ASTAGES;
-  const uint32_t bar_accfull = bar_emptyA0 + 8 * ASTAGES, bar_accempty = bar_accfull + 8;
+  const uint32_t bar_accfull = bar_emptyA0 + 8 * ASTAGES, bar_accempty = bar_accfull + 16;   // one pair per accumulator set
   // setup-only scratch aliased onto the (not yet used) B stages: x [n*Q][128] and gout [O][128]
   float* xs = (float*)stages;
   float* gsx = xs + g.n * Q * 128;
@@ -280,13 +292,15 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
       tc::mbar_init(bar_fullA0 + 8 * s, 8);      // 8 producer warps
       tc::mbar_init(bar_emptyA0 + 8 * s, 1);     // tcgen05.commit
     }
-    tc::mbar_init(bar_accfull, 1);
-    tc::mbar_init(bar_accempty, 4);              // 4 epilogue warps
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(bar_accfull + 8 * s, 1);
+      tc::mbar_init(bar_accempty + 8 * s, G_EPI_WARPS);
+    }
     tc::fence_barrier_init();
   }
   if (warp == 2) tc::tmem_alloc(tc::smem_u32(tmem_slot), TMEM_COLS);
   {
-    // a thread owns one patch row (pr) and every fourth factor (G_THREADS = 4 x 128): ONE patch-origin computation, the Q
+    // a thread owns one patch row (pr) and every fifth factor (G_THREADS = 5 x 128): ONE patch-origin computation, the Q
     // loads of a factor issued together and — F16 — its range normalisation in the same pass: the factor vector (and the
     // gout row) is scaled by a power of two so that its largest magnitude lies in [0.5, 1); exact, undone by the
     // epilogue through rowexp
@@ -365,7 +379,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
       for (int idx = tid; idx < g.BH * 128; idx += G_THREADS) tabE[idx] = kr_entry(g.m, g.b_nh, idx >> 7, idx & 127);
       for (int idx = tid; idx < g.BL * 128; idx += G_THREADS)
         tabE[g.BH * 128 + idx] = kr_entry(g.m + g.b_nh, g.b_nl, idx >> 7, idx & 127);
-      for (int idx = tid; idx < O * 128; idx += G_THREADS) outs[idx] = 0.f;
+      for (int idx = tid; idx < 2 * O * 128; idx += G_THREADS) outs[idx] = 0.f;
     }
     if (MODE == MODE_DKR2)
       for (int idx = tid; idx < O * 128; idx += G_THREADS) tabE[idx] = gsx[idx];
@@ -386,9 +400,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
   // F16: exponent that turns an accumulator value into the true product: patch normalisation, 2^15 of the generated
   // row and the core's global scale
   const int core_exp = F16 ? core_scale_exp(__ldg(a.core_absmax)) : 0;
-  const uint32_t tmem_main = *tmem_slot;
-  const uint32_t tmem_small = tmem_main + (uint32_t)BN;
-  const uint32_t tmem_a0 = tmem_main + 2u * (uint32_t)BN;   // stage s: hi at +64*s, lo at +64*s + 32
+  // accumulator set s (only set 0 without dbuf): main at +2*BN*s, small at +2*BN*s + BN; then the A stages
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_a0 = tmem_base + (a.dbuf ? 4u : 2u) * (uint32_t)BN;   // stage s: hi at +64*s, lo at +64*s + 32
   const int total_it = a.ntiles * a.nk;
 
   if (warp == 0) {
@@ -422,7 +436,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
       const int sg = u % a.nseg;
       const int kc0 = sg * a.kseg, kc1 = (kc0 + a.kseg < a.nk) ? kc0 + a.kseg : a.nk;
       long long ta = TCG_CLK();
-      if (u > 0) tc::mbar_wait(bar_accempty, (uint32_t)((u - 1) & 1));  // epilogue has drained the previous segment
+      const int set = a.dbuf ? (u & 1) : 0, nuse = a.dbuf ? (u >> 1) : u;   // nuse: earlier uses of this accumulator set
+      const uint32_t tmem_main = tmem_base + (uint32_t)(2 * BN * set), tmem_small = tmem_main + (uint32_t)BN;
+      if (nuse > 0) tc::mbar_wait(bar_accempty + 8 * set, (uint32_t)((nuse - 1) & 1));  // epilogue has drained this set
       dbg_waitAcc += TCG_CLK() - ta;
       tc::tc_fence_after();
       for (int kc = kc0; kc < kc1; ++kc) {
@@ -458,7 +474,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
           }
           tc::umma_commit(bar_emptyA0 + 8 * sa);
           tc::umma_commit(bar_emptyB0 + 8 * sb_);
-          if (kc == kc1 - 1) tc::umma_commit(bar_accfull);
+          if (kc == kc1 - 1) tc::umma_commit(bar_accfull + 8 * set);
         }
         __syncwarp();
         if (++sa == ASTAGES) { sa = 0; pha ^= 1; }
@@ -469,7 +485,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
       long long* d = a.dbg + (long long)blockIdx.x * 8;
       d[0] = dbg_waitA; d[1] = dbg_waitB; d[2] = dbg_waitAcc; d[3] = TCG_CLK() - dbg_start;
     }
-  } else if ((warp >= 4 && warp < 8) || warp >= 12) {
+  } else if ((warp >= 4 && warp < 8) || (warp >= 12 && warp < 16)) {
     // =========================== A producers: one patch row (= TMEM lane) and one half of the stage per thread ===========================
     const int ph_ = warp >= 12 ? 1 : 0;        // which half of the stage's K range
     const int pr = (warp & 3) * 32 + lane;
@@ -524,9 +540,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
       long long* d = a.dbg + (long long)blockIdx.x * 8;
       d[4] = dbg_pwait; d[5] = dbg_pst; d[6] = dbg_pgen;
     }
-  } else if (warp >= 8 && warp < 12) {
+  } else if ((warp >= 8 && warp < 12) || warp >= 16) {
     // =========================== epilogue ===========================
-    const int quad = warp & 3;
+    // group 0 (warps 8-11) takes the even 32-column batches of a tile, group 1 (warps 16-19) the odd ones; MODE_DKR2's
+    // reduction runs across batches: group 0 does all of it
+    const int quad = warp & 3, grp = warp >= 16 ? 1 : 0;
+    float* outs_g = outs + grp * O * 128;
+    float* tst = tstage + (grp * 4 + quad) * TST_FLOATS;
     const int pr = quad * 32 + lane;
     const int pl = pl0 + pr;                 // relative to the launch
     const bool pvalid = pl < a.np;
@@ -550,18 +570,22 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
     for (int u = 0; u < nvt; ++u) {
       const int t = u / a.nseg;
       const bool accum = (u % a.nseg) != 0;   // a later K segment of the same column tile: add to what is there
-      tc::mbar_wait(bar_accfull, (uint32_t)(u & 1));
+      const int set = a.dbuf ? (u & 1) : 0, nuse = a.dbuf ? (u >> 1) : u;
+      const uint32_t tmem_main = tmem_base + (uint32_t)(2 * BN * set), tmem_small = tmem_main + (uint32_t)BN;
+      tc::mbar_wait(bar_accfull + 8 * set, (uint32_t)(nuse & 1));
       long long te0 = TCG_CLK();
       tc::tc_fence_after();
       const int n0 = t * BN;
-      if (MODE == MODE_FWD) {
-        fo = n0 / g.Bn; fb = n0 - fo * g.Bn;
-      } else if (MODE == MODE_DKR2) {
+      if (MODE == MODE_DKR2) {
         db = n0 / O;  // BN % O == 0 (checked on the host): every tile starts at o == 0
       }
 #pragma unroll 1
       for (int cb = 0; cb < BN; cb += 32) {
         if (n0 + cb >= a.Ncols) break;   // padding columns of the last tile (warp-uniform): nothing to reduce or store
+        if (MODE == MODE_DKR2 ? grp != 0 : ((cb >> 5) & 1) != grp) continue;
+        if (MODE == MODE_FWD) {          // position of this batch's first column: output o, second-half index b
+          fo = (n0 + cb) / g.Bn; fb = (n0 + cb) - fo * g.Bn;
+        }
         float v[32];
         tc::tmem_ld32(tmem_main + lane_base + (uint32_t)cb, v);
         if (a.passes == 3) {
@@ -577,7 +601,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
           int ncols = a.Ncols - n0 - cb;
           if (BN - cb < ncols) ncols = BN - cb;
           if (ncols > 32) ncols = 32;
-          store_tile(tstage + quad * (32 * 36), v, F16 ? sc1 : 1.f, F16 ? sc2 : 1.f,
+          store_tile(tst, v, F16 ? sc1 : 1.f, F16 ? sc2 : 1.f,
                      a.out + (long long)(u % a.nseg) * a.seg_stride + (long long)row0 * a.ldc + n0 + cb, a.ldc, a.np - row0, ncols,
                      false, lane);
         } else if (MODE == MODE_FWD) {
@@ -586,7 +610,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
             int ncols = a.Ncols - n0 - cb;
             if (BN - cb < ncols) ncols = BN - cb;
             if (ncols > 32) ncols = 32;
-            store_tile(tstage + quad * (32 * 36), v, F16 ? sc1 : 1.f, F16 ? sc2 : 1.f,
+            store_tile(tst, v, F16 ? sc1 : 1.f, F16 ? sc2 : 1.f,
                        a.tsave + (pt0 + quad * 32) * (long long)a.Ncols + n0 + cb, a.Ncols, a.np - row0, ncols, accum, lane);
           }
           // columns cb..cb+31 are b = fb, fb+1, ... (wrapping to the next o at b == Bn; Bn >= 32: at most one wrap)
@@ -609,7 +633,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
               if (i < wrap) s += c; else s2 += c;
             }
             if (wrap <= nvalid) {
-              outs[fo * 128 + pr] += s;
+              outs_g[fo * 128 + pr] += s;
               s = s2; ++fo; fb = fb + nvalid - g.Bn;
             } else {
               fb += nvalid;
@@ -622,12 +646,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
               if (i < nvalid) {
                 s = fmaf(v[i], kr[i], s);
                 if (++fb == g.Bn) {
-                  outs[fo * 128 + pr] += s;
+                  outs_g[fo * 128 + pr] += s;
                   s = 0.f; fb = 0; ++fo;
                 }
               }
             }
           }
+          if (fo < O) outs_g[fo * 128 + pr] += s;   // partial sum of this batch (the next batch recomputes its position)
+          s = 0.f;
         } else {  // MODE_DKR2
           const uint4* cp = (const uint4*)(eidx + cb);
           uint32_t id[32];
@@ -657,24 +683,26 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
           }
         }
       }
-      if (MODE == MODE_FWD) {  // flush the partial sum of this tile (the next tile recomputes its position)
-        if (fo < O) outs[fo * 128 + pr] += s;
-        s = 0.f;
-      }
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(bar_accempty);
+      if (lane == 0) tc::mbar_arrive(bar_accempty + 8 * set);
       dbg_epi += TCG_CLK() - te0;
     }
     if (a.dbg && warp == 8 && lane == 0) a.dbg[(long long)blockIdx.x * 8 + 7] = dbg_epi;
-    if (MODE == MODE_FWD && pvalid) {
-      float* orow = a.out + (pt0 + pr) * O;
-      for (int o = 0; o < O; ++o) orow[o] = F16 ? outs[o * 128 + pr] * fsc1 * fsc2 : outs[o * 128 + pr];
+    if (MODE == MODE_FWD) {
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * G_EPI_WARPS) : "memory");   // both groups' partial sums are in shared memory
+      if (grp == 0 && pvalid) {
+        float* orow = a.out + (pt0 + pr) * O;
+        for (int o = 0; o < O; ++o) {
+          const float r1 = outs[o * 128 + pr] + outs[(O + o) * 128 + pr];
+          orow[o] = F16 ? r1 * fsc1 * fsc2 : r1;
+        }
+      }
     }
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 2) tc::tmem_dealloc(tmem_main, TMEM_COLS);
+  if (warp == 2) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -727,12 +755,25 @@ inline size_t gemm_fixed_smem(const EpsGeom& g, const GemmShape& s, int mode) {
   const int nE = (mode == MODE_FWD) ? (g.BH + g.BL) : (mode == MODE_DKR2 ? g.O : 0);
   const size_t ktab = (size_t)(s.KH + 1 + s.KLb + s.GP);
   const size_t neidx = (mode == MODE_FWD) ? (size_t)g.Bn + (g.Bn > 32 ? g.Bn : 32) : (mode == MODE_DKR2 ? (size_t)MAX_BN : 0);
-  return 1024 + (ktab + nE + (mode == MODE_FWD ? g.O : 0)) * 128 * 4 + ((size_t)s.Hpad + neidx + 4) * 4 + 256 * 4 +
-         (mode == MODE_DKR2 ? 0 : 4 * 32 * 36 * 4) + (2 * MAX_BSTAGES + 2 * ASTAGES + 2) * 8 + 16;
+  return 1024 + (ktab + nE + (mode == MODE_FWD ? 2 * g.O : 0)) * 128 * 4 + ((size_t)s.Hpad + neidx + 4) * 4 + 256 * 4 +
+         (mode == MODE_DKR2 ? 0 : G_EPI_WARPS * TST_FLOATS * 4) + (2 * MAX_BSTAGES + 2 * ASTAGES + 4) * 8 + 16;
 }
 inline size_t bstage_bytes(int BN) { return 2 * (size_t)BN * 128; }   // hi + lo parts, BN rows of 128 bytes
 inline int stage_k(int passes) { return passes == ARITH_F16X3 ? GBK16 : GBK; }
 inline GemmShape shape_auto(const EpsGeom& g, int mode) { return shape_for(g, mode); }
+
+// Two accumulator sets for the forward GEMM when K is shallow: its epilogue (KR2 reduction, the store of T) then costs
+// more than the MMAs of a tile (CIFAR (2, 23 -> 24): 11.0k against 8.6k cycles per 160-column tile, and the T stores of
+// all SMs arrive at HBM in the same burst); alternating sets hide it behind the next tile's MMAs.  The price: tiles of
+// at most 96 columns (4 * BN + 128 <= 512 TMEM columns), i.e. the operand is generated more often, which a deep K does
+// not repay.  DCTN_B200_DBUF_MAXK overrides the K bound (0 = never).
+inline bool gemm_dbuf(const EpsGeom& g, int mode) {
+  if (mode != MODE_FWD) return false;
+  int maxk = 28 * GBK16;
+  if (const char* e = getenv("DCTN_B200_DBUF_MAXK")) maxk = atoi(e);
+  const GemmShape s = shape_auto(g, mode);
+  return s.Kp <= maxk && s.Ncols <= 384;   // few tiles: the extra generation passes stay cheap
+}
 
 // number of shared-memory B stages that fit (0 = does not fit); the setup scratch (x and gout of 128 patches)
 // is aliased onto the stages and must fit too
@@ -757,7 +798,7 @@ inline int pick_bn(const EpsGeom& g, int mode) {
   const GemmShape s = shape_auto(g, mode);
   int best = 0;
   long long best_cost = 0;
-  for (int bn = MAX_BN; bn >= 64; bn -= 16) {
+  for (int bn = gemm_dbuf(g, mode) ? 96 : MAX_BN; bn >= 64; bn -= 16) {
     if (mode == MODE_DKR2 && bn % g.O != 0) continue;
     if (pick_bstages(g, mode, bn) == 0) continue;
     long long cost = (long long)((s.Ncols + bn - 1) / bn) * bn;
@@ -814,6 +855,7 @@ int run_gemm(const EpsGeom& g, int mode, int BN, const float* x, const float* go
   // fp16 stages hold 64 K-values (4 MMAs), tf32 stages 32 (also 4 MMAs): the same number of accumulation steps
   a.kseg = tc::seg_stages(a.nk); a.nseg = (a.nk + a.kseg - 1) / a.kseg;
   a.seg_stride = seg_stride;
+  a.dbuf = gemm_dbuf(g, mode) ? 1 : 0;
   a.packed = packed; a.BN = BN; a.bstages = pick_bstages(g, mode, BN); a.passes = f16 ? 3 : passes; a.out = out; a.ldc = ldc;
   a.core_absmax = absmax;
   a.tsave = tsave;
