@@ -1039,6 +1039,59 @@ __global__ void __launch_bounds__(256) dkr2_from_saved_scalar_kernel(const float
 //   Whi[eh]  = sum_el dKR2[eh*BL + el] * TL[el],   Wlo[el] = sum_eh dKR2[eh*BL + el] * TH[eh]       (stage 1)
 //   d x_j[q] = sum_{e: digit_t(e) = q} W[e] * prod_{t' != t} x_{j'}[digit_t'(e)]                       (stage 2)
 // everything after the read of T lives in the warp's slice of shared memory; dxp[p][j][q] for the factors j >= m.
+// Division-free digit arithmetic for the per-patch leave-one-out code: qd[e] = e / Q for e < nqd, built once per CTA.
+// The digit loops of these kernels divided by the run-time Q two or three times per table entry and factor (~40
+// instructions each): at K = 3, Q = 3 the per-group stage alone was ~3000 instructions per patch.
+__host__ __device__ __forceinline__ int loo_nqd(int EH, int EL, int nfq, int extra) {
+  int m = EH > EL ? EH : EL;
+  if (nfq > m) m = nfq;
+  if (extra > m) m = extra;
+  return m + 1;
+}
+__device__ __forceinline__ void build_qd(int* qd, int nqd, int Q) {
+  for (int e = threadIdx.x; e < nqd; e += blockDim.x) qd[e] = e / Q;
+  __syncthreads();
+}
+// prod over the digits u of entry e (digit 0 slowest) of xg[u*Q + digit_u], leaving out position `skip` (-1: none)
+__device__ __forceinline__ float kr_prod(const float* xg, const int* qd, int Q, int cnt, int e, int skip) {
+  float v = 1.f;
+  for (int u = cnt - 1; u >= 0; --u) {
+    const int e1 = qd[e], d = e - e1 * Q;
+    e = e1;
+    if (u != skip) v *= xg[u * Q + d];
+  }
+  return v;
+}
+// per-group stage of the leave-one-out contraction for one warp:
+//   d x_t[q] = sum_{e: digit_tt(e) = q} W[e] * prod_{u != tt} x_u[digit_u(e)],  W = wH (hi group) | wL (lo group)
+__device__ __forceinline__ void loo_group_stage(const float* wH, const float* wL, const float* xs, const int* qd, int Q, int cnth,
+                                                int cntl, int EH, int EL, int lane, float* __restrict__ dst /* [nf][Q] */) {
+  const int nf = cnth + cntl;
+  for (int item = lane; item < nf * Q; item += 32) {
+    const int t = qd[item], q = item - t * Q;
+    const bool in_hi = t < cnth;
+    const int cnt = in_hi ? cnth : cntl, tt = in_hi ? t : t - cnth;
+    const float* w = in_hi ? wH : wL;
+    const float* xg = xs + (in_hi ? 0 : cnth) * Q;
+    int dstride = 1, npre = 1;
+    for (int u = 0; u < cnt - 1 - tt; ++u) dstride *= Q;
+    for (int u = 0; u < tt; ++u) npre *= Q;
+    float sacc = 0.f;
+    for (int hp = 0; hp < npre; ++hp) {
+      const int e0 = (hp * Q + q) * dstride;
+      for (int lp = 0; lp < dstride; ++lp) sacc = fmaf(w[e0 + lp], kr_prod(xg, qd, Q, cnt, e0 + lp, tt), sacc);
+    }
+    dst[item] = sacc;
+  }
+}
+// patch_origin with 32-bit divisions (the tcgen05 paths require P < 2^31)
+__device__ __forceinline__ long long patch_origin32(const EpsGeom& g, long long p) {
+  const unsigned hw = (unsigned)(g.Ho * g.Wo), pu = (unsigned)p;
+  const unsigned b = pu / hw, r = pu - b * hw;
+  const unsigned h = r / (unsigned)g.Wo, w = r - h * (unsigned)g.Wo;
+  return (((long long)b * g.H + h) * (long long)g.W + w) * g.Q;
+}
+
 constexpr int LOO2_WARPS = 8;
 template <bool VEC>
 __global__ void __launch_bounds__(32 * LOO2_WARPS) loo2_from_saved_kernel(EpsGeom g, const float* __restrict__ x, const float* __restrict__ T,
@@ -1049,6 +1102,9 @@ __global__ void __launch_bounds__(32 * LOO2_WARPS) loo2_from_saved_kernel(EpsGeo
   const int BLS = BL | 1;                                   // padded row stride of the dKR2 matrix [BH][BL]
   const int per_warp = BH * BLS + 2 * (BH + BL) + nf * Q + O;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nqd = loo_nqd(BH, BL, nf * Q, Bn);
+  int* qd = (int*)(l2_smem + LOO2_WARPS * per_warp);
+  build_qd(qd, nqd, Q);
   float* dk = l2_smem + warp * per_warp;
   float* tH = dk + BH * BLS;   // [BH] then tL [BL]
   float* tL = tH + BH;
@@ -1058,21 +1114,16 @@ __global__ void __launch_bounds__(32 * LOO2_WARPS) loo2_from_saved_kernel(EpsGeo
   float* gs = xs + nf * Q;
   for (long long pl = (long long)blockIdx.x * LOO2_WARPS + warp; pl < np; pl += (long long)gridDim.x * LOO2_WARPS) {
     const long long p = p0 + pl;
-    const long long o0 = patch_origin(g, p);
-    for (int i = lane; i < nf * Q; i += 32) xs[i] = __ldg(&x[o0 + g.foff[g.m + i / Q] + i % Q]);
+    const long long o0 = patch_origin32(g, p);
+    for (int i = lane; i < nf * Q; i += 32) {
+      const int j = qd[i];
+      xs[i] = __ldg(&x[o0 + g.foff[g.m + j] + (i - j * Q)]);
+    }
     for (int o = lane; o < O; o += 32) gs[o] = __ldg(&gout[p * O + o]);
     __syncwarp();
     for (int e = lane; e < BH + BL; e += 32) {
       const bool hi = e < BH;
-      int ee = hi ? e : e - BH;
-      const int j0 = hi ? 0 : g.b_nh, cnt = hi ? g.b_nh : g.b_nl;
-      float v = 1.f;
-      for (int u = cnt - 1; u >= 0; --u) {
-        const int d = ee % Q;
-        ee /= Q;
-        v *= xs[(j0 + u) * Q + d];
-      }
-      tH[e] = v;   // tL follows tH
+      tH[e] = kr_prod(xs + (hi ? 0 : g.b_nh) * Q, qd, Q, hi ? g.b_nh : g.b_nl, hi ? e : e - BH, -1);   // tL follows tH
     }
     const float* trow = T + p * (long long)Bn * O;
     if (VEC) {     // Bn % 4 == 0 and BL % 4 == 0: four consecutive b stay in one row of the [BH][BL] matrix
@@ -1112,10 +1163,32 @@ __global__ void __launch_bounds__(32 * LOO2_WARPS) loo2_from_saved_kernel(EpsGeo
         }
       }
     } else {
-      for (int b = lane; b < Bn; b += 32) {
-        float sacc = 0.f;
-        for (int o = 0; o < O; ++o) sacc = fmaf(__ldcs(trow + (long long)o * Bn + b), gs[o], sacc);
-        dk[(b / BL) * BLS + b % BL] = sacc;
+      // two chunks of 32 b and eight outputs per pass, all sixteen loads issued before the first use: a loop that
+      // consumes each load at once waits one HBM latency per element (K = 3, Q = 3: 18 dependent loads per patch,
+      // 657 us for 657 MB at B = 512)
+      for (int b = lane; b < Bn; b += 64) {
+        const bool two = b + 32 < Bn;
+        float s0 = 0.f, s1 = 0.f;
+        for (int o0 = 0; o0 < O; o0 += 8) {
+          float va[8], vb[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            va[k] = vb[k] = 0.f;
+            if (o0 + k < O) {
+              const float* src = trow + (long long)(o0 + k) * Bn + b;
+              va[k] = __ldcs(src);
+              if (two) vb[k] = __ldcs(src + 32);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float gv = (o0 + k < O) ? gs[o0 + k] : 0.f;
+            s0 = fmaf(va[k], gv, s0);
+            s1 = fmaf(vb[k], gv, s1);
+          }
+        }
+        dk[(b / BL) * BLS + b % BL] = s0;
+        if (two) dk[((b + 32) / BL) * BLS + (b + 32) % BL] = s1;
       }
     }
     __syncwarp();
@@ -1130,30 +1203,7 @@ __global__ void __launch_bounds__(32 * LOO2_WARPS) loo2_from_saved_kernel(EpsGeo
       wL[el] = sacc;
     }
     __syncwarp();
-    for (int item = lane; item < nf * Q; item += 32) {
-      const int t = item / Q, q = item - t * Q;
-      const bool in_hi = t < g.b_nh;
-      const int cnt = in_hi ? g.b_nh : g.b_nl, tt = in_hi ? t : t - g.b_nh, Eg = in_hi ? BH : BL;
-      const float* w = in_hi ? wH : wL;
-      const float* xg = xs + (in_hi ? 0 : g.b_nh) * Q;
-      int dstride = 1;
-      for (int u = 0; u < cnt - 1 - tt; ++u) dstride *= Q;
-      float sacc = 0.f;
-      const int others = Eg / Q;
-      for (int oe = 0; oe < others; ++oe) {
-        const int lo_part = oe % dstride, hi_part = oe / dstride;
-        const int e = (hi_part * Q + q) * dstride + lo_part;
-        float v = w[e];
-        int ee = e;
-        for (int u = cnt - 1; u >= 0; --u) {
-          const int d = ee % Q;
-          ee /= Q;
-          if (u != tt) v *= xg[u * Q + d];
-        }
-        sacc += v;
-      }
-      dxp[(p * g.n + g.m + t) * Q + q] = sacc;
-    }
+    loo_group_stage(wH, wL, xs, qd, Q, g.b_nh, g.b_nl, BH, BL, lane, dxp + (p * g.n + g.m) * Q);
     __syncwarp();
   }
 }
@@ -1206,8 +1256,122 @@ inline int launch_loo_groups(const EpsGeom& g, const float* x, const float* W, i
   DCTN_CUDA_CHECK_RET(cudaGetLastError());
   return 0;
 }
+// First-half leave-one-out for the generic GEMM path: dKR1 (np x A, possibly as several K-segment slices that are summed
+// here, in slice order) -> d x_j for the factors of the first half, one WARP per patch.
+//   Whi[eh] = sum_el dKR1[eh*EL + el] * TL[el],   Wlo[el] = sum_eh dKR1[eh*EL + el] * TH[eh],   then the per-group stage.
+// A lane owns ROWS eh = lane, lane + 32, ... of the [EH][EL] matrix: Whi[eh] is a private sum, Wlo[el] a private partial
+// per lane (EL <= ELB registers) reduced across the warp once per patch — three instructions per matrix element and no
+// per-element index arithmetic.  The 32 rows a warp reads together are contiguous (32 * EL floats): every sector that
+// the first load of a row brings into L1 is used by the following ones.  Replaces sum_slices_kernel +
+// loo_staged_kernel, whose staging loop spent four integer divisions per element (CIFAR (2, 12 -> 24): 522 us for a
+// 425 MB matrix; a first warp-per-patch version with a segmented shuffle reduction per row issued 3000 instructions per
+// patch at K = 3, Q = 3 — profiles/r02f_loo_ncu.txt).
+constexpr int LOO1_WARPS = 8;
+template <int ELB>
+__global__ void __launch_bounds__(32 * LOO1_WARPS) loo1_rows_kernel(EpsGeom g, const float* __restrict__ x, const float* __restrict__ dkr,
+                                                                    long long slice_stride, int nslices, long long p0, int np,
+                                                                    float* __restrict__ dxp) {
+  extern __shared__ float l1_smem[];
+  const int Q = g.Q, EH = g.AH, EL = g.AL, cnth = g.a_nh, cntl = g.a_nl, nf = g.m, E = g.A;
+  const int per_warp = 2 * EH + 2 * EL + nf * Q;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* qd = (int*)(l1_smem + LOO1_WARPS * per_warp);
+  build_qd(qd, loo_nqd(EH, EL, nf * Q, 0), Q);
+  float* tH = l1_smem + warp * per_warp;
+  float* tL = tH + EH;
+  float* wH = tL + EL;
+  float* wL = wH + EH;
+  float* xs = wL + EL;
+  for (long long pl = (long long)blockIdx.x * LOO1_WARPS + warp; pl < np; pl += (long long)gridDim.x * LOO1_WARPS) {
+    const long long p = p0 + pl;
+    const long long org = patch_origin32(g, p);
+    for (int i = lane; i < nf * Q; i += 32) {
+      const int j = qd[i];
+      xs[i] = __ldg(&x[org + g.foff[j] + (i - j * Q)]);
+    }
+    __syncwarp();
+    for (int e = lane; e < EH; e += 32) tH[e] = kr_prod(xs, qd, Q, cnth, e, -1);
+    for (int e = lane; e < EL; e += 32) tL[e] = kr_prod(xs + cnth * Q, qd, Q, cntl, e, -1);
+    __syncwarp();
+    float tlr[ELB], accl[ELB];
+#pragma unroll
+    for (int el = 0; el < ELB; ++el) {
+      tlr[el] = el < EL ? tL[el] : 0.f;
+      accl[el] = 0.f;
+    }
+    const float* mat = dkr + pl * (long long)E;
+    for (int eh0 = 0; eh0 < EH; eh0 += 32) {
+      const int eh = eh0 + lane;
+      const bool valid = eh < EH;
+      const float* rowp = mat + (long long)(valid ? eh : 0) * EL;
+      float d[ELB];
+#pragma unroll
+      for (int el = 0; el < ELB; ++el) d[el] = (valid && el < EL) ? __ldg(rowp + el) : 0.f;
+      for (int sl = 1; sl < nslices; ++sl) {
+        const float* r2 = rowp + (long long)sl * slice_stride;
+        float t[ELB];
+#pragma unroll
+        for (int el = 0; el < ELB; ++el) t[el] = (valid && el < EL) ? __ldg(r2 + el) : 0.f;
+#pragma unroll
+        for (int el = 0; el < ELB; ++el) d[el] += t[el];
+      }
+      const float th = valid ? tH[eh] : 0.f;
+      float whi = 0.f;
+#pragma unroll
+      for (int el = 0; el < ELB; ++el) {
+        whi = fmaf(d[el], tlr[el], whi);
+        accl[el] = fmaf(d[el], th, accl[el]);
+      }
+      if (valid) wH[eh] = whi;
+    }
+#pragma unroll
+    for (int el = 0; el < ELB; ++el) {
+      if (el < EL) {   // warp-uniform
+        float v = accl[el];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) wL[el] = v;
+      }
+    }
+    __syncwarp();
+    loo_group_stage(wH, wL, xs, qd, Q, cnth, cntl, EH, EL, lane, dxp + p * g.n * Q);
+    __syncwarp();
+  }
+}
+inline size_t loo1_smem(const EpsGeom& g) {
+  return ((size_t)LOO1_WARPS * (size_t)(2 * g.AH + 2 * g.AL + g.m * g.Q) + (size_t)loo_nqd(g.AH, g.AL, g.m * g.Q, 0)) * sizeof(float);
+}
+inline bool loo1_rows_ok(const EpsGeom& g) {
+  if (const char* e = getenv("DCTN_B200_LOO1")) return e[0] == '1' && g.AL <= 32 && loo1_smem(g) <= 48 * 1024;
+  // long rows only: the per-patch fixed cost of a warp (origin, tables, the per-group stage on 15-40 lanes) is ~2000
+  // instructions — K = 3, Q = 3 (A = 243): 946 us against 676 us of the staged kernel; CIFAR (2, 23 -> 24) (A = 529, nine
+  // slices): 341 against 312 us of sum_slices + staged; CIFAR (2, 12 -> 24) (A = 1728): 222 against 522 us
+  return g.A >= 1024 && g.AL >= 1 && g.AL <= 32 && loo1_smem(g) <= 48 * 1024;
+}
+template <int ELB>
+int launch_loo1_rows_inst(const EpsGeom& g, const float* x, const float* dkr, long long slice_stride, int nslices, long long p0, int np,
+                          float* dxp, cudaStream_t st) {
+  int blocks = (np + LOO1_WARPS - 1) / LOO1_WARPS;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  loo1_rows_kernel<ELB><<<blocks, 32 * LOO1_WARPS, loo1_smem(g), st>>>(g, x, dkr, slice_stride, nslices, p0, np, dxp);
+  dctn_count_launch();
+  DCTN_CUDA_CHECK_RET(cudaGetLastError());
+  return 0;
+}
+inline int launch_loo1_rows(const EpsGeom& g, const float* x, const float* dkr, long long slice_stride, int nslices, long long p0, int np,
+                            float* dxp, cudaStream_t st) {
+  const int EL = g.AL;
+  if (EL <= 4) return launch_loo1_rows_inst<4>(g, x, dkr, slice_stride, nslices, p0, np, dxp, st);
+  if (EL <= 8) return launch_loo1_rows_inst<8>(g, x, dkr, slice_stride, nslices, p0, np, dxp, st);
+  if (EL <= 12) return launch_loo1_rows_inst<12>(g, x, dkr, slice_stride, nslices, p0, np, dxp, st);
+  if (EL <= 16) return launch_loo1_rows_inst<16>(g, x, dkr, slice_stride, nslices, p0, np, dxp, st);
+  if (EL <= 24) return launch_loo1_rows_inst<24>(g, x, dkr, slice_stride, nslices, p0, np, dxp, st);
+  return launch_loo1_rows_inst<32>(g, x, dkr, slice_stride, nslices, p0, np, dxp, st);
+}
+
 inline size_t loo2_smem(const EpsGeom& g) {
-  return (size_t)LOO2_WARPS * (size_t)(g.BH * (g.BL | 1) + 2 * (g.BH + g.BL) + (g.n - g.m) * g.Q + g.O) * sizeof(float);
+  return ((size_t)LOO2_WARPS * (size_t)(g.BH * (g.BL | 1) + 2 * (g.BH + g.BL) + (g.n - g.m) * g.Q + g.O) +
+          (size_t)loo_nqd(g.BH, g.BL, (g.n - g.m) * g.Q, g.Bn)) * sizeof(float);
 }
 }  // namespace
 
@@ -1259,6 +1423,9 @@ static int backward_input_impl(const EpsGeom& g, const float* x, const float* co
       if (fast1) rc = tcfast_gemm(g, 0, x, gout, packed1, absmax, p0, np, dkr1, g.A, nullptr, st);
       else rc = run_gemm(g, MODE_STORE, BN1, x, gout, packed1, p0, np, dkr1, g.A, passes, st, absmax, nullptr, (long long)pc * g.A);
       if (rc) return rc;
+      if (!fast1 && loo1_rows_ok(g)) {   // slices summed and both leave-one-out stages in one pass over dKR1
+        if ((rc = launch_loo1_rows(g, x, dkr1, (long long)pc * g.A, nslice1, p0, np, dxp, st))) return rc;
+      } else {
       if (nslice1 > 1) {
         const long long count = (long long)np * g.A;
         int blocks = (int)((count + 255) / 256);
@@ -1268,6 +1435,7 @@ static int backward_input_impl(const EpsGeom& g, const float* x, const float* co
         DCTN_CUDA_CHECK_RET(cudaGetLastError());
       }
       if ((rc = launch_loo<float>(g, x, dkr1, p0, np, 0, dxp, st))) return rc;
+      }
     }
     if (fused2) {
       int blocks = (np + LOO2_WARPS - 1) / LOO2_WARPS;
