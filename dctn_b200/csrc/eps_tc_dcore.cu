@@ -120,6 +120,13 @@ __global__ void __launch_bounds__(256) build_tables16_kernel(EpsGeom g, const fl
   float* tlo = wp + CH;            // [BL][64]: second-half lo group, evaluated once and reused for every o
   float* tal = tlo + g.BL * CH;    // [AL][64]: first-half lo group
   float* tbh = tal + g.AL * CH;    // [BH][64]: second-half hi group times the patch weight
+  int* qd = (int*)(tbh + g.BH * CH);   // qd[e] = e / Q for e below the largest group size: digit walks without divisions
+  {
+    int nqd = g.AH > g.AL ? g.AH : g.AL;
+    if (g.BH > nqd) nqd = g.BH;
+    if (g.BL > nqd) nqd = g.BL;
+    for (int e = threadIdx.x; e < nqd; e += blockDim.x) qd[e] = e / Q;
+  }
   const long long p0 = (long long)blockIdx.x * CH;
   const int lq = (Q & (Q - 1)) == 0 ? 31 - __clz(Q) : -1;      // log2(Q) when Q is a power of two: digits by shifts
   {
@@ -158,7 +165,7 @@ __global__ void __launch_bounds__(256) build_tables16_kernel(EpsGeom g, const fl
     for (int u = cnt - 1; u >= 0; --u) {
       int d;
       if (lq >= 0) { d = e & (Q - 1); e >>= lq; }
-      else { d = e % Q; e /= Q; }
+      else { const int e1 = qd[e]; d = e - e1 * Q; e = e1; }
       v *= xs[((j0 + u) * Q + d) * CH + i];
     }
     return v;
@@ -619,7 +626,10 @@ inline size_t table_floats(const EpsGeom& g) {
   return (size_t)((g.P + CH - 1) / CH) * (size_t)(g.AH + (size_t)g.BH * g.AL) * TS_;
 }
 inline size_t table_kernel_smem(const EpsGeom& g) {
-  return (size_t)((g.n * g.Q + g.O + g.BL + g.AL + g.BH) * CH + CH) * sizeof(float);
+  int nqd = g.AH > g.AL ? g.AH : g.AL;
+  if (g.BH > nqd) nqd = g.BH;
+  if (g.BL > nqd) nqd = g.BL;
+  return (size_t)((g.n * g.Q + g.O + g.BL + g.AL + g.BH) * CH + CH + nqd) * sizeof(float);
 }
 inline size_t bimg_words(const EpsGeom& g, int NT, int ntile) { return (size_t)((g.P + CH - 1) / CH) * (size_t)ntile * 2 * NT * 32; }
 

@@ -185,6 +185,37 @@ def test_tcgen05_generic_q_layers_vs_oracle(shape):
     assert rel_err(xd.grad, want_dx) <= 1e-5
 
 
+@pytest.mark.parametrize("shape,force", [((5, 32, 32, 13, 2, 8), False), ((3, 30, 30, 5, 3, 4), False), ((6, 31, 31, 6, 2, 24), True),
+                                         ((5, 32, 32, 23, 2, 24), True), ((7, 28, 28, 3, 3, 5), True)])
+def test_first_half_leave_one_out_rows_kernel_vs_oracle(shape, force, monkeypatch):
+    """Input gradient of generic-Q layers through the warp-per-patch first-half leave-one-out kernel (loo1_rows_kernel) in
+    its register-block instantiations: Q = 13 (lo group of 13 -> 16 registers) and K = 3, Q = 5 (25 -> 32) select it by
+    themselves (A >= 1024); DCTN_B200_LOO1=1 forces it for Q = 6 (8 registers), Q = 23 (24, nine K-segment slices summed
+    in the kernel) and K = 3, Q = 3 (12, 27 rows)."""
+    from dctn_b200 import _lib
+    from dctn_b200.eps import eps, kernel_families
+
+    if force:
+        monkeypatch.setenv("DCTN_B200_LOO1", "1")
+    B, H, W, Q, K, Oq = shape
+    gen = torch.Generator().manual_seed(171 + Q)
+    n = K * K
+    x = (torch.randn(1, B, H, W, Q, generator=gen, dtype=torch.float64) * 0.8).float()
+    core = (torch.randn(*(Q,) * n, Oq, generator=gen, dtype=torch.float64) * Q ** (-n / 2)).float()
+    gout = torch.randn(B, H - K + 1, W - K + 1, Oq, generator=gen, dtype=torch.float64).float()
+    c = core.to(DEV).requires_grad_(True)
+    xd = x.to(DEV).requires_grad_(True)
+    fams = kernel_families(c, xd)
+    assert fams["backward_input"] == _lib.FAMILY_TCGEN05, fams
+    out = eps(c, xd)
+    out.backward(gout.to(DEV))
+    want = O.eps_4step(core.double(), x.double())
+    want_dc, want_dx = O.eps_grads(core.double(), x.double(), gout.double())
+    assert rel_err(out, want) <= 1e-5
+    assert rel_err(c.grad, want_dc) <= 1e-5
+    assert rel_err(xd.grad, want_dx) <= 1e-5
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 def test_eps_module_forward_backward(dtype):
     """EPS(nn.Module) (dctn/eps.py:73-96): parameter `core`, He-style init std, forward = eps(core, input)."""
