@@ -442,6 +442,12 @@ __global__ void __launch_bounds__(NTHREADS) loo_staged_kernel(EpsGeom g, const T
   T* wH = tL + LPT * EL;                   // [LPT][EH]
   T* wL = wH + LPT * EH;                   // [LPT][EL]
   T* xs = wL + LPT * EL;
+  int* qd = reinterpret_cast<int*>(xs + LPT * xs_stride);   // qd[e] = e / Q, e < max(EH, EL, nf*Q) + 1
+  {
+    int nqd = EH > EL ? EH : EL;
+    if (nf * Q > nqd) nqd = nf * Q;
+    for (int e = threadIdx.x; e <= nqd; e += NTHREADS) qd[e] = e / Q;   // visible after the barrier below
+  }
   const int pl0 = blockIdx.x * LPT;
   const int npl = (np - pl0 < LPT) ? (np - pl0) : LPT;
   // (1) stage the rows: contiguous npl*E elements of dkr starting at pl0*E
@@ -459,10 +465,15 @@ __global__ void __launch_bounds__(NTHREADS) loo_staged_kernel(EpsGeom g, const T
           const double2 f = *reinterpret_cast<const double2*>(src + i);
           v[0] = f.x; v[1] = f.y;
         }
+        // E % V == 0: the V elements stay inside one patch; one (patch, row, column) decode per vector, then a walk
+        const int pl = i / E, e = i - pl * E;
+        const int eh = e / EL;
+        int el = e - eh * EL;
+        T* dst = M + (pl * EH + eh) * ELS + el;
 #pragma unroll
         for (int u = 0; u < V; ++u) {
-          const int e = (i + u) % E, pl = (i + u) / E;
-          M[(pl * EH + e / EL) * ELS + e % EL] = v[u];
+          *dst++ = v[u];
+          if (++el == EL) { el = 0; dst += ELS - EL; }
         }
       }
     } else {
@@ -498,32 +509,33 @@ __global__ void __launch_bounds__(NTHREADS) loo_staged_kernel(EpsGeom g, const T
     wH[item] = s;
   }
   __syncthreads();
+  // per-group stage without divisions: qd[e] = e / Q (built above), nested walks over the digits before / after position tt
   for (int item = threadIdx.x; item < LPT * nf * Q; item += NTHREADS) {
     const int pl = item / (nf * Q);
     const int r = item - pl * nf * Q;
-    const int t = r / Q, q = r - t * Q;
+    const int t = qd[r], q = r - t * Q;
     if (pl >= npl) continue;
     const bool in_hi = t < cnth;
     const int cnt = in_hi ? cnth : cntl;
     const int tt = in_hi ? t : t - cnth;
-    const int Eg = in_hi ? EH : EL;
     const T* w = (in_hi ? wH + pl * EH : wL + pl * EL);
     const T* xr = xs + pl * xs_stride + (in_hi ? 0 : cnth) * Q;
-    int dstride = 1;
+    int dstride = 1, npre = 1;
     for (int u = 0; u < cnt - 1 - tt; ++u) dstride *= Q;
+    for (int u = 0; u < tt; ++u) npre *= Q;
     T s = T(0);
-    const int others = Eg / Q;
-    for (int oe = 0; oe < others; ++oe) {
-      const int lo_part = oe % dstride, hi_part = oe / dstride;
-      const int e = (hi_part * Q + q) * dstride + lo_part;
-      T v = w[e];
-      int ee = e;
-      for (int u = cnt - 1; u >= 0; --u) {
-        const int d = ee % Q;
-        ee /= Q;
-        if (u != tt) v *= xr[u * Q + d];
+    for (int hp = 0; hp < npre; ++hp) {
+      const int e0 = (hp * Q + q) * dstride;
+      for (int lp = 0; lp < dstride; ++lp) {
+        T v = w[e0 + lp];
+        int ee = e0 + lp;
+        for (int u = cnt - 1; u >= 0; --u) {
+          const int e1 = qd[ee], d = ee - e1 * Q;
+          ee = e1;
+          if (u != tt) v *= xr[u * Q + d];
+        }
+        s += v;
       }
-      s += v;
     }
     dxp[((p0 + pl0 + pl) * g.n + (j0 + t)) * Q + q] = s;
   }
@@ -669,7 +681,9 @@ int launch_loo(const EpsGeom& g, const T* x, const T* dkr, long long p0, int np,
   const int EH = half ? g.BH : g.AH, EL = half ? g.BL : g.AL;
   const int nf = cnth + cntl;
   {
-    const size_t ssm = ((size_t)LPT * EH * (EL | 1) + (size_t)LPT * 2 * (EH + EL) + (size_t)LPT * ((nf * g.Q) | 1)) * sizeof(T) + 16;
+    const int nqd = (EH > EL ? (EH > nf * g.Q ? EH : nf * g.Q) : (EL > nf * g.Q ? EL : nf * g.Q)) + 1;
+    const size_t ssm = ((size_t)LPT * EH * (EL | 1) + (size_t)LPT * 2 * (EH + EL) + (size_t)LPT * ((nf * g.Q) | 1)) * sizeof(T) +
+                       (size_t)nqd * sizeof(int) + 16;
     if (ssm <= 100 * 1024) {   // at least two CTAs per SM
       DCTN_CUDA_CHECK_RET(cudaFuncSetAttribute(loo_staged_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
       loo_staged_kernel<T><<<(np + LPT - 1) / LPT, NTHREADS, ssm, st>>>(g, x, dkr, p0, np, j0, cnth, EH, cntl, EL, dxp);
