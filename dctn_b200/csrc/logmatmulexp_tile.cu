@@ -31,6 +31,7 @@ namespace {
 
 constexpr int LT = 32;          // output tile LT x LT, 256 threads, 2 x 2 outputs per thread
 constexpr int LTH = 256;
+static_assert(LT == 32, "the staging loops map one lane to one tile column");
 constexpr size_t LME_SMEM_LIMIT = 200 * 1024;
 
 template <typename T> struct Lim;
@@ -42,6 +43,16 @@ __device__ __forceinline__ float xlog(float v) { return logf(v); }
 __device__ __forceinline__ double xlog(double v) { return log(v); }
 template <typename T> __device__ __forceinline__ T ninf() { return -(T)INFINITY; }
 template <typename T> __device__ __forceinline__ bool finite_(T v) { return v - v == T(0); }
+// One element global -> shared without a register round trip (LDGSTS): a CTA stages its whole operand tiles with every
+// copy in flight at once and waits ONCE — the plain load/store loops paid one HBM latency per handful of elements
+// (27 us for a 256 x 256 product on 64 CTAs; 17.8 us with the asynchronous copies, profiles/r02g_cfg5_launches.txt).
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(T* dst_smem, const T* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  if (sizeof(T) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------------- forward
 template <typename T>
@@ -60,14 +71,23 @@ __global__ void __launch_bounds__(LTH) lme_tile_fwd_kernel(const T* __restrict__
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int t0 = blockIdx.y * LT, i0 = blockIdx.x * LT;
   if (tid == 0) { s_unsafe = 0; s_badA = 0; s_badB = 0; }
-  for (int idx = tid; idx < LT * R; idx += LTH) {
-    const int tl = idx / R, r = idx - tl * R;
-    As[tl * RP + r] = (t0 + tl < Th) ? A[(long long)(t0 + tl) * R + r] : ninf<T>();
+  // a warp takes whole rows (A: LT/8 rows of R elements, B: R/8 rows of LT = 32 elements): coalesced, no index division
+  for (int tl = warp; tl < LT; tl += LTH / 32) {
+    const bool rowok = t0 + tl < Th;
+    const T* src = A + (long long)(t0 + tl) * R;
+    for (int r = lane; r < R; r += 32) {
+      if (rowok) cp_async_elem(As + tl * RP + r, src + r);
+      else As[tl * RP + r] = ninf<T>();
+    }
   }
-  for (int idx = tid; idx < R * LT; idx += LTH) {
-    const int r = idx / LT, il = idx - r * LT;
-    Bs[idx] = (i0 + il < I) ? B[(long long)r * I + i0 + il] : ninf<T>();
+  {
+    const bool colok = i0 + lane < I;
+    for (int r = warp; r < R; r += LTH / 32) {
+      if (colok) cp_async_elem(Bs + r * LT + lane, B + (long long)r * I + i0 + lane);
+      else Bs[r * LT + lane] = ninf<T>();
+    }
   }
+  cp_async_wait_all();
   __syncthreads();
   // row maxima / finite minima of As: one warp per 4 rows
   for (int tl = warp; tl < LT; tl += LTH / 32) {
@@ -128,10 +148,9 @@ __global__ void __launch_bounds__(LTH) lme_tile_fwd_kernel(const T* __restrict__
   const int ty = tid >> 4, tx = tid & 15;   // outputs (2 ty + u, 2 tx + v)
   T res[2][2];
   if (!exact) {
-    for (int idx = tid; idx < LT * R; idx += LTH) {
-      const int tl = idx / R, r = idx - tl * R;
+    for (int tl = warp; tl < LT; tl += LTH / 32) {
       const T m = mrow[tl];
-      As[tl * RP + r] = (m == ninf<T>()) ? T(0) : xexp(As[tl * RP + r] - m);
+      for (int r = lane; r < R; r += 32) As[tl * RP + r] = (m == ninf<T>()) ? T(0) : xexp(As[tl * RP + r] - m);
     }
     for (int idx = tid; idx < R * LT; idx += LTH) {
       const T n = ncol[idx & (LT - 1)];
@@ -210,21 +229,35 @@ __global__ void __launch_bounds__(LTH) lme_tile_bwd_kernel(const T* __restrict__
     T* Os = Gs + LT * KP;       // [LT][KP]  out (exact only)
     T* Bs = Os + LT * KP;       // [LT][KP]  exp(B - n) (fast) or B (exact)
     const int t0 = blockIdx.y * LT, r0 = blockIdx.x * LT;
-    for (int idx = tid; idx < LT * I; idx += LTH) {
-      const int l = idx / I, i = idx - l * I;
+    const int warp = tid >> 5, lane = tid & 31;
+    // raw gout / out / B rows staged with asynchronous copies (all in flight at once), then transformed in place
+    for (int l = warp; l < LT; l += LTH / 32) {
       const int t = t0 + l, r = r0 + l;
-      T g = T(0), o = T(0), b = ninf<T>();
-      if (t < Th) { g = gout[(long long)t * I + i]; o = out[(long long)t * I + i]; }
-      if (r < R) b = B[(long long)r * I + i];
-      if (!exact) {
-        const T n = colmax[i];
-        const T m = (t < Th) ? rowmax[t] : ninf<T>();
-        g = (g == T(0) || o == ninf<T>()) ? T(0) : g * xexp(m + n - o);
-        b = (n == ninf<T>()) ? T(0) : xexp(b - n);
+      for (int i = lane; i < I; i += 32) {
+        if (t < Th) {
+          cp_async_elem(Gs + l * KP + i, gout + (long long)t * I + i);
+          cp_async_elem(Os + l * KP + i, out + (long long)t * I + i);
+        } else {
+          Gs[l * KP + i] = T(0); Os[l * KP + i] = T(0);
+        }
+        if (r < R) cp_async_elem(Bs + l * KP + i, B + (long long)r * I + i);
+        else Bs[l * KP + i] = ninf<T>();
       }
-      Gs[l * KP + i] = g; Os[l * KP + i] = o; Bs[l * KP + i] = b;
     }
+    cp_async_wait_all();
     __syncthreads();
+    if (!exact) {
+      for (int l = warp; l < LT; l += LTH / 32) {
+        const T m = (t0 + l < Th) ? rowmax[t0 + l] : ninf<T>();
+        for (int i = lane; i < I; i += 32) {
+          const T n = colmax[i];
+          const T g = Gs[l * KP + i], o = Os[l * KP + i], b = Bs[l * KP + i];
+          Gs[l * KP + i] = (g == T(0) || o == ninf<T>()) ? T(0) : g * xexp(m + n - o);
+          Bs[l * KP + i] = (n == ninf<T>()) ? T(0) : xexp(b - n);
+        }
+      }
+      __syncthreads();
+    }
     if (!exact) {
       const T* g0 = Gs + (2 * ty) * KP;
       const T* g1 = g0 + KP;
@@ -266,21 +299,34 @@ __global__ void __launch_bounds__(LTH) lme_tile_bwd_kernel(const T* __restrict__
     T* Gs = As + (size_t)Th * LT;     // [Th][LT]  G (fast) or gout (exact)
     T* Os = Gs + (size_t)Th * LT;     // [Th][LT]  out (exact only)
     const int r0 = blockIdx.y * LT, i0 = blockIdx.x * LT;
-    for (int idx = tid; idx < Th * LT; idx += LTH) {
-      const int t = idx / LT, l = idx - t * LT;
-      const int r = r0 + l, i = i0 + l;
-      T a = ninf<T>(), g = T(0), o = T(0);
-      if (r < R) a = A[(long long)t * R + r];
-      if (i < I) { g = gout[(long long)t * I + i]; o = out[(long long)t * I + i]; }
-      if (!exact) {
-        const T m = rowmax[t];
-        const T n = (i < I) ? colmax[i] : ninf<T>();
-        a = (m == ninf<T>()) ? T(0) : xexp(a - m);
-        g = (g == T(0) || o == ninf<T>()) ? T(0) : g * xexp(m + n - o);
+    const int warp = tid >> 5, lane = tid & 31;   // lane = column l of the tile (LT == 32), a warp takes rows t
+    {
+      const int r = r0 + lane, i = i0 + lane;
+      for (int t = warp; t < Th; t += LTH / 32) {
+        const int idx = t * LT + lane;
+        if (r < R) cp_async_elem(As + idx, A + (long long)t * R + r);
+        else As[idx] = ninf<T>();
+        if (i < I) {
+          cp_async_elem(Gs + idx, gout + (long long)t * I + i);
+          cp_async_elem(Os + idx, out + (long long)t * I + i);
+        } else {
+          Gs[idx] = T(0); Os[idx] = T(0);
+        }
       }
-      As[idx] = a; Gs[idx] = g; Os[idx] = o;
+      cp_async_wait_all();
+      __syncthreads();
+      if (!exact) {
+        const T n = (i < I) ? colmax[i] : ninf<T>();
+        for (int t = warp; t < Th; t += LTH / 32) {
+          const int idx = t * LT + lane;
+          const T m = rowmax[t];
+          const T a = As[idx], g = Gs[idx], o = Os[idx];
+          As[idx] = (m == ninf<T>()) ? T(0) : xexp(a - m);
+          Gs[idx] = (g == T(0) || o == ninf<T>()) ? T(0) : g * xexp(m + n - o);
+        }
+        __syncthreads();
+      }
     }
-    __syncthreads();
     if (!exact) {
       const T* a = As + 2 * ty;
       const T* g = Gs + 2 * tx;

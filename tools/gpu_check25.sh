@@ -1,20 +1,8 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"loo1_warp_kernel|loo2_from_saved" -c 2 -o gpurun_out/prof_loo python tools/kbench.py --layers k3q3 --batch 512 --kinds input --train --once > gpurun_out/ncu_loo.log 2>&1
-echo "ncu rc=$?"
-ncu -i gpurun_out/prof_loo.ncu-rep --page raw --csv > gpurun_out/prof_loo_raw.csv 2>/dev/null
-python tools/ncu_summary.py gpurun_out/prof_loo_raw.csv
-python - <<'P'
-import csv
-rows=list(csv.reader(open("gpurun_out/prof_loo_raw.csv")))
-hdr=rows[0]
-for r in rows[2:]:
-    d=dict(zip(hdr,r))
-    print(d.get("Kernel Name","?")[:60])
-    for k,v in d.items():
-        if ("stalled" in k and "per_issue_active" in k) or k in ("smsp__inst_executed.sum","sm__warps_active.avg.pct_of_peak_sustained_active","smsp__cycles_active.avg","launch__occupancy_limit_registers","launch__occupancy_limit_shared_mem","launch__waves_per_multiprocessor","smsp__thread_inst_executed_per_inst_executed.ratio"):
-            try:
-                if float(v.replace(",",""))>0.3: print("   ",k,v)
-            except: pass
-P
-rm -f gpurun_out/prof_loo.ncu-rep
+timeout 600 python -m pytest tests -m gpu -q -x -k "logmatmulexp or lme or convsbs or conv_sbs" > gpurun_out/pytest_lme.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_lme.log
+grep -E "passed|failed|FAILED|rc=|^E  " gpurun_out/pytest_lme.log | cut -c1-300 | tail -8
+for wl in cfg5_chain cfg5_convsbs; do timeout 400 python bench.py --workload $wl --steps 20 --warmup 5 > gpurun_out/r02g_bench_$wl.json 2> gpurun_out/r02g_bench_$wl.err; python -c "
+import json; d=json.load(open('gpurun_out/r02g_bench_$wl.json')); print('$wl', d['value'], d['unit'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'cpu', d['cpu_baseline']['value'], 'fwd call ms', d['roofline'].get('ms_per_call'))"; done
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_cfg5.csv python bench.py --workload cfg5_chain --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_cfg5.log 2>&1
+grep "lme" gpurun_out/launches_cfg5.csv | tail -12 | awk -F'","' '{print substr($5,1,60), $NF}'
