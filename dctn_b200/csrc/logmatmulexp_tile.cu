@@ -29,8 +29,14 @@
 
 namespace {
 
-constexpr int LT = 32;          // output tile LT x LT, 256 threads, 2 x 2 outputs per thread
-constexpr int LTH = 256;
+constexpr int LT = 32;          // output tile LT x LT
+constexpr int RT = 1;           // RT x RT outputs per thread.  One: a 256 x 256 product is only 64 tiles, so each tile gets 32 warps.
+                                // Measured (profiles/r02g_cfg5_launches.txt): 256 threads x (2 x 2) forward 17.7 / backward 20.3 us,
+                                // 1024 threads x (1 x 1) 17.5 / 17.7 us — the product loop is bound by shared-memory wavefronts
+                                // (two loads per FMA), the rest is launch + one HBM round trip; a 4 x 4 register tile over
+                                // k-major operands would cut the wavefronts 8x (not written)
+constexpr int LTH = (LT / RT) * (LT / RT);
+constexpr int NPART = LTH / 32; // threads per column in the column reductions
 static_assert(LT == 32, "the staging loops map one lane to one tile column");
 constexpr size_t LME_SMEM_LIMIT = 200 * 1024;
 
@@ -126,14 +132,14 @@ __global__ void __launch_bounds__(LTH) lme_tile_fwd_kernel(const T* __restrict__
       mn = v < mn ? v : mn;
     }
     red[part * LT + c] = mx;
-    red[(8 + part) * LT + c] = mn;
+    red[(NPART + part) * LT + c] = mn;
     if (bad) s_unsafe = 1;
   }
   __syncthreads();
   if (tid < LT) {
     T mx = ninf<T>(), mn = -ninf<T>();
-    for (int p = 0; p < 8; ++p) {
-      const T a = red[p * LT + tid], b = red[(8 + p) * LT + tid];
+    for (int p = 0; p < NPART; ++p) {
+      const T a = red[p * LT + tid], b = red[(NPART + p) * LT + tid];
       mx = a > mx ? a : mx;
       mn = b < mn ? b : mn;
     }
@@ -145,8 +151,8 @@ __global__ void __launch_bounds__(LTH) lme_tile_fwd_kernel(const T* __restrict__
   if (exact && tid == 0) atomicOr(flag, 1);
   if (blockIdx.x == 0 && tid < LT && t0 + tid < Th) rowmax[t0 + tid] = mrow[tid];
   if (blockIdx.y == 0 && tid < LT && i0 + tid < I) colmax[i0 + tid] = ncol[tid];
-  const int ty = tid >> 4, tx = tid & 15;   // outputs (2 ty + u, 2 tx + v)
-  T res[2][2];
+  const int ty = tid / (LT / RT), tx = tid % (LT / RT);   // outputs (RT ty + u, RT tx + v)
+  T res[RT][RT];
   if (!exact) {
     for (int tl = warp; tl < LT; tl += LTH / 32) {
       const T m = mrow[tl];
@@ -157,31 +163,34 @@ __global__ void __launch_bounds__(LTH) lme_tile_fwd_kernel(const T* __restrict__
       Bs[idx] = (n == ninf<T>()) ? T(0) : xexp(Bs[idx] - n);
     }
     __syncthreads();
-    T acc[2][2] = {{T(0), T(0)}, {T(0), T(0)}};
-    const T* a0 = As + (2 * ty) * RP;
-    const T* a1 = a0 + RP;
-    const T* b = Bs + 2 * tx;
-#pragma unroll 4
+    T acc[RT][RT] = {};
+    const T* a0 = As + (RT * ty) * RP;
+    const T* b = Bs + RT * tx;
+#pragma unroll 8
     for (int r = 0; r < R; ++r) {
-      const T x0 = a0[r], x1 = a1[r], y0 = b[r * LT], y1 = b[r * LT + 1];
-      acc[0][0] += x0 * y0; acc[0][1] += x0 * y1;
-      acc[1][0] += x1 * y0; acc[1][1] += x1 * y1;
+      T xv[RT], yv[RT];
+#pragma unroll
+      for (int u = 0; u < RT; ++u) { xv[u] = a0[u * RP + r]; yv[u] = b[r * LT + u]; }
+#pragma unroll
+      for (int u = 0; u < RT; ++u)
+#pragma unroll
+        for (int v = 0; v < RT; ++v) acc[u][v] += xv[u] * yv[v];
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < RT; ++u)
 #pragma unroll
-      for (int v = 0; v < 2; ++v) {
-        const T m = mrow[2 * ty + u], n = ncol[2 * tx + v];
+      for (int v = 0; v < RT; ++v) {
+        const T m = mrow[RT * ty + u], n = ncol[RT * tx + v];
         res[u][v] = (m == ninf<T>() || n == ninf<T>() || acc[u][v] == T(0)) ? ninf<T>() : m + n + xlog(acc[u][v]);
       }
   } else {
     // per-element max-shifted logsumexp (the arithmetic of lme_fwd_kernel) from the raw operands in shared memory
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < RT; ++u)
 #pragma unroll
-      for (int v = 0; v < 2; ++v) {
-        const T* a = As + (2 * ty + u) * RP;
-        const T* b = Bs + 2 * tx + v;
+      for (int v = 0; v < RT; ++v) {
+        const T* a = As + (RT * ty + u) * RP;
+        const T* b = Bs + RT * tx + v;
         T m = ninf<T>();
         for (int r = 0; r < R; ++r) {
           const T w = a[r] + b[r * LT];
@@ -202,10 +211,10 @@ __global__ void __launch_bounds__(LTH) lme_tile_fwd_kernel(const T* __restrict__
       }
   }
 #pragma unroll
-  for (int u = 0; u < 2; ++u)
+  for (int u = 0; u < RT; ++u)
 #pragma unroll
-    for (int v = 0; v < 2; ++v) {
-      const int t = t0 + 2 * ty + u, i = i0 + 2 * tx + v;
+    for (int v = 0; v < RT; ++v) {
+      const int t = t0 + RT * ty + u, i = i0 + RT * tx + v;
       if (t < Th && i < I) out[(long long)t * I + i] = res[u][v];
     }
 }
@@ -219,9 +228,9 @@ __global__ void __launch_bounds__(LTH) lme_tile_bwd_kernel(const T* __restrict__
                                                            T* __restrict__ dst, int Th, int R, int I) {
   extern __shared__ unsigned char lme_smem_raw[];
   T* sm = reinterpret_cast<T*>(lme_smem_raw);
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int tid = threadIdx.x, ty = tid / (LT / RT), tx = tid % (LT / RT);
   const bool exact = *flag != 0;
-  T acc[2][2] = {{T(0), T(0)}, {T(0), T(0)}};
+  T acc[RT][RT] = {};
   if (WHICH == 0) {
     // rows: X[t][i] (t tile), Y[r][i] (r tile), K = i, both rows contiguous in K
     const int KP = I | 1;
@@ -259,22 +268,24 @@ __global__ void __launch_bounds__(LTH) lme_tile_bwd_kernel(const T* __restrict__
       __syncthreads();
     }
     if (!exact) {
-      const T* g0 = Gs + (2 * ty) * KP;
-      const T* g1 = g0 + KP;
-      const T* b0 = Bs + (2 * tx) * KP;
-      const T* b1 = b0 + KP;
-#pragma unroll 4
+      const T* g0 = Gs + (RT * ty) * KP;
+      const T* b0 = Bs + (RT * tx) * KP;
+#pragma unroll 8
       for (int i = 0; i < I; ++i) {
-        const T x0 = g0[i], x1 = g1[i], y0 = b0[i], y1 = b1[i];
-        acc[0][0] += x0 * y0; acc[0][1] += x0 * y1;
-        acc[1][0] += x1 * y0; acc[1][1] += x1 * y1;
+        T xv[RT], yv[RT];
+#pragma unroll
+        for (int u = 0; u < RT; ++u) { xv[u] = g0[u * KP + i]; yv[u] = b0[u * KP + i]; }
+#pragma unroll
+        for (int u = 0; u < RT; ++u)
+#pragma unroll
+          for (int v = 0; v < RT; ++v) acc[u][v] += xv[u] * yv[v];
       }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < RT; ++u)
 #pragma unroll
-      for (int v = 0; v < 2; ++v) {
-        const int t = t0 + 2 * ty + u, r = r0 + 2 * tx + v;
+      for (int v = 0; v < RT; ++v) {
+        const int t = t0 + RT * ty + u, r = r0 + RT * tx + v;
         if (t >= Th || r >= R) continue;
         const T a = A[(long long)t * R + r];
         T res;
@@ -282,9 +293,9 @@ __global__ void __launch_bounds__(LTH) lme_tile_bwd_kernel(const T* __restrict__
           const T m = rowmax[t];
           res = (m == ninf<T>()) ? T(0) : xexp(a - m) * acc[u][v];
         } else {
-          const T* g = Gs + (2 * ty + u) * KP;
-          const T* o = Os + (2 * ty + u) * KP;
-          const T* b = Bs + (2 * tx + v) * KP;
+          const T* g = Gs + (RT * ty + u) * KP;
+          const T* o = Os + (RT * ty + u) * KP;
+          const T* b = Bs + (RT * tx + v) * KP;
           res = T(0);
           for (int i = 0; i < I; ++i) {
             const T gv = g[i];
@@ -328,20 +339,24 @@ __global__ void __launch_bounds__(LTH) lme_tile_bwd_kernel(const T* __restrict__
       }
     }
     if (!exact) {
-      const T* a = As + 2 * ty;
-      const T* g = Gs + 2 * tx;
-#pragma unroll 4
+      const T* a = As + RT * ty;
+      const T* g = Gs + RT * tx;
+#pragma unroll 8
       for (int t = 0; t < Th; ++t) {
-        const T x0 = a[t * LT], x1 = a[t * LT + 1], y0 = g[t * LT], y1 = g[t * LT + 1];
-        acc[0][0] += x0 * y0; acc[0][1] += x0 * y1;
-        acc[1][0] += x1 * y0; acc[1][1] += x1 * y1;
+        T xv[RT], yv[RT];
+#pragma unroll
+        for (int u = 0; u < RT; ++u) { xv[u] = a[t * LT + u]; yv[u] = g[t * LT + u]; }
+#pragma unroll
+        for (int u = 0; u < RT; ++u)
+#pragma unroll
+          for (int v = 0; v < RT; ++v) acc[u][v] += xv[u] * yv[v];
       }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < RT; ++u)
 #pragma unroll
-      for (int v = 0; v < 2; ++v) {
-        const int r = r0 + 2 * ty + u, i = i0 + 2 * tx + v;
+      for (int v = 0; v < RT; ++v) {
+        const int r = r0 + RT * ty + u, i = i0 + RT * tx + v;
         if (r >= R || i >= I) continue;
         const T b = B[(long long)r * I + i];
         T res;
@@ -351,8 +366,8 @@ __global__ void __launch_bounds__(LTH) lme_tile_bwd_kernel(const T* __restrict__
         } else {
           res = T(0);
           for (int t = 0; t < Th; ++t) {
-            const T gv = Gs[t * LT + 2 * tx + v];
-            res += (gv != T(0)) ? gv * xexp(As[t * LT + 2 * ty + u] + b - Os[t * LT + 2 * tx + v]) : T(0);
+            const T gv = Gs[t * LT + RT * tx + v];
+            res += (gv != T(0)) ? gv * xexp(As[t * LT + RT * ty + u] + b - Os[t * LT + RT * tx + v]) : T(0);
           }
         }
         dst[(long long)r * I + i] = res;
@@ -360,7 +375,7 @@ __global__ void __launch_bounds__(LTH) lme_tile_bwd_kernel(const T* __restrict__
   }
 }
 
-template <typename T> size_t fwd_smem(int R) { return ((size_t)LT * (R | 1) + (size_t)R * LT + 2 * LT + 16 * LT) * sizeof(T); }
+template <typename T> size_t fwd_smem(int R) { return ((size_t)LT * (R | 1) + (size_t)R * LT + 2 * LT + 2 * NPART * LT) * sizeof(T); }
 template <typename T> size_t bwd_a_smem(int I) { return (size_t)3 * LT * (I | 1) * sizeof(T); }
 template <typename T> size_t bwd_b_smem(int Th) { return (size_t)3 * Th * LT * sizeof(T); }
 
