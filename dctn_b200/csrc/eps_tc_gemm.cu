@@ -871,10 +871,11 @@ int run_gemm(const EpsGeom& g, int mode, int BN, const float* x, const float* go
   }
 #endif
   const size_t smem = gemm_fixed_smem(g, s, mode) + a.bstages * bstage_bytes(BN);
+#ifdef DCTN_TCG_TIMING
   if (getenv("DCTN_DEBUG_SHAPE"))
-    fprintf(stderr, "[tcg shape] mode=%d BN=%d NB=%d smem=%zu nf=%d cr=%d G=%d GP=%d RB=%d H=%d Hpad=%d KH=%d KLb=%d Kp=%d nk=%d ntiles=%d kseg=%d\n",
-            mode, BN, a.bstages, smem, a.nf, a.cr, a.G, a.GP, a.RB, a.H, a.Hpad, a.KH, a.KLb, a.Kp, a.nk, a.ntiles, a.kseg);
-  if (getenv("DCTN_DEBUG_SKIP_GEMM")) return 0;
+    fprintf(stderr, "[tcg shape] mode=%d BN=%d NB=%d smem=%zu nf=%d cr=%d G=%d GP=%d RB=%d H=%d Hpad=%d KH=%d KLb=%d Kp=%d nk=%d ntiles=%d kseg=%d dbuf=%d\n",
+            mode, BN, a.bstages, smem, a.nf, a.cr, a.G, a.GP, a.RB, a.H, a.Hpad, a.KH, a.KLb, a.Kp, a.nk, a.ntiles, a.kseg, a.dbuf);
+#endif
   int rc;
   if (mode == MODE_STORE) rc = f16 ? launch_gemm_inst<MODE_STORE, true>(a, smem, st) : launch_gemm_inst<MODE_STORE, false>(a, smem, st);
   else if (mode == MODE_FWD) rc = f16 ? launch_gemm_inst<MODE_FWD, true>(a, smem, st) : launch_gemm_inst<MODE_FWD, false>(a, smem, st);
@@ -1426,15 +1427,15 @@ static int backward_input_impl(const EpsGeom& g, const float* x, const float* co
       if (!fast1 && loo1_rows_ok(g)) {   // slices summed and both leave-one-out stages in one pass over dKR1
         if ((rc = launch_loo1_rows(g, x, dkr1, (long long)pc * g.A, nslice1, p0, np, dxp, st))) return rc;
       } else {
-      if (nslice1 > 1) {
-        const long long count = (long long)np * g.A;
-        int blocks = (int)((count + 255) / 256);
-        if (blocks > 148 * 16) blocks = 148 * 16;
-        sum_slices_kernel<<<blocks, 256, 0, st>>>(dkr1, (long long)pc * g.A, count, nslice1);
-        dctn_count_launch();
-        DCTN_CUDA_CHECK_RET(cudaGetLastError());
-      }
-      if ((rc = launch_loo<float>(g, x, dkr1, p0, np, 0, dxp, st))) return rc;
+        if (nslice1 > 1) {
+          const long long count = (long long)np * g.A;
+          int blocks = (int)((count + 255) / 256);
+          if (blocks > 148 * 16) blocks = 148 * 16;
+          sum_slices_kernel<<<blocks, 256, 0, st>>>(dkr1, (long long)pc * g.A, count, nslice1);
+          dctn_count_launch();
+          DCTN_CUDA_CHECK_RET(cudaGetLastError());
+        }
+        if ((rc = launch_loo<float>(g, x, dkr1, p0, np, 0, dxp, st))) return rc;
       }
     }
     if (fused2) {
